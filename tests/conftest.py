@@ -1,0 +1,32 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def tsukuba():
+    import numpy as np
+    return np.load(os.path.join(GOLDEN, "tsukuba_orb2000.npz"))
+
+
+@pytest.fixture(scope="session")
+def tsukuba_golden():
+    import numpy as np
+    return np.load(os.path.join(GOLDEN, "tsukuba_golden.npz"))
+
+
+@pytest.fixture(scope="session")
+def synthetic_golden():
+    import numpy as np
+    return np.load(os.path.join(GOLDEN, "synthetic_golden.npz"))
