@@ -1,0 +1,198 @@
+/*
+ * mvslam_b200.h — C ABI of libmvslam_b200.so: the B200 (sm_100a) implementation of mvSLAM's
+ * two-view front-end hot path (descriptor matching -> RANSAC fundamental/essential matrix ->
+ * pose recovery -> linear triangulation).
+ *
+ * The reference (lonelycorn/mvSLAM) has no plugin/FFI layer; its boundary for this path is a set
+ * of C++ entry points.  Each function below names the reference interface it replaces
+ * (file:line relative to the reference tree).  the headers under include/mvslam/ wrap this ABI back into the
+ * reference's C++ signatures (namespace mvSLAM); INTEGRATION.md shows how a maintainer binds it.
+ *
+ * Conventions
+ *   - plain C types only; all matrices row-major doubles (the adapters convert from Eigen's
+ *     column-major storage); points are AoS.
+ *   - the caller owns every host buffer; outputs are written only on success of the stage that
+ *     produces them (sfm-solve.cpp:364-366 swaps outputs in only on success).
+ *   - every entry point is synchronous w.r.t. the host unless its name ends in _enqueue;
+ *     a ctx is bound to one device and one stream and is NOT thread-safe (one ctx per thread).
+ *   - there is NO CPU fallback: without a CUDA device mvs_create fails with MVS_E_CUDA.
+ *   - host pointers may be pageable or pinned; pinned buffers make the copies asynchronous.
+ */
+#ifndef MVSLAM_B200_H
+#define MVSLAM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVS_ABI_VERSION 1
+
+/* status codes (reference: bool / assert / empty vector; SURVEY.md §8b "Errors") */
+enum {
+    MVS_OK = 0,
+    MVS_E_BAD_ARG = 1,          /* precondition the reference asserts on (visual-feature.cpp:56, sfm-solve.cpp:37-41,292) */
+    MVS_E_TOO_FEW_POINTS = 2,   /* < 8 correspondences (estimator-RANSAC.cpp:25-29) */
+    MVS_E_NO_MODEL = 3,         /* inlier_count_best == 0 (estimator-RANSAC.cpp:89) */
+    MVS_E_TOO_FEW_INLIERS = 4,  /* < VF_MATCH_INLIER_MIN (sfm-solve.cpp:326-334) */
+    MVS_E_NO_CHEIRALITY = 5,    /* no candidate leaves a point in front of both cameras (sfm-solve.cpp:345-356) */
+    MVS_E_CUDA = 6,             /* CUDA runtime/driver failure; see mvs_last_error */
+    MVS_E_CAPACITY = 7,         /* caller-provided output capacity too small */
+    MVS_E_UNSUPPORTED = 8
+};
+
+enum { MVS_SCORE_ALGEBRAIC = 0, /* |x2^T F x1| < max_error_sq, estimator-RANSAC.cpp:114-117 (parity mode) */
+       MVS_SCORE_SAMPSON = 1    /* Sampson distance, the score of cv::findEssentialMat used by the default build */ };
+
+typedef struct mvs_ctx mvs_ctx;
+
+/* cv::DMatch as the reference uses it (base/image.hpp:31-35): queryIdx indexes the second/pair
+ * frame, trainIdx the first/base frame (visual-feature.cpp:59-60), imgIdx is always 0. */
+typedef struct {
+    int32_t query;
+    int32_t train;
+    float   distance;
+} mvs_match;
+
+/* constants of visual-feature.cpp:21-24 and ImagePair::Params (image-pair.hpp:25-31) */
+typedef struct {
+    double  ratio;        /* NEAREST_NEIGHBOR_DIST_RATIO, 0.7 */
+    double  max_dist;     /* < 0: keep all (match_visual_features default -1; VO default 10) */
+    int32_t cross_check;  /* reference: CROSS_CHECK=false */
+    int32_t reserved;
+} mvs_match_params;
+
+/* constants of sfm-solve.cpp:18-23,67 made explicit */
+typedef struct {
+    int32_t  n_hypotheses; /* H >= 1; H == 1 is the reference (single sample {0..7}) */
+    int32_t  score_mode;   /* MVS_SCORE_* */
+    double   max_error_sq; /* <= 0: reference default 5e-2 / (K00*K11), sfm-solve.cpp:311 */
+    uint64_t seed;         /* seeds the rows >= 1 of the sample table (mvs_sample_table) */
+    int32_t  min_inliers;  /* <= 0: VF_MATCH_INLIER_MIN = 8 */
+    int32_t  reserved;
+    uint64_t pair_id_base; /* batch entry i samples with pair_id = pair_id_base + i (sharding-invariant results) */
+} mvs_ransac_params;
+
+/* fixed-size record of one solved pair == what ImagePair holds after reconstruct()
+ * (image-pair.hpp:52-60) plus the intermediate models, all doubles row-major */
+typedef struct {
+    int32_t status;
+    int32_t n_matches;        /* M: ratio/max_dist survivors (== n for mvs_sfm_solve) */
+    int32_t n_inliers;        /* inliers of the winning hypothesis */
+    int32_t best_hypothesis;  /* row of the sample table that won */
+    int32_t n_points;         /* triangulated points that passed cheirality == ImagePair::match_inlier_count */
+    int32_t candidate;        /* 0..3 = (Ra,+t),(Ra,-t),(Rb,+t),(Rb,-t), sfm-solve.cpp:259-281 */
+    double  residual;         /* sum of residuals over the inliers of the winner */
+    double  F[9];             /* winning de-normalised 8-point model */
+    double  E[9];             /* after the (s,s,0) projection, sfm-solve.cpp:73-87 */
+    double  R1to2[9];
+    double  t1to2[3];
+    double  R2in1[9];         /* pose2in1 = SE3(SO3(R1to2), t1to2).inverse(), sfm-solve.cpp:364 */
+    double  t2in1[3];
+    uint64_t match_inlier_ssd; /* sum of squared descriptor distances over the reconstructed points (image-pair.cpp:166) */
+} mvs_pair_result;
+
+/* per-stage device time accumulated on the ctx stream while profiling is enabled */
+enum { MVS_STAGE_KNN = 0, MVS_STAGE_MATCH_FINALIZE, MVS_STAGE_HYPOTHESES, MVS_STAGE_SCORE,
+       MVS_STAGE_SELECT, MVS_STAGE_TRIANGULATE, MVS_STAGE_FINALIZE, MVS_STAGE_L2, MVS_N_STAGES };
+typedef struct {
+    double   ms[MVS_N_STAGES];
+    uint64_t launches[MVS_N_STAGES];
+} mvs_profile;
+
+/* ---- context ---------------------------------------------------------------------------- */
+int  mvs_abi_version(void);
+const char *mvs_status_string(int status);
+/* Creates a context on CUDA device `device` with its own non-blocking stream.  Replaces the
+ * reference's hidden globals (static matcher visual-feature.cpp:12-25, global camera
+ * camera-manager.cpp:10). */
+int  mvs_create(mvs_ctx **out, int device);
+void mvs_destroy(mvs_ctx *ctx);
+const char *mvs_last_error(const mvs_ctx *ctx);
+/* Run all work of this ctx on a caller-owned cudaStream_t (e.g. torch's current stream). */
+int  mvs_set_stream(mvs_ctx *ctx, void *cuda_stream);
+int  mvs_synchronize(mvs_ctx *ctx);
+int  mvs_profile_enable(mvs_ctx *ctx, int on);
+int  mvs_profile_read(mvs_ctx *ctx, mvs_profile *out, int reset);
+/* number of kernels this ctx has launched so far */
+uint64_t mvs_kernel_launches(const mvs_ctx *ctx);
+
+/* ---- matching: VisualFeature::match_visual_features (source/vision/visual-feature.cpp:51-80,
+ *      decl visual-feature.hpp:23-26) ------------------------------------------------------------ */
+/* cv::BFMatcher(NORM_HAMMING).knnMatch(query, train, k=2) (visual-feature.cpp:59-62):
+ * idx/dist are [nq][2]; ties resolve to the lowest train index. desc_bytes must be 32. nt >= 2. */
+int mvs_knn2_hamming(mvs_ctx *ctx, const uint8_t *query, int nq, const uint8_t *train, int nt,
+                     int desc_bytes, int32_t *idx, int32_t *dist);
+/* knnMatch + Lowe ratio + max_dist (+ optional cross-check) + sort.  Output order: distance
+ * ascending, then queryIdx ascending (the reference's std::sort leaves ties unspecified). */
+int mvs_match_hamming(mvs_ctx *ctx, const uint8_t *query, int nq, const uint8_t *train, int nt,
+                      int desc_bytes, const mvs_match_params *params,
+                      mvs_match *out, int capacity, int *n_out);
+/* float descriptors, NORM_L2 (BASELINE config 4): tensor-core contraction + exact FP32 re-rank */
+int mvs_knn2_l2(mvs_ctx *ctx, const float *query, int nq, const float *train, int nt, int dim,
+                int32_t *idx, float *dist);
+int mvs_match_l2(mvs_ctx *ctx, const float *query, int nq, const float *train, int nt, int dim,
+                 const mvs_match_params *params, mvs_match *out, int capacity, int *n_out);
+
+/* ---- geometry --------------------------------------------------------------------------- */
+/* find_fundamental_matrix (source/vision/fundamental-matrix.cpp:204-267, decl fundamental-matrix.hpp:16-19)
+ * for n_sets independent 8-point samples: p1s/p2s are [n_sets][8][3], F_out is [n_sets][9]. */
+int mvs_find_fundamental_matrix(mvs_ctx *ctx, const double *p1s, const double *p2s, int n_sets, double *F_out);
+
+/* The seeded sample table shared bit-for-bit by the device sampler and the CPU oracle: row 0 is
+ * {0..7} (the reference's only sample, estimator-RANSAC.cpp:41-48), rows >= 1 hold 8 distinct
+ * indices < n_points.  Pure host function. out is [H][8]. */
+void mvs_sample_table(uint64_t seed, uint64_t pair_id, uint32_t n_points, int H, uint32_t *out);
+
+/* FundamentalMatrixEstimatorRANSAC::compute (source/vision/estimator-RANSAC.cpp:16-90, decl
+ * estimator-RANSAC.hpp:20-24) over an explicit sample table samples[H][8] (NULL: seeded table of
+ * params->seed, pair_id 0).  p1/p2 are [n][3] homogeneous ideal-camera points.
+ * all_counts (optional) receives the inlier count of every hypothesis. */
+int mvs_ransac_fundamental(mvs_ctx *ctx, const double *p1, const double *p2, int n,
+                           const uint32_t *samples, const mvs_ransac_params *params,
+                           double F[9], uint8_t *inlier_mask, int *inlier_count, double *residual,
+                           int *best_hypothesis, int32_t *all_counts);
+
+/* sfm_solve (source/vision/sfm-solve.cpp:285-368, decl source/vision/sfm.hpp:30-35), own branch of
+ * find_essential_matrix (:64-90).  xy1/xy2 are [n][2] pixel coordinates, K row-major.
+ * points [capacity][3], indexes [capacity]; inlier_mask [n] optional. */
+int mvs_sfm_solve(mvs_ctx *ctx, const double *xy1, const double *xy2, int n, const double K[9],
+                  const mvs_ransac_params *params, const uint32_t *samples,
+                  mvs_pair_result *result, uint8_t *inlier_mask,
+                  double *points, uint64_t *indexes, int capacity);
+
+/* sfm_triangulate (source/vision/sfm-solve.cpp:370-394, decl sfm.hpp:47-53); poses are
+ * camera-to-world (R row-major as held by the SO3, t). */
+int mvs_sfm_triangulate(mvs_ctx *ctx, const double *xy1, const double *xy2, int n, const double K[9],
+                        const double R1[9], const double t1[3], const double R2[9], const double t2[3],
+                        double *points, uint64_t *indexes, int capacity, int *n_out);
+
+/* ---- batched image pairs: ImagePair::ImagePair + reconstruct (source/front-end/image-pair.cpp:30-71,
+ *      115-174) for many (base, pair) frame pairs per call; the natural batch of
+ *      VisualOdometer::initialize (visual-odometer.cpp:289-296) and of all-pairs reconstruction ---- */
+/* Make n_frames frames resident in HBM: desc[f] is [counts[f]][32] bytes (cv::Mat CV_8U rows),
+ * kp[f] is [counts[f]][2] float (cv::KeyPoint::pt).  Replaces the previous frame table. */
+int mvs_frames_upload(mvs_ctx *ctx, int n_frames, const uint8_t *const *desc, const float *const *kp,
+                      const int32_t *counts, int desc_bytes);
+/* Solve pairs[i] = (base frame, pair frame) for i < n_pairs against the resident frames.
+ * results[n_pairs] always filled (status per pair; one bad pair never aborts the batch).
+ * Optional per-pair detail outputs use a common stride `capacity` (>= max keypoint count of any
+ * pair frame, else MVS_E_CAPACITY): matches[n_pairs][capacity], inlier_mask[n_pairs][capacity],
+ * points[n_pairs][capacity][3], indexes[n_pairs][capacity] (index into that pair's matches). */
+int mvs_pair_batch(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, const double K[9],
+                   const mvs_match_params *mparams, const mvs_ransac_params *rparams,
+                   mvs_pair_result *results, mvs_match *matches, uint8_t *inlier_mask,
+                   double *points, uint64_t *indexes, int capacity);
+/* Same, but only enqueues the device work and the device->host copies on the ctx stream;
+ * the host buffers are valid after mvs_synchronize(). */
+int mvs_pair_batch_enqueue(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, const double K[9],
+                           const mvs_match_params *mparams, const mvs_ransac_params *rparams,
+                           mvs_pair_result *results, mvs_match *matches, uint8_t *inlier_mask,
+                           double *points, uint64_t *indexes, int capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVSLAM_B200_H */

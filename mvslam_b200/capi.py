@@ -1,0 +1,269 @@
+"""ctypes binding of include/mvslam_b200.h (the C ABI of libmvslam_b200.so)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+(OK, E_BAD_ARG, E_TOO_FEW_POINTS, E_NO_MODEL, E_TOO_FEW_INLIERS, E_NO_CHEIRALITY, E_CUDA, E_CAPACITY,
+ E_UNSUPPORTED) = range(9)
+SCORE_ALGEBRAIC, SCORE_SAMPSON = 0, 1
+STAGES = ("knn", "match_finalize", "hypotheses", "score", "select", "triangulate", "finalize", "l2")
+
+MATCH_DTYPE = np.dtype([("query", np.int32), ("train", np.int32), ("distance", np.float32)])
+RESULT_DTYPE = np.dtype([
+    ("status", np.int32), ("n_matches", np.int32), ("n_inliers", np.int32), ("best_hypothesis", np.int32),
+    ("n_points", np.int32), ("candidate", np.int32), ("residual", np.float64), ("F", np.float64, (3, 3)),
+    ("E", np.float64, (3, 3)), ("R1to2", np.float64, (3, 3)), ("t1to2", np.float64, (3,)),
+    ("R2in1", np.float64, (3, 3)), ("t2in1", np.float64, (3,)), ("match_inlier_ssd", np.uint64)])
+
+
+class MatchParams(C.Structure):
+    _fields_ = [("ratio", C.c_double), ("max_dist", C.c_double), ("cross_check", C.c_int32), ("reserved", C.c_int32)]
+
+
+class RansacParams(C.Structure):
+    _fields_ = [("n_hypotheses", C.c_int32), ("score_mode", C.c_int32), ("max_error_sq", C.c_double),
+                ("seed", C.c_uint64), ("min_inliers", C.c_int32), ("reserved", C.c_int32),
+                ("pair_id_base", C.c_uint64)]
+
+
+class PairResult(C.Structure):
+    _fields_ = [("status", C.c_int32), ("n_matches", C.c_int32), ("n_inliers", C.c_int32),
+                ("best_hypothesis", C.c_int32), ("n_points", C.c_int32), ("candidate", C.c_int32),
+                ("residual", C.c_double), ("F", C.c_double * 9), ("E", C.c_double * 9),
+                ("R1to2", C.c_double * 9), ("t1to2", C.c_double * 3), ("R2in1", C.c_double * 9),
+                ("t2in1", C.c_double * 3), ("match_inlier_ssd", C.c_uint64)]
+
+
+assert C.sizeof(PairResult) == RESULT_DTYPE.itemsize == 376
+
+
+class Profile(C.Structure):
+    _fields_ = [("ms", C.c_double * len(STAGES)), ("launches", C.c_uint64 * len(STAGES))]
+
+
+class MvsError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"mvslam_b200 status {status}: {msg}")
+        self.status = status
+
+
+def lib_path():
+    return os.path.join(_HERE, "libmvslam_b200.so")
+
+
+_lib = None
+
+
+def load_library():
+    """Load libmvslam_b200.so.  Raises (no fallback) if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not os.path.exists(p):
+        raise ImportError(f"{p} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(nvcc, sm_100a). mvslam_b200 has no CPU fallback.")
+    L = C.CDLL(p)
+    L.mvs_status_string.restype = C.c_char_p
+    L.mvs_last_error.restype = C.c_char_p
+    L.mvs_last_error.argtypes = [C.c_void_p]
+    L.mvs_kernel_launches.restype = C.c_uint64
+    L.mvs_kernel_launches.argtypes = [C.c_void_p]
+    L.mvs_destroy.restype = None
+    L.mvs_destroy.argtypes = [C.c_void_p]
+    L.mvs_sample_table.restype = None
+    if L.mvs_abi_version() != 1:
+        raise ImportError("libmvslam_b200.so ABI version mismatch")
+    _lib = L
+    return L
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    return C.c_void_p(int(a))          # raw address (e.g. torch pinned tensor .data_ptr())
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def sample_table(seed, pair_id, n_points, H):
+    """Host copy of the device sampler (mvs_sample_table)."""
+    out = np.empty((H, 8), np.uint32)
+    load_library().mvs_sample_table(C.c_uint64(seed), C.c_uint64(pair_id), C.c_uint32(n_points), int(H), _p(out))
+    return out
+
+
+class Context:
+    """One context per (thread, CUDA device): owns the stream and the HBM workspace."""
+
+    def __init__(self, device=0, stream=None):
+        self._L = load_library()
+        h = C.c_void_p()
+        st = self._L.mvs_create(C.byref(h), int(device))
+        if st != OK:
+            raise MvsError(st, "mvs_create failed (no CUDA device / not sm_100?): "
+                           + self._L.mvs_status_string(st).decode())
+        self._h = h
+        self.device = device
+        self._frame_counts = None
+        if stream is not None:
+            self.set_stream(stream)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.mvs_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, st, ok=(OK,)):
+        if st not in ok:
+            raise MvsError(st, (self._L.mvs_last_error(self._h) or b"").decode()
+                           + " [" + self._L.mvs_status_string(st).decode() + "]")
+        return st
+
+    # ---- plumbing
+    def set_stream(self, cuda_stream):
+        self._check(self._L.mvs_set_stream(self._h, C.c_void_p(int(cuda_stream))))
+
+    def synchronize(self):
+        self._check(self._L.mvs_synchronize(self._h))
+
+    def profile_enable(self, on=True):
+        self._check(self._L.mvs_profile_enable(self._h, int(bool(on))))
+
+    def profile_read(self, reset=True):
+        pr = Profile()
+        self._check(self._L.mvs_profile_read(self._h, C.byref(pr), int(bool(reset))))
+        return {s: (pr.ms[i], int(pr.launches[i])) for i, s in enumerate(STAGES)}
+
+    def kernel_launches(self):
+        return int(self._L.mvs_kernel_launches(self._h))
+
+    # ---- matching
+    def knn2_hamming(self, query, train):
+        q = np.ascontiguousarray(query, np.uint8); t = np.ascontiguousarray(train, np.uint8)
+        idx = np.empty((q.shape[0], 2), np.int32); dist = np.empty((q.shape[0], 2), np.int32)
+        self._check(self._L.mvs_knn2_hamming(self._h, _p(q), q.shape[0], _p(t), t.shape[0],
+                                             q.shape[1] if q.ndim == 2 else 0, _p(idx), _p(dist)))
+        return idx, dist
+
+    def match_hamming(self, query, train, ratio=0.7, max_dist=-1.0, cross_check=False):
+        q = np.ascontiguousarray(query, np.uint8); t = np.ascontiguousarray(train, np.uint8)
+        out = np.empty(max(q.shape[0], 1), MATCH_DTYPE); n = C.c_int(0)
+        mp = MatchParams(ratio, max_dist, int(cross_check), 0)
+        self._check(self._L.mvs_match_hamming(self._h, _p(q), q.shape[0], _p(t), t.shape[0],
+                                              q.shape[1] if q.ndim == 2 else 0, C.byref(mp), _p(out),
+                                              out.shape[0], C.byref(n)))
+        return out[:n.value].copy()
+
+    def knn2_l2(self, query, train):
+        q = np.ascontiguousarray(query, np.float32); t = np.ascontiguousarray(train, np.float32)
+        idx = np.empty((q.shape[0], 2), np.int32); dist = np.empty((q.shape[0], 2), np.float32)
+        self._check(self._L.mvs_knn2_l2(self._h, _p(q), q.shape[0], _p(t), t.shape[0], q.shape[1], _p(idx), _p(dist)))
+        return idx, dist
+
+    def match_l2(self, query, train, ratio=0.7, max_dist=-1.0, cross_check=False):
+        q = np.ascontiguousarray(query, np.float32); t = np.ascontiguousarray(train, np.float32)
+        out = np.empty(max(q.shape[0], 1), MATCH_DTYPE); n = C.c_int(0)
+        mp = MatchParams(ratio, max_dist, int(cross_check), 0)
+        self._check(self._L.mvs_match_l2(self._h, _p(q), q.shape[0], _p(t), t.shape[0], q.shape[1], C.byref(mp),
+                                         _p(out), out.shape[0], C.byref(n)))
+        return out[:n.value].copy()
+
+    # ---- geometry
+    def find_fundamental_matrix(self, p1s, p2s):
+        p1s = _f64(p1s).reshape(-1, 8, 3); p2s = _f64(p2s).reshape(-1, 8, 3)
+        F = np.empty((p1s.shape[0], 3, 3))
+        self._check(self._L.mvs_find_fundamental_matrix(self._h, _p(p1s), _p(p2s), p1s.shape[0], _p(F)))
+        return F
+
+    def ransac_fundamental(self, p1, p2, samples=None, H=1, max_error_sq=1e-3, mode=SCORE_ALGEBRAIC, seed=0,
+                           want_all=False):
+        p1 = _f64(p1); p2 = _f64(p2); n = p1.shape[0]
+        if samples is not None:
+            samples = np.ascontiguousarray(samples, np.uint32); H = samples.shape[0]
+        rp = RansacParams(H, mode, max_error_sq, seed, 0, 0, 0)
+        F = np.zeros((3, 3)); mask = np.zeros(max(n, 1), np.uint8)
+        cnt = C.c_int(); res = C.c_double(); bh = C.c_int(-1)
+        allc = np.zeros(H, np.int32) if want_all else None
+        st = self._L.mvs_ransac_fundamental(self._h, _p(p1), _p(p2), n, _p(samples), C.byref(rp), _p(F), _p(mask),
+                                            C.byref(cnt), C.byref(res), C.byref(bh), _p(allc))
+        self._check(st, (OK, E_TOO_FEW_POINTS, E_NO_MODEL))
+        out = dict(status=st, F=F, mask=mask[:n], count=cnt.value, residual=res.value, best_h=bh.value)
+        if want_all:
+            out["all_counts"] = allc
+        return out
+
+    def sfm_solve(self, xy1, xy2, K, samples=None, H=1, seed=0, pair_id=0, mode=SCORE_ALGEBRAIC, max_error_sq=0.0):
+        xy1 = _f64(xy1); xy2 = _f64(xy2); n = xy1.shape[0]
+        if samples is not None:
+            samples = np.ascontiguousarray(samples, np.uint32); H = samples.shape[0]
+        rp = RansacParams(H, mode, max_error_sq, seed, 0, 0, pair_id)
+        res = np.zeros(1, RESULT_DTYPE); mask = np.zeros(max(n, 1), np.uint8)
+        pts = np.empty((max(n, 1), 3)); idx = np.empty(max(n, 1), np.uint64)
+        st = self._L.mvs_sfm_solve(self._h, _p(xy1), _p(xy2), n, _p(_f64(K)), C.byref(rp), _p(samples), _p(res),
+                                   _p(mask), _p(pts), _p(idx), max(n, 1))
+        self._check(st, (OK, E_TOO_FEW_POINTS, E_NO_MODEL, E_TOO_FEW_INLIERS, E_NO_CHEIRALITY))
+        r = res[0]
+        d = {k: (r[k].copy() if r[k].ndim else r[k].item()) for k in RESULT_DTYPE.names}
+        m = d["n_points"] if st == OK else 0
+        d["mask"] = mask[:n]; d["points"] = pts[:m].copy(); d["indexes"] = idx[:m].copy()
+        return d
+
+    def sfm_triangulate(self, xy1, xy2, K, R1, t1, R2, t2):
+        xy1 = _f64(xy1); xy2 = _f64(xy2); n = xy1.shape[0]
+        pts = np.empty((max(n, 1), 3)); idx = np.empty(max(n, 1), np.uint64); m = C.c_int(0)
+        self._check(self._L.mvs_sfm_triangulate(self._h, _p(xy1), _p(xy2), n, _p(_f64(K)), _p(_f64(R1)), _p(_f64(t1)),
+                                                _p(_f64(R2)), _p(_f64(t2)), _p(pts), _p(idx), max(n, 1), C.byref(m)))
+        return pts[:m.value].copy(), idx[:m.value].copy()
+
+    # ---- batched pairs
+    def frames_upload(self, descs, kps):
+        descs = [np.ascontiguousarray(d, np.uint8) for d in descs]
+        kps = [np.ascontiguousarray(k, np.float32) for k in kps]
+        nf = len(descs)
+        dptr = (C.c_void_p * nf)(*[d.ctypes.data for d in descs])
+        kptr = (C.c_void_p * nf)(*[k.ctypes.data for k in kps])
+        counts = np.array([d.shape[0] for d in descs], np.int32)
+        self._check(self._L.mvs_frames_upload(self._h, nf, dptr, kptr, _p(counts), 32))
+        self._frame_counts = counts
+
+    def pair_batch(self, pairs, K, ratio=0.7, max_dist=-1.0, cross_check=False, H=1, seed=0, mode=SCORE_ALGEBRAIC,
+                   max_error_sq=0.0, pair_id_base=0, details=True, out=None, enqueue_only=False):
+        """Returns (results[RESULT_DTYPE], details dict or None).  `out` may hold preallocated (e.g. pinned)
+        buffers: dict(results=addr/array, matches=, mask=, points=, indexes=, capacity=int)."""
+        pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2); npairs = pairs.shape[0]
+        mp = MatchParams(ratio, max_dist, int(cross_check), 0)
+        rp = RansacParams(H, mode, max_error_sq, seed, 0, 0, pair_id_base)
+        fn = self._L.mvs_pair_batch_enqueue if enqueue_only else self._L.mvs_pair_batch
+        if out is not None:
+            st = fn(self._h, _p(pairs), npairs, _p(_f64(K)), C.byref(mp), C.byref(rp), _p(out["results"]),
+                    _p(out.get("matches")), _p(out.get("mask")), _p(out.get("points")), _p(out.get("indexes")),
+                    int(out.get("capacity", 0)))
+            self._check(st)
+            return None, None
+        res = np.zeros(npairs, RESULT_DTYPE)
+        det = None
+        if details:
+            cap = int(self._frame_counts[pairs[:, 1]].max())
+            det = dict(matches=np.zeros((npairs, cap), MATCH_DTYPE), mask=np.zeros((npairs, cap), np.uint8),
+                       points=np.zeros((npairs, cap, 3)), indexes=np.zeros((npairs, cap), np.uint64), capacity=cap)
+        st = fn(self._h, _p(pairs), npairs, _p(_f64(K)), C.byref(mp), C.byref(rp), _p(res),
+                _p(det["matches"]) if det else None, _p(det["mask"]) if det else None,
+                _p(det["points"]) if det else None, _p(det["indexes"]) if det else None, det["capacity"] if det else 0)
+        self._check(st)
+        return res, det

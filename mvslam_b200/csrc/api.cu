@@ -1,0 +1,781 @@
+// api.cu — context, HBM workspace and the extern "C" entry points of libmvslam_b200.so.
+// Everything here is host-side plumbing: argument checks, host<->device copies, stage launches.
+// There is deliberately no CPU implementation of any stage.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "l2.h"
+
+using namespace mvs;
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct Pending { int stage; cudaEvent_t a, b; };
+
+}  // namespace
+
+struct mvs_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    uint64_t launches = 0;
+    // resident frame table
+    DevBuf d_desc, d_kp, d_foff, d_fcnt;
+    std::vector<int32_t> h_off, h_cnt;
+    // scratch frame table of the two-set matcher entry points
+    DevBuf t_desc, t_foff, t_fcnt;
+    // workspace
+    DevBuf d_pairs, d_partial, d_rev, d_matches, d_nmatch, d_points, d_state, d_Fall, d_pc, d_pr, d_mask,
+        d_valid, d_tri, d_opts, d_oidx, d_results, d_table, d_in1, d_in2, d_knn_i, d_knn_d, d_counts;
+    mvs::L2Workspace l2;
+    // profiling
+    bool prof = false;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<Pending> pending;
+    mvs_profile acc;
+};
+
+namespace {
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                  \
+            return MVS_E_CUDA;                                                                \
+        }                                                                                     \
+    } while (0)
+
+int fail(mvs_ctx *ctx, int code, const char *msg)
+{
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+cudaEvent_t get_event(mvs_ctx *ctx)
+{
+    if (!ctx->ev_pool.empty()) { cudaEvent_t e = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct StageTimer {
+    mvs_ctx *ctx; int stage; cudaEvent_t a = nullptr;
+    StageTimer(mvs_ctx *c, int s, int n_launch = 1) : ctx(c), stage(s)
+    {
+        ctx->launches += (uint64_t)n_launch;
+        ctx->acc.launches[stage] += (uint64_t)n_launch;
+        if (ctx->prof) { a = get_event(ctx); cudaEventRecord(a, ctx->stream); }
+    }
+    ~StageTimer()
+    {
+        if (a) { cudaEvent_t b = get_event(ctx); cudaEventRecord(b, ctx->stream); ctx->pending.push_back({stage, a, b}); }
+    }
+};
+
+// ---- host copies of the tiny SE3/SO3 algebra needed to prepare inputs (same operation order as
+//      the device versions; reference source/math/lie-group.hpp:75-96,203-225, camera.cpp:14-18)
+void h_cross3(const double a[3], const double b[3], double o[3])
+{
+    o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+}
+void h_rectify(const double R[9], double out[9])
+{
+    double n0 = std::sqrt(R[0] * R[0] + R[1] * R[1] + R[2] * R[2]);
+    double u0[3] = {R[0] / n0, R[1] / n0, R[2] / n0};
+    double d = R[3] * u0[0] + R[4] * u0[1] + R[5] * u0[2];
+    double u1[3] = {R[3] - d * u0[0], R[4] - d * u0[1], R[5] - d * u0[2]}, u2[3];
+    h_cross3(u0, u1, u2);
+    for (int k = 0; k < 3; ++k) { out[k] = u0[k]; out[3 + k] = u1[k]; out[6 + k] = u2[k]; }
+}
+void h_mat3_vec(const double A[9], const double v[3], double o[3])
+{
+    for (int i = 0; i < 3; ++i) o[i] = A[i * 3] * v[0] + A[i * 3 + 1] * v[1] + A[i * 3 + 2] * v[2];
+}
+void h_se3_inverse(const double R[9], const double t[3], double Ro[9], double to[3])
+{
+    double Rt[9], v[3];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Rt[i * 3 + j] = R[j * 3 + i];
+    h_rectify(Rt, Ro);
+    h_mat3_vec(Ro, t, v);
+    to[0] = -v[0]; to[1] = -v[1]; to[2] = -v[2];
+}
+void h_se3_compose(const double Ra[9], const double ta[3], const double Rb[9], const double tb[3], double Ro[9], double to[3])
+{
+    double P[9], v[3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) P[i * 3 + j] = Ra[i * 3] * Rb[j] + Ra[i * 3 + 1] * Rb[3 + j] + Ra[i * 3 + 2] * Rb[6 + j];
+    h_rectify(P, Ro);
+    h_mat3_vec(Ra, tb, v);
+    to[0] = v[0] + ta[0]; to[1] = v[1] + ta[1]; to[2] = v[2] + ta[2];
+}
+void h_inverse3(const double K[9], double Ki[9])
+{   // Eigen's fixed 3x3 inverse: cofactor^T * (1/det)
+    double c00 = K[4] * K[8] - K[5] * K[7], c01 = K[5] * K[6] - K[3] * K[8], c02 = K[3] * K[7] - K[4] * K[6];
+    double c10 = K[2] * K[7] - K[1] * K[8], c11 = K[0] * K[8] - K[2] * K[6], c12 = K[1] * K[6] - K[0] * K[7];
+    double c20 = K[1] * K[5] - K[2] * K[4], c21 = K[2] * K[3] - K[0] * K[5], c22 = K[0] * K[4] - K[1] * K[3];
+    double det = K[0] * c00 + K[1] * c01 + K[2] * c02, id = 1.0 / det;
+    Ki[0] = c00 * id; Ki[1] = c10 * id; Ki[2] = c20 * id;
+    Ki[3] = c01 * id; Ki[4] = c11 * id; Ki[5] = c21 * id;
+    Ki[6] = c02 * id; Ki[7] = c12 * id; Ki[8] = c22 * id;
+}
+
+struct RansacCfg { int H; int mode; double thr; uint64_t seed; int min_inl; uint64_t pair_base; };
+
+int resolve_ransac(mvs_ctx *ctx, const mvs_ransac_params *rp, const double *K, RansacCfg &c)
+{
+    c.H = rp ? rp->n_hypotheses : 1;
+    c.mode = rp ? rp->score_mode : MVS_SCORE_ALGEBRAIC;
+    c.thr = rp ? rp->max_error_sq : 0.0;
+    c.seed = rp ? rp->seed : 0;
+    c.pair_base = rp ? rp->pair_id_base : 0;
+    c.min_inl = (rp && rp->min_inliers > 0) ? rp->min_inliers : kMinInliers;
+    if (c.H < 1) return fail(ctx, MVS_E_BAD_ARG, "n_hypotheses must be >= 1");
+    if (c.mode != MVS_SCORE_ALGEBRAIC && c.mode != MVS_SCORE_SAMPSON) return fail(ctx, MVS_E_BAD_ARG, "bad score_mode");
+    if (!(c.thr > 0.0)) {
+        if (!K) return fail(ctx, MVS_E_BAD_ARG, "max_error_sq must be > 0");
+        c.thr = kMaxErrorSq / K[0] / K[4];  // sfm-solve.cpp:311
+    }
+    if (!(c.thr > kEpsilon)) return fail(ctx, MVS_E_BAD_ARG, "max_error_sq must be > epsilon");  // sfm-solve.cpp:39
+    return MVS_OK;
+}
+
+// K3..K5 (+K6,K7) over n_pairs pairs whose correspondences sit in d_points[pairs][p_stride][6]
+int run_geometry(mvs_ctx *ctx, int n_pairs, int p_stride, const RansacCfg &rc, bool unit_z, const uint32_t *d_table,
+                 uint64_t pair_id_base, bool decompose, bool want_all_counts, const mvs_match *d_matches)
+{
+    const int tiles = score_tiles(p_stride);
+    CK(ctx->d_Fall.ensure((size_t)n_pairs * rc.H * 9 * sizeof(double)));
+    CK(ctx->d_pc.ensure((size_t)n_pairs * tiles * rc.H * sizeof(uint32_t)));
+    CK(ctx->d_pr.ensure((size_t)n_pairs * tiles * rc.H * sizeof(double)));
+    CK(ctx->d_mask.ensure((size_t)n_pairs * p_stride));
+    if (want_all_counts) CK(ctx->d_counts.ensure((size_t)n_pairs * rc.H * sizeof(int32_t)));
+    PairState *state = ctx->d_state.as<PairState>();
+    {
+        StageTimer t(ctx, MVS_STAGE_HYPOTHESES);
+        HypArgs a{};
+        a.points = ctx->d_points.as<double>(); a.p_stride = p_stride; a.state = state; a.n_fixed = 0;
+        a.table = d_table; a.seed = rc.seed; a.pair_id_base = pair_id_base; a.H = rc.H; a.F_all = ctx->d_Fall.as<double>();
+        launch_hypotheses(a, n_pairs, ctx->stream);
+    }
+    {
+        StageTimer t(ctx, MVS_STAGE_SCORE);
+        ScoreArgs a{};
+        a.points = ctx->d_points.as<double>(); a.p_stride = p_stride; a.state = state; a.F_all = ctx->d_Fall.as<double>();
+        a.H = rc.H; a.max_error_sq = rc.thr; a.tiles = tiles; a.part_count = ctx->d_pc.as<uint32_t>(); a.part_res = ctx->d_pr.as<double>();
+        launch_score(a, rc.mode, unit_z, n_pairs, ctx->stream);
+    }
+    {
+        StageTimer t(ctx, MVS_STAGE_SELECT);
+        SelectArgs a{};
+        a.points = ctx->d_points.as<double>(); a.p_stride = p_stride; a.state = state; a.F_all = ctx->d_Fall.as<double>();
+        a.H = rc.H; a.part_count = ctx->d_pc.as<uint32_t>(); a.part_res = ctx->d_pr.as<double>(); a.tiles = tiles;
+        a.max_error_sq = rc.thr; a.min_inliers = rc.min_inl; a.decompose = decompose ? 1 : 0;
+        a.mask = ctx->d_mask.as<uint8_t>(); a.all_counts = want_all_counts ? ctx->d_counts.as<int32_t>() : nullptr;
+        launch_select(a, rc.mode, unit_z, n_pairs, ctx->stream);
+    }
+    if (!decompose) return MVS_OK;
+    CK(ctx->d_valid.ensure((size_t)n_pairs * 4 * p_stride));
+    CK(ctx->d_tri.ensure((size_t)n_pairs * 4 * p_stride * 3 * sizeof(double)));
+    CK(ctx->d_opts.ensure((size_t)n_pairs * p_stride * 3 * sizeof(double)));
+    CK(ctx->d_oidx.ensure((size_t)n_pairs * p_stride * sizeof(uint64_t)));
+    CK(ctx->d_results.ensure((size_t)n_pairs * sizeof(mvs_pair_result)));
+    {
+        StageTimer t(ctx, MVS_STAGE_TRIANGULATE);
+        TriArgs a{};
+        a.points = ctx->d_points.as<double>(); a.p_stride = p_stride; a.state = state; a.mask = ctx->d_mask.as<uint8_t>();
+        a.n_cand = 4; a.valid = ctx->d_valid.as<uint8_t>(); a.tri = ctx->d_tri.as<double>();
+        launch_triangulate(a, p_stride, n_pairs, ctx->stream);
+    }
+    {
+        StageTimer t(ctx, MVS_STAGE_FINALIZE);
+        FinishArgs a{};
+        a.state = state; a.p_stride = p_stride; a.n_cand = 4; a.valid = ctx->d_valid.as<uint8_t>(); a.tri = ctx->d_tri.as<double>();
+        a.matches = d_matches; a.out_points = ctx->d_opts.as<double>(); a.out_index = ctx->d_oidx.as<uint64_t>();
+        a.results = ctx->d_results.as<mvs_pair_result>();
+        launch_finish(a, n_pairs, ctx->stream);
+    }
+    CK(cudaGetLastError());
+    return MVS_OK;
+}
+
+int choose_splits(int q_tiles, int n_pairs, int nt_max)
+{
+    const int train_tiles = std::max(1, (nt_max + 255) / 256);
+    const long ctas = (long)q_tiles * n_pairs;
+    const long target = 148L * 6;  // a few CTAs of 256 threads per SM
+    long s = (target + ctas - 1) / ctas;
+    s = std::max(1L, std::min<long>(s, train_tiles));
+    return (int)std::min<long>(s, 64);
+}
+
+bool unit_z_intrinsics(const double Ki[9]) { return Ki[6] == 0.0 && Ki[7] == 0.0 && Ki[8] == 1.0; }
+
+}  // namespace
+
+// ============================================================================================ C ABI
+extern "C" {
+
+int mvs_abi_version(void) { return MVS_ABI_VERSION; }
+
+const char *mvs_status_string(int s)
+{
+    switch (s) {
+    case MVS_OK: return "ok";
+    case MVS_E_BAD_ARG: return "bad argument";
+    case MVS_E_TOO_FEW_POINTS: return "fewer than 8 correspondences";
+    case MVS_E_NO_MODEL: return "no model with any inlier";
+    case MVS_E_TOO_FEW_INLIERS: return "fewer inliers than the minimum";
+    case MVS_E_NO_CHEIRALITY: return "no candidate pose passes the cheirality test";
+    case MVS_E_CUDA: return "CUDA error";
+    case MVS_E_CAPACITY: return "output capacity too small";
+    case MVS_E_UNSUPPORTED: return "unsupported";
+    default: return "unknown status";
+    }
+}
+
+int mvs_create(mvs_ctx **out, int device)
+{
+    if (!out) return MVS_E_BAD_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return MVS_E_CUDA;  // no CPU fallback
+    if (device < 0 || device >= count) return MVS_E_BAD_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return MVS_E_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return MVS_E_CUDA;
+    if (prop.major != 10) return MVS_E_UNSUPPORTED;  // sm_100a binary only
+    mvs_ctx *ctx = new mvs_ctx();
+    ctx->device = device;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MVS_E_CUDA; }
+    ctx->own_stream = true;
+    std::memset(&ctx->acc, 0, sizeof(ctx->acc));
+    *out = ctx;
+    return MVS_OK;
+}
+
+void mvs_destroy(mvs_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf *bufs[] = {&ctx->d_desc, &ctx->d_kp, &ctx->d_foff, &ctx->d_fcnt, &ctx->t_desc, &ctx->t_foff, &ctx->t_fcnt,
+                      &ctx->d_pairs, &ctx->d_partial, &ctx->d_rev, &ctx->d_matches, &ctx->d_nmatch, &ctx->d_points,
+                      &ctx->d_state, &ctx->d_Fall, &ctx->d_pc, &ctx->d_pr, &ctx->d_mask, &ctx->d_valid, &ctx->d_tri,
+                      &ctx->d_opts, &ctx->d_oidx, &ctx->d_results, &ctx->d_table, &ctx->d_in1, &ctx->d_in2,
+                      &ctx->d_knn_i, &ctx->d_knn_d, &ctx->d_counts};
+    for (DevBuf *b : bufs) b->release();
+    ctx->l2.release();
+    for (auto &p : ctx->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *mvs_last_error(const mvs_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int mvs_set_stream(mvs_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return MVS_E_BAD_ARG;
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    ctx->own_stream = false;
+    return MVS_OK;
+}
+
+int mvs_synchronize(mvs_ctx *ctx)
+{
+    if (!ctx) return MVS_E_BAD_ARG;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MVS_OK;
+}
+
+int mvs_profile_enable(mvs_ctx *ctx, int on)
+{
+    if (!ctx) return MVS_E_BAD_ARG;
+    ctx->prof = on != 0;
+    return MVS_OK;
+}
+
+int mvs_profile_read(mvs_ctx *ctx, mvs_profile *out, int reset)
+{
+    if (!ctx || !out) return MVS_E_BAD_ARG;
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (auto &p : ctx->pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) ctx->acc.ms[p.stage] += (double)ms;
+        ctx->ev_pool.push_back(p.a); ctx->ev_pool.push_back(p.b);
+    }
+    ctx->pending.clear();
+    *out = ctx->acc;
+    if (reset) std::memset(&ctx->acc, 0, sizeof(ctx->acc));
+    return MVS_OK;
+}
+
+uint64_t mvs_kernel_launches(const mvs_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+void mvs_sample_table(uint64_t seed, uint64_t pair_id, uint32_t n_points, int H, uint32_t *out)
+{
+    for (int h = 0; h < H; ++h) {
+        uint32_t row[8];
+        sample_row(seed, pair_id, n_points, h, row);
+        for (int j = 0; j < 8; ++j) out[(size_t)h * 8 + j] = row[j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------ matching
+static int match_two_sets(mvs_ctx *ctx, const uint8_t *query, int nq, const uint8_t *train, int nt, int desc_bytes,
+                          const mvs_match_params *mp, bool want_knn, int *n_out_dev_ready)
+{
+    (void)n_out_dev_ready;
+    if (!ctx) return MVS_E_BAD_ARG;
+    if (!query || !train || nq < 1) return fail(ctx, MVS_E_BAD_ARG, "null descriptors or nq < 1");
+    if (nt < 2) return fail(ctx, MVS_E_BAD_ARG, "knnMatch(k=2) needs at least 2 train descriptors");
+    if (desc_bytes != 32) return fail(ctx, MVS_E_UNSUPPORTED, "only 256-bit (32-byte) descriptors are supported");
+    if (nq > (int)kIdxMask || nt > (int)kIdxMask) return fail(ctx, MVS_E_UNSUPPORTED, "more than 2^22-1 descriptors per side");
+    CK(cudaSetDevice(ctx->device));
+    // scratch frame table: frame 0 = train, frame 1 = query
+    CK(ctx->t_desc.ensure(((size_t)nq + nt) * 32));
+    CK(ctx->t_foff.ensure(2 * sizeof(int32_t)));
+    CK(ctx->t_fcnt.ensure(2 * sizeof(int32_t)));
+    const int32_t off[2] = {0, nt}, cnt[2] = {nt, nq};
+    CK(cudaMemcpyAsync(ctx->t_desc.p, train, (size_t)nt * 32, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->t_desc.as<uint8_t>() + (size_t)nt * 32, query, (size_t)nq * 32, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->t_foff.p, off, sizeof(off), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->t_fcnt.p, cnt, sizeof(cnt), cudaMemcpyHostToDevice, ctx->stream));
+    const bool cross = mp && mp->cross_check;
+    const int splits = choose_splits((nq + 255) / 256, 1, nt);
+    const int rsplits = cross ? choose_splits((nt + 255) / 256, 1, nq) : 0;
+    CK(ctx->d_partial.ensure((size_t)splits * nq * sizeof(uint2)));
+    if (cross) CK(ctx->d_rev.ensure((size_t)rsplits * nt * sizeof(uint2)));
+    CK(ctx->d_matches.ensure((size_t)nq * sizeof(mvs_match)));
+    CK(ctx->d_nmatch.ensure(sizeof(int32_t)));
+    if (want_knn) { CK(ctx->d_knn_i.ensure((size_t)nq * 2 * sizeof(int32_t))); CK(ctx->d_knn_d.ensure((size_t)nq * 2 * sizeof(int32_t))); }
+    KnnArgs ka{};
+    ka.desc = ctx->t_desc.as<uint4>(); ka.frame_off = ctx->t_foff.as<int32_t>(); ka.frame_cnt = ctx->t_fcnt.as<int32_t>();
+    ka.pairs = nullptr; ka.partial = ctx->d_partial.as<uint2>(); ka.q_stride = nq; ka.reverse = 0;
+    {
+        StageTimer t(ctx, MVS_STAGE_KNN, cross ? 2 : 1);
+        launch_knn2_hamming(ka, nq, splits, 1, ctx->stream);
+        if (cross) {
+            KnnArgs kr = ka;
+            kr.partial = ctx->d_rev.as<uint2>(); kr.q_stride = nt; kr.reverse = 1;
+            launch_knn2_hamming(kr, nt, rsplits, 1, ctx->stream);
+        }
+    }
+    FinalizeArgs fa{};
+    fa.frame_off = ka.frame_off; fa.frame_cnt = ka.frame_cnt; fa.pairs = nullptr;
+    fa.partial = ka.partial; fa.splits = splits; fa.q_stride = nq;
+    fa.rev_partial = cross ? ctx->d_rev.as<uint2>() : nullptr; fa.rev_splits = rsplits; fa.rev_stride = nt;
+    fa.ratio = mp ? mp->ratio : 0.7; fa.max_dist = mp ? mp->max_dist : -1.0;
+    fa.kp = nullptr; fa.matches = ctx->d_matches.as<mvs_match>(); fa.n_matches = ctx->d_nmatch.as<int32_t>();
+    fa.points = nullptr; fa.state = nullptr;
+    fa.knn_idx = want_knn ? ctx->d_knn_i.as<int32_t>() : nullptr; fa.knn_dist = want_knn ? ctx->d_knn_d.as<int32_t>() : nullptr;
+    {
+        StageTimer t(ctx, MVS_STAGE_MATCH_FINALIZE);
+        CK(launch_match_finalize(fa, nq, 1, ctx->stream));
+    }
+    CK(cudaGetLastError());
+    return MVS_OK;
+}
+
+int mvs_knn2_hamming(mvs_ctx *ctx, const uint8_t *query, int nq, const uint8_t *train, int nt, int desc_bytes,
+                     int32_t *idx, int32_t *dist)
+{
+    if (!idx || !dist) return fail(ctx, MVS_E_BAD_ARG, "null output");
+    mvs_match_params mp{0.7, -1.0, 0, 0};
+    int st = match_two_sets(ctx, query, nq, train, nt, desc_bytes, &mp, true, nullptr);
+    if (st != MVS_OK) return st;
+    CK(cudaMemcpyAsync(idx, ctx->d_knn_i.p, (size_t)nq * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(dist, ctx->d_knn_d.p, (size_t)nq * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MVS_OK;
+}
+
+int mvs_match_hamming(mvs_ctx *ctx, const uint8_t *query, int nq, const uint8_t *train, int nt, int desc_bytes,
+                      const mvs_match_params *params, mvs_match *out, int capacity, int *n_out)
+{
+    if (!n_out) return fail(ctx, MVS_E_BAD_ARG, "null n_out");
+    *n_out = 0;
+    int st = match_two_sets(ctx, query, nq, train, nt, desc_bytes, params, false, nullptr);
+    if (st != MVS_OK) return st;
+    int32_t m = 0;
+    CK(cudaMemcpyAsync(&m, ctx->d_nmatch.p, sizeof(m), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (m > capacity) { *n_out = m; return fail(ctx, MVS_E_CAPACITY, "match capacity too small"); }
+    if (m > 0) {
+        if (!out) return fail(ctx, MVS_E_BAD_ARG, "null output");
+        CK(cudaMemcpyAsync(out, ctx->d_matches.p, (size_t)m * sizeof(mvs_match), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    *n_out = m;
+    return MVS_OK;
+}
+
+int mvs_knn2_l2(mvs_ctx *ctx, const float *query, int nq, const float *train, int nt, int dim, int32_t *idx, float *dist)
+{
+    if (!ctx) return MVS_E_BAD_ARG;
+    if (!query || !train || !idx || !dist || nq < 1) return fail(ctx, MVS_E_BAD_ARG, "null argument or nq < 1");
+    if (nt < 2) return fail(ctx, MVS_E_BAD_ARG, "knnMatch(k=2) needs at least 2 train descriptors");
+    CK(cudaSetDevice(ctx->device));
+    StageTimer t(ctx, MVS_STAGE_L2, 0);
+    std::string err;
+    int nl = 0;
+    int st = mvs::l2_knn2(ctx->l2, ctx->stream, query, nq, train, nt, dim, idx, dist, nullptr, nullptr, 0, nullptr, &nl, err);
+    ctx->launches += nl; ctx->acc.launches[MVS_STAGE_L2] += nl;
+    if (st != MVS_OK) ctx->err = err;
+    return st;
+}
+
+int mvs_match_l2(mvs_ctx *ctx, const float *query, int nq, const float *train, int nt, int dim,
+                 const mvs_match_params *params, mvs_match *out, int capacity, int *n_out)
+{
+    if (!ctx) return MVS_E_BAD_ARG;
+    if (!query || !train || !n_out || nq < 1) return fail(ctx, MVS_E_BAD_ARG, "null argument or nq < 1");
+    if (nt < 2) return fail(ctx, MVS_E_BAD_ARG, "knnMatch(k=2) needs at least 2 train descriptors");
+    CK(cudaSetDevice(ctx->device));
+    StageTimer t(ctx, MVS_STAGE_L2, 0);
+    std::string err;
+    int nl = 0;
+    mvs_match_params mp = params ? *params : mvs_match_params{0.7, -1.0, 0, 0};
+    int st = mvs::l2_knn2(ctx->l2, ctx->stream, query, nq, train, nt, dim, nullptr, nullptr, &mp, out, capacity, n_out, &nl, err);
+    ctx->launches += nl; ctx->acc.launches[MVS_STAGE_L2] += nl;
+    if (st != MVS_OK) ctx->err = err;
+    return st;
+}
+
+// ------------------------------------------------------------------------------------------ geometry
+int mvs_find_fundamental_matrix(mvs_ctx *ctx, const double *p1s, const double *p2s, int n_sets, double *F_out)
+{
+    if (!ctx) return MVS_E_BAD_ARG;
+    if (!p1s || !p2s || !F_out || n_sets < 1) return fail(ctx, MVS_E_BAD_ARG, "null argument or n_sets < 1");
+    CK(cudaSetDevice(ctx->device));
+    const size_t in_b = (size_t)n_sets * 24 * sizeof(double);
+    CK(ctx->d_in1.ensure(in_b)); CK(ctx->d_in2.ensure(in_b));
+    CK(ctx->d_Fall.ensure((size_t)n_sets * (9 + 48) * sizeof(double)));
+    CK(cudaMemcpyAsync(ctx->d_in1.p, p1s, in_b, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_in2.p, p2s, in_b, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        StageTimer t(ctx, MVS_STAGE_HYPOTHESES);
+        launch_fundamental_sets(ctx->d_in1.as<double>(), ctx->d_in2.as<double>(), n_sets, ctx->d_Fall.as<double>(), ctx->stream);
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(F_out, ctx->d_Fall.p, (size_t)n_sets * 9 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MVS_OK;
+}
+
+static int upload_table(mvs_ctx *ctx, const uint32_t *samples, int H, int n, const uint32_t **d_table)
+{
+    *d_table = nullptr;
+    if (!samples) return MVS_OK;
+    for (size_t i = 0; i < (size_t)H * 8; ++i)
+        if (samples[i] >= (uint32_t)n) return fail(ctx, MVS_E_BAD_ARG, "sample index out of range");
+    CK(ctx->d_table.ensure((size_t)H * 8 * sizeof(uint32_t)));
+    CK(cudaMemcpyAsync(ctx->d_table.p, samples, (size_t)H * 8 * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    *d_table = ctx->d_table.as<uint32_t>();
+    return MVS_OK;
+}
+
+static int init_state(mvs_ctx *ctx, int n)
+{
+    PairState st;
+    std::memset(&st, 0, sizeof(st));
+    st.status = n < 8 ? MVS_E_TOO_FEW_POINTS : MVS_OK;
+    st.n_matches = n; st.best_h = -1; st.candidate = -1;
+    CK(ctx->d_state.ensure(sizeof(PairState)));
+    CK(cudaMemcpyAsync(ctx->d_state.p, &st, sizeof(st), cudaMemcpyHostToDevice, ctx->stream));
+    return MVS_OK;
+}
+
+int mvs_ransac_fundamental(mvs_ctx *ctx, const double *p1, const double *p2, int n, const uint32_t *samples,
+                           const mvs_ransac_params *params, double F[9], uint8_t *inlier_mask, int *inlier_count,
+                           double *residual, int *best_hypothesis, int32_t *all_counts)
+{
+    if (!ctx) return MVS_E_BAD_ARG;
+    if (!p1 || !p2 || n < 0) return fail(ctx, MVS_E_BAD_ARG, "null points");
+    if (inlier_count) *inlier_count = 0;
+    if (n < 8) return fail(ctx, MVS_E_TOO_FEW_POINTS, "fewer than 8 correspondences");  // estimator-RANSAC.cpp:25-29
+    RansacCfg rc;
+    int st = resolve_ransac(ctx, params, nullptr, rc);
+    if (st != MVS_OK) return st;
+    CK(cudaSetDevice(ctx->device));
+    std::vector<double> inter((size_t)n * 6);
+    bool unit_z = true;
+    for (int i = 0; i < n; ++i) {
+        for (int k = 0; k < 3; ++k) { inter[(size_t)i * 6 + k] = p1[(size_t)i * 3 + k]; inter[(size_t)i * 6 + 3 + k] = p2[(size_t)i * 3 + k]; }
+        unit_z = unit_z && p1[(size_t)i * 3 + 2] == 1.0 && p2[(size_t)i * 3 + 2] == 1.0;
+    }
+    CK(ctx->d_points.ensure(inter.size() * sizeof(double)));
+    CK(cudaMemcpyAsync(ctx->d_points.p, inter.data(), inter.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    const uint32_t *d_table = nullptr;
+    if ((st = upload_table(ctx, samples, rc.H, n, &d_table)) != MVS_OK) return st;
+    if ((st = init_state(ctx, n)) != MVS_OK) return st;
+    if ((st = run_geometry(ctx, 1, n, rc, unit_z, d_table, rc.pair_base, false, all_counts != nullptr, nullptr)) != MVS_OK) return st;
+    PairState hs;
+    CK(cudaMemcpyAsync(&hs, ctx->d_state.p, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
+    if (inlier_mask) CK(cudaMemcpyAsync(inlier_mask, ctx->d_mask.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (all_counts) CK(cudaMemcpyAsync(all_counts, ctx->d_counts.p, (size_t)rc.H * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (F) std::memcpy(F, hs.F, sizeof(hs.F));
+    if (inlier_count) *inlier_count = hs.n_inliers;
+    if (residual) *residual = hs.residual;
+    if (best_hypothesis) *best_hypothesis = hs.best_h;
+    return hs.status;
+}
+
+int mvs_sfm_solve(mvs_ctx *ctx, const double *xy1, const double *xy2, int n, const double K[9],
+                  const mvs_ransac_params *params, const uint32_t *samples, mvs_pair_result *result,
+                  uint8_t *inlier_mask, double *points, uint64_t *indexes, int capacity)
+{
+    if (!ctx) return MVS_E_BAD_ARG;
+    if (!xy1 || !xy2 || !K || !result || n < 0) return fail(ctx, MVS_E_BAD_ARG, "null argument");
+    std::memset(result, 0, sizeof(*result));
+    result->n_matches = n; result->best_hypothesis = -1; result->candidate = -1;
+    if (n < 8) { result->status = MVS_E_TOO_FEW_POINTS; return fail(ctx, MVS_E_TOO_FEW_POINTS, "fewer than 8 correspondences"); }
+    RansacCfg rc;
+    int st = resolve_ransac(ctx, params, K, rc);
+    if (st != MVS_OK) return st;
+    CK(cudaSetDevice(ctx->device));
+    NormArgs na;
+    h_inverse3(K, na.Kinv);
+    const bool unit_z = unit_z_intrinsics(na.Kinv);
+    const size_t xb = (size_t)n * 2 * sizeof(double);
+    CK(ctx->d_in1.ensure(xb)); CK(ctx->d_in2.ensure(xb));
+    CK(ctx->d_points.ensure((size_t)n * 6 * sizeof(double)));
+    CK(ctx->d_state.ensure(sizeof(PairState)));
+    CK(cudaMemcpyAsync(ctx->d_in1.p, xy1, xb, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_in2.p, xy2, xb, cudaMemcpyHostToDevice, ctx->stream));
+    const uint32_t *d_table = nullptr;
+    if ((st = upload_table(ctx, samples, rc.H, n, &d_table)) != MVS_OK) return st;
+    {
+        StageTimer t(ctx, MVS_STAGE_MATCH_FINALIZE);
+        launch_normalize_points(ctx->d_in1.as<double>(), ctx->d_in2.as<double>(), n, na, ctx->d_points.as<double>(),
+                                ctx->d_state.as<PairState>(), ctx->stream);
+    }
+    if ((st = run_geometry(ctx, 1, n, rc, unit_z, d_table, rc.pair_base, true, false, nullptr)) != MVS_OK) return st;
+    CK(cudaMemcpyAsync(result, ctx->d_results.p, sizeof(*result), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (inlier_mask && result->status != MVS_E_TOO_FEW_POINTS)
+        CK(cudaMemcpyAsync(inlier_mask, ctx->d_mask.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (result->status == MVS_OK) {
+        if (result->n_points > capacity) return fail(ctx, MVS_E_CAPACITY, "point capacity too small");
+        if (points) CK(cudaMemcpyAsync(points, ctx->d_opts.p, (size_t)result->n_points * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (indexes) CK(cudaMemcpyAsync(indexes, ctx->d_oidx.p, (size_t)result->n_points * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return result->status;
+}
+
+int mvs_sfm_triangulate(mvs_ctx *ctx, const double *xy1, const double *xy2, int n, const double K[9],
+                        const double R1[9], const double t1[3], const double R2[9], const double t2[3],
+                        double *points, uint64_t *indexes, int capacity, int *n_out)
+{
+    if (!ctx) return MVS_E_BAD_ARG;
+    if (!xy1 || !xy2 || !K || !R1 || !t1 || !R2 || !t2 || !n_out || n < 0) return fail(ctx, MVS_E_BAD_ARG, "null argument");
+    *n_out = 0;
+    if (n == 0) return MVS_OK;
+    CK(cudaSetDevice(ctx->device));
+    // T_1_to_2 = pose2.inverse() * pose1 (sfm-solve.cpp:382)
+    PairState st;
+    std::memset(&st, 0, sizeof(st));
+    double Ri[9], ti[3];
+    h_se3_inverse(R2, t2, Ri, ti);
+    h_se3_compose(Ri, ti, R1, t1, st.Rc[0], st.tc);
+    st.status = MVS_OK; st.n_matches = n; st.best_h = -1; st.candidate = -1;
+    NormArgs na;
+    h_inverse3(K, na.Kinv);
+    const size_t xb = (size_t)n * 2 * sizeof(double);
+    CK(ctx->d_in1.ensure(xb)); CK(ctx->d_in2.ensure(xb));
+    CK(ctx->d_points.ensure((size_t)n * 6 * sizeof(double)));
+    CK(ctx->d_state.ensure(sizeof(PairState)));
+    CK(ctx->d_valid.ensure((size_t)4 * n));
+    CK(ctx->d_tri.ensure((size_t)4 * n * 3 * sizeof(double)));
+    CK(ctx->d_opts.ensure((size_t)n * 3 * sizeof(double)));
+    CK(ctx->d_oidx.ensure((size_t)n * sizeof(uint64_t)));
+    CK(ctx->d_results.ensure(sizeof(mvs_pair_result)));
+    CK(cudaMemcpyAsync(ctx->d_in1.p, xy1, xb, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_in2.p, xy2, xb, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        StageTimer t(ctx, MVS_STAGE_MATCH_FINALIZE);
+        launch_normalize_points(ctx->d_in1.as<double>(), ctx->d_in2.as<double>(), n, na, ctx->d_points.as<double>(), nullptr, ctx->stream);
+    }
+    CK(cudaMemcpyAsync(ctx->d_state.p, &st, sizeof(st), cudaMemcpyHostToDevice, ctx->stream));
+    {
+        StageTimer t(ctx, MVS_STAGE_TRIANGULATE);
+        TriArgs a{};
+        a.points = ctx->d_points.as<double>(); a.p_stride = n; a.state = ctx->d_state.as<PairState>(); a.mask = nullptr;
+        a.n_cand = 1; a.valid = ctx->d_valid.as<uint8_t>(); a.tri = ctx->d_tri.as<double>();
+        launch_triangulate(a, n, 1, ctx->stream);
+    }
+    {
+        StageTimer t(ctx, MVS_STAGE_FINALIZE);
+        FinishArgs a{};
+        a.state = ctx->d_state.as<PairState>(); a.p_stride = n; a.n_cand = 1; a.valid = ctx->d_valid.as<uint8_t>();
+        a.tri = ctx->d_tri.as<double>(); a.matches = nullptr; a.out_points = ctx->d_opts.as<double>();
+        a.out_index = ctx->d_oidx.as<uint64_t>(); a.results = ctx->d_results.as<mvs_pair_result>();
+        launch_finish(a, 1, ctx->stream);
+    }
+    CK(cudaGetLastError());
+    mvs_pair_result r;
+    CK(cudaMemcpyAsync(&r, ctx->d_results.p, sizeof(r), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int m = r.n_points;
+    if (m > capacity) { *n_out = m; return fail(ctx, MVS_E_CAPACITY, "point capacity too small"); }
+    if (m > 0) {
+        if (points) CK(cudaMemcpyAsync(points, ctx->d_opts.p, (size_t)m * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (indexes) CK(cudaMemcpyAsync(indexes, ctx->d_oidx.p, (size_t)m * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    *n_out = m;
+    return MVS_OK;
+}
+
+// ------------------------------------------------------------------------------------------ batch
+int mvs_frames_upload(mvs_ctx *ctx, int n_frames, const uint8_t *const *desc, const float *const *kp,
+                      const int32_t *counts, int desc_bytes)
+{
+    if (!ctx) return MVS_E_BAD_ARG;
+    if (n_frames < 1 || !desc || !kp || !counts) return fail(ctx, MVS_E_BAD_ARG, "null argument or n_frames < 1");
+    if (desc_bytes != 32) return fail(ctx, MVS_E_UNSUPPORTED, "only 256-bit (32-byte) descriptors are supported");
+    CK(cudaSetDevice(ctx->device));
+    std::vector<int32_t> off(n_frames), cnt(n_frames);
+    size_t total = 0;
+    for (int f = 0; f < n_frames; ++f) {
+        if (counts[f] < 0 || counts[f] > (int)kIdxMask) return fail(ctx, MVS_E_BAD_ARG, "bad keypoint count");
+        if (counts[f] > 0 && (!desc[f] || !kp[f])) return fail(ctx, MVS_E_BAD_ARG, "null frame buffer");
+        off[f] = (int32_t)total; cnt[f] = counts[f];
+        total += (size_t)counts[f];
+        if (total > 0x7FFFFFFFull) return fail(ctx, MVS_E_UNSUPPORTED, "more than 2^31 keypoints in the frame table");
+    }
+    CK(ctx->d_desc.ensure(std::max<size_t>(total, 1) * 32));
+    CK(ctx->d_kp.ensure(std::max<size_t>(total, 1) * sizeof(float2)));
+    CK(ctx->d_foff.ensure((size_t)n_frames * sizeof(int32_t)));
+    CK(ctx->d_fcnt.ensure((size_t)n_frames * sizeof(int32_t)));
+    for (int f = 0; f < n_frames; ++f) {
+        if (!cnt[f]) continue;
+        CK(cudaMemcpyAsync(ctx->d_desc.as<uint8_t>() + (size_t)off[f] * 32, desc[f], (size_t)cnt[f] * 32, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_kp.as<float2>() + off[f], kp[f], (size_t)cnt[f] * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CK(cudaMemcpyAsync(ctx->d_foff.p, off.data(), (size_t)n_frames * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_fcnt.p, cnt.data(), (size_t)n_frames * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));  // off/cnt are stack/vector memory
+    ctx->h_off.swap(off); ctx->h_cnt.swap(cnt);
+    return MVS_OK;
+}
+
+int mvs_pair_batch_enqueue(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, const double K[9],
+                           const mvs_match_params *mparams, const mvs_ransac_params *rparams,
+                           mvs_pair_result *results, mvs_match *matches, uint8_t *inlier_mask,
+                           double *points, uint64_t *indexes, int capacity)
+{
+    if (!ctx) return MVS_E_BAD_ARG;
+    if (!pairs || n_pairs < 1 || !K || !results) return fail(ctx, MVS_E_BAD_ARG, "null argument or n_pairs < 1");
+    if (ctx->h_cnt.empty()) return fail(ctx, MVS_E_BAD_ARG, "no frames uploaded (mvs_frames_upload)");
+    const int nf = (int)ctx->h_cnt.size();
+    int max_nq = 0, max_nt = 0;
+    for (int i = 0; i < n_pairs; ++i) {
+        const int a = pairs[2 * i], b = pairs[2 * i + 1];
+        if (a < 0 || a >= nf || b < 0 || b >= nf || a == b) return fail(ctx, MVS_E_BAD_ARG, "bad frame index in pairs");  // image-pair.cpp:49
+        if (ctx->h_cnt[b] < 1 || ctx->h_cnt[a] < 2) return fail(ctx, MVS_E_BAD_ARG, "frame with too few keypoints (visual-feature.cpp:56)");
+        max_nq = std::max(max_nq, ctx->h_cnt[b]); max_nt = std::max(max_nt, ctx->h_cnt[a]);
+    }
+    const bool details = matches || inlier_mask || points || indexes;
+    if (details && capacity < max_nq) return fail(ctx, MVS_E_CAPACITY, "detail capacity smaller than the largest pair frame");
+    RansacCfg rc;
+    int st = resolve_ransac(ctx, rparams, K, rc);
+    if (st != MVS_OK) return st;
+    CK(cudaSetDevice(ctx->device));
+    const int qs = max_nq;
+    const bool cross = mparams && mparams->cross_check;
+    const int splits = choose_splits((max_nq + 255) / 256, n_pairs, max_nt);
+    const int rsplits = cross ? choose_splits((max_nt + 255) / 256, n_pairs, max_nq) : 0;
+    CK(ctx->d_pairs.ensure((size_t)n_pairs * sizeof(int2)));
+    CK(ctx->d_partial.ensure((size_t)n_pairs * splits * qs * sizeof(uint2)));
+    if (cross) CK(ctx->d_rev.ensure((size_t)n_pairs * rsplits * max_nt * sizeof(uint2)));
+    CK(ctx->d_matches.ensure((size_t)n_pairs * qs * sizeof(mvs_match)));
+    CK(ctx->d_nmatch.ensure((size_t)n_pairs * sizeof(int32_t)));
+    CK(ctx->d_points.ensure((size_t)n_pairs * qs * 6 * sizeof(double)));
+    CK(ctx->d_state.ensure((size_t)n_pairs * sizeof(PairState)));
+    CK(cudaMemcpyAsync(ctx->d_pairs.p, pairs, (size_t)n_pairs * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+
+    KnnArgs ka{};
+    ka.desc = ctx->d_desc.as<uint4>(); ka.frame_off = ctx->d_foff.as<int32_t>(); ka.frame_cnt = ctx->d_fcnt.as<int32_t>();
+    ka.pairs = ctx->d_pairs.as<int2>(); ka.partial = ctx->d_partial.as<uint2>(); ka.q_stride = qs; ka.reverse = 0;
+    {
+        StageTimer t(ctx, MVS_STAGE_KNN, cross ? 2 : 1);
+        launch_knn2_hamming(ka, max_nq, splits, n_pairs, ctx->stream);
+        if (cross) {
+            KnnArgs kr = ka;
+            kr.partial = ctx->d_rev.as<uint2>(); kr.q_stride = max_nt; kr.reverse = 1;
+            launch_knn2_hamming(kr, max_nt, rsplits, n_pairs, ctx->stream);
+        }
+    }
+    FinalizeArgs fa{};
+    fa.frame_off = ka.frame_off; fa.frame_cnt = ka.frame_cnt; fa.pairs = ka.pairs;
+    fa.partial = ka.partial; fa.splits = splits; fa.q_stride = qs;
+    fa.rev_partial = cross ? ctx->d_rev.as<uint2>() : nullptr; fa.rev_splits = rsplits; fa.rev_stride = max_nt;
+    fa.ratio = mparams ? mparams->ratio : 0.7; fa.max_dist = mparams ? mparams->max_dist : -1.0;
+    fa.kp = ctx->d_kp.as<float2>();
+    h_inverse3(K, fa.Kinv);
+    const bool unit_z = unit_z_intrinsics(fa.Kinv);
+    fa.matches = ctx->d_matches.as<mvs_match>(); fa.n_matches = ctx->d_nmatch.as<int32_t>();
+    fa.points = ctx->d_points.as<double>(); fa.state = ctx->d_state.as<PairState>();
+    fa.knn_idx = nullptr; fa.knn_dist = nullptr;
+    {
+        StageTimer t(ctx, MVS_STAGE_MATCH_FINALIZE);
+        CK(launch_match_finalize(fa, max_nq, n_pairs, ctx->stream));
+    }
+    if ((st = run_geometry(ctx, n_pairs, qs, rc, unit_z, nullptr, rc.pair_base, true, false, ctx->d_matches.as<mvs_match>())) != MVS_OK) return st;
+
+    CK(cudaMemcpyAsync(results, ctx->d_results.p, (size_t)n_pairs * sizeof(mvs_pair_result), cudaMemcpyDeviceToHost, ctx->stream));
+    if (matches)
+        CK(cudaMemcpy2DAsync(matches, (size_t)capacity * sizeof(mvs_match), ctx->d_matches.p, (size_t)qs * sizeof(mvs_match),
+                             (size_t)qs * sizeof(mvs_match), n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+    if (inlier_mask)
+        CK(cudaMemcpy2DAsync(inlier_mask, (size_t)capacity, ctx->d_mask.p, (size_t)qs, (size_t)qs, n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+    if (points)
+        CK(cudaMemcpy2DAsync(points, (size_t)capacity * 24, ctx->d_opts.p, (size_t)qs * 24, (size_t)qs * 24, n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+    if (indexes)
+        CK(cudaMemcpy2DAsync(indexes, (size_t)capacity * 8, ctx->d_oidx.p, (size_t)qs * 8, (size_t)qs * 8, n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+    return MVS_OK;
+}
+
+int mvs_pair_batch(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, const double K[9],
+                   const mvs_match_params *mparams, const mvs_ransac_params *rparams,
+                   mvs_pair_result *results, mvs_match *matches, uint8_t *inlier_mask,
+                   double *points, uint64_t *indexes, int capacity)
+{
+    int st = mvs_pair_batch_enqueue(ctx, pairs, n_pairs, K, mparams, rparams, results, matches, inlier_mask, points, indexes, capacity);
+    if (st != MVS_OK) return st;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MVS_OK;
+}
+
+}  // extern "C"

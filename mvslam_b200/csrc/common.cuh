@@ -1,0 +1,323 @@
+// common.cuh — shared device helpers for libmvslam_b200 (sm_100a).
+//
+// Numerical contract: every geometry kernel computes in FP64 with separate multiplies and adds
+// (the translation units are compiled with -fmad=false) in the operation order of the reference's
+// Eigen/OpenCV code path, so the results can be compared against the CPU oracle to round-off.
+#pragma once
+#include <cfloat>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "../../include/mvslam_b200.h"
+
+namespace mvs {
+
+// source/system-config.hpp:8-14
+constexpr double kEpsilon = DBL_EPSILON;
+constexpr double kTolerance = DBL_EPSILON * 1000.0;
+constexpr double kInfinity = DBL_MAX / 10.0;
+// source/vision/sfm-solve.cpp:18-21
+constexpr double kMaxErrorSq = 5e-2;
+constexpr int kMinInliers = 8;
+
+constexpr double kSvdEps = 2.0 * DBL_EPSILON;
+constexpr double kSvdRankTol = 1e-12;
+constexpr int kSvdMaxSweeps = 30;
+
+// Hamming top-2 keys pack (distance << 22 | index): lexicographic (distance, index) order in one
+// unsigned compare, i.e. OpenCV's lowest-index tie-break for free.  Limits n to 2^22 per side.
+constexpr int kIdxBits = 22;
+constexpr uint32_t kIdxMask = (1u << kIdxBits) - 1u;
+constexpr uint32_t kKeyNone = 0xFFFFFFFFu;
+
+// per-pair device state threaded through the stages
+struct PairState {
+    int32_t status;
+    int32_t n_matches;
+    int32_t n_inliers;
+    int32_t best_h;
+    int32_t n_points;
+    int32_t candidate;
+    int32_t tri_count[4];
+    double residual;
+    double F[9];
+    double E[9];
+    double Rc[2][9];
+    double tc[3];
+};
+
+// ------------------------------------------------------------------------------------------
+// Jacobi rotation of a column pair (p<q): restates the inner step of cv::SVDecomp's one-sided
+// Jacobi (un-vendored OpenCV; the reference calls it through source/math/svd.hpp:65).
+// Returns false when the pair is already orthogonal to working precision.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool jacobi_cs(double a, double b, double g, double &c, double &s)
+{
+    if (fabs(g) <= kSvdEps * sqrt(a * b)) return false;
+    const double g2 = g * 2.0, beta = a - b;
+    const double gamma = sqrt(g2 * g2 + beta * beta);
+    if (beta < 0) {
+        const double delta = (gamma - beta) * 0.5;
+        s = sqrt(delta / gamma);
+        c = g2 / (gamma * s * 2.0);
+    } else {
+        c = sqrt((gamma + beta) / (gamma * 2.0));
+        s = g2 / (gamma * c * 2.0);
+    }
+    return true;
+}
+
+template <int N>
+__device__ __forceinline__ bool jacobi_pair(double (&W)[N][N], double (&V)[N][N], const int p, const int q)
+{
+    double a = 0.0, b = 0.0, g = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        a += W[k][p] * W[k][p];
+        b += W[k][q] * W[k][q];
+        g += W[k][p] * W[k][q];
+    }
+    double c, s;
+    if (!jacobi_cs(a, b, g, c, s)) return false;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const double wp = W[k][p], wq = W[k][q];
+        W[k][p] = c * wp + s * wq;
+        W[k][q] = c * wq - s * wp;
+        const double vp = V[k][p], vq = V[k][q];
+        V[k][p] = c * vp + s * vq;
+        V[k][q] = c * vq - s * vp;
+    }
+    return true;
+}
+
+// One-sided Jacobi SVD core, one thread per matrix, everything in registers (all indices are
+// compile-time after unrolling).  Round-robin pair order identical to the oracle's.
+template <int N>
+__device__ __forceinline__ void jacobi_svd(double (&W)[N][N], double (&V)[N][N])
+{
+    constexpr int M = (N + 1) & ~1;
+    constexpr int R = M - 1;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < kSvdMaxSweeps; ++sweep) {
+        bool changed = false;
+#pragma unroll
+        for (int s = 0; s < R; ++s) {
+            if (M - 1 < N) changed |= jacobi_pair<N>(W, V, s, M - 1);
+#pragma unroll
+            for (int k = 1; k < M / 2; ++k) {
+                const int i = (s + k) % R, j = (s - k + R) % R;
+                const int p = i < j ? i : j, q = i < j ? j : i;
+                changed |= jacobi_pair<N>(W, V, p, q);
+            }
+        }
+        if (!changed) break;
+    }
+}
+
+__device__ __forceinline__ void cross3(const double a[3], const double b[3], double o[3])
+{
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+// 3x3 SVD with FULL_UV semantics: A row-major in, U row-major, w descending, Vt row-major.
+static __device__ __noinline__ void svd3(const double A[9], double U[9], double w[3], double Vt[9])
+{
+    double W[3][3], V[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) W[i][j] = A[i * 3 + j];
+    jacobi_svd<3>(W, V);
+    double sig[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) s += W[k][j] * W[k][j];
+        sig[j] = sqrt(s);
+    }
+    // stable descending order of 3 values
+    int o0 = 0, o1 = 1, o2 = 2;
+    if (sig[o0] < sig[o1]) { int t = o0; o0 = o1; o1 = t; }
+    if (sig[o1] < sig[o2]) {
+        int t = o1; o1 = o2; o2 = t;
+        if (sig[o0] < sig[o1]) { t = o0; o0 = o1; o1 = t; }
+    }
+    const int ord[3] = {o0, o1, o2};
+    double Wc[3][3], Vc[3][3];  // columns in sorted order (dynamic gather done once through selects)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int o = ord[j];
+            Wc[k][j] = o == 0 ? W[k][0] : (o == 1 ? W[k][1] : W[k][2]);
+            Vc[k][j] = o == 0 ? V[k][0] : (o == 1 ? V[k][1] : V[k][2]);
+        }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        w[j] = ord[j] == 0 ? sig[0] : (ord[j] == 1 ? sig[1] : sig[2]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) Vt[j * 3 + k] = Vc[k][j];
+    }
+    const double thr = kSvdRankTol * w[0];
+    int nvalid = 0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        if (nvalid == j && w[j] > thr && w[j] > 0.0) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) U[k * 3 + j] = Wc[k][j] / w[j];
+            nvalid = j + 1;
+        }
+    }
+    for (int j = nvalid; j < 3; ++j) {
+        if (j == 2) {
+            const double u0[3] = {U[0], U[3], U[6]}, u1[3] = {U[1], U[4], U[7]};
+            double u2[3];
+            cross3(u0, u1, u2);
+            U[2] = u2[0]; U[5] = u2[1]; U[8] = u2[2];
+            continue;
+        }
+        // Gram-Schmidt of the unit vector least aligned with the existing columns (rank <= 1 inputs)
+        int best = 0;
+        double bestv = CUDART_INF;
+        for (int e = 0; e < 3; ++e) {
+            double v = 0.0;
+            for (int c = 0; c < j; ++c) v += U[e * 3 + c] * U[e * 3 + c];
+            if (v < bestv) { bestv = v; best = e; }
+        }
+        double x[3];
+        for (int k = 0; k < 3; ++k) x[k] = (k == best) ? 1.0 : 0.0;
+        for (int pass = 0; pass < 2; ++pass)
+            for (int c = 0; c < j; ++c) {
+                double d = 0.0;
+                for (int k = 0; k < 3; ++k) d += x[k] * U[k * 3 + c];
+                for (int k = 0; k < 3; ++k) x[k] -= d * U[k * 3 + c];
+            }
+        double nn = 0.0;
+        for (int k = 0; k < 3; ++k) nn += x[k] * x[k];
+        nn = sqrt(nn);
+        for (int k = 0; k < 3; ++k) U[k * 3 + j] = x[k] / nn;
+    }
+}
+
+__device__ __forceinline__ void mat3_mul(const double A[9], const double B[9], double C[9])
+{
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            C[i * 3 + j] = A[i * 3 + 0] * B[0 * 3 + j] + A[i * 3 + 1] * B[1 * 3 + j] + A[i * 3 + 2] * B[2 * 3 + j];
+}
+
+__device__ __forceinline__ void mat3_transpose(const double A[9], double T[9])
+{
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) T[i * 3 + j] = A[j * 3 + i];
+}
+
+__device__ __forceinline__ void mat3_vec(const double A[9], const double v[3], double o[3])
+{
+#pragma unroll
+    for (int i = 0; i < 3; ++i) o[i] = A[i * 3 + 0] * v[0] + A[i * 3 + 1] * v[1] + A[i * 3 + 2] * v[2];
+}
+
+__device__ __forceinline__ double det3(const double M[9])
+{
+    return M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
+}
+
+// SO3::rectify (source/math/lie-group.hpp:84-96): row 1 is NOT normalised (reference quirk).
+__device__ __forceinline__ void so3_rectify(const double R[9], double out[9])
+{
+    const double n0 = sqrt(R[0] * R[0] + R[1] * R[1] + R[2] * R[2]);
+    const double u0[3] = {R[0] / n0, R[1] / n0, R[2] / n0};
+    const double d = R[3] * u0[0] + R[4] * u0[1] + R[5] * u0[2];
+    const double u1[3] = {R[3] - d * u0[0], R[4] - d * u0[1], R[5] - d * u0[2]};
+    double u2[3];
+    cross3(u0, u1, u2);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { out[k] = u0[k]; out[3 + k] = u1[k]; out[6 + k] = u2[k]; }
+}
+
+// SE3::inverse (lie-group.hpp:203-207) with SO3::inverse (:75-79)
+__device__ __forceinline__ void se3_inverse(const double R[9], const double t[3], double Rout[9], double tout[3])
+{
+    double Rt[9], v[3];
+    mat3_transpose(R, Rt);
+    so3_rectify(Rt, Rout);
+    mat3_vec(Rout, t, v);
+    tout[0] = -v[0]; tout[1] = -v[1]; tout[2] = -v[2];
+}
+
+// residual of one correspondence, evaluated as (p2^T F) p1 (estimator-RANSAC.cpp:114-116).
+// UNIT_Z: both points have z == 1.0 exactly, so the multiplications by z are exact no-ops.
+template <bool UNIT_Z, int MODE>
+__device__ __forceinline__ double point_residual(double x1, double y1, double z1, double x2, double y2, double z2,
+                                                 const double (&F)[9])
+{
+    double v0, v1, v2, r;
+    if (UNIT_Z) {
+        v0 = (x2 * F[0] + y2 * F[3]) + F[6];
+        v1 = (x2 * F[1] + y2 * F[4]) + F[7];
+        v2 = (x2 * F[2] + y2 * F[5]) + F[8];
+        r = (v0 * x1 + v1 * y1) + v2;
+    } else {
+        v0 = (x2 * F[0] + y2 * F[3]) + z2 * F[6];
+        v1 = (x2 * F[1] + y2 * F[4]) + z2 * F[7];
+        v2 = (x2 * F[2] + y2 * F[5]) + z2 * F[8];
+        r = (v0 * x1 + v1 * y1) + v2 * z1;
+    }
+    if (MODE == MVS_SCORE_ALGEBRAIC) return fabs(r);
+    double l0, l1;
+    if (UNIT_Z) {
+        l0 = (F[0] * x1 + F[1] * y1) + F[2];
+        l1 = (F[3] * x1 + F[4] * y1) + F[5];
+    } else {
+        l0 = (F[0] * x1 + F[1] * y1) + F[2] * z1;
+        l1 = (F[3] * x1 + F[4] * y1) + F[5] * z1;
+    }
+    const double den = (l0 * l0 + l1 * l1) + (v0 * v0 + v1 * v1);
+    return (r * r) / den;
+}
+
+// splitmix64 — the seeded sample generator shared with the oracle (integer, bit-exact)
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x)
+{
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+
+__host__ __device__ __forceinline__ void sample_row(uint64_t seed, uint64_t pair_id, uint32_t n_points, int h,
+                                                    uint32_t row[8])
+{
+    if (h == 0 || n_points < 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) row[j] = (uint32_t)j;
+        return;
+    }
+    uint64_t st = splitmix64(seed ^ splitmix64(pair_id * 0xD1B54A32D192ED03ULL + (uint64_t)h));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        for (;;) {
+            st = splitmix64(st);
+            const uint32_t v = (uint32_t)(((st >> 32) * (uint64_t)n_points) >> 32);
+            bool dup = false;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) dup |= (k < j) && (row[k] == v);
+            if (!dup) { row[j] = v; break; }
+        }
+    }
+}
+
+}  // namespace mvs

@@ -1,0 +1,105 @@
+// kernels.h — argument blocks and host-side launchers of the device stages (internal).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace mvs {
+
+// frame table resident in HBM: descriptors as 2 x uint4 (32 B) per keypoint, keypoints as float2
+struct KnnArgs {
+    const uint4 *desc;
+    const int32_t *frame_off;  // first keypoint of each frame in desc / kp
+    const int32_t *frame_cnt;
+    const int2 *pairs;         // (base, pair) per batch entry; nullptr: frame 0 = train, frame 1 = query
+    uint2 *partial;            // [pairs][splits][q_stride] packed (best1, best2) keys
+    int q_stride;
+    int reverse;               // 1: roles swapped (cross-check pass)
+};
+
+struct FinalizeArgs {
+    const int32_t *frame_off;
+    const int32_t *frame_cnt;
+    const int2 *pairs;
+    const uint2 *partial; int splits; int q_stride;
+    const uint2 *rev_partial; int rev_splits; int rev_stride;
+    double ratio, max_dist;
+    const float2 *kp;          // nullptr: no gather
+    double Kinv[9];
+    mvs_match *matches;        // [pairs][q_stride]
+    int32_t *n_matches;        // [pairs]
+    double *points;            // [pairs][q_stride][6] = (x1,y1,z1,x2,y2,z2) or nullptr
+    PairState *state;          // [pairs] or nullptr
+    int32_t *knn_idx, *knn_dist;  // optional raw knnMatch output [pairs][q_stride][2]
+};
+
+struct NormArgs { double Kinv[9]; };
+
+struct HypArgs {
+    const double *points;      // [pairs][p_stride][6]
+    int p_stride;
+    const PairState *state;    // n_matches / status per pair (nullptr: use n_fixed)
+    int n_fixed;
+    const uint32_t *table;     // explicit [H][8] sample table shared by all pairs, or nullptr -> seeded sampler
+    uint64_t seed;
+    uint64_t pair_id_base;
+    int H;
+    double *F_all;             // [pairs][H][9]
+};
+
+struct ScoreArgs {
+    const double *points; int p_stride;
+    const PairState *state; int n_fixed;
+    const double *F_all; int H;
+    double max_error_sq;
+    int tiles;                 // point tiles per pair
+    uint32_t *part_count;      // [pairs][tiles][H]
+    double *part_res;          // [pairs][tiles][H]
+};
+
+struct SelectArgs {
+    const double *points; int p_stride;
+    PairState *state; int n_fixed;
+    const double *F_all; int H;
+    const uint32_t *part_count; const double *part_res; int tiles;
+    double max_error_sq;
+    int min_inliers;
+    int decompose;             // 0: stop after the mask (mvs_ransac_fundamental)
+    uint8_t *mask;             // [pairs][p_stride]
+    int32_t *all_counts;       // optional [pairs][H]
+};
+
+struct TriArgs {
+    const double *points; int p_stride;
+    PairState *state; int n_fixed;
+    const uint8_t *mask;       // nullptr: all ones
+    int n_cand;                // 4 (recover_pose_and_points) or 1 (sfm_triangulate: Rc[0], tc as given)
+    uint8_t *valid;            // [pairs][4][p_stride]
+    double *tri;               // [pairs][4][p_stride][3]
+};
+
+struct FinishArgs {
+    PairState *state; int n_fixed; int p_stride;
+    int n_cand;
+    const uint8_t *valid; const double *tri;
+    const mvs_match *matches;  // optional, for match_inlier_ssd
+    double *out_points;        // [pairs][p_stride][3]
+    uint64_t *out_index;       // [pairs][p_stride]
+    mvs_pair_result *results;  // [pairs]
+};
+
+void launch_knn2_hamming(const KnnArgs &a, int max_nq, int splits, int n_pairs, cudaStream_t s);
+int finalize_sort_capacity(int max_nq);
+cudaError_t launch_match_finalize(const FinalizeArgs &a, int max_nq, int n_pairs, cudaStream_t s);
+void launch_normalize_points(const double *xy1, const double *xy2, int n, const NormArgs &a, double *pts, PairState *st,
+                             cudaStream_t s);
+
+void launch_hypotheses(const HypArgs &a, int n_pairs, cudaStream_t s);
+void launch_fundamental_sets(const double *p1s, const double *p2s, int n_sets, double *F_out, cudaStream_t s);
+int score_tiles(int max_points);
+void launch_score(const ScoreArgs &a, int mode, bool unit_z, int n_pairs, cudaStream_t s);
+void launch_select(const SelectArgs &a, int mode, bool unit_z, int n_pairs, cudaStream_t s);
+void launch_triangulate(const TriArgs &a, int max_points, int n_pairs, cudaStream_t s);
+void launch_finish(const FinishArgs &a, int n_pairs, cudaStream_t s);
+
+}  // namespace mvs

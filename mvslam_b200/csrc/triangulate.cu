@@ -1,0 +1,193 @@
+// triangulate.cu — batched linear (DLT) triangulation with cheirality, candidate selection and
+// the final pose record.
+//
+//   K6 triangulate_kernel : triangulate_points (reference source/vision/sfm-solve.cpp:134-227) for
+//                           the 4 (R,t) candidates of recover_pose_and_points (:232-284); one thread
+//                           per (point, candidate), the 4x4 SVD solved in registers.
+//   K7 finish_kernel      : strict-'>' candidate choice (:259-281), order-preserving compaction of
+//                           the surviving points + original indexes, pose2in1 = SE3(SO3(R),t).inverse()
+//                           (:364), ImagePair bookkeeping (source/front-end/image-pair.cpp:158-167).
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mvs {
+
+constexpr int TRI_THREADS = 128;
+
+__global__ void __launch_bounds__(TRI_THREADS)
+triangulate_kernel(TriArgs a)
+{
+    __shared__ int s_cnt;
+    const int pair = blockIdx.z, cand = blockIdx.y;
+    PairState *st = a.state + pair;
+    if (st->status != MVS_OK) return;
+    const int n = st->n_matches;
+    if ((int)(blockIdx.x * TRI_THREADS) >= n) return;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+
+    // candidate order (Ra,+t),(Ra,-t),(Rb,+t),(Rb,-t)
+    double R[9], t[3], Rr[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = st->Rc[cand >> 1][i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) t[i] = (cand & 1) ? -st->tc[i] : st->tc[i];
+    so3_rectify(R, Rr);  // P2 = SE3(SO3(R), t).get_matrix() (:155)
+
+    const int i = blockIdx.x * TRI_THREADS + threadIdx.x;
+    bool ok = false;
+    double pt[3] = {0.0, 0.0, 0.0};
+    if (i < n && (!a.mask || a.mask[(size_t)pair * a.p_stride + i] != 0)) {
+        const double *p = a.points + ((size_t)pair * a.p_stride + i) * 6;
+        const double x1 = p[0], y1 = p[1], x2 = p[3], y2 = p[4];
+        double W[4][4], V[4][4];
+        // rows 0,1: x1[k]*P1.row(2) - P1.row(k) with P1 = I4 (:185-188)
+        W[0][0] = x1 * 0.0 - 1.0; W[0][1] = x1 * 0.0 - 0.0; W[0][2] = x1 * 1.0 - 0.0; W[0][3] = x1 * 0.0 - 0.0;
+        W[1][0] = y1 * 0.0 - 0.0; W[1][1] = y1 * 0.0 - 1.0; W[1][2] = y1 * 1.0 - 0.0; W[1][3] = y1 * 0.0 - 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double p2j = j < 3 ? Rr[6 + j] : t[2];
+            const double p0j = j < 3 ? Rr[0 + j] : t[0];
+            const double p1j = j < 3 ? Rr[3 + j] : t[1];
+            W[2][j] = x2 * p2j - p0j;
+            W[3][j] = y2 * p2j - p1j;
+        }
+        jacobi_svd<4>(W, V);
+        // X = V column of the smallest singular value (V.col(3), :193-195)
+        double best = CUDART_INF;
+        int bj = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s += W[k][j] * W[k][j];
+            s = sqrt(s);
+            if (s <= best) { best = s; bj = j; }
+        }
+        double X[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) X[k] = bj == 0 ? V[k][0] : (bj == 1 ? V[k][1] : (bj == 2 ? V[k][2] : V[k][3]));
+        if (!(fabs(X[3]) < kTolerance)) {
+            const double scale = 1.0 / X[3];
+            pt[0] = X[0] * scale; pt[1] = X[1] * scale; pt[2] = X[2] * scale;
+            if (!(pt[2] < kTolerance)) {
+                const double z2 = (R[6] * pt[0] + R[7] * pt[1] + R[8] * pt[2]) + t[2];  // un-rectified R (:218)
+                ok = !(z2 < kTolerance);
+            }
+        }
+    }
+    if (i < n) {
+        const size_t o = ((size_t)pair * 4 + cand) * a.p_stride + i;
+        a.valid[o] = ok ? 1 : 0;
+        double *tp = a.tri + o * 3;
+        tp[0] = pt[0]; tp[1] = pt[1]; tp[2] = pt[2];
+    }
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
+    if ((threadIdx.x & 31) == 0 && bal) atomicAdd(&s_cnt, __popc(bal));
+    __syncthreads();
+    if (threadIdx.x == 0 && s_cnt) atomicAdd(&st->tri_count[cand], s_cnt);
+}
+
+constexpr int FIN2_THREADS = 256;
+
+__global__ void __launch_bounds__(FIN2_THREADS)
+finish_kernel(FinishArgs a)
+{
+    __shared__ int s_cand, s_base, s_warp[FIN2_THREADS / 32];
+    __shared__ unsigned long long s_ssd;
+    const int pair = blockIdx.x;
+    PairState *st = a.state + pair;
+    mvs_pair_result *res = a.results ? a.results + pair : nullptr;
+    if (threadIdx.x == 0) {
+        int cand = -1;
+        if (st->status == MVS_OK) {
+            int best = 0;
+            for (int c = 0; c < a.n_cand; ++c)
+                if (st->tri_count[c] > best) { best = st->tri_count[c]; cand = c; }
+            if (cand < 0) st->status = MVS_E_NO_CHEIRALITY;
+            st->candidate = cand;
+            st->n_points = best;
+        }
+        s_cand = cand; s_base = 0; s_ssd = 0ull;
+    }
+    __syncthreads();
+    const int cand = s_cand;
+    const int n = st->n_matches;
+    if (cand >= 0) {
+        const uint8_t *valid = a.valid + ((size_t)pair * 4 + cand) * a.p_stride;
+        const double *tri = a.tri + ((size_t)pair * 4 + cand) * a.p_stride * 3;
+        double *op = a.out_points + (size_t)pair * a.p_stride * 3;
+        uint64_t *oi = a.out_index + (size_t)pair * a.p_stride;
+        const mvs_match *mt = a.matches ? a.matches + (size_t)pair * a.p_stride : nullptr;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        unsigned long long ssd = 0ull;
+        for (int i0 = 0; i0 < n; i0 += FIN2_THREADS) {
+            const int i = i0 + threadIdx.x;
+            const bool f = (i < n) && valid[i];
+            const unsigned bal = __ballot_sync(0xFFFFFFFFu, f);
+            if (lane == 0) s_warp[warp] = __popc(bal);
+            __syncthreads();
+            int off = s_base;
+            for (int w = 0; w < warp; ++w) off += s_warp[w];
+            if (f) {
+                const int r = off + __popc(bal & ((1u << lane) - 1u));
+                op[3 * (size_t)r] = tri[3 * (size_t)i]; op[3 * (size_t)r + 1] = tri[3 * (size_t)i + 1];
+                op[3 * (size_t)r + 2] = tri[3 * (size_t)i + 2];
+                oi[r] = (uint64_t)i;
+                if (mt) { const unsigned long long d = (unsigned long long)mt[i].distance; ssd += d * d; }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int tot = 0;
+                for (int w = 0; w < FIN2_THREADS / 32; ++w) tot += s_warp[w];
+                s_base += tot;
+            }
+            __syncthreads();
+        }
+        if (ssd) atomicAdd(&s_ssd, ssd);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && res) {
+        res->status = st->status;
+        res->n_matches = st->n_matches;
+        res->n_inliers = st->n_inliers;
+        res->best_hypothesis = st->best_h;
+        res->n_points = st->n_points;
+        res->candidate = st->candidate;
+        res->residual = st->residual;
+        const bool have_model = (st->status == MVS_OK || st->status == MVS_E_TOO_FEW_INLIERS ||
+                                 st->status == MVS_E_NO_CHEIRALITY || st->status == MVS_E_NO_MODEL);
+        for (int i = 0; i < 9; ++i) {
+            res->F[i] = have_model ? st->F[i] : 0.0;
+            res->E[i] = (have_model && st->status != MVS_E_NO_MODEL) ? st->E[i] : 0.0;
+            res->R1to2[i] = 0.0; res->R2in1[i] = 0.0;
+        }
+        for (int i = 0; i < 3; ++i) { res->t1to2[i] = 0.0; res->t2in1[i] = 0.0; }
+        res->match_inlier_ssd = 0;
+        if (cand >= 0) {
+            double R[9], t[3], Rr[9], Ri[9], ti[3];
+            for (int i = 0; i < 9; ++i) R[i] = st->Rc[cand >> 1][i];
+            for (int i = 0; i < 3; ++i) t[i] = (cand & 1) ? -st->tc[i] : st->tc[i];
+            so3_rectify(R, Rr);
+            se3_inverse(Rr, t, Ri, ti);
+            for (int i = 0; i < 9; ++i) { res->R1to2[i] = R[i]; res->R2in1[i] = Ri[i]; }
+            for (int i = 0; i < 3; ++i) { res->t1to2[i] = t[i]; res->t2in1[i] = ti[i]; }
+            res->match_inlier_ssd = s_ssd;
+        }
+    }
+}
+
+void launch_triangulate(const TriArgs &a, int max_points, int n_pairs, cudaStream_t s)
+{
+    dim3 grid(max_points > 0 ? (max_points + TRI_THREADS - 1) / TRI_THREADS : 1, a.n_cand, n_pairs);
+    triangulate_kernel<<<grid, TRI_THREADS, 0, s>>>(a);
+}
+
+void launch_finish(const FinishArgs &a, int n_pairs, cudaStream_t s)
+{
+    finish_kernel<<<n_pairs, FIN2_THREADS, 0, s>>>(a);
+}
+
+}  // namespace mvs

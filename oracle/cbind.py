@@ -180,14 +180,14 @@ def _result_dict(r):
     return d
 
 
-def sfm_solve(xy1, xy2, K, samples=None, H=1, seed=0, pair_id=0, mode=SCORE_ALGEBRAIC):
+def sfm_solve(xy1, xy2, K, samples=None, H=1, seed=0, pair_id=0, mode=SCORE_ALGEBRAIC, max_error_sq=0.0):
     xy1 = _f64(xy1); xy2 = _f64(xy2); n = xy1.shape[0]
     if samples is not None:
         samples = np.ascontiguousarray(samples, np.uint32); H = samples.shape[0]
     res = PairResult(); mask = np.zeros(max(n, 1), np.uint8)
     pts = np.empty((max(n, 1), 3)); idx = np.empty(max(n, 1), np.uint64)
     lib().orc_sfm_solve(_p(xy1), _p(xy2), n, _p(_f64(K)), _p(samples), H, C.c_uint64(seed),
-                        C.c_uint64(pair_id), mode, C.byref(res), _p(mask), _p(pts), _p(idx))
+                        C.c_uint64(pair_id), mode, C.c_double(max_error_sq), C.byref(res), _p(mask), _p(pts), _p(idx))
     d = _result_dict(res)
     d["mask"] = mask[:n]; d["points"] = pts[:res.n_points].copy(); d["indexes"] = idx[:res.n_points].copy()
     return d
@@ -202,7 +202,7 @@ def sfm_triangulate(xy1, xy2, K, R1, t1, R2, t2):
 
 
 def image_pair(desc1, kp1, desc2, kp2, K, ratio=0.7, max_dist=-1.0, cross_check=False, H=1, seed=0,
-               pair_id=0, mode=SCORE_ALGEBRAIC):
+               pair_id=0, mode=SCORE_ALGEBRAIC, max_error_sq=0.0):
     desc1 = np.ascontiguousarray(desc1, np.uint8); desc2 = np.ascontiguousarray(desc2, np.uint8)
     kp1 = np.ascontiguousarray(kp1, np.float32); kp2 = np.ascontiguousarray(kp2, np.float32)
     n1, n2 = desc1.shape[0], desc2.shape[0]
@@ -211,7 +211,7 @@ def image_pair(desc1, kp1, desc2, kp2, K, ratio=0.7, max_dist=-1.0, cross_check=
     pts = np.empty((cap, 3)); idx = np.empty(cap, np.uint64)
     lib().orc_image_pair(_p(desc1), _p(kp1), n1, _p(desc2), _p(kp2), n2, desc1.shape[1], _p(_f64(K)),
                          C.c_double(ratio), C.c_double(max_dist), int(cross_check), H, C.c_uint64(seed),
-                         C.c_uint64(pair_id), mode, C.byref(res), _p(matches), _p(mask), _p(pts), _p(idx))
+                         C.c_uint64(pair_id), mode, C.c_double(max_error_sq), C.byref(res), _p(matches), _p(mask), _p(pts), _p(idx))
     d = _result_dict(res)
     d["matches"] = matches[:res.n_matches].copy(); d["mask"] = mask[:res.n_matches].copy()
     d["points"] = pts[:res.n_points].copy(); d["indexes"] = idx[:res.n_points].copy()
@@ -219,7 +219,7 @@ def image_pair(desc1, kp1, desc2, kp2, K, ratio=0.7, max_dist=-1.0, cross_check=
 
 
 def pair_batch(descs, kps, pairs, K, ratio=0.7, max_dist=-1.0, cross_check=False, H=1, seed=0,
-               mode=SCORE_ALGEBRAIC, threads=0):
+               mode=SCORE_ALGEBRAIC, threads=0, max_error_sq=0.0):
     descs = [np.ascontiguousarray(d, np.uint8) for d in descs]
     kps = [np.ascontiguousarray(k, np.float32) for k in kps]
     nf = len(descs)
@@ -230,7 +230,7 @@ def pair_batch(descs, kps, pairs, K, ratio=0.7, max_dist=-1.0, cross_check=False
     res = (PairResult * npairs)()
     lib().orc_pair_batch(dptr, kptr, _p(counts), nf, _p(pairs), npairs, descs[0].shape[1], _p(_f64(K)),
                          C.c_double(ratio), C.c_double(max_dist), int(cross_check), H, C.c_uint64(seed), mode,
-                         threads, res)
+                         C.c_double(max_error_sq), threads, res)
     return [_result_dict(r) for r in res]
 
 

@@ -661,7 +661,7 @@ int orc_recover_pose_and_points(const double E[9], const double *p1, const doubl
 
 /* sfm_solve, sfm-solve.cpp:285-368 (own-branch find_essential_matrix :64-90) */
 int orc_sfm_solve(const double *xy1, const double *xy2, int n, const double K[9],
-                  const uint32_t *samples, int H, uint64_t seed, uint64_t pair_id, int score_mode,
+                  const uint32_t *samples, int H, uint64_t seed, uint64_t pair_id, int score_mode, double max_error_sq_override,
                   orc_pair_result *res, uint8_t *mask_out, double *pts, uint64_t *idx)
 {
     memset(res, 0, sizeof(*res));
@@ -679,6 +679,7 @@ int orc_sfm_solve(const double *xy1, const double *xy2, int n, const double K[9]
         samples = tab;
     }
     double max_error_sq = ORC_MAX_ERROR_SQ / K[0] / K[4]; /* :311 */
+    if (max_error_sq_override > 0) max_error_sq = max_error_sq_override;
     int st = orc_ransac_fundamental(p1, p2, n, samples, H, max_error_sq, score_mode, res->F, mask,
                                     &res->n_inliers, &res->residual, &res->best_hypothesis, NULL, NULL);
     if (st == ORC_OK) {
@@ -723,7 +724,7 @@ int orc_sfm_triangulate(const double *xy1, const double *xy2, int n, const doubl
 int orc_image_pair(const uint8_t *desc1, const float *kp1, int n1,
                    const uint8_t *desc2, const float *kp2, int n2, int desc_bytes,
                    const double K[9], double ratio, double max_dist, int cross_check,
-                   int H, uint64_t seed, uint64_t pair_id, int score_mode,
+                   int H, uint64_t seed, uint64_t pair_id, int score_mode, double max_error_sq_override,
                    orc_pair_result *res, orc_match *matches, uint8_t *mask, double *pts, uint64_t *idx)
 {
     memset(res, 0, sizeof(*res));
@@ -737,7 +738,7 @@ int orc_image_pair(const uint8_t *desc1, const float *kp1, int n1,
         xy1[2 * i] = (double)kp1[2 * matches[i].train]; xy1[2 * i + 1] = (double)kp1[2 * matches[i].train + 1];
         xy2[2 * i] = (double)kp2[2 * matches[i].query]; xy2[2 * i + 1] = (double)kp2[2 * matches[i].query + 1];
     }
-    int st = orc_sfm_solve(xy1, xy2, m, K, NULL, H, seed, pair_id, score_mode, res, mask, pts, idx);
+    int st = orc_sfm_solve(xy1, xy2, m, K, NULL, H, seed, pair_id, score_mode, max_error_sq_override, res, mask, pts, idx);
     res->n_matches = m;
     free(xy1); free(xy2);
     return st;
@@ -755,7 +756,7 @@ int orc_max_threads(void)
 int orc_pair_batch(const uint8_t *const *desc, const float *const *kp, const int32_t *counts, int n_frames,
                    const int32_t *pairs, int n_pairs, int desc_bytes,
                    const double K[9], double ratio, double max_dist, int cross_check,
-                   int H, uint64_t seed, int score_mode, int threads, orc_pair_result *res)
+                   int H, uint64_t seed, int score_mode, double max_error_sq_override, int threads, orc_pair_result *res)
 {
     (void)n_frames;
 #ifdef _OPENMP
@@ -770,7 +771,7 @@ int orc_pair_batch(const uint8_t *const *desc, const float *const *kp, const int
         double *pts = (double *)malloc(sizeof(double) * 3 * (size_t)cap);
         uint64_t *idx = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)cap);
         orc_image_pair(desc[a], kp[a], counts[a], desc[b], kp[b], counts[b], desc_bytes, K, ratio, max_dist,
-                       cross_check, H, seed, (uint64_t)p, score_mode, &res[p], mt, mask, pts, idx);
+                       cross_check, H, seed, (uint64_t)p, score_mode, max_error_sq_override, &res[p], mt, mask, pts, idx);
         free(mt); free(mask); free(pts); free(idx);
     }
     return ORC_OK;

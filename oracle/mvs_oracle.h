@@ -112,7 +112,7 @@ typedef struct {
 
 /* sfm_solve (source/vision/sfm-solve.cpp:285-368). samples==NULL -> H rows from orc_sample_table(seed,pair_id). */
 int orc_sfm_solve(const double *xy1, const double *xy2, int n, const double K[9],
-                  const uint32_t *samples, int H, uint64_t seed, uint64_t pair_id, int score_mode,
+                  const uint32_t *samples, int H, uint64_t seed, uint64_t pair_id, int score_mode, double max_error_sq_override,
                   orc_pair_result *res, uint8_t *mask /*[n] or NULL*/,
                   double *pts /*[n][3]*/, uint64_t *idx /*[n]*/);
 /* sfm_triangulate (source/vision/sfm-solve.cpp:370-394) */
@@ -125,7 +125,7 @@ int orc_sfm_triangulate(const double *xy1, const double *xy2, int n, const doubl
 int orc_image_pair(const uint8_t *desc1, const float *kp1, int n1,
                    const uint8_t *desc2, const float *kp2, int n2, int desc_bytes,
                    const double K[9], double ratio, double max_dist, int cross_check,
-                   int H, uint64_t seed, uint64_t pair_id, int score_mode,
+                   int H, uint64_t seed, uint64_t pair_id, int score_mode, double max_error_sq_override,
                    orc_pair_result *res, orc_match *matches /*cap n2*/, uint8_t *mask /*cap n2*/,
                    double *pts /*cap n2*3*/, uint64_t *idx /*cap n2*/);
 
@@ -133,7 +133,7 @@ int orc_image_pair(const uint8_t *desc1, const float *kp1, int n1,
 int orc_pair_batch(const uint8_t *const *desc, const float *const *kp, const int32_t *counts, int n_frames,
                    const int32_t *pairs /*[n_pairs][2] = (base, pair)*/, int n_pairs, int desc_bytes,
                    const double K[9], double ratio, double max_dist, int cross_check,
-                   int H, uint64_t seed, int score_mode, int threads, orc_pair_result *res /*[n_pairs]*/);
+                   int H, uint64_t seed, int score_mode, double max_error_sq_override, int threads, orc_pair_result *res /*[n_pairs]*/);
 
 int orc_max_threads(void);
 

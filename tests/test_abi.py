@@ -1,0 +1,64 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol that
+include/mvslam_b200.h declares, struct layouts agree, host-only entry points work, and the product
+refuses to run without a CUDA device (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import mvslam_b200 as mvs
+from oracle import cbind as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "mvslam_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mvs_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = mvs.load_library()
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/mvslam_b200.h but not exported"
+    assert L.mvs_abi_version() == 1
+
+
+def test_struct_layouts():
+    assert ctypes.sizeof(mvs.PairResult) == mvs.RESULT_DTYPE.itemsize == 376
+    assert mvs.MATCH_DTYPE.itemsize == 12
+    assert ctypes.sizeof(mvs.RansacParams) == 40 and ctypes.sizeof(mvs.MatchParams) == 24
+
+
+def test_host_sample_table_matches_oracle():
+    for seed, pid, n, H in [(0, 0, 8, 16), (1, 5, 91, 1024), (2**63, 2**40, 8192, 300)]:
+        assert np.array_equal(mvs.sample_table(seed, pid, n, H), orc.sample_table(seed, pid, n, H))
+
+
+def test_status_strings():
+    L = mvs.load_library()
+    assert L.mvs_status_string(0) == b"ok"
+    assert b"CUDA" in L.mvs_status_string(mvs.E_CUDA)
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    with pytest.raises(mvs.MvsError) as e:
+        mvs.Context(0)
+    assert e.value.status == mvs.E_CUDA
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "mvslam_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")) or f == "Makefile":
+                txt = open(os.path.join(dp, f)).read()
+                assert "oracle" not in txt.replace("the oracle", "").replace("CPU oracle", "").replace("oracle's", ""), f

@@ -1,0 +1,354 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (libmvslam_b200.so via ctypes),
+against the CPU oracle (oracle/mvs_oracle.c) on the same seeded inputs, against the committed golden
+fixtures, and — at the BASELINE sizes — through size-independent properties.
+
+Bars: Hamming matches bit-exact (indices, distances, order); identical inlier sets / counts for
+identical sample tables; E within 1e-5 (Frobenius-normalised, sign-free), pose within 1e-6,
+points within 1e-4 relative (the north-star tolerances), and much tighter where stated.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import mvslam_b200 as mvs
+from mvslam_b200 import synth
+from oracle import cbind as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = mvs.Context(0)
+    yield c
+    c.close()
+
+
+def same_up_to_scale(Fa, Fb, atol):
+    Fa = Fa / np.linalg.norm(Fa); Fb = Fb / np.linalg.norm(Fb)
+    return min(np.abs(Fa - Fb).max(), np.abs(Fa + Fb).max()) <= atol
+
+
+def as_mvs(m):
+    return m.view(mvs.MATCH_DTYPE)
+
+
+def general_scene(n, seed, noise=0.0, outl=0.0):
+    r = np.random.default_rng(seed)
+    K = synth.K_S8K
+    X = np.stack([r.uniform(-4, 4, n), r.uniform(-4, 4, n), r.uniform(4, 12, n)], 1)
+    rv = r.normal(size=3); rv *= 0.1 / np.linalg.norm(rv)
+    R = synth._rodrigues(rv); t = r.normal(size=3); t *= 0.5 / np.linalg.norm(t)
+    x1, _ = synth._project(K, np.eye(3), np.zeros(3), X)
+    x2, _ = synth._project(K, R, t, X)
+    x1 = x1 + r.normal(size=x1.shape) * noise; x2 = x2 + r.normal(size=x2.shape) * noise
+    no = int(outl * n)
+    x2[:no] = r.uniform(0, 1, (no, 2)) * [1280, 720]
+    p = r.permutation(n)
+    return K, x1[p], x2[p]
+
+
+# ------------------------------------------------------------------------------------------ matcher
+@pytest.mark.parametrize("nq,nt,rand_bytes", [(1, 2, 32), (7, 3, 32), (257, 300, 32), (500, 411, 3), (1759, 1748, 32),
+                                              (3000, 2500, 2), (256, 256, 32), (513, 8192, 32)])
+def test_knn2_hamming_bit_exact(ctx, nq, nt, rand_bytes):
+    rng = np.random.default_rng(nq * 7919 + nt)
+    q = np.zeros((nq, 32), np.uint8); t = np.zeros((nt, 32), np.uint8)
+    q[:, :rand_bytes] = rng.integers(0, 256, (nq, rand_bytes)); t[:, :rand_bytes] = rng.integers(0, 256, (nt, rand_bytes))
+    t[nt // 2] = t[0]
+    ig, dg = ctx.knn2_hamming(q, t)
+    io, do = orc.knn2_hamming(q, t)
+    assert np.array_equal(ig, io) and np.array_equal(dg, do)
+
+
+@pytest.mark.parametrize("max_dist,cross", [(-1.0, False), (10.0, False), (30.0, False), (-1.0, True), (64.0, True)])
+def test_match_hamming_vs_oracle(ctx, max_dist, cross):
+    d1, _, d2, _, _ = synth.synthetic_pair(11, n=3000)
+    g = ctx.match_hamming(d2, d1, 0.7, max_dist, cross)
+    o = orc.match_hamming(d2, d1, 0.7, max_dist, cross)
+    assert len(g) == len(o) > 0
+    assert np.array_equal(g, as_mvs(o))
+
+
+def test_match_hamming_golden_tsukuba(ctx, tsukuba, tsukuba_golden):
+    for a in range(1, 5):
+        for md in (10, 30, -1):
+            m = ctx.match_hamming(tsukuba[f"desc{a + 1}"], tsukuba[f"desc{a}"], 0.7, float(md))
+            tag = f"p{a}{a + 1}_md{md}_"
+            assert np.array_equal(m["query"], tsukuba_golden[tag + "q"])
+            assert np.array_equal(m["train"], tsukuba_golden[tag + "t"])
+            assert np.array_equal(m["distance"], tsukuba_golden[tag + "d"])
+
+
+def test_match_edge_cases(ctx):
+    rng = np.random.default_rng(0)
+    q = rng.integers(0, 256, (5, 32), dtype=np.uint8)
+    with pytest.raises(mvs.MvsError) as e:          # knnMatch(k=2) with a single train row: reference UB -> BAD_ARG
+        ctx.match_hamming(q, q[:1])
+    assert e.value.status == mvs.E_BAD_ARG
+    with pytest.raises(mvs.MvsError):
+        ctx.match_hamming(np.zeros((4, 16), np.uint8), np.zeros((4, 16), np.uint8))   # only 256-bit descriptors
+    m = ctx.match_hamming(q, np.repeat(q[:1], 4, axis=0))    # all train identical: ratio test rejects everything
+    assert len(m) == 0
+    m = ctx.match_hamming(q, q)                               # self match: d1 = 0 < 0.7 * d2
+    assert np.array_equal(m["query"], m["train"]) and len(m) == 5 and np.all(m["distance"] == 0)
+
+
+def test_match_full_size_properties(ctx):
+    """BASELINE config 3 size (8192 x 8192 x 256 bit): bit-exact vs oracle on a query subset, plus
+    idempotence and agreement of first neighbours with the planted permutation."""
+    d1, _, d2, _, tr = synth.synthetic_pair(0, n=8192)
+    ig, dg = ctx.knn2_hamming(d2, d1)
+    sub = np.random.default_rng(1).choice(8192, 256, replace=False)
+    io, do = orc.knn2_hamming(d2[sub], d1)
+    assert np.array_equal(ig[sub], io) and np.array_equal(dg[sub], do)
+    ig2, dg2 = ctx.knn2_hamming(d2, d1)
+    assert np.array_equal(ig, ig2) and np.array_equal(dg, dg2)
+    planted = tr["inlier"][tr["perm"]]
+    assert (ig[planted, 0] == tr["perm"][planted]).mean() > 0.999
+    assert np.all(dg[:, 0] <= dg[:, 1])
+
+
+# ------------------------------------------------------------------------------------------ 8-point / RANSAC
+def test_find_fundamental_matrix_vs_oracle(ctx):
+    K, x1, x2 = general_scene(400, 3, noise=0.3)
+    p1 = orc.normalize_points(K, x1); p2 = orc.normalize_points(K, x2)
+    tab = orc.sample_table(9, 1, 400, 200)
+    Fg = ctx.find_fundamental_matrix(p1[tab], p2[tab])
+    exact = 0
+    for h in range(200):
+        Fo = orc.find_fundamental_matrix(p1[tab[h]], p2[tab[h]])
+        assert same_up_to_scale(Fg[h], Fo, 1e-9)
+        exact += np.array_equal(Fg[h], Fo)
+    print(f"bit-identical F: {exact}/200")
+    assert exact >= 100      # same operation order on both sides: most hypotheses agree to the last bit
+
+
+@pytest.mark.parametrize("mode", [mvs.SCORE_ALGEBRAIC, mvs.SCORE_SAMPSON])
+@pytest.mark.parametrize("n,H,noise,outl,thr", [(300, 64, 0.0, 0.3, 1e-7), (1000, 513, 0.3, 0.3, 1e-3),
+                                                (1500, 300, 0.5, 0.5, 1e-6), (8, 1, 0.0, 0.0, 1e-7)])
+def test_ransac_identical_inlier_sets(ctx, mode, n, H, noise, outl, thr):
+    K, x1, x2 = general_scene(n, n + H, noise, outl)
+    p1 = orc.normalize_points(K, x1); p2 = orc.normalize_points(K, x2)
+    tab = orc.sample_table(4, 2, n, H)
+    g = ctx.ransac_fundamental(p1, p2, samples=tab, max_error_sq=thr, mode=mode, want_all=True)
+    o = orc.ransac_fundamental(p1, p2, tab, thr, mode, want_all=True)
+    assert g["status"] == o["status"]
+    assert np.array_equal(g["all_counts"], o["all_counts"])      # every hypothesis, not only the winner
+    if noise > 0:                                                # noise-free: residual ties are pure round-off
+        assert g["best_h"] == o["best_h"]
+        assert np.array_equal(g["mask"], o["mask"])
+        assert same_up_to_scale(g["F"], o["F"], 1e-9)
+        assert np.isclose(g["residual"], o["residual"], rtol=1e-9)
+    assert g["count"] == o["count"]
+
+
+def test_ransac_general_z_points(ctx):
+    """FundamentalMatrixEstimatorRANSAC::compute takes arbitrary homogeneous 3-vectors."""
+    K, x1, x2 = general_scene(200, 77, 0.2, 0.2)
+    p1 = orc.normalize_points(K, x1); p2 = orc.normalize_points(K, x2)
+    s = np.random.default_rng(0).uniform(0.5, 2.0, (200, 1))
+    p1 = p1 * s; p2 = p2 * s[::-1]
+    tab = orc.sample_table(1, 1, 200, 50)
+    g = ctx.ransac_fundamental(p1, p2, samples=tab, max_error_sq=1e-3, want_all=True)
+    o = orc.ransac_fundamental(p1, p2, tab, 1e-3, 0, want_all=True)
+    assert np.array_equal(g["all_counts"], o["all_counts"]) and g["best_h"] == o["best_h"]
+    assert np.array_equal(g["mask"], o["mask"])
+
+
+def test_ransac_seeded_table_on_device_equals_host_table(ctx):
+    K, x1, x2 = general_scene(500, 5, 0.3, 0.3)
+    p1 = orc.normalize_points(K, x1); p2 = orc.normalize_points(K, x2)
+    a = ctx.ransac_fundamental(p1, p2, samples=None, H=128, seed=99, max_error_sq=1e-3, want_all=True)
+    b = ctx.ransac_fundamental(p1, p2, samples=mvs.sample_table(99, 0, 500, 128), max_error_sq=1e-3, want_all=True)
+    assert np.array_equal(a["all_counts"], b["all_counts"]) and np.array_equal(a["F"], b["F"])
+
+
+# ------------------------------------------------------------------------------------------ sfm_solve / triangulate
+def check_solution(g, o, pose_tol=1e-9, strict=True):
+    assert g["status"] == o["status"]
+    if o["status"] != orc.OK:
+        return
+    assert g["n_inliers"] == o["n_inliers"] and g["n_points"] == o["n_points"]
+    if strict:
+        assert g["best_hypothesis"] == o["best_hypothesis"] and g["candidate"] == o["candidate"]
+        assert np.array_equal(g["mask"], o["mask"]) and np.array_equal(g["indexes"], o["indexes"])
+        assert same_up_to_scale(g["E"], o["E"], 1e-9)
+        assert np.allclose(g["points"], o["points"], rtol=1e-7, atol=1e-9)
+    assert np.allclose(g["R2in1"], o["R2in1"], atol=pose_tol) and np.allclose(g["t2in1"], o["t2in1"], atol=pose_tol)
+
+
+@pytest.mark.parametrize("mode", [mvs.SCORE_ALGEBRAIC, mvs.SCORE_SAMPSON])
+def test_sfm_solve_vs_oracle_and_golden(ctx, synthetic_golden, mode):
+    s = synthetic_golden
+    tagm = "alg_" if mode == mvs.SCORE_ALGEBRAIC else "smp_"
+    for c in range(4):
+        xy1, xy2, K, tab = s[f"s{c}_xy1"], s[f"s{c}_xy2"], s[f"s{c}_K"], s[f"s{c}_tab"]
+        g = ctx.sfm_solve(xy1, xy2, K, samples=tab, mode=mode)
+        o = orc.sfm_solve(xy1, xy2, K, samples=tab, mode=mode)
+        check_solution(g, o, strict=(c >= 2))
+        t = f"s{c}_{tagm}"
+        assert (g["status"] == mvs.OK) == bool(s[t + "ok"])
+        if g["status"] == mvs.OK:      # Oracle-A (cv2.SVDecomp) golden: north-star tolerances
+            assert g["n_inliers"] == int(s[t + "n_inliers"])
+            assert np.allclose(g["R2in1"], s[t + "R2in1"], atol=1e-6)
+            if c >= 2:
+                assert same_up_to_scale(g["E"], s[t + "E"], 1e-5)
+                assert np.allclose(g["points"], s[t + "points"], rtol=1e-4, atol=1e-6)
+
+
+def test_sfm_solve_reference_single_sample_lshape(ctx, synthetic_golden):
+    """H=1 == the reference's behaviour (sample {0..7}); L-shape rig of test/test-sfm.cpp."""
+    s = synthetic_golden
+    g = ctx.sfm_solve(s["lshape_xy1"], s["lshape_xy2"], np.eye(3))
+    assert g["status"] == mvs.OK and g["n_points"] == 8
+    assert np.allclose(g["t2in1"], [1, 0, 0], atol=1e-9) and np.allclose(g["R2in1"], np.eye(3), atol=1e-9)
+    assert np.allclose(g["points"], s["lshape_P"], atol=1e-9)
+    check_solution(g, orc.sfm_solve(s["lshape_xy1"], s["lshape_xy2"], np.eye(3)), strict=False)
+
+
+def test_sfm_solve_tsukuba_golden(ctx, tsukuba, tsukuba_golden):
+    K = tsukuba["K"]; gl = tsukuba_golden
+    for a in range(1, 5):
+        for md, H in ((10, 1), (30, 1), (-1, 1)):
+            tag = f"p{a}{a + 1}_md{md}_"
+            xy1 = tsukuba[f"kp{a}"][gl[tag + "t"]]; xy2 = tsukuba[f"kp{a + 1}"][gl[tag + "q"]]
+            g = ctx.sfm_solve(xy1, xy2, K)
+            o = orc.sfm_solve(xy1, xy2, K)
+            check_solution(g, o, pose_tol=1e-7)
+            # reference expectation (test/test-image-pair.cpp:40-45): pose ~ (I,(1,0,0)) to 1e-3
+            assert np.allclose(g["t2in1"], [1, 0, 0], atol=1e-3) and np.allclose(g["R2in1"], np.eye(3), atol=1e-3)
+        tag = f"p{a}{a + 1}_md30_"
+        xy1 = tsukuba[f"kp{a}"][gl[tag + "t"]]; xy2 = tsukuba[f"kp{a + 1}"][gl[tag + "q"]]
+        g = ctx.sfm_solve(xy1, xy2, K, samples=gl[tag + "tab256"])
+        assert g["n_inliers"] == int(gl[tag + "h256_n_inliers"])
+        assert np.allclose(g["t2in1"], gl[tag + "h256_t2in1"], atol=1e-6)
+
+
+def test_sfm_triangulate_cube_known_answer(ctx, synthetic_golden):
+    """test/test-sfm.cpp:92-155"""
+    s = synthetic_golden
+    pts, idx = ctx.sfm_triangulate(s["cube_xy1"], s["cube_xy2"], np.eye(3), np.eye(3), np.zeros(3), np.eye(3),
+                                   np.array([1.0, 0, 0]))
+    assert np.array_equal(idx, np.arange(8)) and np.allclose(pts, s["cube_P"], atol=1e-3)
+    po, io = orc.sfm_triangulate(s["cube_xy1"], s["cube_xy2"], np.eye(3), np.eye(3), np.zeros(3), np.eye(3),
+                                 np.array([1.0, 0, 0]))
+    assert np.allclose(pts, po, atol=1e-12)
+
+
+def test_sfm_triangulate_general_and_behind_camera(ctx):
+    K, x1, x2 = general_scene(700, 21, 0.2, 0.3)
+    R2 = synth._rodrigues(np.array([0.02, -0.05, 0.01])); t2 = np.array([0.4, 0.1, -0.2])
+    pg, ig = ctx.sfm_triangulate(x1, x2, K, np.eye(3), np.zeros(3), R2, t2)
+    po, io = orc.sfm_triangulate(x1, x2, K, np.eye(3), np.zeros(3), R2, t2)
+    assert 0 < len(io) < 700 and np.array_equal(ig, io)
+    assert np.allclose(pg, po, rtol=1e-9, atol=1e-10)
+
+
+def test_failure_codes(ctx):
+    xy = np.random.default_rng(0).uniform(0, 100, (5, 2))
+    assert ctx.sfm_solve(xy, xy, np.eye(3))["status"] == mvs.E_TOO_FEW_POINTS
+    r = np.random.default_rng(1)
+    xa = r.uniform(0, 1000, (60, 2)); xb = r.uniform(0, 1000, (60, 2))
+    g = ctx.sfm_solve(xa, xb, synth.K_S8K, H=16, seed=3)
+    o = orc.sfm_solve(xa, xb, synth.K_S8K, H=16, seed=3)
+    assert g["status"] == o["status"] == mvs.E_TOO_FEW_INLIERS
+    assert g["points"].shape[0] == 0
+
+
+# ------------------------------------------------------------------------------------------ batched pairs
+def test_pair_batch_tsukuba_all_pairs(ctx, tsukuba):
+    """ImagePair ctor + reconstruct over every ordered pair of the 5 bundled frames, VO default max_dist=10."""
+    descs = [tsukuba[f"desc{i}"] for i in range(1, 6)]; kps = [tsukuba[f"kp{i}"] for i in range(1, 6)]
+    K = tsukuba["K"]
+    pairs = [(a, b) for a in range(5) for b in range(5) if a != b]
+    ctx.frames_upload(descs, kps)
+    for md, H in ((10.0, 1), (30.0, 64)):
+        res, det = ctx.pair_batch(pairs, K, max_dist=md, H=H, seed=7)
+        for i, (a, b) in enumerate(pairs):
+            o = orc.image_pair(descs[a], kps[a], descs[b], kps[b], K, max_dist=md, H=H, seed=7, pair_id=i)
+            r = res[i]; m = r["n_matches"]
+            assert m == o["n_matches"] and np.array_equal(det["matches"][i][:m], as_mvs(o["matches"]))
+            assert r["status"] == o["status"]
+            if o["status"] != orc.OK:
+                continue
+            assert r["n_inliers"] == o["n_inliers"] and r["best_hypothesis"] == o["best_hypothesis"]
+            assert np.array_equal(det["mask"][i][:m], o["mask"])
+            n = r["n_points"]
+            assert n == o["n_points"] and np.array_equal(det["indexes"][i][:n], o["indexes"])
+            assert np.allclose(det["points"][i][:n], o["points"], rtol=1e-6, atol=1e-8)
+            assert np.allclose(r["R2in1"], o["R2in1"], atol=1e-7) and np.allclose(r["t2in1"], o["t2in1"], atol=1e-7)
+            ssd = int((o["matches"]["distance"][o["indexes"].astype(int)].astype(np.int64) ** 2).sum())
+            assert int(r["match_inlier_ssd"]) == ssd
+
+
+@pytest.mark.parametrize("mode,thr", [(mvs.SCORE_SAMPSON, 0.0), (mvs.SCORE_ALGEBRAIC, 1e-3)])
+def test_pair_batch_synthetic_s8k_shape(ctx, mode, thr):
+    """Config-3-shaped pairs (general motion, 0.5 px noise, outliers), ragged keypoint counts in one batch,
+    sharding-invariant sampling through pair_id_base."""
+    sizes = [2048, 1500, 2048, 777]
+    frames_d, frames_k, pairs = [], [], []
+    for p, n in enumerate(sizes):
+        d1, k1, d2, k2, _ = synth.synthetic_pair(100 + p, n=n)
+        frames_d += [d1, d2]; frames_k += [k1, k2]; pairs.append((2 * p, 2 * p + 1))
+    ctx.frames_upload(frames_d, frames_k)
+    res, det = ctx.pair_batch(pairs, synth.K_S8K, H=256, seed=5, mode=mode, max_error_sq=thr)
+    for i, (a, b) in enumerate(pairs):
+        o = orc.image_pair(frames_d[a], frames_k[a], frames_d[b], frames_k[b], synth.K_S8K, H=256, seed=5, pair_id=i,
+                           mode=mode, max_error_sq=thr)
+        r = res[i]; m = r["n_matches"]
+        assert r["status"] == o["status"] == mvs.OK
+        assert m == o["n_matches"] and np.array_equal(det["matches"][i][:m], as_mvs(o["matches"]))
+        assert r["n_inliers"] == o["n_inliers"] and r["best_hypothesis"] == o["best_hypothesis"]
+        assert np.array_equal(det["mask"][i][:m], o["mask"])
+        assert r["n_points"] == o["n_points"]
+        assert same_up_to_scale(r["E"], o["E"], 1e-9)
+        assert np.allclose(r["R2in1"], o["R2in1"], atol=1e-9) and np.allclose(r["t2in1"], o["t2in1"], atol=1e-9)
+        assert np.allclose(det["points"][i][:r["n_points"]], o["points"], rtol=1e-7, atol=1e-9)
+    # the second half of the batch alone, with pair_id_base=2, must reproduce entries 2,3
+    res2, _ = ctx.pair_batch(pairs[2:], synth.K_S8K, H=256, seed=5, mode=mode, max_error_sq=thr, pair_id_base=2)
+    for k in ("n_inliers", "best_hypothesis", "n_points", "R2in1", "t2in1", "F"):
+        assert np.array_equal(res2[k], res[2:][k])
+
+
+def test_pair_batch_full_size_8k_h4096(ctx):
+    """BASELINE config 3 at full size (8192 kpts, H=4096): oracle check of the whole pipeline on one pair."""
+    d1, k1, d2, k2, tr = synth.synthetic_pair(1, n=8192)
+    ctx.frames_upload([d1, d2], [k1, k2])
+    res, det = ctx.pair_batch([(0, 1)], synth.K_S8K, H=4096, seed=1, mode=mvs.SCORE_SAMPSON)
+    r = res[0]
+    o = orc.image_pair(d1, k1, d2, k2, synth.K_S8K, H=4096, seed=1, mode=orc.SCORE_SAMPSON)
+    assert r["status"] == o["status"] == 0 and r["n_matches"] == o["n_matches"]
+    assert r["n_inliers"] == o["n_inliers"] and r["best_hypothesis"] == o["best_hypothesis"]
+    assert np.array_equal(det["mask"][0][:r["n_matches"]], o["mask"]) and r["n_points"] == o["n_points"]
+    assert np.allclose(r["R2in1"], o["R2in1"], atol=1e-9) and np.allclose(r["t2in1"], o["t2in1"], atol=1e-9)
+    # sanity against the planted motion (pose2in1 = (R,t)^-1, |t| = 1)
+    tt = -tr["R"].T @ tr["t"]; tt /= np.linalg.norm(tt)
+    assert np.allclose(r["R2in1"], tr["R"].T, atol=2e-2) and np.allclose(r["t2in1"], tt, atol=0.15)
+
+
+def test_pair_batch_bad_pairs_do_not_abort_batch(ctx):
+    d1, k1, d2, k2, _ = synth.synthetic_pair(5, n=512, noise_px=1e-4)
+    rng = np.random.default_rng(0)
+    junk = rng.integers(0, 256, (300, 32), dtype=np.uint8); junk_k = rng.uniform(0, 700, (300, 2)).astype(np.float32)
+    ctx.frames_upload([d1, d2, junk], [k1, k2, junk_k])
+    res, _ = ctx.pair_batch([(0, 1), (0, 2), (1, 0)], synth.K_S8K, H=32, seed=1, details=False)
+    assert res[0]["status"] == mvs.OK and res[2]["status"] == mvs.OK
+    assert res[1]["status"] in (mvs.E_TOO_FEW_POINTS, mvs.E_TOO_FEW_INLIERS, mvs.E_NO_MODEL)
+    with pytest.raises(mvs.MvsError):
+        ctx.pair_batch([(0, 0)], synth.K_S8K)
+    with pytest.raises(mvs.MvsError):
+        ctx.pair_batch([(0, 9)], synth.K_S8K)
+
+
+def test_profile_and_launch_counters(ctx, tsukuba):
+    descs = [tsukuba[f"desc{i}"] for i in range(1, 3)]; kps = [tsukuba[f"kp{i}"] for i in range(1, 3)]
+    ctx.frames_upload(descs, kps)
+    ctx.profile_enable(True); ctx.profile_read(reset=True)
+    n0 = ctx.kernel_launches()
+    ctx.pair_batch([(0, 1)] * 8, tsukuba["K"], max_dist=10.0, H=64, details=False)
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+    assert ctx.kernel_launches() - n0 == 7
+    assert all(prof[s][1] == 1 and prof[s][0] > 0 for s in mvs.STAGES[:7])
