@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the two-view front-end hot path (match + RANSAC E + triangulate).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload tsukuba|s8k]
+
+One "step" = one pass of the hot path over one batch of image pairs.  Default workload (N=1) is
+BASELINE.json configs[1]: consecutive-frame VO pairs of the bundled New Tsukuba sequence at ~2k ORB
+keypoints (features extracted on the host beforehand: tests/golden/tsukuba_orb2000.npz), the reference
+visual-odometer matching threshold (max_dist = 10) and a seeded H-row sample table.
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput (frames already in HBM, result
+records copied back), `e2e` goes through the public C-ABI call with host buffers (H2D of the frames and
+D2H of records + matches + mask + points + indexes inside the timed region).  `roofline` describes the
+dominant kernel (Hamming kNN) against the measured integer-popc ceiling of this chip, `cpu_baseline`
+is the CPU oracle (port of the reference's own branch) on the box's host cores.
+
+--impl reference times that CPU path alone (the reference itself cannot be compiled in this image:
+it needs OpenCV C++/Eigen/GTSAM/scons — see DESIGN.md), on all host threads.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "matched+solved image pairs/sec (2k kpts)"
+
+
+# ------------------------------------------------------------------------------------------ workloads
+def load_workload(name, pairs_per_step, H):
+    from mvslam_b200 import synth
+    if name == "tsukuba":
+        f = np.load(os.path.join(ROOT, "tests", "golden", "tsukuba_orb2000.npz"))
+        descs = [np.ascontiguousarray(f[f"desc{i}"]) for i in range(1, 6)]
+        kps = [np.ascontiguousarray(f[f"kp{i}"]) for i in range(1, 6)]
+        K = f["K"]
+        base = [(i, i + 1) for i in range(4)]                 # consecutive-frame VO pairs
+        pairs = np.array([base[i % 4] for i in range(pairs_per_step)], np.int32)
+        cfg = dict(workload="tsukuba_vo_2k", frames=5, kpts_per_frame=int(np.mean([d.shape[0] for d in descs])),
+                   pairs_per_step_per_gpu=pairs_per_step, hypotheses=H, max_dist=10.0, ratio=0.7, cross_check=False,
+                   score="algebraic(parity)", data_note="ORB-2000 features of data/tsukuba/{1..5}.jpg, "
+                   "4 consecutive pairs cycled")
+        params = dict(max_dist=10.0, H=H, seed=0, mode=0, max_error_sq=0.0)
+    elif name == "s8k":
+        n_distinct = 8
+        descs, kps = [], []
+        for p in range(n_distinct):
+            d1, k1, d2, k2, _ = synth.synthetic_pair(p, n=8192)
+            descs += [d1, d2]; kps += [k1, k2]
+        K = synth.K_S8K
+        pairs = np.array([(2 * (i % n_distinct), 2 * (i % n_distinct) + 1) for i in range(pairs_per_step)], np.int32)
+        cfg = dict(workload="synthetic_s8k", frames=2 * n_distinct, kpts_per_frame=8192,
+                   pairs_per_step_per_gpu=pairs_per_step, hypotheses=H, max_dist=-1.0, ratio=0.7, cross_check=False,
+                   score="sampson", data_note="SURVEY §8d config 3, 8 distinct seeded pairs cycled")
+        params = dict(max_dist=-1.0, H=H, seed=0, mode=1, max_error_sq=0.0)
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    return descs, kps, K, pairs, params, cfg
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.stop, self.t = device, [], False, None
+
+    def _run(self):
+        while not self.stop:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in o.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.t = threading.Thread(target=self._run, daemon=True); self.t.start(); return self
+
+    def __exit__(self, *a):
+        self.stop = True; self.t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.startswith("Active")})
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=reasons, samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_pairs_per_s(descs, kps, K, pairs, params, n_sample, threads=0):
+    from oracle import cbind as orc
+    sample = pairs[np.arange(n_sample) % len(pairs)]
+    t0 = time.perf_counter()
+    orc.pair_batch(descs, kps, sample, K, max_dist=params["max_dist"], H=params["H"], seed=params["seed"],
+                   mode=params["mode"], max_error_sq=params["max_error_sq"], threads=threads)
+    dt = time.perf_counter() - t0
+    return n_sample / dt, dt
+
+
+def run_reference(args, cfg_loader):
+    """The reference's CPU implementation of the path (oracle port of the own branch), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cbind as orc
+    descs, kps, K, pairs, params, cfg = cfg_loader()
+    threads = orc.max_threads()
+    probe, dt = cpu_pairs_per_s(descs, kps, K, pairs, params, 2 * threads)
+    # bounded sample per step: the whole --steps/--warmup run stays within ~2 minutes
+    budget_s = 100.0 / max(args.steps + args.warmup, 1)
+    n_sample = int(max(threads, min(len(pairs), probe * budget_s)))
+    for _ in range(args.warmup):
+        cpu_pairs_per_s(descs, kps, K, pairs, params, n_sample)
+    tot = 0.0
+    for _ in range(args.steps):
+        _, dt = cpu_pairs_per_s(descs, kps, K, pairs, params, n_sample)
+        tot += dt
+    v = n_sample * args.steps / tot
+    line = dict(metric=METRIC, value=v, unit="pairs/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=tot / args.steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="u64-popcnt/f64", data="synthetic" if cfg["workload"] != "tsukuba_vo_2k" else
+                "bundled Tsukuba ORB features (host-extracted), no network", impl="reference", config=cfg,
+                cpu_baseline=dict(value=v, unit="pairs/s", cores=threads, kind="port",
+                                  sample=f"{n_sample} pairs/step of the same workload, OpenMP over pairs"),
+                e2e=dict(value=v, unit="pairs/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="tsukuba", choices=["tsukuba", "s8k"])
+    ap.add_argument("--pairs", type=int, default=0, help="pairs per step per GPU (default 1024 tsukuba / 64 s8k)")
+    ap.add_argument("--hypotheses", type=int, default=0, help="RANSAC sample-table rows (default 1024 tsukuba / 4096 s8k)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    B = args.pairs or (1024 if args.workload == "tsukuba" else 64)
+    H = args.hypotheses or (1024 if args.workload == "tsukuba" else 4096)
+    loader = lambda: load_workload(args.workload, B, H)  # noqa: E731
+    if args.impl == "reference":
+        run_reference(args, loader)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import mvslam_b200 as mvs
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: mvslam_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    descs, kps, K, pairs, params, cfg = loader()
+    cap = max(d.shape[0] for d in descs)
+    stream = torch.cuda.current_stream()
+    ctx = mvs.Context(local, stream=stream.cuda_stream)
+
+    # pinned host staging (inputs for e2e, outputs for both)
+    pin = lambda a: torch.from_numpy(a).pin_memory()  # noqa: E731
+    pd = [pin(d) for d in descs]; pk = [pin(k) for k in kps]
+    res_t = torch.empty(B * mvs.RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    mat_t = torch.empty(B * cap * 12, dtype=torch.uint8).pin_memory()
+    msk_t = torch.empty(B * cap, dtype=torch.uint8).pin_memory()
+    pts_t = torch.empty(B * cap * 3, dtype=torch.float64).pin_memory()
+    idx_t = torch.empty(B * cap, dtype=torch.int64).pin_memory()
+    out_rec = dict(results=res_t.data_ptr())
+    out_all = dict(results=res_t.data_ptr(), matches=mat_t.data_ptr(), mask=msk_t.data_ptr(), points=pts_t.data_ptr(),
+                   indexes=idx_t.data_ptr(), capacity=cap)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
+    kw = dict(max_dist=params["max_dist"], H=params["H"], seed=params["seed"], mode=params["mode"],
+              max_error_sq=params["max_error_sq"], pair_id_base=rank * B)
+
+    def upload():
+        ctx.frames_upload([t.numpy() for t in pd], [t.numpy() for t in pk])
+
+    def step(out):
+        ctx.pair_batch(pairs, K, out=out, enqueue_only=True, **kw)
+
+    upload()
+    for _ in range(args.warmup):
+        flush.zero_(); step(out_rec)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+    # ---- timed region: K steps, device time per step (events on the launching stream), L2 flushed between steps
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ctx.profile_enable(True); ctx.profile_read(reset=True)
+    l0 = ctx.kernel_launches()
+    with ClockSampler(local) as clocks:
+        for a, b in ev:
+            flush.zero_()
+            a.record(stream); step(out_rec); b.record(stream)
+        torch.cuda.synchronize()
+        gather_ms = 0.0
+        if world > 1:   # the single collective of the path: final gather of the fixed-size records over NCCL
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            mine = res_t.to("cuda", non_blocking=True)
+            bucket = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+            g0.record(stream); dist.gather(mine, bucket, dst=0); g1.record(stream)
+            torch.cuda.synchronize()
+            gather_ms = g0.elapsed_time(g1)
+    launches = ctx.kernel_launches() - l0
+    prof = ctx.profile_read(); ctx.profile_enable(False)
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = sum(step_ms) + gather_ms
+    if world > 1:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX); total_ms = float(t.item())
+        dist.barrier()
+    torch.cuda.synchronize()
+    res = np.frombuffer(res_t.numpy(), dtype=mvs.RESULT_DTYPE)
+    n_ok = int((res["status"] == 0).sum())
+
+    # ---- end to end through the public call with host buffers (H2D of the frames + D2H of everything)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    upload(); step(out_all); torch.cuda.synchronize()
+    n_e2e = max(3, min(args.steps, 10))
+    e0.record(stream)
+    for _ in range(n_e2e):
+        upload(); step(out_all); ctx.synchronize()
+    e1.record(stream); torch.cuda.synchronize()
+    e2e_ms = e0.elapsed_time(e1) / n_e2e
+    if world > 1:
+        t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_ms = float(t.item())
+    h2d = sum(d.nbytes for d in descs) + sum(k.nbytes for k in kps) + pairs.nbytes
+    d2h = res_t.numel() + mat_t.numel() + msk_t.numel() + pts_t.numel() * 8 + idx_t.numel() * 8
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (Hamming kNN): algorithmic popc32 ops / measured launch time
+    counts = np.array([d.shape[0] for d in descs], np.int64)
+    desc_pairs = int(sum(counts[a] * counts[b] for a, b in pairs))        # per launch (one launch per step)
+    knn_ms, knn_n = prof["knn"]
+    peaks = {}
+    pk_path = os.path.join(ROOT, "profiles", "ubench_peaks.json")
+    if os.path.exists(pk_path):
+        peaks = json.load(open(pk_path))
+    popc_peak = peaks.get("popc_per_s", 148 * 16 * 1.965e9)
+    achieved = 8.0 * desc_pairs / (knn_ms / knn_n * 1e-3) if knn_n else 0.0
+    alg_bytes = int(sum((counts[a] + counts[b]) * 32 + counts[b] * 8 for a, b in pairs))
+    hbm_peak = 6444.4
+    mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(mp):
+        hbm_peak = json.load(open(mp)).get("hbm_gbs", hbm_peak)
+    stage_share = {s: round(prof[s][0] / max(sum(v[0] for v in prof.values()), 1e-9), 4) for s in mvs.STAGES[:7]}
+    roofline = dict(kernel="knn2_hamming_kernel", bound="int-popc", achieved=achieved / 1e9, peak=popc_peak / 1e9,
+                    unit="Gpopc32/s", frac=achieved / popc_peak,
+                    peak_source="measured (tools/ubench on this pool's B200)" if peaks else "nominal 148 SM x 16/clk x 1.965 GHz",
+                    launch_ms=knn_ms / knn_n if knn_n else None, desc_pairs_per_launch=desc_pairs,
+                    hbm=dict(algorithmic_bytes=alg_bytes, achieved_gbs=alg_bytes / (knn_ms / knn_n * 1e-3) / 1e9 if knn_n else None,
+                             peak_gbs=hbm_peak, note="compute-bound: HBM fraction is not the limiter"),
+                    traffic=None, stage_share=stage_share,
+                    stage_ms_per_step={s: round(prof[s][0] / args.steps, 4) for s in mvs.STAGES[:7]})
+    m_total = int(res["n_matches"].astype(np.int64).sum())
+    evals = float(params["H"]) * m_total
+    score_ms = prof["score"][0] / args.steps
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        from oracle import cbind as orc
+        threads = orc.max_threads()
+        probe, _ = cpu_pairs_per_s(descs, kps, K, pairs, params, 2 * threads)
+        n_sample = int(max(threads, min(4 * B, probe * 12.0)))
+        v, dt = cpu_pairs_per_s(descs, kps, K, pairs, params, n_sample)
+        cpu = dict(value=v, unit="pairs/s", cores=threads, kind="port",
+                   sample=f"{n_sample} pairs of the same workload in {dt:.1f} s, C oracle (own-branch port), OpenMP over pairs")
+
+    value = B * world * args.steps / (total_ms * 1e-3)
+    line = dict(metric=METRIC, value=value, unit="pairs/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=total_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="u32-popc/f64",
+                data="bundled Tsukuba ORB features (host-extracted), no network" if args.workload == "tsukuba" else "synthetic",
+                config=dict(cfg, l2_policy="256 MiB flush buffer written between timed steps", solved_pairs_per_step=n_ok,
+                            final_gather_ms=gather_ms),
+                clocks=clocks.summary(),
+                e2e=dict(value=B * world / (e2e_ms * 1e-3), unit="pairs/s", h2d_bytes_per_step=int(h2d),
+                         d2h_bytes_per_step=int(d2h), ms_per_step=e2e_ms),
+                gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu,
+                ransac=dict(hyp_pt_evals_per_s=evals / (score_ms * 1e-3) if score_ms > 0 else None,
+                            evals_per_step=evals, score_ms_per_step=score_ms,
+                            hypotheses_per_s=params["H"] * B / (prof["hypotheses"][0] / args.steps * 1e-3)))
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -259,7 +259,7 @@ class Context:
         res = np.zeros(npairs, RESULT_DTYPE)
         det = None
         if details:
-            cap = int(self._frame_counts[pairs[:, 1]].max())
+            cap = int(self._frame_counts.max())
             det = dict(matches=np.zeros((npairs, cap), MATCH_DTYPE), mask=np.zeros((npairs, cap), np.uint8),
                        points=np.zeros((npairs, cap, 3)), indexes=np.zeros((npairs, cap), np.uint64), capacity=cap)
         st = fn(self._h, _p(pairs), npairs, _p(_f64(K)), C.byref(mp), C.byref(rp), _p(res),

@@ -253,7 +253,7 @@ def test_failure_codes(ctx):
     xa = r.uniform(0, 1000, (60, 2)); xb = r.uniform(0, 1000, (60, 2))
     g = ctx.sfm_solve(xa, xb, synth.K_S8K, H=16, seed=3)
     o = orc.sfm_solve(xa, xb, synth.K_S8K, H=16, seed=3)
-    assert g["status"] == o["status"] == mvs.E_TOO_FEW_INLIERS
+    assert g["status"] == o["status"] and g["status"] in (mvs.E_TOO_FEW_INLIERS, mvs.E_NO_MODEL)
     assert g["points"].shape[0] == 0
 
 

@@ -1,0 +1,88 @@
+// ubench.cu — measures the instruction-pipe ceilings the kernels are graded against (SURVEY.md §8d:
+// "take popc rate from a micro-benchmark on the box"): POPC, LOP3, IADD3, VIMNMX, DADD, DMUL, DFMA
+// per second on the whole chip, plus the mixed Hamming inner-loop ceiling.  Prints one JSON object.
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+constexpr int ILP = 8;
+constexpr int ITERS = 4096;
+
+enum Op { POPC, XOR, IADD3, MNMX, DADD, DMUL, DFMA, HAMMING };
+
+template <int OP>
+__global__ void __launch_bounds__(256) k(uint32_t *out, uint32_t seed, double dseed)
+{
+    uint32_t r[ILP], acc = 0;
+    double d[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) { r[i] = seed * (threadIdx.x + 1) + i * 0x9E3779B9u; d[i] = dseed + i + threadIdx.x; }
+    uint32_t q[8], b1 = 0xFFFFFFFFu, b2 = 0xFFFFFFFFu;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q[i] = seed ^ (i * 0x85EBCA6Bu + threadIdx.x);
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) {
+            if (OP == POPC) r[i] = __popc(r[i]) + 0x55555555u;         // 1 POPC + 1 IADD per op: see note below
+            if (OP == XOR) r[i] = (r[i] ^ seed) ^ (r[i] >> 1);
+            if (OP == IADD3) r[i] = r[i] + seed + it;
+            if (OP == MNMX) r[i] = max(min(r[i], seed + it), (uint32_t)it);
+            if (OP == DADD) d[i] = d[i] + dseed;
+            if (OP == DMUL) d[i] = d[i] * dseed;
+            if (OP == DFMA) d[i] = fma(d[i], dseed, dseed);
+        }
+        if (OP == HAMMING) {   // the matcher's inner loop on synthetic "train" words: 8 XOR + 8 POPC + adds + top-2
+#pragma unroll
+            for (int j = 0; j < ILP; ++j) {
+                uint32_t dist = 0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) dist += __popc(q[w] ^ (r[j] + w * 0x01000193u + it));
+                const uint32_t key = (dist << 22) + it * ILP + j;
+                const uint32_t hi = max(b1, key);
+                b1 = min(b1, key);
+                b2 = min(b2, hi);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) acc += r[i] + (uint32_t)d[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc + b1 + b2;
+}
+
+template <int OP>
+double run(uint32_t *out, int blocks, double ops_per_iter)
+{
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    k<OP><<<blocks, 256>>>(out, 12345u, 1.0000001);
+    cudaDeviceSynchronize();
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(a);
+        k<OP><<<blocks, 256>>>(out, 12345u + rep, 1.0000001);
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        float ms; cudaEventElapsedTime(&ms, a, b);
+        if (ms < best) best = ms;
+    }
+    return (double)blocks * 256 * ITERS * ops_per_iter / (best * 1e-3);
+}
+
+int main()
+{
+    cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
+    const int blocks = p.multiProcessorCount * 8;
+    uint32_t *out; cudaMalloc(&out, (size_t)blocks * 256 * 4);
+    int clk = 0; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
+    printf("{\"gpu\": \"%s\", \"sms\": %d, \"sm_clock_khz_max\": %d", p.name, p.multiProcessorCount, clk);
+    printf(", \"popc_per_s\": %.4e", run<POPC>(out, blocks, ILP));
+    printf(", \"lop3_per_s\": %.4e", run<XOR>(out, blocks, ILP * 2));
+    printf(", \"iadd3_per_s\": %.4e", run<IADD3>(out, blocks, ILP));
+    printf(", \"vimnmx_per_s\": %.4e", run<MNMX>(out, blocks, ILP * 2));
+    printf(", \"dadd_per_s\": %.4e", run<DADD>(out, blocks, ILP));
+    printf(", \"dmul_per_s\": %.4e", run<DMUL>(out, blocks, ILP));
+    printf(", \"dfma_per_s\": %.4e", run<DFMA>(out, blocks, ILP));
+    printf(", \"hamming256_pairs_per_s\": %.4e", run<HAMMING>(out, blocks, ILP));
+    printf("}\n");
+    return cudaGetLastError() != cudaSuccess;
+}
