@@ -17,18 +17,23 @@
 namespace mvs {
 
 // ------------------------------------------------------------------------------------------
-// K3.  The 9x9 problem SVD(A^T A) is solved by a one-sided Jacobi in which lane c of a 9-lane
-// group owns column c of W (= A^T A) and of V in registers.  The round-robin order pairs every
-// column with exactly one partner per step, so a step is: fetch the partner's columns with warp
-// shuffles, form the three inner products, compute the rotation (both lanes of a pair compute the
-// same c,s), rotate the own column.  3 groups (27 lanes) per warp; lanes 27..31 shadow lanes 0..4.
+// K3.  The 9x9 problem SVD(A^T A) is solved by a one-sided Jacobi laid out as a systolic "chess
+// tournament": a hypothesis is owned by 5 lanes (seats); every seat holds the two columns of W (= A^T A)
+// and of V that meet in the current step, so the three inner products, the rotation parameters and the
+// rotation itself are lane-local (one c,s computation per column pair).  Between steps the columns
+// move one seat along the ring  top1<-top2<-top3<-top4<-bot4<-bot3<-bot2<-bot1<-bot0<-top1  with two
+// warp shuffles per element.  Seat 0 pairs the bye (9 columns, 10 players) with player s.  In step s
+// seat k>=1 holds players ((s+k) mod 9, (s-k) mod 9): exactly the oracle's round-robin order.
+// 6 hypotheses (30 lanes) per warp; lanes 30,31 shadow lanes 0,1.
 // ------------------------------------------------------------------------------------------
 constexpr int HYP_WARPS = 4;
+constexpr int HYP_PER_WARP = 6;
 constexpr unsigned FULL = 0xFFFFFFFFu;
 
-// find_normalization_transform (fundamental-matrix.cpp:18-54) of the 8 sampled points of one image
+// find_normalization_transform (fundamental-matrix.cpp:18-54) of the 8 sampled points of one image;
+// T = [[s,0,tx],[0,s,ty],[0,0,1]] returned as (s, tx, ty)
 __device__ __forceinline__ void normalize8(const double *pts, const uint32_t (&idx)[8], int off,
-                                           double (&nx)[8], double (&ny)[8], double (&T)[9])
+                                           double (&nx)[8], double (&ny)[8], double (&T)[3])
 {
     double px[8], py[8], pz[8];
 #pragma unroll
@@ -51,9 +56,7 @@ __device__ __forceinline__ void normalize8(const double *pts, const uint32_t (&i
     scale = 1.4142135623730951 / scale;  // sqrt(2.0) correctly rounded
 #pragma unroll
     for (int i = 0; i < 8; ++i) { nx[i] *= scale; ny[i] *= scale; }
-    T[0] = scale; T[1] = 0.0; T[2] = -mx * scale;
-    T[3] = 0.0; T[4] = scale; T[5] = -my * scale;
-    T[6] = 0.0; T[7] = 0.0; T[8] = 1.0;
+    T[0] = scale; T[1] = -mx * scale; T[2] = -my * scale;
 }
 
 __device__ __forceinline__ double sel9(const double (&a)[9], int c)
@@ -64,81 +67,96 @@ __device__ __forceinline__ double sel9(const double (&a)[9], int c)
     return r;
 }
 
-// Cooperative 8-point solve by the 9 lanes [gbase, gbase+9) of a warp (all 32 lanes must call).
+// Cooperative 8-point solve by the 5 lanes [gbase, gbase+5) of a warp (all 32 lanes must call).
 // pts: [.][6] correspondences, idx: the 8 sampled rows. Every lane of the group returns the full F.
-__device__ __forceinline__ void eight_point_group(const double *pts, const uint32_t (&idx)[8], int c, int gbase,
+__device__ __forceinline__ void eight_point_group(const double *pts, const uint32_t (&idx)[8], int k, int gbase,
                                                   double (&F)[9])
 {
-    double T1[9], T2[9];
-    double wc[9], vc[9];
+    double T1[3], T2[3];
+    double wt[9], vt[9], wb[9], vb[9];
+    int pt = k, pb = (k == 0) ? 0 : 9 - k;  // players (columns) held at step 0; seat 0's top is the bye
     {
         double x1[8], y1[8], x2[8], y2[8];
         normalize8(pts, idx, 0, x1, y1, T1);
         normalize8(pts, idx, 3, x2, y2, T2);
-        // column c of A^T A, accumulated over the 8 rows in order (fundamental-matrix.cpp:76-111)
+        // columns pt, pb of A^T A, accumulated over the 8 rows in order (fundamental-matrix.cpp:76-111)
 #pragma unroll
-        for (int i = 0; i < 9; ++i) wc[i] = 0.0;
+        for (int i = 0; i < 9; ++i) { wt[i] = 0.0; wb[i] = 0.0; }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const double a[9] = {x2[k] * x1[k], x2[k] * y1[k], x2[k], y2[k] * x1[k], y2[k] * y1[k], y2[k], x1[k], y1[k], 1.0};
-            const double ac = sel9(a, c);
+        for (int r = 0; r < 8; ++r) {
+            const double a[9] = {x2[r] * x1[r], x2[r] * y1[r], x2[r], y2[r] * x1[r], y2[r] * y1[r], y2[r], x1[r], y1[r], 1.0};
+            const double at = sel9(a, pt), ab = sel9(a, pb);
 #pragma unroll
-            for (int i = 0; i < 9; ++i) wc[i] += a[i] * ac;
+            for (int i = 0; i < 9; ++i) { wt[i] += a[i] * at; wb[i] += a[i] * ab; }
         }
 #pragma unroll
-        for (int i = 0; i < 9; ++i) vc[i] = (i == c) ? 1.0 : 0.0;
+        for (int i = 0; i < 9; ++i) { vt[i] = (i == pt) ? 1.0 : 0.0; vb[i] = (i == pb) ? 1.0 : 0.0; }
     }
-    const unsigned gmask = 0x1FFu << gbase;
+    const int src_next = gbase + min(k + 1, 4), src_prev = gbase + max(k - 1, 0);
+    int step = 0;
     for (int sweep = 0; sweep < kSvdMaxSweeps; ++sweep) {
         bool changed = false;
-        for (int s = 0; s < 9; ++s) {
-            const bool bye = (c == s);
-            const int pc = bye ? c : (2 * s - c + 9) % 9;
-            const int src = gbase + pc;
-            double own = 0.0;
+        for (int s9 = 0; s9 < 9; ++s9) {
+            double at = 0.0, ab = 0.0, g = 0.0;
 #pragma unroll
-            for (int k = 0; k < 9; ++k) own += wc[k] * wc[k];
-            const double par = __shfl_sync(FULL, own, src);
-            double pw[9], g = 0.0;
-#pragma unroll
-            for (int k = 0; k < 9; ++k) {
-                pw[k] = __shfl_sync(FULL, wc[k], src);
-                g += wc[k] * pw[k];
+            for (int i = 0; i < 9; ++i) {
+                at = fma(wt[i], wt[i], at);
+                ab = fma(wb[i], wb[i], ab);
+                g = fma(wt[i], wb[i], g);   // products commute exactly
             }
-            const bool first = c < pc;  // this lane holds column p of the pair (p<q)
+            const bool top_first = pt < pb;  // the column with the smaller index is "p" of the pair (p<q)
             double cs, sn;
-            const bool rot = !bye && jacobi_cs(first ? own : par, first ? par : own, g, cs, sn);
-            const double ssn = first ? sn : -sn;  // p: c*wp + s*wq ; q: c*wq - s*wp
+            const bool rot = (k != 0) && jacobi_cs(top_first ? at : ab, top_first ? ab : at, g, cs, sn);
+            if (rot) {
+                // p' = c*p + s*q ; q' = c*q - s*p
+                const double st = top_first ? sn : -sn;   // top' = c*top + st*bot ; bot' = c*bot - st*top
 #pragma unroll
-            for (int k = 0; k < 9; ++k) {
-                const double pv = __shfl_sync(FULL, vc[k], src);
-                if (rot) {
-                    wc[k] = first ? (cs * wc[k] + sn * pw[k]) : (cs * wc[k] - sn * pw[k]);
-                    vc[k] = first ? (cs * vc[k] + sn * pv) : (cs * vc[k] - sn * pv);
+                for (int i = 0; i < 9; ++i) {
+                    const double a0 = wt[i], b0 = wb[i];
+                    wt[i] = fma(cs, a0, st * b0);
+                    wb[i] = fma(cs, b0, -(st * a0));
+                    const double a1 = vt[i], b1 = vb[i];
+                    vt[i] = fma(cs, a1, st * b1);
+                    vb[i] = fma(cs, b1, -(st * a1));
                 }
             }
-            (void)ssn;
             changed |= rot;
+            // ring move to the seating of the next step
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                const double tn = __shfl_sync(FULL, wt[i], src_next), bp = __shfl_sync(FULL, wb[i], src_prev);
+                wt[i] = (k == 4) ? wb[i] : tn;
+                wb[i] = (k == 0) ? tn : bp;
+                const double un = __shfl_sync(FULL, vt[i], src_next), up = __shfl_sync(FULL, vb[i], src_prev);
+                vt[i] = (k == 4) ? vb[i] : un;
+                vb[i] = (k == 0) ? un : up;
+            }
+            ++step;
+            const int sm = step % 9;
+            pt = (sm + k) % 9;
+            pb = (k == 0) ? sm : (sm - k + 9) % 9;
         }
         if (__ballot_sync(FULL, changed) == 0u) break;
-        (void)gmask;
     }
-    // f = V column of the smallest singular value (vt.row(8), fundamental-matrix.cpp:114-118);
-    // among equal values the later column, as a stable descending sort would leave it last
-    double sig = 0.0;
+    // f = V column of the smallest singular value (vt.row(8), fundamental-matrix.cpp:114-118); among
+    // equal values the column with the larger index, as a stable descending sort would leave it last
+    double sg_t = 0.0, sg_b = 0.0;
 #pragma unroll
-    for (int k = 0; k < 9; ++k) sig += wc[k] * wc[k];
-    sig = sqrt(sig);
+    for (int i = 0; i < 9; ++i) { sg_t = fma(wt[i], wt[i], sg_t); sg_b = fma(wb[i], wb[i], sg_b); }
+    sg_t = (k == 0) ? CUDART_INF : sqrt(sg_t);
+    sg_b = sqrt(sg_b);
     double best = CUDART_INF;
-    int bj = 0;
+    int bj = -1, blane = 0, btop = 0;
 #pragma unroll
-    for (int j = 0; j < 9; ++j) {
-        const double v = __shfl_sync(FULL, sig, gbase + j);
-        if (v <= best) { best = v; bj = j; }
+    for (int l = 0; l < 5; ++l) {
+        const double vt_ = __shfl_sync(FULL, sg_t, gbase + l), vb_ = __shfl_sync(FULL, sg_b, gbase + l);
+        const int jt = __shfl_sync(FULL, pt, gbase + l), jb = __shfl_sync(FULL, pb, gbase + l);
+        if (l != 0 && (vt_ < best || (vt_ == best && jt > bj))) { best = vt_; bj = jt; blane = l; btop = 1; }
+        if (vb_ < best || (vb_ == best && jb > bj)) { best = vb_; bj = jb; blane = l; btop = 0; }
     }
     double Fp[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) Fp[i] = __shfl_sync(FULL, vc[i], gbase + bj);
+    for (int i = 0; i < 9; ++i) Fp[i] = __shfl_sync(FULL, btop ? vt[i] : vb[i], gbase + blane);
     // singular constraint (fundamental-matrix.cpp:128-136), then F = T2^T * F * T1 (:245)
     double U[9], w[3], Vt[9], Fh[9], T2t[9], tmp[9];
     svd3(Fp, U, w, Vt);
@@ -147,9 +165,11 @@ __device__ __forceinline__ void eight_point_group(const double *pts, const uint3
 #pragma unroll
         for (int j = 0; j < 3; ++j)
             Fh[i * 3 + j] = (U[i * 3 + 0] * w[0]) * Vt[0 * 3 + j] + (U[i * 3 + 1] * w[1]) * Vt[1 * 3 + j];
-    mat3_transpose(T2, T2t);
+    const double T1m[9] = {T1[0], 0.0, T1[1], 0.0, T1[0], T1[2], 0.0, 0.0, 1.0};
+    const double T2m[9] = {T2[0], 0.0, T2[1], 0.0, T2[0], T2[2], 0.0, 0.0, 1.0};
+    mat3_transpose(T2m, T2t);
     mat3_mul(T2t, Fh, tmp);
-    mat3_mul(tmp, T1, F);
+    mat3_mul(tmp, T1m, F);
 }
 
 __global__ void __launch_bounds__(HYP_WARPS * 32)
@@ -162,10 +182,10 @@ hypotheses_kernel(HypArgs a)
         n = a.state[pair].n_matches;
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = lane < 27 ? lane / 9 : 0;
-    const int c = lane < 27 ? lane % 9 : lane - 27;
-    const int gbase = g * 9;
-    const int h0 = (blockIdx.x * HYP_WARPS + warp) * 3;
+    const int g = lane < 30 ? lane / 5 : 0;
+    const int c = lane < 30 ? lane % 5 : lane - 30;
+    const int gbase = g * 5;
+    const int h0 = (blockIdx.x * HYP_WARPS + warp) * HYP_PER_WARP;
     if (h0 >= a.H) return;  // warp-uniform
     const int h = min(h0 + g, a.H - 1);
     uint32_t idx[8];
@@ -177,7 +197,7 @@ hypotheses_kernel(HypArgs a)
     }
     double F[9];
     eight_point_group(a.points + (size_t)pair * a.p_stride * 6, idx, c, gbase, F);
-    if (lane < 27 && c == 0 && h0 + g < a.H) {
+    if (lane < 30 && c == 0 && h0 + g < a.H) {
         double *o = a.F_all + ((size_t)pair * a.H + h) * 9;
 #pragma unroll
         for (int i = 0; i < 9; ++i) o[i] = F[i];
@@ -189,29 +209,30 @@ __global__ void __launch_bounds__(HYP_WARPS * 32)
 fundamental_sets_kernel(const double *p1s, const double *p2s, int n_sets, double *pts6, double *F_out)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = lane < 27 ? lane / 9 : 0;
-    const int c = lane < 27 ? lane % 9 : lane - 27;
-    const int gbase = g * 9;
-    const int h0 = (blockIdx.x * HYP_WARPS + warp) * 3;
+    const int g = lane < 30 ? lane / 5 : 0;
+    const int c = lane < 30 ? lane % 5 : lane - 30;
+    const int gbase = g * 5;
+    const int h0 = (blockIdx.x * HYP_WARPS + warp) * HYP_PER_WARP;
     if (h0 >= n_sets) return;
     const int h = min(h0 + g, n_sets - 1);
     (void)pts6;
     // gather this set into a per-lane view through a tiny index table over a virtual [8][6] block
     // stored in global scratch (written by the same lanes, then re-read; volume is negligible)
     double *blk = pts6 + (size_t)h * 48;
-    if (lane < 27 && c < 8) {
+    if (lane < 30) {
+        for (int r = c; r < 8; r += 5)
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            blk[c * 6 + k] = p1s[((size_t)h * 8 + c) * 3 + k];
-            blk[c * 6 + 3 + k] = p2s[((size_t)h * 8 + c) * 3 + k];
-        }
+            for (int k = 0; k < 3; ++k) {
+                blk[r * 6 + k] = p1s[((size_t)h * 8 + r) * 3 + k];
+                blk[r * 6 + 3 + k] = p2s[((size_t)h * 8 + r) * 3 + k];
+            }
     }
     __syncwarp();
     __threadfence_block();
     const uint32_t idx[8] = {0, 1, 2, 3, 4, 5, 6, 7};
     double F[9];
     eight_point_group(blk, idx, c, gbase, F);
-    if (lane < 27 && c == 0 && h0 + g < n_sets) {
+    if (lane < 30 && c == 0 && h0 + g < n_sets) {
 #pragma unroll
         for (int i = 0; i < 9; ++i) F_out[(size_t)h * 9 + i] = F[i];
     }
@@ -262,17 +283,18 @@ score_kernel(ScoreArgs a)
 #pragma unroll 4
     for (int i = 0; i < cnt; ++i) {
         double r;
+        bool in;
         if (UNIT_Z) {
             const double2 u = *reinterpret_cast<const double2 *>(sp + 4 * i);
             const double2 v = *reinterpret_cast<const double2 *>(sp + 4 * i + 2);
-            r = point_residual<true, MODE>(u.x, u.y, 1.0, v.x, v.y, 1.0, F);
+            in = point_residual<true, MODE>(u.x, u.y, 1.0, v.x, v.y, 1.0, F, thr, r);
         } else {
             const double2 u = *reinterpret_cast<const double2 *>(sp + 6 * i);
             const double2 v = *reinterpret_cast<const double2 *>(sp + 6 * i + 2);
             const double2 w = *reinterpret_cast<const double2 *>(sp + 6 * i + 4);
-            r = point_residual<false, MODE>(u.x, u.y, v.x, v.y, w.x, w.y, F);
+            in = point_residual<false, MODE>(u.x, u.y, v.x, v.y, w.x, w.y, F, thr, r);
         }
-        if (r < thr) { ++c; res += r; }
+        if (in) { ++c; res += r; }
     }
     const size_t o = ((size_t)pair * a.tiles + tile) * a.H + h;
     a.part_count[o] = c;
@@ -408,15 +430,15 @@ select_kernel(SelectArgs a)
     uint8_t *mask = a.mask + (size_t)pair * a.p_stride;
     for (int i = threadIdx.x; i < n; i += SEL_THREADS) {
         const double *p = pts + (size_t)i * 6;
-        const double r = point_residual<UNIT_Z, MODE>(p[0], p[1], p[2], p[3], p[4], p[5], F);
-        mask[i] = (r < a.max_error_sq) ? 1 : 0;
+        double r;
+        mask[i] = point_residual<UNIT_Z, MODE>(p[0], p[1], p[2], p[3], p[4], p[5], F, a.max_error_sq, r) ? 1 : 0;
     }
 }
 
 // ------------------------------------------------------------------------------------------ launchers
 void launch_hypotheses(const HypArgs &a, int n_pairs, cudaStream_t s)
 {
-    const int per_block = HYP_WARPS * 3;
+    const int per_block = HYP_WARPS * HYP_PER_WARP;
     dim3 grid((a.H + per_block - 1) / per_block, n_pairs);
     hypotheses_kernel<<<grid, HYP_WARPS * 32, 0, s>>>(a);
 }
@@ -425,7 +447,7 @@ void launch_fundamental_sets(const double *p1s, const double *p2s, int n_sets, d
 {
     // scratch for the interleaved [n_sets][8][6] view lives right behind F_out's device buffer: the
     // caller passes F_out with room for n_sets*9 + n_sets*48 doubles
-    const int per_block = HYP_WARPS * 3;
+    const int per_block = HYP_WARPS * HYP_PER_WARP;
     fundamental_sets_kernel<<<(n_sets + per_block - 1) / per_block, HYP_WARPS * 32, 0, s>>>(
         p1s, p2s, n_sets, F_out + (size_t)n_sets * 9, F_out);
 }

@@ -173,38 +173,42 @@ int orc_match_l2(const float *q, int nq, const float *t, int nt, int dim,
  * ------------------------------------------------------------------------------------------ */
 #define SVD_MAX_N 9
 #define SVD_MAX_SWEEPS 30
-#define SVD_EPS (2.0 * DBL_EPSILON)
+#define SVD_EPS2 ((2.0 * DBL_EPSILON) * (2.0 * DBL_EPSILON))
 #define SVD_RANK_TOL 1e-12
 
+/* One rotation.  The explicit fma() calls are part of the numerical contract shared bit-for-bit with
+ * the CUDA kernels (DFMA there, a hardware FMA here when built with -mfma, glibc's exact fma() otherwise);
+ * nothing else is contracted (-ffp-contract=off). */
 static void jacobi_rotate(int n, double W[SVD_MAX_N][SVD_MAX_N], double V[SVD_MAX_N][SVD_MAX_N],
                           int p, int q, int *changed)
 {
     double a = 0.0, b = 0.0, g = 0.0;
     for (int k = 0; k < n; ++k) {
-        a += W[k][p] * W[k][p];
-        b += W[k][q] * W[k][q];
-        g += W[k][p] * W[k][q];
+        a = fma(W[k][p], W[k][p], a);
+        b = fma(W[k][q], W[k][q], b);
+        g = fma(W[k][p], W[k][q], g);
     }
-    if (fabs(g) <= SVD_EPS * sqrt(a * b)) return;
+    /* |g| <= eps * sqrt(a*b), evaluated without the square root */
+    if (g * g <= (SVD_EPS2 * a) * b) return;
     *changed = 1;
     double g2 = g * 2.0, beta = a - b;
-    double gamma = sqrt(g2 * g2 + beta * beta);
+    double gamma = sqrt(fma(g2, g2, beta * beta));
+    double inv = 1.0 / (gamma * 2.0);
     double c, s;
     if (beta < 0) {
-        double delta = (gamma - beta) * 0.5;
-        s = sqrt(delta / gamma);
-        c = g2 / (gamma * s * 2.0);
+        s = sqrt((gamma - beta) * inv);
+        c = (g2 * inv) / s;
     } else {
-        c = sqrt((gamma + beta) / (gamma * 2.0));
-        s = g2 / (gamma * c * 2.0);
+        c = sqrt((gamma + beta) * inv);
+        s = (g2 * inv) / c;
     }
     for (int k = 0; k < n; ++k) {
         double wp = W[k][p], wq = W[k][q];
-        W[k][p] = c * wp + s * wq;
-        W[k][q] = c * wq - s * wp;
+        W[k][p] = fma(c, wp, s * wq);
+        W[k][q] = fma(c, wq, -(s * wp));
         double vp = V[k][p], vq = V[k][q];
-        V[k][p] = c * vp + s * vq;
-        V[k][q] = c * vq - s * vp;
+        V[k][p] = fma(c, vp, s * vq);
+        V[k][q] = fma(c, vq, -(s * vp));
     }
 }
 
@@ -495,17 +499,27 @@ void orc_sample_table(uint64_t seed, uint64_t pair_id, uint32_t n_points, int H,
 /* residual of one correspondence.  ALGEBRAIC = |p2^T F p1| evaluated as (p2^T F) p1
  * (estimator-RANSAC.cpp:114-116).  SAMPSON = r^2 / (|(F p1)_xy|^2 + |(F^T p2)_xy|^2), the score of
  * cv::findEssentialMat's RANSAC (default-build branch, sfm-solve.cpp:42-63; north-star mode). */
-static inline double point_residual(const double *a /*p1*/, const double *b /*p2*/, const double F[9], int mode)
+/* ALGEBRAIC: e = |r| < thr.  SAMPSON: r^2 / den < thr, decided as r^2 < thr * den (den > 0) so that the
+ * division is only needed for the residual of actual inliers.  Explicit fma() = shared contract with the GPU. */
+static inline int point_residual(const double *a /*p1*/, const double *b /*p2*/, const double F[9], int mode,
+                                 double thr, double *res)
 {
-    double v0 = b[0] * F[0] + b[1] * F[3] + b[2] * F[6];
-    double v1 = b[0] * F[1] + b[1] * F[4] + b[2] * F[7];
-    double v2 = b[0] * F[2] + b[1] * F[5] + b[2] * F[8];
-    double r = v0 * a[0] + v1 * a[1] + v2 * a[2];
-    if (mode == ORC_SCORE_ALGEBRAIC) return r < 0 ? -r : r;
-    double l0 = F[0] * a[0] + F[1] * a[1] + F[2] * a[2];
-    double l1 = F[3] * a[0] + F[4] * a[1] + F[5] * a[2];
-    double den = (l0 * l0 + l1 * l1) + (v0 * v0 + v1 * v1);
-    return (r * r) / den;
+    double v0 = fma(b[0], F[0], fma(b[1], F[3], b[2] * F[6]));
+    double v1 = fma(b[0], F[1], fma(b[1], F[4], b[2] * F[7]));
+    double v2 = fma(b[0], F[2], fma(b[1], F[5], b[2] * F[8]));
+    double r = fma(v0, a[0], fma(v1, a[1], v2 * a[2]));
+    if (mode == ORC_SCORE_ALGEBRAIC) {
+        double e = r < 0 ? -r : r;
+        *res = e;
+        return e < thr;
+    }
+    double l0 = fma(F[0], a[0], fma(F[1], a[1], F[2] * a[2]));
+    double l1 = fma(F[3], a[0], fma(F[4], a[1], F[5] * a[2]));
+    double den = fma(l0, l0, l1 * l1) + fma(v0, v0, v1 * v1);
+    double r2 = r * r;
+    if (!(r2 < thr * den)) return 0;
+    *res = r2 / den;
+    return 1;
 }
 
 /* count_inliers, estimator-RANSAC.cpp:100-129 (strict '<', residual summed over inliers in order) */
@@ -515,8 +529,8 @@ int orc_count_inliers(const double *p1, const double *p2, int n, const double F[
     int cnt = 0;
     double res = 0.0;
     for (int i = 0; i < n; ++i) {
-        double r = point_residual(p1 + 3 * i, p2 + 3 * i, F, score_mode);
-        if (r < max_error_sq) { ++cnt; res += r; if (mask) mask[i] = 1; }
+        double r;
+        if (point_residual(p1 + 3 * i, p2 + 3 * i, F, score_mode, max_error_sq, &r)) { ++cnt; res += r; if (mask) mask[i] = 1; }
         else if (mask) mask[i] = 0;
     }
     *residual = res;
