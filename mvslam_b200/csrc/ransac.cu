@@ -17,23 +17,26 @@
 namespace mvs {
 
 // ------------------------------------------------------------------------------------------
-// K3.  The 9x9 problem SVD(A^T A) is solved by a one-sided Jacobi laid out as a systolic "chess
-// tournament": a hypothesis is owned by 5 lanes (seats); every seat holds the two columns of W (= A^T A)
-// and of V that meet in the current step, so the three inner products, the rotation parameters and the
-// rotation itself are lane-local (one c,s computation per column pair).  Between steps the columns
-// move one seat along the ring  top1<-top2<-top3<-top4<-bot4<-bot3<-bot2<-bot1<-bot0<-top1  with two
-// warp shuffles per element.  Seat 0 pairs the bye (9 columns, 10 players) with player s.  In step s
-// seat k>=1 holds players ((s+k) mod 9, (s-k) mod 9): exactly the oracle's round-robin order.
-// 6 hypotheses (30 lanes) per warp; lanes 30,31 shadow lanes 0,1.
+// K3.  f = vt.row(8) of SVD(A^T A) (fundamental-matrix.cpp:104-118) is the right singular vector of the
+// 8x9 matrix A for its zero singular value.  It is computed from A itself (no squared condition number,
+// ~1000x more accurate than the A^T A route): a one-sided Jacobi orthogonalises the 8
+// columns of A^T, then f is the unit vector orthogonal to all of them (2 passes of modified Gram-Schmidt).
+// Layout: a systolic "chess tournament" — a hypothesis is owned by 4 lanes (seats); every seat holds the
+// two length-9 columns that meet in the current step, so inner products, rotation parameters and the
+// rotation are lane-local (one c,s per column pair, nothing redundant).  Between steps the columns move
+// one seat along the ring  top1<-top2<-top3<-bot3<-bot2<-bot1<-bot0<-top1  (player 7 stays in seat 0)
+// with two warp shuffles per element.  In step s seat 0 holds players (7, s), seat k holds
+// ((s+k) mod 7, (s-k) mod 7): exactly the oracle's round-robin order.  8 hypotheses per warp.
 // ------------------------------------------------------------------------------------------
 constexpr int HYP_WARPS = 4;
-constexpr int HYP_PER_WARP = 6;
+constexpr int HYP_PER_WARP = 8;
 constexpr unsigned FULL = 0xFFFFFFFFu;
 
-// find_normalization_transform (fundamental-matrix.cpp:18-54) of the 8 sampled points of one image;
-// T = [[s,0,tx],[0,s,ty],[0,0,1]] returned as (s, tx, ty)
+// find_normalization_transform (fundamental-matrix.cpp:18-54) of the 8 sampled points of one image:
+// returns T = [[s,0,tx],[0,s,ty],[0,0,1]] as (s, tx, ty) and the centroid (mx, my); the normalised
+// coordinates of a point are then ((x - mx) * s, (y - my) * s), the same operations the reference applies.
 __device__ __forceinline__ void normalize8(const double *pts, const uint32_t (&idx)[8], int off,
-                                           double (&nx)[8], double (&ny)[8], double (&T)[3])
+                                           double (&T)[3], double &mx, double &my)
 {
     double px[8], py[8], pz[8];
 #pragma unroll
@@ -41,7 +44,8 @@ __device__ __forceinline__ void normalize8(const double *pts, const uint32_t (&i
         const double *p = pts + (size_t)idx[i] * 6 + off;
         px[i] = p[0]; py[i] = p[1]; pz[i] = p[2];
     }
-    double mx = 0.0, my = 0.0, mz = 0.0;
+    double mz = 0.0;
+    mx = 0.0; my = 0.0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) { mx += px[i]; my += py[i]; mz += pz[i]; }
     mx *= 0.125; my *= 0.125; mz *= 0.125;
@@ -50,13 +54,27 @@ __device__ __forceinline__ void normalize8(const double *pts, const uint32_t (&i
     for (int i = 0; i < 8; ++i) {
         const double dx = px[i] - mx, dy = py[i] - my, dz = pz[i] - mz;
         scale += sqrt(dx * dx + dy * dy + dz * dz);
-        nx[i] = dx; ny[i] = dy;
     }
     scale *= 0.125;
     scale = 1.4142135623730951 / scale;  // sqrt(2.0) correctly rounded
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { nx[i] *= scale; ny[i] *= scale; }
     T[0] = scale; T[1] = -mx * scale; T[2] = -my * scale;
+}
+
+__device__ __forceinline__ uint32_t sel8(const uint32_t (&a)[8], int c)
+{
+    uint32_t r = a[0];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) r = (c == k) ? a[k] : r;
+    return r;
+}
+
+// row of A for one normalised correspondence (fundamental-matrix.cpp:76-87)
+__device__ __forceinline__ void epipolar_row(const double *p, const double (&T1)[3], double mx1, double my1,
+                                             const double (&T2)[3], double mx2, double my2, double (&a)[9])
+{
+    const double x1 = (p[0] - mx1) * T1[0], y1 = (p[1] - my1) * T1[0];
+    const double x2 = (p[3] - mx2) * T2[0], y2 = (p[4] - my2) * T2[0];
+    a[0] = x2 * x1; a[1] = x2 * y1; a[2] = x2; a[3] = y2 * x1; a[4] = y2 * y1; a[5] = y2; a[6] = x1; a[7] = y1; a[8] = 1.0;
 }
 
 __device__ __forceinline__ double sel9(const double (&a)[9], int c)
@@ -67,36 +85,27 @@ __device__ __forceinline__ double sel9(const double (&a)[9], int c)
     return r;
 }
 
-// Cooperative 8-point solve by the 5 lanes [gbase, gbase+5) of a warp (all 32 lanes must call).
+// Cooperative 8-point solve by the 4 lanes [gbase, gbase+4) of a warp (all 32 lanes must call).
 // pts: [.][6] correspondences, idx: the 8 sampled rows. Every lane of the group returns the full F.
 __device__ __forceinline__ void eight_point_group(const double *pts, const uint32_t (&idx)[8], int k, int gbase,
                                                   double (&F)[9])
 {
     double T1[3], T2[3];
-    double wt[9], vt[9], wb[9], vb[9];
-    int pt = k, pb = (k == 0) ? 0 : 9 - k;  // players (columns) held at step 0; seat 0's top is the bye
+    double wt[9], wb[9];
+    int pt = (k == 0) ? 7 : k, pb = (k == 0) ? 0 : 7 - k;  // players (= sample rows) held at step 0
     {
-        double x1[8], y1[8], x2[8], y2[8];
-        normalize8(pts, idx, 0, x1, y1, T1);
-        normalize8(pts, idx, 3, x2, y2, T2);
-        // columns pt, pb of A^T A, accumulated over the 8 rows in order (fundamental-matrix.cpp:76-111)
-#pragma unroll
-        for (int i = 0; i < 9; ++i) { wt[i] = 0.0; wb[i] = 0.0; }
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const double a[9] = {x2[r] * x1[r], x2[r] * y1[r], x2[r], y2[r] * x1[r], y2[r] * y1[r], y2[r], x1[r], y1[r], 1.0};
-            const double at = sel9(a, pt), ab = sel9(a, pb);
-#pragma unroll
-            for (int i = 0; i < 9; ++i) { wt[i] += a[i] * at; wb[i] += a[i] * ab; }
-        }
-#pragma unroll
-        for (int i = 0; i < 9; ++i) { vt[i] = (i == pt) ? 1.0 : 0.0; vb[i] = (i == pb) ? 1.0 : 0.0; }
+        double mx1, my1, mx2, my2;
+        normalize8(pts, idx, 0, T1, mx1, my1);
+        normalize8(pts, idx, 3, T2, mx2, my2);
+        // column r of A^T = row r of A: this seat only needs the rows of its two players
+        epipolar_row(pts + (size_t)sel8(idx, pt) * 6, T1, mx1, my1, T2, mx2, my2, wt);
+        epipolar_row(pts + (size_t)sel8(idx, pb) * 6, T1, mx1, my1, T2, mx2, my2, wb);
     }
-    const int src_next = gbase + min(k + 1, 4), src_prev = gbase + max(k - 1, 0);
+    const int src_next = gbase + min(k + 1, 3), src_prev = gbase + max(k - 1, 0);
     int step = 0;
     for (int sweep = 0; sweep < kSvdMaxSweeps; ++sweep) {
         bool changed = false;
-        for (int s9 = 0; s9 < 9; ++s9) {
+        for (int s7 = 0; s7 < 7; ++s7) {
             double at = 0.0, ab = 0.0, g = 0.0;
 #pragma unroll
             for (int i = 0; i < 9; ++i) {
@@ -106,7 +115,7 @@ __device__ __forceinline__ void eight_point_group(const double *pts, const uint3
             }
             const bool top_first = pt < pb;  // the column with the smaller index is "p" of the pair (p<q)
             double cs, sn;
-            const bool rot = (k != 0) && jacobi_cs(top_first ? at : ab, top_first ? ab : at, g, cs, sn);
+            const bool rot = jacobi_cs(top_first ? at : ab, top_first ? ab : at, g, cs, sn);
             if (rot) {
                 // p' = c*p + s*q ; q' = c*q - s*p
                 const double st = top_first ? sn : -sn;   // top' = c*top + st*bot ; bot' = c*bot - st*top
@@ -115,9 +124,6 @@ __device__ __forceinline__ void eight_point_group(const double *pts, const uint3
                     const double a0 = wt[i], b0 = wb[i];
                     wt[i] = fma(cs, a0, st * b0);
                     wb[i] = fma(cs, b0, -(st * a0));
-                    const double a1 = vt[i], b1 = vb[i];
-                    vt[i] = fma(cs, a1, st * b1);
-                    vb[i] = fma(cs, b1, -(st * a1));
                 }
             }
             changed |= rot;
@@ -125,46 +131,72 @@ __device__ __forceinline__ void eight_point_group(const double *pts, const uint3
 #pragma unroll
             for (int i = 0; i < 9; ++i) {
                 const double tn = __shfl_sync(FULL, wt[i], src_next), bp = __shfl_sync(FULL, wb[i], src_prev);
-                wt[i] = (k == 4) ? wb[i] : tn;
+                wt[i] = (k == 0) ? wt[i] : ((k == 3) ? wb[i] : tn);
                 wb[i] = (k == 0) ? tn : bp;
-                const double un = __shfl_sync(FULL, vt[i], src_next), up = __shfl_sync(FULL, vb[i], src_prev);
-                vt[i] = (k == 4) ? vb[i] : un;
-                vb[i] = (k == 0) ? un : up;
             }
             ++step;
-            const int sm = step % 9;
-            pt = (sm + k) % 9;
-            pb = (k == 0) ? sm : (sm - k + 9) % 9;
+            const int sm = step % 7;
+            pt = (k == 0) ? 7 : (sm + k) % 7;
+            pb = (k == 0) ? sm : (sm - k + 7) % 7;
         }
         if (__ballot_sync(FULL, changed) == 0u) break;
     }
-    // f = V column of the smallest singular value (vt.row(8), fundamental-matrix.cpp:114-118); among
-    // equal values the column with the larger index, as a stable descending sort would leave it last
-    double sg_t = 0.0, sg_b = 0.0;
+    // f: unit vector orthogonal to the 8 (now mutually orthogonal) columns, visited in player order
+    double nt = 0.0, nb = 0.0;
 #pragma unroll
-    for (int i = 0; i < 9; ++i) { sg_t = fma(wt[i], wt[i], sg_t); sg_b = fma(wb[i], wb[i], sg_b); }
-    sg_t = (k == 0) ? CUDART_INF : sqrt(sg_t);
-    sg_b = sqrt(sg_b);
-    double best = CUDART_INF;
-    int bj = -1, blane = 0, btop = 0;
+    for (int i = 0; i < 9; ++i) { nt = fma(wt[i], wt[i], nt); nb = fma(wb[i], wb[i], nb); }
+    const double it = nt > 0.0 ? 1.0 / nt : 0.0, ib = nb > 0.0 ? 1.0 / nb : 0.0;
+    double t[9], x[9];
 #pragma unroll
-    for (int l = 0; l < 5; ++l) {
-        const double vt_ = __shfl_sync(FULL, sg_t, gbase + l), vb_ = __shfl_sync(FULL, sg_b, gbase + l);
-        const int jt = __shfl_sync(FULL, pt, gbase + l), jb = __shfl_sync(FULL, pb, gbase + l);
-        if (l != 0 && (vt_ < best || (vt_ == best && jt > bj))) { best = vt_; bj = jt; blane = l; btop = 1; }
-        if (vb_ < best || (vb_ == best && jb > bj)) { best = vb_; bj = jb; blane = l; btop = 0; }
+    for (int i = 0; i < 9; ++i) { t[i] = 0.0; x[i] = 0.0; }
+    // pass -1 accumulates t (the squared projections of the unit vectors), passes 0,1 are the Gram-Schmidt
+    int best = 0;
+#pragma unroll 1
+    for (int pass = -1; pass < 2; ++pass) {
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j) {
+            const bool mt = (pt == j), mb = (pb == j);
+            const unsigned holders = __ballot_sync(FULL, mt || mb);
+            const int src = gbase + __ffs((holders >> gbase) & 0xFu) - 1;
+            const double inv = __shfl_sync(FULL, mt ? it : ib, src);
+            double w[9], d = 0.0;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                w[i] = __shfl_sync(FULL, mt ? wt[i] : wb[i], src);
+                d = fma(x[i], w[i], d);
+            }
+            if (pass < 0) {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) t[i] = fma(w[i] * w[i], inv, t[i]);
+            } else {
+                d *= inv;
+#pragma unroll
+                for (int i = 0; i < 9; ++i) x[i] = fma(-d, w[i], x[i]);
+            }
+        }
+        if (pass < 0) {
+            double tb = t[0];
+#pragma unroll
+            for (int i = 1; i < 9; ++i) if (t[i] < tb) { tb = t[i]; best = i; }
+#pragma unroll
+            for (int i = 0; i < 9; ++i) x[i] = (i == best) ? 1.0 : 0.0;
+        }
     }
+    double nx = 0.0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) nx = fma(x[i], x[i], nx);
+    nx = sqrt(nx);
     double Fp[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) Fp[i] = __shfl_sync(FULL, btop ? vt[i] : vb[i], gbase + blane);
+    for (int i = 0; i < 9; ++i) Fp[i] = x[i] / nx;
     // singular constraint (fundamental-matrix.cpp:128-136), then F = T2^T * F * T1 (:245)
-    double U[9], w[3], Vt[9], Fh[9], T2t[9], tmp[9];
-    svd3(Fp, U, w, Vt);
+    double U[9], w3[3], Vt[9], Fh[9], T2t[9], tmp[9];
+    svd3(Fp, U, w3, Vt);
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int j = 0; j < 3; ++j)
-            Fh[i * 3 + j] = (U[i * 3 + 0] * w[0]) * Vt[0 * 3 + j] + (U[i * 3 + 1] * w[1]) * Vt[1 * 3 + j];
+            Fh[i * 3 + j] = (U[i * 3 + 0] * w3[0]) * Vt[0 * 3 + j] + (U[i * 3 + 1] * w3[1]) * Vt[1 * 3 + j];
     const double T1m[9] = {T1[0], 0.0, T1[1], 0.0, T1[0], T1[2], 0.0, 0.0, 1.0};
     const double T2m[9] = {T2[0], 0.0, T2[1], 0.0, T2[0], T2[2], 0.0, 0.0, 1.0};
     mat3_transpose(T2m, T2t);
@@ -182,9 +214,9 @@ hypotheses_kernel(HypArgs a)
         n = a.state[pair].n_matches;
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = lane < 30 ? lane / 5 : 0;
-    const int c = lane < 30 ? lane % 5 : lane - 30;
-    const int gbase = g * 5;
+    const int g = lane >> 2;
+    const int c = lane & 3;
+    const int gbase = g * 4;
     const int h0 = (blockIdx.x * HYP_WARPS + warp) * HYP_PER_WARP;
     if (h0 >= a.H) return;  // warp-uniform
     const int h = min(h0 + g, a.H - 1);
@@ -197,7 +229,7 @@ hypotheses_kernel(HypArgs a)
     }
     double F[9];
     eight_point_group(a.points + (size_t)pair * a.p_stride * 6, idx, c, gbase, F);
-    if (lane < 30 && c == 0 && h0 + g < a.H) {
+    if (c == 0 && h0 + g < a.H) {
         double *o = a.F_all + ((size_t)pair * a.H + h) * 9;
 #pragma unroll
         for (int i = 0; i < 9; ++i) o[i] = F[i];
@@ -209,9 +241,9 @@ __global__ void __launch_bounds__(HYP_WARPS * 32)
 fundamental_sets_kernel(const double *p1s, const double *p2s, int n_sets, double *pts6, double *F_out)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = lane < 30 ? lane / 5 : 0;
-    const int c = lane < 30 ? lane % 5 : lane - 30;
-    const int gbase = g * 5;
+    const int g = lane >> 2;
+    const int c = lane & 3;
+    const int gbase = g * 4;
     const int h0 = (blockIdx.x * HYP_WARPS + warp) * HYP_PER_WARP;
     if (h0 >= n_sets) return;
     const int h = min(h0 + g, n_sets - 1);
@@ -219,8 +251,8 @@ fundamental_sets_kernel(const double *p1s, const double *p2s, int n_sets, double
     // gather this set into a per-lane view through a tiny index table over a virtual [8][6] block
     // stored in global scratch (written by the same lanes, then re-read; volume is negligible)
     double *blk = pts6 + (size_t)h * 48;
-    if (lane < 30) {
-        for (int r = c; r < 8; r += 5)
+    {
+        for (int r = c; r < 8; r += 4)
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 blk[r * 6 + k] = p1s[((size_t)h * 8 + r) * 3 + k];
@@ -232,7 +264,7 @@ fundamental_sets_kernel(const double *p1s, const double *p2s, int n_sets, double
     const uint32_t idx[8] = {0, 1, 2, 3, 4, 5, 6, 7};
     double F[9];
     eight_point_group(blk, idx, c, gbase, F);
-    if (lane < 30 && c == 0 && h0 + g < n_sets) {
+    if (c == 0 && h0 + g < n_sets) {
 #pragma unroll
         for (int i = 0; i < 9; ++i) F_out[(size_t)h * 9 + i] = F[i];
     }

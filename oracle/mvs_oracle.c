@@ -419,6 +419,72 @@ static void find_normalization_transform(const double *p /*[8][3]*/, double np[8
     T[6] = 0; T[7] = 0; T[8] = 1;
 }
 
+/* The reference obtains f as vt.row(8) of cv::SVDecomp(A^T A) (fundamental-matrix.cpp:104-118), i.e. the
+ * right singular vector of the 8x9 matrix A for its zero singular value.  That vector is computed here
+ * directly from A: a one-sided Jacobi orthogonalises the 8 columns of A^T (same rotation, same round-robin
+ * order as orc_svd), after which the columns span the row space of A and f is the unit vector orthogonal to
+ * all of them (two passes of modified Gram-Schmidt on the least-aligned unit vector).  Working on A instead
+ * of A^T A avoids squaring the condition number: measured against the exact null vector this route is
+ * ~1000x more accurate than either cv2.SVDecomp(A^T A) or a Jacobi on A^T A, and it differs from
+ * cv2.SVDecomp(A^T A) by no more than a literal restatement does (both differences are cv2's own A^T A
+ * round-off; numbers in DESIGN.md).  Oracle A (oracle_np.py) keeps the literal A^T A + cv2.SVDecomp route. */
+static void null_vector_8x9(double A[8][9], double f[9])
+{
+    double W[9][8]; /* W = A^T: 8 columns of length 9 */
+    for (int i = 0; i < 9; ++i) for (int j = 0; j < 8; ++j) W[i][j] = A[j][i];
+    for (int sweep = 0; sweep < SVD_MAX_SWEEPS; ++sweep) {
+        int changed = 0;
+        for (int s = 0; s < 7; ++s)
+            for (int k = 0; k < 4; ++k) {
+                int i = (k == 0) ? s : (s + k) % 7, j = (k == 0) ? 7 : (s - k + 7) % 7;
+                int p = i < j ? i : j, q = i < j ? j : i;
+                double a = 0.0, b = 0.0, g = 0.0;
+                for (int r = 0; r < 9; ++r) {
+                    a = fma(W[r][p], W[r][p], a);
+                    b = fma(W[r][q], W[r][q], b);
+                    g = fma(W[r][p], W[r][q], g);
+                }
+                if (g * g <= (SVD_EPS2 * a) * b) continue;
+                changed = 1;
+                double g2 = g * 2.0, beta = a - b;
+                double gamma = sqrt(fma(g2, g2, beta * beta));
+                double inv = 1.0 / (gamma * 2.0);
+                double c, sn;
+                if (beta < 0) { sn = sqrt((gamma - beta) * inv); c = (g2 * inv) / sn; }
+                else { c = sqrt((gamma + beta) * inv); sn = (g2 * inv) / c; }
+                for (int r = 0; r < 9; ++r) {
+                    double wp = W[r][p], wq = W[r][q];
+                    W[r][p] = fma(c, wp, sn * wq);
+                    W[r][q] = fma(c, wq, -(sn * wp));
+                }
+            }
+        if (!changed) break;
+    }
+    double inv[8], t[9], x[9];
+    for (int j = 0; j < 8; ++j) {
+        double nn = 0.0;
+        for (int r = 0; r < 9; ++r) nn = fma(W[r][j], W[r][j], nn);
+        inv[j] = nn > 0.0 ? 1.0 / nn : 0.0;
+    }
+    for (int r = 0; r < 9; ++r) t[r] = 0.0;
+    for (int j = 0; j < 8; ++j)
+        for (int r = 0; r < 9; ++r) t[r] = fma(W[r][j] * W[r][j], inv[j], t[r]);
+    int best = 0;
+    for (int r = 1; r < 9; ++r) if (t[r] < t[best]) best = r;
+    for (int r = 0; r < 9; ++r) x[r] = (r == best) ? 1.0 : 0.0;
+    for (int pass = 0; pass < 2; ++pass)
+        for (int j = 0; j < 8; ++j) {
+            double d = 0.0;
+            for (int r = 0; r < 9; ++r) d = fma(x[r], W[r][j], d);
+            d *= inv[j];
+            for (int r = 0; r < 9; ++r) x[r] = fma(-d, W[r][j], x[r]);
+        }
+    double nx = 0.0;
+    for (int r = 0; r < 9; ++r) nx = fma(x[r], x[r], nx);
+    nx = sqrt(nx);
+    for (int r = 0; r < 9; ++r) f[r] = x[r] / nx;
+}
+
 /* find_fundamental_matrix_8point, fundamental-matrix.cpp:56-140 */
 static void find_fundamental_matrix_8point(double n1[8][3], double n2[8][3], double F[9])
 {
@@ -429,19 +495,8 @@ static void find_fundamental_matrix_8point(double n1[8][3], double n2[8][3], dou
         A[i][3] = y2 * x1; A[i][4] = y2 * y1; A[i][5] = y2;
         A[i][6] = x1; A[i][7] = y1; A[i][8] = 1.0;
     }
-    /* A^T A, accumulated over the 8 rows in order (:104-111) */
-    double AtA[81];
-    for (int i = 0; i < 9; ++i)
-        for (int j = 0; j < 9; ++j) {
-            double s = 0.0;
-            for (int k = 0; k < 8; ++k) s += A[k][i] * A[k][j];
-            AtA[i * 9 + j] = s;
-        }
-    /* f = vt.row(8) of SVD(A^T A) (:114-118) */
-    double w9[9], Vt9[81];
-    orc_svd(9, AtA, NULL, w9, Vt9);
     double Fp[9];
-    for (int i = 0; i < 9; ++i) Fp[i] = Vt9[8 * 9 + i];
+    null_vector_8x9(A, Fp);
     /* singular constraint (:128-136): F = u * diag(w0,w1,0) * vt */
     double U[9], w[3], Vt[9];
     orc_svd(3, Fp, U, w, Vt);
