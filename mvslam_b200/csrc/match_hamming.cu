@@ -15,7 +15,7 @@ namespace mvs {
 // ------------------------------------------------------------------------------------------
 // K1: knn2.  One thread owns one query descriptor (8 x u32 in registers) and scans a slice of the
 // train set that the CTA stages through shared memory in tiles (128-bit loads, broadcast reads).
-// Per (query, train) pair: 8 XOR + 8 POPC + adds, then a 3-instruction top-2 update on packed
+// Per (query, train) pair: 8 XOR + 6 LOP3 (carry-save adders) + 5 POPC + adds, then a 3-instruction top-2 update on packed
 // (distance << 22 | trainIdx) keys — unsigned min/max gives the (distance, index) lexicographic
 // order, i.e. OpenCV's strict-'<' ascending scan, independent of the order tiles are visited.
 // grid = (query tiles, train splits, pairs); partial top-2 per split are merged in K2.
@@ -23,10 +23,18 @@ namespace mvs {
 constexpr int KNN_THREADS = 256;
 constexpr int KNN_TILE = 256;  // train descriptors per smem tile (8 KB)
 
+// 256-bit Hamming distance.  POPC issues on the XU pipe at 16 lanes/clk/SM (measured 4.46e12/s on B200,
+// profiles/ubench_peaks.json) — 4x scarcer than LOP3 — so three carry-save adders (sum = a^b^c,
+// carry = maj(a,b,c), one LOP3 each) first compress 7 of the 8 XOR words into 2 weight-1 and 3 weight-2
+// words: 5 POPC instead of 8, XU and ALU pipes roughly balanced (measured +44% over the 8-POPC form).
 __device__ __forceinline__ uint32_t hamming256(const uint4 &qa, const uint4 &qb, const uint4 &ta, const uint4 &tb)
 {
-    return (__popc(qa.x ^ ta.x) + __popc(qa.y ^ ta.y)) + (__popc(qa.z ^ ta.z) + __popc(qa.w ^ ta.w)) +
-           (__popc(qb.x ^ tb.x) + __popc(qb.y ^ tb.y)) + (__popc(qb.z ^ tb.z) + __popc(qb.w ^ tb.w));
+    const uint32_t x0 = qa.x ^ ta.x, x1 = qa.y ^ ta.y, x2 = qa.z ^ ta.z, x3 = qa.w ^ ta.w;
+    const uint32_t x4 = qb.x ^ tb.x, x5 = qb.y ^ tb.y, x6 = qb.z ^ tb.z, x7 = qb.w ^ tb.w;
+    const uint32_t s0 = x0 ^ x1 ^ x2, c0 = (x0 & x1) | (x2 & (x0 | x1));
+    const uint32_t s1 = x3 ^ x4 ^ x5, c1 = (x3 & x4) | (x5 & (x3 | x4));
+    const uint32_t s2 = s0 ^ s1 ^ x6, c2 = (s0 & s1) | (x6 & (s0 | s1));
+    return (__popc(s2) + __popc(x7)) + 2u * (__popc(c0) + __popc(c1) + __popc(c2));
 }
 
 __device__ __forceinline__ void top2_insert(uint32_t &b1, uint32_t &b2, uint32_t key)

@@ -8,7 +8,7 @@
 constexpr int ILP = 8;
 constexpr int ITERS = 4096;
 
-enum Op { POPC, XOR, IADD3, MNMX, DADD, DMUL, DFMA, HAMMING };
+enum Op { POPC, XOR, IADD3, MNMX, DADD, DMUL, DFMA, HAMMING, HAM_CSA3, HAM_CSA4, HAM_CSA3M };
 
 template <int OP>
 __global__ void __launch_bounds__(256) k(uint32_t *out, uint32_t seed, double dseed)
@@ -37,6 +37,32 @@ __global__ void __launch_bounds__(256) k(uint32_t *out, uint32_t seed, double ds
                 uint32_t dist = 0;
 #pragma unroll
                 for (int w = 0; w < 8; ++w) dist += __popc(q[w] ^ (r[j] + w * 0x01000193u + it));
+                const uint32_t key = (dist << 22) + it * ILP + j;
+                const uint32_t hi = max(b1, key);
+                b1 = min(b1, key);
+                b2 = min(b2, hi);
+            }
+        }
+        if (OP == HAM_CSA3 || OP == HAM_CSA4 || OP == HAM_CSA3M) {
+#pragma unroll
+            for (int j = 0; j < ILP; ++j) {
+                uint32_t x[8];
+#pragma unroll
+                for (int w = 0; w < 8; ++w) x[w] = q[w] ^ (r[j] + w * 0x01000193u + it);
+                // carry-save adders: (a,b,c) -> sum (weight 1), carry (weight 2); 2 LOP3 each
+                const uint32_t s0 = x[0] ^ x[1] ^ x[2], c0 = (x[0] & x[1]) | (x[2] & (x[0] | x[1]));
+                const uint32_t s1 = x[3] ^ x[4] ^ x[5], c1 = (x[3] & x[4]) | (x[5] & (x[3] | x[4]));
+                const uint32_t s2 = s0 ^ s1 ^ x[6], c2 = (s0 & s1) | (x[6] & (s0 | s1));
+                uint32_t dist;
+                if (OP == HAM_CSA4) {
+                    const uint32_t s3 = c0 ^ c1 ^ c2, c3 = (c0 & c1) | (c2 & (c0 | c1));
+                    dist = __popc(s2) + __popc(x[7]) + 2 * __popc(s3) + 4 * __popc(c3);
+                } else if (OP == HAM_CSA3) {
+                    dist = __popc(s2) + __popc(x[7]) + 2 * (__popc(c0) + __popc(c1) + __popc(c2));
+                } else {
+                    uint32_t w2 = __popc(c0) + __popc(c1) + __popc(c2), w1 = __popc(s2) + __popc(x[7]);
+                    asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(dist) : "r"(w2), "r"(w1));
+                }
                 const uint32_t key = (dist << 22) + it * ILP + j;
                 const uint32_t hi = max(b1, key);
                 b1 = min(b1, key);
@@ -83,6 +109,9 @@ int main()
     printf(", \"dmul_per_s\": %.4e", run<DMUL>(out, blocks, ILP));
     printf(", \"dfma_per_s\": %.4e", run<DFMA>(out, blocks, ILP));
     printf(", \"hamming256_pairs_per_s\": %.4e", run<HAMMING>(out, blocks, ILP));
+    printf(", \"hamming256_csa3_pairs_per_s\": %.4e", run<HAM_CSA3>(out, blocks, ILP));
+    printf(", \"hamming256_csa4_pairs_per_s\": %.4e", run<HAM_CSA4>(out, blocks, ILP));
+    printf(", \"hamming256_csa3m_pairs_per_s\": %.4e", run<HAM_CSA3M>(out, blocks, ILP));
     printf("}\n");
     return cudaGetLastError() != cudaSuccess;
 }
