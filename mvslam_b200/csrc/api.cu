@@ -172,7 +172,7 @@ int run_geometry(mvs_ctx *ctx, int n_pairs, int p_stride, const RansacCfg &rc, b
     const int tiles = score_tiles(p_stride);
     CK(ctx->d_Fall.ensure((size_t)n_pairs * rc.H * 9 * sizeof(double)));
     CK(ctx->d_pc.ensure((size_t)n_pairs * tiles * rc.H * sizeof(uint32_t)));
-    CK(ctx->d_pr.ensure((size_t)n_pairs * tiles * rc.H * sizeof(double)));
+    CK(ctx->d_pr.ensure((size_t)n_pairs * rc.H * 2 * sizeof(int32_t)));
     CK(ctx->d_mask.ensure((size_t)n_pairs * p_stride));
     if (want_all_counts) CK(ctx->d_counts.ensure((size_t)n_pairs * rc.H * sizeof(int32_t)));
     PairState *state = ctx->d_state.as<PairState>();
@@ -187,14 +187,14 @@ int run_geometry(mvs_ctx *ctx, int n_pairs, int p_stride, const RansacCfg &rc, b
         StageTimer t(ctx, MVS_STAGE_SCORE);
         ScoreArgs a{};
         a.points = ctx->d_points.as<double>(); a.p_stride = p_stride; a.state = state; a.F_all = ctx->d_Fall.as<double>();
-        a.H = rc.H; a.max_error_sq = rc.thr; a.tiles = tiles; a.part_count = ctx->d_pc.as<uint32_t>(); a.part_res = ctx->d_pr.as<double>();
+        a.H = rc.H; a.max_error_sq = rc.thr; a.tiles = tiles; a.part_count = ctx->d_pc.as<uint32_t>();
         launch_score(a, rc.mode, unit_z, n_pairs, ctx->stream);
     }
     {
         StageTimer t(ctx, MVS_STAGE_SELECT);
         SelectArgs a{};
         a.points = ctx->d_points.as<double>(); a.p_stride = p_stride; a.state = state; a.F_all = ctx->d_Fall.as<double>();
-        a.H = rc.H; a.part_count = ctx->d_pc.as<uint32_t>(); a.part_res = ctx->d_pr.as<double>(); a.tiles = tiles;
+        a.H = rc.H; a.part_count = ctx->d_pc.as<uint32_t>(); a.ties = ctx->d_pr.as<int32_t>(); a.tiles = tiles;
         a.max_error_sq = rc.thr; a.min_inliers = rc.min_inl; a.decompose = decompose ? 1 : 0;
         a.mask = ctx->d_mask.as<uint8_t>(); a.all_counts = want_all_counts ? ctx->d_counts.as<int32_t>() : nullptr;
         launch_select(a, rc.mode, unit_z, n_pairs, ctx->stream);

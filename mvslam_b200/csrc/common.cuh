@@ -265,7 +265,7 @@ __device__ __forceinline__ void se3_inverse(const double R[9], const double t[3]
 // ALGEBRAIC: inlier iff |r| < thr, residual |r|.  SAMPSON: inlier iff r^2 < thr * den (den > 0, i.e.
 // r^2/den < thr without the division), residual r^2/den computed for inliers only.
 // UNIT_Z: both points have z == 1.0 exactly, so the multiplications by z are exact no-ops.
-template <bool UNIT_Z, int MODE>
+template <bool UNIT_Z, int MODE, bool WANT_RES = true>
 __device__ __forceinline__ bool point_residual(double x1, double y1, double z1, double x2, double y2, double z2,
                                                const double (&F)[9], double thr, double &res)
 {
@@ -296,7 +296,7 @@ __device__ __forceinline__ bool point_residual(double x1, double y1, double z1, 
     const double den = fma(l0, l0, l1 * l1) + fma(v0, v0, v1 * v1);
     const double r2 = r * r;
     if (!(r2 < thr * den)) return false;
-    res = r2 / den;
+    if (WANT_RES) res = r2 / den;
     return true;
 }
 

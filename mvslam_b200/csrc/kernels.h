@@ -54,14 +54,14 @@ struct ScoreArgs {
     double max_error_sq;
     int tiles;                 // point tiles per pair
     uint32_t *part_count;      // [pairs][tiles][H]
-    double *part_res;          // [pairs][tiles][H]
 };
 
 struct SelectArgs {
     const double *points; int p_stride;
     PairState *state; int n_fixed;
     const double *F_all; int H;
-    const uint32_t *part_count; const double *part_res; int tiles;
+    const uint32_t *part_count; int tiles;
+    int32_t *ties;             // scratch [pairs][2][H]: total counts, then the hypotheses sharing the best count
     double max_error_sq;
     int min_inliers;
     int decompose;             // 0: stop after the mask (mvs_ransac_fundamental)

@@ -272,8 +272,9 @@ fundamental_sets_kernel(const double *p1s, const double *p2s, int n_sets, double
 
 // ------------------------------------------------------------------------------------------
 // K4.  thread = hypothesis (F in registers), correspondences streamed through shared memory as
-// broadcast 128-bit reads; grid = (H/128, point tiles, pairs).  Each thread keeps a private
-// (count, residual) for its tile, summed over the tile's points in index order.
+// broadcast 128-bit reads; grid = (H/128, point tiles, pairs).  Each thread keeps a private inlier
+// count for its tile.  The residual sum only breaks ties between hypotheses with equal counts
+// (estimator-RANSAC.cpp:76-84), so it is evaluated in K5 for the tied leaders only.
 // ------------------------------------------------------------------------------------------
 constexpr int SC_THREADS = 128;
 constexpr int SC_TILE = 512;
@@ -311,7 +312,6 @@ score_kernel(ScoreArgs a)
     for (int i = 0; i < 9; ++i) F[i] = Fg[i];
     const double thr = a.max_error_sq;
     uint32_t c = 0;
-    double res = 0.0;
 #pragma unroll 4
     for (int i = 0; i < cnt; ++i) {
         double r;
@@ -319,18 +319,16 @@ score_kernel(ScoreArgs a)
         if (UNIT_Z) {
             const double2 u = *reinterpret_cast<const double2 *>(sp + 4 * i);
             const double2 v = *reinterpret_cast<const double2 *>(sp + 4 * i + 2);
-            in = point_residual<true, MODE>(u.x, u.y, 1.0, v.x, v.y, 1.0, F, thr, r);
+            in = point_residual<true, MODE, false>(u.x, u.y, 1.0, v.x, v.y, 1.0, F, thr, r);
         } else {
             const double2 u = *reinterpret_cast<const double2 *>(sp + 6 * i);
             const double2 v = *reinterpret_cast<const double2 *>(sp + 6 * i + 2);
             const double2 w = *reinterpret_cast<const double2 *>(sp + 6 * i + 4);
-            in = point_residual<false, MODE>(u.x, u.y, v.x, v.y, w.x, w.y, F, thr, r);
+            in = point_residual<false, MODE, false>(u.x, u.y, v.x, v.y, w.x, w.y, F, thr, r);
         }
-        if (in) { ++c; res += r; }
+        c += in ? 1u : 0u;
     }
-    const size_t o = ((size_t)pair * a.tiles + tile) * a.H + h;
-    a.part_count[o] = c;
-    a.part_res[o] = res;
+    a.part_count[((size_t)pair * a.tiles + tile) * a.H + h] = c;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -392,39 +390,93 @@ template <bool UNIT_Z, int MODE>
 __global__ void __launch_bounds__(SEL_THREADS)
 select_kernel(SelectArgs a)
 {
+    __shared__ uint32_t s_cnt[SEL_THREADS / 32];
     __shared__ Best s_best[SEL_THREADS / 32];
     __shared__ double s_F[9];
-    __shared__ int s_go;
+    __shared__ uint32_t s_max;
+    __shared__ int s_nties;
     const int pair = blockIdx.x;
     PairState *st = a.state + pair;
     if (st->status != MVS_OK) return;
     const int n = st->n_matches;
     const int tiles_used = (n + SC_TILE - 1) / SC_TILE;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double *pts = a.points + (size_t)pair * a.p_stride * 6;
+    int32_t *ties = a.ties + (size_t)pair * a.H * 2;   // [0,H): total counts, [H,2H): tie list
 
-    Best b; b.cnt = 0; b.res = kInfinity; b.h = 0x7FFFFFFF;
+    // ---- total inlier count of every hypothesis, block-wide maximum
+    uint32_t cmax = 0;
     for (int h = threadIdx.x; h < a.H; h += SEL_THREADS) {
-        Best x; x.cnt = 0; x.res = 0.0; x.h = h;
-        for (int t = 0; t < tiles_used; ++t) {
-            const size_t o = ((size_t)pair * a.tiles + t) * a.H + h;
-            x.cnt += a.part_count[o];
-            x.res += a.part_res[o];
-        }
-        if (a.all_counts) a.all_counts[(size_t)pair * a.H + h] = (int32_t)x.cnt;
-        if (better(x, b)) b = x;
+        uint32_t c = 0;
+        for (int t = 0; t < tiles_used; ++t) c += a.part_count[((size_t)pair * a.tiles + t) * a.H + h];
+        ties[h] = (int32_t)c;   // parked here until the tie list is built
+        if (a.all_counts) a.all_counts[(size_t)pair * a.H + h] = (int32_t)c;
+        cmax = max(cmax, c);
     }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        Best o;
-        o.cnt = __shfl_xor_sync(FULL, b.cnt, off);
-        o.res = __shfl_xor_sync(FULL, b.res, off);
-        o.h = __shfl_xor_sync(FULL, b.h, off);
-        if (better(o, b)) b = o;
-    }
-    if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = b;
+    cmax = __reduce_max_sync(FULL, cmax);
+    if (lane == 0) s_cnt[warp] = cmax;
+    if (threadIdx.x == 0) s_nties = 0;
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int w = 1; w < SEL_THREADS / 32; ++w)
-            if (better(s_best[w], b)) b = s_best[w];
+        uint32_t m = 0;
+        for (int w = 0; w < SEL_THREADS / 32; ++w) m = max(m, s_cnt[w]);
+        s_max = m;
+    }
+    __syncthreads();
+    cmax = s_max;
+
+    // ---- best-model rule (estimator-RANSAC.cpp:76-84): most inliers, then the smaller residual sum,
+    //      then the earlier hypothesis.  Only the hypotheses tied at the top need their residual sum.
+    Best b; b.cnt = cmax; b.res = kInfinity; b.h = 0x7FFFFFFF;
+    if (cmax == 0) {
+        if (threadIdx.x == 0) { b.res = 0.0; b.h = 0; s_best[0] = b; }   // every residual sum is 0: the first one wins
+        __syncthreads();
+    } else {
+        // list the tied hypotheses (any order: the comparator below is a total order)
+        int32_t *list = ties + a.H;
+        for (int h = threadIdx.x; h < a.H; h += SEL_THREADS)
+            if ((uint32_t)ties[h] == cmax) list[atomicAdd(&s_nties, 1)] = h;
+        __syncthreads();
+        const int nties = s_nties;
+        // L lanes cooperate on one tied hypothesis: L = 32 when ties are rare (noisy data), down to one
+        // thread per hypothesis when (almost) every hypothesis ties (noise-free data)
+        int L = 32;
+        while (L > 1 && nties * L > SEL_THREADS) L >>= 1;
+        const int sub = threadIdx.x & (L - 1);
+        double F[9];
+        for (int t = threadIdx.x / L; t < nties; t += SEL_THREADS / L) {
+            const int h = list[t];
+            const double *Fg = a.F_all + ((size_t)pair * a.H + h) * 9;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) F[i] = Fg[i];
+            double res = 0.0;
+            for (int i = sub; i < n; i += L) {
+                const double *p = pts + (size_t)i * 6;
+                double r;
+                if (point_residual<UNIT_Z, MODE>(p[0], p[1], p[2], p[3], p[4], p[5], F, a.max_error_sq, r)) res += r;
+            }
+            for (int off = L >> 1; off > 0; off >>= 1) res += __shfl_xor_sync(__activemask(), res, off);
+            Best x; x.cnt = cmax; x.res = res; x.h = h;
+            if (better(x, b)) b = x;
+        }
+        // fold the per-thread leaders of the warp
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            Best o;
+            o.cnt = cmax;
+            o.res = __shfl_xor_sync(FULL, b.res, off);
+            o.h = __shfl_xor_sync(FULL, b.h, off);
+            if (better(o, b)) b = o;
+        }
+        if (lane == 0) s_best[warp] = b;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (cmax != 0) {
+            b = s_best[0];
+            for (int w = 1; w < SEL_THREADS / 32; ++w)
+                if (better(s_best[w], b)) b = s_best[w];
+        } else b = s_best[0];
         st->best_h = b.h;
         st->n_inliers = (int)b.cnt;
         st->residual = b.res;
@@ -450,20 +502,17 @@ select_kernel(SelectArgs a)
         }
         st->tri_count[0] = st->tri_count[1] = st->tri_count[2] = st->tri_count[3] = 0;
         st->status = status;
-        s_go = 1;
     }
     __syncthreads();
-    (void)s_go;
     // inlier mask of the winner (estimator-RANSAC.cpp:112-127), same residual expression as K4
     double F[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) F[i] = s_F[i];
-    const double *pts = a.points + (size_t)pair * a.p_stride * 6;
     uint8_t *mask = a.mask + (size_t)pair * a.p_stride;
     for (int i = threadIdx.x; i < n; i += SEL_THREADS) {
         const double *p = pts + (size_t)i * 6;
         double r;
-        mask[i] = point_residual<UNIT_Z, MODE>(p[0], p[1], p[2], p[3], p[4], p[5], F, a.max_error_sq, r) ? 1 : 0;
+        mask[i] = point_residual<UNIT_Z, MODE, false>(p[0], p[1], p[2], p[3], p[4], p[5], F, a.max_error_sq, r) ? 1 : 0;
     }
 }
 
