@@ -1,0 +1,78 @@
+// visual-feature.hpp — VisualFeature with the reference's matching entry points
+// (reference source/vision/visual-feature.hpp:14-93), forwarding to the C ABI.
+#pragma once
+#include <utility>
+
+#include "types.hpp"
+
+namespace mvSLAM {
+
+class VisualFeature {
+public:
+    VisualFeature() = default;
+    /** keypoints + 32-byte descriptors as produced by cv::ORB (extraction stays on the host, outside the path) */
+    VisualFeature(VisualFeatureConfig::DetectorResultType kps, VisualFeatureConfig::ExtractorResultType desc,
+                  int image_width, int image_height)
+        : m_keypoints(std::move(kps)), m_descriptors(std::move(desc)), m_image_width(image_width), m_image_height(image_height)
+    {
+        if (m_descriptors.size() != m_keypoints.size() * 32) throw b200::Error(MVS_E_BAD_ARG, "descriptor rows must be 32 bytes");
+    }
+
+    /** Matches from 2 to 1 (query = vf2, train = vf1) sorted by ascending distance
+     *  (visual-feature.hpp:23-26, visual-feature.cpp:51-80); empty when nothing survives. */
+    static VisualFeatureConfig::MatchResultType match_visual_features(const VisualFeature &vf1, const VisualFeature &vf2,
+                                                                       ScalarType max_dist = -1)
+    {
+        if (!vf1.valid() || !vf2.valid()) throw b200::Error(MVS_E_BAD_ARG, "invalid VisualFeature");  // :56 assert
+        mvs_ctx *ctx = b200::Context::thread_default().get();
+        std::vector<mvs_match> out(vf2.size());
+        int n = 0;
+        const mvs_match_params mp{0.7, max_dist, 0, 0};
+        int st = mvs_match_hamming(ctx, vf2.m_descriptors.data(), (int)vf2.size(), vf1.m_descriptors.data(), (int)vf1.size(),
+                                   32, &mp, out.data(), (int)out.size(), &n);
+        b200::check(ctx, st, "match_visual_features");
+        VisualFeatureConfig::MatchResultType r(n);
+        for (int i = 0; i < n; ++i) { r[i].queryIdx = out[i].query; r[i].trainIdx = out[i].train; r[i].distance = out[i].distance; }
+        return r;
+    }
+
+    /** visual-feature.hpp:45-48 / visual-feature.cpp:93-119 (keypoints gathered; the reference's descriptor copy
+     *  is buggy (:115) and unused downstream, so descriptors are gathered correctly here). */
+    static std::pair<VisualFeature, VisualFeature> match_and_filter_visual_features(const VisualFeature &vf1,
+                                                                                     const VisualFeature &vf2,
+                                                                                     ScalarType max_dist = -1)
+    {
+        auto matches = match_visual_features(vf1, vf2, max_dist);
+        VisualFeature f1, f2;
+        f1.m_image_width = f2.m_image_width = vf1.m_image_width;
+        f1.m_image_height = f2.m_image_height = vf1.m_image_height;
+        for (const auto &m : matches) {
+            f1.m_keypoints.push_back(vf1.m_keypoints[m.trainIdx]);
+            f1.m_descriptors.insert(f1.m_descriptors.end(), vf1.m_descriptors.begin() + 32 * m.trainIdx,
+                                    vf1.m_descriptors.begin() + 32 * (m.trainIdx + 1));
+            f2.m_keypoints.push_back(vf2.m_keypoints[m.queryIdx]);
+            f2.m_descriptors.insert(f2.m_descriptors.end(), vf2.m_descriptors.begin() + 32 * m.queryIdx,
+                                    vf2.m_descriptors.begin() + 32 * (m.queryIdx + 1));
+        }
+        return std::make_pair(f1, f2);
+    }
+
+    size_t size() const { return m_keypoints.size(); }
+    const VisualFeatureConfig::DetectorResultType &get_keypoints() const { return m_keypoints; }
+    const VisualFeatureConfig::ExtractorResultType &get_descriptors() const { return m_descriptors; }
+    std::vector<ImagePoint> get_image_points() const   // visual-feature.cpp:179-190
+    {
+        std::vector<ImagePoint> r;
+        r.reserve(m_keypoints.size());
+        for (const auto &kp : m_keypoints) r.emplace_back(kp.pt.x, kp.pt.y);
+        return r;
+    }
+    bool valid() const { return size() > 0 && m_image_width > 0 && m_image_height > 0; }
+
+private:
+    VisualFeatureConfig::DetectorResultType m_keypoints;
+    VisualFeatureConfig::ExtractorResultType m_descriptors;
+    int m_image_width = -1, m_image_height = -1;
+};
+
+}  // namespace mvSLAM

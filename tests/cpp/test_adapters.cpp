@@ -1,0 +1,124 @@
+// C++ drop-in check: the reference's own synthetic-geometry tests (test/test-sfm.cpp sfm_triangulate_cube,
+// the L-shape rig of sfm_refine_L_shape fed to sfm_solve) and the ImagePair / matcher entry points, written
+// against the adapters in include/mvslam/ exactly the way the reference's tests call its functions.
+#include <cstdio>
+#include <algorithm>
+#include <cstdlib>
+#include <random>
+
+#include <mvslam/image-pair.hpp>
+
+using namespace mvSLAM;
+
+#define ASSERT_TRUE(c) do { if (!(c)) { std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #c); return false; } } while (0)
+#define ASSERT_EQUAL(a, b, tol) ASSERT_TRUE(std::fabs((a) - (b)) <= (tol))
+
+static std::vector<Point3> rig(bool cube)
+{
+    std::vector<Point3> p;
+    if (cube) { for (int x = -1; x <= 1; x += 2) for (int y = -1; y <= 1; y += 2) for (int z = -1; z <= 1; z += 2) p.emplace_back(x, y, z); }
+    else p = {{1, 0, 0}, {0, 0, 0}, {0, 2, 0}, {1, 0, 3}, {0, 0, 3}, {0, 2, 3}, {0.5, 0, 1.5}, {0, 1, 1.5}};
+    return p;
+}
+
+static void project(const std::vector<Point3> &P, double tx, std::vector<ImagePoint> &out)
+{   // K = I, camera at (tx, 0, 0), no rotation
+    out.clear();
+    for (auto &p : P) out.emplace_back((p[0] - tx) / p[2], p[1] / p[2]);
+}
+
+static bool sfm_triangulate_cube()   // test/test-sfm.cpp:92-155
+{
+    auto P = rig(true);
+    for (auto &p : P) { p[0] += 0.6; p[2] += 3.0; }
+    std::vector<ImagePoint> x1, x2;
+    project(P, 0.0, x1); project(P, 1.0, x2);
+    std::vector<Point3> pts; std::vector<size_t> idx;
+    sfm_triangulate(x1, x2, Matrix3Type::Identity(), SE3(), SE3(SO3(), Vector3Type(1, 0, 0)), pts, idx);
+    ASSERT_TRUE(pts.size() == P.size());
+    for (size_t i = 0; i < P.size(); ++i) for (int j = 0; j < 3; ++j) ASSERT_EQUAL(P[i][j], pts[i][j], 1e-3);
+    return true;
+}
+
+static bool sfm_solve_L_shape()      // rig of test/test-sfm.cpp:173-177, solved with the own 8-point branch
+{
+    const double roll = 1.5, pitch = 0.7;
+    const double cr = std::cos(roll), sr = std::sin(roll), cp = std::cos(pitch), sp = std::sin(pitch);
+    auto P = rig(false);
+    for (auto &p : P) {   // R = Ry(pitch) * Rx(roll), scale 0.5, t = (0.6, 0, 3)
+        double x = 0.5 * p[0], y = 0.5 * p[1], z = 0.5 * p[2];
+        double y1 = cr * y - sr * z, z1 = sr * y + cr * z;
+        p = Point3(cp * x + sp * z1 + 0.6, y1, -sp * x + cp * z1 + 3.0);
+    }
+    std::vector<ImagePoint> x1, x2;
+    project(P, 0.0, x1); project(P, 1.0, x2);
+    Transformation pose; std::vector<Point3> pts; std::vector<size_t> idx;
+    ASSERT_TRUE(sfm_solve(x1, x2, Matrix3Type::Identity(), pose, pts, idx));
+    ASSERT_EQUAL(pose.translation()[0], 1.0, 1e-3); ASSERT_EQUAL(pose.translation()[1], 0.0, 1e-3); ASSERT_EQUAL(pose.translation()[2], 0.0, 1e-3);
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) ASSERT_EQUAL(pose.rotation().get_matrix()(i, j), i == j ? 1.0 : 0.0, 1e-3);
+    ASSERT_TRUE(pts.size() == 8);
+    for (size_t i = 0; i < 8; ++i) for (int j = 0; j < 3; ++j) ASSERT_EQUAL(P[i][j], pts[i][j], 1e-3);
+    // too few points: false, outputs untouched
+    x1.resize(5); x2.resize(5);
+    Transformation keep = pose;
+    ASSERT_TRUE(!sfm_solve(x1, x2, Matrix3Type::Identity(), pose, pts, idx));
+    ASSERT_EQUAL(pose.translation()[0], keep.translation()[0], 0.0);
+    return true;
+}
+
+static bool image_pair_and_matcher()
+{
+    std::mt19937 rng(7);
+    const int n = 600;
+    // scene + two cameras (K = [500 0 320; 0 500 240]), descriptors = random 256 bit, pair frame permuted with bit noise
+    Matrix3Type K = Matrix3Type::Identity(); K(0, 0) = K(1, 1) = 500; K(0, 2) = 320; K(1, 2) = 240;
+    std::uniform_real_distribution<double> ux(-3, 3), uz(4, 10);
+    VisualFeatureConfig::DetectorResultType k1(n), k2(n);
+    VisualFeatureConfig::ExtractorResultType d1(n * 32), d2(n * 32);
+    std::vector<int> perm(n);
+    for (int i = 0; i < n; ++i) perm[i] = i;
+    std::shuffle(perm.begin(), perm.end(), rng);
+    for (int i = 0; i < n; ++i) {
+        double X = ux(rng), Y = ux(rng), Z = uz(rng);
+        k1[i].pt.x = (float)(500 * X / Z + 320); k1[i].pt.y = (float)(500 * Y / Z + 240);
+        int j = perm[i];
+        k2[j].pt.x = (float)(500 * (X - 0.5) / Z + 320); k2[j].pt.y = (float)(500 * Y / Z + 240);
+        for (int b = 0; b < 32; ++b) { d1[i * 32 + b] = (uint8_t)rng(); d2[j * 32 + b] = d1[i * 32 + b] ^ (uint8_t)(1u << (rng() % 8)) * (b % 11 == 0); }
+    }
+    auto f1 = std::make_shared<Frame>(); f1->id = 0; f1->visual_feature = VisualFeature(k1, d1, 640, 480);
+    auto f2 = std::make_shared<Frame>(); f2->id = 1; f2->visual_feature = VisualFeature(k2, d2, 640, 480);
+    auto matches = VisualFeature::match_visual_features(f1->visual_feature, f2->visual_feature, 10);
+    ASSERT_TRUE(matches.size() == (size_t)n);
+    for (size_t i = 0; i < matches.size(); ++i) {
+        ASSERT_TRUE(perm[matches[i].trainIdx] == matches[i].queryIdx);
+        if (i) ASSERT_TRUE(matches[i - 1].distance <= matches[i].distance);
+    }
+    auto both = VisualFeature::match_and_filter_visual_features(f1->visual_feature, f2->visual_feature, 10);
+    ASSERT_TRUE(both.first.size() == (size_t)n && both.second.size() == (size_t)n);
+    b200::ransac_defaults().n_hypotheses = 64;
+    b200::ransac_defaults().max_error_sq = 1e-6;      // float keypoints: ~1e-5 px noise
+    ImagePair ip(f1, f2, K, ImagePair::get_default_params());
+    ASSERT_TRUE(ip.valid);
+    ASSERT_TRUE(ip.match_inlier_count > (uint32_t)(0.9 * n));
+    ASSERT_EQUAL(ip.T_pair_to_base.translation()[0], 1.0, 1e-3);     // camera 2 sits at +x; |t| = 1
+    for (const auto &mp : ip.matched_points) ASSERT_TRUE(perm[mp.vf_idx_in_base] == (int)mp.vf_idx_in_pair);
+    auto batch = ImagePair::solve_batch({f1, f2}, {{0, 1}, {1, 0}}, K, ImagePair::get_default_params());
+    ASSERT_TRUE(batch.size() == 2 && batch[0].valid && batch[1].valid);
+    ASSERT_EQUAL(batch[1].T_pair_to_base.translation()[0], -1.0, 1e-3);
+    return true;
+}
+
+int main()
+{
+    int fails = 0;
+    struct { const char *name; bool (*fn)(); } tests[] = {{"sfm_triangulate_cube", sfm_triangulate_cube},
+                                                           {"sfm_solve_L_shape", sfm_solve_L_shape},
+                                                           {"image_pair_and_matcher", image_pair_and_matcher}};
+    for (auto &t : tests) {
+        bool ok = false;
+        try { ok = t.fn(); } catch (const std::exception &e) { std::printf("exception: %s\n", e.what()); }
+        std::printf("%s %s\n", ok ? "PASSED" : "FAILED", t.name);
+        fails += !ok;
+    }
+    return fails;
+}

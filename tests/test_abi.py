@@ -62,3 +62,16 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")) or f == "Makefile":
                 txt = open(os.path.join(dp, f)).read()
                 assert "oracle" not in txt.replace("the oracle", "").replace("CPU oracle", "").replace("oracle's", ""), f
+
+
+def test_cpp_adapters_compile_and_refuse_to_run_without_gpu():
+    import subprocess
+    import torch
+    exe = os.path.join(ROOT, "tests", "cpp", "test_adapters")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "test_adapters.cpp"), "-o", exe,
+                    "-L" + os.path.join(ROOT, "mvslam_b200"), "-lmvslam_b200", "-Wl,-rpath,$ORIGIN/../../mvslam_b200"],
+                   check=True)
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode != 0 and "no CPU fallback" in r.stdout
