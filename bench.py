@@ -202,7 +202,12 @@ def main():
     for _ in range(args.warmup):
         flush.zero_(); step(out_rec)
     torch.cuda.synchronize()
-    if world > 1:
+    if world > 1:   # warm the communicator: the first NCCL collective pays the lazy connection setup
+        w_mine = res_t.to("cuda")
+        w_bucket = [torch.empty_like(w_mine) for _ in range(world)] if rank == 0 else None
+        for _ in range(2):
+            dist.gather(w_mine, w_bucket, dst=0)
+        torch.cuda.synchronize()
         dist.barrier()
     torch.cuda.synchronize()
 

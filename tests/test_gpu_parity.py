@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 import mvslam_b200 as mvs
-from mvslam_b200 import synth
+from mvslam_b200 import shard, synth
 from oracle import cbind as orc
 
 pytestmark = pytest.mark.gpu
