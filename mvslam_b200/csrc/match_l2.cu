@@ -1,19 +1,634 @@
-// match_l2.cu — placeholder until the tcgen05 L2 matcher lands (see l2.h).
+// match_l2.cu — float-descriptor (NORM_L2) brute-force kNN(2) for BASELINE config 4 (SURF-style
+// 64-float descriptors, 32k x 32k): cv::BFMatcher(NORM_L2).knnMatch(k=2) semantics
+// (reference source/vision/visual-feature.cpp:59-62 with a float VisualFeatureConfig::MatcherNormType).
+//
+//   d^2(q,t) = |q|^2 + |t|^2 - 2 q.t : the contraction S = Q T^T runs on the 5th-gen tensor cores
+//   (tcgen05.mma kind::tf32, FP32 accumulators in TMEM, operands staged by TMA with 128B swizzle), the
+//   epilogue reads the accumulators back with tcgen05.ld and keeps the KC best columns of every row by
+//   the approximate score a = |t|^2 - 2 S; the 32k x 32k matrix is never materialised.
+//   A second kernel re-ranks the candidates with exact FP32 distances (sequential fmaf over the
+//   dimension) and proves per query that TF32 rounding cannot have hidden a true neighbour
+//   (kth-best approximate score - 2nd-best > 2 * error bound); the rare queries that fail the proof are
+//   recomputed by an exact brute-force kernel.  Result = exact FP32 top-2 with (distance, index) tie-break.
+//
+// Warp roles of the GEMM kernel (192 threads, 1 CTA per SM-resident tile of 128 queries):
+//   warp 0   TMA producer (A once, B tiles through a STAGES-deep mbarrier ring)
+//   warp 1   TMEM allocator + single-thread tcgen05.mma issuer, double-buffered accumulators
+//   warps 2-5 epilogue: thread <-> query row (TMEM lane), running top-KC in registers
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
 #include "l2.h"
 
 namespace mvs {
+
+namespace {
+
+constexpr int BM = 128;         // query rows per CTA  (UMMA M)
+constexpr int BN = 128;         // train rows per tile (UMMA N)
+constexpr int KSLAB = 32;       // floats per 128-byte swizzle slab
+constexpr int KC = 8;           // candidates kept per (row, split)
+constexpr int GEMM_THREADS = 192;
+constexpr uint32_t TMEM_COLS = 2 * BN;   // two accumulator buffers
+
+// ------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major operand, 128-byte swizzle, dense slab of [rows][128 B]: LBO = 16 B (unused for swizzled K-major),
+// SBO = 1024 B (8 rows x 128 B), descriptor version 1 (Blackwell), layout_type 2 = SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;                 // leading byte offset (>>4)
+    d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset (>>4)
+    d |= (uint64_t)1 << 46;                 // version
+    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    return d;
+}
+// kind::tf32, FP32 accumulate, A and B K-major, M = 128, N = BN
+constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(kInstrDesc), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------ small kernels
+__global__ void l2_norms_kernel(const float *x, int n, int ld, int dim, float *out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s = 0.f;
+    for (int k = 0; k < dim; ++k) s = fmaf(x[(size_t)i * ld + k], x[(size_t)i * ld + k], s);
+    out[i] = s;
+}
+
+__global__ void l2_pad_kernel(const float *src, int n, int dim, float *dst, int ld)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)n * ld) return;
+    const int r = (int)(i / ld), c = (int)(i % ld);
+    dst[i] = c < dim ? src[(size_t)r * dim + c] : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------ GEMM + top-KC
+template <int KSLABS, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+l2_gemm_topk_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapT,
+                    const float *__restrict__ t2, int nq, int nt, int tiles_per_split, int splits,
+                    float *__restrict__ cand_val, int32_t *__restrict__ cand_idx)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: A (KSLABS x 16 KB), B (STAGES x KSLABS x 16 KB), t2 tiles (2 x BN floats), barriers
+    uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = base;
+    uint8_t *sB = sA + KSLABS * BM * 128;
+    float *sT2 = (float *)(sB + STAGES * KSLABS * BN * 128);
+    uint64_t *bars = (uint64_t *)(sT2 + 2 * BN);
+    uint64_t *barA = bars, *full = bars + 1, *empty = full + STAGES, *tfull = empty + STAGES, *tempty = tfull + 2;
+    uint32_t *tmem_slot = (uint32_t *)(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * BM;
+    const int split = blockIdx.y;
+    const int tiles_total = (nt + BN - 1) / BN;
+    const int tile_begin = split * tiles_per_split;
+    const int tile_end = min(tiles_total, tile_begin + tiles_per_split);
+    const int n_tiles = max(0, tile_end - tile_begin);
+
+    if (threadIdx.x == 0) {
+        mbar_init(barA, 1);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0 && n_tiles > 0) {
+            mbar_expect_tx(barA, KSLABS * BM * 128);
+            for (int ks = 0; ks < KSLABS; ++ks) tma_load_2d(&mapQ, barA, sA + ks * BM * 128, ks * KSLAB, q0);
+            for (int i = 0; i < n_tiles; ++i) {
+                const int s = i % STAGES;
+                if (i >= STAGES) mbar_wait(empty + s, ((i / STAGES) - 1) & 1);
+                mbar_expect_tx(full + s, KSLABS * BN * 128);
+                for (int ks = 0; ks < KSLABS; ++ks)
+                    tma_load_2d(&mapT, full + s, sB + (s * KSLABS + ks) * BN * 128, ks * KSLAB, (tile_begin + i) * BN);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0 && n_tiles > 0) {
+            mbar_wait(barA, 0);
+            for (int i = 0; i < n_tiles; ++i) {
+                const int s = i % STAGES, acc = i & 1;
+                if (i >= 2) mbar_wait(tempty + acc, ((i >> 1) - 1) & 1);   // epilogue drained this accumulator
+                mbar_wait(full + s, (i / STAGES) & 1);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+#pragma unroll
+                for (int ks = 0; ks < KSLABS; ++ks) {
+                    const uint32_t a_addr = smem_u32(sA + ks * BM * 128);
+                    const uint32_t b_addr = smem_u32(sB + (s * KSLABS + ks) * BN * 128);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)   // UMMA_K = 8 tf32 = 32 bytes inside the 128-byte swizzle atom
+                        umma_tf32(d_tmem, make_smem_desc(a_addr + k * 32), make_smem_desc(b_addr + k * 32), (ks | k) ? 1u : 0u);
+                }
+                tcgen05_commit(empty + s);     // B stage reusable once these MMAs retire
+                tcgen05_commit(tfull + acc);   // accumulator ready for the epilogue
+            }
+        }
+    } else {
+        // ===== epilogue: thread <-> row =====
+        const int et = threadIdx.x - 64;                 // 0..127
+        const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
+        const int row = quarter * 32 + lane;             // row within the tile == TMEM lane
+        float val[KC];
+        int idx[KC];
+#pragma unroll
+        for (int i = 0; i < KC; ++i) { val[i] = CUDART_INF_F; idx[i] = -1; }
+        for (int i = 0; i < n_tiles; ++i) {
+            const int acc = i & 1;
+            const int col0 = (tile_begin + i) * BN;
+            // stage |t|^2 of this tile (+inf beyond nt so padded columns never win)
+            {
+                const int c = col0 + et;
+                sT2[acc * BN + et] = (c < nt) ? __ldg(t2 + c) : CUDART_INF_F;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(tfull + acc, (i >> 1) & 1);
+            tcgen05_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c0, v);
+                const float4 *tt = reinterpret_cast<const float4 *>(sT2 + acc * BN + c0);
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 t4 = tt[j4];
+                    const float tv[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int j = j4 * 4 + jj;
+                        const float a = fmaf(-2.f, __uint_as_float(v[j]), tv[jj]);
+                        if (a < val[KC - 1]) {
+                            val[KC - 1] = a; idx[KC - 1] = col0 + c0 + j;
+#pragma unroll
+                            for (int p = KC - 1; p > 0; --p)
+                                if (val[p] < val[p - 1]) {
+                                    const float tv2 = val[p]; val[p] = val[p - 1]; val[p - 1] = tv2;
+                                    const int ti = idx[p]; idx[p] = idx[p - 1]; idx[p - 1] = ti;
+                                }
+                        }
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            mbar_arrive(tempty + acc);
+        }
+        const int q = q0 + row;
+        if (q < nq) {
+            float *ov = cand_val + ((size_t)q * splits + split) * KC;
+            int32_t *oi = cand_idx + ((size_t)q * splits + split) * KC;
+#pragma unroll
+            for (int i = 0; i < KC; ++i) { ov[i] = val[i]; oi[i] = idx[i]; }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------ exact re-rank
+__device__ __forceinline__ float exact_d2(const float *__restrict__ q, const float *__restrict__ t, int dim)
+{
+    float s = 0.f;
+    for (int k = 0; k < dim; ++k) { const float e = q[k] - t[k]; s = fmaf(e, e, s); }
+    return s;
+}
+
+__device__ __forceinline__ unsigned long long key_of(float d2, int idx)
+{
+    return ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned int)idx;   // d2 >= 0: bit order == value order
+}
+
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long k)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, k, off);
+        k = o < k ? o : k;
+    }
+    return k;
+}
+
+// one warp per query: exact distances of the candidates, top-2 by (distance, index), TF32-safety proof
+__global__ void l2_rerank_kernel(const float *__restrict__ Q, const float *__restrict__ T, int ldq, int ldt, int dim,
+                                 const float *__restrict__ q2, float tmax, int nq, int nt, int splits,
+                                 const float *__restrict__ cand_val, const int32_t *__restrict__ cand_idx,
+                                 int32_t *__restrict__ out_idx, float *__restrict__ out_d2, uint8_t *__restrict__ flag)
+{
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const int nc = splits * KC;
+    unsigned long long b1 = ~0ull, b2 = ~0ull;
+    float a1 = CUDART_INF_F, a2 = CUDART_INF_F;       // two smallest approximate scores
+    float kth_min = CUDART_INF_F;                     // smallest "worst kept" score over the splits with a full list
+    for (int c = lane; c < nc; c += 32) {
+        const int id = cand_idx[(size_t)q * nc + c];
+        const float av = cand_val[(size_t)q * nc + c];
+        if ((c % KC) == KC - 1 && id >= 0) kth_min = fminf(kth_min, av);
+        if (id < 0) continue;
+        const unsigned long long k = key_of(exact_d2(Q + (size_t)q * ldq, T + (size_t)id * ldt, dim), id);
+        if (k < b1) { b2 = b1; b1 = k; } else if (k < b2) b2 = k;
+        if (av < a1) { a2 = a1; a1 = av; } else if (av < a2) a2 = av;
+    }
+    // warp top-2 of the exact keys (keys are unique: one train index lives in exactly one split)
+    const unsigned long long g1 = warp_min_u64(b1);
+    const unsigned long long mine2 = (b1 == g1) ? b2 : b1;
+    const unsigned long long g2 = warp_min_u64(mine2);
+    // warp 2nd-smallest approximate score
+    float m1 = a1;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m1 = fminf(m1, __shfl_xor_sync(0xFFFFFFFFu, m1, off));
+    const unsigned has = __ballot_sync(0xFFFFFFFFu, a1 == m1);
+    const int owner = __ffs(has) - 1;
+    float m2 = (lane == owner) ? a2 : a1;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        m2 = fminf(m2, __shfl_xor_sync(0xFFFFFFFFu, m2, off));
+        kth_min = fminf(kth_min, __shfl_xor_sync(0xFFFFFFFFu, kth_min, off));
+    }
+    if (lane == 0) {
+        // |S_tf32 - S| <= |q||t| 2^-9 (1+eps) (each operand keeps 10 mantissa bits), a = |t|^2 - 2S
+        const float qn = sqrtf(q2[q]);
+        const float E = qn * tmax * 0.0041f + 2e-6f * (tmax * tmax + 2.f * qn * tmax);
+        const bool proven = (kth_min - m2) > 2.f * E;     // kth_min = +inf: every column was kept
+        out_idx[2 * q] = (g1 == ~0ull) ? -1 : (int)(g1 & 0xFFFFFFFFu);
+        out_idx[2 * q + 1] = (g2 == ~0ull) ? -1 : (int)(g2 & 0xFFFFFFFFu);
+        out_d2[2 * q] = __uint_as_float((unsigned)(g1 >> 32));
+        out_d2[2 * q + 1] = __uint_as_float((unsigned)(g2 >> 32));
+        flag[q] = proven ? 0 : 1;
+    }
+}
+
+// exact brute force for the queries whose proof failed (one CTA per flagged query)
+__global__ void l2_fallback_kernel(const float *__restrict__ Q, const float *__restrict__ T, int ldq, int ldt, int dim,
+                                   int nt, const uint8_t *__restrict__ flag, int32_t *__restrict__ out_idx,
+                                   float *__restrict__ out_d2, unsigned int *__restrict__ n_fallback)
+{
+    const int q = blockIdx.x;
+    if (!flag[q]) return;
+    __shared__ unsigned long long s1[8], s2[8];
+    unsigned long long b1 = ~0ull, b2 = ~0ull;
+    for (int t = threadIdx.x; t < nt; t += blockDim.x) {
+        const unsigned long long k = key_of(exact_d2(Q + (size_t)q * ldq, T + (size_t)t * ldt, dim), t);
+        if (k < b1) { b2 = b1; b1 = k; } else if (k < b2) b2 = k;
+    }
+    const unsigned long long g1 = warp_min_u64(b1);
+    const unsigned long long g2 = warp_min_u64((b1 == g1) ? b2 : b1);
+    if ((threadIdx.x & 31) == 0) { s1[threadIdx.x >> 5] = g1; s2[threadIdx.x >> 5] = g2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long f1 = ~0ull, f2 = ~0ull;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+            const unsigned long long c[2] = {s1[w], s2[w]};
+            for (int j = 0; j < 2; ++j) { if (c[j] < f1) { f2 = f1; f1 = c[j]; } else if (c[j] < f2) f2 = c[j]; }
+        }
+        out_idx[2 * q] = (f1 == ~0ull) ? -1 : (int)(f1 & 0xFFFFFFFFu);
+        out_idx[2 * q + 1] = (f2 == ~0ull) ? -1 : (int)(f2 & 0xFFFFFFFFu);
+        out_d2[2 * q] = __uint_as_float((unsigned)(f1 >> 32));
+        out_d2[2 * q + 1] = __uint_as_float((unsigned)(f2 >> 32));
+        atomicAdd(n_fallback, 1u);
+    }
+}
+
+__global__ void l2_sqrt_kernel(const float *d2, int n, float *d)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) d[i] = sqrtf(d2[i]);
+}
+
+// Lowe ratio + max_dist (+ cross-check) on float distances, then sort by (distance, queryIdx); one CTA.
+// keys live in global memory (up to 2^22 queries); 64-bit key = distance bits << 32 | query.
+__global__ void __launch_bounds__(1024)
+l2_filter_sort_kernel(const int32_t *idx, const float *dist, int nq, double ratio, double max_dist,
+                      const int32_t *rev_idx, unsigned long long *keys, mvs_match *out, int32_t *n_out)
+{
+    __shared__ int s_count;
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+        const int i1 = idx[2 * q], i2 = idx[2 * q + 1];
+        if (i1 < 0 || i2 < 0) continue;
+        const double d1 = (double)dist[2 * q], d2 = (double)dist[2 * q + 1];
+        bool keep = (d1 < ratio * d2) && ((max_dist < 0) || (d1 <= max_dist));   // visual-feature.cpp:66-68
+        if (keep && rev_idx) keep = (rev_idx[2 * i1] == q);
+        if (keep) keys[atomicAdd(&s_count, 1)] = ((unsigned long long)__float_as_uint(dist[2 * q]) << 32) | (unsigned)q;
+    }
+    __syncthreads();
+    const int m = s_count;
+    int n2 = 1;
+    while (n2 < m) n2 <<= 1;
+    for (int i = m + threadIdx.x; i < n2; i += blockDim.x) keys[i] = ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= n2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const unsigned long long x = keys[i], y = keys[l];
+                    if ((x > y) == ((i & k) == 0)) { keys[i] = y; keys[l] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const int q = (int)(keys[i] & 0xFFFFFFFFu);
+        mvs_match mm;
+        mm.query = q; mm.train = idx[2 * q]; mm.distance = dist[2 * q];
+        out[i] = mm;
+    }
+    if (threadIdx.x == 0) *n_out = m;
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// [rows][ld] float matrix, box = 32 floats (one 128-byte swizzle slab) x box_rows; out-of-range rows read as zero
+bool make_map(CUtensorMap *m, const float *ptr, int rows, int ld, int kpad, int box_rows)
+{
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t gdim[2] = {(cuuint64_t)kpad, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)KSLAB, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)ptr, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+enum { B_Q = 0, B_T, B_NORM, B_CAND_V, B_CAND_I, B_OUT, B_MISC, B_KEYS };
+
+cudaError_t ensure(L2Workspace &ws, int i, size_t bytes)
+{
+    if (bytes <= ws.cap[i]) return cudaSuccess;
+    if (ws.buf[i]) cudaFree(ws.buf[i]);
+    ws.buf[i] = nullptr; ws.cap[i] = 0;
+    const size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&ws.buf[i], want);
+    if (e == cudaSuccess) ws.cap[i] = want;
+    return e;
+}
+
+template <int KSLABS>
+cudaError_t launch_gemm(const CUtensorMap &mq, const CUtensorMap &mt, const float *t2, int nq, int nt, int tiles_per_split,
+                        int splits, float *cv, int32_t *ci, cudaStream_t s)
+{
+    constexpr int STAGES = (KSLABS <= 2) ? 4 : 2;
+    const size_t smem = 1024 + (size_t)KSLABS * BM * 128 + (size_t)STAGES * KSLABS * BN * 128 + 2 * BN * sizeof(float) +
+                        (1 + 2 * STAGES + 4) * sizeof(uint64_t) + 16;
+    auto kern = l2_gemm_topk_kernel<KSLABS, STAGES>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid((nq + BM - 1) / BM, splits);
+    kern<<<grid, GEMM_THREADS, smem, s>>>(mq, mt, t2, nq, nt, tiles_per_split, splits, cv, ci);
+    return cudaGetLastError();
+}
+
+#define L2CK(call)                                                                     \
+    do {                                                                               \
+        cudaError_t e__ = (call);                                                      \
+        if (e__ != cudaSuccess) { err = std::string(#call) + ": " + cudaGetErrorString(e__); return MVS_E_CUDA; } \
+    } while (0)
+
+// train-dimension splits so that (query tiles x splits) covers the 148 SMs a few times over
+void plan_splits(int na, int nb, int &splits, int &tiles_per_split)
+{
+    const int tiles_total = (nb + BN - 1) / BN;
+    const int qtiles = (na + BM - 1) / BM;
+    splits = std::max(1, std::min(16, (148 * 4 + qtiles - 1) / qtiles));
+    splits = std::min(splits, std::max(1, tiles_total / 4));
+    tiles_per_split = (tiles_total + splits - 1) / splits;
+    splits = (tiles_total + tiles_per_split - 1) / tiles_per_split;
+}
+
+// tensor-core pass: top-KC candidates per (row of A, split of B) into ws.buf[B_CAND_V/B_CAND_I]
+int gemm_candidates(L2Workspace &ws, cudaStream_t stream, const float *dA, int na, const float *dB, int nb, int ld,
+                    int kpad, const float *d_normB, int splits, int tiles_per_split, std::string &err)
+{
+    L2CK(ensure(ws, B_CAND_V, (size_t)na * splits * KC * sizeof(float)));
+    L2CK(ensure(ws, B_CAND_I, (size_t)na * splits * KC * sizeof(int32_t)));
+    CUtensorMap mq, mt;
+    if (!make_map(&mq, dA, na, ld, kpad, BM) || !make_map(&mt, dB, nb, ld, kpad, BN)) {
+        err = "cuTensorMapEncodeTiled failed";
+        return MVS_E_CUDA;
+    }
+    float *cv = (float *)ws.buf[B_CAND_V];
+    int32_t *ci = (int32_t *)ws.buf[B_CAND_I];
+    cudaError_t e;
+    switch (kpad / KSLAB) {
+    case 1: e = launch_gemm<1>(mq, mt, d_normB, na, nb, tiles_per_split, splits, cv, ci, stream); break;
+    case 2: e = launch_gemm<2>(mq, mt, d_normB, na, nb, tiles_per_split, splits, cv, ci, stream); break;
+    case 3: e = launch_gemm<3>(mq, mt, d_normB, na, nb, tiles_per_split, splits, cv, ci, stream); break;
+    case 4: e = launch_gemm<4>(mq, mt, d_normB, na, nb, tiles_per_split, splits, cv, ci, stream); break;
+    default: err = "descriptor dimension above 128 floats"; return MVS_E_UNSUPPORTED;
+    }
+    L2CK(e);
+    return MVS_OK;
+}
+
+}  // namespace
 
 void L2Workspace::release()
 {
     for (int i = 0; i < 8; ++i) { if (buf[i]) cudaFree(buf[i]); buf[i] = nullptr; cap[i] = 0; }
 }
 
-int l2_knn2(L2Workspace &, cudaStream_t, const float *, int, const float *, int, int, int32_t *, float *,
-            const mvs_match_params *, mvs_match *, int, int *, int *n_launches, std::string &err)
+int l2_knn2(L2Workspace &ws, cudaStream_t stream, const float *query, int nq, const float *train, int nt, int dim,
+            int32_t *idx, float *dist, const mvs_match_params *mp, mvs_match *out, int capacity, int *n_out,
+            int *n_launches, std::string &err)
 {
+    int nl = 0;
     if (n_launches) *n_launches = 0;
-    err = "float L2 matcher not built yet";
-    return MVS_E_UNSUPPORTED;
+    if (n_out) *n_out = 0;
+    if (dim < 1 || dim > 128) { err = "float descriptors: 1 <= dim <= 128 supported"; return MVS_E_UNSUPPORTED; }
+    if (nq > (1 << 22) || nt > (1 << 22)) { err = "more than 2^22 descriptors per side"; return MVS_E_UNSUPPORTED; }
+    const int kpad = ((dim + KSLAB - 1) / KSLAB) * KSLAB;
+    const bool cross = mp && mp->cross_check;
+    // device copies (padded to a multiple of 32 floats per row when needed)
+    L2CK(ensure(ws, B_Q, (size_t)nq * kpad * sizeof(float) + (size_t)nq * dim * sizeof(float)));
+    L2CK(ensure(ws, B_T, (size_t)nt * kpad * sizeof(float) + (size_t)nt * dim * sizeof(float)));
+    float *dQ = (float *)ws.buf[B_Q], *dT = (float *)ws.buf[B_T];
+    if (kpad == dim) {
+        L2CK(cudaMemcpyAsync(dQ, query, (size_t)nq * dim * sizeof(float), cudaMemcpyHostToDevice, stream));
+        L2CK(cudaMemcpyAsync(dT, train, (size_t)nt * dim * sizeof(float), cudaMemcpyHostToDevice, stream));
+    } else {
+        float *rq = dQ + (size_t)nq * kpad, *rt = dT + (size_t)nt * kpad;
+        L2CK(cudaMemcpyAsync(rq, query, (size_t)nq * dim * sizeof(float), cudaMemcpyHostToDevice, stream));
+        L2CK(cudaMemcpyAsync(rt, train, (size_t)nt * dim * sizeof(float), cudaMemcpyHostToDevice, stream));
+        l2_pad_kernel<<<(unsigned)(((size_t)nq * kpad + 255) / 256), 256, 0, stream>>>(rq, nq, dim, dQ, kpad);
+        l2_pad_kernel<<<(unsigned)(((size_t)nt * kpad + 255) / 256), 256, 0, stream>>>(rt, nt, dim, dT, kpad);
+        nl += 2;
+    }
+    // norms, |t|max (host reduction of nt floats: part of the error bound, not of the distance computation)
+    L2CK(ensure(ws, B_NORM, ((size_t)nq + nt) * sizeof(float)));
+    float *nQ = (float *)ws.buf[B_NORM], *nT = nQ + nq;
+    l2_norms_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(dQ, nq, kpad, dim, nQ);
+    l2_norms_kernel<<<(nt + 255) / 256, 256, 0, stream>>>(dT, nt, kpad, dim, nT);
+    nl += 2;
+    std::vector<float> hn((size_t)nq + nt);
+    L2CK(cudaMemcpyAsync(hn.data(), nQ, hn.size() * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    L2CK(cudaStreamSynchronize(stream));
+    float qmax = 0.f, tmax = 0.f;
+    for (int i = 0; i < nq; ++i) qmax = std::max(qmax, hn[i]);
+    for (int i = 0; i < nt; ++i) tmax = std::max(tmax, hn[nq + i]);
+    qmax = std::sqrt(qmax); tmax = std::sqrt(tmax);
+
+    const int passes = cross ? 2 : 1;
+    // outputs: forward idx/d2/dist/flag, reverse idx/d2/flag
+    const size_t per_f = (size_t)nq * (2 * 4 + 2 * 4 + 2 * 4 + 1) + 64, per_r = (size_t)nt * (2 * 4 + 2 * 4 + 1) + 64;
+    L2CK(ensure(ws, B_OUT, per_f + per_r + 64));
+    uint8_t *ob = (uint8_t *)ws.buf[B_OUT];
+    int32_t *f_idx = (int32_t *)ob; float *f_d2 = (float *)(f_idx + 2 * (size_t)nq); float *f_dist = f_d2 + 2 * (size_t)nq;
+    uint8_t *f_flag = (uint8_t *)(f_dist + 2 * (size_t)nq);
+    uint8_t *rb = ob + ((per_f + 15) & ~(size_t)15);
+    int32_t *r_idx = (int32_t *)rb; float *r_d2 = (float *)(r_idx + 2 * (size_t)nt); uint8_t *r_flag = (uint8_t *)(r_d2 + 2 * (size_t)nt);
+    L2CK(ensure(ws, B_MISC, 64));
+    unsigned int *d_nfb = (unsigned int *)ws.buf[B_MISC];
+    int32_t *d_nout = (int32_t *)(d_nfb + 4);
+    L2CK(cudaMemsetAsync(d_nfb, 0, 64, stream));
+
+    for (int pass = 0; pass < passes; ++pass) {
+        const float *A = pass == 0 ? dQ : dT, *Bm = pass == 0 ? dT : dQ;
+        const int na = pass == 0 ? nq : nt, nb = pass == 0 ? nt : nq;
+        float *nA = pass == 0 ? nQ : nT, *nB = pass == 0 ? nT : nQ;
+        int32_t *o_idx = pass == 0 ? f_idx : r_idx; float *o_d2 = pass == 0 ? f_d2 : r_d2; uint8_t *o_flag = pass == 0 ? f_flag : r_flag;
+        const float bmax = pass == 0 ? tmax : qmax;
+        int splits, tps;
+        plan_splits(na, nb, splits, tps);
+        int st = gemm_candidates(ws, stream, A, na, Bm, nb, kpad, kpad, nB, splits, tps, err);
+        if (st != MVS_OK) return st;
+        nl += 1;
+        l2_rerank_kernel<<<(na + 7) / 8, 256, 0, stream>>>(A, Bm, kpad, kpad, dim, nA, bmax, na, nb, splits,
+                                                           (const float *)ws.buf[B_CAND_V], (const int32_t *)ws.buf[B_CAND_I],
+                                                           o_idx, o_d2, o_flag);
+        l2_fallback_kernel<<<na, 256, 0, stream>>>(A, Bm, kpad, kpad, dim, nb, o_flag, o_idx, o_d2, d_nfb + pass);
+        nl += 2;
+    }
+    l2_sqrt_kernel<<<(2 * nq + 255) / 256, 256, 0, stream>>>(f_d2, 2 * nq, f_dist);
+    nl += 1;
+    L2CK(cudaGetLastError());
+    if (idx) L2CK(cudaMemcpyAsync(idx, f_idx, (size_t)nq * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    if (dist) L2CK(cudaMemcpyAsync(dist, f_dist, (size_t)nq * 2 * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    if (mp && n_out) {
+        int n2 = 1;
+        while (n2 < nq) n2 <<= 1;
+        L2CK(ensure(ws, B_KEYS, (size_t)n2 * sizeof(unsigned long long) + (size_t)nq * sizeof(mvs_match)));
+        unsigned long long *keys = (unsigned long long *)ws.buf[B_KEYS];
+        mvs_match *dm = (mvs_match *)(keys + n2);
+        l2_filter_sort_kernel<<<1, 1024, 0, stream>>>(f_idx, f_dist, nq, mp->ratio, mp->max_dist, cross ? r_idx : nullptr, keys, dm, d_nout);
+        nl += 1;
+        L2CK(cudaGetLastError());
+        int32_t m = 0;
+        L2CK(cudaMemcpyAsync(&m, d_nout, sizeof(m), cudaMemcpyDeviceToHost, stream));
+        L2CK(cudaStreamSynchronize(stream));
+        *n_out = m;
+        if (m > capacity) { err = "match capacity too small"; return MVS_E_CAPACITY; }
+        if (m > 0) {
+            if (!out) { err = "null output"; return MVS_E_BAD_ARG; }
+            L2CK(cudaMemcpyAsync(out, dm, (size_t)m * sizeof(mvs_match), cudaMemcpyDeviceToHost, stream));
+        }
+    }
+    L2CK(cudaStreamSynchronize(stream));
+    if (n_launches) *n_launches = nl;
+    return MVS_OK;
 }
 
 }  // namespace mvs
