@@ -135,6 +135,10 @@ int mvs_knn2_l2(mvs_ctx *ctx, const float *query, int nq, const float *train, in
                 int32_t *idx, float *dist);
 int mvs_match_l2(mvs_ctx *ctx, const float *query, int nq, const float *train, int nt, int dim,
                  const mvs_match_params *params, mvs_match *out, int capacity, int *n_out);
+/* Diagnostics of the last L2 call: out[0] = queries whose TF32-safety proof failed and were recomputed by the
+ * exact brute-force kernel (forward pass), out[1] = same for the cross-check pass, out[2] = device time of the
+ * tensor-core kernel(s) in microseconds, out[3] = device time of the whole call in microseconds. */
+int mvs_l2_stats(const mvs_ctx *ctx, uint64_t out[4]);
 
 /* ---- geometry --------------------------------------------------------------------------- */
 /* find_fundamental_matrix (source/vision/fundamental-matrix.cpp:204-267, decl fundamental-matrix.hpp:16-19)

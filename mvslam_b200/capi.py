@@ -184,6 +184,11 @@ class Context:
                                          _p(out), out.shape[0], C.byref(n)))
         return out[:n.value].copy()
 
+    def l2_stats(self):
+        out = (C.c_uint64 * 4)()
+        self._check(self._L.mvs_l2_stats(self._h, out))
+        return dict(fallback_fwd=int(out[0]), fallback_rev=int(out[1]), gemm_us=int(out[2]), total_us=int(out[3]))
+
     # ---- geometry
     def find_fundamental_matrix(self, p1s, p2s):
         p1s = _f64(p1s).reshape(-1, 8, 3); p2s = _f64(p2s).reshape(-1, 8, 3)

@@ -470,6 +470,13 @@ int mvs_match_l2(mvs_ctx *ctx, const float *query, int nq, const float *train, i
     return st;
 }
 
+int mvs_l2_stats(const mvs_ctx *ctx, uint64_t out[4])
+{
+    if (!ctx || !out) return MVS_E_BAD_ARG;
+    for (int i = 0; i < 4; ++i) out[i] = ctx->l2.stats[i];
+    return MVS_OK;
+}
+
 // ------------------------------------------------------------------------------------------ geometry
 int mvs_find_fundamental_matrix(mvs_ctx *ctx, const double *p1s, const double *p2s, int n_sets, double *F_out)
 {

@@ -11,6 +11,8 @@ namespace mvs {
 struct L2Workspace {
     void *buf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint64_t stats[4] = {0, 0, 0, 0};     // fallbacks fwd, fallbacks rev, gemm us, total us
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     void release();
 };
 

@@ -4,17 +4,20 @@
 //
 //   d^2(q,t) = |q|^2 + |t|^2 - 2 q.t : the contraction S = Q T^T runs on the 5th-gen tensor cores
 //   (tcgen05.mma kind::tf32, FP32 accumulators in TMEM, operands staged by TMA with 128B swizzle), the
-//   epilogue reads the accumulators back with tcgen05.ld and keeps the KC best columns of every row by
-//   the approximate score a = |t|^2 - 2 S; the 32k x 32k matrix is never materialised.
-//   A second kernel re-ranks the candidates with exact FP32 distances (sequential fmaf over the
-//   dimension) and proves per query that TF32 rounding cannot have hidden a true neighbour
-//   (kth-best approximate score - 2nd-best > 2 * error bound); the rare queries that fail the proof are
-//   recomputed by an exact brute-force kernel.  Result = exact FP32 top-2 with (distance, index) tie-break.
+//   epilogue reads the accumulators back with tcgen05.ld and streams the approximate scores
+//   a = |t|^2 - 2 S through a running (best, second-best) pair per row; every column whose score is within
+//   2E of the running second-best is appended to the row's candidate list, E being a rigorous bound of the
+//   TF32 rounding error of a (|S_tf32 - S| <= |q||t| 2^-9).  The 32k x 32k matrix is never materialised.
+//   Any column that is NOT listed is therefore provably farther than both of the two approximately-best
+//   columns, so the exact top-2 is inside the list: a second kernel re-ranks the listed columns with exact
+//   FP32 distances (sequential fmaf over the dimension), (distance, index) tie-break.  Only a list
+//   overflow (heavily duplicated data) sends a query to the exact brute-force kernel.
 //
-// Warp roles of the GEMM kernel (192 threads, 1 CTA per SM-resident tile of 128 queries):
+// Warp roles of the GEMM kernel (320 threads, 1 CTA per SM-resident tile of 128 queries):
 //   warp 0   TMA producer (A once, B tiles through a STAGES-deep mbarrier ring)
 //   warp 1   TMEM allocator + single-thread tcgen05.mma issuer, double-buffered accumulators
-//   warps 2-5 epilogue: thread <-> query row (TMEM lane), running top-KC in registers
+//   warps 2-9 epilogue: thread <-> query row (TMEM lane) x half of the tile's columns; a 32-column chunk
+//             costs 32 FFMA + a min tree + one warp vote unless some lane has a column to list
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -33,8 +36,9 @@ namespace {
 constexpr int BM = 128;         // query rows per CTA  (UMMA M)
 constexpr int BN = 128;         // train rows per tile (UMMA N)
 constexpr int KSLAB = 32;       // floats per 128-byte swizzle slab
-constexpr int KC = 8;           // candidates kept per (row, split)
-constexpr int GEMM_THREADS = 192;
+constexpr int KC = 48;          // candidate slots per (row, split, column-half) list
+constexpr int EPI_WARPS = 8;         // two per TMEM lane quarter: each takes half of a tile's columns
+constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
 constexpr uint32_t TMEM_COLS = 2 * BN;   // two accumulator buffers
 
 // ------------------------------------------------------------------------------------------ PTX helpers
@@ -112,10 +116,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
 }
 
 // ------------------------------------------------------------------------------------------ small kernels
-__global__ void l2_norms_kernel(const float *x, int n, int ld, int dim, float *out)
+__global__ void l2_norms_kernel(const float *x, int n, int n_padded, int ld, int dim, float *out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= n_padded) return;
+    if (i >= n) { out[i] = CUDART_INF_F; return; }
     float s = 0.f;
     for (int k = 0; k < dim; ++k) s = fmaf(x[(size_t)i * ld + k], x[(size_t)i * ld + k], s);
     out[i] = s;
@@ -133,16 +138,16 @@ __global__ void l2_pad_kernel(const float *src, int n, int dim, float *dst, int 
 template <int KSLABS, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 l2_gemm_topk_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapT,
-                    const float *__restrict__ t2, int nq, int nt, int tiles_per_split, int splits,
-                    float *__restrict__ cand_val, int32_t *__restrict__ cand_idx)
+                    const float *__restrict__ t2 /* padded with +inf to a multiple of BN */,
+                    const float *__restrict__ q2, float tmax, int nq, int nt, int tiles_per_split, int splits,
+                    float *__restrict__ cand_val, int32_t *__restrict__ cand_idx, int32_t *__restrict__ cand_cnt)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: A (KSLABS x 16 KB), B (STAGES x KSLABS x 16 KB), t2 tiles (2 x BN floats), barriers
     uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = base;
     uint8_t *sB = sA + KSLABS * BM * 128;
-    float *sT2 = (float *)(sB + STAGES * KSLABS * BN * 128);
-    uint64_t *bars = (uint64_t *)(sT2 + 2 * BN);
+    uint64_t *bars = (uint64_t *)(sB + STAGES * KSLABS * BN * 128);
     uint64_t *barA = bars, *full = bars + 1, *empty = full + STAGES, *tfull = empty + STAGES, *tempty = tfull + 2;
     uint32_t *tmem_slot = (uint32_t *)(tempty + 2);
 
@@ -157,7 +162,7 @@ l2_gemm_topk_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
     if (threadIdx.x == 0) {
         mbar_init(barA, 1);
         for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 128); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, EPI_WARPS * 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -205,47 +210,58 @@ l2_gemm_topk_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
             }
         }
     } else {
-        // ===== epilogue: thread <-> row =====
-        const int et = threadIdx.x - 64;                 // 0..127
+        // ===== epilogue: thread <-> (row, column half) =====
         const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;                // which 64 columns of every 128-column tile
         const int row = quarter * 32 + lane;             // row within the tile == TMEM lane
-        float val[KC];
-        int idx[KC];
-#pragma unroll
-        for (int i = 0; i < KC; ++i) { val[i] = CUDART_INF_F; idx[i] = -1; }
+        const int q = q0 + row;
+        const size_t list = ((size_t)min(q, nq - 1) * splits + split) * 2 + half;
+        float *lv = cand_val + list * KC;
+        int32_t *li = cand_idx + list * KC;
+        // error bound of a = |t|^2 - 2 S_tf32: each operand keeps 10 mantissa bits
+        const float qn = sqrtf(q2[min(q, nq - 1)]);
+        const float twoE = 2.f * (qn * tmax * 0.0041f + 2e-6f * (tmax * tmax + 2.f * qn * tmax));
+        // rows beyond nq (zero-filled by TMA) never list anything: their threshold is -inf
+        float b1 = CUDART_INF_F, b2 = CUDART_INF_F, thr = (q < nq) ? CUDART_INF_F : -CUDART_INF_F;
+        int cnt = 0;
         for (int i = 0; i < n_tiles; ++i) {
             const int acc = i & 1;
-            const int col0 = (tile_begin + i) * BN;
-            // stage |t|^2 of this tile (+inf beyond nt so padded columns never win)
-            {
-                const int c = col0 + et;
-                sT2[acc * BN + et] = (c < nt) ? __ldg(t2 + c) : CUDART_INF_F;
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int col0 = (tile_begin + i) * BN + half * (BN / 2);
             mbar_wait(tfull + acc, (i >> 1) & 1);
             tcgen05_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = 0; c0 < BN / 2; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(taddr + c0, v);
-                const float4 *tt = reinterpret_cast<const float4 *>(sT2 + acc * BN + c0);
+                const float4 *tt = reinterpret_cast<const float4 *>(t2 + col0 + c0);   // same address in every lane
+                float a[32], m4[8];
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
-                    const float4 t4 = tt[j4];
-                    const float tv[4] = {t4.x, t4.y, t4.z, t4.w};
+                    const float4 t4 = __ldg(tt + j4);
+                    a[4 * j4 + 0] = fmaf(-2.f, __uint_as_float(v[4 * j4 + 0]), t4.x);
+                    a[4 * j4 + 1] = fmaf(-2.f, __uint_as_float(v[4 * j4 + 1]), t4.y);
+                    a[4 * j4 + 2] = fmaf(-2.f, __uint_as_float(v[4 * j4 + 2]), t4.z);
+                    a[4 * j4 + 3] = fmaf(-2.f, __uint_as_float(v[4 * j4 + 3]), t4.w);
+                    m4[j4] = fminf(fminf(a[4 * j4], a[4 * j4 + 1]), fminf(a[4 * j4 + 2], a[4 * j4 + 3]));
+                }
+                const float m = fminf(fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3])), fminf(fminf(m4[4], m4[5]), fminf(m4[6], m4[7])));
+                if (__any_sync(0xFFFFFFFFu, m <= thr)) {
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const int j = j4 * 4 + jj;
-                        const float a = fmaf(-2.f, __uint_as_float(v[j]), tv[jj]);
-                        if (a < val[KC - 1]) {
-                            val[KC - 1] = a; idx[KC - 1] = col0 + c0 + j;
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        if (m4[j4] <= thr) {
 #pragma unroll
-                            for (int p = KC - 1; p > 0; --p)
-                                if (val[p] < val[p - 1]) {
-                                    const float tv2 = val[p]; val[p] = val[p - 1]; val[p - 1] = tv2;
-                                    const int ti = idx[p]; idx[p] = idx[p - 1]; idx[p - 1] = ti;
+                            for (int jj = 0; jj < 4; ++jj) {
+                                const float av = a[4 * j4 + jj];
+                                if (av <= thr) {
+                                    if (cnt < KC) { lv[cnt] = av; li[cnt] = col0 + c0 + 4 * j4 + jj; }
+                                    ++cnt;
+                                    const float hi = fmaxf(b1, av);
+                                    b1 = fminf(b1, av);
+                                    b2 = fminf(b2, hi);
+                                    thr = b2 + twoE;
                                 }
+                            }
                         }
                     }
                 }
@@ -253,13 +269,7 @@ l2_gemm_topk_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
             tcgen05_fence_before();
             mbar_arrive(tempty + acc);
         }
-        const int q = q0 + row;
-        if (q < nq) {
-            float *ov = cand_val + ((size_t)q * splits + split) * KC;
-            int32_t *oi = cand_idx + ((size_t)q * splits + split) * KC;
-#pragma unroll
-            for (int i = 0; i < KC; ++i) { ov[i] = val[i]; oi[i] = idx[i]; }
-        }
+        if (q < nq) cand_cnt[list] = cnt;
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -292,58 +302,61 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long k)
     return k;
 }
 
-// one warp per query: exact distances of the candidates, top-2 by (distance, index), TF32-safety proof
+// one warp per query: lists -> global second-best approximate score a2 -> exact distances of the entries
+// with a <= a2 + 2E -> top-2 by (distance, index).  A list that overflowed flags the query for the exact kernel.
 __global__ void l2_rerank_kernel(const float *__restrict__ Q, const float *__restrict__ T, int ldq, int ldt, int dim,
-                                 const float *__restrict__ q2, float tmax, int nq, int nt, int splits,
+                                 const float *__restrict__ q2, float tmax, int nq, int nt, int lists,
                                  const float *__restrict__ cand_val, const int32_t *__restrict__ cand_idx,
+                                 const int32_t *__restrict__ cand_cnt,
                                  int32_t *__restrict__ out_idx, float *__restrict__ out_d2, uint8_t *__restrict__ flag)
 {
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (q >= nq) return;
-    const int nc = splits * KC;
-    unsigned long long b1 = ~0ull, b2 = ~0ull;
-    float a1 = CUDART_INF_F, a2 = CUDART_INF_F;       // two smallest approximate scores
-    float kth_min = CUDART_INF_F;                     // smallest "worst kept" score over the splits with a full list
-    for (int c = lane; c < nc; c += 32) {
-        const int id = cand_idx[(size_t)q * nc + c];
-        const float av = cand_val[(size_t)q * nc + c];
-        if ((c % KC) == KC - 1 && id >= 0) kth_min = fminf(kth_min, av);
-        if (id < 0) continue;
-        const unsigned long long k = key_of(exact_d2(Q + (size_t)q * ldq, T + (size_t)id * ldt, dim), id);
-        if (k < b1) { b2 = b1; b1 = k; } else if (k < b2) b2 = k;
-        if (av < a1) { a2 = a1; a1 = av; } else if (av < a2) a2 = av;
+    const float qn = sqrtf(q2[q]);
+    const float twoE = 2.f * (qn * tmax * 0.0041f + 2e-6f * (tmax * tmax + 2.f * qn * tmax));
+    bool overflow = false;
+    float a1 = CUDART_INF_F, a2 = CUDART_INF_F;
+    for (int l = 0; l < lists; ++l) {
+        const int c = cand_cnt[(size_t)q * lists + l];
+        overflow |= c > KC;
+        for (int e = lane; e < min(c, KC); e += 32) {
+            const float av = cand_val[((size_t)q * lists + l) * KC + e];
+            if (av < a1) { a2 = a1; a1 = av; } else if (av < a2) a2 = av;
+        }
     }
-    // warp top-2 of the exact keys (keys are unique: one train index lives in exactly one split)
-    const unsigned long long g1 = warp_min_u64(b1);
-    const unsigned long long mine2 = (b1 == g1) ? b2 : b1;
-    const unsigned long long g2 = warp_min_u64(mine2);
-    // warp 2nd-smallest approximate score
+    // warp-wide second smallest approximate score
     float m1 = a1;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) m1 = fminf(m1, __shfl_xor_sync(0xFFFFFFFFu, m1, off));
-    const unsigned has = __ballot_sync(0xFFFFFFFFu, a1 == m1);
-    const int owner = __ffs(has) - 1;
+    const int owner = __ffs(__ballot_sync(0xFFFFFFFFu, a1 == m1)) - 1;
     float m2 = (lane == owner) ? a2 : a1;
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        m2 = fminf(m2, __shfl_xor_sync(0xFFFFFFFFu, m2, off));
-        kth_min = fminf(kth_min, __shfl_xor_sync(0xFFFFFFFFu, kth_min, off));
+    for (int off = 16; off > 0; off >>= 1) m2 = fminf(m2, __shfl_xor_sync(0xFFFFFFFFu, m2, off));
+    const float keep = m2 + twoE;
+    unsigned long long b1 = ~0ull, b2 = ~0ull;
+    for (int l = 0; l < lists; ++l) {
+        const int c = min(cand_cnt[(size_t)q * lists + l], KC);
+        for (int e = lane; e < c; e += 32) {
+            const size_t o = ((size_t)q * lists + l) * KC + e;
+            if (!(cand_val[o] <= keep)) continue;
+            const int id = cand_idx[o];
+            const unsigned long long k = key_of(exact_d2(Q + (size_t)q * ldq, T + (size_t)id * ldt, dim), id);
+            if (k < b1) { b2 = b1; b1 = k; } else if (k < b2) b2 = k;
+        }
     }
+    const unsigned long long g1 = warp_min_u64(b1);
+    const unsigned long long g2 = warp_min_u64((b1 == g1) ? b2 : b1);
     if (lane == 0) {
-        // |S_tf32 - S| <= |q||t| 2^-9 (1+eps) (each operand keeps 10 mantissa bits), a = |t|^2 - 2S
-        const float qn = sqrtf(q2[q]);
-        const float E = qn * tmax * 0.0041f + 2e-6f * (tmax * tmax + 2.f * qn * tmax);
-        const bool proven = (kth_min - m2) > 2.f * E;     // kth_min = +inf: every column was kept
         out_idx[2 * q] = (g1 == ~0ull) ? -1 : (int)(g1 & 0xFFFFFFFFu);
         out_idx[2 * q + 1] = (g2 == ~0ull) ? -1 : (int)(g2 & 0xFFFFFFFFu);
         out_d2[2 * q] = __uint_as_float((unsigned)(g1 >> 32));
         out_d2[2 * q + 1] = __uint_as_float((unsigned)(g2 >> 32));
-        flag[q] = proven ? 0 : 1;
+        flag[q] = overflow ? 1 : 0;
     }
 }
 
-// exact brute force for the queries whose proof failed (one CTA per flagged query)
+// exact brute force for the queries whose candidate list overflowed (one CTA per flagged query)
 __global__ void l2_fallback_kernel(const float *__restrict__ Q, const float *__restrict__ T, int ldq, int ldt, int dim,
                                    int nt, const uint8_t *__restrict__ flag, int32_t *__restrict__ out_idx,
                                    float *__restrict__ out_d2, unsigned int *__restrict__ n_fallback)
@@ -468,17 +481,17 @@ cudaError_t ensure(L2Workspace &ws, int i, size_t bytes)
 }
 
 template <int KSLABS>
-cudaError_t launch_gemm(const CUtensorMap &mq, const CUtensorMap &mt, const float *t2, int nq, int nt, int tiles_per_split,
-                        int splits, float *cv, int32_t *ci, cudaStream_t s)
+cudaError_t launch_gemm(const CUtensorMap &mq, const CUtensorMap &mt, const float *t2, const float *q2, float tmax, int nq,
+                        int nt, int tiles_per_split, int splits, float *cv, int32_t *ci, int32_t *cc, cudaStream_t s)
 {
     constexpr int STAGES = (KSLABS <= 2) ? 4 : 2;
-    const size_t smem = 1024 + (size_t)KSLABS * BM * 128 + (size_t)STAGES * KSLABS * BN * 128 + 2 * BN * sizeof(float) +
+    const size_t smem = 1024 + (size_t)KSLABS * BM * 128 + (size_t)STAGES * KSLABS * BN * 128 +
                         (1 + 2 * STAGES + 4) * sizeof(uint64_t) + 16;
     auto kern = l2_gemm_topk_kernel<KSLABS, STAGES>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((nq + BM - 1) / BM, splits);
-    kern<<<grid, GEMM_THREADS, smem, s>>>(mq, mt, t2, nq, nt, tiles_per_split, splits, cv, ci);
+    kern<<<grid, GEMM_THREADS, smem, s>>>(mq, mt, t2, q2, tmax, nq, nt, tiles_per_split, splits, cv, ci, cc);
     return cudaGetLastError();
 }
 
@@ -488,23 +501,31 @@ cudaError_t launch_gemm(const CUtensorMap &mq, const CUtensorMap &mt, const floa
         if (e__ != cudaSuccess) { err = std::string(#call) + ": " + cudaGetErrorString(e__); return MVS_E_CUDA; } \
     } while (0)
 
-// train-dimension splits so that (query tiles x splits) covers the 148 SMs a few times over
+// train-dimension splits: fill the 148 SMs in balanced waves (1 CTA per SM), as few splits as possible
+// because every split restarts the per-row candidate stream
 void plan_splits(int na, int nb, int &splits, int &tiles_per_split)
 {
     const int tiles_total = (nb + BN - 1) / BN;
     const int qtiles = (na + BM - 1) / BM;
-    splits = std::max(1, std::min(16, (148 * 4 + qtiles - 1) / qtiles));
-    splits = std::min(splits, std::max(1, tiles_total / 4));
+    const int smax = std::max(1, std::min(8, tiles_total / 8));
+    double best_eff = -1.0;
+    splits = 1;
+    for (int s = 1; s <= smax; ++s) {
+        const long ctas = (long)qtiles * s;
+        const double eff = (double)ctas / (double)(((ctas + 147) / 148) * 148);
+        if (eff > best_eff + 0.02) { best_eff = eff; splits = s; }
+    }
     tiles_per_split = (tiles_total + splits - 1) / splits;
     splits = (tiles_total + tiles_per_split - 1) / tiles_per_split;
 }
 
 // tensor-core pass: top-KC candidates per (row of A, split of B) into ws.buf[B_CAND_V/B_CAND_I]
 int gemm_candidates(L2Workspace &ws, cudaStream_t stream, const float *dA, int na, const float *dB, int nb, int ld,
-                    int kpad, const float *d_normB, int splits, int tiles_per_split, std::string &err)
+                    int kpad, const float *d_normB, const float *d_normA, float bmax, int splits, int tiles_per_split,
+                    std::string &err)
 {
-    L2CK(ensure(ws, B_CAND_V, (size_t)na * splits * KC * sizeof(float)));
-    L2CK(ensure(ws, B_CAND_I, (size_t)na * splits * KC * sizeof(int32_t)));
+    L2CK(ensure(ws, B_CAND_V, (size_t)na * splits * 2 * KC * sizeof(float)));
+    L2CK(ensure(ws, B_CAND_I, (size_t)na * splits * 2 * (KC + 1) * sizeof(int32_t)));
     CUtensorMap mq, mt;
     if (!make_map(&mq, dA, na, ld, kpad, BM) || !make_map(&mt, dB, nb, ld, kpad, BN)) {
         err = "cuTensorMapEncodeTiled failed";
@@ -512,12 +533,13 @@ int gemm_candidates(L2Workspace &ws, cudaStream_t stream, const float *dA, int n
     }
     float *cv = (float *)ws.buf[B_CAND_V];
     int32_t *ci = (int32_t *)ws.buf[B_CAND_I];
+    int32_t *cc = ci + (size_t)na * splits * 2 * KC;
     cudaError_t e;
     switch (kpad / KSLAB) {
-    case 1: e = launch_gemm<1>(mq, mt, d_normB, na, nb, tiles_per_split, splits, cv, ci, stream); break;
-    case 2: e = launch_gemm<2>(mq, mt, d_normB, na, nb, tiles_per_split, splits, cv, ci, stream); break;
-    case 3: e = launch_gemm<3>(mq, mt, d_normB, na, nb, tiles_per_split, splits, cv, ci, stream); break;
-    case 4: e = launch_gemm<4>(mq, mt, d_normB, na, nb, tiles_per_split, splits, cv, ci, stream); break;
+    case 1: e = launch_gemm<1>(mq, mt, d_normB, d_normA, bmax, na, nb, tiles_per_split, splits, cv, ci, cc, stream); break;
+    case 2: e = launch_gemm<2>(mq, mt, d_normB, d_normA, bmax, na, nb, tiles_per_split, splits, cv, ci, cc, stream); break;
+    case 3: e = launch_gemm<3>(mq, mt, d_normB, d_normA, bmax, na, nb, tiles_per_split, splits, cv, ci, cc, stream); break;
+    case 4: e = launch_gemm<4>(mq, mt, d_normB, d_normA, bmax, na, nb, tiles_per_split, splits, cv, ci, cc, stream); break;
     default: err = "descriptor dimension above 128 floats"; return MVS_E_UNSUPPORTED;
     }
     L2CK(e);
@@ -529,6 +551,7 @@ int gemm_candidates(L2Workspace &ws, cudaStream_t stream, const float *dA, int n
 void L2Workspace::release()
 {
     for (int i = 0; i < 8; ++i) { if (buf[i]) cudaFree(buf[i]); buf[i] = nullptr; cap[i] = 0; }
+    for (int i = 0; i < 4; ++i) { if (ev[i]) cudaEventDestroy(ev[i]); ev[i] = nullptr; }
 }
 
 int l2_knn2(L2Workspace &ws, cudaStream_t stream, const float *query, int nq, const float *train, int nt, int dim,
@@ -537,6 +560,9 @@ int l2_knn2(L2Workspace &ws, cudaStream_t stream, const float *query, int nq, co
 {
     int nl = 0;
     if (n_launches) *n_launches = 0;
+    for (int i = 0; i < 4; ++i) if (!ws.ev[i]) cudaEventCreate(&ws.ev[i]);
+    cudaEventRecord(ws.ev[0], stream);
+    float gemm_ms_total = 0.f;
     if (n_out) *n_out = 0;
     if (dim < 1 || dim > 128) { err = "float descriptors: 1 <= dim <= 128 supported"; return MVS_E_UNSUPPORTED; }
     if (nq > (1 << 22) || nt > (1 << 22)) { err = "more than 2^22 descriptors per side"; return MVS_E_UNSUPPORTED; }
@@ -558,17 +584,19 @@ int l2_knn2(L2Workspace &ws, cudaStream_t stream, const float *query, int nq, co
         nl += 2;
     }
     // norms, |t|max (host reduction of nt floats: part of the error bound, not of the distance computation)
-    L2CK(ensure(ws, B_NORM, ((size_t)nq + nt) * sizeof(float)));
-    float *nQ = (float *)ws.buf[B_NORM], *nT = nQ + nq;
-    l2_norms_kernel<<<(nq + 255) / 256, 256, 0, stream>>>(dQ, nq, kpad, dim, nQ);
-    l2_norms_kernel<<<(nt + 255) / 256, 256, 0, stream>>>(dT, nt, kpad, dim, nT);
+    // squared norms, each array padded with +inf to a multiple of the column tile (padded columns never win)
+    const size_t nqp = ((size_t)nq + BN - 1) / BN * BN, ntp = ((size_t)nt + BN - 1) / BN * BN;
+    L2CK(ensure(ws, B_NORM, (nqp + ntp) * sizeof(float)));
+    float *nQ = (float *)ws.buf[B_NORM], *nT = nQ + nqp;
+    l2_norms_kernel<<<(unsigned)((nqp + 255) / 256), 256, 0, stream>>>(dQ, nq, (int)nqp, kpad, dim, nQ);
+    l2_norms_kernel<<<(unsigned)((ntp + 255) / 256), 256, 0, stream>>>(dT, nt, (int)ntp, kpad, dim, nT);
     nl += 2;
-    std::vector<float> hn((size_t)nq + nt);
+    std::vector<float> hn(nqp + ntp);
     L2CK(cudaMemcpyAsync(hn.data(), nQ, hn.size() * sizeof(float), cudaMemcpyDeviceToHost, stream));
     L2CK(cudaStreamSynchronize(stream));
     float qmax = 0.f, tmax = 0.f;
     for (int i = 0; i < nq; ++i) qmax = std::max(qmax, hn[i]);
-    for (int i = 0; i < nt; ++i) tmax = std::max(tmax, hn[nq + i]);
+    for (int i = 0; i < nt; ++i) tmax = std::max(tmax, hn[nqp + i]);
     qmax = std::sqrt(qmax); tmax = std::sqrt(tmax);
 
     const int passes = cross ? 2 : 1;
@@ -593,14 +621,22 @@ int l2_knn2(L2Workspace &ws, cudaStream_t stream, const float *query, int nq, co
         const float bmax = pass == 0 ? tmax : qmax;
         int splits, tps;
         plan_splits(na, nb, splits, tps);
-        int st = gemm_candidates(ws, stream, A, na, Bm, nb, kpad, kpad, nB, splits, tps, err);
+        cudaEventRecord(ws.ev[2], stream);
+        int st = gemm_candidates(ws, stream, A, na, Bm, nb, kpad, kpad, nB, nA, bmax, splits, tps, err);
         if (st != MVS_OK) return st;
+        cudaEventRecord(ws.ev[3], stream);
         nl += 1;
-        l2_rerank_kernel<<<(na + 7) / 8, 256, 0, stream>>>(A, Bm, kpad, kpad, dim, nA, bmax, na, nb, splits,
+        l2_rerank_kernel<<<(na + 7) / 8, 256, 0, stream>>>(A, Bm, kpad, kpad, dim, nA, bmax, na, nb, splits * 2,
                                                            (const float *)ws.buf[B_CAND_V], (const int32_t *)ws.buf[B_CAND_I],
+                                                           (const int32_t *)ws.buf[B_CAND_I] + (size_t)na * splits * 2 * KC,
                                                            o_idx, o_d2, o_flag);
         l2_fallback_kernel<<<na, 256, 0, stream>>>(A, Bm, kpad, kpad, dim, nb, o_flag, o_idx, o_d2, d_nfb + pass);
         nl += 2;
+        if (passes > 1 || true) {   // per-pass GEMM time (event pair reused, so read it now)
+            cudaEventSynchronize(ws.ev[3]);
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ws.ev[2], ws.ev[3]) == cudaSuccess) gemm_ms_total += ms;
+        }
     }
     l2_sqrt_kernel<<<(2 * nq + 255) / 256, 256, 0, stream>>>(f_d2, 2 * nq, f_dist);
     nl += 1;
@@ -626,7 +662,14 @@ int l2_knn2(L2Workspace &ws, cudaStream_t stream, const float *query, int nq, co
             L2CK(cudaMemcpyAsync(out, dm, (size_t)m * sizeof(mvs_match), cudaMemcpyDeviceToHost, stream));
         }
     }
+    cudaEventRecord(ws.ev[1], stream);
+    unsigned int hfb[2] = {0, 0};
+    L2CK(cudaMemcpyAsync(hfb, d_nfb, sizeof(hfb), cudaMemcpyDeviceToHost, stream));
     L2CK(cudaStreamSynchronize(stream));
+    float tot_ms = 0.f;
+    cudaEventElapsedTime(&tot_ms, ws.ev[0], ws.ev[1]);
+    ws.stats[0] = hfb[0]; ws.stats[1] = hfb[1];
+    ws.stats[2] = (uint64_t)(gemm_ms_total * 1000.f); ws.stats[3] = (uint64_t)(tot_ms * 1000.f);
     if (n_launches) *n_launches = nl;
     return MVS_OK;
 }
