@@ -173,7 +173,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     descs, kps, K, pairs, params, cfg = loader()
-    cap = max(d.shape[0] for d in descs)
+    # detail capacity per pair: every keypoint could match at s8k; the VO threshold (max_dist 10) keeps ~100 of ~1760
+    cap = max(d.shape[0] for d in descs) if args.workload != "tsukuba" else 256
     stream = torch.cuda.current_stream()
     ctx = mvs.Context(local, stream=stream.cuda_stream)
 
@@ -239,6 +240,7 @@ def main():
     torch.cuda.synchronize()
     res = np.frombuffer(res_t.numpy(), dtype=mvs.RESULT_DTYPE)
     n_ok = int((res["status"] == 0).sum())
+    assert int(res["n_matches"].max()) <= cap, "detail capacity too small for this workload"
 
     # ---- end to end through the public call with host buffers (H2D of the frames + D2H of everything)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -182,9 +182,11 @@ int mvs_frames_upload(mvs_ctx *ctx, int n_frames, const uint8_t *const *desc, co
                       const int32_t *counts, int desc_bytes);
 /* Solve pairs[i] = (base frame, pair frame) for i < n_pairs against the resident frames.
  * results[n_pairs] always filled (status per pair; one bad pair never aborts the batch).
- * Optional per-pair detail outputs use a common stride `capacity` (>= max keypoint count of any
- * pair frame, else MVS_E_CAPACITY): matches[n_pairs][capacity], inlier_mask[n_pairs][capacity],
- * points[n_pairs][capacity][3], indexes[n_pairs][capacity] (index into that pair's matches). */
+ * Optional per-pair detail outputs use a common stride `capacity` (>= 1): matches[n_pairs][capacity],
+ * inlier_mask[n_pairs][capacity], points[n_pairs][capacity][3], indexes[n_pairs][capacity] (index into that
+ * pair's matches).  Only the first `capacity` entries of a pair are copied back: a pair whose
+ * results[i].n_matches exceeds `capacity` is truncated (pass the largest pair-frame keypoint count to rule
+ * that out; the VO default max_dist = 10 leaves ~100 matches per 2k-keypoint pair). */
 int mvs_pair_batch(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, const double K[9],
                    const mvs_match_params *mparams, const mvs_ransac_params *rparams,
                    mvs_pair_result *results, mvs_match *matches, uint8_t *inlier_mask,

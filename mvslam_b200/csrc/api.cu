@@ -714,7 +714,7 @@ int mvs_pair_batch_enqueue(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, cons
         max_nq = std::max(max_nq, ctx->h_cnt[b]); max_nt = std::max(max_nt, ctx->h_cnt[a]);
     }
     const bool details = matches || inlier_mask || points || indexes;
-    if (details && capacity < max_nq) return fail(ctx, MVS_E_CAPACITY, "detail capacity smaller than the largest pair frame");
+    if (details && capacity < 1) return fail(ctx, MVS_E_CAPACITY, "detail capacity must be >= 1");
     RansacCfg rc;
     int st = resolve_ransac(ctx, rparams, K, rc);
     if (st != MVS_OK) return st;
@@ -762,15 +762,17 @@ int mvs_pair_batch_enqueue(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, cons
     if ((st = run_geometry(ctx, n_pairs, qs, rc, unit_z, nullptr, rc.pair_base, true, false, ctx->d_matches.as<mvs_match>())) != MVS_OK) return st;
 
     CK(cudaMemcpyAsync(results, ctx->d_results.p, (size_t)n_pairs * sizeof(mvs_pair_result), cudaMemcpyDeviceToHost, ctx->stream));
+    // details: the first min(capacity, stride) entries of every pair (a pair with n_matches > capacity is truncated)
+    const size_t w = (size_t)std::min(capacity, qs);
     if (matches)
         CK(cudaMemcpy2DAsync(matches, (size_t)capacity * sizeof(mvs_match), ctx->d_matches.p, (size_t)qs * sizeof(mvs_match),
-                             (size_t)qs * sizeof(mvs_match), n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+                             w * sizeof(mvs_match), n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
     if (inlier_mask)
-        CK(cudaMemcpy2DAsync(inlier_mask, (size_t)capacity, ctx->d_mask.p, (size_t)qs, (size_t)qs, n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpy2DAsync(inlier_mask, (size_t)capacity, ctx->d_mask.p, (size_t)qs, w, n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
     if (points)
-        CK(cudaMemcpy2DAsync(points, (size_t)capacity * 24, ctx->d_opts.p, (size_t)qs * 24, (size_t)qs * 24, n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpy2DAsync(points, (size_t)capacity * 24, ctx->d_opts.p, (size_t)qs * 24, w * 24, n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
     if (indexes)
-        CK(cudaMemcpy2DAsync(indexes, (size_t)capacity * 8, ctx->d_oidx.p, (size_t)qs * 8, (size_t)qs * 8, n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpy2DAsync(indexes, (size_t)capacity * 8, ctx->d_oidx.p, (size_t)qs * 8, w * 8, n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
     return MVS_OK;
 }
 
