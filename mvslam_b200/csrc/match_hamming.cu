@@ -34,7 +34,12 @@ __device__ __forceinline__ uint32_t hamming256(const uint4 &qa, const uint4 &qb,
     const uint32_t s0 = x0 ^ x1 ^ x2, c0 = (x0 & x1) | (x2 & (x0 | x1));
     const uint32_t s1 = x3 ^ x4 ^ x5, c1 = (x3 & x4) | (x5 & (x3 | x4));
     const uint32_t s2 = s0 ^ s1 ^ x6, c2 = (s0 & s1) | (x6 & (s0 | s1));
+#ifdef MVS_CSA4
+    const uint32_t s3 = c0 ^ c1 ^ c2, c3 = (c0 & c1) | (c2 & (c0 | c1));
+    return (__popc(s2) + __popc(x7)) + 2u * __popc(s3) + 4u * __popc(c3);
+#else
     return (__popc(s2) + __popc(x7)) + 2u * (__popc(c0) + __popc(c1) + __popc(c2));
+#endif
 }
 
 __device__ __forceinline__ void top2_insert(uint32_t &b1, uint32_t &b2, uint32_t key)

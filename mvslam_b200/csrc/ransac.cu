@@ -18,18 +18,13 @@ namespace mvs {
 
 // ------------------------------------------------------------------------------------------
 // K3.  f = vt.row(8) of SVD(A^T A) (fundamental-matrix.cpp:104-118) is the right singular vector of the
-// 8x9 matrix A for its zero singular value.  It is computed from A itself (no squared condition number,
-// ~1000x more accurate than the A^T A route): a one-sided Jacobi orthogonalises the 8
-// columns of A^T, then f is the unit vector orthogonal to all of them (2 passes of modified Gram-Schmidt).
-// Layout: a systolic "chess tournament" — a hypothesis is owned by 4 lanes (seats); every seat holds the
-// two length-9 columns that meet in the current step, so inner products, rotation parameters and the
-// rotation are lane-local (one c,s per column pair, nothing redundant).  Between steps the columns move
-// one seat along the ring  top1<-top2<-top3<-bot3<-bot2<-bot1<-bot0<-top1  (player 7 stays in seat 0)
-// with two warp shuffles per element.  In step s seat 0 holds players (7, s), seat k holds
-// ((s+k) mod 7, (s-k) mod 7): exactly the oracle's round-robin order.  8 hypotheses per warp.
+// 8x9 matrix A for its zero singular value, i.e. the unit vector orthogonal to the 8 rows of A.  It is
+// computed from A itself (no squared condition number, ~1000x more accurate than the A^T A route, see
+// DESIGN.md): Householder QR of A^T (9x8) entirely in registers, f = Q e_8.  One thread per hypothesis —
+// the whole solve is ~450 FMA + 8 sqrt + 8 div, so 32 hypotheses per warp with no communication beats
+// any cooperative layout.  Same explicit-fma operation order as the oracle (bit-identical F).
 // ------------------------------------------------------------------------------------------
-constexpr int HYP_WARPS = 4;
-constexpr int HYP_PER_WARP = 8;
+constexpr int HYP_THREADS = 128;
 constexpr unsigned FULL = 0xFFFFFFFFu;
 
 // find_normalization_transform (fundamental-matrix.cpp:18-54) of the 8 sampled points of one image:
@@ -60,14 +55,6 @@ __device__ __forceinline__ void normalize8(const double *pts, const uint32_t (&i
     T[0] = scale; T[1] = -mx * scale; T[2] = -my * scale;
 }
 
-__device__ __forceinline__ uint32_t sel8(const uint32_t (&a)[8], int c)
-{
-    uint32_t r = a[0];
-#pragma unroll
-    for (int k = 1; k < 8; ++k) r = (c == k) ? a[k] : r;
-    return r;
-}
-
 // row of A for one normalised correspondence (fundamental-matrix.cpp:76-87)
 __device__ __forceinline__ void epipolar_row(const double *p, const double (&T1)[3], double mx1, double my1,
                                              const double (&T2)[3], double mx2, double my2, double (&a)[9])
@@ -77,118 +64,57 @@ __device__ __forceinline__ void epipolar_row(const double *p, const double (&T1)
     a[0] = x2 * x1; a[1] = x2 * y1; a[2] = x2; a[3] = y2 * x1; a[4] = y2 * y1; a[5] = y2; a[6] = x1; a[7] = y1; a[8] = 1.0;
 }
 
-__device__ __forceinline__ double sel9(const double (&a)[9], int c)
+// 8-point solve of one sample by one thread.  pts: [.][6] correspondences, idx: the 8 sampled rows.
+__device__ __forceinline__ void eight_point(const double *pts, const uint32_t (&idx)[8], double (&F)[9])
 {
-    double r = a[0];
+    double T1[3], T2[3], mx1, my1, mx2, my2;
+    normalize8(pts, idx, 0, T1, mx1, my1);
+    normalize8(pts, idx, 3, T2, mx2, my2);
+    // M = A^T (9x8): column r = epipolar row of normalised correspondence r (fundamental-matrix.cpp:76-87)
+    double M[9][8], beta[8];
 #pragma unroll
-    for (int k = 1; k < 9; ++k) r = (c == k) ? a[k] : r;
-    return r;
-}
-
-// Cooperative 8-point solve by the 4 lanes [gbase, gbase+4) of a warp (all 32 lanes must call).
-// pts: [.][6] correspondences, idx: the 8 sampled rows. Every lane of the group returns the full F.
-__device__ __forceinline__ void eight_point_group(const double *pts, const uint32_t (&idx)[8], int k, int gbase,
-                                                  double (&F)[9])
-{
-    double T1[3], T2[3];
-    double wt[9], wb[9];
-    int pt = (k == 0) ? 7 : k, pb = (k == 0) ? 0 : 7 - k;  // players (= sample rows) held at step 0
-    {
-        double mx1, my1, mx2, my2;
-        normalize8(pts, idx, 0, T1, mx1, my1);
-        normalize8(pts, idx, 3, T2, mx2, my2);
-        // column r of A^T = row r of A: this seat only needs the rows of its two players
-        epipolar_row(pts + (size_t)sel8(idx, pt) * 6, T1, mx1, my1, T2, mx2, my2, wt);
-        epipolar_row(pts + (size_t)sel8(idx, pb) * 6, T1, mx1, my1, T2, mx2, my2, wb);
+    for (int r = 0; r < 8; ++r) {
+        double a[9];
+        epipolar_row(pts + (size_t)idx[r] * 6, T1, mx1, my1, T2, mx2, my2, a);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) M[i][r] = a[i];
     }
-    const int src_next = gbase + min(k + 1, 3), src_prev = gbase + max(k - 1, 0);
-    int step = 0;
-    for (int sweep = 0; sweep < kSvdMaxSweeps; ++sweep) {
-        bool changed = false;
-        for (int s7 = 0; s7 < 7; ++s7) {
-            double at = 0.0, ab = 0.0, g = 0.0;
+    // Householder QR of M; reflector v_k overwrites column k
 #pragma unroll
-            for (int i = 0; i < 9; ++i) {
-                at = fma(wt[i], wt[i], at);
-                ab = fma(wb[i], wb[i], ab);
-                g = fma(wt[i], wb[i], g);   // products commute exactly
-            }
-            const bool top_first = pt < pb;  // the column with the smaller index is "p" of the pair (p<q)
-            double cs, sn;
-            const bool rot = jacobi_cs(top_first ? at : ab, top_first ? ab : at, g, cs, sn);
-            if (rot) {
-                // p' = c*p + s*q ; q' = c*q - s*p
-                const double st = top_first ? sn : -sn;   // top' = c*top + st*bot ; bot' = c*bot - st*top
+    for (int k = 0; k < 8; ++k) {
+        double s2 = 0.0;
 #pragma unroll
-                for (int i = 0; i < 9; ++i) {
-                    const double a0 = wt[i], b0 = wb[i];
-                    wt[i] = fma(cs, a0, st * b0);
-                    wb[i] = fma(cs, b0, -(st * a0));
-                }
-            }
-            changed |= rot;
-            // ring move to the seating of the next step
+        for (int i = k; i < 9; ++i) s2 = fma(M[i][k], M[i][k], s2);
+        const double nrm = sqrt(s2);
+        if (!(nrm > 0.0)) { beta[k] = 0.0; continue; }
+        const double x0 = M[k][k];
+        const double alpha = (x0 >= 0.0) ? -nrm : nrm;
+        M[k][k] = x0 - alpha;
+        beta[k] = 2.0 / (2.0 * fma(nrm, fabs(x0), s2));
 #pragma unroll
-            for (int i = 0; i < 9; ++i) {
-                const double tn = __shfl_sync(FULL, wt[i], src_next), bp = __shfl_sync(FULL, wb[i], src_prev);
-                wt[i] = (k == 0) ? wt[i] : ((k == 3) ? wb[i] : tn);
-                wb[i] = (k == 0) ? tn : bp;
-            }
-            ++step;
-            const int sm = step % 7;
-            pt = (k == 0) ? 7 : (sm + k) % 7;
-            pb = (k == 0) ? sm : (sm - k + 7) % 7;
-        }
-        if (__ballot_sync(FULL, changed) == 0u) break;
-    }
-    // f: unit vector orthogonal to the 8 (now mutually orthogonal) columns, visited in player order
-    double nt = 0.0, nb = 0.0;
+        for (int j = k + 1; j < 8; ++j) {
+            double sj = 0.0;
 #pragma unroll
-    for (int i = 0; i < 9; ++i) { nt = fma(wt[i], wt[i], nt); nb = fma(wb[i], wb[i], nb); }
-    const double it = nt > 0.0 ? 1.0 / nt : 0.0, ib = nb > 0.0 ? 1.0 / nb : 0.0;
-    double t[9], x[9];
+            for (int i = k; i < 9; ++i) sj = fma(M[i][k], M[i][j], sj);
+            sj *= beta[k];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) { t[i] = 0.0; x[i] = 0.0; }
-    // pass -1 accumulates t (the squared projections of the unit vectors), passes 0,1 are the Gram-Schmidt
-    int best = 0;
-#pragma unroll 1
-    for (int pass = -1; pass < 2; ++pass) {
-#pragma unroll 1
-        for (int j = 0; j < 8; ++j) {
-            const bool mt = (pt == j), mb = (pb == j);
-            const unsigned holders = __ballot_sync(FULL, mt || mb);
-            const int src = gbase + __ffs((holders >> gbase) & 0xFu) - 1;
-            const double inv = __shfl_sync(FULL, mt ? it : ib, src);
-            double w[9], d = 0.0;
-#pragma unroll
-            for (int i = 0; i < 9; ++i) {
-                w[i] = __shfl_sync(FULL, mt ? wt[i] : wb[i], src);
-                d = fma(x[i], w[i], d);
-            }
-            if (pass < 0) {
-#pragma unroll
-                for (int i = 0; i < 9; ++i) t[i] = fma(w[i] * w[i], inv, t[i]);
-            } else {
-                d *= inv;
-#pragma unroll
-                for (int i = 0; i < 9; ++i) x[i] = fma(-d, w[i], x[i]);
-            }
-        }
-        if (pass < 0) {
-            double tb = t[0];
-#pragma unroll
-            for (int i = 1; i < 9; ++i) if (t[i] < tb) { tb = t[i]; best = i; }
-#pragma unroll
-            for (int i = 0; i < 9; ++i) x[i] = (i == best) ? 1.0 : 0.0;
+            for (int i = k; i < 9; ++i) M[i][j] = fma(-sj, M[i][k], M[i][j]);
         }
     }
-    double nx = 0.0;
-#pragma unroll
-    for (int i = 0; i < 9; ++i) nx = fma(x[i], x[i], nx);
-    nx = sqrt(nx);
+    // f = Q e_8
     double Fp[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) Fp[i] = x[i] / nx;
+    for (int i = 0; i < 9; ++i) Fp[i] = (i == 8) ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 7; k >= 0; --k) {
+        if (beta[k] == 0.0) continue;
+        double sk = 0.0;
+#pragma unroll
+        for (int i = k; i < 9; ++i) sk = fma(M[i][k], Fp[i], sk);
+        sk *= beta[k];
+#pragma unroll
+        for (int i = k; i < 9; ++i) Fp[i] = fma(-sk, M[i][k], Fp[i]);
+    }
     // singular constraint (fundamental-matrix.cpp:128-136), then F = T2^T * F * T1 (:245)
     double U[9], w3[3], Vt[9], Fh[9], T2t[9], tmp[9];
     svd3(Fp, U, w3, Vt);
@@ -204,7 +130,7 @@ __device__ __forceinline__ void eight_point_group(const double *pts, const uint3
     mat3_mul(tmp, T1m, F);
 }
 
-__global__ void __launch_bounds__(HYP_WARPS * 32)
+__global__ void __launch_bounds__(HYP_THREADS)
 hypotheses_kernel(HypArgs a)
 {
     const int pair = blockIdx.y;
@@ -213,13 +139,8 @@ hypotheses_kernel(HypArgs a)
         if (a.state[pair].status != MVS_OK) return;
         n = a.state[pair].n_matches;
     }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = lane >> 2;
-    const int c = lane & 3;
-    const int gbase = g * 4;
-    const int h0 = (blockIdx.x * HYP_WARPS + warp) * HYP_PER_WARP;
-    if (h0 >= a.H) return;  // warp-uniform
-    const int h = min(h0 + g, a.H - 1);
+    const int h = blockIdx.x * HYP_THREADS + threadIdx.x;
+    if (h >= a.H) return;
     uint32_t idx[8];
     if (a.table) {
 #pragma unroll
@@ -228,46 +149,30 @@ hypotheses_kernel(HypArgs a)
         sample_row(a.seed, a.pair_id_base + (uint64_t)pair, (uint32_t)n, h, idx);
     }
     double F[9];
-    eight_point_group(a.points + (size_t)pair * a.p_stride * 6, idx, c, gbase, F);
-    if (c == 0 && h0 + g < a.H) {
-        double *o = a.F_all + ((size_t)pair * a.H + h) * 9;
+    eight_point(a.points + (size_t)pair * a.p_stride * 6, idx, F);
+    double *o = a.F_all + ((size_t)pair * a.H + h) * 9;
 #pragma unroll
-        for (int i = 0; i < 9; ++i) o[i] = F[i];
-    }
+    for (int i = 0; i < 9; ++i) o[i] = F[i];
 }
 
-// a9 entry for explicit 8-point sets: p1s/p2s [n_sets][8][3] -> interleave into the [.][6] layout
-__global__ void __launch_bounds__(HYP_WARPS * 32)
+// a9 entry for explicit 8-point sets: p1s/p2s [n_sets][8][3]
+__global__ void __launch_bounds__(HYP_THREADS)
 fundamental_sets_kernel(const double *p1s, const double *p2s, int n_sets, double *pts6, double *F_out)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = lane >> 2;
-    const int c = lane & 3;
-    const int gbase = g * 4;
-    const int h0 = (blockIdx.x * HYP_WARPS + warp) * HYP_PER_WARP;
-    if (h0 >= n_sets) return;
-    const int h = min(h0 + g, n_sets - 1);
-    (void)pts6;
-    // gather this set into a per-lane view through a tiny index table over a virtual [8][6] block
-    // stored in global scratch (written by the same lanes, then re-read; volume is negligible)
-    double *blk = pts6 + (size_t)h * 48;
-    {
-        for (int r = c; r < 8; r += 4)
+    const int h = blockIdx.x * HYP_THREADS + threadIdx.x;
+    if (h >= n_sets) return;
+    double *blk = pts6 + (size_t)h * 48;   // this set in the interleaved [8][6] layout
+    for (int r = 0; r < 8; ++r)
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                blk[r * 6 + k] = p1s[((size_t)h * 8 + r) * 3 + k];
-                blk[r * 6 + 3 + k] = p2s[((size_t)h * 8 + r) * 3 + k];
-            }
-    }
-    __syncwarp();
-    __threadfence_block();
+        for (int k = 0; k < 3; ++k) {
+            blk[r * 6 + k] = p1s[((size_t)h * 8 + r) * 3 + k];
+            blk[r * 6 + 3 + k] = p2s[((size_t)h * 8 + r) * 3 + k];
+        }
     const uint32_t idx[8] = {0, 1, 2, 3, 4, 5, 6, 7};
     double F[9];
-    eight_point_group(blk, idx, c, gbase, F);
-    if (c == 0 && h0 + g < n_sets) {
+    eight_point(blk, idx, F);
 #pragma unroll
-        for (int i = 0; i < 9; ++i) F_out[(size_t)h * 9 + i] = F[i];
-    }
+    for (int i = 0; i < 9; ++i) F_out[(size_t)h * 9 + i] = F[i];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -519,17 +424,15 @@ select_kernel(SelectArgs a)
 // ------------------------------------------------------------------------------------------ launchers
 void launch_hypotheses(const HypArgs &a, int n_pairs, cudaStream_t s)
 {
-    const int per_block = HYP_WARPS * HYP_PER_WARP;
-    dim3 grid((a.H + per_block - 1) / per_block, n_pairs);
-    hypotheses_kernel<<<grid, HYP_WARPS * 32, 0, s>>>(a);
+    dim3 grid((a.H + HYP_THREADS - 1) / HYP_THREADS, n_pairs);
+    hypotheses_kernel<<<grid, HYP_THREADS, 0, s>>>(a);
 }
 
 void launch_fundamental_sets(const double *p1s, const double *p2s, int n_sets, double *F_out, cudaStream_t s)
 {
     // scratch for the interleaved [n_sets][8][6] view lives right behind F_out's device buffer: the
     // caller passes F_out with room for n_sets*9 + n_sets*48 doubles
-    const int per_block = HYP_WARPS * HYP_PER_WARP;
-    fundamental_sets_kernel<<<(n_sets + per_block - 1) / per_block, HYP_WARPS * 32, 0, s>>>(
+    fundamental_sets_kernel<<<(n_sets + HYP_THREADS - 1) / HYP_THREADS, HYP_THREADS, 0, s>>>(
         p1s, p2s, n_sets, F_out + (size_t)n_sets * 9, F_out);
 }
 

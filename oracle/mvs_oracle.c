@@ -420,69 +420,42 @@ static void find_normalization_transform(const double *p /*[8][3]*/, double np[8
 }
 
 /* The reference obtains f as vt.row(8) of cv::SVDecomp(A^T A) (fundamental-matrix.cpp:104-118), i.e. the
- * right singular vector of the 8x9 matrix A for its zero singular value.  That vector is computed here
- * directly from A: a one-sided Jacobi orthogonalises the 8 columns of A^T (same rotation, same round-robin
- * order as orc_svd), after which the columns span the row space of A and f is the unit vector orthogonal to
- * all of them (two passes of modified Gram-Schmidt on the least-aligned unit vector).  Working on A instead
- * of A^T A avoids squaring the condition number: measured against the exact null vector this route is
- * ~1000x more accurate than either cv2.SVDecomp(A^T A) or a Jacobi on A^T A, and it differs from
- * cv2.SVDecomp(A^T A) by no more than a literal restatement does (both differences are cv2's own A^T A
- * round-off; numbers in DESIGN.md).  Oracle A (oracle_np.py) keeps the literal A^T A + cv2.SVDecomp route. */
+ * right singular vector of the 8x9 matrix A for its zero singular value = the unit vector orthogonal to the
+ * 8 rows of A.  It is computed here directly from A: a Householder QR of A^T (9x8) gives an orthogonal Q
+ * whose last column spans the null space of A; f = Q e_8 (apply the 8 reflectors to e_8 in reverse order).
+ * Working on A instead of A^T A avoids squaring the condition number: measured against the exact null
+ * vector this route is ~1000x more accurate than either cv2.SVDecomp(A^T A) or a Jacobi on A^T A, and it
+ * differs from cv2.SVDecomp(A^T A) by no more than a literal restatement does (both differences are cv2's
+ * own A^T A round-off; numbers in DESIGN.md).  Oracle A (oracle_np.py) keeps the literal A^T A +
+ * cv2.SVDecomp route.  The explicit fma() order below is mirrored one-for-one by the CUDA kernel. */
 static void null_vector_8x9(double A[8][9], double f[9])
 {
-    double W[9][8]; /* W = A^T: 8 columns of length 9 */
-    for (int i = 0; i < 9; ++i) for (int j = 0; j < 8; ++j) W[i][j] = A[j][i];
-    for (int sweep = 0; sweep < SVD_MAX_SWEEPS; ++sweep) {
-        int changed = 0;
-        for (int s = 0; s < 7; ++s)
-            for (int k = 0; k < 4; ++k) {
-                int i = (k == 0) ? s : (s + k) % 7, j = (k == 0) ? 7 : (s - k + 7) % 7;
-                int p = i < j ? i : j, q = i < j ? j : i;
-                double a = 0.0, b = 0.0, g = 0.0;
-                for (int r = 0; r < 9; ++r) {
-                    a = fma(W[r][p], W[r][p], a);
-                    b = fma(W[r][q], W[r][q], b);
-                    g = fma(W[r][p], W[r][q], g);
-                }
-                if (g * g <= (SVD_EPS2 * a) * b) continue;
-                changed = 1;
-                double g2 = g * 2.0, beta = a - b;
-                double gamma = sqrt(fma(g2, g2, beta * beta));
-                double inv = 1.0 / (gamma * 2.0);
-                double c, sn;
-                if (beta < 0) { sn = sqrt((gamma - beta) * inv); c = (g2 * inv) / sn; }
-                else { c = sqrt((gamma + beta) * inv); sn = (g2 * inv) / c; }
-                for (int r = 0; r < 9; ++r) {
-                    double wp = W[r][p], wq = W[r][q];
-                    W[r][p] = fma(c, wp, sn * wq);
-                    W[r][q] = fma(c, wq, -(sn * wp));
-                }
-            }
-        if (!changed) break;
-    }
-    double inv[8], t[9], x[9];
-    for (int j = 0; j < 8; ++j) {
-        double nn = 0.0;
-        for (int r = 0; r < 9; ++r) nn = fma(W[r][j], W[r][j], nn);
-        inv[j] = nn > 0.0 ? 1.0 / nn : 0.0;
-    }
-    for (int r = 0; r < 9; ++r) t[r] = 0.0;
-    for (int j = 0; j < 8; ++j)
-        for (int r = 0; r < 9; ++r) t[r] = fma(W[r][j] * W[r][j], inv[j], t[r]);
-    int best = 0;
-    for (int r = 1; r < 9; ++r) if (t[r] < t[best]) best = r;
-    for (int r = 0; r < 9; ++r) x[r] = (r == best) ? 1.0 : 0.0;
-    for (int pass = 0; pass < 2; ++pass)
-        for (int j = 0; j < 8; ++j) {
-            double d = 0.0;
-            for (int r = 0; r < 9; ++r) d = fma(x[r], W[r][j], d);
-            d *= inv[j];
-            for (int r = 0; r < 9; ++r) x[r] = fma(-d, W[r][j], x[r]);
+    double M[9][8], beta[8];
+    for (int i = 0; i < 9; ++i) for (int j = 0; j < 8; ++j) M[i][j] = A[j][i];
+    for (int k = 0; k < 8; ++k) {
+        double s2 = 0.0;
+        for (int i = k; i < 9; ++i) s2 = fma(M[i][k], M[i][k], s2);
+        const double nrm = sqrt(s2);
+        if (!(nrm > 0.0)) { beta[k] = 0.0; continue; }          /* zero column: H_k = I */
+        const double x0 = M[k][k];
+        const double alpha = (x0 >= 0.0) ? -nrm : nrm;
+        M[k][k] = x0 - alpha;                                    /* v_k stored in place of column k */
+        beta[k] = 2.0 / (2.0 * fma(nrm, fabs(x0), s2));          /* 2 / (v^T v), v^T v = 2 (|x|^2 + |x||x0|) */
+        for (int j = k + 1; j < 8; ++j) {
+            double s = 0.0;
+            for (int i = k; i < 9; ++i) s = fma(M[i][k], M[i][j], s);
+            s *= beta[k];
+            for (int i = k; i < 9; ++i) M[i][j] = fma(-s, M[i][k], M[i][j]);
         }
-    double nx = 0.0;
-    for (int r = 0; r < 9; ++r) nx = fma(x[r], x[r], nx);
-    nx = sqrt(nx);
-    for (int r = 0; r < 9; ++r) f[r] = x[r] / nx;
+    }
+    for (int i = 0; i < 9; ++i) f[i] = (i == 8) ? 1.0 : 0.0;
+    for (int k = 7; k >= 0; --k) {
+        if (beta[k] == 0.0) continue;
+        double s = 0.0;
+        for (int i = k; i < 9; ++i) s = fma(M[i][k], f[i], s);
+        s *= beta[k];
+        for (int i = k; i < 9; ++i) f[i] = fma(-s, M[i][k], f[i]);
+    }
 }
 
 /* find_fundamental_matrix_8point, fundamental-matrix.cpp:56-140 */
