@@ -50,7 +50,7 @@ struct mvs_ctx {
     DevBuf t_desc, t_foff, t_fcnt;
     // workspace
     DevBuf d_pairs, d_partial, d_rev, d_matches, d_nmatch, d_points, d_state, d_Fall, d_pc, d_pr, d_mask,
-        d_valid, d_tri, d_opts, d_oidx, d_results, d_table, d_in1, d_in2, d_knn_i, d_knn_d, d_counts;
+        d_valid, d_tri, d_opts, d_oidx, d_results, d_table, d_in1, d_in2, d_knn_i, d_knn_d, d_counts, d_pres;
     mvs::L2Workspace l2;
     // profiling
     bool prof = false;
@@ -173,6 +173,8 @@ int run_geometry(mvs_ctx *ctx, int n_pairs, int p_stride, const RansacCfg &rc, b
     CK(ctx->d_Fall.ensure((size_t)n_pairs * rc.H * 9 * sizeof(double)));
     CK(ctx->d_pc.ensure((size_t)n_pairs * tiles * rc.H * sizeof(uint32_t)));
     CK(ctx->d_pr.ensure((size_t)n_pairs * rc.H * 2 * sizeof(int32_t)));
+    const bool k4_res = (rc.mode == MVS_SCORE_ALGEBRAIC);
+    if (k4_res) CK(ctx->d_pres.ensure((size_t)n_pairs * tiles * rc.H * sizeof(double)));
     CK(ctx->d_mask.ensure((size_t)n_pairs * p_stride));
     if (want_all_counts) CK(ctx->d_counts.ensure((size_t)n_pairs * rc.H * sizeof(int32_t)));
     PairState *state = ctx->d_state.as<PairState>();
@@ -188,6 +190,7 @@ int run_geometry(mvs_ctx *ctx, int n_pairs, int p_stride, const RansacCfg &rc, b
         ScoreArgs a{};
         a.points = ctx->d_points.as<double>(); a.p_stride = p_stride; a.state = state; a.F_all = ctx->d_Fall.as<double>();
         a.H = rc.H; a.max_error_sq = rc.thr; a.tiles = tiles; a.part_count = ctx->d_pc.as<uint32_t>();
+        a.part_res = k4_res ? ctx->d_pres.as<double>() : nullptr;
         launch_score(a, rc.mode, unit_z, n_pairs, ctx->stream);
     }
     {
@@ -195,6 +198,7 @@ int run_geometry(mvs_ctx *ctx, int n_pairs, int p_stride, const RansacCfg &rc, b
         SelectArgs a{};
         a.points = ctx->d_points.as<double>(); a.p_stride = p_stride; a.state = state; a.F_all = ctx->d_Fall.as<double>();
         a.H = rc.H; a.part_count = ctx->d_pc.as<uint32_t>(); a.ties = ctx->d_pr.as<int32_t>(); a.tiles = tiles;
+        a.part_res = k4_res ? ctx->d_pres.as<double>() : nullptr;
         a.max_error_sq = rc.thr; a.min_inliers = rc.min_inl; a.decompose = decompose ? 1 : 0;
         a.mask = ctx->d_mask.as<uint8_t>(); a.all_counts = want_all_counts ? ctx->d_counts.as<int32_t>() : nullptr;
         launch_select(a, rc.mode, unit_z, n_pairs, ctx->stream);
@@ -288,7 +292,7 @@ void mvs_destroy(mvs_ctx *ctx)
                       &ctx->d_pairs, &ctx->d_partial, &ctx->d_rev, &ctx->d_matches, &ctx->d_nmatch, &ctx->d_points,
                       &ctx->d_state, &ctx->d_Fall, &ctx->d_pc, &ctx->d_pr, &ctx->d_mask, &ctx->d_valid, &ctx->d_tri,
                       &ctx->d_opts, &ctx->d_oidx, &ctx->d_results, &ctx->d_table, &ctx->d_in1, &ctx->d_in2,
-                      &ctx->d_knn_i, &ctx->d_knn_d, &ctx->d_counts};
+                      &ctx->d_knn_i, &ctx->d_knn_d, &ctx->d_counts, &ctx->d_pres};
     for (DevBuf *b : bufs) b->release();
     ctx->l2.release();
     for (auto &p : ctx->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }

@@ -54,6 +54,7 @@ struct ScoreArgs {
     double max_error_sq;
     int tiles;                 // point tiles per pair
     uint32_t *part_count;      // [pairs][tiles][H]
+    double *part_res;          // [pairs][tiles][H] residual sums (ALGEBRAIC mode only, else nullptr)
 };
 
 struct SelectArgs {
@@ -61,6 +62,7 @@ struct SelectArgs {
     PairState *state; int n_fixed;
     const double *F_all; int H;
     const uint32_t *part_count; int tiles;
+    const double *part_res;    // per-tile residual sums when K4 produced them (ALGEBRAIC), else nullptr
     int32_t *ties;             // scratch [pairs][2][H]: total counts, then the hypotheses sharing the best count
     double max_error_sq;
     int min_inliers;

@@ -179,7 +179,8 @@ fundamental_sets_kernel(const double *p1s, const double *p2s, int n_sets, double
 // K4.  thread = hypothesis (F in registers), correspondences streamed through shared memory as
 // broadcast 128-bit reads; grid = (H/128, point tiles, pairs).  Each thread keeps a private inlier
 // count for its tile.  The residual sum only breaks ties between hypotheses with equal counts
-// (estimator-RANSAC.cpp:76-84), so it is evaluated in K5 for the tied leaders only.
+// (estimator-RANSAC.cpp:76-84): in ALGEBRAIC mode it costs one predicated add and is accumulated here
+// (per tile, in point order); in SAMPSON mode it needs a division, so K5 evaluates it for the tied leaders only.
 // ------------------------------------------------------------------------------------------
 constexpr int SC_THREADS = 128;
 constexpr int SC_TILE = 512;
@@ -217,6 +218,8 @@ score_kernel(ScoreArgs a)
     for (int i = 0; i < 9; ++i) F[i] = Fg[i];
     const double thr = a.max_error_sq;
     uint32_t c = 0;
+    double res = 0.0;
+    constexpr bool kRes = (MODE == MVS_SCORE_ALGEBRAIC);
 #pragma unroll 4
     for (int i = 0; i < cnt; ++i) {
         double r;
@@ -224,16 +227,18 @@ score_kernel(ScoreArgs a)
         if (UNIT_Z) {
             const double2 u = *reinterpret_cast<const double2 *>(sp + 4 * i);
             const double2 v = *reinterpret_cast<const double2 *>(sp + 4 * i + 2);
-            in = point_residual<true, MODE, false>(u.x, u.y, 1.0, v.x, v.y, 1.0, F, thr, r);
+            in = point_residual<true, MODE, kRes>(u.x, u.y, 1.0, v.x, v.y, 1.0, F, thr, r);
         } else {
             const double2 u = *reinterpret_cast<const double2 *>(sp + 6 * i);
             const double2 v = *reinterpret_cast<const double2 *>(sp + 6 * i + 2);
             const double2 w = *reinterpret_cast<const double2 *>(sp + 6 * i + 4);
-            in = point_residual<false, MODE, false>(u.x, u.y, v.x, v.y, w.x, w.y, F, thr, r);
+            in = point_residual<false, MODE, kRes>(u.x, u.y, v.x, v.y, w.x, w.y, F, thr, r);
         }
         c += in ? 1u : 0u;
+        if (kRes && in) res += r;
     }
     a.part_count[((size_t)pair * a.tiles + tile) * a.H + h] = c;
+    if (kRes) a.part_res[((size_t)pair * a.tiles + tile) * a.H + h] = res;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -343,6 +348,15 @@ select_kernel(SelectArgs a)
             if ((uint32_t)ties[h] == cmax) list[atomicAdd(&s_nties, 1)] = h;
         __syncthreads();
         const int nties = s_nties;
+        if (a.part_res) {   // K4 already summed the residuals per tile: add the tiles in order
+            for (int t = threadIdx.x; t < nties; t += SEL_THREADS) {
+                const int h = list[t];
+                double res = 0.0;
+                for (int tl = 0; tl < tiles_used; ++tl) res += a.part_res[((size_t)pair * a.tiles + tl) * a.H + h];
+                Best x; x.cnt = cmax; x.res = res; x.h = h;
+                if (better(x, b)) b = x;
+            }
+        } else {
         // L lanes cooperate on one tied hypothesis: L = 32 when ties are rare (noisy data), down to one
         // thread per hypothesis when (almost) every hypothesis ties (noise-free data)
         int L = 32;
@@ -363,6 +377,7 @@ select_kernel(SelectArgs a)
             for (int off = L >> 1; off > 0; off >>= 1) res += __shfl_xor_sync(__activemask(), res, off);
             Best x; x.cnt = cmax; x.res = res; x.h = h;
             if (better(x, b)) b = x;
+        }
         }
         // fold the per-thread leaders of the warp
 #pragma unroll
