@@ -61,6 +61,16 @@ def load_workload(name, pairs_per_step, H):
                    pairs_per_step_per_gpu=pairs_per_step, hypotheses=H, max_dist=-1.0, ratio=0.7, cross_check=False,
                    score="sampson", data_note="SURVEY §8d config 3, 8 distinct seeded pairs cycled")
         params = dict(max_dist=-1.0, H=H, seed=0, mode=1, max_error_sq=0.0)
+    elif name == "w512":
+        n_frames = int(os.environ.get("MVS_W512_FRAMES", "512"))
+        descs, kps = synth.synthetic_window(n_frames=n_frames, n_kp=2048)
+        K = synth.K_S8K
+        pairs = np.array([(a, b) for a in range(n_frames) for b in range(a + 1, n_frames)], np.int32)
+        cfg = dict(workload="synthetic_w512_all_pairs", frames=n_frames, kpts_per_frame=2048, pairs_total=int(len(pairs)),
+                   hypotheses=H, max_dist=-1.0, ratio=0.7, cross_check=False, score="sampson",
+                   data_note="SURVEY §8d config 5: one 20000-point scene, smooth seeded trajectory, all unordered pairs; "
+                             "the pair list is split contiguously over the ranks (strong scaling)")
+        params = dict(max_dist=-1.0, H=H, seed=0, mode=1, max_error_sq=0.0)
     else:
         raise SystemExit(f"unknown workload {name}")
     return descs, kps, K, pairs, params, cfg
@@ -147,14 +157,14 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="tsukuba", choices=["tsukuba", "s8k"])
+    ap.add_argument("--workload", default="tsukuba", choices=["tsukuba", "s8k", "w512"])
     ap.add_argument("--pairs", type=int, default=0, help="pairs per step per GPU (default 1024 tsukuba / 64 s8k)")
     ap.add_argument("--hypotheses", type=int, default=0, help="RANSAC sample-table rows (default 1024 tsukuba / 4096 s8k)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    B = args.pairs or (1024 if args.workload == "tsukuba" else 64)
-    H = args.hypotheses or (1024 if args.workload == "tsukuba" else 4096)
+    B = args.pairs or {"tsukuba": 1024, "s8k": 64, "w512": 0}[args.workload]
+    H = args.hypotheses or {"tsukuba": 1024, "s8k": 4096, "w512": 1024}[args.workload]
     loader = lambda: load_workload(args.workload, B, H)  # noqa: E731
     if args.impl == "reference":
         run_reference(args, loader)
@@ -173,6 +183,17 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     descs, kps, K, pairs, params, cfg = loader()
+    strong = args.workload == "w512"
+    pair_base = 0
+    if strong:   # fixed total job, contiguous shard per rank; else every rank runs its own copy of the batch (weak)
+        from mvslam_b200 import shard
+        lo, hi = shard.shard_bounds(len(pairs), world, rank)
+        pairs, pair_base = pairs[lo:hi], lo
+        B = len(pairs)
+        cfg["pairs_per_step_per_gpu"] = B
+    else:
+        pair_base = rank * B
+    CH = 4096                      # pairs per library call (bounds the HBM workspace)
     # detail capacity per pair: every keypoint could match at s8k; the VO threshold (max_dist 10) keeps ~100 of ~1760
     cap = max(d.shape[0] for d in descs) if args.workload != "tsukuba" else 256
     stream = torch.cuda.current_stream()
@@ -182,32 +203,51 @@ def main():
     pin = lambda a: torch.from_numpy(a).pin_memory()  # noqa: E731
     pd = [pin(d) for d in descs]; pk = [pin(k) for k in kps]
     res_t = torch.empty(B * mvs.RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
-    mat_t = torch.empty(B * cap * 12, dtype=torch.uint8).pin_memory()
-    msk_t = torch.empty(B * cap, dtype=torch.uint8).pin_memory()
-    pts_t = torch.empty(B * cap * 3, dtype=torch.float64).pin_memory()
-    idx_t = torch.empty(B * cap, dtype=torch.int64).pin_memory()
+    Bd = min(B, CH) if not strong else 1      # the all-pairs job returns records only
+    mat_t = torch.empty(Bd * cap * 12, dtype=torch.uint8).pin_memory()
+    msk_t = torch.empty(Bd * cap, dtype=torch.uint8).pin_memory()
+    pts_t = torch.empty(Bd * cap * 3, dtype=torch.float64).pin_memory()
+    idx_t = torch.empty(Bd * cap, dtype=torch.int64).pin_memory()
     out_rec = dict(results=res_t.data_ptr())
     out_all = dict(results=res_t.data_ptr(), matches=mat_t.data_ptr(), mask=msk_t.data_ptr(), points=pts_t.data_ptr(),
-                   indexes=idx_t.data_ptr(), capacity=cap)
+                   indexes=idx_t.data_ptr(), capacity=cap) if not strong else out_rec
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
     kw = dict(max_dist=params["max_dist"], H=params["H"], seed=params["seed"], mode=params["mode"],
-              max_error_sq=params["max_error_sq"], pair_id_base=rank * B)
+              max_error_sq=params["max_error_sq"])
+    item = mvs.RESULT_DTYPE.itemsize
 
     def upload():
         ctx.frames_upload([t.numpy() for t in pd], [t.numpy() for t in pk])
 
     def step(out):
-        ctx.pair_batch(pairs, K, out=out, enqueue_only=True, **kw)
+        for c0 in range(0, B, CH):
+            c1 = min(B, c0 + CH)
+            o = dict(out, results=out["results"] + c0 * item)
+            if "matches" in o:      # detail buffers hold one chunk and are overwritten chunk by chunk
+                assert B <= CH
+            ctx.pair_batch(pairs[c0:c1], K, out=o, enqueue_only=True, pair_id_base=pair_base + c0, **kw)
 
     upload()
     for _ in range(args.warmup):
         flush.zero_(); step(out_rec)
     torch.cuda.synchronize()
+    from mvslam_b200 import shard as _shard
+    n_gather = int(cfg.get("pairs_total", B * world))
+
+    def final_gather():
+        """the single collective of the path: the fixed-size records of every rank -> rank 0 (NCCL)"""
+        local = np.frombuffer(res_t.numpy(), dtype=mvs.RESULT_DTYPE)
+        if strong:
+            return _shard.gather_records(local, n_gather, dist, device=torch.device("cuda", local_dev))
+        mine = res_t.to("cuda", non_blocking=True)
+        bucket = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+        dist.gather(mine, bucket, dst=0)
+        return bucket
+
+    local_dev = local
     if world > 1:   # warm the communicator: the first NCCL collective pays the lazy connection setup
-        w_mine = res_t.to("cuda")
-        w_bucket = [torch.empty_like(w_mine) for _ in range(world)] if rank == 0 else None
         for _ in range(2):
-            dist.gather(w_mine, w_bucket, dst=0)
+            final_gather()
         torch.cuda.synchronize()
         dist.barrier()
     torch.cuda.synchronize()
@@ -224,9 +264,7 @@ def main():
         gather_ms = 0.0
         if world > 1:   # the single collective of the path: final gather of the fixed-size records over NCCL
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            mine = res_t.to("cuda", non_blocking=True)
-            bucket = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
-            g0.record(stream); dist.gather(mine, bucket, dst=0); g1.record(stream)
+            g0.record(stream); final_gather(); g1.record(stream)
             torch.cuda.synchronize()
             gather_ms = g0.elapsed_time(g1)
     launches = ctx.kernel_launches() - l0
@@ -255,7 +293,7 @@ def main():
         t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_ms = float(t.item())
     h2d = sum(d.nbytes for d in descs) + sum(k.nbytes for k in kps) + pairs.nbytes
-    d2h = res_t.numel() + mat_t.numel() + msk_t.numel() + pts_t.numel() * 8 + idx_t.numel() * 8
+    d2h = res_t.numel() + (0 if strong else mat_t.numel() + msk_t.numel() + pts_t.numel() * 8 + idx_t.numel() * 8)
 
     if rank != 0:
         if world > 1:
@@ -264,7 +302,8 @@ def main():
 
     # ---- roofline of the dominant kernel (Hamming kNN): algorithmic popc32 ops / measured launch time
     counts = np.array([d.shape[0] for d in descs], np.int64)
-    desc_pairs = int(sum(counts[a] * counts[b] for a, b in pairs))        # per launch (one launch per step)
+    n_calls = (B + CH - 1) // CH
+    desc_pairs = int((counts[pairs[:, 0]] * counts[pairs[:, 1]]).sum()) // n_calls     # per launch
     knn_ms, knn_n = prof["knn"]
     peaks = {}
     pk_path = os.path.join(ROOT, "profiles", "ubench_peaks.json")
@@ -277,7 +316,7 @@ def main():
     pair_peak = min(popc_rate / 5.0, alu_rate / 18.0)
     launch_s = knn_ms / knn_n * 1e-3 if knn_n else float("inf")
     pair_rate = desc_pairs / launch_s
-    alg_bytes = int(sum((counts[a] + counts[b]) * 32 + counts[b] * 8 for a, b in pairs))
+    alg_bytes = int(((counts[pairs[:, 0]] + counts[pairs[:, 1]]) * 32 + counts[pairs[:, 1]] * 8).sum()) // n_calls
     hbm_peak = 6444.4
     mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(mp):
@@ -297,7 +336,8 @@ def main():
                              note="compute-bound kernel: the HBM fraction is reported for completeness only"),
                     traffic=None, stage_share=stage_share,
                     stage_ms_per_step={s: round(prof[s][0] / args.steps, 4) for s in mvs.STAGES[:7]})
-    m_total = int(res["n_matches"].astype(np.int64).sum())
+    scored = res["n_matches"] >= 8                           # pairs that reach RANSAC
+    m_total = int(res["n_matches"][scored].astype(np.int64).sum())
     evals = float(params["H"]) * m_total
     score_ms = prof["score"][0] / args.steps
 
@@ -311,20 +351,21 @@ def main():
         cpu = dict(value=v, unit="pairs/s", cores=threads, kind="port",
                    sample=f"{n_sample} pairs of the same workload in {dt:.1f} s, C oracle (own-branch port), OpenMP over pairs")
 
-    value = B * world * args.steps / (total_ms * 1e-3)
+    n_job = int(cfg.get("pairs_total", B * world))      # pairs all ranks processed per step
+    value = n_job * args.steps / (total_ms * 1e-3)
     line = dict(metric=METRIC, value=value, unit="pairs/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
-                ms_per_step=total_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype="u32-popc/f64",
+                ms_per_step=total_ms / args.steps, higher_is_better=True, scaling="strong" if strong else "weak",
+                vs_baseline=None, dtype="u32-popc/f64",
                 data="bundled Tsukuba ORB features (host-extracted), no network" if args.workload == "tsukuba" else "synthetic",
                 config=dict(cfg, l2_policy="256 MiB flush buffer written between timed steps", solved_pairs_per_step=n_ok,
                             final_gather_ms=gather_ms),
                 clocks=clocks.summary(),
-                e2e=dict(value=B * world / (e2e_ms * 1e-3), unit="pairs/s", h2d_bytes_per_step=int(h2d),
+                e2e=dict(value=n_job / (e2e_ms * 1e-3), unit="pairs/s", h2d_bytes_per_step=int(h2d),
                          d2h_bytes_per_step=int(d2h), ms_per_step=e2e_ms),
                 gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu,
                 ransac=dict(hyp_pt_evals_per_s=evals / (score_ms * 1e-3) if score_ms > 0 else None,
                             evals_per_step=evals, score_ms_per_step=score_ms,
-                            hypotheses_per_s=params["H"] * B / (prof["hypotheses"][0] / args.steps * 1e-3)))
+                            hypotheses_per_s=params["H"] * int(scored.sum()) / max(prof["hypotheses"][0] / args.steps * 1e-3, 1e-12)))
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
