@@ -234,15 +234,21 @@ def main():
     from mvslam_b200 import shard as _shard
     n_gather = int(cfg.get("pairs_total", B * world))
 
+    # preallocated staging for the final gather: equal-size (padded) shards, pinned on both ends
+    g_item = mvs.RESULT_DTYPE.itemsize
+    g_cap = (max(_shard.shard_bounds(n_gather, world, r)[1] - _shard.shard_bounds(n_gather, world, r)[0]
+                 for r in range(world)) if strong else B) * g_item
+    g_dev = torch.empty(g_cap, dtype=torch.uint8, device="cuda")
+    g_bucket = [torch.empty(g_cap, dtype=torch.uint8, device="cuda") for _ in range(world)] if rank == 0 else None
+    g_host = torch.empty(world * g_cap, dtype=torch.uint8).pin_memory() if rank == 0 else None
+
     def final_gather():
-        """the single collective of the path: the fixed-size records of every rank -> rank 0 (NCCL)"""
-        local = np.frombuffer(res_t.numpy(), dtype=mvs.RESULT_DTYPE)
-        if strong:
-            return _shard.gather_records(local, n_gather, dist, device=torch.device("cuda", local_dev))
-        mine = res_t.to("cuda", non_blocking=True)
-        bucket = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
-        dist.gather(mine, bucket, dst=0)
-        return bucket
+        """the single collective of the path: the fixed-size records of every rank -> rank 0 (NCCL), then to host"""
+        g_dev[:res_t.numel()].copy_(res_t, non_blocking=True)
+        dist.gather(g_dev, g_bucket, dst=0)
+        if rank == 0:
+            for r in range(world):
+                g_host[r * g_cap:(r + 1) * g_cap].copy_(g_bucket[r], non_blocking=True)
 
     local_dev = local
     if world > 1:   # warm the communicator: the first NCCL collective pays the lazy connection setup
