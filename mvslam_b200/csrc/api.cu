@@ -14,6 +14,9 @@
 
 using namespace mvs;
 
+static_assert(sizeof(mvs_pair_result) == 376, "mvs_pair_result layout is part of the ABI");
+static_assert(sizeof(mvs_match) == 12, "mvs_match layout is part of the ABI");
+
 namespace {
 
 struct DevBuf {
@@ -701,13 +704,11 @@ int mvs_frames_upload(mvs_ctx *ctx, int n_frames, const uint8_t *const *desc, co
     return MVS_OK;
 }
 
-int mvs_pair_batch_enqueue(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, const double K[9],
-                           const mvs_match_params *mparams, const mvs_ransac_params *rparams,
-                           mvs_pair_result *results, mvs_match *matches, uint8_t *inlier_mask,
-                           double *points, uint64_t *indexes, int capacity)
+static int pair_batch_chunk(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, const double K[9],
+                            const mvs_match_params *mparams, const mvs_ransac_params *rparams,
+                            mvs_pair_result *results, mvs_match *matches, uint8_t *inlier_mask,
+                            double *points, uint64_t *indexes, int capacity)
 {
-    if (!ctx) return MVS_E_BAD_ARG;
-    if (!pairs || n_pairs < 1 || !K || !results) return fail(ctx, MVS_E_BAD_ARG, "null argument or n_pairs < 1");
     if (ctx->h_cnt.empty()) return fail(ctx, MVS_E_BAD_ARG, "no frames uploaded (mvs_frames_upload)");
     const int nf = (int)ctx->h_cnt.size();
     int max_nq = 0, max_nt = 0;
@@ -719,6 +720,8 @@ int mvs_pair_batch_enqueue(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, cons
     }
     const bool details = matches || inlier_mask || points || indexes;
     if (details && capacity < 1) return fail(ctx, MVS_E_CAPACITY, "detail capacity must be >= 1");
+    if ((size_t)finalize_sort_capacity(max_nq) * sizeof(uint32_t) > 200 * 1024)
+        return fail(ctx, MVS_E_UNSUPPORTED, "more than 32768 keypoints in a pair frame");
     RansacCfg rc;
     int st = resolve_ransac(ctx, rparams, K, rc);
     if (st != MVS_OK) return st;
@@ -777,6 +780,29 @@ int mvs_pair_batch_enqueue(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, cons
         CK(cudaMemcpy2DAsync(points, (size_t)capacity * 24, ctx->d_opts.p, (size_t)qs * 24, w * 24, n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
     if (indexes)
         CK(cudaMemcpy2DAsync(indexes, (size_t)capacity * 8, ctx->d_oidx.p, (size_t)qs * 8, w * 8, n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+    return MVS_OK;
+}
+
+int mvs_pair_batch_enqueue(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, const double K[9],
+                           const mvs_match_params *mparams, const mvs_ransac_params *rparams,
+                           mvs_pair_result *results, mvs_match *matches, uint8_t *inlier_mask,
+                           double *points, uint64_t *indexes, int capacity)
+{
+    if (!ctx) return MVS_E_BAD_ARG;
+    if (!pairs || n_pairs < 1 || !K || !results) return fail(ctx, MVS_E_BAD_ARG, "null argument or n_pairs < 1");
+    // grid.z carries the pair index (<= 65535) and the workspace scales with the batch: large batches run
+    // as stream-ordered chunks; sampling stays invariant through pair_id_base
+    constexpr int kChunk = 8192;
+    for (int c0 = 0; c0 < n_pairs; c0 += kChunk) {
+        const int n = std::min(kChunk, n_pairs - c0);
+        mvs_ransac_params rp = rparams ? *rparams : mvs_ransac_params{1, MVS_SCORE_ALGEBRAIC, 0.0, 0, 0, 0, 0};
+        rp.pair_id_base += (uint64_t)c0;
+        const size_t o = (size_t)c0 * (size_t)std::max(capacity, 0);
+        int st = pair_batch_chunk(ctx, pairs + 2 * (size_t)c0, n, K, mparams, &rp, results + c0,
+                                  matches ? matches + o : nullptr, inlier_mask ? inlier_mask + o : nullptr,
+                                  points ? points + 3 * o : nullptr, indexes ? indexes + o : nullptr, capacity);
+        if (st != MVS_OK) return st;
+    }
     return MVS_OK;
 }
 

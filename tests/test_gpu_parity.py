@@ -402,3 +402,17 @@ dist.barrier(); dist.destroy_process_group()
     with mvs.Context(0) as c:
         single = shard.solve_pairs_sharded(c, descs, kps, pairs, tsukuba["K"], max_dist=30.0, H=128, seed=11)
     assert multi.tobytes() == single.tobytes()
+
+
+def test_pair_batch_large_batch_is_chunked_consistently(ctx, tsukuba):
+    """More pairs than one launch carries (grid.z / workspace chunks of 8192): same records as small batches,
+    sampling tied to the global pair index."""
+    descs = [tsukuba[f"desc{i}"][:300] for i in range(1, 6)]; kps = [tsukuba[f"kp{i}"][:300] for i in range(1, 6)]
+    base = [(a, b) for a in range(5) for b in range(5) if a != b]
+    pairs = np.array([base[i % len(base)] for i in range(9000)], np.int32)
+    ctx.frames_upload(descs, kps)
+    big, _ = ctx.pair_batch(pairs, tsukuba["K"], max_dist=40.0, H=8, seed=2, details=False)
+    lo, hi = 8150, 8250                      # straddles the chunk boundary
+    small, _ = ctx.pair_batch(pairs[lo:hi], tsukuba["K"], max_dist=40.0, H=8, seed=2, details=False, pair_id_base=lo)
+    assert big[lo:hi].tobytes() == small.tobytes()
+    assert (big["status"] == mvs.OK).sum() > 0
