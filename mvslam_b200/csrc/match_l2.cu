@@ -116,7 +116,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
 }
 
 // ------------------------------------------------------------------------------------------ small kernels
-__global__ void l2_norms_kernel(const float *x, int n, int n_padded, int ld, int dim, float *out)
+// squared norms (+inf padding) and their maximum (bit pattern order == value order for floats >= 0)
+__global__ void l2_norms_kernel(const float *x, int n, int n_padded, int ld, int dim, float *out, unsigned int *max_bits)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_padded) return;
@@ -124,6 +125,8 @@ __global__ void l2_norms_kernel(const float *x, int n, int n_padded, int ld, int
     float s = 0.f;
     for (int k = 0; k < dim; ++k) s = fmaf(x[(size_t)i * ld + k], x[(size_t)i * ld + k], s);
     out[i] = s;
+    const unsigned m = __reduce_max_sync(__activemask(), __float_as_uint(s));
+    if ((threadIdx.x & 31) == (__ffs(__activemask()) - 1)) atomicMax(max_bits, m);
 }
 
 __global__ void l2_pad_kernel(const float *src, int n, int dim, float *dst, int ld)
@@ -136,11 +139,11 @@ __global__ void l2_pad_kernel(const float *src, int n, int dim, float *dst, int 
 
 // ------------------------------------------------------------------------------------------ GEMM + top-KC
 template <int KSLABS, int STAGES>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
 l2_gemm_topk_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapT,
                     const float *__restrict__ t2 /* padded with +inf to a multiple of BN */,
-                    const float *__restrict__ q2, float tmax, int nq, int nt, int tiles_per_split, int splits,
-                    float *__restrict__ cand_val, int32_t *__restrict__ cand_idx, int32_t *__restrict__ cand_cnt)
+                    const float *__restrict__ q2, const unsigned int *__restrict__ tmax2_bits, int nq, int nt,
+                    int tiles_per_split, int splits, float *__restrict__ cand_val, int32_t *__restrict__ cand_idx, int32_t *__restrict__ cand_cnt)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: A (KSLABS x 16 KB), B (STAGES x KSLABS x 16 KB), t2 tiles (2 x BN floats), barriers
@@ -220,6 +223,7 @@ l2_gemm_topk_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         int32_t *li = cand_idx + list * KC;
         // error bound of a = |t|^2 - 2 S_tf32: each operand keeps 10 mantissa bits
         const float qn = sqrtf(q2[min(q, nq - 1)]);
+        const float tmax = sqrtf(__uint_as_float(*tmax2_bits));
         const float twoE = 2.f * (qn * tmax * 0.0041f + 2e-6f * (tmax * tmax + 2.f * qn * tmax));
         // rows beyond nq (zero-filled by TMA) never list anything: their threshold is -inf
         float b1 = CUDART_INF_F, b2 = CUDART_INF_F, thr = (q < nq) ? CUDART_INF_F : -CUDART_INF_F;
@@ -305,7 +309,8 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long k)
 // one warp per query: lists -> global second-best approximate score a2 -> exact distances of the entries
 // with a <= a2 + 2E -> top-2 by (distance, index).  A list that overflowed flags the query for the exact kernel.
 __global__ void l2_rerank_kernel(const float *__restrict__ Q, const float *__restrict__ T, int ldq, int ldt, int dim,
-                                 const float *__restrict__ q2, float tmax, int nq, int nt, int lists,
+                                 const float *__restrict__ q2, const unsigned int *__restrict__ tmax2_bits, int nq, int nt,
+                                 int lists,
                                  const float *__restrict__ cand_val, const int32_t *__restrict__ cand_idx,
                                  const int32_t *__restrict__ cand_cnt,
                                  int32_t *__restrict__ out_idx, float *__restrict__ out_d2, uint8_t *__restrict__ flag)
@@ -314,6 +319,7 @@ __global__ void l2_rerank_kernel(const float *__restrict__ Q, const float *__res
     const int lane = threadIdx.x & 31;
     if (q >= nq) return;
     const float qn = sqrtf(q2[q]);
+    const float tmax = sqrtf(__uint_as_float(*tmax2_bits));
     const float twoE = 2.f * (qn * tmax * 0.0041f + 2e-6f * (tmax * tmax + 2.f * qn * tmax));
     bool overflow = false;
     float a1 = CUDART_INF_F, a2 = CUDART_INF_F;
@@ -481,10 +487,10 @@ cudaError_t ensure(L2Workspace &ws, int i, size_t bytes)
 }
 
 template <int KSLABS>
-cudaError_t launch_gemm(const CUtensorMap &mq, const CUtensorMap &mt, const float *t2, const float *q2, float tmax, int nq,
+cudaError_t launch_gemm(const CUtensorMap &mq, const CUtensorMap &mt, const float *t2, const float *q2, const unsigned int *tmax, int nq,
                         int nt, int tiles_per_split, int splits, float *cv, int32_t *ci, int32_t *cc, cudaStream_t s)
 {
-    constexpr int STAGES = (KSLABS <= 2) ? 4 : 2;
+    constexpr int STAGES = 2;   // 2 CTAs per SM (<= 113 KB each): one CTA's MMA/TMA overlaps the other's epilogue
     const size_t smem = 1024 + (size_t)KSLABS * BM * 128 + (size_t)STAGES * KSLABS * BN * 128 +
                         (1 + 2 * STAGES + 4) * sizeof(uint64_t) + 16;
     auto kern = l2_gemm_topk_kernel<KSLABS, STAGES>;
@@ -512,7 +518,7 @@ void plan_splits(int na, int nb, int &splits, int &tiles_per_split)
     splits = 1;
     for (int s = 1; s <= smax; ++s) {
         const long ctas = (long)qtiles * s;
-        const double eff = (double)ctas / (double)(((ctas + 147) / 148) * 148);
+        const double eff = (double)ctas / (double)(((ctas + 295) / 296) * 296);   // 148 SMs x 2 resident CTAs
         if (eff > best_eff + 0.02) { best_eff = eff; splits = s; }
     }
     tiles_per_split = (tiles_total + splits - 1) / splits;
@@ -521,7 +527,7 @@ void plan_splits(int na, int nb, int &splits, int &tiles_per_split)
 
 // tensor-core pass: top-KC candidates per (row of A, split of B) into ws.buf[B_CAND_V/B_CAND_I]
 int gemm_candidates(L2Workspace &ws, cudaStream_t stream, const float *dA, int na, const float *dB, int nb, int ld,
-                    int kpad, const float *d_normB, const float *d_normA, float bmax, int splits, int tiles_per_split,
+                    int kpad, const float *d_normB, const float *d_normA, const unsigned int *bmax, int splits, int tiles_per_split,
                     std::string &err)
 {
     L2CK(ensure(ws, B_CAND_V, (size_t)na * splits * 2 * KC * sizeof(float)));
@@ -584,20 +590,19 @@ int l2_knn2(L2Workspace &ws, cudaStream_t stream, const float *query, int nq, co
         nl += 2;
     }
     // norms, |t|max (host reduction of nt floats: part of the error bound, not of the distance computation)
-    // squared norms, each array padded with +inf to a multiple of the column tile (padded columns never win)
+    // squared norms, each array padded with +inf to a multiple of the column tile (padded columns never win);
+    // their maxima stay on the device (error bound of the TF32 contraction)
     const size_t nqp = ((size_t)nq + BN - 1) / BN * BN, ntp = ((size_t)nt + BN - 1) / BN * BN;
     L2CK(ensure(ws, B_NORM, (nqp + ntp) * sizeof(float)));
+    L2CK(ensure(ws, B_MISC, 128));
+    unsigned int *d_nfb = (unsigned int *)ws.buf[B_MISC];      // [0..1] fallback counters, [4] n_out, [8..9] max |q|^2, |t|^2
+    int32_t *d_nout = (int32_t *)(d_nfb + 4);
+    unsigned int *d_max = d_nfb + 8;
+    L2CK(cudaMemsetAsync(d_nfb, 0, 128, stream));
     float *nQ = (float *)ws.buf[B_NORM], *nT = nQ + nqp;
-    l2_norms_kernel<<<(unsigned)((nqp + 255) / 256), 256, 0, stream>>>(dQ, nq, (int)nqp, kpad, dim, nQ);
-    l2_norms_kernel<<<(unsigned)((ntp + 255) / 256), 256, 0, stream>>>(dT, nt, (int)ntp, kpad, dim, nT);
+    l2_norms_kernel<<<(unsigned)((nqp + 255) / 256), 256, 0, stream>>>(dQ, nq, (int)nqp, kpad, dim, nQ, d_max);
+    l2_norms_kernel<<<(unsigned)((ntp + 255) / 256), 256, 0, stream>>>(dT, nt, (int)ntp, kpad, dim, nT, d_max + 1);
     nl += 2;
-    std::vector<float> hn(nqp + ntp);
-    L2CK(cudaMemcpyAsync(hn.data(), nQ, hn.size() * sizeof(float), cudaMemcpyDeviceToHost, stream));
-    L2CK(cudaStreamSynchronize(stream));
-    float qmax = 0.f, tmax = 0.f;
-    for (int i = 0; i < nq; ++i) qmax = std::max(qmax, hn[i]);
-    for (int i = 0; i < nt; ++i) tmax = std::max(tmax, hn[nqp + i]);
-    qmax = std::sqrt(qmax); tmax = std::sqrt(tmax);
 
     const int passes = cross ? 2 : 1;
     // outputs: forward idx/d2/dist/flag, reverse idx/d2/flag
@@ -608,17 +613,13 @@ int l2_knn2(L2Workspace &ws, cudaStream_t stream, const float *query, int nq, co
     uint8_t *f_flag = (uint8_t *)(f_dist + 2 * (size_t)nq);
     uint8_t *rb = ob + ((per_f + 15) & ~(size_t)15);
     int32_t *r_idx = (int32_t *)rb; float *r_d2 = (float *)(r_idx + 2 * (size_t)nt); uint8_t *r_flag = (uint8_t *)(r_d2 + 2 * (size_t)nt);
-    L2CK(ensure(ws, B_MISC, 64));
-    unsigned int *d_nfb = (unsigned int *)ws.buf[B_MISC];
-    int32_t *d_nout = (int32_t *)(d_nfb + 4);
-    L2CK(cudaMemsetAsync(d_nfb, 0, 64, stream));
 
     for (int pass = 0; pass < passes; ++pass) {
         const float *A = pass == 0 ? dQ : dT, *Bm = pass == 0 ? dT : dQ;
         const int na = pass == 0 ? nq : nt, nb = pass == 0 ? nt : nq;
         float *nA = pass == 0 ? nQ : nT, *nB = pass == 0 ? nT : nQ;
         int32_t *o_idx = pass == 0 ? f_idx : r_idx; float *o_d2 = pass == 0 ? f_d2 : r_d2; uint8_t *o_flag = pass == 0 ? f_flag : r_flag;
-        const float bmax = pass == 0 ? tmax : qmax;
+        const unsigned int *bmax = pass == 0 ? d_max + 1 : d_max;
         int splits, tps;
         plan_splits(na, nb, splits, tps);
         cudaEventRecord(ws.ev[2], stream);
