@@ -169,7 +169,7 @@ int resolve_ransac(mvs_ctx *ctx, const mvs_ransac_params *rp, const double *K, R
 }
 
 // K3..K5 (+K6,K7) over n_pairs pairs whose correspondences sit in d_points[pairs][p_stride][6]
-int run_geometry(mvs_ctx *ctx, int n_pairs, int p_stride, const RansacCfg &rc, bool unit_z, const uint32_t *d_table,
+int run_geometry(mvs_ctx *ctx, int n_pairs, int p_stride, const RansacCfg &rc, bool unit_z, double zc1, double zc2, const uint32_t *d_table,
                  uint64_t pair_id_base, bool decompose, bool want_all_counts, const mvs_match *d_matches)
 {
     const int tiles = score_tiles(p_stride);
@@ -192,7 +192,7 @@ int run_geometry(mvs_ctx *ctx, int n_pairs, int p_stride, const RansacCfg &rc, b
         StageTimer t(ctx, MVS_STAGE_SCORE);
         ScoreArgs a{};
         a.points = ctx->d_points.as<double>(); a.p_stride = p_stride; a.state = state; a.F_all = ctx->d_Fall.as<double>();
-        a.H = rc.H; a.max_error_sq = rc.thr; a.tiles = tiles; a.part_count = ctx->d_pc.as<uint32_t>();
+        a.H = rc.H; a.max_error_sq = rc.thr; a.zc1 = zc1; a.zc2 = zc2; a.tiles = tiles; a.part_count = ctx->d_pc.as<uint32_t>();
         a.part_res = k4_res ? ctx->d_pres.as<double>() : nullptr;
         launch_score(a, rc.mode, unit_z, n_pairs, ctx->stream);
     }
@@ -202,7 +202,7 @@ int run_geometry(mvs_ctx *ctx, int n_pairs, int p_stride, const RansacCfg &rc, b
         a.points = ctx->d_points.as<double>(); a.p_stride = p_stride; a.state = state; a.F_all = ctx->d_Fall.as<double>();
         a.H = rc.H; a.part_count = ctx->d_pc.as<uint32_t>(); a.ties = ctx->d_pr.as<int32_t>(); a.tiles = tiles;
         a.part_res = k4_res ? ctx->d_pres.as<double>() : nullptr;
-        a.max_error_sq = rc.thr; a.min_inliers = rc.min_inl; a.decompose = decompose ? 1 : 0;
+        a.max_error_sq = rc.thr; a.zc1 = zc1; a.zc2 = zc2; a.min_inliers = rc.min_inl; a.decompose = decompose ? 1 : 0;
         a.mask = ctx->d_mask.as<uint8_t>(); a.all_counts = want_all_counts ? ctx->d_counts.as<int32_t>() : nullptr;
         launch_select(a, rc.mode, unit_z, n_pairs, ctx->stream);
     }
@@ -241,7 +241,8 @@ int choose_splits(int q_tiles, int n_pairs, int nt_max)
     return (int)std::min<long>(s, 64);
 }
 
-bool unit_z_intrinsics(const double Ki[9]) { return Ki[6] == 0.0 && Ki[7] == 0.0 && Ki[8] == 1.0; }
+// K^-1 (u,v,1) has the constant z = Kinv[8] for every point when the last row of K^-1 is (0, 0, c)
+bool unit_z_intrinsics(const double Ki[9]) { return Ki[6] == 0.0 && Ki[7] == 0.0; }
 
 }  // namespace
 
@@ -541,17 +542,18 @@ int mvs_ransac_fundamental(mvs_ctx *ctx, const double *p1, const double *p2, int
     if (st != MVS_OK) return st;
     CK(cudaSetDevice(ctx->device));
     std::vector<double> inter((size_t)n * 6);
-    bool unit_z = true;
+    bool unit_z = true;   // "constant z per image": the points come from K^-1 (u,v,1)
+    const double zc1 = p1[2], zc2 = p2[2];
     for (int i = 0; i < n; ++i) {
         for (int k = 0; k < 3; ++k) { inter[(size_t)i * 6 + k] = p1[(size_t)i * 3 + k]; inter[(size_t)i * 6 + 3 + k] = p2[(size_t)i * 3 + k]; }
-        unit_z = unit_z && p1[(size_t)i * 3 + 2] == 1.0 && p2[(size_t)i * 3 + 2] == 1.0;
+        unit_z = unit_z && p1[(size_t)i * 3 + 2] == zc1 && p2[(size_t)i * 3 + 2] == zc2;
     }
     CK(ctx->d_points.ensure(inter.size() * sizeof(double)));
     CK(cudaMemcpyAsync(ctx->d_points.p, inter.data(), inter.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     const uint32_t *d_table = nullptr;
     if ((st = upload_table(ctx, samples, rc.H, n, &d_table)) != MVS_OK) return st;
     if ((st = init_state(ctx, n)) != MVS_OK) return st;
-    if ((st = run_geometry(ctx, 1, n, rc, unit_z, d_table, rc.pair_base, false, all_counts != nullptr, nullptr)) != MVS_OK) return st;
+    if ((st = run_geometry(ctx, 1, n, rc, unit_z, zc1, zc2, d_table, rc.pair_base, false, all_counts != nullptr, nullptr)) != MVS_OK) return st;
     PairState hs;
     CK(cudaMemcpyAsync(&hs, ctx->d_state.p, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
     if (inlier_mask) CK(cudaMemcpyAsync(inlier_mask, ctx->d_mask.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -593,7 +595,7 @@ int mvs_sfm_solve(mvs_ctx *ctx, const double *xy1, const double *xy2, int n, con
         launch_normalize_points(ctx->d_in1.as<double>(), ctx->d_in2.as<double>(), n, na, ctx->d_points.as<double>(),
                                 ctx->d_state.as<PairState>(), ctx->stream);
     }
-    if ((st = run_geometry(ctx, 1, n, rc, unit_z, d_table, rc.pair_base, true, false, nullptr)) != MVS_OK) return st;
+    if ((st = run_geometry(ctx, 1, n, rc, unit_z, na.Kinv[8], na.Kinv[8], d_table, rc.pair_base, true, false, nullptr)) != MVS_OK) return st;
     CK(cudaMemcpyAsync(result, ctx->d_results.p, sizeof(*result), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if (inlier_mask && result->status != MVS_E_TOO_FEW_POINTS)
@@ -766,7 +768,7 @@ static int pair_batch_chunk(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, con
         StageTimer t(ctx, MVS_STAGE_MATCH_FINALIZE);
         CK(launch_match_finalize(fa, max_nq, n_pairs, ctx->stream));
     }
-    if ((st = run_geometry(ctx, n_pairs, qs, rc, unit_z, nullptr, rc.pair_base, true, false, ctx->d_matches.as<mvs_match>())) != MVS_OK) return st;
+    if ((st = run_geometry(ctx, n_pairs, qs, rc, unit_z, fa.Kinv[8], fa.Kinv[8], nullptr, rc.pair_base, true, false, ctx->d_matches.as<mvs_match>())) != MVS_OK) return st;
 
     CK(cudaMemcpyAsync(results, ctx->d_results.p, (size_t)n_pairs * sizeof(mvs_pair_result), cudaMemcpyDeviceToHost, ctx->stream));
     // details: the first min(capacity, stride) entries of every pair (a pair with n_matches > capacity is truncated)

@@ -264,17 +264,29 @@ __device__ __forceinline__ void se3_inverse(const double R[9], const double t[3]
 // Residual of one correspondence, r = (p2^T F) p1 (estimator-RANSAC.cpp:114-116).
 // ALGEBRAIC: inlier iff |r| < thr, residual |r|.  SAMPSON: inlier iff r^2 < thr * den (den > 0, i.e.
 // r^2/den < thr without the division), residual r^2/den computed for inliers only.
-// UNIT_Z: both points have z == 1.0 exactly, so the multiplications by z are exact no-ops.
-template <bool UNIT_Z, int MODE, bool WANT_RES = true>
+// CONST_Z: every point of image 1 has the same z (= zc.z1) and every point of image 2 the same z (= zc.z2),
+// which is what K^-1 (u,v,1) produces for a pinhole K (z = Kinv[8], usually 1 - 1ulp, not exactly 1).  The
+// products z*F are then per-hypothesis constants (FzConst) — the same operands, hence the same bits, as
+// multiplying per point.
+struct FzConst { double z1, F2z, F5z, F6z, F7z, F8z; };
+
+__device__ __forceinline__ FzConst make_fz(const double (&F)[9], double z1, double z2)
+{
+    FzConst c;
+    c.z1 = z1; c.F2z = F[2] * z1; c.F5z = F[5] * z1; c.F6z = z2 * F[6]; c.F7z = z2 * F[7]; c.F8z = z2 * F[8];
+    return c;
+}
+
+template <bool CONST_Z, int MODE, bool WANT_RES = true>
 __device__ __forceinline__ bool point_residual(double x1, double y1, double z1, double x2, double y2, double z2,
-                                               const double (&F)[9], double thr, double &res)
+                                               const double (&F)[9], const FzConst &zc, double thr, double &res)
 {
     double v0, v1, v2, r;
-    if (UNIT_Z) {
-        v0 = fma(x2, F[0], fma(y2, F[3], F[6]));
-        v1 = fma(x2, F[1], fma(y2, F[4], F[7]));
-        v2 = fma(x2, F[2], fma(y2, F[5], F[8]));
-        r = fma(v0, x1, fma(v1, y1, v2));
+    if (CONST_Z) {
+        v0 = fma(x2, F[0], fma(y2, F[3], zc.F6z));
+        v1 = fma(x2, F[1], fma(y2, F[4], zc.F7z));
+        v2 = fma(x2, F[2], fma(y2, F[5], zc.F8z));
+        r = fma(v0, x1, fma(v1, y1, v2 * zc.z1));
     } else {
         v0 = fma(x2, F[0], fma(y2, F[3], z2 * F[6]));
         v1 = fma(x2, F[1], fma(y2, F[4], z2 * F[7]));
@@ -286,9 +298,9 @@ __device__ __forceinline__ bool point_residual(double x1, double y1, double z1, 
         return res < thr;
     }
     double l0, l1;
-    if (UNIT_Z) {
-        l0 = fma(F[0], x1, fma(F[1], y1, F[2]));
-        l1 = fma(F[3], x1, fma(F[4], y1, F[5]));
+    if (CONST_Z) {
+        l0 = fma(F[0], x1, fma(F[1], y1, zc.F2z));
+        l1 = fma(F[3], x1, fma(F[4], y1, zc.F5z));
     } else {
         l0 = fma(F[0], x1, fma(F[1], y1, F[2] * z1));
         l1 = fma(F[3], x1, fma(F[4], y1, F[5] * z1));

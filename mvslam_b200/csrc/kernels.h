@@ -52,6 +52,7 @@ struct ScoreArgs {
     const PairState *state; int n_fixed;
     const double *F_all; int H;
     double max_error_sq;
+    double zc1, zc2;           // constant z of image 1 / image 2 points (const-z kernels)
     int tiles;                 // point tiles per pair
     uint32_t *part_count;      // [pairs][tiles][H]
     double *part_res;          // [pairs][tiles][H] residual sums (ALGEBRAIC mode only, else nullptr)
@@ -65,6 +66,7 @@ struct SelectArgs {
     const double *part_res;    // per-tile residual sums when K4 produced them (ALGEBRAIC), else nullptr
     int32_t *ties;             // scratch [pairs][2][H]: total counts, then the hypotheses sharing the best count
     double max_error_sq;
+    double zc1, zc2;
     int min_inliers;
     int decompose;             // 0: stop after the mask (mvs_ransac_fundamental)
     uint8_t *mask;             // [pairs][p_stride]
@@ -99,8 +101,8 @@ void launch_normalize_points(const double *xy1, const double *xy2, int n, const 
 void launch_hypotheses(const HypArgs &a, int n_pairs, cudaStream_t s);
 void launch_fundamental_sets(const double *p1s, const double *p2s, int n_sets, double *F_out, cudaStream_t s);
 int score_tiles(int max_points);
-void launch_score(const ScoreArgs &a, int mode, bool unit_z, int n_pairs, cudaStream_t s);
-void launch_select(const SelectArgs &a, int mode, bool unit_z, int n_pairs, cudaStream_t s);
+void launch_score(const ScoreArgs &a, int mode, bool const_z, int n_pairs, cudaStream_t s);
+void launch_select(const SelectArgs &a, int mode, bool const_z, int n_pairs, cudaStream_t s);
 void launch_triangulate(const TriArgs &a, int max_points, int n_pairs, cudaStream_t s);
 void launch_finish(const FinishArgs &a, int n_pairs, cudaStream_t s);
 

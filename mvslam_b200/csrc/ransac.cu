@@ -216,6 +216,7 @@ score_kernel(ScoreArgs a)
     const double *Fg = a.F_all + ((size_t)pair * a.H + h) * 9;
 #pragma unroll
     for (int i = 0; i < 9; ++i) F[i] = Fg[i];
+    const FzConst zc = make_fz(F, a.zc1, a.zc2);
     const double thr = a.max_error_sq;
     uint32_t c = 0;
     double res = 0.0;
@@ -227,12 +228,12 @@ score_kernel(ScoreArgs a)
         if (UNIT_Z) {
             const double2 u = *reinterpret_cast<const double2 *>(sp + 4 * i);
             const double2 v = *reinterpret_cast<const double2 *>(sp + 4 * i + 2);
-            in = point_residual<true, MODE, kRes>(u.x, u.y, 1.0, v.x, v.y, 1.0, F, thr, r);
+            in = point_residual<true, MODE, kRes>(u.x, u.y, 0.0, v.x, v.y, 0.0, F, zc, thr, r);
         } else {
             const double2 u = *reinterpret_cast<const double2 *>(sp + 6 * i);
             const double2 v = *reinterpret_cast<const double2 *>(sp + 6 * i + 2);
             const double2 w = *reinterpret_cast<const double2 *>(sp + 6 * i + 4);
-            in = point_residual<false, MODE, kRes>(u.x, u.y, v.x, v.y, w.x, w.y, F, thr, r);
+            in = point_residual<false, MODE, kRes>(u.x, u.y, v.x, v.y, w.x, w.y, F, zc, thr, r);
         }
         c += in ? 1u : 0u;
         if (kRes && in) res += r;
@@ -368,11 +369,12 @@ select_kernel(SelectArgs a)
             const double *Fg = a.F_all + ((size_t)pair * a.H + h) * 9;
 #pragma unroll
             for (int i = 0; i < 9; ++i) F[i] = Fg[i];
+            const FzConst zc = make_fz(F, a.zc1, a.zc2);
             double res = 0.0;
             for (int i = sub; i < n; i += L) {
                 const double *p = pts + (size_t)i * 6;
                 double r;
-                if (point_residual<UNIT_Z, MODE>(p[0], p[1], p[2], p[3], p[4], p[5], F, a.max_error_sq, r)) res += r;
+                if (point_residual<UNIT_Z, MODE>(p[0], p[1], p[2], p[3], p[4], p[5], F, zc, a.max_error_sq, r)) res += r;
             }
             for (int off = L >> 1; off > 0; off >>= 1) res += __shfl_xor_sync(__activemask(), res, off);
             Best x; x.cnt = cmax; x.res = res; x.h = h;
@@ -428,11 +430,12 @@ select_kernel(SelectArgs a)
     double F[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) F[i] = s_F[i];
+    const FzConst zc = make_fz(F, a.zc1, a.zc2);
     uint8_t *mask = a.mask + (size_t)pair * a.p_stride;
     for (int i = threadIdx.x; i < n; i += SEL_THREADS) {
         const double *p = pts + (size_t)i * 6;
         double r;
-        mask[i] = point_residual<UNIT_Z, MODE, false>(p[0], p[1], p[2], p[3], p[4], p[5], F, a.max_error_sq, r) ? 1 : 0;
+        mask[i] = point_residual<UNIT_Z, MODE, false>(p[0], p[1], p[2], p[3], p[4], p[5], F, zc, a.max_error_sq, r) ? 1 : 0;
     }
 }
 
