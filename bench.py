@@ -327,6 +327,12 @@ def main():
     mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(mp):
         hbm_peak = json.load(open(mp)).get("hbm_gbs", hbm_peak)
+    traffic = None      # dram read+write bytes per launch from the committed ncu --set full capture of this workload
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        if tj.get("workload") == cfg["workload"] and B == 1024:
+            traffic = tj["dram_bytes"].get("knn2_hamming_kernel")
     tot_ms = max(sum(v[0] for v in prof.values()), 1e-9)
     stage_share = {s: round(prof[s][0] / tot_ms, 4) for s in mvs.STAGES[:7]}
     roofline = dict(kernel="knn2_hamming_kernel", bound="int-pipes (XU popc / ALU lop3); not hbm, not tensor",
@@ -340,7 +346,7 @@ def main():
                     hbm=dict(algorithmic_bytes=alg_bytes, achieved_gbs=alg_bytes / launch_s / 1e9, peak_gbs=hbm_peak,
                              frac=alg_bytes / launch_s / 1e9 / hbm_peak,
                              note="compute-bound kernel: the HBM fraction is reported for completeness only"),
-                    traffic=None, stage_share=stage_share,
+                    traffic=traffic, stage_share=stage_share,
                     stage_ms_per_step={s: round(prof[s][0] / args.steps, 4) for s in mvs.STAGES[:7]})
     scored = res["n_matches"] >= 8                           # pairs that reach RANSAC
     m_total = int(res["n_matches"][scored].astype(np.int64).sum())

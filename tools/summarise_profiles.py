@@ -101,6 +101,20 @@ if os.path.exists(lp):
         for k, v in sorted(agg.items(), key=lambda x: -x[1][1]):
             f.write(f"| {k} | {v[0]} | {v[1]:.1f} | {v[1] / tot:.3f} |\n")
 
+# DRAM traffic per launch of every kernel of the default workload (bench.py fills roofline.traffic from it)
+pp = os.path.join(G, f"prof_path_{R}.ncu-rep")
+if os.path.exists(pp):
+    H, U, data = raw(pp)
+    idx = {h: i for i, h in enumerate(H)}
+    traffic = {}
+    for r in data:
+        name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "").replace("mvs::", "").split("<")[0]
+        scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        b = sum(float(r[idx[k]].replace(",", "")) * scale.get(U[idx[k]], 1) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        traffic[name] = int(b)
+    json.dump(dict(workload="tsukuba_vo_2k", source=f"profiles/ncu_summary_{R}.md (ncu --set full, per launch)", dram_bytes=traffic),
+              open(os.path.join(P, "ncu_traffic.json"), "w"), indent=1)
+
 for f in os.listdir(G):
     if f.endswith(f"_{R}.json"):
         shutil.copy(os.path.join(G, f), os.path.join(P, f))
