@@ -161,6 +161,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=0, help="pairs per step per GPU (default 1024 tsukuba / 64 s8k)")
     ap.add_argument("--hypotheses", type=int, default=0, help="RANSAC sample-table rows (default 1024 tsukuba / 4096 s8k)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bounded", action="store_true", help="opt-in early-abandon matcher (identical matches, less work)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     B = args.pairs or {"tsukuba": 1024, "s8k": 64, "w512": 0}[args.workload]
@@ -213,7 +214,8 @@ def main():
                    indexes=idx_t.data_ptr(), capacity=cap) if not strong else out_rec
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
     kw = dict(max_dist=params["max_dist"], H=params["H"], seed=params["seed"], mode=params["mode"],
-              max_error_sq=params["max_error_sq"])
+              max_error_sq=params["max_error_sq"], bounded=args.bounded)
+    cfg["bounded_search"] = bool(args.bounded)
     item = mvs.RESULT_DTYPE.itemsize
 
     def upload():
@@ -285,6 +287,32 @@ def main():
     res = np.frombuffer(res_t.numpy(), dtype=mvs.RESULT_DTYPE)
     n_ok = int((res["status"] == 0).sum())
     assert int(res["n_matches"].max()) <= cap, "detail capacity too small for this workload"
+
+    # ---- optional extra: the same workload with the opt-in early-abandon matcher (identical results, less work)
+    bounded_extra = None
+    if params["max_dist"] >= 0 and not args.bounded and world == 1:
+        kwb = dict(kw, bounded=True)
+
+        def step_b():
+            for c0 in range(0, B, CH):
+                c1 = min(B, c0 + CH)
+                ctx.pair_batch(pairs[c0:c1], K, out=dict(results=res_t.data_ptr() + c0 * item), enqueue_only=True,
+                               pair_id_base=pair_base + c0, **kwb)
+        ref_bytes = res_t.numpy().tobytes()
+        for _ in range(args.warmup):
+            flush.zero_(); step_b()
+        torch.cuda.synchronize()
+        evb = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        ctx.profile_enable(True); ctx.profile_read(reset=True)
+        for a, b in evb:
+            flush.zero_(); a.record(stream); step_b(); b.record(stream)
+        torch.cuda.synchronize()
+        pb = ctx.profile_read(); ctx.profile_enable(False)
+        msb = sum(a.elapsed_time(b) for a, b in evb) / args.steps
+        bounded_extra = dict(value=B / (msb * 1e-3), unit="pairs/s", ms_per_step=msb, knn_ms_per_step=pb["knn"][0] / args.steps,
+                             identical_records=bool(res_t.numpy().tobytes() == ref_bytes),
+                             note="mvs_match_params.bounded=1: train descriptors provably beyond the ratio/max_dist decision "
+                                  "bound are abandoned after 96 bits; not used for `value`, `e2e` or `roofline`")
 
     # ---- end to end through the public call with host buffers (H2D of the frames + D2H of everything)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -374,7 +402,7 @@ def main():
                 clocks=clocks.summary(),
                 e2e=dict(value=n_job / (e2e_ms * 1e-3), unit="pairs/s", h2d_bytes_per_step=int(h2d),
                          d2h_bytes_per_step=int(d2h), ms_per_step=e2e_ms),
-                gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu,
+                gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, bounded_search=bounded_extra,
                 ransac=dict(hyp_pt_evals_per_s=evals / (score_ms * 1e-3) if score_ms > 0 else None,
                             evals_per_step=evals, score_ms_per_step=score_ms,
                             hypotheses_per_s=params["H"] * int(scored.sum()) / max(prof["hypotheses"][0] / args.steps * 1e-3, 1e-12)))

@@ -61,7 +61,9 @@ typedef struct {
     double  ratio;        /* NEAREST_NEIGHBOR_DIST_RATIO, 0.7 */
     double  max_dist;     /* < 0: keep all (match_visual_features default -1; VO default 10) */
     int32_t cross_check;  /* reference: CROSS_CHECK=false */
-    int32_t reserved;
+    int32_t bounded;      /* 1 (needs max_dist >= 0): early-abandon train descriptors that are provably too far to
+                             change the filtered result (distance >= B, B = smallest integer with ratio*B > max_dist):
+                             the returned matches are bit-identical, only the work shrinks.  0 = evaluate every pair. */
 } mvs_match_params;
 
 /* constants of sfm-solve.cpp:18-23,67 made explicit */

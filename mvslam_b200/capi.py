@@ -20,7 +20,7 @@ RESULT_DTYPE = np.dtype([
 
 
 class MatchParams(C.Structure):
-    _fields_ = [("ratio", C.c_double), ("max_dist", C.c_double), ("cross_check", C.c_int32), ("reserved", C.c_int32)]
+    _fields_ = [("ratio", C.c_double), ("max_dist", C.c_double), ("cross_check", C.c_int32), ("bounded", C.c_int32)]
 
 
 class RansacParams(C.Structure):
@@ -161,10 +161,10 @@ class Context:
                                              q.shape[1] if q.ndim == 2 else 0, _p(idx), _p(dist)))
         return idx, dist
 
-    def match_hamming(self, query, train, ratio=0.7, max_dist=-1.0, cross_check=False):
+    def match_hamming(self, query, train, ratio=0.7, max_dist=-1.0, cross_check=False, bounded=False):
         q = np.ascontiguousarray(query, np.uint8); t = np.ascontiguousarray(train, np.uint8)
         out = np.empty(max(q.shape[0], 1), MATCH_DTYPE); n = C.c_int(0)
-        mp = MatchParams(ratio, max_dist, int(cross_check), 0)
+        mp = MatchParams(ratio, max_dist, int(cross_check), int(bounded))
         self._check(self._L.mvs_match_hamming(self._h, _p(q), q.shape[0], _p(t), t.shape[0],
                                               q.shape[1] if q.ndim == 2 else 0, C.byref(mp), _p(out),
                                               out.shape[0], C.byref(n)))
@@ -248,11 +248,11 @@ class Context:
         self._frame_counts = counts
 
     def pair_batch(self, pairs, K, ratio=0.7, max_dist=-1.0, cross_check=False, H=1, seed=0, mode=SCORE_ALGEBRAIC,
-                   max_error_sq=0.0, pair_id_base=0, details=True, out=None, enqueue_only=False):
+                   max_error_sq=0.0, pair_id_base=0, details=True, out=None, enqueue_only=False, bounded=False):
         """Returns (results[RESULT_DTYPE], details dict or None).  `out` may hold preallocated (e.g. pinned)
         buffers: dict(results=addr/array, matches=, mask=, points=, indexes=, capacity=int)."""
         pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2); npairs = pairs.shape[0]
-        mp = MatchParams(ratio, max_dist, int(cross_check), 0)
+        mp = MatchParams(ratio, max_dist, int(cross_check), int(bounded))
         rp = RansacParams(H, mode, max_error_sq, seed, 0, 0, pair_id_base)
         fn = self._L.mvs_pair_batch_enqueue if enqueue_only else self._L.mvs_pair_batch
         if out is not None:

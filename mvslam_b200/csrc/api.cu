@@ -242,6 +242,16 @@ int choose_splits(int q_tiles, int n_pairs, int nt_max)
 }
 
 // K^-1 (u,v,1) has the constant z = Kinv[8] for every point when the last row of K^-1 is (0, 0, c)
+// bounded search (mvs_match_params.bounded): smallest integer B > max_dist with ratio * B > max_dist, evaluated
+// with the same double arithmetic as the filter; 0 disables (max_dist < 0, or nothing to gain)
+uint32_t search_bound(const mvs_match_params *mp)
+{
+    if (!mp || !mp->bounded || mp->max_dist < 0 || !(mp->ratio > 0)) return 0;
+    uint32_t b = (uint32_t)std::min(300.0, std::floor(mp->max_dist)) + 1;
+    while (b <= 256 && !(mp->ratio * (double)(float)b > mp->max_dist)) ++b;
+    return b > 256 ? 0 : b;      // beyond the largest possible distance: plain evaluation
+}
+
 bool unit_z_intrinsics(const double Ki[9]) { return Ki[6] == 0.0 && Ki[7] == 0.0; }
 
 }  // namespace
@@ -388,6 +398,7 @@ static int match_two_sets(mvs_ctx *ctx, const uint8_t *query, int nq, const uint
     KnnArgs ka{};
     ka.desc = ctx->t_desc.as<uint4>(); ka.frame_off = ctx->t_foff.as<int32_t>(); ka.frame_cnt = ctx->t_fcnt.as<int32_t>();
     ka.pairs = nullptr; ka.partial = ctx->d_partial.as<uint2>(); ka.q_stride = nq; ka.reverse = 0;
+    ka.bound = want_knn ? 0 : search_bound(mp);
     {
         StageTimer t(ctx, MVS_STAGE_KNN, cross ? 2 : 1);
         launch_knn2_hamming(ka, nq, splits, 1, ctx->stream);
@@ -401,7 +412,7 @@ static int match_two_sets(mvs_ctx *ctx, const uint8_t *query, int nq, const uint
     fa.frame_off = ka.frame_off; fa.frame_cnt = ka.frame_cnt; fa.pairs = nullptr;
     fa.partial = ka.partial; fa.splits = splits; fa.q_stride = nq;
     fa.rev_partial = cross ? ctx->d_rev.as<uint2>() : nullptr; fa.rev_splits = rsplits; fa.rev_stride = nt;
-    fa.ratio = mp ? mp->ratio : 0.7; fa.max_dist = mp ? mp->max_dist : -1.0;
+    fa.ratio = mp ? mp->ratio : 0.7; fa.max_dist = mp ? mp->max_dist : -1.0; fa.bound = ka.bound;
     fa.kp = nullptr; fa.matches = ctx->d_matches.as<mvs_match>(); fa.n_matches = ctx->d_nmatch.as<int32_t>();
     fa.points = nullptr; fa.state = nullptr;
     fa.knn_idx = want_knn ? ctx->d_knn_i.as<int32_t>() : nullptr; fa.knn_dist = want_knn ? ctx->d_knn_d.as<int32_t>() : nullptr;
@@ -744,6 +755,7 @@ static int pair_batch_chunk(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, con
     KnnArgs ka{};
     ka.desc = ctx->d_desc.as<uint4>(); ka.frame_off = ctx->d_foff.as<int32_t>(); ka.frame_cnt = ctx->d_fcnt.as<int32_t>();
     ka.pairs = ctx->d_pairs.as<int2>(); ka.partial = ctx->d_partial.as<uint2>(); ka.q_stride = qs; ka.reverse = 0;
+    ka.bound = search_bound(mparams);
     {
         StageTimer t(ctx, MVS_STAGE_KNN, cross ? 2 : 1);
         launch_knn2_hamming(ka, max_nq, splits, n_pairs, ctx->stream);
@@ -757,7 +769,7 @@ static int pair_batch_chunk(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, con
     fa.frame_off = ka.frame_off; fa.frame_cnt = ka.frame_cnt; fa.pairs = ka.pairs;
     fa.partial = ka.partial; fa.splits = splits; fa.q_stride = qs;
     fa.rev_partial = cross ? ctx->d_rev.as<uint2>() : nullptr; fa.rev_splits = rsplits; fa.rev_stride = max_nt;
-    fa.ratio = mparams ? mparams->ratio : 0.7; fa.max_dist = mparams ? mparams->max_dist : -1.0;
+    fa.ratio = mparams ? mparams->ratio : 0.7; fa.max_dist = mparams ? mparams->max_dist : -1.0; fa.bound = ka.bound;
     fa.kp = ctx->d_kp.as<float2>();
     h_inverse3(K, fa.Kinv);
     const bool unit_z = unit_z_intrinsics(fa.Kinv);

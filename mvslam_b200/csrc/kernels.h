@@ -15,6 +15,7 @@ struct KnnArgs {
     uint2 *partial;            // [pairs][splits][q_stride] packed (best1, best2) keys
     int q_stride;
     int reverse;               // 1: roles swapped (cross-check pass)
+    uint32_t bound;            // bounded search: distances >= bound are "far" (0 = evaluate everything)
 };
 
 struct FinalizeArgs {
@@ -24,6 +25,7 @@ struct FinalizeArgs {
     const uint2 *partial; int splits; int q_stride;
     const uint2 *rev_partial; int rev_splits; int rev_stride;
     double ratio, max_dist;
+    uint32_t bound;            // bounded search: recorded distances >= bound only mean "far" (0 = exact everywhere)
     const float2 *kp;          // nullptr: no gather
     double Kinv[9];
     mvs_match *matches;        // [pairs][q_stride]

@@ -49,6 +49,7 @@ __device__ __forceinline__ void top2_insert(uint32_t &b1, uint32_t &b2, uint32_t
     b2 = min(b2, hi);
 }
 
+template <bool BOUNDED>
 __global__ void __launch_bounds__(KNN_THREADS)
 knn2_hamming_kernel(KnnArgs a)
 {
@@ -83,11 +84,30 @@ knn2_hamming_kernel(KnnArgs a)
         __syncthreads();
         const uint32_t kbase = (uint32_t)t0;
         int j = 0;
+        if (BOUNDED) {
+            // early abandon: the first 96 bits already put this train descriptor at distance >= bound for
+            // every query of the warp -> it cannot change any filtered result (match_finalize_kernel)
 #pragma unroll 4
-        for (; j + 1 <= cnt; ++j) {
-            const uint4 ta = tile[2 * j], tb = tile[2 * j + 1];
-            const uint32_t d = hamming256(qa, qb, ta, tb);
-            top2_insert(b1, b2, (d << kIdxBits) + (kbase + (uint32_t)j));
+            for (; j + 1 <= cnt; ++j) {
+                const uint4 ta = tile[2 * j];
+                const uint32_t x0 = qa.x ^ ta.x, x1 = qa.y ^ ta.y, x2 = qa.z ^ ta.z;
+                const uint32_t s0 = x0 ^ x1 ^ x2, c0 = (x0 & x1) | (x2 & (x0 | x1));
+                const uint32_t pc0 = __popc(c0);
+                if (__all_sync(0xFFFFFFFFu, __popc(s0) + 2u * pc0 >= a.bound)) continue;
+                const uint4 tb = tile[2 * j + 1];
+                const uint32_t x3 = qa.w ^ ta.w, x4 = qb.x ^ tb.x, x5 = qb.y ^ tb.y, x6 = qb.z ^ tb.z, x7 = qb.w ^ tb.w;
+                const uint32_t s1 = x3 ^ x4 ^ x5, c1 = (x3 & x4) | (x5 & (x3 | x4));
+                const uint32_t s2 = s0 ^ s1 ^ x6, c2 = (s0 & s1) | (x6 & (s0 | s1));
+                const uint32_t d = (__popc(s2) + __popc(x7)) + 2u * (pc0 + __popc(c1) + __popc(c2));
+                top2_insert(b1, b2, (d << kIdxBits) + (kbase + (uint32_t)j));
+            }
+        } else {
+#pragma unroll 4
+            for (; j + 1 <= cnt; ++j) {
+                const uint4 ta = tile[2 * j], tb = tile[2 * j + 1];
+                const uint32_t d = hamming256(qa, qb, ta, tb);
+                top2_insert(b1, b2, (d << kIdxBits) + (kbase + (uint32_t)j));
+            }
         }
     }
     if (q < nq) a.partial[((size_t)pair * gridDim.y + blockIdx.y) * a.q_stride + q] = make_uint2(b1, b2);
@@ -133,10 +153,13 @@ match_finalize_kernel(FinalizeArgs a)
             ki[0] = b.x == kKeyNone ? -1 : (int)(b.x & kIdxMask); kd[0] = b.x == kKeyNone ? -1 : (int)(b.x >> kIdxBits);
             ki[1] = b.y == kKeyNone ? -1 : (int)(b.y & kIdxMask); kd[1] = b.y == kKeyNone ? -1 : (int)(b.y >> kIdxBits);
         }
-        if (b.y == kKeyNone || nt < 2) continue;
-        // the reference compares float distances promoted to double (visual-feature.cpp:66-68)
+        if (nt < 2) continue;
+        const bool far2 = a.bound && (b.y == kKeyNone || (b.y >> kIdxBits) >= a.bound);   // bounded search: d2 >= bound
+        if (b.x == kKeyNone || (b.y == kKeyNone && !far2)) continue;
+        // the reference compares float distances promoted to double (visual-feature.cpp:66-68);
+        // a "far" second neighbour passes the ratio test for every d1 <= max_dist by construction of the bound
         const double d1 = (double)(float)(b.x >> kIdxBits), d2 = (double)(float)(b.y >> kIdxBits);
-        bool keep = (d1 < a.ratio * d2) && ((a.max_dist < 0) || (d1 <= a.max_dist));
+        bool keep = (far2 || d1 < a.ratio * d2) && ((a.max_dist < 0) || (d1 <= a.max_dist));
         if (keep && rpart) {  // cross-check: q must be the nearest query of its train descriptor
             const uint2 rb = merge_partials(rpart, a.rev_splits, a.rev_stride, (int)(b.x & kIdxMask));
             keep = ((int)(rb.x & kIdxMask) == q);
@@ -224,7 +247,8 @@ __global__ void normalize_points_kernel(const double *xy1, const double *xy2, in
 void launch_knn2_hamming(const KnnArgs &a, int max_nq, int splits, int n_pairs, cudaStream_t s)
 {
     dim3 grid((max_nq + KNN_THREADS - 1) / KNN_THREADS, splits, n_pairs);
-    knn2_hamming_kernel<<<grid, KNN_THREADS, 0, s>>>(a);
+    if (a.bound) knn2_hamming_kernel<true><<<grid, KNN_THREADS, 0, s>>>(a);
+    else knn2_hamming_kernel<false><<<grid, KNN_THREADS, 0, s>>>(a);
 }
 
 int finalize_sort_capacity(int max_nq)

@@ -416,3 +416,32 @@ def test_pair_batch_large_batch_is_chunked_consistently(ctx, tsukuba):
     small, _ = ctx.pair_batch(pairs[lo:hi], tsukuba["K"], max_dist=40.0, H=8, seed=2, details=False, pair_id_base=lo)
     assert big[lo:hi].tobytes() == small.tobytes()
     assert (big["status"] == mvs.OK).sum() > 0
+
+
+@pytest.mark.parametrize("max_dist,cross", [(0.0, False), (10.0, False), (30.0, False), (64.0, True), (10.0, True), (200.0, False)])
+def test_bounded_search_returns_identical_matches(ctx, tsukuba, max_dist, cross):
+    """mvs_match_params.bounded: early-abandoned train descriptors can never change the filtered result."""
+    sets = [(tsukuba["desc2"], tsukuba["desc1"])]
+    d1, _, d2, _, _ = synth.synthetic_pair(21, n=2500)
+    sets.append((d2, d1))
+    rng = np.random.default_rng(3)                      # tie-heavy, small distances: many candidates inside the bound
+    a = np.zeros((700, 32), np.uint8); b = np.zeros((650, 32), np.uint8)
+    a[:, :2] = rng.integers(0, 256, (700, 2)); b[:, :2] = rng.integers(0, 256, (650, 2))
+    sets.append((a, b))
+    for q, t in sets:
+        full = ctx.match_hamming(q, t, 0.7, max_dist, cross, bounded=False)
+        fast = ctx.match_hamming(q, t, 0.7, max_dist, cross, bounded=True)
+        assert np.array_equal(full, fast)
+        assert np.array_equal(full, as_mvs(orc.match_hamming(q, t, 0.7, max_dist, cross)))
+
+
+def test_bounded_pair_batch_identical_records(ctx, tsukuba):
+    descs = [tsukuba[f"desc{i}"] for i in range(1, 6)]; kps = [tsukuba[f"kp{i}"] for i in range(1, 6)]
+    pairs = [(a, b) for a in range(5) for b in range(5) if a != b]
+    ctx.frames_upload(descs, kps)
+    for md in (10.0, 30.0):
+        r0, d0 = ctx.pair_batch(pairs, tsukuba["K"], max_dist=md, H=32, seed=1)
+        r1, d1 = ctx.pair_batch(pairs, tsukuba["K"], max_dist=md, H=32, seed=1, bounded=True)
+        assert r0.tobytes() == r1.tobytes()
+        for k in ("matches", "mask", "points", "indexes"):
+            assert np.array_equal(d0[k], d1[k])
