@@ -63,7 +63,7 @@ public:
         std::vector<mvs_match> matches((size_t)np * cap);
         std::vector<double> pts((size_t)np * cap * 3);
         std::vector<uint64_t> idx((size_t)np * cap);
-        const mvs_match_params mp{0.7, params.max_match_inlier_distance, 0, 0};
+        const mvs_match_params mp{0.7, params.max_match_inlier_distance, 0, 1};
         b200::check(ctx, mvs_pair_batch(ctx, pr.data(), np, K.m, &mp, &b200::ransac_defaults(), res.data(), matches.data(),
                                         nullptr, pts.data(), idx.data(), cap), "ImagePair: pair_batch");
         std::vector<ImagePair> out;

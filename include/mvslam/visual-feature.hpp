@@ -27,7 +27,7 @@ public:
         mvs_ctx *ctx = b200::Context::thread_default().get();
         std::vector<mvs_match> out(vf2.size());
         int n = 0;
-        const mvs_match_params mp{0.7, max_dist, 0, 0};
+        const mvs_match_params mp{0.7, max_dist, 0, 1};   // bounded: identical matches, less work when max_dist >= 0
         int st = mvs_match_hamming(ctx, vf2.m_descriptors.data(), (int)vf2.size(), vf1.m_descriptors.data(), (int)vf1.size(),
                                    32, &mp, out.data(), (int)out.size(), &n);
         b200::check(ctx, st, "match_visual_features");

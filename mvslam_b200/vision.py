@@ -45,7 +45,7 @@ class VisualFeature:
 def match_visual_features(vf1, vf2, max_dist=-1.0, ctx=None):
     """Matches from 2 to 1 (query = vf2, train = vf1), ascending distance; empty if none."""
     ctx = ctx or default_context()
-    return ctx.match_hamming(vf2.descriptors, vf1.descriptors, 0.7, float(max_dist), False)
+    return ctx.match_hamming(vf2.descriptors, vf1.descriptors, 0.7, float(max_dist), False, bounded=True)
 
 
 def sfm_solve(p1, p2, K, ctx=None, **kw):
@@ -65,4 +65,5 @@ def image_pairs(frames, pairs, K, max_match_inlier_distance=10.0, ctx=None, **kw
     """Batch of ImagePair constructions: frames = [VisualFeature], pairs = [(base, pair)]."""
     ctx = ctx or default_context()
     ctx.frames_upload([f.descriptors for f in frames], [f.keypoints for f in frames])
+    kw.setdefault("bounded", True)
     return ctx.pair_batch(pairs, K, max_dist=max_match_inlier_distance, **kw)
