@@ -111,8 +111,17 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
+def host_threads():
+    """all host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which must not throttle the CPU arm)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_pairs_per_s(descs, kps, K, pairs, params, n_sample, threads=0):
     from oracle import cbind as orc
+    threads = threads or host_threads()
     sample = pairs[np.arange(n_sample) % len(pairs)]
     t0 = time.perf_counter()
     orc.pair_batch(descs, kps, sample, K, max_dist=params["max_dist"], H=params["H"], seed=params["seed"],
@@ -128,7 +137,7 @@ def run_reference(args, cfg_loader):
         return
     from oracle import cbind as orc
     descs, kps, K, pairs, params, cfg = cfg_loader()
-    threads = orc.max_threads()
+    threads = host_threads()
     probe, dt = cpu_pairs_per_s(descs, kps, K, pairs, params, 2 * threads)
     # bounded sample per step: the whole --steps/--warmup run stays within ~2 minutes
     budget_s = 100.0 / max(args.steps + args.warmup, 1)
@@ -383,8 +392,7 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        from oracle import cbind as orc
-        threads = orc.max_threads()
+        threads = host_threads()
         probe, _ = cpu_pairs_per_s(descs, kps, K, pairs, params, 2 * threads)
         n_sample = int(max(threads, min(4 * B, probe * 12.0)))
         v, dt = cpu_pairs_per_s(descs, kps, K, pairs, params, n_sample)
