@@ -184,7 +184,7 @@ int run_geometry(mvs_ctx *ctx, int n_pairs, int p_stride, const RansacCfg &rc, b
     {
         StageTimer t(ctx, MVS_STAGE_HYPOTHESES);
         HypArgs a{};
-        a.points = ctx->d_points.as<double>(); a.p_stride = p_stride; a.state = state; a.n_fixed = 0;
+        a.points = ctx->d_points.as<double>(); a.p_stride = p_stride; a.state = state;
         a.table = d_table; a.seed = rc.seed; a.pair_id_base = pair_id_base; a.H = rc.H; a.F_all = ctx->d_Fall.as<double>();
         launch_hypotheses(a, n_pairs, ctx->stream);
     }

@@ -40,8 +40,7 @@ struct NormArgs { double Kinv[9]; };
 struct HypArgs {
     const double *points;      // [pairs][p_stride][6]
     int p_stride;
-    const PairState *state;    // n_matches / status per pair (nullptr: use n_fixed)
-    int n_fixed;
+    const PairState *state;    // n_matches / status per pair
     const uint32_t *table;     // explicit [H][8] sample table shared by all pairs, or nullptr -> seeded sampler
     uint64_t seed;
     uint64_t pair_id_base;
@@ -51,7 +50,7 @@ struct HypArgs {
 
 struct ScoreArgs {
     const double *points; int p_stride;
-    const PairState *state; int n_fixed;
+    const PairState *state;
     const double *F_all; int H;
     double max_error_sq;
     double zc1, zc2;           // constant z of image 1 / image 2 points (const-z kernels)
@@ -62,7 +61,7 @@ struct ScoreArgs {
 
 struct SelectArgs {
     const double *points; int p_stride;
-    PairState *state; int n_fixed;
+    PairState *state;
     const double *F_all; int H;
     const uint32_t *part_count; int tiles;
     const double *part_res;    // per-tile residual sums when K4 produced them (ALGEBRAIC), else nullptr
@@ -77,7 +76,7 @@ struct SelectArgs {
 
 struct TriArgs {
     const double *points; int p_stride;
-    PairState *state; int n_fixed;
+    PairState *state;
     const uint8_t *mask;       // nullptr: all ones
     int n_cand;                // 4 (recover_pose_and_points) or 1 (sfm_triangulate: Rc[0], tc as given)
     uint8_t *valid;            // [pairs][4][p_stride]
@@ -85,7 +84,7 @@ struct TriArgs {
 };
 
 struct FinishArgs {
-    PairState *state; int n_fixed; int p_stride;
+    PairState *state; int p_stride;
     int n_cand;
     const uint8_t *valid; const double *tri;
     const mvs_match *matches;  // optional, for match_inlier_ssd

@@ -1,7 +1,7 @@
 // ransac.cu — seeded RANSAC over the normalised 8-point fundamental-matrix estimator.
 //
 //   K3 hypotheses_kernel : find_fundamental_matrix (reference source/vision/fundamental-matrix.cpp:18-140,
-//                          204-267) for every row of the sample table, 3 hypotheses per warp.
+//                          204-267) for every row of the sample table, one thread per hypothesis.
 //   K4 score_kernel      : count_inliers (source/vision/estimator-RANSAC.cpp:100-129) on the
 //                          hypothesis x correspondence grid.
 //   K5 select_kernel     : best-model rule (estimator-RANSAC.cpp:76-84), inlier mask of the winner,
@@ -134,11 +134,8 @@ __global__ void __launch_bounds__(HYP_THREADS)
 hypotheses_kernel(HypArgs a)
 {
     const int pair = blockIdx.y;
-    int n = a.n_fixed;
-    if (a.state) {
-        if (a.state[pair].status != MVS_OK) return;
-        n = a.state[pair].n_matches;
-    }
+    if (a.state[pair].status != MVS_OK) return;
+    const int n = a.state[pair].n_matches;
     const int h = blockIdx.x * HYP_THREADS + threadIdx.x;
     if (h >= a.H) return;
     uint32_t idx[8];
@@ -192,11 +189,8 @@ score_kernel(ScoreArgs a)
     constexpr int W = UNIT_Z ? 4 : 6;
     __shared__ __align__(16) double sp[SC_TILE * W];
     const int pair = blockIdx.z, tile = blockIdx.y;
-    int n = a.n_fixed;
-    if (a.state) {
-        if (a.state[pair].status != MVS_OK) return;
-        n = a.state[pair].n_matches;
-    }
+    if (a.state[pair].status != MVS_OK) return;
+    const int n = a.state[pair].n_matches;
     const int p0 = tile * SC_TILE;
     if (p0 >= n) return;
     const int cnt = min(SC_TILE, n - p0);

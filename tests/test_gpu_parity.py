@@ -445,3 +445,27 @@ def test_bounded_pair_batch_identical_records(ctx, tsukuba):
         assert r0.tobytes() == r1.tobytes()
         for k in ("matches", "mask", "points", "indexes"):
             assert np.array_equal(d0[k], d1[k])
+
+
+def test_empty_and_degenerate_inputs(ctx):
+    """Empty / minimal inputs: status codes instead of the reference's asserts or undefined behaviour."""
+    q = np.zeros((0, 32), np.uint8); t = np.random.default_rng(0).integers(0, 256, (10, 32), dtype=np.uint8)
+    with pytest.raises(mvs.MvsError) as e:
+        ctx.match_hamming(q, t)                                   # visual-feature.cpp:56 assert(valid())
+    assert e.value.status == mvs.E_BAD_ARG
+    pts, idx = ctx.sfm_triangulate(np.zeros((0, 2)), np.zeros((0, 2)), np.eye(3), np.eye(3), np.zeros(3), np.eye(3), np.ones(3))
+    assert len(pts) == 0 and len(idx) == 0
+    assert ctx.sfm_solve(np.zeros((0, 2)), np.zeros((0, 2)), np.eye(3))["status"] == mvs.E_TOO_FEW_POINTS
+    r = ctx.ransac_fundamental(np.ones((7, 3)), np.ones((7, 3)), H=4, max_error_sq=1e-3)
+    assert r["status"] == mvs.E_TOO_FEW_POINTS                     # estimator-RANSAC.cpp:25-29
+    # all correspondences identical: rank-deficient 8-point system, must not crash or hang
+    same = np.tile(np.array([[10.0, 20.0]]), (20, 1))
+    g = ctx.sfm_solve(same, same, synth.K_S8K, H=4, seed=1)
+    assert g["status"] in (mvs.OK, mvs.E_NO_MODEL, mvs.E_TOO_FEW_INLIERS, mvs.E_NO_CHEIRALITY)
+    # frames with zero keypoints may be uploaded but not paired
+    ctx.frames_upload([t, np.zeros((0, 32), np.uint8)], [np.zeros((10, 2), np.float32), np.zeros((0, 2), np.float32)])
+    with pytest.raises(mvs.MvsError):
+        ctx.pair_batch([(0, 1)], synth.K_S8K)
+    # bad RANSAC parameters
+    with pytest.raises(mvs.MvsError):
+        ctx.sfm_solve(np.zeros((10, 2)), np.zeros((10, 2)), np.eye(3), H=0)
