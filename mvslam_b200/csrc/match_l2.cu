@@ -24,6 +24,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -36,7 +37,7 @@ namespace {
 constexpr int BM = 128;         // query rows per CTA  (UMMA M)
 constexpr int BN = 128;         // train rows per tile (UMMA N)
 constexpr int KSLAB = 32;       // floats per 128-byte swizzle slab
-constexpr int KC = 48;          // candidate slots per (row, split, column-half) list
+constexpr int KC = 64;          // candidate slots per (row, split, column-half) list
 constexpr int EPI_WARPS = 8;         // two per TMEM lane quarter: each takes half of a tile's columns
 constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
 constexpr uint32_t TMEM_COLS = 2 * BN;   // two accumulator buffers
@@ -507,20 +508,16 @@ cudaError_t launch_gemm(const CUtensorMap &mq, const CUtensorMap &mt, const floa
         if (e__ != cudaSuccess) { err = std::string(#call) + ": " + cudaGetErrorString(e__); return MVS_E_CUDA; } \
     } while (0)
 
-// train-dimension splits: fill the 148 SMs in balanced waves (1 CTA per SM), as few splits as possible
-// because every split restarts the per-row candidate stream
+// train-dimension splits.  Every split restarts the per-row candidate stream, and short streams make the
+// epilogue's slow path fire more often (measured on 32k x 32k: 1 split 0.35 ms, 2: 0.39, 4: 0.46, 8: 0.52), so:
+// as few splits as still give every SM a CTA or two.
 void plan_splits(int na, int nb, int &splits, int &tiles_per_split)
 {
     const int tiles_total = (nb + BN - 1) / BN;
     const int qtiles = (na + BM - 1) / BM;
-    const int smax = std::max(1, std::min(8, tiles_total / 8));
-    double best_eff = -1.0;
-    splits = 1;
-    for (int s = 1; s <= smax; ++s) {
-        const long ctas = (long)qtiles * s;
-        const double eff = (double)ctas / (double)(((ctas + 295) / 296) * 296);   // 148 SMs x 2 resident CTAs
-        if (eff > best_eff + 0.02) { best_eff = eff; splits = s; }
-    }
+    const int smax = std::max(1, std::min(16, tiles_total / 8));
+    splits = std::max(1, std::min(smax, (222 + qtiles - 1) / qtiles));
+    if (const char *e = getenv("MVS_L2_SPLITS")) splits = std::max(1, std::min(smax, atoi(e)));   // tuning override
     tiles_per_split = (tiles_total + splits - 1) / splits;
     splits = (tiles_total + tiles_per_split - 1) / tiles_per_split;
 }
