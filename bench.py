@@ -23,7 +23,6 @@ import os
 import statistics
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -78,36 +77,45 @@ def load_workload(name, pairs_per_step, H):
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """`nvidia-smi -lms 50` running beside the timed region (one background process, parsed afterwards)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
-        self.device, self.rows, self.stop, self.t = device, [], False, None
-
-    def _run(self):
-        while not self.stop:
-            try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
-                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in o.strip().split(",")])
-            except Exception:
-                pass
-            time.sleep(0.2)
+        self.device, self.rows, self.proc = device, [], None
 
     def __enter__(self):
-        self.t = threading.Thread(target=self._run, daemon=True); self.t.start(); return self
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.15)      # let the first sample land before the region starts
+        except Exception:
+            self.proc = None
+        return self
 
     def __exit__(self, *a):
-        self.stop = True; self.t.join(timeout=6)
+        if self.proc is None:
+            return
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill(); out = ""
+        self.rows = [[c.strip() for c in line.split(",")] for line in out.strip().splitlines() if line.strip()]
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        ok = [r for r in self.rows if len(r) >= 7]
+        num = lambda v: float(v) if v.replace(".", "", 1).isdigit() else None  # noqa: E731
+        sm = [num(r[0]) for r in ok if num(r[0]) is not None]
+        mx = [num(r[1]) for r in ok if num(r[1]) is not None]
+        pw = [num(r[2]) for r in ok if num(r[2]) is not None]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.startswith("Active")})
+        reasons = sorted({n for r in ok for n, v in zip(names, r[3:7]) if v.startswith("Active")})
         return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=reasons, samples=len(sm))
+                    power_w_max=max(pw) if pw else None, reasons=reasons, samples=len(sm))
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
