@@ -402,7 +402,7 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         threads = host_threads()
         probe, _ = cpu_pairs_per_s(descs, kps, K, pairs, params, 2 * threads)
-        n_sample = int(max(threads, min(4 * B, probe * 12.0)))
+        n_sample = int(max(threads, probe * 15.0))          # ~15 s of CPU work on all host cores
         v, dt = cpu_pairs_per_s(descs, kps, K, pairs, params, n_sample)
         cpu = dict(value=v, unit="pairs/s", cores=threads, kind="port",
                    sample=f"{n_sample} pairs of the same workload in {dt:.1f} s, C oracle (own-branch port), OpenMP over pairs")
