@@ -1,0 +1,41 @@
+// feature-io.hpp — tiny binary container for pre-extracted features and the reference's camera file, so that the
+// C++ tools can run without OpenCV (ORB extraction stays on the host side of the boundary).
+//   file = "MVSF" | int32 n | int32 width | int32 height | n x (float x, float y) | n x 32 descriptor bytes
+#pragma once
+#include <cstdio>
+#include <fstream>
+#include <string>
+
+#include "visual-feature.hpp"
+
+namespace mvSLAM {
+
+inline VisualFeature load_visual_feature(const std::string &filename)
+{
+    std::ifstream in(filename, std::ios::binary);
+    char magic[4];
+    int32_t n = 0, w = 0, h = 0;
+    in.read(magic, 4);
+    in.read(reinterpret_cast<char *>(&n), 4); in.read(reinterpret_cast<char *>(&w), 4); in.read(reinterpret_cast<char *>(&h), 4);
+    if (!in || std::string(magic, 4) != "MVSF" || n < 0) throw b200::Error(MVS_E_BAD_ARG, "bad feature file " + filename);
+    VisualFeatureConfig::DetectorResultType kps(n);
+    std::vector<float> xy((size_t)n * 2);
+    in.read(reinterpret_cast<char *>(xy.data()), (std::streamsize)(xy.size() * sizeof(float)));
+    for (int i = 0; i < n; ++i) { kps[i].pt.x = xy[2 * i]; kps[i].pt.y = xy[2 * i + 1]; }
+    VisualFeatureConfig::ExtractorResultType desc((size_t)n * 32);
+    in.read(reinterpret_cast<char *>(desc.data()), (std::streamsize)desc.size());
+    if (!in) throw b200::Error(MVS_E_BAD_ARG, "truncated feature file " + filename);
+    return VisualFeature(std::move(kps), std::move(desc), w, h);
+}
+
+/** PinholeCamera::load_from_file (reference source/vision/camera.cpp:105-123): first line "fx fy shear px py". */
+inline CameraIntrinsics load_camera_intrinsics(const std::string &filename)
+{
+    std::ifstream in(filename);
+    CameraIntrinsics K = Matrix3Type::Identity();
+    in >> K(0, 0) >> K(1, 1) >> K(0, 1) >> K(0, 2) >> K(1, 2);
+    if (!in) throw b200::Error(MVS_E_BAD_ARG, "bad camera file " + filename);
+    return K;
+}
+
+}  // namespace mvSLAM

@@ -469,3 +469,33 @@ def test_empty_and_degenerate_inputs(ctx):
     # bad RANSAC parameters
     with pytest.raises(mvs.MvsError):
         ctx.sfm_solve(np.zeros((10, 2)), np.zeros((10, 2)), np.eye(3), H=0)
+
+
+def test_cpp_tools_reconstruct_scene_and_vo_pairs(tmp_path, tsukuba, tsukuba_golden):
+    """tools/reconstruct_scene and tools/visual_odometer_pairs (C++ over the adapters) on the bundled Tsukuba features:
+    the pose the reference's tests expect (test-image-pair.cpp:40-45, test-visual-odometer.cpp:98-102: (I,(1,0,0)) to 1e-3)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "tsu")
+    subprocess.run([sys.executable, os.path.join(root, "tools", "export_features.py"), "npz",
+                    os.path.join(root, "tests", "golden", "tsukuba_orb2000.npz"), out], check=True)
+    r = subprocess.run([os.path.join(root, "tools", "reconstruct_scene"), out + "/1.mvsf", out + "/2.mvsf", out + "/camera.config", "30"],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = r.stdout.splitlines()
+    assert lines[0] == f"matches = {len(tsukuba_golden['p12_md30_q'])}"
+    rows = [l for l in lines if "|" in l]
+    Rt = np.array([[float(x) for x in l.replace("|", " ").split()] for l in rows])
+    assert np.allclose(Rt[:, :3], np.eye(3), atol=1e-3) and np.allclose(Rt[:, 3], [1, 0, 0], atol=1e-3)
+    npts = int([l for l in lines if l.startswith("pointsin1_scaled")][0].split("=")[1])
+    o = orc.image_pair(tsukuba["desc1"], tsukuba["kp1"], tsukuba["desc2"], tsukuba["kp2"], tsukuba["K"], max_dist=30.0)
+    assert npts == o["n_points"]
+    r = subprocess.run([os.path.join(root, "tools", "visual_odometer_pairs"), out], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    fl = [l for l in r.stdout.splitlines() if l.startswith("frame")]
+    assert len(fl) == 4
+    for i, l in enumerate(fl):
+        assert f"{i + 1} pair(s)" in l and "valid=1" in l
+        t = [float(x) for x in l.split("t=(")[1].rstrip(")").split()]
+        assert np.allclose(t, [1, 0, 0], atol=1e-3)
