@@ -182,6 +182,11 @@ int mvs_sfm_triangulate(mvs_ctx *ctx, const double *xy1, const double *xy2, int 
  * kp[f] is [counts[f]][2] float (cv::KeyPoint::pt).  Replaces the previous frame table. */
 int mvs_frames_upload(mvs_ctx *ctx, int n_frames, const uint8_t *const *desc, const float *const *kp,
                       const int32_t *counts, int desc_bytes);
+/* Append one frame to the resident table (what FrameManager::add_frame does per new image,
+ * source/front-end/frame-manager.cpp:107-125); returns its index through *frame_index.  mvs_frames_upload
+ * with n_frames = 0 is not allowed: start a new sequence with mvs_frames_clear. */
+int mvs_frames_append(mvs_ctx *ctx, const uint8_t *desc, const float *kp, int32_t count, int desc_bytes, int32_t *frame_index);
+int mvs_frames_clear(mvs_ctx *ctx);
 /* Solve pairs[i] = (base frame, pair frame) for i < n_pairs against the resident frames.
  * results[n_pairs] always filled (status per pair; one bad pair never aborts the batch).
  * Optional per-pair detail outputs use a common stride `capacity` (>= 1): matches[n_pairs][capacity],

@@ -247,6 +247,18 @@ class Context:
         self._check(self._L.mvs_frames_upload(self._h, nf, dptr, kptr, _p(counts), 32))
         self._frame_counts = counts
 
+    def frames_clear(self):
+        self._check(self._L.mvs_frames_clear(self._h))
+        self._frame_counts = np.zeros(0, np.int32)
+
+    def frames_append(self, desc, kp):
+        desc = np.ascontiguousarray(desc, np.uint8); kp = np.ascontiguousarray(kp, np.float32)
+        idx = C.c_int32(-1)
+        self._check(self._L.mvs_frames_append(self._h, _p(desc), _p(kp), desc.shape[0], 32, C.byref(idx)))
+        prev = self._frame_counts if self._frame_counts is not None else np.zeros(0, np.int32)
+        self._frame_counts = np.concatenate([prev, np.array([desc.shape[0]], np.int32)])
+        return idx.value
+
     def pair_batch(self, pairs, K, ratio=0.7, max_dist=-1.0, cross_check=False, H=1, seed=0, mode=SCORE_ALGEBRAIC,
                    max_error_sq=0.0, pair_id_base=0, details=True, out=None, enqueue_only=False, bounded=False):
         """Returns (results[RESULT_DTYPE], details dict or None).  `out` may hold preallocated (e.g. pinned)

@@ -797,6 +797,53 @@ static int pair_batch_chunk(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, con
     return MVS_OK;
 }
 
+int mvs_frames_clear(mvs_ctx *ctx)
+{
+    if (!ctx) return MVS_E_BAD_ARG;
+    ctx->h_off.clear(); ctx->h_cnt.clear();
+    return MVS_OK;
+}
+
+int mvs_frames_append(mvs_ctx *ctx, const uint8_t *desc, const float *kp, int32_t count, int desc_bytes, int32_t *frame_index)
+{
+    if (!ctx) return MVS_E_BAD_ARG;
+    if (count < 0 || count > (int)kIdxMask || (count > 0 && (!desc || !kp))) return fail(ctx, MVS_E_BAD_ARG, "bad frame");
+    if (desc_bytes != 32) return fail(ctx, MVS_E_UNSUPPORTED, "only 256-bit (32-byte) descriptors are supported");
+    CK(cudaSetDevice(ctx->device));
+    const int nf = (int)ctx->h_cnt.size();
+    const size_t used = nf ? (size_t)ctx->h_off[nf - 1] + (size_t)ctx->h_cnt[nf - 1] : 0;
+    const size_t total = used + (size_t)count;
+    if (total > 0x7FFFFFFFull) return fail(ctx, MVS_E_UNSUPPORTED, "more than 2^31 keypoints in the frame table");
+    // grow geometrically, keeping what is resident (device-to-device copy on the ctx stream)
+    auto grow = [&](DevBuf &b, size_t elem, size_t n_used, size_t n_need) -> cudaError_t {
+        if (n_need * elem <= b.cap) return cudaSuccess;
+        DevBuf nb;
+        cudaError_t e = nb.ensure(std::max(n_need * 2, (size_t)4096) * elem);
+        if (e != cudaSuccess) return e;
+        if (n_used) e = cudaMemcpyAsync(nb.p, b.p, n_used * elem, cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e != cudaSuccess) { nb.release(); return e; }
+        cudaStreamSynchronize(ctx->stream);
+        b.release();
+        b = nb;
+        return cudaSuccess;
+    };
+    CK(grow(ctx->d_desc, 32, used, std::max<size_t>(total, 1)));
+    CK(grow(ctx->d_kp, sizeof(float2), used, std::max<size_t>(total, 1)));
+    CK(grow(ctx->d_foff, sizeof(int32_t), (size_t)nf, (size_t)nf + 1));
+    CK(grow(ctx->d_fcnt, sizeof(int32_t), (size_t)nf, (size_t)nf + 1));
+    const int32_t off = (int32_t)used;
+    if (count) {
+        CK(cudaMemcpyAsync(ctx->d_desc.as<uint8_t>() + used * 32, desc, (size_t)count * 32, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_kp.as<float2>() + used, kp, (size_t)count * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CK(cudaMemcpyAsync(ctx->d_foff.as<int32_t>() + nf, &off, sizeof(off), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_fcnt.as<int32_t>() + nf, &count, sizeof(count), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->h_off.push_back(off); ctx->h_cnt.push_back(count);
+    if (frame_index) *frame_index = nf;
+    return MVS_OK;
+}
+
 int mvs_pair_batch_enqueue(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, const double K[9],
                            const mvs_match_params *mparams, const mvs_ransac_params *rparams,
                            mvs_pair_result *results, mvs_match *matches, uint8_t *inlier_mask,

@@ -499,3 +499,19 @@ def test_cpp_tools_reconstruct_scene_and_vo_pairs(tmp_path, tsukuba, tsukuba_gol
         assert f"{i + 1} pair(s)" in l and "valid=1" in l
         t = [float(x) for x in l.split("t=(")[1].rstrip(")").split()]
         assert np.allclose(t, [1, 0, 0], atol=1e-3)
+
+
+def test_frames_append_equals_bulk_upload(ctx, tsukuba):
+    """Streaming use (FrameManager::add_frame per image): appended frames behave exactly like a bulk upload."""
+    descs = [tsukuba[f"desc{i}"] for i in range(1, 6)]; kps = [tsukuba[f"kp{i}"] for i in range(1, 6)]
+    pairs = [(0, 1), (1, 2), (0, 4), (3, 2)]
+    ctx.frames_upload(descs, kps)
+    ref, dref = ctx.pair_batch(pairs, tsukuba["K"], max_dist=30.0, H=16, seed=4)
+    ctx.frames_clear()
+    for i in range(5):
+        assert ctx.frames_append(descs[i], kps[i]) == i
+        if i == 1:
+            one, _ = ctx.pair_batch([(0, 1)], tsukuba["K"], max_dist=30.0, H=16, seed=4)
+            assert one.tobytes() == ref[:1].tobytes()
+    got, dgot = ctx.pair_batch(pairs, tsukuba["K"], max_dist=30.0, H=16, seed=4)
+    assert got.tobytes() == ref.tobytes() and np.array_equal(dgot["matches"], dref["matches"])
