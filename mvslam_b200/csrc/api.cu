@@ -369,9 +369,8 @@ void mvs_sample_table(uint64_t seed, uint64_t pair_id, uint32_t n_points, int H,
 
 // ------------------------------------------------------------------------------------------ matching
 static int match_two_sets(mvs_ctx *ctx, const uint8_t *query, int nq, const uint8_t *train, int nt, int desc_bytes,
-                          const mvs_match_params *mp, bool want_knn, int *n_out_dev_ready)
+                          const mvs_match_params *mp, bool want_knn)
 {
-    (void)n_out_dev_ready;
     if (!ctx) return MVS_E_BAD_ARG;
     if (!query || !train || nq < 1) return fail(ctx, MVS_E_BAD_ARG, "null descriptors or nq < 1");
     if (nt < 2) return fail(ctx, MVS_E_BAD_ARG, "knnMatch(k=2) needs at least 2 train descriptors");
@@ -429,7 +428,7 @@ int mvs_knn2_hamming(mvs_ctx *ctx, const uint8_t *query, int nq, const uint8_t *
 {
     if (!idx || !dist) return fail(ctx, MVS_E_BAD_ARG, "null output");
     mvs_match_params mp{0.7, -1.0, 0, 0};
-    int st = match_two_sets(ctx, query, nq, train, nt, desc_bytes, &mp, true, nullptr);
+    int st = match_two_sets(ctx, query, nq, train, nt, desc_bytes, &mp, true);
     if (st != MVS_OK) return st;
     CK(cudaMemcpyAsync(idx, ctx->d_knn_i.p, (size_t)nq * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(dist, ctx->d_knn_d.p, (size_t)nq * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -442,7 +441,7 @@ int mvs_match_hamming(mvs_ctx *ctx, const uint8_t *query, int nq, const uint8_t 
 {
     if (!n_out) return fail(ctx, MVS_E_BAD_ARG, "null n_out");
     *n_out = 0;
-    int st = match_two_sets(ctx, query, nq, train, nt, desc_bytes, params, false, nullptr);
+    int st = match_two_sets(ctx, query, nq, train, nt, desc_bytes, params, false);
     if (st != MVS_OK) return st;
     int32_t m = 0;
     CK(cudaMemcpyAsync(&m, ctx->d_nmatch.p, sizeof(m), cudaMemcpyDeviceToHost, ctx->stream));

@@ -630,7 +630,7 @@ int l2_knn2(L2Workspace &ws, cudaStream_t stream, const float *query, int nq, co
                                                            o_idx, o_d2, o_flag);
         l2_fallback_kernel<<<na, 256, 0, stream>>>(A, Bm, kpad, kpad, dim, nb, o_flag, o_idx, o_d2, d_nfb + pass);
         nl += 2;
-        if (passes > 1 || true) {   // per-pass GEMM time (event pair reused, so read it now)
+        {   // per-pass GEMM time (the event pair is reused by the cross-check pass, so read it now)
             cudaEventSynchronize(ws.ev[3]);
             float ms = 0.f;
             if (cudaEventElapsedTime(&ms, ws.ev[2], ws.ev[3]) == cudaSuccess) gemm_ms_total += ms;
