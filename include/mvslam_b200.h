@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MVS_ABI_VERSION 1
+#define MVS_ABI_VERSION 2
 
 /* status codes (reference: bool / assert / empty vector; SURVEY.md §8b "Errors") */
 enum {
@@ -96,9 +96,28 @@ typedef struct {
     uint64_t match_inlier_ssd; /* sum of squared descriptor distances over the reconstructed points (image-pair.cpp:166) */
 } mvs_pair_result;
 
+/* cv::KeyPoint as cv::ORB fills it (class_id is always -1 and is not carried) */
+typedef struct {
+    float   x, y;      /* pt, level-0 pixel coordinates (level coordinates times the level scale) */
+    float   size;     /* patchSize (31) times the level scale */
+    float   angle;    /* degrees, [0, 360) */
+    float   response; /* Harris response */
+    int32_t octave;   /* pyramid level */
+} mvs_keypoint;
+
+/* cv::ORB::create(nfeatures) — the only parameter the reference sets (MAX_FEATURE_COUNT = 500,
+ * source/vision/visual-feature.cpp:9-17); the rest are OpenCV's defaults: scaleFactor 1.2f, nlevels 8,
+ * edgeThreshold 31, firstLevel 0, WTA_K 2, HARRIS_SCORE, patchSize 31, fastThreshold 20. */
+typedef struct {
+    int32_t n_features;
+    int32_t reserved[3];
+} mvs_orb_params;
+
 /* per-stage device time accumulated on the ctx stream while profiling is enabled */
 enum { MVS_STAGE_KNN = 0, MVS_STAGE_MATCH_FINALIZE, MVS_STAGE_HYPOTHESES, MVS_STAGE_SCORE,
-       MVS_STAGE_SELECT, MVS_STAGE_TRIANGULATE, MVS_STAGE_FINALIZE, MVS_STAGE_L2, MVS_N_STAGES };
+       MVS_STAGE_SELECT, MVS_STAGE_TRIANGULATE, MVS_STAGE_FINALIZE, MVS_STAGE_L2,
+       MVS_STAGE_ORB_PYRAMID, MVS_STAGE_ORB_FAST, MVS_STAGE_ORB_HARRIS, MVS_STAGE_ORB_SELECT,
+       MVS_STAGE_ORB_BLUR, MVS_STAGE_ORB_DESCRIBE, MVS_N_STAGES };
 typedef struct {
     double   ms[MVS_N_STAGES];
     uint64_t launches[MVS_N_STAGES];
@@ -120,6 +139,26 @@ int  mvs_profile_enable(mvs_ctx *ctx, int on);
 int  mvs_profile_read(mvs_ctx *ctx, mvs_profile *out, int reset);
 /* number of kernels this ctx has launched so far */
 uint64_t mvs_kernel_launches(const mvs_ctx *ctx);
+
+/* ---- feature extraction: VisualFeature::extract (source/vision/visual-feature.cpp:40-49, decl
+ *      visual-feature.hpp:14) = cv::ORB detect + compute, the step FrameManager::add_frame runs per new image
+ *      (source/front-end/frame-manager.cpp:107-125) ------------------------------------------------------------ */
+/* n_images 8-bit grayscale images of one size (images[i] -> height rows of stride_bytes).  Keypoints come out
+ * compact: image i owns the slots [sum(counts[0..i)), +counts[i]) of keypoints[] / descriptors[][32]; `capacity` is the
+ * number of slots the caller provided (MVS_E_CAPACITY, with counts[] filled, when too small).  counts, keypoints and
+ * descriptors are each optional.  Order within an image (new contract; cv::ORB's order is whatever std::nth_element
+ * leaves): pyramid level ascending, then y, then x in level coordinates.  The keypoint SET, responses, angles and
+ * descriptor bytes are those of cv::ORB (see oracle/orb_np.py for the pin).
+ * append_frames != 0: every image also becomes a new frame of the resident frame table (as mvs_frames_append would
+ * make it, but device to device: descriptors never visit the host); *first_frame = index of image 0's frame.
+ * A pyramid level keeps at most 4096 keypoints (quota plus ties at the cut-off response): MVS_E_CAPACITY beyond. */
+int mvs_orb_extract(mvs_ctx *ctx, const uint8_t *const *images, int n_images, int width, int height, int stride_bytes,
+                    const mvs_orb_params *params, int append_frames, int32_t *first_frame,
+                    int32_t *counts, mvs_keypoint *keypoints, uint8_t *descriptors, int64_t capacity);
+/* Same with the images already in device memory: d_images is [n_images][height][stride_bytes] contiguous. */
+int mvs_orb_extract_device(mvs_ctx *ctx, const void *d_images, int n_images, int width, int height, int stride_bytes,
+                           const mvs_orb_params *params, int append_frames, int32_t *first_frame,
+                           int32_t *counts, mvs_keypoint *keypoints, uint8_t *descriptors, int64_t capacity);
 
 /* ---- matching: VisualFeature::match_visual_features (source/vision/visual-feature.cpp:51-80,
  *      decl visual-feature.hpp:23-26) ------------------------------------------------------------ */

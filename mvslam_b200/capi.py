@@ -9,7 +9,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 (OK, E_BAD_ARG, E_TOO_FEW_POINTS, E_NO_MODEL, E_TOO_FEW_INLIERS, E_NO_CHEIRALITY, E_CUDA, E_CAPACITY,
  E_UNSUPPORTED) = range(9)
 SCORE_ALGEBRAIC, SCORE_SAMPSON = 0, 1
-STAGES = ("knn", "match_finalize", "hypotheses", "score", "select", "triangulate", "finalize", "l2")
+STAGES = ("knn", "match_finalize", "hypotheses", "score", "select", "triangulate", "finalize", "l2",
+          "orb_pyramid", "orb_fast", "orb_harris", "orb_select", "orb_blur", "orb_describe")
 
 MATCH_DTYPE = np.dtype([("query", np.int32), ("train", np.int32), ("distance", np.float32)])
 RESULT_DTYPE = np.dtype([
@@ -17,6 +18,8 @@ RESULT_DTYPE = np.dtype([
     ("n_points", np.int32), ("candidate", np.int32), ("residual", np.float64), ("F", np.float64, (3, 3)),
     ("E", np.float64, (3, 3)), ("R1to2", np.float64, (3, 3)), ("t1to2", np.float64, (3,)),
     ("R2in1", np.float64, (3, 3)), ("t2in1", np.float64, (3,)), ("match_inlier_ssd", np.uint64)])
+KEYPOINT_DTYPE = np.dtype([("x", np.float32), ("y", np.float32), ("size", np.float32), ("angle", np.float32),
+                           ("response", np.float32), ("octave", np.int32)])
 
 
 class MatchParams(C.Structure):
@@ -38,6 +41,10 @@ class PairResult(C.Structure):
 
 
 assert C.sizeof(PairResult) == RESULT_DTYPE.itemsize == 376
+
+
+class OrbParams(C.Structure):
+    _fields_ = [("n_features", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 class Profile(C.Structure):
@@ -75,7 +82,7 @@ def load_library():
     L.mvs_destroy.restype = None
     L.mvs_destroy.argtypes = [C.c_void_p]
     L.mvs_sample_table.restype = None
-    if L.mvs_abi_version() != 1:
+    if L.mvs_abi_version() != 2:
         raise ImportError("libmvslam_b200.so ABI version mismatch")
     _lib = L
     return L
@@ -152,6 +159,50 @@ class Context:
 
     def kernel_launches(self):
         return int(self._L.mvs_kernel_launches(self._h))
+
+    # ---- feature extraction
+    def orb_extract(self, images, n_features=500, append_frames=False, want=True, device_ptr=None, shape=None):
+        """VisualFeature::extract for a list/array of equal-size 8-bit grayscale images.
+
+        Returns (counts int32[n], keypoints KEYPOINT_DTYPE[total], descriptors uint8[total][32], first_frame).
+        device_ptr/shape=(n, h, stride, w): the images already live in device memory (contiguous)."""
+        op = OrbParams(int(n_features), (C.c_int32 * 3)(0, 0, 0))
+        first = C.c_int32(-1)
+        if device_ptr is None:
+            imgs = [np.ascontiguousarray(im, np.uint8) for im in images]
+            n = len(imgs); h, w = imgs[0].shape; stride = w
+            assert all(im.shape == (h, w) for im in imgs), "images must share one size"
+            ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in imgs])
+        else:
+            n, h, stride, w = shape
+        counts = np.zeros(n, np.int32)
+
+        def call(kp, desc, cap, append):
+            if device_ptr is None:
+                return self._L.mvs_orb_extract(self._h, ptrs, n, w, h, stride, C.byref(op), int(append), C.byref(first),
+                                               _p(counts), _p(kp), _p(desc), C.c_int64(cap))
+            return self._L.mvs_orb_extract_device(self._h, C.c_void_p(int(device_ptr)), n, w, h, stride, C.byref(op),
+                                                  int(append), C.byref(first), _p(counts), _p(kp), _p(desc), C.c_int64(cap))
+        if not want:
+            self._check(call(None, None, 0, append_frames))
+            kp = desc = None
+        else:
+            cap = n * (int(n_features) + 64)
+            kp = np.zeros(cap, KEYPOINT_DTYPE); desc = np.zeros((cap, 32), np.uint8)
+            st = call(kp, desc, cap, append_frames)
+            if st == E_CAPACITY and counts.sum() > cap:      # ties at a cut-off: retry with the exact size
+                if append_frames:
+                    raise MvsError(st, "orb_extract: capacity (frames were appended; fetch sizes from counts)")
+                cap = int(counts.sum())
+                kp = np.zeros(cap, KEYPOINT_DTYPE); desc = np.zeros((cap, 32), np.uint8)
+                st = call(kp, desc, cap, False)
+            self._check(st)
+            tot = int(counts.sum())
+            kp, desc = kp[:tot], desc[:tot]
+        if append_frames:
+            prev = self._frame_counts if self._frame_counts is not None else np.zeros(0, np.int32)
+            self._frame_counts = np.concatenate([prev, counts])
+        return counts, kp, desc, first.value
 
     # ---- matching
     def knn2_hamming(self, query, train):

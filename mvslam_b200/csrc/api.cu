@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "l2.h"
+#include "orb.h"
 
 using namespace mvs;
 
@@ -55,6 +56,12 @@ struct mvs_ctx {
     DevBuf d_pairs, d_partial, d_rev, d_matches, d_nmatch, d_points, d_state, d_Fall, d_pc, d_pr, d_mask,
         d_valid, d_tri, d_opts, d_oidx, d_results, d_table, d_in1, d_in2, d_knn_i, d_knn_d, d_counts, d_pres;
     mvs::L2Workspace l2;
+    // feature extraction (orb.cu): pyramid geometry cached per (width, height, nfeatures), workspace, last results
+    int orb_w = 0, orb_h = 0, orb_nf = -1;
+    mvs::OrbGeom orb_geom;
+    DevBuf o_tabs, o_stage, o_pyr, o_blur, o_cxy, o_cval, o_cnt, o_kidx, o_kcnt, o_off, o_kp, o_desc;
+    int32_t *o_pinned = nullptr;
+    size_t o_pinned_cap = 0;
     // profiling
     bool prof = false;
     std::vector<cudaEvent_t> ev_pool;
@@ -306,7 +313,10 @@ void mvs_destroy(mvs_ctx *ctx)
                       &ctx->d_pairs, &ctx->d_partial, &ctx->d_rev, &ctx->d_matches, &ctx->d_nmatch, &ctx->d_points,
                       &ctx->d_state, &ctx->d_Fall, &ctx->d_pc, &ctx->d_pr, &ctx->d_mask, &ctx->d_valid, &ctx->d_tri,
                       &ctx->d_opts, &ctx->d_oidx, &ctx->d_results, &ctx->d_table, &ctx->d_in1, &ctx->d_in2,
-                      &ctx->d_knn_i, &ctx->d_knn_d, &ctx->d_counts, &ctx->d_pres};
+                      &ctx->d_knn_i, &ctx->d_knn_d, &ctx->d_counts, &ctx->d_pres, &ctx->o_tabs, &ctx->o_stage,
+                      &ctx->o_pyr, &ctx->o_blur, &ctx->o_cxy, &ctx->o_cval, &ctx->o_cnt, &ctx->o_kidx, &ctx->o_kcnt,
+                      &ctx->o_off, &ctx->o_kp, &ctx->o_desc};
+    if (ctx->o_pinned) cudaFreeHost(ctx->o_pinned);
     for (DevBuf *b : bufs) b->release();
     ctx->l2.release();
     for (auto &p : ctx->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
@@ -796,6 +806,21 @@ static int pair_batch_chunk(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, con
     return MVS_OK;
 }
 
+// grow a device buffer geometrically, keeping the first n_used elements (device-to-device copy on the ctx stream)
+static cudaError_t grow_keep(mvs_ctx *ctx, DevBuf &b, size_t elem, size_t n_used, size_t n_need)
+{
+    if (n_need * elem <= b.cap) return cudaSuccess;
+    DevBuf nb;
+    cudaError_t e = nb.ensure(std::max(n_need * 2, (size_t)4096) * elem);
+    if (e != cudaSuccess) return e;
+    if (n_used) e = cudaMemcpyAsync(nb.p, b.p, n_used * elem, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e != cudaSuccess) { nb.release(); return e; }
+    cudaStreamSynchronize(ctx->stream);
+    b.release();
+    b = nb;
+    return cudaSuccess;
+}
+
 int mvs_frames_clear(mvs_ctx *ctx)
 {
     if (!ctx) return MVS_E_BAD_ARG;
@@ -813,23 +838,10 @@ int mvs_frames_append(mvs_ctx *ctx, const uint8_t *desc, const float *kp, int32_
     const size_t used = nf ? (size_t)ctx->h_off[nf - 1] + (size_t)ctx->h_cnt[nf - 1] : 0;
     const size_t total = used + (size_t)count;
     if (total > 0x7FFFFFFFull) return fail(ctx, MVS_E_UNSUPPORTED, "more than 2^31 keypoints in the frame table");
-    // grow geometrically, keeping what is resident (device-to-device copy on the ctx stream)
-    auto grow = [&](DevBuf &b, size_t elem, size_t n_used, size_t n_need) -> cudaError_t {
-        if (n_need * elem <= b.cap) return cudaSuccess;
-        DevBuf nb;
-        cudaError_t e = nb.ensure(std::max(n_need * 2, (size_t)4096) * elem);
-        if (e != cudaSuccess) return e;
-        if (n_used) e = cudaMemcpyAsync(nb.p, b.p, n_used * elem, cudaMemcpyDeviceToDevice, ctx->stream);
-        if (e != cudaSuccess) { nb.release(); return e; }
-        cudaStreamSynchronize(ctx->stream);
-        b.release();
-        b = nb;
-        return cudaSuccess;
-    };
-    CK(grow(ctx->d_desc, 32, used, std::max<size_t>(total, 1)));
-    CK(grow(ctx->d_kp, sizeof(float2), used, std::max<size_t>(total, 1)));
-    CK(grow(ctx->d_foff, sizeof(int32_t), (size_t)nf, (size_t)nf + 1));
-    CK(grow(ctx->d_fcnt, sizeof(int32_t), (size_t)nf, (size_t)nf + 1));
+    CK(grow_keep(ctx, ctx->d_desc, 32, used, std::max<size_t>(total, 1)));
+    CK(grow_keep(ctx, ctx->d_kp, sizeof(float2), used, std::max<size_t>(total, 1)));
+    CK(grow_keep(ctx, ctx->d_foff, sizeof(int32_t), (size_t)nf, (size_t)nf + 1));
+    CK(grow_keep(ctx, ctx->d_fcnt, sizeof(int32_t), (size_t)nf, (size_t)nf + 1));
     const int32_t off = (int32_t)used;
     if (count) {
         CK(cudaMemcpyAsync(ctx->d_desc.as<uint8_t>() + used * 32, desc, (size_t)count * 32, cudaMemcpyHostToDevice, ctx->stream));
@@ -875,6 +887,162 @@ int mvs_pair_batch(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, const double
     if (st != MVS_OK) return st;
     CK(cudaStreamSynchronize(ctx->stream));
     return MVS_OK;
+}
+
+// ------------------------------------------------------------------------------------------ feature extraction
+// VisualFeature::extract (visual-feature.cpp:40-49) for a batch of same-size images.  Two device passes per chunk of
+// images with one small device->host read between them (the per-level keypoint counts size the compact outputs).
+static int orb_extract_impl(mvs_ctx *ctx, const uint8_t *const *h_images, const uint8_t *d_images, int n_images, int width,
+                            int height, int stride, const mvs_orb_params *params, int append_frames, int32_t *first_frame,
+                            int32_t *counts, mvs_keypoint *keypoints, uint8_t *descriptors, int64_t capacity)
+{
+    if (!ctx) return MVS_E_BAD_ARG;
+    if (n_images < 1 || (!h_images && !d_images) || width < 1 || height < 1 || stride < width)
+        return fail(ctx, MVS_E_BAD_ARG, "orb_extract: null images, n_images < 1 or bad size/stride");
+    const int nf = params ? params->n_features : 500;   // visual-feature.cpp:9 MAX_FEATURE_COUNT
+    if (nf < 0) return fail(ctx, MVS_E_BAD_ARG, "orb_extract: n_features < 0");
+    if (width > 65535 || height > 65535) return fail(ctx, MVS_E_UNSUPPORTED, "orb_extract: image side > 65535");
+    if ((keypoints || descriptors) && capacity < 0) return fail(ctx, MVS_E_CAPACITY, "orb_extract: negative capacity");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->orb_w != width || ctx->orb_h != height || ctx->orb_nf != nf) {
+        std::vector<int32_t> tabs;
+        if (!orb_make_geometry(width, height, nf, ctx->orb_geom, tabs))
+            return fail(ctx, MVS_E_UNSUPPORTED, "orb_extract: image too small for an 8-level pyramid");
+        CK(cudaStreamSynchronize(ctx->stream));   // earlier work may still read the old tables
+        CK(ctx->o_tabs.ensure(std::max<size_t>(tabs.size(), 1) * sizeof(int32_t)));
+        CK(cudaMemcpy(ctx->o_tabs.p, tabs.data(), tabs.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        ctx->orb_w = width; ctx->orb_h = height; ctx->orb_nf = nf;
+    }
+    const OrbGeom &g = ctx->orb_geom;
+    // chunk size: keep the workspace (2 pyramids + candidate lists + kept lists per image) near 2 GB
+    const size_t per_image = 2 * (size_t)g.slab + 8 * (size_t)g.cand_total + (size_t)kOrbLevels * kOrbSortCap * 4 + (size_t)height * stride;
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_images, ((size_t)2 << 30) / per_image));
+    CK(ctx->o_stage.ensure((size_t)chunk * height * stride));
+    CK(ctx->o_pyr.ensure((size_t)chunk * g.slab));
+    CK(ctx->o_blur.ensure((size_t)chunk * g.slab));
+    CK(ctx->o_cxy.ensure((size_t)chunk * g.cand_total * 4));
+    CK(ctx->o_cval.ensure((size_t)chunk * g.cand_total * 4));
+    CK(ctx->o_cnt.ensure((size_t)chunk * kOrbLevels * 257 * sizeof(int32_t)));
+    CK(ctx->o_kidx.ensure((size_t)chunk * kOrbLevels * kOrbSortCap * 4));
+    CK(ctx->o_kcnt.ensure((size_t)chunk * kOrbLevels * sizeof(int32_t)));
+    CK(ctx->o_off.ensure((size_t)chunk * sizeof(int32_t)));
+    const size_t pin_need = (size_t)chunk * (kOrbLevels + 1);
+    if (ctx->o_pinned_cap < pin_need) {
+        if (ctx->o_pinned) cudaFreeHost(ctx->o_pinned);
+        ctx->o_pinned = nullptr; ctx->o_pinned_cap = 0;
+        CK(cudaMallocHost((void **)&ctx->o_pinned, pin_need * sizeof(int32_t)));
+        ctx->o_pinned_cap = pin_need;
+    }
+    OrbBuffers b{};
+    b.pyr = ctx->o_pyr.as<uint8_t>(); b.blur = ctx->o_blur.as<uint8_t>(); b.tabs = ctx->o_tabs.as<int32_t>();
+    b.cand_xy = ctx->o_cxy.as<uint32_t>(); b.cand_val = ctx->o_cval.as<float>();
+    b.cand_cnt = ctx->o_cnt.as<int32_t>(); b.hist = b.cand_cnt + (size_t)chunk * kOrbLevels;
+    b.kept_idx = ctx->o_kidx.as<uint32_t>(); b.kept_cnt = ctx->o_kcnt.as<int32_t>();
+
+    // where the results go: the resident frame table (append) or the ctx's own result buffers
+    const int frames0 = (int)ctx->h_cnt.size();
+    const size_t used0 = (append_frames && frames0) ? (size_t)ctx->h_off[frames0 - 1] + (size_t)ctx->h_cnt[frames0 - 1] : 0;
+    size_t total = 0;                       // keypoints produced so far in this call
+    std::vector<int32_t> img_count(n_images);
+    for (int c0 = 0; c0 < n_images; c0 += chunk) {
+        const int n = std::min(chunk, n_images - c0);
+        const uint8_t *stage = nullptr;
+        if (d_images) {
+            stage = d_images + (size_t)c0 * height * stride;
+        } else {
+            for (int i = 0; i < n; ++i) {
+                if (!h_images[c0 + i]) return fail(ctx, MVS_E_BAD_ARG, "orb_extract: null image");
+                CK(cudaMemcpyAsync(ctx->o_stage.as<uint8_t>() + (size_t)i * height * stride, h_images[c0 + i], (size_t)height * stride,
+                                   cudaMemcpyHostToDevice, ctx->stream));
+            }
+            stage = ctx->o_stage.as<uint8_t>();
+        }
+        CK(cudaMemsetAsync(b.cand_cnt, 0, (size_t)chunk * kOrbLevels * 257 * sizeof(int32_t), ctx->stream));
+        {
+            StageTimer t(ctx, MVS_STAGE_ORB_PYRAMID, kOrbLevels);
+            launch_orb_import(g, b, stage, stride, n, ctx->stream);
+            for (int l = 1; l < kOrbLevels; ++l) launch_orb_resize(g, b, l, n, ctx->stream);
+        }
+        { StageTimer t(ctx, MVS_STAGE_ORB_FAST, g.fast_tiles ? 1 : 0); launch_orb_fast(g, b, n, ctx->stream); }
+        { StageTimer t(ctx, MVS_STAGE_ORB_HARRIS); launch_orb_harris(g, b, n, ctx->stream); }
+        { StageTimer t(ctx, MVS_STAGE_ORB_SELECT); launch_orb_select(g, b, n, ctx->stream); }
+        CK(cudaMemcpyAsync(ctx->o_pinned, b.kept_cnt, (size_t)n * kOrbLevels * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        { StageTimer t(ctx, MVS_STAGE_ORB_BLUR); launch_orb_blur(g, b, n, ctx->stream); }
+        CK(cudaStreamSynchronize(ctx->stream));
+        int32_t *off = ctx->o_pinned + (size_t)chunk * kOrbLevels;
+        size_t chunk_total = 0;
+        for (int i = 0; i < n; ++i) {
+            int32_t c = 0;
+            for (int l = 0; l < kOrbLevels; ++l) {
+                const int32_t k = ctx->o_pinned[i * kOrbLevels + l];
+                if (k < 0) return fail(ctx, MVS_E_CAPACITY, "orb_extract: more than 4096 keypoints tie at a level's cut-off response");
+                c += k;
+            }
+            img_count[c0 + i] = c;
+            off[i] = (int32_t)(total + chunk_total);
+            chunk_total += (size_t)c;
+        }
+        if (used0 + total + chunk_total > 0x7FFFFFFFull) return fail(ctx, MVS_E_UNSUPPORTED, "more than 2^31 keypoints");
+        CK(grow_keep(ctx, ctx->o_kp, sizeof(mvs_keypoint), total, std::max<size_t>(total + chunk_total, 1)));
+        OrbDescribeArgs d{};
+        d.img_off = ctx->o_off.as<int32_t>();
+        d.kp = ctx->o_kp.as<mvs_keypoint>();
+        if (append_frames) {
+            CK(grow_keep(ctx, ctx->d_desc, 32, used0 + total, std::max<size_t>(used0 + total + chunk_total, 1)));
+            CK(grow_keep(ctx, ctx->d_kp, sizeof(float2), used0 + total, std::max<size_t>(used0 + total + chunk_total, 1)));
+            d.desc = ctx->d_desc.as<uint8_t>() + used0 * 32;
+            d.frame_kp = ctx->d_kp.as<float2>() + used0;
+        } else {
+            CK(grow_keep(ctx, ctx->o_desc, 32, total, std::max<size_t>(total + chunk_total, 1)));
+            d.desc = ctx->o_desc.as<uint8_t>();
+        }
+        CK(cudaMemcpyAsync(ctx->o_off.p, off, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        {
+            StageTimer t(ctx, MVS_STAGE_ORB_DESCRIBE);
+            launch_orb_describe(g, b, d, n, n >= 64 ? 4 : (n >= 8 ? 16 : 64), ctx->stream);
+        }
+        CK(cudaStreamSynchronize(ctx->stream));   // the pinned offsets are rewritten by the next chunk
+        total += chunk_total;
+    }
+    if (counts) std::memcpy(counts, img_count.data(), (size_t)n_images * sizeof(int32_t));
+    if (append_frames) {
+        // frame table bookkeeping (as mvs_frames_append, for all new frames at once)
+        CK(grow_keep(ctx, ctx->d_foff, sizeof(int32_t), (size_t)frames0, (size_t)frames0 + n_images));
+        CK(grow_keep(ctx, ctx->d_fcnt, sizeof(int32_t), (size_t)frames0, (size_t)frames0 + n_images));
+        std::vector<int32_t> offs(n_images);
+        size_t at = used0;
+        for (int i = 0; i < n_images; ++i) { offs[i] = (int32_t)at; at += (size_t)img_count[i]; }
+        CK(cudaMemcpyAsync(ctx->d_foff.as<int32_t>() + frames0, offs.data(), (size_t)n_images * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_fcnt.as<int32_t>() + frames0, img_count.data(), (size_t)n_images * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < n_images; ++i) { ctx->h_off.push_back(offs[i]); ctx->h_cnt.push_back(img_count[i]); }
+        if (first_frame) *first_frame = frames0;
+    }
+    if ((keypoints || descriptors) && (int64_t)total > capacity)
+        return fail(ctx, MVS_E_CAPACITY, "orb_extract: keypoint capacity too small (counts are filled)");
+    if (keypoints && total)
+        CK(cudaMemcpyAsync(keypoints, ctx->o_kp.p, total * sizeof(mvs_keypoint), cudaMemcpyDeviceToHost, ctx->stream));
+    if (descriptors && total)
+        CK(cudaMemcpyAsync(descriptors, append_frames ? ctx->d_desc.as<uint8_t>() + used0 * 32 : ctx->o_desc.as<uint8_t>(), total * 32,
+                           cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MVS_OK;
+}
+
+int mvs_orb_extract(mvs_ctx *ctx, const uint8_t *const *images, int n_images, int width, int height, int stride_bytes,
+                    const mvs_orb_params *params, int append_frames, int32_t *first_frame,
+                    int32_t *counts, mvs_keypoint *keypoints, uint8_t *descriptors, int64_t capacity)
+{
+    return orb_extract_impl(ctx, images, nullptr, n_images, width, height, stride_bytes, params, append_frames, first_frame,
+                            counts, keypoints, descriptors, capacity);
+}
+
+int mvs_orb_extract_device(mvs_ctx *ctx, const void *d_images, int n_images, int width, int height, int stride_bytes,
+                           const mvs_orb_params *params, int append_frames, int32_t *first_frame,
+                           int32_t *counts, mvs_keypoint *keypoints, uint8_t *descriptors, int64_t capacity)
+{
+    return orb_extract_impl(ctx, nullptr, static_cast<const uint8_t *>(d_images), n_images, width, height, stride_bytes, params,
+                            append_frames, first_frame, counts, keypoints, descriptors, capacity);
 }
 
 }  // extern "C"

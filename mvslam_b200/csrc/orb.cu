@@ -1,0 +1,585 @@
+// orb.cu — feature extraction on the device: the cv::ORB pipeline that VisualFeature::extract runs
+// (reference source/vision/visual-feature.cpp:9-17,40-49; cv::ORB::create(MAX_FEATURE_COUNT), every other
+// parameter at its OpenCV default).  OpenCV itself is not vendored by the reference; the stages below follow the
+// published algorithm (8-level 1.2x pyramid by bit-exact fixed-point bilinear resize, FAST-9/16 with 3x3 non-max
+// suppression, Harris re-scoring, intensity-centroid orientation, 7x7 sigma-2 Gaussian, steered BRIEF) and are
+// pinned bit-for-bit against cv2 by the test suite (tests/test_orb_*.py).
+//
+// Everything is integer or explicitly-rounded FP32 arithmetic: this file is compiled with -fmad=false and uses
+// fmaf() exactly where OpenCV's FMA-contracted separable filter does.
+//
+//   O1 orb_resize_kernel    level l from level l-1 (7 launches; 8.8 fixed point, round at 16 fractional bits)
+//   O2 orb_fast_kernel      FAST score + 3x3 NMS per 32x16 tile -> candidate list + score histogram
+//   O3 orb_harris_kernel    first retainBest (2 x quota by FAST score, histogram threshold) + Harris response
+//   O4 orb_select_kernel    second retainBest (quota by Harris response, radix select), raster-order sort
+//   O5 orb_blur_kernel      7x7 Gaussian, reflect-101
+//   O6 orb_describe_kernel  warp per keypoint: IC angle, fastAtan2, 256 steered tests -> 32 bytes
+#include <cmath>
+#include <vector>
+
+#include "orb.h"
+#include "orb_pattern.h"
+
+namespace mvs {
+
+// ------------------------------------------------------------------------------------------ host geometry
+static inline int cv_round_f(float v) { return (int)lrintf(v); }
+
+bool orb_make_geometry(int w, int h, int nfeatures, OrbGeom &g, std::vector<int32_t> &tabs)
+{
+    const double scale_factor = (double)1.2f;   // ORB::create(float scaleFactor = 1.2f) stored as double
+    tabs.clear();
+    int off = 0, cand = 0, ftiles = 0, btiles = 0;
+    // nfeaturesPerLevel (orb.cpp computeKeyPoints)
+    const float factor = (float)(1.0 / scale_factor);
+    float nd = nfeatures * (1 - factor) / (1 - (float)std::pow((double)factor, (double)kOrbLevels));
+    int sum = 0;
+    for (int l = 0; l < kOrbLevels; ++l) {
+        OrbLevel &L = g.lv[l];
+        L.scale = (float)std::pow(scale_factor, (double)l);
+        const float inv = 1.0f / L.scale;
+        L.w = cv_round_f(w * inv);
+        L.h = cv_round_f(h * inv);
+        if (L.w < 1 || L.h < 1) return false;
+        L.pitch = (L.w + 15) & ~15;
+        L.off = off;
+        off += L.pitch * L.h;
+        if (l < kOrbLevels - 1) {
+            L.quota = cv_round_f(nd);
+            sum += L.quota;
+            nd *= factor;
+        } else {
+            L.quota = std::max(nfeatures - sum, 0);
+        }
+        const int rw = L.w - 2 * kOrbEdge, rh = L.h - 2 * kOrbEdge;   // KeyPointsFilter::runByImageBorder region
+        L.cand_off = cand;
+        L.cand_cap = (rw > 0 && rh > 0) ? ((rw + 1) / 2) * ((rh + 1) / 2) : 0;   // strict 3x3 maxima: one per 2x2 block
+        cand += L.cand_cap;
+        L.tile_off = ftiles;
+        if (rw > 0 && rh > 0) ftiles += ((rw + 31) / 32) * ((rh + 15) / 16);
+        L.blur_tile_off = btiles;
+        btiles += ((L.w + 31) / 32) * ((L.h + 31) / 32);
+        // resize tables (imgproc resize.cpp, INTER_LINEAR_EXACT 8-bit: interpolationLinear<ufixedpoint16>)
+        L.tab_off = (int)tabs.size();
+        if (l > 0) {
+            const OrbLevel &P = g.lv[l - 1];
+            for (int axis = 0; axis < 2; ++axis) {
+                const int src = axis ? P.h : P.w, dst = axis ? L.h : L.w;
+                const double inv_scale = (double)dst / (double)src, sc = 1.0 / inv_scale;
+                std::vector<int32_t> ofs(dst), al(dst);
+                for (int d = 0; d < dst; ++d) {
+                    double f = (d + 0.5) * sc - 0.5;
+                    int s0 = (int)std::floor(f);
+                    f -= s0;
+                    if (s0 < 0) { ofs[d] = 0; al[d] = 0; }
+                    else if (s0 >= src - 1) { ofs[d] = src - 1; al[d] = 0; }
+                    else { ofs[d] = s0; al[d] = (int)std::nearbyint(f * 256.0); }
+                }
+                tabs.insert(tabs.end(), ofs.begin(), ofs.end());
+                tabs.insert(tabs.end(), al.begin(), al.end());
+            }
+        }
+    }
+    g.slab = (off + 255) & ~255;
+    g.cand_total = std::max(cand, 1);
+    g.fast_tiles = ftiles;
+    g.blur_tiles = btiles;
+    const float hs = 1.f / ((1 << 2) * 7 * 255.f);
+    g.harris_scale4 = hs * hs * hs * hs;
+    // umax: end of each row of the circular patch (orb.cpp computeKeyPoints)
+    const int hp = kOrbHalfPatch;
+    int umax[hp + 2];
+    const int vmax = (int)std::floor(hp * std::sqrt(2.f) / 2 + 1);
+    const int vmin = (int)std::ceil(hp * std::sqrt(2.f) / 2);
+    for (int v = 0; v <= vmax; ++v) umax[v] = (int)std::nearbyint(std::sqrt((double)hp * hp - v * v));
+    for (int v = hp, v0 = 0; v >= vmin; --v) {
+        while (umax[v0] == umax[v0 + 1]) ++v0;
+        umax[v] = v0;
+        ++v0;
+    }
+    for (int v = 0; v <= hp; ++v) g.umax[v] = umax[v];
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------ O0 import
+// level 0 of every pyramid slab from a dense [images][h][stride] staging buffer
+__global__ void __launch_bounds__(256)
+orb_import_kernel(const __grid_constant__ OrbGeom g, OrbBuffers b, const uint8_t *stage, int stride)
+{
+    const OrbLevel &L = g.lv[0];
+    const int x = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4;
+    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x >= L.w || y >= L.h) return;
+    const uint8_t *src = stage + ((size_t)blockIdx.z * L.h + y) * stride + x;
+    uint8_t *dst = b.pyr + (size_t)blockIdx.z * g.slab + L.off + (size_t)y * L.pitch + x;
+    if (x + 4 <= L.w && (stride & 3) == 0 && ((uintptr_t)stage & 3) == 0) {
+        *reinterpret_cast<uint32_t *>(dst) = *reinterpret_cast<const uint32_t *>(src);
+    } else {
+        for (int k = 0; k < 4 && x + k < L.w; ++k) dst[k] = src[k];
+    }
+}
+
+void launch_orb_import(const OrbGeom &g, const OrbBuffers &b, const uint8_t *stage, int stride, int n_images, cudaStream_t s)
+{
+    const OrbLevel &L = g.lv[0];
+    dim3 grid((L.w + 255) / 256, (L.h + 3) / 4, n_images);
+    orb_import_kernel<<<grid, 256, 0, s>>>(g, b, stage, stride);
+}
+
+// ------------------------------------------------------------------------------------------ O1 resize
+__global__ void __launch_bounds__(256)
+orb_resize_kernel(const __grid_constant__ OrbGeom g, OrbBuffers b, int level)
+{
+    const OrbLevel &D = g.lv[level];
+    const OrbLevel &S = g.lv[level - 1];
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x >= D.w || y >= D.h) return;
+    const int32_t *tx = b.tabs + D.tab_off, *ty = tx + 2 * D.w;
+    const int x0 = tx[x], ax = tx[D.w + x], y0 = ty[y], ay = ty[D.h + y];
+    const int x1 = min(x0 + 1, S.w - 1), y1 = min(y0 + 1, S.h - 1);
+    const uint8_t *src = b.pyr + (size_t)blockIdx.z * g.slab + S.off;
+    const uint8_t *r0 = src + (size_t)y0 * S.pitch, *r1 = src + (size_t)y1 * S.pitch;
+    const uint32_t h0 = r0[x0] * (256 - ax) + r0[x1] * ax;     // 8.8 fixed point
+    const uint32_t h1 = r1[x0] * (256 - ax) + r1[x1] * ax;
+    const uint32_t v = h0 * (256 - ay) + h1 * ay;              // 16.16
+    b.pyr[(size_t)blockIdx.z * g.slab + D.off + (size_t)y * D.pitch + x] = (uint8_t)((v + (1u << 15)) >> 16);
+}
+
+void launch_orb_resize(const OrbGeom &g, const OrbBuffers &b, int level, int n_images, cudaStream_t s)
+{
+    const OrbLevel &D = g.lv[level];
+    dim3 grid((D.w + 63) / 64, (D.h + 3) / 4, n_images);
+    orb_resize_kernel<<<grid, 256, 0, s>>>(g, b, level);
+}
+
+// ------------------------------------------------------------------------------------------ O2 FAST + NMS
+// cornerScore<16> of fast_score.cpp in closed form: the largest threshold at which the pixel is still a FAST-9
+// corner = max over the 16 arcs of 9 contiguous ring pixels of min(v - ring) (darker arc) or min(ring - v)
+// (brighter arc), minus 1; 0 when that does not exceed the detector threshold.
+__device__ __forceinline__ int fast_corner_score(const uint8_t *c, int p)
+{
+    const int v = c[0];
+    int d[16];
+    d[0] = v - c[3 * p];       d[1] = v - c[3 * p + 1];   d[2] = v - c[2 * p + 2];   d[3] = v - c[p + 3];
+    d[4] = v - c[3];           d[5] = v - c[-p + 3];      d[6] = v - c[-2 * p + 2];  d[7] = v - c[-3 * p + 1];
+    d[8] = v - c[-3 * p];      d[9] = v - c[-3 * p - 1];  d[10] = v - c[-2 * p - 2]; d[11] = v - c[-p - 3];
+    d[12] = v - c[-3];         d[13] = v - c[p - 3];      d[14] = v - c[2 * p - 2];  d[15] = v - c[3 * p - 1];
+    const int t = kOrbFastThreshold;
+    // an arc of 9 contains one pixel of every antipodal pair
+    const bool pb = (max(d[0], d[8]) > t) & (max(d[4], d[12]) > t) & (max(d[2], d[10]) > t) & (max(d[6], d[14]) > t);
+    const bool pd = (min(d[0], d[8]) < -t) & (min(d[4], d[12]) < -t) & (min(d[2], d[10]) < -t) & (min(d[6], d[14]) < -t);
+    if (!(pb | pd)) return 0;
+    int lo2[16], hi2[16], lo4[16], hi4[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { lo2[i] = min(d[i], d[(i + 1) & 15]); hi2[i] = max(d[i], d[(i + 1) & 15]); }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { lo4[i] = min(lo2[i], lo2[(i + 2) & 15]); hi4[i] = max(hi2[i], hi2[(i + 2) & 15]); }
+    int a = -255, bmin = 255;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int lo9 = min(min(lo4[i], lo4[(i + 4) & 15]), d[(i + 8) & 15]);
+        const int hi9 = max(max(hi4[i], hi4[(i + 4) & 15]), d[(i + 8) & 15]);
+        a = max(a, lo9);
+        bmin = min(bmin, hi9);
+    }
+    const int m = max(a, -bmin);
+    return m > t ? m - 1 : 0;
+}
+
+constexpr int FT_W = 32, FT_H = 16;
+
+__global__ void __launch_bounds__(256)
+orb_fast_kernel(const __grid_constant__ OrbGeom g, OrbBuffers b)
+{
+    __shared__ uint8_t px[FT_H + 8][FT_W + 8];
+    __shared__ uint8_t sc[FT_H + 2][FT_W + 4];
+    int l = 0;
+    while (l + 1 < kOrbLevels && (int)blockIdx.x >= g.lv[l + 1].tile_off) ++l;
+    const OrbLevel &L = g.lv[l];
+    const int img = blockIdx.y;
+    const int tiles_x = (L.w - 2 * kOrbEdge + 31) / 32;
+    const int t = blockIdx.x - L.tile_off;
+    const int x0 = kOrbEdge + (t % tiles_x) * FT_W, y0 = kOrbEdge + (t / tiles_x) * FT_H;
+    const uint8_t *src = b.pyr + (size_t)img * g.slab + L.off;
+    for (int i = threadIdx.x; i < (FT_H + 8) * (FT_W + 8); i += 256) {
+        const int r = i / (FT_W + 8), c = i % (FT_W + 8);
+        const int y = min(y0 - 4 + r, L.h - 1), x = min(x0 - 4 + c, L.w - 1);
+        px[r][c] = src[(size_t)y * L.pitch + x];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < (FT_H + 2) * (FT_W + 2); i += 256) {
+        const int r = i / (FT_W + 2), c = i % (FT_W + 2);
+        const int y = y0 - 1 + r, x = x0 - 1 + c;
+        int s = 0;
+        if (x < L.w - 3 && y < L.h - 3) s = fast_corner_score(&px[r + 3][c + 3], FT_W + 8);   // fast.cpp tests rows/cols [3, n-3)
+        sc[r][c] = (uint8_t)s;
+    }
+    __syncthreads();
+    const int tx = threadIdx.x & 31, lane = tx;
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        const int ty = (threadIdx.x >> 5) + pass * 8;
+        const int x = x0 + tx, y = y0 + ty;
+        const int s = sc[ty + 1][tx + 1];
+        bool keep = s > 0 && x < L.w - kOrbEdge && y < L.h - kOrbEdge;
+        if (keep) {
+            keep = s > sc[ty][tx] && s > sc[ty][tx + 1] && s > sc[ty][tx + 2] && s > sc[ty + 1][tx] && s > sc[ty + 1][tx + 2] &&
+                   s > sc[ty + 2][tx] && s > sc[ty + 2][tx + 1] && s > sc[ty + 2][tx + 2];
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (m) {
+            int base = 0;
+            if (lane == __ffs(m) - 1) base = atomicAdd(&b.cand_cnt[img * kOrbLevels + l], __popc(m));
+            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+            if (keep) {
+                const int slot = base + __popc(m & ((1u << lane) - 1));
+                const size_t o = (size_t)img * g.cand_total + L.cand_off + slot;
+                b.cand_xy[o] = (uint32_t)x | ((uint32_t)y << 16);
+                b.cand_val[o] = (float)s;
+                atomicAdd(&b.hist[(img * kOrbLevels + l) * 256 + s], 1);
+            }
+        }
+    }
+}
+
+void launch_orb_fast(const OrbGeom &g, const OrbBuffers &b, int n_images, cudaStream_t s)
+{
+    if (!g.fast_tiles) return;
+    orb_fast_kernel<<<dim3(g.fast_tiles, n_images), 256, 0, s>>>(g, b);
+}
+
+// ------------------------------------------------------------------------------------------ O3 first cut + Harris
+// KeyPointsFilter::retainBest(keypoints, 2 * featuresNum) on the FAST score keeps everything >= the n-th largest
+// score (keypoint.cpp): with integer scores that threshold comes from the 256-bin histogram.
+__global__ void __launch_bounds__(256)
+orb_harris_kernel(const __grid_constant__ OrbGeom g, OrbBuffers b)
+{
+    __shared__ int s_hist[256];
+    __shared__ int s_thr;
+    const int l = blockIdx.y, img = blockIdx.z;
+    const OrbLevel &L = g.lv[l];
+    const int n = b.cand_cnt[img * kOrbLevels + l];
+    if ((int)(blockIdx.x * 256) >= n) return;
+    s_hist[threadIdx.x] = b.hist[(img * kOrbLevels + l) * 256 + threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int want = 2 * L.quota;
+        int thr = 0;
+        if (n > want) {
+            thr = 256;                       // want == 0: drop everything
+            int acc = 0;
+            for (int s = 255; s >= 0 && want > 0; --s) {
+                acc += s_hist[s];
+                if (acc >= want) { thr = s; break; }
+            }
+        }
+        s_thr = thr;
+    }
+    __syncthreads();
+    const int thr = s_thr;
+    const uint8_t *im = b.pyr + (size_t)img * g.slab + L.off;
+    const int p = L.pitch;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        const size_t o = (size_t)img * g.cand_total + L.cand_off + i;
+        if (b.cand_val[o] < (float)thr) { b.cand_val[o] = -INFINITY; continue; }
+        const uint32_t xy = b.cand_xy[o];
+        const uint8_t *c0 = im + (size_t)((int)(xy >> 16) - 3) * p + (int)(xy & 0xffff) - 3;
+        int a = 0, bb = 0, c = 0;
+        for (int r = 0; r < 7; ++r) {
+            const uint8_t *q = c0 + r * p;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                const int ix = (q[k + 1] - q[k - 1]) * 2 + (q[k - p + 1] - q[k - p - 1]) + (q[k + p + 1] - q[k + p - 1]);
+                const int iy = (q[k + p] - q[k - p]) * 2 + (q[k + p - 1] - q[k - p - 1]) + (q[k + p + 1] - q[k - p + 1]);
+                a += ix * ix; bb += iy * iy; c += ix * iy;
+            }
+        }
+        // ((float)a * b - (float)c * c - harris_k * ((float)a + b) * ((float)a + b)) * scale^4, one rounding per operation
+        const float fa = (float)a, fb = (float)bb, fc = (float)c;
+        const float tr = __fadd_rn(fa, fb);
+        const float r = __fsub_rn(__fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc)), __fmul_rn(__fmul_rn(0.04f, tr), tr));
+        b.cand_val[o] = __fmul_rn(r, g.harris_scale4);
+    }
+}
+
+void launch_orb_harris(const OrbGeom &g, const OrbBuffers &b, int n_images, cudaStream_t s)
+{
+    int most = 1;
+    for (int l = 0; l < kOrbLevels; ++l) most = std::max(most, g.lv[l].cand_cap);
+    const int gx = std::min((most + 255) / 256, n_images >= 32 ? 8 : 64);
+    orb_harris_kernel<<<dim3(gx, kOrbLevels, n_images), 256, 0, s>>>(g, b);
+}
+
+// ------------------------------------------------------------------------------------------ O4 second cut + order
+__device__ __forceinline__ uint32_t float_order(float f)
+{
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(256)
+orb_select_kernel(const __grid_constant__ OrbGeom g, OrbBuffers b)
+{
+    __shared__ unsigned long long keys[kOrbSortCap];
+    __shared__ int s_hist[256];
+    __shared__ int s_a, s_b;
+    const int l = blockIdx.x, img = blockIdx.y;
+    const OrbLevel &L = g.lv[l];
+    const int n = b.cand_cnt[img * kOrbLevels + l];
+    const float *val = b.cand_val + (size_t)img * g.cand_total + L.cand_off;
+    const uint32_t *xy = b.cand_xy + (size_t)img * g.cand_total + L.cand_off;
+    int32_t *out_cnt = b.kept_cnt + img * kOrbLevels + l;
+    if (n == 0 || L.quota == 0) { if (threadIdx.x == 0) *out_cnt = 0; return; }
+    // survivors of the first cut
+    if (threadIdx.x == 0) s_a = 0;
+    __syncthreads();
+    int mine = 0;
+    for (int i = threadIdx.x; i < n; i += 256) mine += val[i] != -INFINITY;
+    if (mine) atomicAdd(&s_a, mine);
+    __syncthreads();
+    const int survivors = s_a;
+    __syncthreads();
+    uint32_t thr = 0;       // ordered-uint threshold: keep float_order(val) >= thr
+    if (survivors > L.quota) {
+        // retainBest(featuresNum): the quota-th largest response, by 4 x 8-bit radix select
+        uint32_t prefix = 0, mask = 0;
+        int need = L.quota;
+        for (int pass = 3; pass >= 0; --pass) {
+            s_hist[threadIdx.x] = 0;
+            __syncthreads();
+            for (int i = threadIdx.x; i < n; i += 256) {
+                const float v = val[i];
+                const uint32_t u = float_order(v);
+                if (v != -INFINITY && (u & mask) == prefix) atomicAdd(&s_hist[(u >> (8 * pass)) & 255], 1);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int acc = 0, digit = 0;
+                for (int d = 255; d >= 0; --d) {
+                    if (acc + s_hist[d] >= need) { digit = d; break; }
+                    acc += s_hist[d];
+                }
+                s_a = digit; s_b = need - acc;
+            }
+            __syncthreads();
+            prefix |= (uint32_t)s_a << (8 * pass);
+            mask |= 0xffu << (8 * pass);
+            need = s_b;
+            __syncthreads();
+        }
+        thr = prefix;
+    }
+    if (threadIdx.x == 0) s_a = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const float v = val[i];
+        if (v != -INFINITY && float_order(v) >= thr) {
+            const int slot = atomicAdd(&s_a, 1);
+            if (slot < kOrbSortCap) keys[slot] = ((unsigned long long)xy[i] << 32) | (uint32_t)i;   // (y, x) raster key
+        }
+    }
+    __syncthreads();
+    const int kept = s_a;
+    if (kept > kOrbSortCap) { if (threadIdx.x == 0) *out_cnt = -1; return; }
+    int cap = 1;
+    while (cap < kept) cap <<= 1;
+    for (int i = kept + threadIdx.x; i < cap; i += 256) keys[i] = ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= cap; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < cap; i += 256) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const unsigned long long x = keys[i], y = keys[p];
+                    if ((x > y) == ((i & k) == 0)) { keys[i] = y; keys[p] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    uint32_t *out = b.kept_idx + (size_t)(img * kOrbLevels + l) * kOrbSortCap;
+    for (int i = threadIdx.x; i < kept; i += 256) out[i] = (uint32_t)keys[i];
+    if (threadIdx.x == 0) *out_cnt = kept;
+}
+
+void launch_orb_select(const OrbGeom &g, const OrbBuffers &b, int n_images, cudaStream_t s)
+{
+    orb_select_kernel<<<dim3(kOrbLevels, n_images), 256, 0, s>>>(g, b);
+}
+
+// ------------------------------------------------------------------------------------------ O5 Gaussian 7x7
+// GaussianBlur(level, 7x7, sigma 2, BORDER_REFLECT_101) of orb.cpp runs OpenCV's float separable filter on the 8-bit
+// level (the level is a sub-matrix, so the fixed-point path is not taken): row pass left to right, column pass centre
+// first then symmetric pairs, every multiply-add fused, result rounded half-to-even.  getGaussianKernel(7, 2, CV_32F):
+__constant__ float c_gauss[4] = {0x1.ba95c0p-3f, 0x1.869472p-3f, 0x1.0c70fcp-3f, 0x1.1f5f62p-4f};   // centre, +-1, +-2, +-3
+
+__device__ __forceinline__ int reflect101(int i, int n)
+{
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;
+    return i;
+}
+
+__global__ void __launch_bounds__(256)
+orb_blur_kernel(const __grid_constant__ OrbGeom g, OrbBuffers b)
+{
+    __shared__ uint8_t in[38][40];
+    __shared__ float row[38][32];
+    int l = 0;
+    while (l + 1 < kOrbLevels && (int)blockIdx.x >= g.lv[l + 1].blur_tile_off) ++l;
+    const OrbLevel &L = g.lv[l];
+    const int img = blockIdx.y;
+    const int tiles_x = (L.w + 31) / 32;
+    const int t = blockIdx.x - L.blur_tile_off;
+    const int x0 = (t % tiles_x) * 32, y0 = (t / tiles_x) * 32;
+    const uint8_t *src = b.pyr + (size_t)img * g.slab + L.off;
+    for (int i = threadIdx.x; i < 38 * 38; i += 256) {
+        const int r = i / 38, c = i % 38;
+        in[r][c] = src[(size_t)reflect101(y0 - 3 + r, L.h) * L.pitch + reflect101(x0 - 3 + c, L.w)];
+    }
+    __syncthreads();
+    const float k0 = c_gauss[0], k1 = c_gauss[1], k2 = c_gauss[2], k3 = c_gauss[3];
+    for (int i = threadIdx.x; i < 38 * 32; i += 256) {
+        const int r = i >> 5, c = i & 31;
+        float s = __fmul_rn(k3, (float)in[r][c]);
+        s = fmaf(k2, (float)in[r][c + 1], s);
+        s = fmaf(k1, (float)in[r][c + 2], s);
+        s = fmaf(k0, (float)in[r][c + 3], s);
+        s = fmaf(k1, (float)in[r][c + 4], s);
+        s = fmaf(k2, (float)in[r][c + 5], s);
+        s = fmaf(k3, (float)in[r][c + 6], s);
+        row[r][c] = s;
+    }
+    __syncthreads();
+    uint8_t *dst = b.blur + (size_t)img * g.slab + L.off;
+    for (int i = threadIdx.x; i < 32 * 32; i += 256) {
+        const int r = i >> 5, c = i & 31;
+        const int x = x0 + c, y = y0 + r;
+        if (x >= L.w || y >= L.h) continue;
+        float s = __fmul_rn(k0, row[r + 3][c]);
+        s = fmaf(k1, __fadd_rn(row[r + 4][c], row[r + 2][c]), s);
+        s = fmaf(k2, __fadd_rn(row[r + 5][c], row[r + 1][c]), s);
+        s = fmaf(k3, __fadd_rn(row[r + 6][c], row[r][c]), s);
+        dst[(size_t)y * L.pitch + x] = (uint8_t)min(max(__float2int_rn(s), 0), 255);
+    }
+}
+
+void launch_orb_blur(const OrbGeom &g, const OrbBuffers &b, int n_images, cudaStream_t s)
+{
+    orb_blur_kernel<<<dim3(g.blur_tiles, n_images), 256, 0, s>>>(g, b);
+}
+
+// ------------------------------------------------------------------------------------------ O6 orientation + rBRIEF
+// cv::fastAtan2 (degrees, 7th-order odd polynomial, FP32, one rounding per operation)
+__device__ __forceinline__ float fast_atan2_deg(float y, float x)
+{
+    const float s = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = __fmul_rn(0.9997878412794807f, s), p3 = __fmul_rn(-0.3258083974640975f, s);
+    const float p5 = __fmul_rn(0.1555786518463281f, s), p7 = __fmul_rn(-0.04432655554792128f, s);
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float eps = 2.220446049250313e-16f;
+    float a;
+    if (ax >= ay) {
+        const float c = __fdiv_rn(ay, __fadd_rn(ax, eps)), c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        const float c = __fdiv_rn(ax, __fadd_rn(ay, eps)), c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+__constant__ int8_t c_pattern[1024];
+
+__global__ void __launch_bounds__(256)
+orb_describe_kernel(const __grid_constant__ OrbGeom g, OrbBuffers b, OrbDescribeArgs d)
+{
+    // pattern transposed for conflict-free access: s_pat[k][lane] = point k (0..15) of the byte `lane`
+    __shared__ char2 s_pat[16][32];
+    __shared__ int s_start[kOrbLevels + 1];
+    const int img = blockIdx.y;
+    for (int i = threadIdx.x; i < 512; i += 256)
+        s_pat[i & 15][i >> 4] = make_char2(c_pattern[2 * i], c_pattern[2 * i + 1]);
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int l = 0; l < kOrbLevels; ++l) { s_start[l] = acc; acc += max(b.kept_cnt[img * kOrbLevels + l], 0); }
+        s_start[kOrbLevels] = acc;
+    }
+    __syncthreads();
+    const int total = s_start[kOrbLevels];
+    const int lane = threadIdx.x & 31;
+    const int warps = gridDim.x * 8;
+    const size_t out0 = (size_t)d.img_off[img];
+    for (int k = blockIdx.x * 8 + (threadIdx.x >> 5); k < total; k += warps) {
+        int l = 0;
+        while (k >= s_start[l + 1]) ++l;
+        const OrbLevel &L = g.lv[l];
+        const uint32_t ci = b.kept_idx[(size_t)(img * kOrbLevels + l) * kOrbSortCap + (k - s_start[l])];
+        const size_t o = (size_t)img * g.cand_total + L.cand_off + ci;
+        const uint32_t xy = b.cand_xy[o];
+        const int cx = xy & 0xffff, cy = xy >> 16;
+        // ICAngles: moments over the circular patch of the un-blurred level; lane = u + 15
+        const uint8_t *im = b.pyr + (size_t)img * g.slab + L.off + (size_t)cy * L.pitch + cx;
+        const int u = lane - kOrbHalfPatch;
+        int m10 = 0, m01 = 0;
+        if (lane < 31) {
+            for (int v = -kOrbHalfPatch; v <= kOrbHalfPatch; ++v) {
+                if (abs(u) <= g.umax[abs(v)]) {
+                    const int p = im[v * L.pitch + u];
+                    m10 += u * p; m01 += v * p;
+                }
+            }
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            m10 += __shfl_xor_sync(0xffffffffu, m10, s);
+            m01 += __shfl_xor_sync(0xffffffffu, m01, s);
+        }
+        const float angle = fast_atan2_deg((float)m01, (float)m10);
+        // computeOrbDescriptors: angle in radians (float), cos/sin evaluated in double and rounded to float
+        const float rad = __fmul_rn(angle, (float)(3.14159265358979323846 / 180.f));
+        const float ca = (float)cos((double)rad), sa = (float)sin((double)rad);
+        const uint8_t *bl = b.blur + (size_t)img * g.slab + L.off + (size_t)cy * L.pitch + cx;
+        int byte = 0;
+#pragma unroll
+        for (int bit = 0; bit < 8; ++bit) {
+            const char2 q0 = s_pat[2 * bit][lane], q1 = s_pat[2 * bit + 1][lane];
+            const int x0 = __float2int_rn(__fsub_rn(__fmul_rn((float)q0.x, ca), __fmul_rn((float)q0.y, sa)));
+            const int y0 = __float2int_rn(__fadd_rn(__fmul_rn((float)q0.x, sa), __fmul_rn((float)q0.y, ca)));
+            const int x1 = __float2int_rn(__fsub_rn(__fmul_rn((float)q1.x, ca), __fmul_rn((float)q1.y, sa)));
+            const int y1 = __float2int_rn(__fadd_rn(__fmul_rn((float)q1.x, sa), __fmul_rn((float)q1.y, ca)));
+            byte |= (int)(bl[y0 * L.pitch + x0] < bl[y1 * L.pitch + x1]) << bit;
+        }
+        d.desc[(out0 + k) * 32 + lane] = (uint8_t)byte;
+        if (lane == 0) {
+            const float px = __fmul_rn((float)cx, L.scale), py = __fmul_rn((float)cy, L.scale);
+            if (d.kp) {
+                mvs_keypoint kp;
+                kp.x = px; kp.y = py;
+                kp.size = __fmul_rn(31.f, L.scale);
+                kp.angle = angle;
+                kp.response = b.cand_val[o];
+                kp.octave = l;
+                d.kp[out0 + k] = kp;
+            }
+            if (d.frame_kp) d.frame_kp[out0 + k] = make_float2(px, py);
+        }
+    }
+}
+
+void launch_orb_describe(const OrbGeom &g, const OrbBuffers &b, const OrbDescribeArgs &d, int n_images, int ctas_per_image,
+                         cudaStream_t s)
+{
+    static bool pattern_loaded[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 64 || !pattern_loaded[dev]) {   // synchronous copy: complete before any kernel that reads it is enqueued
+        cudaMemcpyToSymbol(c_pattern, MVS_ORB_PATTERN, sizeof(MVS_ORB_PATTERN));
+        if (dev < 64) pattern_loaded[dev] = true;
+    }
+    orb_describe_kernel<<<dim3(ctas_per_image, n_images), 256, 0, s>>>(g, b, d);
+}
+
+}  // namespace mvs

@@ -93,3 +93,31 @@ def synthetic_l2(nq=32768, nt=32768, dim=64, seed=1234):
     C = Q[:m] + 0.05 * r2.normal(size=(m, dim)).astype(np.float32)
     T[perm] = C / np.linalg.norm(C, axis=1, keepdims=True)
     return np.ascontiguousarray(Q), np.ascontiguousarray(T)
+
+
+def synthetic_image(seed, width=640, height=480, n_shapes=220):
+    """Seeded 8-bit grayscale test image with plenty of corners at several scales: smooth background, overlapping
+    rectangles and triangles of random intensity, mild noise.  Input generator for the feature-extraction tests/bench."""
+    rng = np.random.Generator(np.random.PCG64(0x0B5E0000 + seed))
+    coarse = rng.random((height // 32 + 2, width // 32 + 2)) * 120 + 40
+    yy = np.arange(height) / 32.0
+    xx = np.arange(width) / 32.0
+    y0 = yy.astype(int); x0 = xx.astype(int)
+    fy = (yy - y0)[:, None]; fx = (xx - x0)[None, :]
+    img = ((1 - fy) * (1 - fx) * coarse[y0][:, x0] + (1 - fy) * fx * coarse[y0][:, x0 + 1]
+           + fy * (1 - fx) * coarse[y0 + 1][:, x0] + fy * fx * coarse[y0 + 1][:, x0 + 1])
+    Y, X = np.mgrid[0:height, 0:width]
+    for _ in range(n_shapes):
+        cx, cy = rng.integers(0, width), rng.integers(0, height)
+        sz = int(rng.integers(4, 70))
+        val = float(rng.integers(0, 256))
+        if rng.random() < 0.6:
+            a = rng.random() * np.pi
+            u = (X - cx) * np.cos(a) + (Y - cy) * np.sin(a)
+            v = -(X - cx) * np.sin(a) + (Y - cy) * np.cos(a)
+            m = (np.abs(u) < sz) & (np.abs(v) < sz * (0.3 + 0.7 * rng.random()))
+        else:
+            m = (X - cx >= 0) & (Y - cy >= 0) & ((X - cx) + (Y - cy) * (0.5 + rng.random()) < sz)
+        img = np.where(m, 0.75 * val + 0.25 * img, img)
+    img = img + rng.normal(0, 2.0, img.shape)
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)

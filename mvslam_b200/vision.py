@@ -1,5 +1,6 @@
 """Python mirror of the reference's entry points for this path (same names / argument meaning):
 
+  VisualFeature.extract(image)                              source/vision/visual-feature.hpp:14
   VisualFeature.match_visual_features(vf1, vf2, max_dist)   source/vision/visual-feature.hpp:23-26
   sfm_solve(p1, p2, K)                                      source/vision/sfm.hpp:30-35
   sfm_triangulate(p1, p2, K, pose1, pose2)                  source/vision/sfm.hpp:47-53
@@ -23,13 +24,21 @@ def default_context():
 
 
 class VisualFeature:
-    """Keypoints + descriptors of one frame (source/vision/visual-feature.hpp:91-93).  Extraction (ORB)
-    is outside the hot path and stays with the caller (cv2.ORB on the host)."""
+    """Keypoints + descriptors of one frame (source/vision/visual-feature.hpp:91-93)."""
 
     def __init__(self, keypoints_xy, descriptors, image_width=-1, image_height=-1):
         self.keypoints = np.ascontiguousarray(keypoints_xy, np.float32).reshape(-1, 2)
         self.descriptors = np.ascontiguousarray(descriptors, np.uint8)
         self.image_width, self.image_height = image_width, image_height
+
+    @staticmethod
+    def extract(image, n_features=500, ctx=None):
+        """cv::ORB detect + compute on the device (visual-feature.cpp:40-49; MAX_FEATURE_COUNT = 500, :9)."""
+        ctx = ctx or default_context()
+        _, kp, desc, _ = ctx.orb_extract([image], n_features)
+        vf = VisualFeature(np.stack([kp["x"], kp["y"]], 1), desc, image.shape[1], image.shape[0])
+        vf.cv_keypoints = kp
+        return vf
 
     def size(self):
         return self.keypoints.shape[0]
