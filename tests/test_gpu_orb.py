@@ -1,0 +1,160 @@
+"""GPU parity tests of feature extraction: mvs_orb_extract (CUDA, through the C ABI) against the committed cv2.ORB
+goldens, against the numpy oracle (oracle/orb_np.py) on seeded synthetic images, and — where cv2 is importable on the
+box — against the live third-party routine the reference calls (source/vision/visual-feature.cpp:9-17,40-49).
+
+Bar: bit-exact — identical keypoint set (compared in the canonical order level, y, x), identical float32 pt / size /
+angle / response, identical 32 descriptor bytes."""
+import os
+
+import numpy as np
+import pytest
+
+import mvslam_b200 as mvs
+from mvslam_b200 import synth
+from oracle import orb_np as O
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = mvs.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def gray():
+    return np.load(os.path.join(GOLDEN, "tsukuba_gray.npz"))["gray"]
+
+
+def split(counts, kp, desc):
+    out, at = [], 0
+    for c in counts:
+        out.append((kp[at:at + c], desc[at:at + c]))
+        at += c
+    return out
+
+
+def assert_same(ref, kp, desc, what=""):
+    assert len(ref["pt"]) == len(kp), f"{what}: {len(ref['pt'])} vs {len(kp)} keypoints"
+    assert np.array_equal(ref["pt"][:, 0], kp["x"]) and np.array_equal(ref["pt"][:, 1], kp["y"]), f"{what}: pt"
+    assert np.array_equal(ref["octave"], kp["octave"]), f"{what}: octave"
+    assert np.array_equal(ref["size"], kp["size"]), f"{what}: size"
+    assert np.array_equal(ref["response"], kp["response"]), f"{what}: response"
+    assert np.array_equal(ref["angle"], kp["angle"]), f"{what}: angle"
+    bad = int((ref["desc"] != desc).any(1).sum())
+    assert bad == 0, f"{what}: {bad} of {len(kp)} descriptors differ"
+
+
+def test_tsukuba_matches_cv2_golden(ctx, gray):
+    gold = np.load(os.path.join(GOLDEN, "orb_golden.npz"))
+    for nf, frames in ((500, (1, 2, 3, 4, 5)), (2000, (1, 2))):
+        counts, kp, desc, _ = ctx.orb_extract([gray[f - 1] for f in frames], nf)
+        for f, (k, d) in zip(frames, split(counts, kp, desc)):
+            ref = {n: gold[f"n{nf}_f{f}_{n}"] for n in ("pt", "octave", "size", "angle", "response", "desc")}
+            assert_same(ref, k, d, f"tsukuba frame {f} nfeatures {nf}")
+
+
+@pytest.mark.parametrize("w,h,nf,n_img", [(640, 480, 500, 3), (333, 257, 2000, 2), (200, 150, 1000, 1), (70, 66, 500, 2),
+                                          (1280, 720, 4000, 1)])
+def test_synthetic_matches_oracle(ctx, w, h, nf, n_img):
+    imgs = [synth.synthetic_image(100 + 7 * i + w, w, h) for i in range(n_img)]
+    counts, kp, desc, _ = ctx.orb_extract(imgs, nf)
+    assert counts.sum() > 0
+    for i, (k, d) in enumerate(split(counts, kp, desc)):
+        assert_same(O.orb_extract(imgs[i], nf), k, d, f"synthetic {w}x{h} image {i}")
+
+
+def test_matches_live_cv2(ctx):
+    cv2 = pytest.importorskip("cv2")
+    imgs = [synth.synthetic_image(900 + i, 512, 384) for i in range(4)]
+    counts, kp, desc, _ = ctx.orb_extract(imgs, 1500)
+    scales = O.level_scales()
+    for i, (k, d) in enumerate(split(counts, kp, desc)):
+        orb = cv2.ORB_create(1500)
+        ck = orb.detect(imgs[i], None)             # the reference's two calls
+        ck, cd = orb.compute(imgs[i], ck)
+        pt = np.array([c.pt for c in ck], np.float32); octv = np.array([c.octave for c in ck], np.int32)
+        inv = np.array([np.float32(1) / scales[o] for o in octv], np.float32)
+        lxy = np.rint(pt * inv[:, None]).astype(np.int32)
+        order = np.lexsort((lxy[:, 0], lxy[:, 1], octv))
+        ref = dict(pt=pt[order], octave=octv[order], size=np.array([c.size for c in ck], np.float32)[order],
+                   angle=np.array([c.angle for c in ck], np.float32)[order],
+                   response=np.array([c.response for c in ck], np.float32)[order], desc=cd[order])
+        assert_same(ref, k, d, f"live cv2 image {i}")
+
+
+def test_degenerate_inputs(ctx):
+    flat = np.full((120, 160), 77, np.uint8)
+    counts, kp, desc, _ = ctx.orb_extract([flat, flat], 500)
+    assert counts.tolist() == [0, 0] and len(kp) == 0
+    img = synth.synthetic_image(5, 320, 240)
+    counts, kp, desc, _ = ctx.orb_extract([img], 0)            # nfeatures = 0 keeps nothing
+    assert counts.tolist() == [0]
+    with pytest.raises(mvs.MvsError) as e:                      # level 7 would be empty (cv2 asserts in resize)
+        ctx.orb_extract([np.zeros((1, 1), np.uint8)], 500)
+    assert e.value.status == mvs.E_UNSUPPORTED
+    counts, _, _, _ = ctx.orb_extract([np.zeros((2, 2), np.uint8)], 500)   # tiny but valid: no interior, no keypoints
+    assert counts.tolist() == [0]
+    # batch result equals per-image result (no cross-image state)
+    a = synth.synthetic_image(6, 320, 240)
+    c2, k2, d2, _ = ctx.orb_extract([img, a, img], 700)
+    c1, k1, d1, _ = ctx.orb_extract([img], 700)
+    parts = split(c2, k2, d2)
+    assert np.array_equal(parts[0][1], d1) and np.array_equal(parts[2][1], d1) and np.array_equal(parts[0][0], k1)
+
+
+def test_ties_at_the_cutoff_are_kept(ctx):
+    """retainBest keeps every keypoint whose response equals the cut-off: a periodic image has many such ties."""
+    tile = synth.synthetic_image(8, 64, 64)
+    img = np.tile(tile, (6, 8))
+    r = O.orb_extract(img, 300)
+    counts, kp, desc, _ = ctx.orb_extract([img], 300)
+    assert counts[0] == len(r["pt"]) and counts[0] > 300
+    assert_same(r, kp, desc, "periodic image")
+
+
+def test_device_images_and_frame_table_handoff(ctx, gray):
+    """Images already in HBM; extracted frames go straight into the resident frame table and pair_batch sees exactly
+    what it would have seen had the host uploaded the same features."""
+    import torch
+    K = np.array([[350.0, 0, 192], [0, 350.0, 144], [0, 0, 1]])
+    dev = torch.from_numpy(gray[:3].copy()).cuda()
+    ctx.frames_clear()
+    counts, kp, desc, first = ctx.orb_extract(None, 2000, append_frames=True, device_ptr=dev.data_ptr(),
+                                               shape=(3, gray.shape[1], gray.shape[2], gray.shape[2]))
+    assert first == 0
+    res_dev, det_dev = ctx.pair_batch([(0, 1), (1, 2), (0, 2)], K, max_dist=10.0, H=64)
+    parts = split(counts, kp, desc)
+    ctx.frames_upload([d for _, d in parts], [np.stack([k["x"], k["y"]], 1) for k, _ in parts])
+    res_up, det_up = ctx.pair_batch([(0, 1), (1, 2), (0, 2)], K, max_dist=10.0, H=64)
+    assert res_dev.tobytes() == res_up.tobytes()
+    assert np.array_equal(det_dev["matches"], det_up["matches"])
+    assert (res_dev["status"] == mvs.OK).all() and (res_dev["n_points"] > 20).all()
+    # a second append continues the table
+    c2, _, _, first2 = ctx.orb_extract([gray[3]], 2000, append_frames=True)
+    assert first2 == 3
+    res, _ = ctx.pair_batch([(2, 3)], K, max_dist=10.0, H=64)
+    assert res["status"][0] == mvs.OK
+    ctx.frames_clear()
+
+
+def test_strided_rows(ctx):
+    img = synth.synthetic_image(12, 300, 200)
+    padded = np.zeros((200, 320), np.uint8); padded[:, :300] = img
+    L = mvs.load_library()
+    import ctypes as C
+    op = mvs.OrbParams(500, (C.c_int32 * 3)(0, 0, 0))
+    counts = np.zeros(1, np.int32); kp = np.zeros(600, mvs.KEYPOINT_DTYPE); desc = np.zeros((600, 32), np.uint8)
+    ptrs = (C.c_void_p * 1)(padded.ctypes.data)
+    st = L.mvs_orb_extract(ctx._h, ptrs, 1, 300, 200, 320, C.byref(op), 0, None, counts.ctypes.data_as(C.c_void_p),
+                           kp.ctypes.data_as(C.c_void_p), desc.ctypes.data_as(C.c_void_p), C.c_int64(600))
+    assert st == mvs.OK
+    c1, k1, d1, _ = ctx.orb_extract([img], 500)
+    assert counts[0] == c1[0] and np.array_equal(desc[:counts[0]], d1) and np.array_equal(kp[:counts[0]], k1)
+    # capacity too small: counts still filled
+    st = L.mvs_orb_extract(ctx._h, ptrs, 1, 300, 200, 320, C.byref(op), 0, None, counts.ctypes.data_as(C.c_void_p),
+                           kp.ctypes.data_as(C.c_void_p), desc.ctypes.data_as(C.c_void_p), C.c_int64(10))
+    assert st == mvs.E_CAPACITY and counts[0] == c1[0]
