@@ -167,6 +167,72 @@ def run_reference(args, cfg_loader):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------ feature extraction extra
+def extraction_extra(ctx, stream, n_img=256, nf=2000, steps=5, cpu=True):
+    """SURVEY 8(f) rank 1: VisualFeature::extract (cv::ORB detect + compute) on the device for a batch of the bundled
+    Tsukuba frames — device-resident and end to end from pinned host images — next to cv2.ORB (the third-party routine
+    the reference calls) on the host cores.  Reported beside the headline; not part of `value`."""
+    import torch
+    import mvslam_b200 as mvs
+    gp = os.path.join(ROOT, "tests", "golden", "tsukuba_gray.npz")
+    if not os.path.exists(gp):
+        return None
+    gray = np.load(gp)["gray"]
+    h, w = gray.shape[1:]
+    host = torch.from_numpy(np.stack([gray[i % len(gray)] for i in range(n_img)])).pin_memory()
+    dev = host.cuda()
+    shape = (n_img, h, w, w)
+    cap = n_img * (nf + 64)
+    kp_t = torch.empty(cap * mvs.KEYPOINT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    de_t = torch.empty(cap * 32, dtype=torch.uint8).pin_memory()
+    out = dict(kp=kp_t.data_ptr(), desc=de_t.data_ptr(), capacity=cap)
+    imgs = [host[i].numpy() for i in range(n_img)]
+    for _ in range(3):
+        counts, _, _, _ = ctx.orb_extract(None, nf, want=False, device_ptr=dev.data_ptr(), shape=shape)
+    ctx.profile_enable(True); ctx.profile_read(reset=True)
+    l0 = ctx.kernel_launches()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(steps):
+        ctx.orb_extract(None, nf, want=False, device_ptr=dev.data_ptr(), shape=shape)
+    b.record(stream); torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    prof = ctx.profile_read(); ctx.profile_enable(False)
+    launches = (ctx.kernel_launches() - l0) // steps
+    ctx.orb_extract(imgs, nf, out=out)
+    a.record(stream)
+    for _ in range(steps):
+        ctx.orb_extract(imgs, nf, out=out)
+    b.record(stream); torch.cuda.synchronize()
+    e2e_ms = a.elapsed_time(b) / steps
+    t0 = time.perf_counter()
+    for _ in range(20):
+        ctx.orb_extract(imgs[:1], nf, out=out)
+    lat_us = (time.perf_counter() - t0) / 20 * 1e6
+    pyr_px = sum(int(round(w / 1.2 ** l)) * int(round(h / 1.2 ** l)) for l in range(8))
+    r = dict(what="VisualFeature::extract = cv::ORB(nfeatures) detect+compute, bit-exact vs cv2 (tests/test_gpu_orb.py)",
+             images_per_step=n_img, width=w, height=h, n_features=nf, keypoints_per_image=float(counts.mean()),
+             value=n_img / (ms * 1e-3), unit="frames/s", ms_per_step=ms, gpu_launches_per_step=int(launches),
+             e2e=dict(value=n_img / (e2e_ms * 1e-3), unit="frames/s", ms_per_step=e2e_ms, h2d_bytes_per_step=int(host.numel()),
+                      d2h_bytes_per_step=int(counts.sum()) * (32 + mvs.KEYPOINT_DTYPE.itemsize) + 4 * n_img),
+             single_frame_latency_us=lat_us,
+             stage_ms_per_step={k: round(v[0] / steps, 4) for k, v in prof.items() if k.startswith("orb")},
+             pyramid_pixels_per_image=pyr_px)
+    if cpu:
+        try:
+            import cv2
+            cv2.setNumThreads(host_threads())
+            orb = cv2.ORB_create(nf)
+            t0 = time.perf_counter(); n = 0
+            while time.perf_counter() - t0 < 4.0:
+                k = orb.detect(imgs[n % n_img], None); orb.compute(imgs[n % n_img], k); n += 1
+            r["cpu_baseline"] = dict(value=n / (time.perf_counter() - t0), unit="frames/s", cores=host_threads(), kind="reference",
+                                     sample=f"{n} frames in 4 s, cv2 {cv2.__version__} ORB detect+compute (OpenCV's own threading)")
+        except ImportError:
+            r["cpu_baseline"] = None
+    return r
+
+
 # ------------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -407,6 +473,10 @@ def main():
         cpu = dict(value=v, unit="pairs/s", cores=threads, kind="port",
                    sample=f"{n_sample} pairs of the same workload in {dt:.1f} s, C oracle (own-branch port), OpenMP over pairs")
 
+    extract = None
+    if world == 1 and args.workload == "tsukuba":
+        extract = extraction_extra(ctx, stream, cpu=not args.no_cpu_baseline)
+
     n_job = int(cfg.get("pairs_total", B * world))      # pairs all ranks processed per step
     value = n_job * args.steps / (total_ms * 1e-3)
     line = dict(metric=METRIC, value=value, unit="pairs/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
@@ -419,6 +489,7 @@ def main():
                 e2e=dict(value=n_job / (e2e_ms * 1e-3), unit="pairs/s", h2d_bytes_per_step=int(h2d),
                          d2h_bytes_per_step=int(d2h), ms_per_step=e2e_ms),
                 gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, bounded_search=bounded_extra,
+                extraction=extract,
                 ransac=dict(hyp_pt_evals_per_s=evals / (score_ms * 1e-3) if score_ms > 0 else None,
                             evals_per_step=evals, score_ms_per_step=score_ms,
                             hypotheses_per_s=params["H"] * int(scored.sum()) / max(prof["hypotheses"][0] / args.steps * 1e-3, 1e-12)))

@@ -47,9 +47,19 @@ struct ImagePoint {  // cv::Point_<ScalarType>
     ImagePoint(ScalarType x_, ScalarType y_) : x(x_), y(y_) {}
 };
 
-struct KeyPoint {    // the fields of cv::KeyPoint the path reads
+struct KeyPoint {    // cv::KeyPoint
     struct { float x, y; } pt{0, 0};
-    int octave = 0;
+    float size = 0, angle = -1, response = 0;
+    int octave = 0, class_id = -1;
+};
+
+struct ImageGrayscale {   // the fields of a CV_8UC1 cv::Mat that VisualFeature::extract reads (source/base/image.hpp:21-23)
+    int rows = 0, cols = 0;
+    size_t step = 0;      // bytes per row
+    const uint8_t *data = nullptr;
+    ImageGrayscale() = default;
+    ImageGrayscale(int rows_, int cols_, const uint8_t *data_, size_t step_ = 0)
+        : rows(rows_), cols(cols_), step(step_ ? step_ : (size_t)cols_), data(data_) {}
 };
 
 struct DMatch {      // cv::DMatch

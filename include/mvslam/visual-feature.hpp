@@ -10,12 +10,67 @@ namespace mvSLAM {
 class VisualFeature {
 public:
     VisualFeature() = default;
-    /** keypoints + 32-byte descriptors as produced by cv::ORB (extraction stays on the host, outside the path) */
+    /** keypoints + 32-byte descriptors as produced by cv::ORB (e.g. extracted elsewhere) */
     VisualFeature(VisualFeatureConfig::DetectorResultType kps, VisualFeatureConfig::ExtractorResultType desc,
                   int image_width, int image_height)
         : m_keypoints(std::move(kps)), m_descriptors(std::move(desc)), m_image_width(image_width), m_image_height(image_height)
     {
         if (m_descriptors.size() != m_keypoints.size() * 32) throw b200::Error(MVS_E_BAD_ARG, "descriptor rows must be 32 bytes");
+    }
+
+    static constexpr int MAX_FEATURE_COUNT = 500;   // visual-feature.cpp:9
+
+    /** visual-feature.hpp:14 / visual-feature.cpp:40-49: cv::ORB::create(MAX_FEATURE_COUNT) detect + compute, on the
+     *  device.  Same keypoint set, responses, angles and descriptor bytes as cv::ORB; order is (level, y, x). */
+    static VisualFeature extract(const ImageGrayscale &image, int n_features = MAX_FEATURE_COUNT)
+    {
+        return std::move(extract_batch({image}, n_features)[0]);
+    }
+
+    /** Many same-size images in one device pass (what FrameManager::add_frame does per image,
+     *  source/front-end/frame-manager.cpp:107-125, for a whole window at once). */
+    static std::vector<VisualFeature> extract_batch(const std::vector<ImageGrayscale> &images, int n_features = MAX_FEATURE_COUNT)
+    {
+        if (images.empty()) return {};
+        mvs_ctx *ctx = b200::Context::thread_default().get();
+        const int n = (int)images.size(), w = images[0].cols, h = images[0].rows;
+        const size_t step = images[0].step;
+        std::vector<const uint8_t *> ptrs(n);
+        for (int i = 0; i < n; ++i) {
+            if (images[i].cols != w || images[i].rows != h || images[i].step != step || !images[i].data)
+                throw b200::Error(MVS_E_BAD_ARG, "extract_batch: images must share one size and stride");
+            ptrs[i] = images[i].data;
+        }
+        const mvs_orb_params op{n_features, {0, 0, 0}};
+        std::vector<int32_t> counts(n);
+        int64_t cap = (int64_t)n * (n_features + 64);
+        std::vector<mvs_keypoint> kp((size_t)cap);
+        std::vector<uint8_t> desc((size_t)cap * 32);
+        int st = mvs_orb_extract(ctx, ptrs.data(), n, w, h, (int)step, &op, 0, nullptr, counts.data(), kp.data(), desc.data(), cap);
+        if (st == MVS_E_CAPACITY) {   // many keypoints tied at a cut-off response: counts[] holds the exact sizes
+            cap = 0;
+            for (int c : counts) cap += c;
+            if (cap > (int64_t)kp.size()) {
+                kp.resize((size_t)cap); desc.resize((size_t)cap * 32);
+                st = mvs_orb_extract(ctx, ptrs.data(), n, w, h, (int)step, &op, 0, nullptr, counts.data(), kp.data(), desc.data(), cap);
+            }
+        }
+        b200::check(ctx, st, "VisualFeature::extract");
+        std::vector<VisualFeature> out(n);
+        size_t at = 0;
+        for (int i = 0; i < n; ++i) {
+            VisualFeature &vf = out[i];
+            vf.m_image_width = w; vf.m_image_height = h;
+            vf.m_keypoints.resize(counts[i]);
+            for (int k = 0; k < counts[i]; ++k) {
+                const mvs_keypoint &s = kp[at + k];
+                KeyPoint &d = vf.m_keypoints[k];
+                d.pt.x = s.x; d.pt.y = s.y; d.size = s.size; d.angle = s.angle; d.response = s.response; d.octave = s.octave;
+            }
+            vf.m_descriptors.assign(desc.begin() + at * 32, desc.begin() + (at + counts[i]) * 32);
+            at += (size_t)counts[i];
+        }
+        return out;
     }
 
     /** Matches from 2 to 1 (query = vf2, train = vf1) sorted by ascending distance

@@ -161,11 +161,12 @@ class Context:
         return int(self._L.mvs_kernel_launches(self._h))
 
     # ---- feature extraction
-    def orb_extract(self, images, n_features=500, append_frames=False, want=True, device_ptr=None, shape=None):
+    def orb_extract(self, images, n_features=500, append_frames=False, want=True, device_ptr=None, shape=None, out=None):
         """VisualFeature::extract for a list/array of equal-size 8-bit grayscale images.
 
         Returns (counts int32[n], keypoints KEYPOINT_DTYPE[total], descriptors uint8[total][32], first_frame).
-        device_ptr/shape=(n, h, stride, w): the images already live in device memory (contiguous)."""
+        device_ptr/shape=(n, h, stride, w): the images already live in device memory (contiguous).
+        out=dict(kp=addr, desc=addr, capacity=int): preallocated (e.g. pinned) result buffers; returns counts only."""
         op = OrbParams(int(n_features), (C.c_int32 * 3)(0, 0, 0))
         first = C.c_int32(-1)
         if device_ptr is None:
@@ -183,7 +184,10 @@ class Context:
                                                _p(counts), _p(kp), _p(desc), C.c_int64(cap))
             return self._L.mvs_orb_extract_device(self._h, C.c_void_p(int(device_ptr)), n, w, h, stride, C.byref(op),
                                                   int(append), C.byref(first), _p(counts), _p(kp), _p(desc), C.c_int64(cap))
-        if not want:
+        if out is not None:
+            self._check(call(out["kp"], out["desc"], int(out["capacity"]), append_frames))
+            kp = desc = None
+        elif not want:
             self._check(call(None, None, 0, append_frames))
             kp = desc = None
         else:

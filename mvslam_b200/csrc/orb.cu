@@ -188,12 +188,27 @@ __device__ __forceinline__ int fast_corner_score(const uint8_t *c, int p)
 }
 
 constexpr int FT_W = 32, FT_H = 16;
+constexpr int FT_PW = FT_W + 8, FT_PH = FT_H + 8;      // pixel tile (halo 4: 1 for the NMS ring + 3 for the FAST ring)
+constexpr int FT_SW = FT_W + 2, FT_SH = FT_H + 2;      // score tile
+
+// Cheap necessary condition on 4 of the 8 antipodal pairs (an arc of 9 contains one pixel of every pair).
+__device__ __forceinline__ bool fast_maybe_corner(const uint8_t *c, int p)
+{
+    const int v = c[0], t = kOrbFastThreshold;
+    const int d0 = v - c[3 * p], d8 = v - c[-3 * p], d4 = v - c[3], d12 = v - c[-3];
+    const bool pb = (max(d0, d8) > t) & (max(d4, d12) > t), pd = (min(d0, d8) < -t) & (min(d4, d12) < -t);
+    if (!(pb | pd)) return false;
+    const int d2 = v - c[2 * p + 2], d10 = v - c[-2 * p - 2], d6 = v - c[-2 * p + 2], d14 = v - c[2 * p - 2];
+    return (pb & (max(d2, d10) > t) & (max(d6, d14) > t)) | (pd & (min(d2, d10) < -t) & (min(d6, d14) < -t));
+}
 
 __global__ void __launch_bounds__(256)
 orb_fast_kernel(const __grid_constant__ OrbGeom g, OrbBuffers b)
 {
-    __shared__ uint8_t px[FT_H + 8][FT_W + 8];
-    __shared__ uint8_t sc[FT_H + 2][FT_W + 4];
+    __shared__ __align__(16) uint8_t px[FT_PH][FT_PW];
+    __shared__ uint8_t sc[FT_SH][FT_SW + 2];
+    __shared__ uint16_t todo[FT_SH * FT_SW];
+    __shared__ int n_todo;
     int l = 0;
     while (l + 1 < kOrbLevels && (int)blockIdx.x >= g.lv[l + 1].tile_off) ++l;
     const OrbLevel &L = g.lv[l];
@@ -202,18 +217,44 @@ orb_fast_kernel(const __grid_constant__ OrbGeom g, OrbBuffers b)
     const int t = blockIdx.x - L.tile_off;
     const int x0 = kOrbEdge + (t % tiles_x) * FT_W, y0 = kOrbEdge + (t / tiles_x) * FT_H;
     const uint8_t *src = b.pyr + (size_t)img * g.slab + L.off;
-    for (int i = threadIdx.x; i < (FT_H + 8) * (FT_W + 8); i += 256) {
-        const int r = i / (FT_W + 8), c = i % (FT_W + 8);
-        const int y = min(y0 - 4 + r, L.h - 1), x = min(x0 - 4 + c, L.w - 1);
-        px[r][c] = src[(size_t)y * L.pitch + x];
+    if (threadIdx.x == 0) n_todo = 0;
+    // pixel tile rows [y0-4, y0+20) x cols [x0-4, x0+36): x0 - 4 = 27 + 32k is odd, so the 4-byte words start at x0 - 7
+    // (11 words per row cover the tile); rows beyond the image repeat the last row (never used by a tested pixel)
+    for (int i = threadIdx.x; i < FT_PH * 11; i += 256) {
+        const int r = i / 11, wd = i % 11;
+        const int y = min(y0 - 4 + r, L.h - 1);
+        const int xw = x0 - 7 + 4 * wd;                        // multiple of 4
+        uint32_t v = 0;
+        if (xw < L.pitch) v = *reinterpret_cast<const uint32_t *>(src + (size_t)y * L.pitch + xw);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = 4 * wd + k - 3;                      // column inside px
+            if (c >= 0 && c < FT_PW) px[r][c] = (uint8_t)(v >> (8 * k));
+        }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < (FT_H + 2) * (FT_W + 2); i += 256) {
-        const int r = i / (FT_W + 2), c = i % (FT_W + 2);
+    // phase 1: cheap rejection; survivors are queued so that phase 2 runs the full score on dense warps
+    for (int i0 = 0; i0 < FT_SH * FT_SW; i0 += 256) {         // uniform trip count: full-warp ballots
+        const int i = i0 + threadIdx.x;
+        const bool in = i < FT_SH * FT_SW;
+        const int r = in ? i / FT_SW : 0, c = in ? i % FT_SW : 0;
         const int y = y0 - 1 + r, x = x0 - 1 + c;
-        int s = 0;
-        if (x < L.w - 3 && y < L.h - 3) s = fast_corner_score(&px[r + 3][c + 3], FT_W + 8);   // fast.cpp tests rows/cols [3, n-3)
-        sc[r][c] = (uint8_t)s;
+        if (in) sc[r][c] = 0;
+        const bool maybe = in && x < L.w - 3 && y < L.h - 3 && fast_maybe_corner(&px[r + 3][c + 3], FT_PW);   // fast.cpp tests [3, n-3)
+        const unsigned m = __ballot_sync(0xffffffffu, maybe);
+        if (maybe) {
+            const unsigned lane = threadIdx.x & 31;
+            int base = 0;
+            if (lane == __ffs(m) - 1) base = atomicAdd(&n_todo, __popc(m));
+            base = __shfl_sync(m, base, __ffs(m) - 1);
+            todo[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)i;
+        }
+    }
+    __syncthreads();
+    const int n = n_todo;
+    for (int j = threadIdx.x; j < n; j += 256) {
+        const int i = todo[j], r = i / FT_SW, c = i % FT_SW;
+        sc[r][c] = (uint8_t)fast_corner_score(&px[r + 3][c + 3], FT_PW);
     }
     __syncthreads();
     const int tx = threadIdx.x & 31, lane = tx;
@@ -249,45 +290,57 @@ void launch_orb_fast(const OrbGeom &g, const OrbBuffers &b, int n_images, cudaSt
     orb_fast_kernel<<<dim3(g.fast_tiles, n_images), 256, 0, s>>>(g, b);
 }
 
+// 256 threads, one histogram bin each: the largest bin d whose suffix count sum_{j >= d} h[j] reaches `need`
+// (the bin that holds the need-th largest element); out[0] = d, out[1] = how many of bin d are still needed.
+// Requires sum(h) >= need >= 1.  Ends with a barrier.
+__device__ __forceinline__ void suffix_pick_256(int h, int need, int *warp_tot /*[8]*/, int *out /*[2]*/)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int v = h;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_down_sync(0xffffffffu, v, o);
+        if (lane + o < 32) v += u;
+    }
+    if (lane == 0) warp_tot[w] = v;
+    __syncthreads();
+    for (int k = w + 1; k < 8; ++k) v += warp_tot[k];
+    if (v >= need && v - h < need) { out[0] = threadIdx.x; out[1] = need - (v - h); }
+    __syncthreads();
+}
+
 // ------------------------------------------------------------------------------------------ O3 first cut + Harris
 // KeyPointsFilter::retainBest(keypoints, 2 * featuresNum) on the FAST score keeps everything >= the n-th largest
 // score (keypoint.cpp): with integer scores that threshold comes from the 256-bin histogram.
 __global__ void __launch_bounds__(256)
 orb_harris_kernel(const __grid_constant__ OrbGeom g, OrbBuffers b)
 {
-    __shared__ int s_hist[256];
-    __shared__ int s_thr;
+    __shared__ int s_wt[8], s_out[2];
     const int l = blockIdx.y, img = blockIdx.z;
     const OrbLevel &L = g.lv[l];
     const int n = b.cand_cnt[img * kOrbLevels + l];
-    if ((int)(blockIdx.x * 256) >= n) return;
-    s_hist[threadIdx.x] = b.hist[(img * kOrbLevels + l) * 256 + threadIdx.x];
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const int want = 2 * L.quota;
-        int thr = 0;
-        if (n > want) {
-            thr = 256;                       // want == 0: drop everything
-            int acc = 0;
-            for (int s = 255; s >= 0 && want > 0; --s) {
-                acc += s_hist[s];
-                if (acc >= want) { thr = s; break; }
-            }
+    if ((int)(blockIdx.x * 32) >= n) return;
+    const int want = 2 * L.quota;
+    int thr = 0;
+    if (n > want) {
+        thr = 256;                           // want == 0: drop everything
+        if (want > 0) {
+            suffix_pick_256(b.hist[(img * kOrbLevels + l) * 256 + threadIdx.x], want, s_wt, s_out);
+            thr = s_out[0];
         }
-        s_thr = thr;
     }
-    __syncthreads();
-    const int thr = s_thr;
     const uint8_t *im = b.pyr + (size_t)img * g.slab + L.off;
     const int p = L.pitch;
-    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
-        const size_t o = (size_t)img * g.cand_total + L.cand_off + i;
-        if (b.cand_val[o] < (float)thr) { b.cand_val[o] = -INFINITY; continue; }
-        const uint32_t xy = b.cand_xy[o];
-        const uint8_t *c0 = im + (size_t)((int)(xy >> 16) - 3) * p + (int)(xy & 0xffff) - 3;
+    // 8 lanes per candidate: lane r < 7 sums row r of the 7x7 block, then a 3-step shuffle reduction
+    const int sub = threadIdx.x & 7;
+    for (int i0 = blockIdx.x * 32; i0 < n; i0 += gridDim.x * 32) {     // uniform trip count: full-warp shuffles below
+        const int i = i0 + (threadIdx.x >> 3);
+        const size_t o = (size_t)img * g.cand_total + L.cand_off + min(i, n - 1);
+        const bool live = i < n && b.cand_val[o] >= (float)thr;
         int a = 0, bb = 0, c = 0;
-        for (int r = 0; r < 7; ++r) {
-            const uint8_t *q = c0 + r * p;
+        if (live && sub < 7) {
+            const uint32_t xy = b.cand_xy[o];
+            const uint8_t *q = im + (size_t)((int)(xy >> 16) - 3 + sub) * p + (int)(xy & 0xffff) - 3;
 #pragma unroll
             for (int k = 0; k < 7; ++k) {
                 const int ix = (q[k + 1] - q[k - 1]) * 2 + (q[k - p + 1] - q[k - p - 1]) + (q[k + p + 1] - q[k + p - 1]);
@@ -295,11 +348,23 @@ orb_harris_kernel(const __grid_constant__ OrbGeom g, OrbBuffers b)
                 a += ix * ix; bb += iy * iy; c += ix * iy;
             }
         }
-        // ((float)a * b - (float)c * c - harris_k * ((float)a + b) * ((float)a + b)) * scale^4, one rounding per operation
-        const float fa = (float)a, fb = (float)bb, fc = (float)c;
-        const float tr = __fadd_rn(fa, fb);
-        const float r = __fsub_rn(__fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc)), __fmul_rn(__fmul_rn(0.04f, tr), tr));
-        b.cand_val[o] = __fmul_rn(r, g.harris_scale4);
+#pragma unroll
+        for (int s = 4; s > 0; s >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, s);
+            bb += __shfl_xor_sync(0xffffffffu, bb, s);
+            c += __shfl_xor_sync(0xffffffffu, c, s);
+        }
+        if (sub == 0 && i < n) {
+            float r = -INFINITY;
+            if (live) {
+                // ((float)a * b - (float)c * c - harris_k * ((float)a + b) * ((float)a + b)) * scale^4, one rounding per operation
+                const float fa = (float)a, fb = (float)bb, fc = (float)c;
+                const float tr = __fadd_rn(fa, fb);
+                r = __fmul_rn(__fsub_rn(__fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc)), __fmul_rn(__fmul_rn(0.04f, tr), tr)),
+                              g.harris_scale4);
+            }
+            b.cand_val[o] = r;
+        }
     }
 }
 
@@ -307,7 +372,7 @@ void launch_orb_harris(const OrbGeom &g, const OrbBuffers &b, int n_images, cuda
 {
     int most = 1;
     for (int l = 0; l < kOrbLevels; ++l) most = std::max(most, g.lv[l].cand_cap);
-    const int gx = std::min((most + 255) / 256, n_images >= 32 ? 8 : 64);
+    const int gx = std::min((most + 31) / 32, n_images >= 32 ? 16 : 128);
     orb_harris_kernel<<<dim3(gx, kOrbLevels, n_images), 256, 0, s>>>(g, b);
 }
 
@@ -323,7 +388,7 @@ orb_select_kernel(const __grid_constant__ OrbGeom g, OrbBuffers b)
 {
     __shared__ unsigned long long keys[kOrbSortCap];
     __shared__ int s_hist[256];
-    __shared__ int s_a, s_b;
+    __shared__ int s_a, s_wt[8], s_out[2];
     const int l = blockIdx.x, img = blockIdx.y;
     const OrbLevel &L = g.lv[l];
     const int n = b.cand_cnt[img * kOrbLevels + l];
@@ -354,18 +419,10 @@ orb_select_kernel(const __grid_constant__ OrbGeom g, OrbBuffers b)
                 if (v != -INFINITY && (u & mask) == prefix) atomicAdd(&s_hist[(u >> (8 * pass)) & 255], 1);
             }
             __syncthreads();
-            if (threadIdx.x == 0) {
-                int acc = 0, digit = 0;
-                for (int d = 255; d >= 0; --d) {
-                    if (acc + s_hist[d] >= need) { digit = d; break; }
-                    acc += s_hist[d];
-                }
-                s_a = digit; s_b = need - acc;
-            }
-            __syncthreads();
-            prefix |= (uint32_t)s_a << (8 * pass);
+            suffix_pick_256(s_hist[threadIdx.x], need, s_wt, s_out);
+            prefix |= (uint32_t)s_out[0] << (8 * pass);
             mask |= 0xffu << (8 * pass);
-            need = s_b;
+            need = s_out[1];
             __syncthreads();
         }
         thr = prefix;
@@ -415,16 +472,41 @@ __constant__ float c_gauss[4] = {0x1.ba95c0p-3f, 0x1.869472p-3f, 0x1.0c70fcp-3f,
 
 __device__ __forceinline__ int reflect101(int i, int n)
 {
+    if (n >= 8) {                       // one reflection is enough for |overhang| <= n - 2; indices further out feed no output
+        if (i < 0) i = -i;
+        if (i >= n) i = 2 * n - 2 - i;
+        return min(max(i, 0), n - 1);
+    }
     if (n == 1) return 0;
     while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;
     return i;
 }
 
+__device__ __forceinline__ float gauss_row7(const float *p, float k0, float k1, float k2, float k3)
+{
+    float s = __fmul_rn(k3, p[0]);
+    s = fmaf(k2, p[1], s); s = fmaf(k1, p[2], s); s = fmaf(k0, p[3], s);
+    s = fmaf(k1, p[4], s); s = fmaf(k2, p[5], s); s = fmaf(k3, p[6], s);
+    return s;
+}
+
+__device__ __forceinline__ uint32_t gauss_col7(float c, float a1, float b1, float a2, float b2, float a3, float b3,
+                                               float k0, float k1, float k2, float k3)
+{
+    float s = __fmul_rn(k0, c);
+    s = fmaf(k1, __fadd_rn(a1, b1), s);
+    s = fmaf(k2, __fadd_rn(a2, b2), s);
+    s = fmaf(k3, __fadd_rn(a3, b3), s);
+    return (uint32_t)min(max(__float2int_rn(s), 0), 255);
+}
+
+// 32x32 output tile: 38 x 40 input bytes as 10 aligned words per row, row pass 4 outputs per thread (float4 to shared
+// memory), column pass 4 adjacent columns per thread (7 LDS.128, one 32-bit store).
 __global__ void __launch_bounds__(256)
 orb_blur_kernel(const __grid_constant__ OrbGeom g, OrbBuffers b)
 {
-    __shared__ uint8_t in[38][40];
-    __shared__ float row[38][32];
+    __shared__ uint32_t in[38][10];
+    __shared__ __align__(16) float row[38][32];
     int l = 0;
     while (l + 1 < kOrbLevels && (int)blockIdx.x >= g.lv[l + 1].blur_tile_off) ++l;
     const OrbLevel &L = g.lv[l];
@@ -433,34 +515,47 @@ orb_blur_kernel(const __grid_constant__ OrbGeom g, OrbBuffers b)
     const int t = blockIdx.x - L.blur_tile_off;
     const int x0 = (t % tiles_x) * 32, y0 = (t / tiles_x) * 32;
     const uint8_t *src = b.pyr + (size_t)img * g.slab + L.off;
-    for (int i = threadIdx.x; i < 38 * 38; i += 256) {
-        const int r = i / 38, c = i % 38;
-        in[r][c] = src[(size_t)reflect101(y0 - 3 + r, L.h) * L.pitch + reflect101(x0 - 3 + c, L.w)];
+    const bool interior = x0 >= 4 && x0 + 36 <= L.w && y0 >= 3 && y0 + 35 <= L.h;
+    for (int i = threadIdx.x; i < 380; i += 256) {
+        const int r = i / 10, wd = i % 10;
+        uint32_t v = 0;
+        if (interior) {
+            v = *reinterpret_cast<const uint32_t *>(src + (size_t)(y0 - 3 + r) * L.pitch + x0 - 4 + 4 * wd);
+        } else {
+            const uint8_t *rp = src + (size_t)reflect101(y0 - 3 + r, L.h) * L.pitch;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v |= (uint32_t)rp[reflect101(x0 - 4 + 4 * wd + k, L.w)] << (8 * k);
+        }
+        in[r][wd] = v;
     }
     __syncthreads();
     const float k0 = c_gauss[0], k1 = c_gauss[1], k2 = c_gauss[2], k3 = c_gauss[3];
-    for (int i = threadIdx.x; i < 38 * 32; i += 256) {
-        const int r = i >> 5, c = i & 31;
-        float s = __fmul_rn(k3, (float)in[r][c]);
-        s = fmaf(k2, (float)in[r][c + 1], s);
-        s = fmaf(k1, (float)in[r][c + 2], s);
-        s = fmaf(k0, (float)in[r][c + 3], s);
-        s = fmaf(k1, (float)in[r][c + 4], s);
-        s = fmaf(k2, (float)in[r][c + 5], s);
-        s = fmaf(k3, (float)in[r][c + 6], s);
-        row[r][c] = s;
+    for (int i = threadIdx.x; i < 38 * 8; i += 256) {
+        const int r = i >> 3, gq = i & 7;
+        const uint32_t w0 = in[r][gq], w1 = in[r][gq + 1], w2 = in[r][gq + 2];
+        float p[10];                    // tile columns 4gq+1 .. 4gq+10 = outputs 4gq..4gq+3 with their +-3 neighbours
+        p[0] = (float)((w0 >> 8) & 255); p[1] = (float)((w0 >> 16) & 255); p[2] = (float)(w0 >> 24);
+        p[3] = (float)(w1 & 255); p[4] = (float)((w1 >> 8) & 255); p[5] = (float)((w1 >> 16) & 255); p[6] = (float)(w1 >> 24);
+        p[7] = (float)(w2 & 255); p[8] = (float)((w2 >> 8) & 255); p[9] = (float)((w2 >> 16) & 255);
+        float4 o;
+        o.x = gauss_row7(p, k0, k1, k2, k3); o.y = gauss_row7(p + 1, k0, k1, k2, k3);
+        o.z = gauss_row7(p + 2, k0, k1, k2, k3); o.w = gauss_row7(p + 3, k0, k1, k2, k3);
+        *reinterpret_cast<float4 *>(&row[r][4 * gq]) = o;
     }
     __syncthreads();
-    uint8_t *dst = b.blur + (size_t)img * g.slab + L.off;
-    for (int i = threadIdx.x; i < 32 * 32; i += 256) {
-        const int r = i >> 5, c = i & 31;
-        const int x = x0 + c, y = y0 + r;
-        if (x >= L.w || y >= L.h) continue;
-        float s = __fmul_rn(k0, row[r + 3][c]);
-        s = fmaf(k1, __fadd_rn(row[r + 4][c], row[r + 2][c]), s);
-        s = fmaf(k2, __fadd_rn(row[r + 5][c], row[r + 1][c]), s);
-        s = fmaf(k3, __fadd_rn(row[r + 6][c], row[r][c]), s);
-        dst[(size_t)y * L.pitch + x] = (uint8_t)min(max(__float2int_rn(s), 0), 255);
+    const int r = threadIdx.x >> 3, gq = threadIdx.x & 7;
+    const int x = x0 + 4 * gq, y = y0 + r;
+    if (x < L.w && y < L.h) {
+        const float4 c = *reinterpret_cast<const float4 *>(&row[r + 3][4 * gq]);
+        const float4 a1 = *reinterpret_cast<const float4 *>(&row[r + 4][4 * gq]), b1 = *reinterpret_cast<const float4 *>(&row[r + 2][4 * gq]);
+        const float4 a2 = *reinterpret_cast<const float4 *>(&row[r + 5][4 * gq]), b2 = *reinterpret_cast<const float4 *>(&row[r + 1][4 * gq]);
+        const float4 a3 = *reinterpret_cast<const float4 *>(&row[r + 6][4 * gq]), b3 = *reinterpret_cast<const float4 *>(&row[r][4 * gq]);
+        const uint32_t v = gauss_col7(c.x, a1.x, b1.x, a2.x, b2.x, a3.x, b3.x, k0, k1, k2, k3) |
+                           gauss_col7(c.y, a1.y, b1.y, a2.y, b2.y, a3.y, b3.y, k0, k1, k2, k3) << 8 |
+                           gauss_col7(c.z, a1.z, b1.z, a2.z, b2.z, a3.z, b3.z, k0, k1, k2, k3) << 16 |
+                           gauss_col7(c.w, a1.w, b1.w, a2.w, b2.w, a3.w, b3.w, k0, k1, k2, k3) << 24;
+        // the row padding (pitch is a multiple of 16) absorbs the bytes beyond the image width
+        *reinterpret_cast<uint32_t *>(b.blur + (size_t)img * g.slab + L.off + (size_t)y * L.pitch + x) = v;
     }
 }
 

@@ -108,12 +108,48 @@ static bool image_pair_and_matcher()
     return true;
 }
 
+// VisualFeature::extract (visual-feature.hpp:14) on two renderings of the same rectangles shifted by 6 pixels:
+// the extracted features match each other under that shift, like utility/test-visual-feature.cpp:25-35 shows by eye.
+static bool extract_and_match()
+{
+    const int W = 320, H = 240, shift = 6;
+    std::mt19937 rng(11);
+    struct Box { int x, y, w, h, v; };
+    std::vector<Box> boxes(60);
+    for (auto &b : boxes) b = {(int)(rng() % W), (int)(rng() % H), 8 + (int)(rng() % 50), 8 + (int)(rng() % 40), (int)(rng() % 256)};
+    auto render = [&](int dx) {
+        std::vector<uint8_t> im((size_t)W * H, 90);
+        for (const auto &b : boxes)
+            for (int y = std::max(b.y, 0); y < std::min(b.y + b.h, H); ++y)
+                for (int x = std::max(b.x + dx, 0); x < std::min(b.x + dx + b.w, W); ++x) im[(size_t)y * W + x] = (uint8_t)b.v;
+        return im;
+    };
+    const std::vector<uint8_t> a = render(0), b = render(shift);
+    VisualFeature f1 = VisualFeature::extract(ImageGrayscale(H, W, a.data()));
+    VisualFeature f2 = VisualFeature::extract(ImageGrayscale(H, W, b.data()));
+    ASSERT_TRUE(f1.valid() && f2.valid());
+    ASSERT_TRUE(f1.size() > 100 && f1.size() <= 500 + 64);
+    auto batch = VisualFeature::extract_batch({ImageGrayscale(H, W, a.data()), ImageGrayscale(H, W, b.data())});
+    ASSERT_TRUE(batch.size() == 2 && batch[0].get_descriptors() == f1.get_descriptors() && batch[1].get_descriptors() == f2.get_descriptors());
+    for (size_t i = 1; i < f1.size(); ++i) ASSERT_TRUE(f1.get_keypoints()[i - 1].octave <= f1.get_keypoints()[i].octave);
+    auto matches = VisualFeature::match_visual_features(f1, f2, 30);
+    ASSERT_TRUE(matches.size() > 50);
+    size_t consistent = 0;
+    for (const auto &m : matches) {
+        const auto &p1 = f1.get_keypoints()[m.trainIdx].pt; const auto &p2 = f2.get_keypoints()[m.queryIdx].pt;
+        consistent += std::fabs(p2.x - p1.x - shift) < 2.5f && std::fabs(p2.y - p1.y) < 2.5f;
+    }
+    ASSERT_TRUE(consistent * 10 >= matches.size() * 9);
+    return true;
+}
+
 int main()
 {
     int fails = 0;
     struct { const char *name; bool (*fn)(); } tests[] = {{"sfm_triangulate_cube", sfm_triangulate_cube},
                                                            {"sfm_solve_L_shape", sfm_solve_L_shape},
-                                                           {"image_pair_and_matcher", image_pair_and_matcher}};
+                                                           {"image_pair_and_matcher", image_pair_and_matcher},
+                                                           {"extract_and_match", extract_and_match}};
     for (auto &t : tests) {
         bool ok = false;
         try { ok = t.fn(); } catch (const std::exception &e) { std::printf("exception: %s\n", e.what()); }
