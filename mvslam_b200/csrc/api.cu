@@ -971,6 +971,7 @@ static int orb_extract_impl(mvs_ctx *ctx, const uint8_t *const *h_images, const 
         CK(cudaStreamSynchronize(ctx->stream));
         int32_t *off = ctx->o_pinned + (size_t)chunk * kOrbLevels;
         size_t chunk_total = 0;
+        int32_t most = 0;
         for (int i = 0; i < n; ++i) {
             int32_t c = 0;
             for (int l = 0; l < kOrbLevels; ++l) {
@@ -979,6 +980,7 @@ static int orb_extract_impl(mvs_ctx *ctx, const uint8_t *const *h_images, const 
                 c += k;
             }
             img_count[c0 + i] = c;
+            most = std::max(most, c);
             off[i] = (int32_t)(total + chunk_total);
             chunk_total += (size_t)c;
         }
@@ -999,7 +1001,7 @@ static int orb_extract_impl(mvs_ctx *ctx, const uint8_t *const *h_images, const 
         CK(cudaMemcpyAsync(ctx->o_off.p, off, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
         {
             StageTimer t(ctx, MVS_STAGE_ORB_DESCRIBE);
-            launch_orb_describe(g, b, d, n, n >= 64 ? 4 : (n >= 8 ? 16 : 64), ctx->stream);
+            launch_orb_describe(g, b, d, n, most, ctx->stream);
         }
         CK(cudaStreamSynchronize(ctx->stream));   // the pinned offsets are rewritten by the next chunk
         total += chunk_total;

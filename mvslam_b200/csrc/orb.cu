@@ -588,6 +588,11 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x)
 
 __constant__ int8_t c_pattern[1024];
 
+// A warp takes G keypoints per pass: moments and descriptor bits are computed by the whole warp for one keypoint at a
+// time, while the scalar part in between (fastAtan2, double-precision cos/sin, the keypoint record) runs once with
+// lane j working on keypoint j.  G = 32 amortises the trigonometry best; small G keeps more warps busy when a call
+// holds few keypoints (single-frame latency).
+template <int G>
 __global__ void __launch_bounds__(256)
 orb_describe_kernel(const __grid_constant__ OrbGeom g, OrbBuffers b, OrbDescribeArgs d)
 {
@@ -607,64 +612,89 @@ orb_describe_kernel(const __grid_constant__ OrbGeom g, OrbBuffers b, OrbDescribe
     const int lane = threadIdx.x & 31;
     const int warps = gridDim.x * 8;
     const size_t out0 = (size_t)d.img_off[img];
-    for (int k = blockIdx.x * 8 + (threadIdx.x >> 5); k < total; k += warps) {
-        int l = 0;
-        while (k >= s_start[l + 1]) ++l;
-        const OrbLevel &L = g.lv[l];
-        const uint32_t ci = b.kept_idx[(size_t)(img * kOrbLevels + l) * kOrbSortCap + (k - s_start[l])];
-        const size_t o = (size_t)img * g.cand_total + L.cand_off + ci;
-        const uint32_t xy = b.cand_xy[o];
-        const int cx = xy & 0xffff, cy = xy >> 16;
+    const uint8_t *pyr = b.pyr + (size_t)img * g.slab, *blur = b.blur + (size_t)img * g.slab;
+    for (int base = (blockIdx.x * 8 + (threadIdx.x >> 5)) * G; base < total; base += warps * G) {
+        // lane j < G owns keypoint base + j
+        const int k = base + lane;
+        const bool own = lane < G && k < total;
+        int l = 0, cx = 0, cy = 0;
+        float resp = 0.f;
+        if (own) {
+            while (k >= s_start[l + 1]) ++l;
+            const uint32_t ci = b.kept_idx[(size_t)(img * kOrbLevels + l) * kOrbSortCap + (k - s_start[l])];
+            const size_t o = (size_t)img * g.cand_total + g.lv[l].cand_off + ci;
+            const uint32_t xy = b.cand_xy[o];
+            cx = xy & 0xffff; cy = xy >> 16;
+            resp = b.cand_val[o];
+        }
+        const int n_here = min(G, total - base);
         // ICAngles: moments over the circular patch of the un-blurred level; lane = u + 15
-        const uint8_t *im = b.pyr + (size_t)img * g.slab + L.off + (size_t)cy * L.pitch + cx;
         const int u = lane - kOrbHalfPatch;
-        int m10 = 0, m01 = 0;
-        if (lane < 31) {
-            for (int v = -kOrbHalfPatch; v <= kOrbHalfPatch; ++v) {
-                if (abs(u) <= g.umax[abs(v)]) {
-                    const int p = im[v * L.pitch + u];
-                    m10 += u * p; m01 += v * p;
+        int m10_own = 0, m01_own = 0;
+        for (int j = 0; j < n_here; ++j) {
+            const int jl = __shfl_sync(0xffffffffu, l, j), jx = __shfl_sync(0xffffffffu, cx, j), jy = __shfl_sync(0xffffffffu, cy, j);
+            const int pitch = g.lv[jl].pitch;
+            const uint8_t *im = pyr + g.lv[jl].off + (size_t)jy * pitch + jx;
+            int m10 = 0, m01 = 0;
+            if (lane < 31) {
+                for (int v = -kOrbHalfPatch; v <= kOrbHalfPatch; ++v) {
+                    if (abs(u) <= g.umax[abs(v)]) {
+                        const int p = im[v * pitch + u];
+                        m10 += u * p; m01 += v * p;
+                    }
                 }
             }
-        }
 #pragma unroll
-        for (int s = 16; s > 0; s >>= 1) {
-            m10 += __shfl_xor_sync(0xffffffffu, m10, s);
-            m01 += __shfl_xor_sync(0xffffffffu, m01, s);
+            for (int s = 16; s > 0; s >>= 1) {
+                m10 += __shfl_xor_sync(0xffffffffu, m10, s);
+                m01 += __shfl_xor_sync(0xffffffffu, m01, s);
+            }
+            if (lane == j) { m10_own = m10; m01_own = m01; }
         }
-        const float angle = fast_atan2_deg((float)m01, (float)m10);
-        // computeOrbDescriptors: angle in radians (float), cos/sin evaluated in double and rounded to float
-        const float rad = __fmul_rn(angle, (float)(3.14159265358979323846 / 180.f));
-        const float ca = (float)cos((double)rad), sa = (float)sin((double)rad);
-        const uint8_t *bl = b.blur + (size_t)img * g.slab + L.off + (size_t)cy * L.pitch + cx;
-        int byte = 0;
-#pragma unroll
-        for (int bit = 0; bit < 8; ++bit) {
-            const char2 q0 = s_pat[2 * bit][lane], q1 = s_pat[2 * bit + 1][lane];
-            const int x0 = __float2int_rn(__fsub_rn(__fmul_rn((float)q0.x, ca), __fmul_rn((float)q0.y, sa)));
-            const int y0 = __float2int_rn(__fadd_rn(__fmul_rn((float)q0.x, sa), __fmul_rn((float)q0.y, ca)));
-            const int x1 = __float2int_rn(__fsub_rn(__fmul_rn((float)q1.x, ca), __fmul_rn((float)q1.y, sa)));
-            const int y1 = __float2int_rn(__fadd_rn(__fmul_rn((float)q1.x, sa), __fmul_rn((float)q1.y, ca)));
-            byte |= (int)(bl[y0 * L.pitch + x0] < bl[y1 * L.pitch + x1]) << bit;
-        }
-        d.desc[(out0 + k) * 32 + lane] = (uint8_t)byte;
-        if (lane == 0) {
-            const float px = __fmul_rn((float)cx, L.scale), py = __fmul_rn((float)cy, L.scale);
+        // per-keypoint scalars, one keypoint per lane
+        float angle = 0.f, ca = 1.f, sa = 0.f;
+        if (own) {
+            angle = fast_atan2_deg((float)m01_own, (float)m10_own);
+            // computeOrbDescriptors: angle in radians (float), cos/sin evaluated in double and rounded to float
+            const float rad = __fmul_rn(angle, (float)(3.14159265358979323846 / 180.f));
+            double sd, cd;
+            sincos((double)rad, &sd, &cd);
+            ca = (float)cd; sa = (float)sd;
+            const float scale = g.lv[l].scale;
+            const float px = __fmul_rn((float)cx, scale), py = __fmul_rn((float)cy, scale);
             if (d.kp) {
                 mvs_keypoint kp;
                 kp.x = px; kp.y = py;
-                kp.size = __fmul_rn(31.f, L.scale);
+                kp.size = __fmul_rn(31.f, scale);
                 kp.angle = angle;
-                kp.response = b.cand_val[o];
+                kp.response = resp;
                 kp.octave = l;
                 d.kp[out0 + k] = kp;
             }
             if (d.frame_kp) d.frame_kp[out0 + k] = make_float2(px, py);
         }
+        // steered BRIEF: lane = descriptor byte
+        for (int j = 0; j < n_here; ++j) {
+            const int jl = __shfl_sync(0xffffffffu, l, j), jx = __shfl_sync(0xffffffffu, cx, j), jy = __shfl_sync(0xffffffffu, cy, j);
+            const float jc = __shfl_sync(0xffffffffu, ca, j), js = __shfl_sync(0xffffffffu, sa, j);
+            const int pitch = g.lv[jl].pitch;
+            const uint8_t *bl = blur + g.lv[jl].off + (size_t)jy * pitch + jx;
+            int byte = 0;
+#pragma unroll
+            for (int bit = 0; bit < 8; ++bit) {
+                const char2 q0 = s_pat[2 * bit][lane], q1 = s_pat[2 * bit + 1][lane];
+                const int x0 = __float2int_rn(__fsub_rn(__fmul_rn((float)q0.x, jc), __fmul_rn((float)q0.y, js)));
+                const int y0 = __float2int_rn(__fadd_rn(__fmul_rn((float)q0.x, js), __fmul_rn((float)q0.y, jc)));
+                const int x1 = __float2int_rn(__fsub_rn(__fmul_rn((float)q1.x, jc), __fmul_rn((float)q1.y, js)));
+                const int y1 = __float2int_rn(__fadd_rn(__fmul_rn((float)q1.x, js), __fmul_rn((float)q1.y, jc)));
+                byte |= (int)(bl[y0 * pitch + x0] < bl[y1 * pitch + x1]) << bit;
+            }
+            d.desc[(out0 + base + j) * 32 + lane] = (uint8_t)byte;
+        }
     }
 }
 
-void launch_orb_describe(const OrbGeom &g, const OrbBuffers &b, const OrbDescribeArgs &d, int n_images, int ctas_per_image,
+void launch_orb_describe(const OrbGeom &g, const OrbBuffers &b, const OrbDescribeArgs &d, int n_images, int max_keypoints,
                          cudaStream_t s)
 {
     static bool pattern_loaded[64] = {};
@@ -674,7 +704,12 @@ void launch_orb_describe(const OrbGeom &g, const OrbBuffers &b, const OrbDescrib
         cudaMemcpyToSymbol(c_pattern, MVS_ORB_PATTERN, sizeof(MVS_ORB_PATTERN));
         if (dev < 64) pattern_loaded[dev] = true;
     }
-    orb_describe_kernel<<<dim3(ctas_per_image, n_images), 256, 0, s>>>(g, b, d);
+    // enough warps to fill the GPU (148 SMs x 8 resident CTAs) before the group size grows
+    const int kp = std::max(max_keypoints, 1);
+    auto ctas = [&](int G) { return (kp + 8 * G - 1) / (8 * G); };
+    if ((long)ctas(32) * n_images >= 1184) orb_describe_kernel<32><<<dim3(ctas(32), n_images), 256, 0, s>>>(g, b, d);
+    else if ((long)ctas(8) * n_images >= 592) orb_describe_kernel<8><<<dim3(ctas(8), n_images), 256, 0, s>>>(g, b, d);
+    else orb_describe_kernel<2><<<dim3(ctas(2), n_images), 256, 0, s>>>(g, b, d);
 }
 
 }  // namespace mvs

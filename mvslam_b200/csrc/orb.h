@@ -64,7 +64,7 @@ void launch_orb_fast(const OrbGeom &g, const OrbBuffers &b, int n_images, cudaSt
 void launch_orb_harris(const OrbGeom &g, const OrbBuffers &b, int n_images, cudaStream_t s);
 void launch_orb_select(const OrbGeom &g, const OrbBuffers &b, int n_images, cudaStream_t s);
 void launch_orb_blur(const OrbGeom &g, const OrbBuffers &b, int n_images, cudaStream_t s);
-void launch_orb_describe(const OrbGeom &g, const OrbBuffers &b, const OrbDescribeArgs &d, int n_images, int ctas_per_image,
+void launch_orb_describe(const OrbGeom &g, const OrbBuffers &b, const OrbDescribeArgs &d, int n_images, int max_keypoints,
                          cudaStream_t s);
 
 }  // namespace mvs
