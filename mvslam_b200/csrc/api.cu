@@ -959,9 +959,8 @@ static int orb_extract_impl(mvs_ctx *ctx, const uint8_t *const *h_images, const 
         }
         CK(cudaMemsetAsync(b.cand_cnt, 0, (size_t)chunk * kOrbLevels * 257 * sizeof(int32_t), ctx->stream));
         {
-            StageTimer t(ctx, MVS_STAGE_ORB_PYRAMID, kOrbLevels);
-            launch_orb_import(g, b, stage, stride, n, ctx->stream);
-            for (int l = 1; l < kOrbLevels; ++l) launch_orb_resize(g, b, l, n, ctx->stream);
+            StageTimer t(ctx, MVS_STAGE_ORB_PYRAMID);
+            launch_orb_pyramid(g, b, stage, stride, n, ctx->stream);
         }
         { StageTimer t(ctx, MVS_STAGE_ORB_FAST, g.fast_tiles ? 1 : 0); launch_orb_fast(g, b, n, ctx->stream); }
         { StageTimer t(ctx, MVS_STAGE_ORB_HARRIS); launch_orb_harris(g, b, n, ctx->stream); }

@@ -8,7 +8,7 @@
 // Everything is integer or explicitly-rounded FP32 arithmetic: this file is compiled with -fmad=false and uses
 // fmaf() exactly where OpenCV's FMA-contracted separable filter does.
 //
-//   O1 orb_resize_kernel    level l from level l-1 (7 launches; 8.8 fixed point, round at 16 fractional bits)
+//   O1 orb_pyramid_kernel   one thread-block cluster per image: level 0 copy + 7 chained fixed-point resizes
 //   O2 orb_fast_kernel      FAST score + 3x3 NMS per 32x16 tile -> candidate list + score histogram
 //   O3 orb_harris_kernel    first retainBest (2 x quota by FAST score, histogram threshold) + Harris response
 //   O4 orb_select_kernel    second retainBest (quota by Harris response, radix select), raster-order sort
@@ -43,7 +43,7 @@ bool orb_make_geometry(int w, int h, int nfeatures, OrbGeom &g, std::vector<int3
         if (L.w < 1 || L.h < 1) return false;
         L.pitch = (L.w + 15) & ~15;
         L.off = off;
-        off += L.pitch * L.h;
+        off += (L.pitch * L.h + 127) & ~127;      // levels start on their own 128-byte line
         if (l < kOrbLevels - 1) {
             L.quota = cv_round_f(nd);
             sum += L.quota;
@@ -59,24 +59,24 @@ bool orb_make_geometry(int w, int h, int nfeatures, OrbGeom &g, std::vector<int3
         if (rw > 0 && rh > 0) ftiles += ((rw + 31) / 32) * ((rh + 15) / 16);
         L.blur_tile_off = btiles;
         btiles += ((L.w + 31) / 32) * ((L.h + 31) / 32);
-        // resize tables (imgproc resize.cpp, INTER_LINEAR_EXACT 8-bit: interpolationLinear<ufixedpoint16>)
+        // resize tables (imgproc resize.cpp, INTER_LINEAR_EXACT 8-bit: interpolationLinear<ufixedpoint16>), one packed
+        // int per destination index: source offset | 8.8 weight of the next source pixel << 16; x table padded to 4
         L.tab_off = (int)tabs.size();
         if (l > 0) {
             const OrbLevel &P = g.lv[l - 1];
             for (int axis = 0; axis < 2; ++axis) {
                 const int src = axis ? P.h : P.w, dst = axis ? L.h : L.w;
                 const double inv_scale = (double)dst / (double)src, sc = 1.0 / inv_scale;
-                std::vector<int32_t> ofs(dst), al(dst);
                 for (int d = 0; d < dst; ++d) {
                     double f = (d + 0.5) * sc - 0.5;
-                    int s0 = (int)std::floor(f);
+                    int s0 = (int)std::floor(f), al = 0;
                     f -= s0;
-                    if (s0 < 0) { ofs[d] = 0; al[d] = 0; }
-                    else if (s0 >= src - 1) { ofs[d] = src - 1; al[d] = 0; }
-                    else { ofs[d] = s0; al[d] = (int)std::nearbyint(f * 256.0); }
+                    if (s0 < 0) s0 = 0;
+                    else if (s0 >= src - 1) s0 = src - 1;
+                    else al = (int)std::nearbyint(f * 256.0);
+                    tabs.push_back(s0 | (al << 16));
                 }
-                tabs.insert(tabs.end(), ofs.begin(), ofs.end());
-                tabs.insert(tabs.end(), al.begin(), al.end());
+                while (tabs.size() & 3) tabs.push_back(0);
             }
         }
     }
@@ -101,56 +101,73 @@ bool orb_make_geometry(int w, int h, int nfeatures, OrbGeom &g, std::vector<int3
     return true;
 }
 
-// ------------------------------------------------------------------------------------------ O0 import
-// level 0 of every pyramid slab from a dense [images][h][stride] staging buffer
-__global__ void __launch_bounds__(256)
-orb_import_kernel(const __grid_constant__ OrbGeom g, OrbBuffers b, const uint8_t *stage, int stride)
+// ------------------------------------------------------------------------------------------ O1 pyramid
+// One thread-block cluster (8 CTAs x 512 threads) per image builds the whole pyramid: level 0 is copied from the
+// staging buffer, level l is resized from level l-1 (cv::resize INTER_LINEAR_EXACT, 8-bit: horizontal pass in 8.8 fixed
+// point, vertical pass rounded at 16 fractional bits), with a cluster barrier (release/acquire) between levels instead
+// of a kernel boundary (the acquire side makes the other SMs' global writes visible to ordinary loads; every level starts
+// on its own 128-byte line).  A thread produces 4 adjacent pixels (one packed x-table int4 load, one 32-bit store).
+constexpr int kPyrCluster = 8, kPyrThreads = 512;
+
+__device__ __forceinline__ void cluster_sync_all()
 {
-    const OrbLevel &L = g.lv[0];
-    const int x = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4;
-    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (x >= L.w || y >= L.h) return;
-    const uint8_t *src = stage + ((size_t)blockIdx.z * L.h + y) * stride + x;
-    uint8_t *dst = b.pyr + (size_t)blockIdx.z * g.slab + L.off + (size_t)y * L.pitch + x;
-    if (x + 4 <= L.w && (stride & 3) == 0 && ((uintptr_t)stage & 3) == 0) {
-        *reinterpret_cast<uint32_t *>(dst) = *reinterpret_cast<const uint32_t *>(src);
-    } else {
-        for (int k = 0; k < 4 && x + k < L.w; ++k) dst[k] = src[k];
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __cluster_dims__(kPyrCluster, 1, 1) __launch_bounds__(kPyrThreads)
+orb_pyramid_kernel(const __grid_constant__ OrbGeom g, OrbBuffers b, const uint8_t *stage, int stride)
+{
+    const int img = blockIdx.x / kPyrCluster;
+    const int tid = (blockIdx.x % kPyrCluster) * kPyrThreads + threadIdx.x, nthr = kPyrCluster * kPyrThreads;
+    uint8_t *slab = b.pyr + (size_t)img * g.slab;
+    const uint8_t *img0 = stage + (size_t)img * g.lv[0].h * stride;
+    {   // level 0
+        const OrbLevel &L = g.lv[0];
+        const int wq = (L.w + 3) >> 2;
+        const bool words = (stride & 3) == 0 && ((uintptr_t)stage & 3) == 0;
+        for (int i = tid; i < wq * L.h; i += nthr) {
+            const int y = i / wq, x = (i - y * wq) * 4;
+            const uint8_t *sp = img0 + (size_t)y * stride + x;
+            uint32_t v = 0;
+            if (words && x + 4 <= L.w) v = *reinterpret_cast<const uint32_t *>(sp);
+            else for (int k = 0; k < 4 && x + k < L.w; ++k) v |= (uint32_t)sp[k] << (8 * k);
+            *reinterpret_cast<uint32_t *>(slab + L.off + (size_t)y * L.pitch + x) = v;
+        }
+    }
+    for (int l = 1; l < kOrbLevels; ++l) {
+        const OrbLevel &D = g.lv[l];
+        const OrbLevel &S = g.lv[l - 1];
+        const uint8_t *src = l == 1 ? img0 : slab + S.off;      // level 1 reads the input itself: no wait for the copy
+        const int sp = l == 1 ? stride : S.pitch;
+        const int wq = (D.w + 3) >> 2;
+        const int4 *tx = reinterpret_cast<const int4 *>(b.tabs + D.tab_off);
+        const int32_t *ty = b.tabs + D.tab_off + wq * 4;
+        uint8_t *dst = slab + D.off;
+        for (int i = tid; i < wq * D.h; i += nthr) {
+            const int y = i / wq, xq = i - y * wq;
+            const int4 t4 = tx[xq];
+            const int tyv = ty[y];
+            const int y0 = tyv & 0xffff, ay = tyv >> 16, y1 = min(y0 + 1, S.h - 1);
+            const uint8_t *r0 = src + (size_t)y0 * sp, *r1 = src + (size_t)y1 * sp;
+            const int te[4] = {t4.x, t4.y, t4.z, t4.w};
+            uint32_t out = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int x0 = te[k] & 0xffff, ax = te[k] >> 16, x1 = min(x0 + 1, S.w - 1);
+                const uint32_t h0 = r0[x0] * (256 - ax) + r0[x1] * ax;     // 8.8 fixed point
+                const uint32_t h1 = r1[x0] * (256 - ax) + r1[x1] * ax;
+                const uint32_t v = h0 * (256 - ay) + h1 * ay;                                // 16.16
+                out |= ((v + (1u << 15)) >> 16) << (8 * k);
+            }
+            *reinterpret_cast<uint32_t *>(dst + (size_t)y * D.pitch + 4 * xq) = out;   // row padding absorbs x >= w
+        }
+        if (l + 1 < kOrbLevels) cluster_sync_all();
     }
 }
 
-void launch_orb_import(const OrbGeom &g, const OrbBuffers &b, const uint8_t *stage, int stride, int n_images, cudaStream_t s)
+void launch_orb_pyramid(const OrbGeom &g, const OrbBuffers &b, const uint8_t *stage, int stride, int n_images, cudaStream_t s)
 {
-    const OrbLevel &L = g.lv[0];
-    dim3 grid((L.w + 255) / 256, (L.h + 3) / 4, n_images);
-    orb_import_kernel<<<grid, 256, 0, s>>>(g, b, stage, stride);
-}
-
-// ------------------------------------------------------------------------------------------ O1 resize
-__global__ void __launch_bounds__(256)
-orb_resize_kernel(const __grid_constant__ OrbGeom g, OrbBuffers b, int level)
-{
-    const OrbLevel &D = g.lv[level];
-    const OrbLevel &S = g.lv[level - 1];
-    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (x >= D.w || y >= D.h) return;
-    const int32_t *tx = b.tabs + D.tab_off, *ty = tx + 2 * D.w;
-    const int x0 = tx[x], ax = tx[D.w + x], y0 = ty[y], ay = ty[D.h + y];
-    const int x1 = min(x0 + 1, S.w - 1), y1 = min(y0 + 1, S.h - 1);
-    const uint8_t *src = b.pyr + (size_t)blockIdx.z * g.slab + S.off;
-    const uint8_t *r0 = src + (size_t)y0 * S.pitch, *r1 = src + (size_t)y1 * S.pitch;
-    const uint32_t h0 = r0[x0] * (256 - ax) + r0[x1] * ax;     // 8.8 fixed point
-    const uint32_t h1 = r1[x0] * (256 - ax) + r1[x1] * ax;
-    const uint32_t v = h0 * (256 - ay) + h1 * ay;              // 16.16
-    b.pyr[(size_t)blockIdx.z * g.slab + D.off + (size_t)y * D.pitch + x] = (uint8_t)((v + (1u << 15)) >> 16);
-}
-
-void launch_orb_resize(const OrbGeom &g, const OrbBuffers &b, int level, int n_images, cudaStream_t s)
-{
-    const OrbLevel &D = g.lv[level];
-    dim3 grid((D.w + 63) / 64, (D.h + 3) / 4, n_images);
-    orb_resize_kernel<<<grid, 256, 0, s>>>(g, b, level);
+    orb_pyramid_kernel<<<n_images * kPyrCluster, kPyrThreads, 0, s>>>(g, b, stage, stride);
 }
 
 // ------------------------------------------------------------------------------------------ O2 FAST + NMS

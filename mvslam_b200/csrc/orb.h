@@ -23,7 +23,7 @@ struct OrbLevel {
     int cand_off, cand_cap;  // slice of the per-image candidate list (every 3x3 maximum fits)
     int tile_off;          // first FAST tile / first blur tile of this level in the flattened tile index
     int blur_tile_off;
-    int tab_off;           // resize tables of this level: xofs[w], xalpha[w], yofs[h], yalpha[h] (int32)
+    int tab_off;           // resize tables of this level (int32, packed offset | weight << 16): x[w padded to 4], y[h]
     float scale;           // layerScale
 };
 
@@ -58,8 +58,7 @@ struct OrbDescribeArgs {
 // Host side: geometry of the pyramid for a w x h image and nfeatures; fills tabs_host (resize tables).
 bool orb_make_geometry(int w, int h, int nfeatures, OrbGeom &g, std::vector<int32_t> &tabs_host);
 
-void launch_orb_import(const OrbGeom &g, const OrbBuffers &b, const uint8_t *stage, int stride, int n_images, cudaStream_t s);
-void launch_orb_resize(const OrbGeom &g, const OrbBuffers &b, int level, int n_images, cudaStream_t s);
+void launch_orb_pyramid(const OrbGeom &g, const OrbBuffers &b, const uint8_t *stage, int stride, int n_images, cudaStream_t s);
 void launch_orb_fast(const OrbGeom &g, const OrbBuffers &b, int n_images, cudaStream_t s);
 void launch_orb_harris(const OrbGeom &g, const OrbBuffers &b, int n_images, cudaStream_t s);
 void launch_orb_select(const OrbGeom &g, const OrbBuffers &b, int n_images, cudaStream_t s);
