@@ -9,6 +9,9 @@ python bench.py --workload s8k --steps 5 --warmup 3 > gpurun_out/bench_s8k_$R.js
 python bench.py --workload w512 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_w512_$R.json 2>/dev/null
 python tools/l2_bench.py 32768 5 > gpurun_out/l2_bench_$R.json 2>/dev/null
 ./tools/ubench > gpurun_out/ubench_$R.json
+python tools/orb_bench.py 256 2000 10 > gpurun_out/orb_bench_$R.json 2>/dev/null
+python tools/orb_bench.py 1 2000 10 > gpurun_out/orb_bench1_$R.json 2>/dev/null
+python tools/orb_bench.py 64 500 10 > gpurun_out/orb_bench500_$R.json 2>/dev/null
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
 $CMD > gpurun_out/plain_$R.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$R.csv $CMD > gpurun_out/ncu_launch_$R.log 2>&1
@@ -18,4 +21,6 @@ python tools/l2_bench.py 32768 2 > gpurun_out/plain3_$R.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:l2_gemm -s 1 -c 1 -o gpurun_out/prof_l2_$R python tools/l2_bench.py 32768 2 > gpurun_out/ncu_l2_$R.log 2>&1
 python bench.py --workload s8k --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain4_$R.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:"score_kernel" -s 3 -c 1 -o gpurun_out/prof_score_s8k_$R python bench.py --workload s8k --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_score_$R.log 2>&1
+python tools/orb_bench.py 256 2000 3 > gpurun_out/plain5_$R.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:"orb_" -s 18 -c 6 -o gpurun_out/prof_orb_$R python tools/orb_bench.py 256 2000 1 > gpurun_out/ncu_orb_$R.log 2>&1
 ls -la gpurun_out

@@ -47,6 +47,23 @@ if l2:
           f"tcgen05 tf32 kernel {l2['gemm_ms']:.3f} ms ({l2['gemm_tflops']:.0f} TFLOP/s of contraction incl. the fused candidate epilogue), "
           f"whole call {l2['total_device_ms']:.2f} ms device / {l2['wall_ms']:.2f} ms wall including the 16.8 MB host-to-device copy; "
           f"{l2['fallbacks']} queries needed the exact fallback.", ""]
+ob, ob1, ob5 = (load(n) for n in ("orb_bench", "orb_bench1", "orb_bench500"))
+if ob:
+    st = ob["stage_ms_per_batch"]
+    L += ["## SURVEY 8(f) rank 1 — `VisualFeature::extract` (cv::ORB detect + compute) on the device (`tools/orb_bench.py`)", "",
+          f"Bit-exact against cv2 {'4.13.0'} (tests/test_gpu_orb.py).  {ob['images']} Tsukuba frames ({ob['width']}x{ob['height']}) per call, "
+          f"nfeatures {ob['n_features']} ({ob['keypoints_per_image']:.0f} keypoints per frame):", "",
+          "| | frames/s |", "|---|---|",
+          f"| device-resident images | {ob['device_resident_frames_per_s']:,.0f} ({ob['device_resident_ms_per_batch']:.2f} ms per call) |",
+          f"| end to end from pageable host images, keypoints + descriptors back on the host | {ob['e2e_frames_per_s']:,.0f} |",
+          f"| cv2.ORB detect + compute on the host, {ob['cv2_threads']} threads | {ob['cv2_orb_frames_per_s']:,.0f} |", "",
+          "Stage times per call (ms): " + ", ".join(f"{k[4:]} {v}" for k, v in st.items()), ""]
+    if ob1:
+        L += [f"One frame per call (the VO case): {ob1['single_frame_latency_us_median']:.0f} us median wall time per `mvs_orb_extract` "
+              f"(kernels: " + ", ".join(f"{k[4:]} {v * 1e3:.0f} us" for k, v in ob1["stage_ms_per_batch"].items()) + ").", ""]
+    if ob5:
+        L += [f"Reference setting nfeatures = 500 (`MAX_FEATURE_COUNT`), {ob5['images']} frames per call: "
+              f"{ob5['device_resident_frames_per_s']:,.0f} frames/s device-resident, cv2 {ob5['cv2_orb_frames_per_s']:,.0f}.", ""]
 if ub:
     L += ["## Measured instruction-pipe ceilings (`tools/ubench`)", "", "| pipe | ops/s (chip) | per clk per SM @1.965 GHz |", "|---|---|---|"]
     for k in ("popc_per_s", "lop3_per_s", "vimnmx_per_s", "iadd3_per_s", "dfma_per_s", "dadd_per_s", "dmul_per_s"):
