@@ -209,6 +209,27 @@ def extraction_extra(ctx, stream, n_img=256, nf=2000, steps=5, cpu=True):
     for _ in range(20):
         ctx.orb_extract(imgs[:1], nf, out=out)
     lat_us = (time.perf_counter() - t0) / 20 * 1e6
+    # pixels -> poses: extract a window of frames straight into the resident frame table, then match + solve the
+    # consecutive pairs (the visual-odometer loop of utility/visual-odometer.cpp, batched); host images in, records out
+    K = np.array([[350.0, 0, 192], [0, 350.0, 144], [0, 0, 1]])          # data/tsukuba/camera.config
+    n_vo = min(n_img, 64)
+    seq = [imgs[i] for i in range(n_vo)]
+    vo_pairs = np.array([(i, i + 1) for i in range(n_vo - 1)], np.int32)
+    res_t = torch.empty((n_vo - 1) * mvs.RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+
+    def vo_step():
+        ctx.frames_clear()
+        ctx.orb_extract(seq, nf, append_frames=True, want=False)
+        ctx.pair_batch(vo_pairs, K, max_dist=10.0, H=1024, out=dict(results=res_t.data_ptr()), bounded=True)
+    for _ in range(2):
+        vo_step()
+    a.record(stream)
+    for _ in range(steps):
+        vo_step()
+    b.record(stream); torch.cuda.synchronize()
+    vo_ms = a.elapsed_time(b) / steps
+    vo_res = np.frombuffer(res_t.numpy(), dtype=mvs.RESULT_DTYPE)
+    ctx.frames_clear()
     pyr_px = sum(int(round(w / 1.2 ** l)) * int(round(h / 1.2 ** l)) for l in range(8))
     r = dict(what="VisualFeature::extract = cv::ORB(nfeatures) detect+compute, bit-exact vs cv2 (tests/test_gpu_orb.py)",
              images_per_step=n_img, width=w, height=h, n_features=nf, keypoints_per_image=float(counts.mean()),
@@ -216,6 +237,10 @@ def extraction_extra(ctx, stream, n_img=256, nf=2000, steps=5, cpu=True):
              e2e=dict(value=n_img / (e2e_ms * 1e-3), unit="frames/s", ms_per_step=e2e_ms, h2d_bytes_per_step=int(host.numel()),
                       d2h_bytes_per_step=int(counts.sum()) * (32 + mvs.KEYPOINT_DTYPE.itemsize) + 4 * n_img),
              single_frame_latency_us=lat_us,
+             pixels_to_poses=dict(value=n_vo / (vo_ms * 1e-3), unit="frames/s", frames_per_step=n_vo, ms_per_step=vo_ms,
+                                  solved_pairs=int((vo_res["status"] == 0).sum()), pairs=int(len(vo_pairs)),
+                                  note="host images -> mvs_orb_extract(append_frames) -> mvs_pair_batch over consecutive pairs "
+                                       "(max_dist 10, H 1024, bounded matcher) -> records on the host"),
              stage_ms_per_step={k: round(v[0] / steps, 4) for k, v in prof.items() if k.startswith("orb")},
              pyramid_pixels_per_image=pyr_px)
     if cpu:

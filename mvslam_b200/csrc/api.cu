@@ -950,10 +950,14 @@ static int orb_extract_impl(mvs_ctx *ctx, const uint8_t *const *h_images, const 
         if (d_images) {
             stage = d_images + (size_t)c0 * height * stride;
         } else {
-            for (int i = 0; i < n; ++i) {
+            const size_t isz = (size_t)height * stride;
+            for (int i = 0; i < n;) {      // one copy per run of images that are contiguous in host memory
                 if (!h_images[c0 + i]) return fail(ctx, MVS_E_BAD_ARG, "orb_extract: null image");
-                CK(cudaMemcpyAsync(ctx->o_stage.as<uint8_t>() + (size_t)i * height * stride, h_images[c0 + i], (size_t)height * stride,
+                int j = i + 1;
+                while (j < n && h_images[c0 + j] == h_images[c0 + j - 1] + isz) ++j;
+                CK(cudaMemcpyAsync(ctx->o_stage.as<uint8_t>() + (size_t)i * isz, h_images[c0 + i], (size_t)(j - i) * isz,
                                    cudaMemcpyHostToDevice, ctx->stream));
+                i = j;
             }
             stage = ctx->o_stage.as<uint8_t>();
         }
