@@ -269,6 +269,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=0, help="pairs per step per GPU (default 1024 tsukuba / 64 s8k)")
     ap.add_argument("--hypotheses", type=int, default=0, help="RANSAC sample-table rows (default 1024 tsukuba / 4096 s8k)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="only the headline workload (used for the ncu launch list)")
     ap.add_argument("--bounded", action="store_true", help="opt-in early-abandon matcher (identical matches, less work)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -398,7 +399,7 @@ def main():
 
     # ---- optional extra: the same workload with the opt-in early-abandon matcher (identical results, less work)
     bounded_extra = None
-    if params["max_dist"] >= 0 and not args.bounded and world == 1:
+    if params["max_dist"] >= 0 and not args.bounded and world == 1 and not args.no_extras:
         kwb = dict(kw, bounded=True)
 
         def step_b():
@@ -499,7 +500,7 @@ def main():
                    sample=f"{n_sample} pairs of the same workload in {dt:.1f} s, C oracle (own-branch port), OpenMP over pairs")
 
     extract = None
-    if world == 1 and args.workload == "tsukuba":
+    if world == 1 and args.workload == "tsukuba" and not args.no_extras:
         extract = extraction_extra(ctx, stream, cpu=not args.no_cpu_baseline)
 
     n_job = int(cfg.get("pairs_total", B * world))      # pairs all ranks processed per step

@@ -29,7 +29,7 @@ class PairResult(C.Structure):
 
 
 def build(force=False):
-    src = [os.path.join(_HERE, f) for f in ("mvs_oracle.c", "mvs_oracle.h", "Makefile")]
+    src = [os.path.join(_HERE, f) for f in ("mvs_oracle.c", "mvs_oracle.h", "pnp_oracle.c", "pnp_oracle.h", "Makefile")]
     if (not force and os.path.exists(_LIB_PATH)
             and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in src)):
         return _LIB_PATH
@@ -236,3 +236,49 @@ def pair_batch(descs, kps, pairs, K, ratio=0.7, max_dist=-1.0, cross_check=False
 
 def max_threads():
     return lib().orc_max_threads()
+
+
+# ---------------------------------------------------------------- pnp_solve (oracle/pnp_oracle.c)
+def pnp_sample_table(seed, problem_id, n_points, H):
+    out = np.empty((H, 4), np.uint32)
+    lib().orc_pnp_sample_table(C.c_uint64(seed), C.c_uint64(problem_id), C.c_uint32(n_points), int(H), _p(out))
+    return out
+
+
+def solve_quartic(c):
+    c = np.ascontiguousarray(c, np.float64); r = np.zeros(4)
+    n = lib().orc_solve_quartic(_p(c), _p(r))
+    return r[:n]
+
+
+def p3p(bearings, world):
+    f = np.ascontiguousarray(bearings, np.float64).reshape(3, 3); X = np.ascontiguousarray(world, np.float64).reshape(3, 3)
+    R = np.zeros((4, 3, 3)); t = np.zeros((4, 3))
+    n = lib().orc_p3p(_p(f), _p(X), _p(R), _p(t))
+    return R[:n], t[:n]
+
+
+def pnp_hypotheses(world, image, K, samples):
+    """(valid[H], R[H,3,3], t[H,3]) world->camera, one P3P hypothesis per sample row."""
+    w = np.ascontiguousarray(world, np.float64); im = np.ascontiguousarray(image, np.float64)
+    K = np.ascontiguousarray(K, np.float64); s = np.ascontiguousarray(samples, np.uint32)
+    H = s.shape[0]
+    R = np.zeros((H, 3, 3)); t = np.zeros((H, 3)); ok = np.zeros(H, bool)
+    L = lib()
+    for h in range(H):
+        ok[h] = bool(L.orc_pnp_hypothesis(_p(w), _p(im), _p(s[h]), _p(K), _p(R[h]), _p(t[h])))
+    return ok, R, t
+
+
+def pnp_solve(world, image, K, samples=None, H=100, seed=0, problem_id=0, reproj_error=0.05, refine_iters=10):
+    w = np.ascontiguousarray(world, np.float64); im = np.ascontiguousarray(image, np.float64)
+    K = np.ascontiguousarray(K, np.float64); n = w.shape[0]
+    if samples is not None:
+        samples = np.ascontiguousarray(samples, np.uint32); H = samples.shape[0]
+    R = np.zeros((3, 3)); t = np.zeros(3); mask = np.zeros(max(n, 1), np.uint8)
+    Rp = np.zeros((3, 3)); tp = np.zeros(3); counts = np.zeros(H, np.int32)
+    ni = C.c_int(0); bh = C.c_int(-1)
+    st = lib().orc_pnp_solve(_p(w), _p(im), n, _p(K), _p(samples), int(H), C.c_uint64(seed), C.c_uint64(problem_id),
+                             C.c_double(reproj_error), int(refine_iters), _p(R), _p(t), _p(mask), C.byref(ni), C.byref(bh),
+                             _p(Rp), _p(tp), _p(counts))
+    return dict(status=st, R=R, t=t, mask=mask[:n], n_inliers=ni.value, best_h=bh.value, R_p3p=Rp, t_p3p=tp, all_counts=counts)

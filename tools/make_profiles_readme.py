@@ -69,5 +69,17 @@ if ub:
     for k in ("popc_per_s", "lop3_per_s", "vimnmx_per_s", "iadd3_per_s", "dfma_per_s", "dadd_per_s", "dmul_per_s"):
         L.append(f"| {k[:-6]} | {ub[k]:.3e} | {ub[k] / 148 / 1.965e9:.1f} |")
     L.append("")
+if t and t.get("extraction"):
+    ex = t["extraction"]
+    L += ["## Extraction inside `bench.py` (field `extraction` of the default line; pinned host images, preallocated pinned outputs)", "",
+          f"{ex['value']:,.0f} frames/s device-resident, {ex['e2e']['value']:,.0f} frames/s end to end "
+          f"({ex['e2e']['h2d_bytes_per_step'] / 1e6:.1f} MB in, {ex['e2e']['d2h_bytes_per_step'] / 1e6:.1f} MB out per {ex['images_per_step']}-frame step); "
+          f"cv2.ORB on {ex['cpu_baseline']['cores']} host threads: {ex['cpu_baseline']['value']:,.0f} frames/s." if ex.get("cpu_baseline") else "",
+          "", f"Pixels to poses (host images -> `mvs_orb_extract(append_frames)` -> `mvs_pair_batch` over consecutive pairs -> records on the host): "
+          f"{ex['pixels_to_poses']['value']:,.0f} frames/s ({ex['pixels_to_poses']['frames_per_step']} frames per step, "
+          f"{ex['pixels_to_poses']['solved_pairs']} of {ex['pixels_to_poses']['pairs']} pairs solved; the 5 frames are cycled, so every fifth pair spans the whole sequence).", ""]
+static = os.path.join(P, f"README_static_{R}.md")      # hand-written tables of runs this script does not redo (multi-GPU, latency)
+if os.path.exists(static):
+    L += [open(static).read()]
 open(os.path.join(P, "README.md"), "w").write("\n".join(L))
 print("\n".join(L))

@@ -96,7 +96,7 @@ if os.path.exists(lp):
         agg[k][0] += 1; agg[k][1] += v
     tot = sum(v[1] for v in agg.values())
     with open(os.path.join(P, f"ncu_launch_shares_{R}.md"), "w") as f:
-        f.write(f"# kernel shares of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline` ({R})\n\n"
+        f.write(f"# kernel shares of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras` ({R})\n\n"
                 "`ncu --metrics gpu__time_duration.sum --clock-control none` (cold-cache, serialised: compare shares).\n\n"
                 "| kernel | launches | total us | share |\n|---|---|---|---|\n")
         for k, v in sorted(agg.items(), key=lambda x: -x[1][1]):
