@@ -113,11 +113,31 @@ typedef struct {
     int32_t reserved[3];
 } mvs_orb_params;
 
+/* constants of pnp-solve.cpp:48-52 made explicit */
+typedef struct {
+    int32_t  n_hypotheses;       /* <= 0: 100 (iterationsCount) */
+    int32_t  refine_iterations;  /* < 0: 10 Gauss-Newton steps on the inliers; 0: return the winning minimal-sample pose */
+    double   reprojection_error; /* <= 0: 0.05 pixels (reprojectionError) */
+    uint64_t seed;               /* seeds rows >= 1 of the 4-point sample table (mvs_pnp_sample_table) */
+    uint64_t problem_id_base;    /* batch entry i samples with problem_id = problem_id_base + i */
+    int32_t  min_inliers;        /* <= 0: 4 */
+    int32_t  reserved;
+} mvs_pnp_params;
+
+typedef struct {
+    int32_t status;              /* MVS_OK, MVS_E_TOO_FEW_POINTS (< 4), MVS_E_NO_MODEL */
+    int32_t n_points;
+    int32_t n_inliers;           /* consensus of the winning minimal-sample pose */
+    int32_t best_hypothesis;
+    double  R_c2w[9], t_c2w[3];          /* pose: camera to world, SE3(R, t).inverse() of pnp-solve.cpp:99-101 */
+    double  R_w2c_p3p[9], t_w2c_p3p[3];  /* the winning P3P pose (world to camera) before refinement */
+} mvs_pnp_result;
+
 /* per-stage device time accumulated on the ctx stream while profiling is enabled */
 enum { MVS_STAGE_KNN = 0, MVS_STAGE_MATCH_FINALIZE, MVS_STAGE_HYPOTHESES, MVS_STAGE_SCORE,
        MVS_STAGE_SELECT, MVS_STAGE_TRIANGULATE, MVS_STAGE_FINALIZE, MVS_STAGE_L2,
        MVS_STAGE_ORB_PYRAMID, MVS_STAGE_ORB_FAST, MVS_STAGE_ORB_HARRIS, MVS_STAGE_ORB_SELECT,
-       MVS_STAGE_ORB_BLUR, MVS_STAGE_ORB_DESCRIBE, MVS_N_STAGES };
+       MVS_STAGE_ORB_BLUR, MVS_STAGE_ORB_DESCRIBE, MVS_STAGE_PNP, MVS_N_STAGES };
 typedef struct {
     double   ms[MVS_N_STAGES];
     uint64_t launches[MVS_N_STAGES];
@@ -213,6 +233,24 @@ int mvs_sfm_solve(mvs_ctx *ctx, const double *xy1, const double *xy2, int n, con
 int mvs_sfm_triangulate(mvs_ctx *ctx, const double *xy1, const double *xy2, int n, const double K[9],
                         const double R1[9], const double t1[3], const double R2[9], const double t2[3],
                         double *points, uint64_t *indexes, int capacity, int *n_out);
+
+/* ---- pnp_solve (source/vision/pnp-solve.cpp:16-104, decl source/vision/pnp.hpp:22-26) = cv::solvePnPRansac with
+ *      SOLVEPNP_P3P: seeded 4-point samples, P3P + 4th-point disambiguation per hypothesis, squared reprojection
+ *      error <= reprojection_error^2 consensus over all hypotheses x points, refinement on the inliers.
+ *      VisualOdometer::track_pnp (source/front-end/visual-odometer.cpp:503-615) is the caller. ---- */
+/* row 0 = {0,1,2,3}; rows >= 1 hold 4 distinct indices < n_points.  Pure host function, out is [H][4]. */
+void mvs_pnp_sample_table(uint64_t seed, uint64_t problem_id, uint32_t n_points, int H, uint32_t *out);
+/* world [n][3], image [n][2] (pixels), K row-major (fx, fy, cx, cy are used, as cv::projectPoints does).
+ * samples: optional explicit [H][4] table (H = params->n_hypotheses).  inlier_mask [n] optional.
+ * all_counts (optional, [H]) receives the consensus size of every hypothesis. */
+int mvs_pnp_solve(mvs_ctx *ctx, const double *world, const double *image, int n, const double K[9],
+                  const mvs_pnp_params *params, const uint32_t *samples, mvs_pnp_result *result,
+                  uint8_t *inlier_mask, int32_t *all_counts);
+/* n_problems independent problems in one pass: problem i owns counts[i] consecutive rows of world / image /
+ * inlier_mask.  results[n_problems] always filled (status per problem). */
+int mvs_pnp_solve_batch(mvs_ctx *ctx, const double *world, const double *image, const int32_t *counts, int n_problems,
+                        const double K[9], const mvs_pnp_params *params, const uint32_t *samples,
+                        mvs_pnp_result *results, uint8_t *inlier_mask);
 
 /* ---- batched image pairs: ImagePair::ImagePair + reconstruct (source/front-end/image-pair.cpp:30-71,
  *      115-174) for many (base, pair) frame pairs per call; the natural batch of

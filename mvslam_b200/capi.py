@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
  E_UNSUPPORTED) = range(9)
 SCORE_ALGEBRAIC, SCORE_SAMPSON = 0, 1
 STAGES = ("knn", "match_finalize", "hypotheses", "score", "select", "triangulate", "finalize", "l2",
-          "orb_pyramid", "orb_fast", "orb_harris", "orb_select", "orb_blur", "orb_describe")
+          "orb_pyramid", "orb_fast", "orb_harris", "orb_select", "orb_blur", "orb_describe", "pnp")
 
 MATCH_DTYPE = np.dtype([("query", np.int32), ("train", np.int32), ("distance", np.float32)])
 RESULT_DTYPE = np.dtype([
@@ -41,6 +41,19 @@ class PairResult(C.Structure):
 
 
 assert C.sizeof(PairResult) == RESULT_DTYPE.itemsize == 376
+
+
+PNP_RESULT_DTYPE = np.dtype([
+    ("status", np.int32), ("n_points", np.int32), ("n_inliers", np.int32), ("best_hypothesis", np.int32),
+    ("R_c2w", np.float64, (3, 3)), ("t_c2w", np.float64, (3,)), ("R_w2c_p3p", np.float64, (3, 3)), ("t_w2c_p3p", np.float64, (3,))])
+
+
+class PnpParams(C.Structure):
+    _fields_ = [("n_hypotheses", C.c_int32), ("refine_iterations", C.c_int32), ("reprojection_error", C.c_double),
+                ("seed", C.c_uint64), ("problem_id_base", C.c_uint64), ("min_inliers", C.c_int32), ("reserved", C.c_int32)]
+
+
+assert PNP_RESULT_DTYPE.itemsize == 208 and C.sizeof(PnpParams) == 40
 
 
 class OrbParams(C.Structure):
@@ -82,6 +95,7 @@ def load_library():
     L.mvs_destroy.restype = None
     L.mvs_destroy.argtypes = [C.c_void_p]
     L.mvs_sample_table.restype = None
+    L.mvs_pnp_sample_table.restype = None
     if L.mvs_abi_version() != 2:
         raise ImportError("libmvslam_b200.so ABI version mismatch")
     _lib = L
@@ -98,6 +112,13 @@ def _p(a):
 
 def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def pnp_sample_table(seed, problem_id, n_points, H):
+    """Host copy of the device 4-point sampler (mvs_pnp_sample_table)."""
+    out = np.empty((H, 4), np.uint32)
+    load_library().mvs_pnp_sample_table(C.c_uint64(seed), C.c_uint64(problem_id), C.c_uint32(n_points), int(H), _p(out))
+    return out
 
 
 def sample_table(seed, pair_id, n_points, H):
@@ -290,6 +311,36 @@ class Context:
         self._check(self._L.mvs_sfm_triangulate(self._h, _p(xy1), _p(xy2), n, _p(_f64(K)), _p(_f64(R1)), _p(_f64(t1)),
                                                 _p(_f64(R2)), _p(_f64(t2)), _p(pts), _p(idx), max(n, 1), C.byref(m)))
         return pts[:m.value].copy(), idx[:m.value].copy()
+
+    # ---- pnp_solve
+    def pnp_solve(self, world, image, K, samples=None, H=100, seed=0, problem_id=0, reproj_error=0.05, refine_iters=10,
+                  want_all=False):
+        w = _f64(world).reshape(-1, 3); im = _f64(image).reshape(-1, 2); n = w.shape[0]
+        if samples is not None:
+            samples = np.ascontiguousarray(samples, np.uint32); H = samples.shape[0]
+        pp = PnpParams(H, refine_iters, reproj_error, seed, problem_id, 0, 0)
+        res = np.zeros(1, PNP_RESULT_DTYPE); mask = np.zeros(max(n, 1), np.uint8)
+        allc = np.zeros(H, np.int32) if want_all else None
+        st = self._L.mvs_pnp_solve(self._h, _p(w), _p(im), n, _p(_f64(K)), C.byref(pp), _p(samples), _p(res), _p(mask), _p(allc))
+        self._check(st, (OK, E_TOO_FEW_POINTS, E_NO_MODEL))
+        r = res[0]
+        d = {k: (r[k].copy() if r[k].ndim else r[k].item()) for k in PNP_RESULT_DTYPE.names}
+        d["mask"] = mask[:n]
+        if want_all:
+            d["all_counts"] = allc
+        return d
+
+    def pnp_solve_batch(self, worlds, images, K, H=100, seed=0, problem_id_base=0, reproj_error=0.05, refine_iters=10):
+        """worlds/images: lists of per-problem arrays.  Returns (results[PNP_RESULT_DTYPE], masks list)."""
+        counts = np.array([len(w) for w in worlds], np.int32)
+        w = _f64(np.concatenate([np.asarray(x, np.float64).reshape(-1, 3) for x in worlds])) if counts.sum() else np.zeros((0, 3))
+        im = _f64(np.concatenate([np.asarray(x, np.float64).reshape(-1, 2) for x in images])) if counts.sum() else np.zeros((0, 2))
+        pp = PnpParams(H, refine_iters, reproj_error, seed, problem_id_base, 0, 0)
+        res = np.zeros(len(counts), PNP_RESULT_DTYPE); mask = np.zeros(max(int(counts.sum()), 1), np.uint8)
+        self._check(self._L.mvs_pnp_solve_batch(self._h, _p(w), _p(im), _p(counts), len(counts), _p(_f64(K)), C.byref(pp), None,
+                                                _p(res), _p(mask)))
+        offs = np.concatenate([[0], np.cumsum(counts)])
+        return res, [mask[offs[i]:offs[i + 1]] for i in range(len(counts))]
 
     # ---- batched pairs
     def frames_upload(self, descs, kps):

@@ -12,6 +12,7 @@
 #include "kernels.h"
 #include "l2.h"
 #include "orb.h"
+#include "pnp.h"
 
 using namespace mvs;
 
@@ -60,6 +61,7 @@ struct mvs_ctx {
     int orb_w = 0, orb_h = 0, orb_nf = -1;
     mvs::OrbGeom orb_geom;
     DevBuf o_tabs, o_stage, o_pyr, o_blur, o_cxy, o_cval, o_cnt, o_kidx, o_kcnt, o_off, o_kp, o_desc;
+    DevBuf p_world, p_image, p_off, p_table, p_poses, p_valid, p_pc, p_maskws, p_mask, p_counts, p_results;
     int32_t *o_pinned = nullptr;
     size_t o_pinned_cap = 0;
     // profiling
@@ -315,7 +317,8 @@ void mvs_destroy(mvs_ctx *ctx)
                       &ctx->d_opts, &ctx->d_oidx, &ctx->d_results, &ctx->d_table, &ctx->d_in1, &ctx->d_in2,
                       &ctx->d_knn_i, &ctx->d_knn_d, &ctx->d_counts, &ctx->d_pres, &ctx->o_tabs, &ctx->o_stage,
                       &ctx->o_pyr, &ctx->o_blur, &ctx->o_cxy, &ctx->o_cval, &ctx->o_cnt, &ctx->o_kidx, &ctx->o_kcnt,
-                      &ctx->o_off, &ctx->o_kp, &ctx->o_desc};
+                      &ctx->o_off, &ctx->o_kp, &ctx->o_desc, &ctx->p_world, &ctx->p_image, &ctx->p_off, &ctx->p_table,
+                      &ctx->p_poses, &ctx->p_valid, &ctx->p_pc, &ctx->p_maskws, &ctx->p_mask, &ctx->p_counts, &ctx->p_results};
     if (ctx->o_pinned) cudaFreeHost(ctx->o_pinned);
     for (DevBuf *b : bufs) b->release();
     ctx->l2.release();
@@ -1048,6 +1051,92 @@ int mvs_orb_extract_device(mvs_ctx *ctx, const void *d_images, int n_images, int
 {
     return orb_extract_impl(ctx, nullptr, static_cast<const uint8_t *>(d_images), n_images, width, height, stride_bytes, params,
                             append_frames, first_frame, counts, keypoints, descriptors, capacity);
+}
+
+// ------------------------------------------------------------------------------------------ pnp_solve
+void mvs_pnp_sample_table(uint64_t seed, uint64_t problem_id, uint32_t n_points, int H, uint32_t *out)
+{
+    pnp_sample_table_host(seed, problem_id, n_points, H, out);
+}
+
+static int pnp_impl(mvs_ctx *ctx, const double *world, const double *image, const int32_t *counts, int n_problems,
+                    const double K[9], const mvs_pnp_params *params, const uint32_t *samples, mvs_pnp_result *results,
+                    uint8_t *inlier_mask, int32_t *all_counts)
+{
+    if (!ctx) return MVS_E_BAD_ARG;
+    if (!counts || n_problems < 1 || !K || !results) return fail(ctx, MVS_E_BAD_ARG, "pnp_solve: null argument or no problem");
+    std::vector<int32_t> off(n_problems + 1, 0);
+    int max_n = 0;
+    for (int i = 0; i < n_problems; ++i) {
+        if (counts[i] < 0) return fail(ctx, MVS_E_BAD_ARG, "pnp_solve: negative point count");
+        if ((int64_t)off[i] + counts[i] > 0x7FFFFFFF) return fail(ctx, MVS_E_UNSUPPORTED, "pnp_solve: more than 2^31 points");
+        off[i + 1] = off[i] + counts[i];
+        max_n = std::max(max_n, counts[i]);
+    }
+    const size_t total = (size_t)off[n_problems];
+    if (total && (!world || !image)) return fail(ctx, MVS_E_BAD_ARG, "pnp_solve: null points");
+    if (!(K[0] != 0.0) || !(K[4] != 0.0)) return fail(ctx, MVS_E_BAD_ARG, "pnp_solve: zero focal length");
+    PnpArgs a{};
+    a.H = params && params->n_hypotheses > 0 ? params->n_hypotheses : 100;        // pnp-solve.cpp:50
+    a.refine_iters = params && params->refine_iterations >= 0 ? params->refine_iterations : 10;
+    const double err = params && params->reprojection_error > 0 ? params->reprojection_error : 0.05;   // :51
+    a.thr2 = err * err;
+    a.seed = params ? params->seed : 0; a.problem_id_base = params ? params->problem_id_base : 0;
+    a.min_inliers = params && params->min_inliers > 0 ? params->min_inliers : 4;
+    a.fx = K[0]; a.fy = K[4]; a.cx = K[2]; a.cy = K[5];
+    a.tiles = pnp_tiles(max_n);
+    if (n_problems > 65535) return fail(ctx, MVS_E_UNSUPPORTED, "pnp_solve: more than 65535 problems per call");
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->p_world.ensure(std::max<size_t>(total, 1) * 24));
+    CK(ctx->p_image.ensure(std::max<size_t>(total, 1) * 16));
+    CK(ctx->p_off.ensure(off.size() * sizeof(int32_t)));
+    CK(ctx->p_poses.ensure((size_t)n_problems * a.H * 12 * sizeof(double)));
+    CK(ctx->p_valid.ensure((size_t)n_problems * a.H));
+    CK(ctx->p_pc.ensure((size_t)n_problems * a.tiles * a.H * sizeof(int32_t)));
+    CK(ctx->p_maskws.ensure(std::max<size_t>(total, 1)));
+    CK(ctx->p_results.ensure((size_t)n_problems * sizeof(mvs_pnp_result)));
+    if (inlier_mask) CK(ctx->p_mask.ensure(std::max<size_t>(total, 1)));
+    if (all_counts) CK(ctx->p_counts.ensure((size_t)n_problems * a.H * sizeof(int32_t)));
+    if (samples) {
+        CK(ctx->p_table.ensure((size_t)a.H * 4 * sizeof(uint32_t)));
+        CK(cudaMemcpyAsync(ctx->p_table.p, samples, (size_t)a.H * 4 * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (total) {
+        CK(cudaMemcpyAsync(ctx->p_world.p, world, total * 24, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->p_image.p, image, total * 16, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CK(cudaMemcpyAsync(ctx->p_off.p, off.data(), off.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    a.world = ctx->p_world.as<double>(); a.image = ctx->p_image.as<double>(); a.offsets = ctx->p_off.as<int32_t>();
+    a.table = samples ? ctx->p_table.as<uint32_t>() : nullptr;
+    a.poses = ctx->p_poses.as<double>(); a.valid = ctx->p_valid.as<uint8_t>(); a.part_count = ctx->p_pc.as<int32_t>();
+    a.mask_ws = ctx->p_maskws.as<uint8_t>(); a.mask = inlier_mask ? ctx->p_mask.as<uint8_t>() : nullptr;
+    a.all_counts = all_counts ? ctx->p_counts.as<int32_t>() : nullptr;
+    a.results = ctx->p_results.as<mvs_pnp_result>();
+    {
+        StageTimer t(ctx, MVS_STAGE_PNP, 3);
+        launch_pnp(a, n_problems, max_n, ctx->stream);
+    }
+    CK(cudaMemcpyAsync(results, ctx->p_results.p, (size_t)n_problems * sizeof(mvs_pnp_result), cudaMemcpyDeviceToHost, ctx->stream));
+    if (inlier_mask && total) CK(cudaMemcpyAsync(inlier_mask, ctx->p_mask.p, total, cudaMemcpyDeviceToHost, ctx->stream));
+    if (all_counts) CK(cudaMemcpyAsync(all_counts, ctx->p_counts.p, (size_t)n_problems * a.H * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));   // off is stack/vector memory; results are host-visible on return
+    return MVS_OK;
+}
+
+int mvs_pnp_solve(mvs_ctx *ctx, const double *world, const double *image, int n, const double K[9],
+                  const mvs_pnp_params *params, const uint32_t *samples, mvs_pnp_result *result,
+                  uint8_t *inlier_mask, int32_t *all_counts)
+{
+    const int32_t cnt = n;
+    int st = pnp_impl(ctx, world, image, &cnt, 1, K, params, samples, result, inlier_mask, all_counts);
+    return st != MVS_OK ? st : result->status;
+}
+
+int mvs_pnp_solve_batch(mvs_ctx *ctx, const double *world, const double *image, const int32_t *counts, int n_problems,
+                        const double K[9], const mvs_pnp_params *params, const uint32_t *samples,
+                        mvs_pnp_result *results, uint8_t *inlier_mask)
+{
+    return pnp_impl(ctx, world, image, counts, n_problems, K, params, samples, results, inlier_mask, nullptr);
 }
 
 }  // extern "C"

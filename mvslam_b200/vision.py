@@ -4,6 +4,7 @@
   VisualFeature.match_visual_features(vf1, vf2, max_dist)   source/vision/visual-feature.hpp:23-26
   sfm_solve(p1, p2, K)                                      source/vision/sfm.hpp:30-35
   sfm_triangulate(p1, p2, K, pose1, pose2)                  source/vision/sfm.hpp:47-53
+  pnp_solve(world_points, image_points, K)                  source/vision/pnp.hpp:22-26
   image_pairs(frames, pairs, K, params)                     ImagePair ctor, source/front-end/image-pair.hpp:38-40
 
 All of them forward to the C ABI (libmvslam_b200.so); none computes anything on the CPU.
@@ -68,6 +69,14 @@ def sfm_solve(p1, p2, K, ctx=None, **kw):
 def sfm_triangulate(p1, p2, K, pose1, pose2, ctx=None):
     ctx = ctx or default_context()
     return ctx.sfm_triangulate(p1, p2, K, pose1[0], pose1[1], pose2[0], pose2[1])
+
+
+def pnp_solve(world_points, image_points, K, ctx=None, **kw):
+    """Returns (ok, (R, t) camera-to-world pose, inlier_point_indexes) like the reference's bool + out-params
+    (pnp-solve.cpp:16-104: cv::solvePnPRansac with P3P, 100 iterations, reprojection error 0.05)."""
+    ctx = ctx or default_context()
+    r = ctx.pnp_solve(world_points, image_points, K, **kw)
+    return r["status"] == capi.OK, (r["R_c2w"], r["t_c2w"]), np.nonzero(r["mask"])[0].astype(np.uint64)
 
 
 def image_pairs(frames, pairs, K, max_match_inlier_distance=10.0, ctx=None, **kw):

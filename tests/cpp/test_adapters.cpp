@@ -7,6 +7,7 @@
 #include <random>
 
 #include <mvslam/image-pair.hpp>
+#include <mvslam/pnp.hpp>
 
 using namespace mvSLAM;
 
@@ -108,6 +109,27 @@ static bool image_pair_and_matcher()
     return true;
 }
 
+// test/test-pnp.cpp:14-63 (pnp_solve_cube): cube rig at (0.6, 0, 3), camera at x = +1, K = I, tolerance 1e-3, no outliers
+static bool pnp_solve_cube()
+{
+    std::vector<Point3> world;
+    std::vector<ImagePoint> image;
+    for (int x = -1; x <= 1; x += 2) for (int y = -1; y <= 1; y += 2) for (int z = -1; z <= 1; z += 2) {
+        Point3 p(x + 0.6, y + 0.0, z + 3.0);
+        world.push_back(p);
+        image.emplace_back((p[0] - 1.0) / p[2], p[1] / p[2]);
+    }
+    Transformation pose;
+    std::vector<size_t> inliers;
+    ASSERT_TRUE(pnp_solve(world, image, Matrix3Type::Identity(), pose, inliers));
+    ASSERT_TRUE(inliers.size() == world.size());
+    ASSERT_EQUAL(pose.translation()[0], 1.0, 1e-3);
+    ASSERT_EQUAL(pose.translation()[1], 0.0, 1e-3);
+    ASSERT_EQUAL(pose.translation()[2], 0.0, 1e-3);
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) ASSERT_EQUAL(pose.rotation().get_matrix()(r, c), r == c ? 1.0 : 0.0, 1e-3);
+    return true;
+}
+
 // VisualFeature::extract (visual-feature.hpp:14) on two renderings of the same rectangles shifted by 6 pixels:
 // the extracted features match each other under that shift, like utility/test-visual-feature.cpp:25-35 shows by eye.
 static bool extract_and_match()
@@ -149,7 +171,8 @@ int main()
     struct { const char *name; bool (*fn)(); } tests[] = {{"sfm_triangulate_cube", sfm_triangulate_cube},
                                                            {"sfm_solve_L_shape", sfm_solve_L_shape},
                                                            {"image_pair_and_matcher", image_pair_and_matcher},
-                                                           {"extract_and_match", extract_and_match}};
+                                                           {"extract_and_match", extract_and_match},
+                                                           {"pnp_solve_cube", pnp_solve_cube}};
     for (auto &t : tests) {
         bool ok = false;
         try { ok = t.fn(); } catch (const std::exception &e) { std::printf("exception: %s\n", e.what()); }
