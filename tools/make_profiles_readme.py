@@ -64,6 +64,18 @@ if ob:
     if ob5:
         L += [f"Reference setting nfeatures = 500 (`MAX_FEATURE_COUNT`), {ob5['images']} frames per call: "
               f"{ob5['device_resident_frames_per_s']:,.0f} frames/s device-resident, cv2 {ob5['cv2_orb_frames_per_s']:,.0f}.", ""]
+pb, pbb = load("pnp_bench"), load("pnp_bench_big")
+if pb:
+    L += ["## SURVEY 8(f) rank 3 — `pnp_solve` (cv::solvePnPRansac with P3P) on the device (`tools/pnp_bench.py`)", "",
+          "Consensus sizes, winner, minimal-sample pose and inlier set bit-exact against the CPU oracle (tests/test_gpu_pnp.py); "
+          "the oracle is pinned against cv2.solveP3P / cv2.solvePnPRansac (tests/test_pnp_oracle.py).", "",
+          "| problems x points x hypotheses | problems/s (kernels) | problems/s (call with host buffers) | hypothesis·point evaluations/s | cv2.solvePnPRansac, 1 host thread |",
+          "|---|---|---|---|---|"]
+    for b_ in (pb, pbb):
+        if b_:
+            L.append(f"| {b_['problems']} x {b_['points_per_problem']} x {b_['hypotheses']} | {b_['problems_per_s_device']:,.0f} | "
+                     f"{b_['e2e_problems_per_s']:,.0f} | {b_['hyp_pt_evals_per_s'] / 1e9:.0f} G | {b_['cv2_solvepnpransac_problems_per_s']:,.0f} |")
+    L += ["", f"One problem per call: {pb['single_problem_latency_us']:.0f} us.", ""]
 if ub:
     L += ["## Measured instruction-pipe ceilings (`tools/ubench`)", "", "| pipe | ops/s (chip) | per clk per SM @1.965 GHz |", "|---|---|---|"]
     for k in ("popc_per_s", "lop3_per_s", "vimnmx_per_s", "iadd3_per_s", "dfma_per_s", "dadd_per_s", "dmul_per_s"):
