@@ -133,11 +133,35 @@ typedef struct {
     double  R_w2c_p3p[9], t_w2c_p3p[3];  /* the winning P3P pose (world to camera) before refinement */
 } mvs_pnp_result;
 
+/* one GenericProjectionFactor of ba.cpp:96-117: image point z with covariance [[cov[0], cov[1]], [cov[1], cov[2]]]
+ * of point `point` seen by camera `frame` (both indexes local to their problem) */
+typedef struct {
+    int32_t frame, point;
+    double  uv[2];
+    double  cov[3];
+} mvs_ba_observation;
+
+/* gtsam::LevenbergMarquardtParams as far as they matter here */
+typedef struct {
+    int32_t max_iterations;      /* <= 0: 100 (GTSAM default) */
+    int32_t reserved;
+    double  lambda_initial;      /* <= 0: 1e-5 (GTSAM default) */
+    double  relative_tolerance;  /* <= 0: 1e-13: stop when the cost decreases by less than this fraction
+                                    (GTSAM stops at 1e-5; iterating further only moves closer to the same minimum) */
+} mvs_ba_params;
+
+typedef struct {
+    int32_t status;              /* MVS_OK, MVS_E_UNSUPPORTED (more than 2 frames), MVS_E_BAD_ARG (prior covariance not PD) */
+    int32_t iterations;
+    double  initial_error;       /* cost at the guesses */
+    double  final_error;         /* cost at the result == optimizer.error(), ba.cpp:154 */
+} mvs_ba_result;
+
 /* per-stage device time accumulated on the ctx stream while profiling is enabled */
 enum { MVS_STAGE_KNN = 0, MVS_STAGE_MATCH_FINALIZE, MVS_STAGE_HYPOTHESES, MVS_STAGE_SCORE,
        MVS_STAGE_SELECT, MVS_STAGE_TRIANGULATE, MVS_STAGE_FINALIZE, MVS_STAGE_L2,
        MVS_STAGE_ORB_PYRAMID, MVS_STAGE_ORB_FAST, MVS_STAGE_ORB_HARRIS, MVS_STAGE_ORB_SELECT,
-       MVS_STAGE_ORB_BLUR, MVS_STAGE_ORB_DESCRIBE, MVS_STAGE_PNP, MVS_N_STAGES };
+       MVS_STAGE_ORB_BLUR, MVS_STAGE_ORB_DESCRIBE, MVS_STAGE_PNP, MVS_STAGE_BA, MVS_N_STAGES };
 typedef struct {
     double   ms[MVS_N_STAGES];
     uint64_t launches[MVS_N_STAGES];
@@ -251,6 +275,23 @@ int mvs_pnp_solve(mvs_ctx *ctx, const double *world, const double *image, int n,
 int mvs_pnp_solve_batch(mvs_ctx *ctx, const double *world, const double *image, const int32_t *counts, int n_problems,
                         const double K[9], const mvs_pnp_params *params, const uint32_t *samples,
                         mvs_pnp_result *results, uint8_t *inlier_mask);
+
+/* ---- ba_frame_pose_and_point (source/vision/ba.cpp:26-156, decl source/vision/ba.hpp:25-36), the optimisation behind
+ *      sfm_refine (sfm-refine.cpp:20-139), pnp_refine (pnp-refine.cpp:16-110) and VisualOdometer::track_refine
+ *      (visual-odometer.cpp:640-800): Levenberg-Marquardt over 1 or 2 camera poses (camera to world) and their points
+ *      with Gaussian priors (prior mean = the guess) and projection factors; estimates come back with the marginal
+ *      covariances gtsam::Marginals would give (blocks of the inverse Gauss-Newton Hessian).
+ *      n_problems independent problems per call; problem i owns n_frames[i] / n_points[i] / n_obs[i] consecutive rows
+ *      of the pose / point / observation arrays.  K = Cal3_S2(K[0], K[4], K[1], K[2], K[5]).
+ *      pose_prior_cov [frames][36] (tangent order: rotation, translation — GTSAM's Pose3) and point_prior_cov
+ *      [points][9]: a NaN in the first element means "no prior".  Outputs are optional except results. ---- */
+int mvs_ba_solve_batch(mvs_ctx *ctx, int n_problems, const double K[9],
+                       const int32_t *n_frames, const int32_t *n_points, const int32_t *n_obs,
+                       const double *pose_R, const double *pose_t, const double *pose_prior_cov,
+                       const double *points, const double *point_prior_cov, const mvs_ba_observation *obs,
+                       const mvs_ba_params *params,
+                       double *pose_R_out, double *pose_t_out, double *pose_cov_out,
+                       double *points_out, double *point_cov_out, mvs_ba_result *results);
 
 /* ---- batched image pairs: ImagePair::ImagePair + reconstruct (source/front-end/image-pair.cpp:30-71,
  *      115-174) for many (base, pair) frame pairs per call; the natural batch of

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
  E_UNSUPPORTED) = range(9)
 SCORE_ALGEBRAIC, SCORE_SAMPSON = 0, 1
 STAGES = ("knn", "match_finalize", "hypotheses", "score", "select", "triangulate", "finalize", "l2",
-          "orb_pyramid", "orb_fast", "orb_harris", "orb_select", "orb_blur", "orb_describe", "pnp")
+          "orb_pyramid", "orb_fast", "orb_harris", "orb_select", "orb_blur", "orb_describe", "pnp", "ba")
 
 MATCH_DTYPE = np.dtype([("query", np.int32), ("train", np.int32), ("distance", np.float32)])
 RESULT_DTYPE = np.dtype([
@@ -54,6 +54,18 @@ class PnpParams(C.Structure):
 
 
 assert PNP_RESULT_DTYPE.itemsize == 208 and C.sizeof(PnpParams) == 40
+
+
+BA_OBS_DTYPE = np.dtype([("frame", np.int32), ("point", np.int32), ("uv", np.float64, (2,)), ("cov", np.float64, (3,))])
+BA_RESULT_DTYPE = np.dtype([("status", np.int32), ("iterations", np.int32), ("initial_error", np.float64), ("final_error", np.float64)])
+
+
+class BaParams(C.Structure):
+    _fields_ = [("max_iterations", C.c_int32), ("reserved", C.c_int32), ("lambda_initial", C.c_double),
+                ("relative_tolerance", C.c_double)]
+
+
+assert BA_OBS_DTYPE.itemsize == 48 and BA_RESULT_DTYPE.itemsize == 24
 
 
 class OrbParams(C.Structure):
@@ -341,6 +353,32 @@ class Context:
                                                 _p(res), _p(mask)))
         offs = np.concatenate([[0], np.cumsum(counts)])
         return res, [mask[offs[i]:offs[i + 1]] for i in range(len(counts))]
+
+    # ---- bundle adjustment
+    def ba_solve_batch(self, K, problems, max_iterations=100, lambda_initial=1e-5, relative_tolerance=1e-13):
+        """problems: list of dict(pose_R [F,3,3], pose_t [F,3], pose_prior_cov [F,6,6] (NaN rows = none), points [P,3],
+        point_prior_cov [P,3,3] (NaN = none), obs BA_OBS_DTYPE[O]).  Returns a list of result dicts."""
+        nf = np.array([len(p["pose_R"]) for p in problems], np.int32)
+        npt = np.array([len(p["points"]) for p in problems], np.int32)
+        no = np.array([len(p["obs"]) for p in problems], np.int32)
+        cat = lambda k, shape: _f64(np.concatenate([np.asarray(p[k], np.float64).reshape(shape) for p in problems]))  # noqa: E731
+        R = cat("pose_R", (-1, 9)); t = cat("pose_t", (-1, 3)); pc = cat("pose_prior_cov", (-1, 36))
+        X = cat("points", (-1, 3)); xc = cat("point_prior_cov", (-1, 9))
+        obs = np.ascontiguousarray(np.concatenate([np.asarray(p["obs"], BA_OBS_DTYPE) for p in problems]))
+        Ro = np.zeros_like(R); to = np.zeros_like(t); pco = np.zeros_like(pc); Xo = np.zeros_like(X); xco = np.zeros_like(xc)
+        res = np.zeros(len(problems), BA_RESULT_DTYPE)
+        bp = BaParams(max_iterations, 0, lambda_initial, relative_tolerance)
+        self._check(self._L.mvs_ba_solve_batch(self._h, len(problems), _p(_f64(K)), _p(nf), _p(npt), _p(no), _p(R), _p(t), _p(pc),
+                                               _p(X), _p(xc), _p(obs), C.byref(bp), _p(Ro), _p(to), _p(pco), _p(Xo), _p(xco), _p(res)))
+        out = []
+        fo = np.concatenate([[0], np.cumsum(nf)]); po = np.concatenate([[0], np.cumsum(npt)])
+        for i in range(len(problems)):
+            f = slice(fo[i], fo[i + 1]); q = slice(po[i], po[i + 1])
+            out.append(dict(status=int(res["status"][i]), iterations=int(res["iterations"][i]),
+                            initial_error=float(res["initial_error"][i]), final_error=float(res["final_error"][i]),
+                            pose_R=Ro[f].reshape(-1, 3, 3), pose_t=to[f], pose_cov=pco[f].reshape(-1, 6, 6),
+                            points=Xo[q], point_cov=xco[q].reshape(-1, 3, 3)))
+        return out
 
     # ---- batched pairs
     def frames_upload(self, descs, kps):

@@ -13,6 +13,7 @@
 #include "l2.h"
 #include "orb.h"
 #include "pnp.h"
+#include "ba.h"
 
 using namespace mvs;
 
@@ -62,6 +63,7 @@ struct mvs_ctx {
     mvs::OrbGeom orb_geom;
     DevBuf o_tabs, o_stage, o_pyr, o_blur, o_cxy, o_cval, o_cnt, o_kidx, o_kcnt, o_off, o_kp, o_desc;
     DevBuf p_world, p_image, p_off, p_table, p_poses, p_valid, p_pc, p_maskws, p_mask, p_counts, p_results;
+    DevBuf b_foff, b_poff, b_R, b_t, b_pc, b_X, b_xc, b_obs, b_ooff, b_ws, b_Ro, b_to, b_pco, b_Xo, b_xco, b_res;
     int32_t *o_pinned = nullptr;
     size_t o_pinned_cap = 0;
     // profiling
@@ -318,7 +320,9 @@ void mvs_destroy(mvs_ctx *ctx)
                       &ctx->d_knn_i, &ctx->d_knn_d, &ctx->d_counts, &ctx->d_pres, &ctx->o_tabs, &ctx->o_stage,
                       &ctx->o_pyr, &ctx->o_blur, &ctx->o_cxy, &ctx->o_cval, &ctx->o_cnt, &ctx->o_kidx, &ctx->o_kcnt,
                       &ctx->o_off, &ctx->o_kp, &ctx->o_desc, &ctx->p_world, &ctx->p_image, &ctx->p_off, &ctx->p_table,
-                      &ctx->p_poses, &ctx->p_valid, &ctx->p_pc, &ctx->p_maskws, &ctx->p_mask, &ctx->p_counts, &ctx->p_results};
+                      &ctx->p_poses, &ctx->p_valid, &ctx->p_pc, &ctx->p_maskws, &ctx->p_mask, &ctx->p_counts, &ctx->p_results,
+                      &ctx->b_foff, &ctx->b_poff, &ctx->b_R, &ctx->b_t, &ctx->b_pc, &ctx->b_X, &ctx->b_xc, &ctx->b_obs, &ctx->b_ooff,
+                      &ctx->b_ws, &ctx->b_Ro, &ctx->b_to, &ctx->b_pco, &ctx->b_Xo, &ctx->b_xco, &ctx->b_res};
     if (ctx->o_pinned) cudaFreeHost(ctx->o_pinned);
     for (DevBuf *b : bufs) b->release();
     ctx->l2.release();
@@ -1137,6 +1141,86 @@ int mvs_pnp_solve_batch(mvs_ctx *ctx, const double *world, const double *image, 
                         mvs_pnp_result *results, uint8_t *inlier_mask)
 {
     return pnp_impl(ctx, world, image, counts, n_problems, K, params, samples, results, inlier_mask, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------ bundle adjustment
+int mvs_ba_solve_batch(mvs_ctx *ctx, int n_problems, const double K[9],
+                       const int32_t *n_frames, const int32_t *n_points, const int32_t *n_obs,
+                       const double *pose_R, const double *pose_t, const double *pose_prior_cov,
+                       const double *points, const double *point_prior_cov, const mvs_ba_observation *obs,
+                       const mvs_ba_params *params,
+                       double *pose_R_out, double *pose_t_out, double *pose_cov_out,
+                       double *points_out, double *point_cov_out, mvs_ba_result *results)
+{
+    if (!ctx) return MVS_E_BAD_ARG;
+    if (n_problems < 1 || !K || !n_frames || !n_points || !n_obs || !pose_R || !pose_t || !pose_prior_cov || !results)
+        return fail(ctx, MVS_E_BAD_ARG, "ba_solve: null argument or no problem");
+    std::vector<int32_t> foff(n_problems + 1, 0), poff(n_problems + 1, 0), ooff(n_problems + 1, 0);
+    for (int i = 0; i < n_problems; ++i) {
+        if (n_frames[i] < 1 || n_points[i] < 0 || n_obs[i] < 0) return fail(ctx, MVS_E_BAD_ARG, "ba_solve: bad problem size");
+        if (n_frames[i] > 2) return fail(ctx, MVS_E_UNSUPPORTED, "ba_solve: more than 2 frames in a problem");
+        if ((int64_t)poff[i] + n_points[i] > 0x7FFFFFFF || (int64_t)ooff[i] + n_obs[i] > 0x7FFFFFFF)
+            return fail(ctx, MVS_E_UNSUPPORTED, "ba_solve: more than 2^31 points or observations");
+        foff[i + 1] = foff[i] + n_frames[i]; poff[i + 1] = poff[i] + n_points[i]; ooff[i + 1] = ooff[i] + n_obs[i];
+    }
+    const size_t NF = (size_t)foff[n_problems], NP = (size_t)poff[n_problems], NO = (size_t)ooff[n_problems];
+    if ((NP && (!points || !point_prior_cov)) || (NO && !obs)) return fail(ctx, MVS_E_BAD_ARG, "ba_solve: null points or observations");
+    // observations grouped by point (counting sort per problem; order within a point is the caller's)
+    std::vector<mvs_ba_observation> sorted(NO);
+    std::vector<int32_t> pobs(NP + 1, 0);
+    for (int i = 0; i < n_problems; ++i) {
+        const int P = n_points[i], F = n_frames[i];
+        for (int o = ooff[i]; o < ooff[i + 1]; ++o) {
+            if (obs[o].point < 0 || obs[o].point >= P || obs[o].frame < 0 || obs[o].frame >= F)
+                return fail(ctx, MVS_E_BAD_ARG, "ba_solve: observation refers to a frame or point outside its problem");
+            ++pobs[(size_t)poff[i] + obs[o].point + 1];
+        }
+    }
+    for (size_t p = 0; p < NP; ++p) pobs[p + 1] += pobs[p];
+    {
+        std::vector<int32_t> at(pobs.begin(), pobs.end() - 1);
+        for (int i = 0; i < n_problems; ++i)
+            for (int o = ooff[i]; o < ooff[i + 1]; ++o) sorted[(size_t)at[(size_t)poff[i] + obs[o].point]++] = obs[o];
+    }
+    CK(cudaSetDevice(ctx->device));
+    auto up = [&](DevBuf &b, const void *src, size_t bytes) -> cudaError_t {
+        cudaError_t e = b.ensure(std::max<size_t>(bytes, 8));
+        if (e != cudaSuccess || !bytes) return e;
+        return cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    };
+    CK(up(ctx->b_foff, foff.data(), foff.size() * 4)); CK(up(ctx->b_poff, poff.data(), poff.size() * 4));
+    CK(up(ctx->b_R, pose_R, NF * 72)); CK(up(ctx->b_t, pose_t, NF * 24)); CK(up(ctx->b_pc, pose_prior_cov, NF * 288));
+    CK(up(ctx->b_X, points, NP * 24)); CK(up(ctx->b_xc, point_prior_cov, NP * 72));
+    CK(up(ctx->b_obs, sorted.data(), NO * sizeof(mvs_ba_observation))); CK(up(ctx->b_ooff, pobs.data(), pobs.size() * 4));
+    CK(ctx->b_ws.ensure(std::max<size_t>(NP, 1) * 48 * 8));
+    CK(ctx->b_Ro.ensure(NF * 72)); CK(ctx->b_to.ensure(NF * 24)); CK(ctx->b_pco.ensure(NF * 288));
+    CK(ctx->b_Xo.ensure(std::max<size_t>(NP, 1) * 24)); CK(ctx->b_xco.ensure(std::max<size_t>(NP, 1) * 72));
+    CK(ctx->b_res.ensure((size_t)n_problems * sizeof(mvs_ba_result)));
+    BaArgs a{};
+    a.fx = K[0]; a.fy = K[4]; a.sk = K[1]; a.u0 = K[2]; a.v0 = K[5];
+    a.frame_off = ctx->b_foff.as<int32_t>(); a.point_off = ctx->b_poff.as<int32_t>();
+    a.pose_R = ctx->b_R.as<double>(); a.pose_t = ctx->b_t.as<double>(); a.pose_prior_cov = ctx->b_pc.as<double>();
+    a.points = ctx->b_X.as<double>(); a.point_prior_cov = ctx->b_xc.as<double>();
+    a.obs = ctx->b_obs.as<mvs_ba_observation>(); a.point_obs_off = ctx->b_ooff.as<int32_t>();
+    a.ws = ctx->b_ws.as<double>();
+    a.pose_R_out = ctx->b_Ro.as<double>(); a.pose_t_out = ctx->b_to.as<double>(); a.pose_cov_out = ctx->b_pco.as<double>();
+    a.points_out = ctx->b_Xo.as<double>(); a.point_cov_out = ctx->b_xco.as<double>();
+    a.results = ctx->b_res.as<mvs_ba_result>();
+    a.max_iter = params && params->max_iterations > 0 ? params->max_iterations : 100;
+    a.lambda0 = params && params->lambda_initial > 0 ? params->lambda_initial : 1e-5;
+    a.rel_tol = params && params->relative_tolerance > 0 ? params->relative_tolerance : 1e-13;
+    {
+        StageTimer t(ctx, MVS_STAGE_BA);
+        CK(launch_ba(a, n_problems, ctx->stream));
+    }
+    CK(cudaMemcpyAsync(results, ctx->b_res.p, (size_t)n_problems * sizeof(mvs_ba_result), cudaMemcpyDeviceToHost, ctx->stream));
+    if (pose_R_out) CK(cudaMemcpyAsync(pose_R_out, ctx->b_Ro.p, NF * 72, cudaMemcpyDeviceToHost, ctx->stream));
+    if (pose_t_out) CK(cudaMemcpyAsync(pose_t_out, ctx->b_to.p, NF * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    if (pose_cov_out) CK(cudaMemcpyAsync(pose_cov_out, ctx->b_pco.p, NF * 288, cudaMemcpyDeviceToHost, ctx->stream));
+    if (points_out && NP) CK(cudaMemcpyAsync(points_out, ctx->b_Xo.p, NP * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    if (point_cov_out && NP) CK(cudaMemcpyAsync(point_cov_out, ctx->b_xco.p, NP * 72, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MVS_OK;
 }
 
 }  // extern "C"
