@@ -1,9 +1,10 @@
-// image-pair.hpp — ImagePair construction (reference source/front-end/image-pair.hpp:8-84,
-// image-pair.cpp:30-71,115-174) and its batched form.  refine()/update() (GTSAM) are outside the hot path.
+// image-pair.hpp — ImagePair (reference source/front-end/image-pair.hpp:8-84, image-pair.cpp:30-237): construction
+// (match + reconstruct) with its batched form, refine() and update().
 #pragma once
 #include <algorithm>
 #include <memory>
 
+#include "ba.hpp"
 #include "sfm.hpp"
 #include "visual-feature.hpp"
 
@@ -23,7 +24,7 @@ public:
     };
     struct Params {
         ScalarType max_match_inlier_distance = 10;      // image-pair.cpp:22-23
-        bool refine_structure_in_constructor = false;   // not supported here (GTSAM)
+        bool refine_structure_in_constructor = false;   // image-pair.cpp:24-25
     };
     static Params get_default_params() { return Params(); }
 
@@ -33,6 +34,42 @@ public:
     {
         std::vector<ImagePair> one = solve_batch({base_frame_, pair_frame_}, {{0, 1}}, K, params);
         *this = std::move(one[0]);
+        if (valid && params.refine_structure_in_constructor) refine();   // image-pair.cpp:62-70
+    }
+
+    /** image-pair.cpp:176-237: two-view bundle adjustment of the pair pose and the matched points (sfm_refine). */
+    bool refine()
+    {
+        if (!valid) throw b200::Error(MVS_E_BAD_ARG, "ImagePair::refine: invalid pair (image-pair.cpp:178)");
+        const auto e1 = base_frame->visual_feature.get_point_estimates(), e2 = pair_frame->visual_feature.get_point_estimates();
+        std::vector<Point2Estimate> b, p;
+        std::vector<Point3> pts;
+        for (const auto &mp : matched_points) { b.push_back(e1[mp.vf_idx_in_base]); p.push_back(e2[mp.vf_idx_in_pair]); pts.push_back(mp.position); }
+        TransformationEstimate T;
+        std::vector<Point3Estimate> pe;
+        valid = sfm_refine(b, p, m_K, T_pair_to_base, pts, T, pe, error);
+        if (valid) {
+            T_pair_to_base = T.mean();
+            T_pair_to_base_covar = T.covar();
+            matched_points_covar.clear();
+            for (size_t i = 0; i < matched_points.size(); ++i) { matched_points[i].position = pe[i].mean(); matched_points_covar.push_back(pe[i].covar()); }
+            refined = true;
+        }
+        return valid;
+    }
+
+    /** image-pair.cpp:77-113: does @p new_frame make a better pair with base_frame?  Replaces *this if so. */
+    bool update(const FramePtr &new_frame)
+    {
+        if (new_frame->id == base_frame->id || new_frame->id == pair_frame->id) return false;
+        Params light = m_params;
+        light.refine_structure_in_constructor = false;
+        ImagePair candidate(base_frame, new_frame, m_K, light);
+        if (!candidate.valid) return false;
+        if (candidate.match_inlier_count < match_inlier_count || candidate.match_inlier_ssd < match_inlier_ssd) return false;
+        candidate.refine();
+        if (candidate.error < error) { std::swap(*this, candidate); return true; }
+        return false;
     }
 
     /** Many (base, pair) constructions in one device pass: frames[i] uploaded once, pairs index into it. */
@@ -70,6 +107,7 @@ public:
         out.reserve(np);
         for (int i = 0; i < np; ++i) {
             ImagePair ip;
+            ip.m_K = K; ip.m_params = params;
             ip.base_frame = frames[pairs[i].first];
             ip.pair_frame = frames[pairs[i].second];
             ip.status = res[i].status;
@@ -99,9 +137,16 @@ public:
     uint32_t match_inlier_ssd = 0;
     Transformation T_pair_to_base;
     std::vector<MatchedPoint> matched_points;
+    // available after refine() (image-pair.hpp:66-69)
+    bool refined = false;
+    ScalarType error = infinity;
+    TransformationUncertainty T_pair_to_base_covar;
+    std::vector<Point3Uncertainty> matched_points_covar;
 
 private:
     ImagePair() = default;
+    CameraIntrinsics m_K;
+    Params m_params;
 };
 
 }  // namespace mvSLAM

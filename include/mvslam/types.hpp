@@ -96,6 +96,30 @@ private:
 };
 using Transformation = SE3;
 
+// StateEstimate<Mean, Covar> (source/math/state-estimate.hpp:6-60) and the aliases of source/base/data-type.hpp:20-29
+template <typename MeanType, typename CovarType>
+class StateEstimate {
+public:
+    StateEstimate() = default;
+    StateEstimate(const MeanType &mean, const CovarType &covar) : _mean(mean), _covar(covar) {}
+    const MeanType &mean() const { return _mean; }
+    const CovarType &covar() const { return _covar; }
+private:
+    MeanType _mean{};
+    CovarType _covar{};
+};
+struct Point2 { ScalarType v[2] = {0, 0}; ScalarType &operator[](size_t i) { return v[i]; } const ScalarType &operator[](size_t i) const { return v[i]; } };
+struct Matrix2Type { ScalarType m[4] = {0, 0, 0, 0}; ScalarType &operator()(size_t r, size_t c) { return m[r * 2 + c]; } const ScalarType &operator()(size_t r, size_t c) const { return m[r * 2 + c]; } };
+struct Matrix6Type { ScalarType m[36] = {}; ScalarType &operator()(size_t r, size_t c) { return m[r * 6 + c]; } const ScalarType &operator()(size_t r, size_t c) const { return m[r * 6 + c]; } };
+using TransformationUncertainty = Matrix6Type;
+using TransformationEstimate = StateEstimate<Transformation, TransformationUncertainty>;
+using Point3Uncertainty = Matrix3Type;
+using Point3Estimate = StateEstimate<Point3, Point3Uncertainty>;
+using Point2Uncertainty = Matrix2Type;
+using Point2Estimate = StateEstimate<Point2, Point2Uncertainty>;
+namespace Id { using Type = uint64_t; }
+using PointIdToPoint2Estimate = std::unordered_map<Id::Type, Point2Estimate>;
+
 namespace b200 {
 
 struct Error : std::runtime_error {

@@ -122,6 +122,19 @@ public:
         for (const auto &kp : m_keypoints) r.emplace_back(kp.pt.x, kp.pt.y);
         return r;
     }
+    /** visual-feature.cpp:192-207: ORB keypoint uncertainty, standard deviation 2^octave * 0.5 pixels */
+    std::vector<Point2Estimate> get_point_estimates() const
+    {
+        std::vector<Point2Estimate> r;
+        r.reserve(m_keypoints.size());
+        for (const auto &kp : m_keypoints) {
+            const ScalarType sd = static_cast<ScalarType>(1 << kp.octave) * 0.5;
+            Point2 mu; mu[0] = kp.pt.x; mu[1] = kp.pt.y;
+            Matrix2Type C; C(0, 0) = C(1, 1) = sd * sd;
+            r.emplace_back(mu, C);
+        }
+        return r;
+    }
     bool valid() const { return size() > 0 && m_image_width > 0 && m_image_height > 0; }
 
 private:

@@ -8,6 +8,7 @@
 
 #include <mvslam/image-pair.hpp>
 #include <mvslam/pnp.hpp>
+#include <mvslam/ba.hpp>
 
 using namespace mvSLAM;
 
@@ -103,6 +104,14 @@ static bool image_pair_and_matcher()
     ASSERT_TRUE(ip.match_inlier_count > (uint32_t)(0.9 * n));
     ASSERT_EQUAL(ip.T_pair_to_base.translation()[0], 1.0, 1e-3);     // camera 2 sits at +x; |t| = 1
     for (const auto &mp : ip.matched_points) ASSERT_TRUE(perm[mp.vf_idx_in_base] == (int)mp.vf_idx_in_pair);
+    {   // ImagePair::refine (image-pair.cpp:176-237): two-view bundle adjustment keeps the solution, adds covariances
+        ImagePair refined = ip;
+        ASSERT_TRUE(refined.refine() && refined.refined);
+        ASSERT_TRUE(refined.error >= 0 && refined.error < 1.0);
+        ASSERT_EQUAL(refined.T_pair_to_base.translation()[0], 1.0, 2e-2);
+        ASSERT_TRUE(refined.matched_points_covar.size() == refined.matched_points.size());
+        for (int k = 0; k < 6; ++k) ASSERT_TRUE(refined.T_pair_to_base_covar(k, k) > 0);
+    }
     auto batch = ImagePair::solve_batch({f1, f2}, {{0, 1}, {1, 0}}, K, ImagePair::get_default_params());
     ASSERT_TRUE(batch.size() == 2 && batch[0].valid && batch[1].valid);
     ASSERT_EQUAL(batch[1].T_pair_to_base.translation()[0], -1.0, 1e-3);
@@ -127,6 +136,48 @@ static bool pnp_solve_cube()
     ASSERT_EQUAL(pose.translation()[1], 0.0, 1e-3);
     ASSERT_EQUAL(pose.translation()[2], 0.0, 1e-3);
     for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) ASSERT_EQUAL(pose.rotation().get_matrix()(r, c), r == c ? 1.0 : 0.0, 1e-3);
+    return true;
+}
+
+// test/test-sfm.cpp:157-290 (sfm_refine_L_shape): noisy observations, guesses and points; everything back within 0.025
+static bool sfm_refine_L_shape()
+{
+    const double tol = 0.025, noise = 5e-3;
+    std::mt19937 rng(3);
+    std::normal_distribution<double> g(0.0, 1.0);
+    const double raw[8][3] = {{1, 0, 0}, {0, 0, 0}, {0, 2, 0}, {1, 0, 3}, {0, 0, 3}, {0, 2, 3}, {0.5, 0, 1.5}, {0, 1, 1.5}};
+    const double cy = std::cos(1.5), sy = std::sin(1.5), cp = std::cos(0.7), sp = std::sin(0.7);
+    std::vector<Point3> X, Xg;
+    std::vector<Point2Estimate> p1, p2;
+    Matrix2Type C; C(0, 0) = C(1, 1) = noise * noise;
+    for (auto &r : raw) {   // 0.5 * Rz(1.5) Ry(0.7) p + (0.6, 0, 3)
+        const double a = cp * r[0] + sp * r[2], b = r[1], c = -sp * r[0] + cp * r[2];
+        Point3 p(0.5 * (cy * a - sy * b) + 0.6, 0.5 * (sy * a + cy * b), 0.5 * c + 3.0);
+        X.push_back(p);
+        Xg.emplace_back(p[0] + 5e-3 * g(rng), p[1] + 5e-3 * g(rng), p[2] + 5e-3 * g(rng));
+        Point2 a1, a2;
+        a1[0] = p[0] / p[2] + noise * g(rng); a1[1] = p[1] / p[2] + noise * g(rng);
+        a2[0] = (p[0] - 1.0) / p[2] + noise * g(rng); a2[1] = p[1] / p[2] + noise * g(rng);
+        p1.emplace_back(a1, C); p2.emplace_back(a2, C);
+    }
+    Transformation guess(SO3(Matrix3Type::Identity()), Vector3Type(1.0 + 4e-3, -3e-3, 5e-3));
+    TransformationEstimate pose;
+    std::vector<Point3Estimate> pts;
+    ScalarType err = -1;
+    ASSERT_TRUE(sfm_refine(p1, p2, Matrix3Type::Identity(), guess, Xg, pose, pts, err));
+    ASSERT_TRUE(err >= 0 && pts.size() == X.size());
+    ASSERT_EQUAL(pose.mean().translation()[0], 1.0, tol);
+    ASSERT_EQUAL(pose.mean().translation()[1], 0.0, tol);
+    ASSERT_EQUAL(pose.mean().translation()[2], 0.0, tol);
+    for (size_t i = 0; i < X.size(); ++i) for (int k = 0; k < 3; ++k) ASSERT_EQUAL(pts[i].mean()[k], X[i][k], tol);
+    for (int k = 0; k < 6; ++k) ASSERT_TRUE(pose.covar()(k, k) > 0);
+    // pnp_refine on the same scene: camera 2 from the noisy points and its observations (test-pnp.cpp:65-160)
+    std::vector<Point3Estimate> world;
+    Matrix3Type Cw; Cw(0, 0) = Cw(1, 1) = Cw(2, 2) = 25e-6;
+    for (auto &p : Xg) world.emplace_back(p, Cw);
+    TransformationEstimate cam;
+    ASSERT_TRUE(pnp_refine(world, p2, Matrix3Type::Identity(), guess, cam, err));
+    ASSERT_EQUAL(cam.mean().translation()[0], 1.0, tol);
     return true;
 }
 
@@ -172,7 +223,8 @@ int main()
                                                            {"sfm_solve_L_shape", sfm_solve_L_shape},
                                                            {"image_pair_and_matcher", image_pair_and_matcher},
                                                            {"extract_and_match", extract_and_match},
-                                                           {"pnp_solve_cube", pnp_solve_cube}};
+                                                           {"pnp_solve_cube", pnp_solve_cube},
+                                                           {"sfm_refine_L_shape", sfm_refine_L_shape}};
     for (auto &t : tests) {
         bool ok = false;
         try { ok = t.fn(); } catch (const std::exception &e) { std::printf("exception: %s\n", e.what()); }
