@@ -356,14 +356,14 @@ def test_profile_and_launch_counters(ctx, tsukuba):
 
 def test_cpp_adapters_reference_signatures():
     """The C++ headers under include/mvslam/ (VisualFeature::match_visual_features, sfm_solve, sfm_triangulate,
-    FundamentalMatrixEstimatorRANSAC, ImagePair) driven like the reference's own tests (tests/cpp/test_adapters.cpp)."""
+    FundamentalMatrixEstimatorRANSAC, ImagePair incl. refine, VisualFeature::extract, pnp_solve, sfm_refine, pnp_refine) driven like the reference's own tests (tests/cpp/test_adapters.cpp)."""
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     exe = os.path.join(root, "tests", "cpp", "test_adapters")
     assert os.path.exists(exe), "run __graft_entry__.build() first"
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert r.stdout.count("PASSED") == 3
+    assert r.stdout.count("PASSED") == 6 and "FAILED" not in r.stdout
 
 
 def test_two_gpu_sharded_equals_single_gpu(tmp_path, tsukuba):
