@@ -503,11 +503,13 @@ def main():
     if world == 1 and args.workload == "tsukuba" and not args.no_extras:
         extract = extraction_extra(ctx, stream, cpu=not args.no_cpu_baseline)
 
-    pnp = None
+    pnp = ba = None
     if world == 1 and args.workload == "tsukuba" and not args.no_extras:
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import pnp_bench                                   # pnp_solve = cv::solvePnPRansac(P3P)
         pnp = pnp_bench.run(ctx, 1024, 500, 100, steps=5, cpu=not args.no_cpu_baseline)
+        import ba_bench                                    # sfm_refine-shaped bundle adjustment
+        ba = ba_bench.run(ctx, 512, 200, steps=3, cpu=not args.no_cpu_baseline)
 
     n_job = int(cfg.get("pairs_total", B * world))      # pairs all ranks processed per step
     value = n_job * args.steps / (total_ms * 1e-3)
@@ -521,7 +523,7 @@ def main():
                 e2e=dict(value=n_job / (e2e_ms * 1e-3), unit="pairs/s", h2d_bytes_per_step=int(h2d),
                          d2h_bytes_per_step=int(d2h), ms_per_step=e2e_ms),
                 gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, bounded_search=bounded_extra,
-                extraction=extract, pnp=pnp,
+                extraction=extract, pnp=pnp, bundle_adjustment=ba,
                 ransac=dict(hyp_pt_evals_per_s=evals / (score_ms * 1e-3) if score_ms > 0 else None,
                             evals_per_step=evals, score_ms_per_step=score_ms,
                             hypotheses_per_s=params["H"] * int(scored.sum()) / max(prof["hypotheses"][0] / args.steps * 1e-3, 1e-12)))

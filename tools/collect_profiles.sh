@@ -14,6 +14,8 @@ python tools/orb_bench.py 1 2000 10 > gpurun_out/orb_bench1_$R.json 2>/dev/null
 python tools/orb_bench.py 64 500 10 > gpurun_out/orb_bench500_$R.json 2>/dev/null
 python tools/pnp_bench.py 1024 500 100 > gpurun_out/pnp_bench_$R.json 2>/dev/null
 python tools/pnp_bench.py 64 5000 4096 > gpurun_out/pnp_bench_big_$R.json 2>/dev/null
+python tools/ba_bench.py 1024 200 > gpurun_out/ba_bench_$R.json 2>/dev/null
+python tools/ba_bench.py 256 1000 > gpurun_out/ba_bench_big_$R.json 2>/dev/null
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras"
 $CMD > gpurun_out/plain_$R.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$R.csv $CMD > gpurun_out/ncu_launch_$R.log 2>&1

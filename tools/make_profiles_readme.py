@@ -76,6 +76,17 @@ if pb:
             L.append(f"| {b_['problems']} x {b_['points_per_problem']} x {b_['hypotheses']} | {b_['problems_per_s_device']:,.0f} | "
                      f"{b_['e2e_problems_per_s']:,.0f} | {b_['hyp_pt_evals_per_s'] / 1e9:.0f} G | {b_['cv2_solvepnpransac_problems_per_s']:,.0f} |")
     L += ["", f"One problem per call: {pb['single_problem_latency_us']:.0f} us.", ""]
+bb, bbb = load("ba_bench"), load("ba_bench_big")
+if bb:
+    L += ["## SURVEY 8(f) rank 4 — bundle adjustment behind `sfm_refine` / `pnp_refine` (`tools/ba_bench.py`)", "",
+          "Cost 1e-9 relative, poses/points 1e-8, covariances 1e-6 relative against the numpy oracle, which is pinned against scipy "
+          "(tests/test_gpu_ba.py, tests/test_ba_oracle.py); GTSAM parity unpinned.", "",
+          "| two-view problems x points | LM iterations | problems/s (kernel) | problems/s (call with host buffers) | numpy oracle, 1 host thread |", "|---|---|---|---|---|"]
+    for b_ in (bb, bbb):
+        if b_:
+            L.append(f"| {b_['problems']} x {b_['points_per_problem']} | {b_['mean_lm_iterations']:.1f} | {b_['problems_per_s_device']:,.0f} | "
+                     f"{b_['e2e_problems_per_s']:,.0f} | {b_['cpu_oracle_problems_per_s']:.1f} |")
+    L += ["", f"One problem per call: {bb['single_problem_latency_us']:.0f} us.", ""]
 if ub:
     L += ["## Measured instruction-pipe ceilings (`tools/ubench`)", "", "| pipe | ops/s (chip) | per clk per SM @1.965 GHz |", "|---|---|---|"]
     for k in ("popc_per_s", "lop3_per_s", "vimnmx_per_s", "iadd3_per_s", "dfma_per_s", "dadd_per_s", "dmul_per_s"):
