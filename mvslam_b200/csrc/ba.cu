@@ -479,16 +479,19 @@ ba_solve_kernel(BaArgs a)
             for (int r = 0; r < 3; ++r)
                 for (int c = 0; c < n; ++c) T[r * n + c] = Vf[r * 3] * w[9 + c * 3] + Vf[r * 3 + 1] * w[9 + c * 3 + 1] + Vf[r * 3 + 2] * w[9 + c * 3 + 2];
             double *out = a.point_cov_out + (size_t)(p0 + j) * 9;
-            for (int r = 0; r < 3; ++r)
-                for (int c = 0; c < 3; ++c) {
-                    double s = Vf[r * 3 + c];
-                    for (int k = 0; k < n; ++k) {
-                        double tc = 0.0;
-                        for (int q = 0; q < n; ++q) tc += s_S[k * n + q] * T[c * n + q];
-                        s += T[r * n + k] * tc;
-                    }
-                    out[r * 3 + c] = s;
+            for (int c = 0; c < 3; ++c) {
+                double m[12];                               // column c of C T^T
+                for (int k = 0; k < n; ++k) {
+                    double tc = 0.0;
+                    for (int q = 0; q < n; ++q) tc += s_S[k * n + q] * T[c * n + q];
+                    m[k] = tc;
                 }
+                for (int r = 0; r < 3; ++r) {
+                    double v = Vf[r * 3 + c];
+                    for (int k = 0; k < n; ++k) v += T[r * n + k] * m[k];
+                    out[r * 3 + c] = v;
+                }
+            }
         }
     }
 }

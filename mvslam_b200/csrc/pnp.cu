@@ -6,7 +6,7 @@
 //   Q1 pnp_hypotheses_kernel      thread = hypothesis: seeded 4-point sample, P3P on three points (Grunert's quartic by
 //                                 Ferrari's method, resolvent cubic by safeguarded Newton), 4th point picks the pose
 //   Q2 pnp_score_kernel           thread = hypothesis (pose in registers), points staged in shared memory tiles,
-//                                 squared reprojection error <= threshold^2, counts per tile
+//                                 squared reprojection error <= threshold^2 (division-free form), counts per tile
 //   Q3 pnp_select_refine_kernel   CTA = problem: first best count, inlier mask, Gauss-Newton on the reprojection
 //                                 error over the inliers (block-reduced 6x6 normal equations, Cholesky), pose inverse
 //
@@ -146,6 +146,18 @@ __device__ __forceinline__ double reproj_err2(const double R[9], const double t[
     return du * du + dv * dv;
 }
 
+// consensus test |K pi(R X + t) - x|^2 <= thr2 multiplied through by z^2 (no division):
+// (fx x + (cx - u) z)^2 + (fy y + (cy - v) z)^2 <= thr2 z^2
+__device__ __forceinline__ bool reproj_inlier(const double R[9], const double t[3], const double X[3], double u, double v,
+                                              double fx, double fy, double cx, double cy, double thr2)
+{
+    const double x = R[0] * X[0] + R[1] * X[1] + R[2] * X[2] + t[0];
+    const double y = R[3] * X[0] + R[4] * X[1] + R[5] * X[2] + t[1];
+    const double z = R[6] * X[0] + R[7] * X[1] + R[8] * X[2] + t[2];
+    const double du = fx * x + (cx - u) * z, dv = fy * y + (cy - v) * z;
+    return du * du + dv * dv <= thr2 * (z * z);
+}
+
 // 4 correspondences -> pose (world to camera): P3P on the first three, the fourth picks among the real solutions
 __device__ bool pnp_hypothesis(const double *world, const double *image, const uint32_t idx[4], double fx, double fy,
                                double cx, double cy, double R[9], double t[3])
@@ -266,7 +278,7 @@ pnp_score_kernel(PnpArgs a)
         for (int k = 0; k < 9; ++k) R[k] = P[k];
         for (int k = 0; k < 3; ++k) t[k] = P[9 + k];
         for (int i = 0; i < m; ++i)
-            cnt += reproj_err2(R, t, sp[i], sp[i][3], sp[i][4], a.fx, a.fy, a.cx, a.cy) <= a.thr2;
+            cnt += reproj_inlier(R, t, sp[i], sp[i][3], sp[i][4], a.fx, a.fy, a.cx, a.cy, a.thr2);
     }
     a.part_count[((size_t)prob * a.tiles + tile) * a.H + h] = cnt;
 }
@@ -274,24 +286,12 @@ pnp_score_kernel(PnpArgs a)
 // ------------------------------------------------------------------------------------------ Q3
 constexpr int PNP_SEL_THREADS = 256;
 
-__device__ __forceinline__ double block_sum(double v, double *scratch /*[8]*/)
-{
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double r = 0.0;
-    for (int w = 0; w < PNP_SEL_THREADS / 32; ++w) r += scratch[w];
-    return r;
-}
-
 __global__ void __launch_bounds__(PNP_SEL_THREADS)
 pnp_select_refine_kernel(PnpArgs a)
 {
     __shared__ unsigned long long s_best;
     __shared__ double s_pose[12];
-    __shared__ double s_red[8];
+    __shared__ double s_part[(PNP_SEL_THREADS / 32) * 27];
     __shared__ double s_sys[27];
     __shared__ int s_stop;
     const int prob = blockIdx.x;
@@ -333,7 +333,7 @@ pnp_select_refine_kernel(PnpArgs a)
     const double *world = a.world + 3 * (size_t)off, *image = a.image + 2 * (size_t)off;
     // inlier flags of the winning minimal-sample pose (what solvePnPRansac returns as inliers)
     for (int i = threadIdx.x; i < n; i += PNP_SEL_THREADS) {
-        const bool in = reproj_err2(R, t, world + 3 * (size_t)i, image[2 * (size_t)i], image[2 * (size_t)i + 1], a.fx, a.fy, a.cx, a.cy) <= a.thr2;
+        const bool in = reproj_inlier(R, t, world + 3 * (size_t)i, image[2 * (size_t)i], image[2 * (size_t)i + 1], a.fx, a.fy, a.cx, a.cy, a.thr2);
         a.mask_ws[off + i] = in ? 1 : 0;
         if (a.mask) a.mask[off + i] = in ? 1 : 0;
     }
@@ -363,9 +363,19 @@ pnp_select_refine_kernel(PnpArgs a)
 #pragma unroll
             for (int r = 0; r < 6; ++r) acc[21 + r] += Ju[r] * ru + Jv[r] * rv;
         }
+        // 27 sums: shuffle tree inside each warp, one shared row per warp, summed in warp order by 27 threads
+#pragma unroll
         for (int k = 0; k < 27; ++k) {
-            const double s = block_sum(acc[k], s_red);
-            if (threadIdx.x == 0) s_sys[k] = s;
+            double v = acc[k];
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+            if ((threadIdx.x & 31) == 0) s_part[(threadIdx.x >> 5) * 27 + k] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < 27) {
+            double v = 0.0;
+            for (int w = 0; w < PNP_SEL_THREADS / 32; ++w) v += s_part[w * 27 + threadIdx.x];
+            s_sys[threadIdx.x] = v;
         }
         __syncthreads();
         if (threadIdx.x == 0) {

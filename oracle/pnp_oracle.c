@@ -7,7 +7,8 @@
  * /root/reference, so this file restates the published algorithm of that call:
  *   - minimal samples of 4 correspondences; P3P on the first three (Grunert's quartic, Haralick et al. 1994,
  *     solved in closed form by Ferrari's method), the fourth picks among the up to four poses by reprojection error;
- *   - consensus: squared reprojection error <= reprojectionError^2 (fx, fy, cx, cy of K; no distortion);
+ *   - consensus: squared reprojection error <= reprojectionError^2 (fx, fy, cx, cy of K; no distortion), evaluated
+ *     in the division-free form (both sides times z^2);
  *   - the model with most inliers wins (first one on ties);
  *   - final pose on the inliers.  OpenCV runs EPnP there; this restatement runs Gauss-Newton on the reprojection
  *     error from the winning P3P pose (the maximum-likelihood refinement EPnP approximates).
@@ -232,12 +233,24 @@ int orc_pnp_hypothesis(const double *world, const double *image, const uint32_t 
     return 1;
 }
 
+/* consensus test |K pi(R X + t) - x|^2 <= thr2, multiplied through by z^2 so that no division is needed:
+ * (fx x + (cx - u) z)^2 + (fy y + (cy - v) z)^2 <= thr2 z^2 */
+static inline int reproj_inlier(const double R[9], const double t[3], const double X[3], const double xy[2],
+                                double fx, double fy, double cx, double cy, double thr2)
+{
+    const double x = R[0] * X[0] + R[1] * X[1] + R[2] * X[2] + t[0];
+    const double y = R[3] * X[0] + R[4] * X[1] + R[5] * X[2] + t[1];
+    const double z = R[6] * X[0] + R[7] * X[1] + R[8] * X[2] + t[2];
+    const double du = fx * x + (cx - xy[0]) * z, dv = fy * y + (cy - xy[1]) * z;
+    return du * du + dv * dv <= thr2 * (z * z);
+}
+
 int orc_pnp_count_inliers(const double *world, const double *image, int n, const double K[9], const double R[9],
                           const double t[3], double thr2, uint8_t *mask)
 {
     int cnt = 0;
     for (int i = 0; i < n; ++i) {
-        const int in = reproj_err2(R, t, world + 3 * (size_t)i, image + 2 * (size_t)i, K[0], K[4], K[2], K[5]) <= thr2;
+        const int in = reproj_inlier(R, t, world + 3 * (size_t)i, image + 2 * (size_t)i, K[0], K[4], K[2], K[5], thr2);
         if (mask) mask[i] = (uint8_t)in;
         cnt += in;
     }
