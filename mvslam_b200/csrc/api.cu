@@ -978,7 +978,6 @@ static int orb_extract_impl(mvs_ctx *ctx, const uint8_t *const *h_images, const 
     const size_t pin_need = (size_t)chunk * (kOrbLevels + 1);
     if (ctx->o_pinned_cap < pin_need) {
         if (ctx->o_pinned) cudaFreeHost(ctx->o_pinned);
-    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
         ctx->o_pinned = nullptr; ctx->o_pinned_cap = 0;
         CK(cudaMallocHost((void **)&ctx->o_pinned, pin_need * sizeof(int32_t)));
         ctx->o_pinned_cap = pin_need;
@@ -1015,12 +1014,13 @@ static int orb_extract_impl(mvs_ctx *ctx, const uint8_t *const *h_images, const 
         {
             StageTimer t(ctx, MVS_STAGE_ORB_PYRAMID);
             launch_orb_pyramid(g, b, stage, stride, n, ctx->stream);
+            CK(cudaGetLastError());
         }
-        { StageTimer t(ctx, MVS_STAGE_ORB_FAST, g.fast_tiles ? 1 : 0); launch_orb_fast(g, b, n, ctx->stream); }
-        { StageTimer t(ctx, MVS_STAGE_ORB_HARRIS); launch_orb_harris(g, b, n, ctx->stream); }
-        { StageTimer t(ctx, MVS_STAGE_ORB_SELECT); launch_orb_select(g, b, n, ctx->stream); }
+        { StageTimer t(ctx, MVS_STAGE_ORB_FAST, g.fast_tiles ? 1 : 0); launch_orb_fast(g, b, n, ctx->stream); CK(cudaGetLastError()); }
+        { StageTimer t(ctx, MVS_STAGE_ORB_HARRIS); launch_orb_harris(g, b, n, ctx->stream); CK(cudaGetLastError()); }
+        { StageTimer t(ctx, MVS_STAGE_ORB_SELECT); launch_orb_select(g, b, n, ctx->stream); CK(cudaGetLastError()); }
         CK(cudaMemcpyAsync(ctx->o_pinned, b.kept_cnt, (size_t)n * kOrbLevels * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-        { StageTimer t(ctx, MVS_STAGE_ORB_BLUR); launch_orb_blur(g, b, n, ctx->stream); }
+        { StageTimer t(ctx, MVS_STAGE_ORB_BLUR); launch_orb_blur(g, b, n, ctx->stream); CK(cudaGetLastError()); }
         CK(cudaStreamSynchronize(ctx->stream));
         int32_t *off = ctx->o_pinned + (size_t)chunk * kOrbLevels;
         size_t chunk_total = 0;
@@ -1055,6 +1055,7 @@ static int orb_extract_impl(mvs_ctx *ctx, const uint8_t *const *h_images, const 
         {
             StageTimer t(ctx, MVS_STAGE_ORB_DESCRIBE);
             launch_orb_describe(g, b, d, n, most, ctx->stream);
+            CK(cudaGetLastError());
         }
         CK(cudaStreamSynchronize(ctx->stream));   // the pinned offsets are rewritten by the next chunk
         total += chunk_total;
@@ -1162,6 +1163,7 @@ static int pnp_impl(mvs_ctx *ctx, const double *world, const double *image, cons
     {
         StageTimer t(ctx, MVS_STAGE_PNP, 3);
         launch_pnp(a, n_problems, max_n, ctx->stream);
+        CK(cudaGetLastError());
     }
     CK(cudaMemcpyAsync(results, ctx->p_results.p, (size_t)n_problems * sizeof(mvs_pnp_result), cudaMemcpyDeviceToHost, ctx->stream));
     if (inlier_mask && total) CK(cudaMemcpyAsync(inlier_mask, ctx->p_mask.p, total, cudaMemcpyDeviceToHost, ctx->stream));
