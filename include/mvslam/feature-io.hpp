@@ -1,8 +1,10 @@
-// feature-io.hpp — tiny binary container for pre-extracted features and the reference's camera file, so that the
-// C++ tools can run without OpenCV (ORB extraction stays on the host side of the boundary).
-//   file = "MVSF" | int32 n | int32 width | int32 height | n x (float x, float y) | n x 32 descriptor bytes
+// feature-io.hpp — file helpers of the C++ tools, so that they run without OpenCV: a tiny binary container for
+// pre-extracted features, binary PGM (P5) images for VisualFeature::extract, and the reference's camera file.
+//   feature file = "MVSF" | int32 n | int32 width | int32 height | n x (float x, float y) | n x 32 descriptor bytes
 #pragma once
+#include <cctype>
 #include <cstdio>
+#include <cstdlib>
 #include <fstream>
 #include <string>
 
@@ -26,6 +28,33 @@ inline VisualFeature load_visual_feature(const std::string &filename)
     in.read(reinterpret_cast<char *>(desc.data()), (std::streamsize)desc.size());
     if (!in) throw b200::Error(MVS_E_BAD_ARG, "truncated feature file " + filename);
     return VisualFeature(std::move(kps), std::move(desc), w, h);
+}
+
+/** 8-bit binary PGM (P5, maxval 255) -> pixels; the returned ImageGrayscale points into `pixels`. */
+inline ImageGrayscale load_pgm(const std::string &filename, std::vector<uint8_t> &pixels)
+{
+    std::ifstream in(filename, std::ios::binary);
+    std::string magic;
+    int w = 0, h = 0, maxval = 0;
+    auto next_token = [&](std::string &tok) {
+        tok.clear();
+        char c;
+        while (in.get(c)) {
+            if (c == '#') { while (in.get(c) && c != '\n') {} continue; }
+            if (!std::isspace((unsigned char)c)) { tok.push_back(c); break; }
+        }
+        while (in.get(c) && !std::isspace((unsigned char)c)) tok.push_back(c);
+    };
+    std::string tok;
+    next_token(magic);
+    next_token(tok); w = std::atoi(tok.c_str());
+    next_token(tok); h = std::atoi(tok.c_str());
+    next_token(tok); maxval = std::atoi(tok.c_str());
+    if (!in || magic != "P5" || w < 1 || h < 1 || maxval != 255) throw b200::Error(MVS_E_BAD_ARG, "bad PGM file " + filename);
+    pixels.resize((size_t)w * h);
+    in.read(reinterpret_cast<char *>(pixels.data()), (std::streamsize)pixels.size());
+    if (!in) throw b200::Error(MVS_E_BAD_ARG, "truncated PGM file " + filename);
+    return ImageGrayscale(h, w, pixels.data());
 }
 
 /** PinholeCamera::load_from_file (reference source/vision/camera.cpp:105-123): first line "fx fy shear px py". */

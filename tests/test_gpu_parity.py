@@ -501,6 +501,27 @@ def test_cpp_tools_reconstruct_scene_and_vo_pairs(tmp_path, tsukuba, tsukuba_gol
         assert np.allclose(t, [1, 0, 0], atol=1e-3)
 
 
+def test_cpp_vo_tool_from_images(tmp_path):
+    """tools/visual_odometer_pairs fed with the Tsukuba frames themselves (PGM): VisualFeature::extract on the device,
+    then the per-frame pair batches; the 2000-feature run recovers the (I, (1, 0, 0)) motion of test-visual-odometer.cpp:98-102."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "tsu_img")
+    subprocess.run([sys.executable, os.path.join(root, "tools", "export_features.py"), "pgm",
+                    os.path.join(root, "tests", "golden", "tsukuba_gray.npz"), out], check=True)
+    r = subprocess.run([os.path.join(root, "tools", "visual_odometer_pairs"), out, "10", "2000"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    ext = [l for l in r.stdout.splitlines() if "keypoints extracted" in l]
+    assert len(ext) == 5 and "1748 keypoints" in ext[0] and "1759 keypoints" in ext[1]      # cv2.ORB_create(2000) counts
+    fl = [l for l in r.stdout.splitlines() if "pair(s)" in l]
+    assert len(fl) == 4
+    for l in fl:
+        assert "valid=1" in l
+        t = [float(x) for x in l.split("t=(")[1].rstrip(")").split()]
+        assert np.allclose(t, [1, 0, 0], atol=1e-3)
+
+
 def test_frames_append_equals_bulk_upload(ctx, tsukuba):
     """Streaming use (FrameManager::add_frame per image): appended frames behave exactly like a bulk upload."""
     descs = [tsukuba[f"desc{i}"] for i in range(1, 6)]; kps = [tsukuba[f"kp{i}"] for i in range(1, 6)]

@@ -2,8 +2,9 @@
 // for every new frame, the ImagePair constructions that VisualOdometer::add_frame issues
 // (source/front-end/visual-odometer.cpp:140-148) and, while initialising, the re-pairings of the queued base frames
 // with the new frame (visual-odometer.cpp:289-296 -> image-pair.cpp:77-113), submitted as ONE batch per frame.
-// Tracking (PnP) and refinement (GTSAM) are outside the path.  Input directory: camera.config + features.txt
-// (one feature file name per line, see include/mvslam/feature-io.hpp).
+// Input directory: camera.config plus either image.txt (one binary PGM file name per line, like the reference's image.txt:
+// features are extracted on the device by VisualFeature::extract, frame-manager.cpp:114) or features.txt (one
+// pre-extracted feature file per line, see include/mvslam/feature-io.hpp).  Optional 3rd argument: nfeatures.
 #include <chrono>
 #include <cstdio>
 #include <fstream>
@@ -13,19 +14,30 @@
 
 int main(int argc, char **argv)
 {
-    if (argc < 2) { std::printf("Usage: %s <input_directory> [frame_queue_size=10]\n", argv[0]); return 1; }
+    if (argc < 2) { std::printf("Usage: %s <input_directory> [frame_queue_size=10] [nfeatures=500]\n", argv[0]); return 1; }
     const std::string dir(argv[1]);
     const size_t queue_size = argc > 2 ? (size_t)std::stoi(argv[2]) : 10;   // visual-odometer.cpp:71-72
+    const int nfeatures = argc > 3 ? std::stoi(argv[3]) : mvSLAM::VisualFeature::MAX_FEATURE_COUNT;
     try {
         const mvSLAM::CameraIntrinsics K = mvSLAM::load_camera_intrinsics(dir + "/camera.config");
-        std::ifstream list(dir + "/features.txt");
+        std::ifstream list(dir + "/image.txt");
+        const bool from_images = list.good();
+        if (!from_images) { list.close(); list.clear(); list.open(dir + "/features.txt"); }
         std::vector<mvSLAM::FramePtr> frames;
+        std::vector<uint8_t> pixels;
         std::string name;
         const auto params = mvSLAM::ImagePair::get_default_params();   // max_match_inlier_distance = 10
         while (list >> name) {
             auto f = std::make_shared<mvSLAM::Frame>();
             f->id = frames.size();
-            f->visual_feature = mvSLAM::load_visual_feature(dir + "/" + name);
+            if (from_images) {
+                const auto t0 = std::chrono::steady_clock::now();
+                f->visual_feature = mvSLAM::VisualFeature::extract(mvSLAM::load_pgm(dir + "/" + name, pixels), nfeatures);
+                const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+                std::printf("frame %zu: %zu keypoints extracted in %.0f us (incl. reading the file)\n", frames.size(), f->visual_feature.size(), us);
+            } else {
+                f->visual_feature = mvSLAM::load_visual_feature(dir + "/" + name);
+            }
             frames.push_back(f);
             if (frames.size() < 2) continue;
             // (base_k, new) for the queued frames, newest base first == consecutive-frame pair first
