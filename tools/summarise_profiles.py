@@ -48,7 +48,9 @@ lines = [f"# ncu summaries ({R})", "",
 for rep, title in ((f"prof_path_{R}.ncu-rep", "two-view path (bench.py default workload, 1024 Tsukuba pairs, H=1024)"),
                    (f"prof_score_s8k_{R}.ncu-rep", "score_kernel on the S8k workload (64 pairs x 8192 kpts, H=4096, Sampson)"),
                    (f"prof_l2_{R}.ncu-rep", "l2_gemm_topk_kernel, 32768 x 32768 x 64 float descriptors"),
-                   (f"prof_orb_{R}.ncu-rep", "feature extraction (tools/orb_bench.py: 256 Tsukuba frames per call, nfeatures 2000)")):
+                   (f"prof_orb_{R}.ncu-rep", "feature extraction (tools/orb_bench.py: 256 Tsukuba frames per call, nfeatures 2000)"),
+                   (f"prof_pnp_{R}.ncu-rep", "pnp_solve (tools/pnp_bench.py: 1024 problems x 500 points x 100 hypotheses)"),
+                   (f"prof_ba_{R}.ncu-rep", "bundle adjustment (tools/ba_bench.py: 1024 two-view problems x 200 points)")):
     path = os.path.join(G, rep)
     if not os.path.exists(path):
         continue
