@@ -423,6 +423,29 @@ def main():
                              note="mvs_match_params.bounded=1: train descriptors provably beyond the ratio/max_dist decision "
                                   "bound are abandoned after 96 bits; not used for `value`, `e2e` or `roofline`")
 
+    # ---- optional extra ("cross-check off (and on, reported separately)"): same batch, cross_check=1
+    cross_extra = None
+    if args.workload == "s8k" and world == 1 and not args.no_extras:
+        def step_x():
+            for c0 in range(0, B, CH):
+                c1 = min(B, c0 + CH)
+                ctx.pair_batch(pairs[c0:c1], K, out=dict(results=res_t.data_ptr() + c0 * item), enqueue_only=True,
+                               pair_id_base=pair_base + c0, cross_check=True, **kw)
+        keep = res_t.numpy().copy()
+        for _ in range(args.warmup):
+            flush.zero_(); step_x()
+        torch.cuda.synchronize()
+        evx = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for a, b in evx:
+            flush.zero_(); a.record(stream); step_x(); b.record(stream)
+        torch.cuda.synchronize()
+        msx = sum(a.elapsed_time(b) for a, b in evx) / args.steps
+        rx = np.frombuffer(res_t.numpy(), dtype=mvs.RESULT_DTYPE)
+        cross_extra = dict(value=B / (msx * 1e-3), unit="pairs/s", ms_per_step=msx, solved_pairs_per_step=int((rx["status"] == 0).sum()),
+                           mean_matches=float(rx["n_matches"].mean()),
+                           note="cross_check=1: a second kNN pass with the roles swapped, matches kept only when mutual")
+        res_t.numpy()[:] = keep
+
     # ---- end to end through the public call with host buffers (H2D of the frames + D2H of everything)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     upload(); step(out_all); torch.cuda.synchronize()
@@ -525,7 +548,7 @@ def main():
                 e2e=dict(value=n_job / (e2e_ms * 1e-3), unit="pairs/s", h2d_bytes_per_step=int(h2d),
                          d2h_bytes_per_step=int(d2h), ms_per_step=e2e_ms),
                 gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, bounded_search=bounded_extra,
-                extraction=extract, pnp=pnp, bundle_adjustment=ba,
+                extraction=extract, pnp=pnp, bundle_adjustment=ba, cross_check=cross_extra,
                 ransac=dict(hyp_pt_evals_per_s=evals / (score_ms * 1e-3) if score_ms > 0 else None,
                             evals_per_step=evals, score_ms_per_step=score_ms,
                             hypotheses_per_s=params["H"] * int(scored.sum()) / max(prof["hypotheses"][0] / args.steps * 1e-3, 1e-12)))

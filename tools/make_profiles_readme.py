@@ -38,6 +38,10 @@ if s8:
           f"knn at {s8['roofline']['frac']:.3f} of the pipe ceiling; scoring {s8['ransac']['hyp_pt_evals_per_s'] / 1e9:.0f} G evals/s "
           "(FP64 pipe 84 % busy in ncu).", "",
           "Stage times per step (ms): " + ", ".join(f"{k} {v}" for k, v in s8["roofline"]["stage_ms_per_step"].items()), ""]
+    if s8.get("cross_check"):
+        cx = s8["cross_check"]
+        L += [f"With cross-check on (second kNN pass, mutual matches only): {cx['value']:,.0f} pairs/s ({cx['ms_per_step']:.2f} ms per step, "
+              f"{cx['mean_matches']:.0f} matches per pair on average).", ""]
 if w5:
     L += ["## configs[4] — all 130,816 pairs of a 512-frame window (2048 keypoints per frame), 1 GPU", "",
           f"{w5['ms_per_step']:.0f} ms for the whole job = {w5['value']:,.0f} pairs/s ({w5['config']['solved_pairs_per_step']:,} pairs solved); "
