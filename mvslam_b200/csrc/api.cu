@@ -19,6 +19,10 @@ using namespace mvs;
 
 static_assert(sizeof(mvs_pair_result) == 376, "mvs_pair_result layout is part of the ABI");
 static_assert(sizeof(mvs_match) == 12, "mvs_match layout is part of the ABI");
+static_assert(sizeof(mvs_keypoint) == 24 && sizeof(mvs_orb_params) == 16, "extraction structs are part of the ABI");
+static_assert(sizeof(mvs_pnp_result) == 208 && sizeof(mvs_pnp_params) == 40, "pnp structs are part of the ABI");
+static_assert(sizeof(mvs_ba_observation) == 48 && sizeof(mvs_ba_result) == 24 && sizeof(mvs_ba_params) == 24, "BA structs are part of the ABI");
+static_assert(MVS_N_STAGES == 16, "mvs_profile layout is part of the ABI (capi.py STAGES)");
 
 namespace {
 
@@ -957,6 +961,10 @@ static int orb_extract_impl(mvs_ctx *ctx, const uint8_t *const *h_images, const 
         std::vector<int32_t> tabs;
         if (!orb_make_geometry(width, height, nf, ctx->orb_geom, tabs))
             return fail(ctx, MVS_E_UNSUPPORTED, "orb_extract: image too small for an 8-level pyramid");
+        if (ctx->orb_geom.lv[0].quota > kOrbSortCap) {      // level 0 has the largest quota (about 0.217 * n_features)
+            ctx->orb_w = 0;
+            return fail(ctx, MVS_E_UNSUPPORTED, "orb_extract: n_features too large (a level keeps at most 4096 keypoints: n_features <= 18800)");
+        }
         CK(cudaStreamSynchronize(ctx->stream));   // earlier work may still read the old tables
         CK(ctx->o_tabs.ensure(std::max<size_t>(tabs.size(), 1) * sizeof(int32_t)));
         CK(cudaMemcpy(ctx->o_tabs.p, tabs.data(), tabs.size() * sizeof(int32_t), cudaMemcpyHostToDevice));

@@ -40,6 +40,21 @@ def test_host_sample_table_matches_oracle():
         assert np.array_equal(mvs.sample_table(seed, pid, n, H), orc.sample_table(seed, pid, n, H))
 
 
+def test_host_pnp_sample_table_matches_oracle():
+    for seed, pid, n, H in [(0, 0, 4, 8), (1, 5, 91, 100), (2**63, 2**40, 5000, 300)]:
+        t = mvs.pnp_sample_table(seed, pid, n, H)
+        assert np.array_equal(t, orc.pnp_sample_table(seed, pid, n, H))
+        assert t.max() < n and all(len(set(r)) == 4 for r in t.tolist())
+    assert mvs.pnp_sample_table(3, 1, 50, 4)[0].tolist() == [0, 1, 2, 3]
+
+
+def test_struct_layouts_of_the_added_stages():
+    assert mvs.KEYPOINT_DTYPE.itemsize == 24 and ctypes.sizeof(mvs.OrbParams) == 16
+    assert mvs.PNP_RESULT_DTYPE.itemsize == 208 and ctypes.sizeof(mvs.PnpParams) == 40
+    assert mvs.BA_OBS_DTYPE.itemsize == 48 and mvs.BA_RESULT_DTYPE.itemsize == 24 and ctypes.sizeof(mvs.BaParams) == 24
+    assert len(mvs.STAGES) == 16
+
+
 def test_status_strings():
     L = mvs.load_library()
     assert L.mvs_status_string(0) == b"ok"

@@ -100,6 +100,9 @@ def test_degenerate_inputs(ctx):
     assert e.value.status == mvs.E_UNSUPPORTED
     counts, _, _, _ = ctx.orb_extract([np.zeros((2, 2), np.uint8)], 500)   # tiny but valid: no interior, no keypoints
     assert counts.tolist() == [0]
+    with pytest.raises(mvs.MvsError) as e:                      # level-0 quota beyond the per-level capacity
+        ctx.orb_extract([img], 30000)
+    assert e.value.status == mvs.E_UNSUPPORTED
     # batch result equals per-image result (no cross-image state)
     a = synth.synthetic_image(6, 320, 240)
     c2, k2, d2, _ = ctx.orb_extract([img, a, img], 700)
