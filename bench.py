@@ -521,6 +521,20 @@ def main():
         v, dt = cpu_pairs_per_s(descs, kps, K, pairs, params, n_sample)
         cpu = dict(value=v, unit="pairs/s", cores=threads, kind="port",
                    sample=f"{n_sample} pairs of the same workload in {dt:.1f} s, C oracle (own-branch port), OpenMP over pairs")
+        try:    # the matcher the reference actually calls (cv::BFMatcher::knnMatch, visual-feature.cpp:59-62), match only
+            import cv2
+            cv2.setNumThreads(threads)
+            bf = cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=False)
+            t0 = time.perf_counter(); k = 0
+            while time.perf_counter() - t0 < 3.0:
+                a, b = pairs[k % len(pairs)]
+                bf.knnMatch(descs[b], descs[a], k=2); k += 1
+            dtm = time.perf_counter() - t0
+            cpu["matcher_cv2"] = dict(value=k / dtm, unit="pairs/s (knnMatch k=2 only)", cores=threads,
+                                      sample=f"{k} pairs in {dtm:.1f} s, cv2 {cv2.__version__} BFMatcher(NORM_HAMMING).knnMatch",
+                                      ours_match_only_pairs_per_s=B * args.steps / max((prof["knn"][0] + prof["match_finalize"][0]) * 1e-3, 1e-12))
+        except ImportError:
+            pass
 
     # ---- extras beside the headline; a failure here must never cost the headline line
     extract = pnp = ba = None

@@ -24,6 +24,9 @@ if t:
           "| | pairs/s | ms per 1024-pair step |", "|---|---|---|",
           f"| device-resident (`value`) | {t['value']:,.0f} | {t['ms_per_step']:.3f} |",
           f"| end to end through the C ABI with host buffers (`e2e`) | {t['e2e']['value']:,.0f} | {t['e2e']['ms_per_step']:.3f} |"]
+    mc = (t.get("cpu_baseline") or {}).get("matcher_cv2")
+    if mc:
+        L += [f"| matcher only: cv2 BFMatcher.knnMatch(k=2) on {mc['cores']} host threads vs K1+K2 | {mc['value']:,.0f} vs {mc['ours_match_only_pairs_per_s']:,.0f} | — |"]
     if ref:
         L += [f"| CPU oracle port, {ref['cpu_baseline']['cores']} host threads (`--impl reference`) | {ref['value']:,.0f} | — |"]
     L += ["", f"Dominant kernel `knn2_hamming_kernel`: {rf['desc_pairs_per_s'] / 1e9:.0f} G descriptor pairs/s = "
