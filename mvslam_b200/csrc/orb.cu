@@ -208,96 +208,111 @@ constexpr int FT_W = 32, FT_H = 16;
 constexpr int FT_PW = FT_W + 8, FT_PH = FT_H + 8;      // pixel tile (halo 4: 1 for the NMS ring + 3 for the FAST ring)
 constexpr int FT_SW = FT_W + 2, FT_SH = FT_H + 2;      // score tile
 
-// Cheap necessary condition on 4 of the 8 antipodal pairs (an arc of 9 contains one pixel of every pair).
-__device__ __forceinline__ bool fast_maybe_corner(const uint8_t *c, int p)
+constexpr int FT_PITCH = 44;       // bytes per pixel-tile row: 11 aligned words starting at x0 - 7
+
+// 4 adjacent bytes starting at byte `off` of a word-aligned shared-memory row
+__device__ __forceinline__ uint32_t ld4_unaligned(const uint32_t *row, int off)
 {
-    const int v = c[0], t = kOrbFastThreshold;
-    const int d0 = v - c[3 * p], d8 = v - c[-3 * p], d4 = v - c[3], d12 = v - c[-3];
-    const bool pb = (max(d0, d8) > t) & (max(d4, d12) > t), pd = (min(d0, d8) < -t) & (min(d4, d12) < -t);
-    if (!(pb | pd)) return false;
-    const int d2 = v - c[2 * p + 2], d10 = v - c[-2 * p - 2], d6 = v - c[-2 * p + 2], d14 = v - c[2 * p - 2];
-    return (pb & (max(d2, d10) > t) & (max(d6, d14) > t)) | (pd & (min(d2, d10) < -t) & (min(d6, d14) < -t));
+    const uint32_t *w = row + (off >> 2);
+    return __funnelshift_r(w[0], w[1], (off & 3) * 8);
+}
+// per byte: bit 7 set iff the byte exceeds the FAST threshold (a > 20 <=> a >= 128 or (a & 127) + 107 >= 128)
+__device__ __forceinline__ uint32_t over_threshold4(uint32_t a)
+{
+    static_assert(kOrbFastThreshold == 20, "0x6b = 127 - threshold");
+    return (((a & 0x7f7f7f7fu) + 0x6b6b6b6bu) | a) & 0x80808080u;
+}
+// Necessary condition for 4 horizontally adjacent centres at once (packed bytes, VABSDIFF4): an arc of 9 contains one
+// pixel of every antipodal pair, so every pair must hold a pixel that differs from the centre by more than the threshold.
+// Sign-agnostic and on 4 of the 8 pairs only: a superset of the corners (11.5 % of the Tsukuba pixels pass, 4.8 % are corners).
+__device__ __forceinline__ uint32_t fast_maybe4(const uint32_t *pxw, int r, int cb)   // cb = byte column of the first centre
+{
+    const uint32_t *row = pxw + r * (FT_PITCH / 4);
+    const uint32_t c = ld4_unaligned(row, cb);
+    uint32_t f = over_threshold4(__vabsdiffu4(c, ld4_unaligned(row + 3 * (FT_PITCH / 4), cb))) |
+                 over_threshold4(__vabsdiffu4(c, ld4_unaligned(row - 3 * (FT_PITCH / 4), cb)));
+    f &= over_threshold4(__vabsdiffu4(c, ld4_unaligned(row, cb + 3))) | over_threshold4(__vabsdiffu4(c, ld4_unaligned(row, cb - 3)));
+    if (!f) return 0;
+    f &= over_threshold4(__vabsdiffu4(c, ld4_unaligned(row + 2 * (FT_PITCH / 4), cb + 2))) |
+         over_threshold4(__vabsdiffu4(c, ld4_unaligned(row - 2 * (FT_PITCH / 4), cb - 2)));
+    f &= over_threshold4(__vabsdiffu4(c, ld4_unaligned(row - 2 * (FT_PITCH / 4), cb + 2))) |
+         over_threshold4(__vabsdiffu4(c, ld4_unaligned(row + 2 * (FT_PITCH / 4), cb - 2)));
+    return f;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)
 orb_fast_kernel(const __grid_constant__ OrbGeom g, OrbBuffers b)
 {
-    __shared__ __align__(16) uint8_t px[FT_PH][FT_PW];
-    __shared__ uint8_t sc[FT_SH][FT_SW + 2];
-    __shared__ uint16_t todo[FT_SH * FT_SW];
-    __shared__ int n_todo;
+    __shared__ uint32_t pxw[FT_PH + 1][FT_PITCH / 4];       // +1 row: the unaligned 4-byte window of the last group may touch it
+    __shared__ __align__(4) uint8_t sc[FT_SH][FT_SW + 2];
+    __shared__ uint16_t todo[FT_SH * FT_SW];       // phase 1 survivors, then the 3x3 maxima: r << 6 | c
+    __shared__ uint16_t corners[FT_H * FT_W];      // positive scores inside the output tile
+    __shared__ int n_todo, n_corner, n_keep, keep_base;
     int l = 0;
     while (l + 1 < kOrbLevels && (int)blockIdx.x >= g.lv[l + 1].tile_off) ++l;
     const OrbLevel &L = g.lv[l];
-    const int img = blockIdx.y;
+    const int img = blockIdx.y, tid = threadIdx.x;
     const int tiles_x = (L.w - 2 * kOrbEdge + 31) / 32;
     const int t = blockIdx.x - L.tile_off;
     const int x0 = kOrbEdge + (t % tiles_x) * FT_W, y0 = kOrbEdge + (t / tiles_x) * FT_H;
     const uint8_t *src = b.pyr + (size_t)img * g.slab + L.off;
-    if (threadIdx.x == 0) n_todo = 0;
-    // pixel tile rows [y0-4, y0+20) x cols [x0-4, x0+36): x0 - 4 = 27 + 32k is odd, so the 4-byte words start at x0 - 7
-    // (11 words per row cover the tile); rows beyond the image repeat the last row (never used by a tested pixel)
-    for (int i = threadIdx.x; i < FT_PH * 11; i += 256) {
-        const int r = i / 11, wd = i % 11;
-        const int y = min(y0 - 4 + r, L.h - 1);
-        const int xw = x0 - 7 + 4 * wd;                        // multiple of 4
-        uint32_t v = 0;
-        if (xw < L.pitch) v = *reinterpret_cast<const uint32_t *>(src + (size_t)y * L.pitch + xw);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int c = 4 * wd + k - 3;                      // column inside px
-            if (c >= 0 && c < FT_PW) px[r][c] = (uint8_t)(v >> (8 * k));
-        }
+    const uint8_t *px = reinterpret_cast<const uint8_t *>(pxw);
+    if (tid == 0) { n_todo = 0; n_corner = 0; n_keep = 0; }
+    if (tid < FT_SH * (FT_SW + 2) / 4) reinterpret_cast<uint32_t *>(sc)[tid] = 0u;
+    // pixel tile: rows [y0-4, y0+20), 11 aligned words per row from x0 - 7 (x0 = 31 + 32k, so x0 - 7 is a multiple of 4);
+    // byte column of image x is x - (x0 - 7).  Rows beyond the image repeat the last row (no tested pixel reads them).
+    for (int i = tid; i < (FT_PH + 1) * 11; i += 256) {
+        const int r = i / 11, wd = i - r * 11;
+        const int y = min(y0 - 4 + r, L.h - 1), xw = x0 - 7 + 4 * wd;
+        pxw[r][wd] = xw < L.pitch ? *reinterpret_cast<const uint32_t *>(src + (size_t)y * L.pitch + xw) : 0u;
     }
     __syncthreads();
-    // phase 1: cheap rejection; survivors are queued so that phase 2 runs the full score on dense warps
-    for (int i0 = 0; i0 < FT_SH * FT_SW; i0 += 256) {         // uniform trip count: full-warp ballots
-        const int i = i0 + threadIdx.x;
-        const bool in = i < FT_SH * FT_SW;
-        const int r = in ? i / FT_SW : 0, c = in ? i % FT_SW : 0;
-        const int y = y0 - 1 + r, x = x0 - 1 + c;
-        if (in) sc[r][c] = 0;
-        const bool maybe = in && x < L.w - 3 && y < L.h - 3 && fast_maybe_corner(&px[r + 3][c + 3], FT_PW);   // fast.cpp tests [3, n-3)
-        const unsigned m = __ballot_sync(0xffffffffu, maybe);
-        if (maybe) {
-            const unsigned lane = threadIdx.x & 31;
-            int base = 0;
-            if (lane == __ffs(m) - 1) base = atomicAdd(&n_todo, __popc(m));
-            base = __shfl_sync(m, base, __ffs(m) - 1);
-            todo[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)i;
+    // phase 1: cheap rejection over the 18 x 34 score positions (origin (x0-1, y0-1)), 4 adjacent positions per thread in
+    // packed bytes; survivors are queued so that phase 2 runs the full score on dense warps
+    if (tid < FT_SH * 9) {
+        const int r = tid / 9, q = tid - r * 9;
+        const uint32_t f = fast_maybe4(&pxw[0][0], r + 3, 4 * q + 6);
+        if (f) {
+            const int y = y0 - 1 + r;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int c = 4 * q + k, x = x0 - 1 + c;
+                if (((f >> (8 * k + 7)) & 1u) && c < FT_SW && x < L.w - 3 && y < L.h - 3)       // fast.cpp tests [3, n-3)
+                    todo[atomicAdd(&n_todo, 1)] = (uint16_t)(r << 6 | c);
+            }
         }
     }
     __syncthreads();
     const int n = n_todo;
-    for (int j = threadIdx.x; j < n; j += 256) {
-        const int i = todo[j], r = i / FT_SW, c = i % FT_SW;
-        sc[r][c] = (uint8_t)fast_corner_score(&px[r + 3][c + 3], FT_PW);
+    for (int j = tid; j < n; j += 256) {
+        const int v = todo[j], r = v >> 6, c = v & 63;
+        const int s = fast_corner_score(px + (r + 3) * FT_PITCH + c + 6, FT_PITCH);
+        sc[r][c] = (uint8_t)s;
+        // candidates for the 3x3 maximum test: corners inside the output tile and inside the detector's border
+        if (s > 0 && r >= 1 && r <= FT_H && c >= 1 && c <= FT_W && x0 - 1 + c < L.w - kOrbEdge && y0 - 1 + r < L.h - kOrbEdge)
+            corners[atomicAdd(&n_corner, 1)] = (uint16_t)v;
     }
     __syncthreads();
-    const int tx = threadIdx.x & 31, lane = tx;
-#pragma unroll
-    for (int pass = 0; pass < 2; ++pass) {
-        const int ty = (threadIdx.x >> 5) + pass * 8;
-        const int x = x0 + tx, y = y0 + ty;
-        const int s = sc[ty + 1][tx + 1];
-        bool keep = s > 0 && x < L.w - kOrbEdge && y < L.h - kOrbEdge;
-        if (keep) {
-            keep = s > sc[ty][tx] && s > sc[ty][tx + 1] && s > sc[ty][tx + 2] && s > sc[ty + 1][tx] && s > sc[ty + 1][tx + 2] &&
-                   s > sc[ty + 2][tx] && s > sc[ty + 2][tx + 1] && s > sc[ty + 2][tx + 2];
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        if (m) {
-            int base = 0;
-            if (lane == __ffs(m) - 1) base = atomicAdd(&b.cand_cnt[img * kOrbLevels + l], __popc(m));
-            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-            if (keep) {
-                const int slot = base + __popc(m & ((1u << lane) - 1));
-                const size_t o = (size_t)img * g.cand_total + L.cand_off + slot;
-                b.cand_xy[o] = (uint32_t)x | ((uint32_t)y << 16);
-                b.cand_val[o] = (float)s;
-                atomicAdd(&b.hist[(img * kOrbLevels + l) * 256 + s], 1);
-            }
-        }
+    const int nc = n_corner;
+    for (int j = tid; j < nc; j += 256) {
+        const int v = corners[j], r = v >> 6, c = v & 63;
+        const int s = sc[r][c];
+        if (s > sc[r - 1][c - 1] && s > sc[r - 1][c] && s > sc[r - 1][c + 1] && s > sc[r][c - 1] && s > sc[r][c + 1] &&
+            s > sc[r + 1][c - 1] && s > sc[r + 1][c] && s > sc[r + 1][c + 1])
+            todo[atomicAdd(&n_keep, 1)] = (uint16_t)v;      // todo is free again
+    }
+    __syncthreads();
+    const int nk = n_keep;
+    if (nk == 0) return;
+    if (tid == 0) keep_base = atomicAdd(&b.cand_cnt[img * kOrbLevels + l], nk);
+    __syncthreads();
+    for (int j = tid; j < nk; j += 256) {
+        const int v = todo[j], r = v >> 6, c = v & 63;
+        const int s = sc[r][c];
+        const size_t o = (size_t)img * g.cand_total + L.cand_off + keep_base + j;
+        b.cand_xy[o] = (uint32_t)(x0 - 1 + c) | ((uint32_t)(y0 - 1 + r) << 16);
+        b.cand_val[o] = (float)s;
+        atomicAdd(&b.hist[(img * kOrbLevels + l) * 256 + s], 1);
     }
 }
 
@@ -519,7 +534,7 @@ __device__ __forceinline__ uint32_t gauss_col7(float c, float a1, float b1, floa
 
 // 32x32 output tile: 38 x 40 input bytes as 10 aligned words per row, row pass 4 outputs per thread (float4 to shared
 // memory), column pass 4 adjacent columns per thread (7 LDS.128, one 32-bit store).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)
 orb_blur_kernel(const __grid_constant__ OrbGeom g, OrbBuffers b)
 {
     __shared__ uint32_t in[38][10];
