@@ -620,6 +620,13 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x)
 
 __constant__ int8_t c_pattern[1024];
 
+// cvRound for |x| < 2^22 without the XU pipe: adding 1.5 * 2^23 leaves the integer, rounded half to even by the FP32 add,
+// in the low mantissa bits
+__device__ __forceinline__ int round_half_even(float x)
+{
+    return __float_as_int(__fadd_rn(x, 12582912.0f)) - 0x4B400000;
+}
+
 // A warp takes G keypoints per pass: moments and descriptor bits are computed by the whole warp for one keypoint at a
 // time, while the scalar part in between (fastAtan2, double-precision cos/sin, the keypoint record) runs once with
 // lane j working on keypoint j.  G = 32 amortises the trigonometry best; small G keeps more warps busy when a call
@@ -628,12 +635,13 @@ template <int G>
 __global__ void __launch_bounds__(256)
 orb_describe_kernel(const __grid_constant__ OrbGeom g, OrbBuffers b, OrbDescribeArgs d)
 {
-    // pattern transposed for conflict-free access: s_pat[k][lane] = point k (0..15) of the byte `lane`
-    __shared__ char2 s_pat[16][32];
+    // pattern transposed for conflict-free access: s_pat[k][lane] = point k (0..15) of the byte `lane`, already as floats
+    // (int -> float conversions and float -> int roundings run on the quarter-rate XU pipe: none is left in the loop)
+    __shared__ float2 s_pat[16][32];
     __shared__ int s_start[kOrbLevels + 1];
     const int img = blockIdx.y;
     for (int i = threadIdx.x; i < 512; i += 256)
-        s_pat[i & 15][i >> 4] = make_char2(c_pattern[2 * i], c_pattern[2 * i + 1]);
+        s_pat[i & 15][i >> 4] = make_float2((float)c_pattern[2 * i], (float)c_pattern[2 * i + 1]);
     if (threadIdx.x == 0) {
         int acc = 0;
         for (int l = 0; l < kOrbLevels; ++l) { s_start[l] = acc; acc += max(b.kept_cnt[img * kOrbLevels + l], 0); }
@@ -714,11 +722,11 @@ orb_describe_kernel(const __grid_constant__ OrbGeom g, OrbBuffers b, OrbDescribe
             int byte = 0;
 #pragma unroll
             for (int bit = 0; bit < 8; ++bit) {
-                const char2 q0 = s_pat[2 * bit][lane], q1 = s_pat[2 * bit + 1][lane];
-                const int x0 = __float2int_rn(__fsub_rn(__fmul_rn((float)q0.x, jc), __fmul_rn((float)q0.y, js)));
-                const int y0 = __float2int_rn(__fadd_rn(__fmul_rn((float)q0.x, js), __fmul_rn((float)q0.y, jc)));
-                const int x1 = __float2int_rn(__fsub_rn(__fmul_rn((float)q1.x, jc), __fmul_rn((float)q1.y, js)));
-                const int y1 = __float2int_rn(__fadd_rn(__fmul_rn((float)q1.x, js), __fmul_rn((float)q1.y, jc)));
+                const float2 q0 = s_pat[2 * bit][lane], q1 = s_pat[2 * bit + 1][lane];
+                const int x0 = round_half_even(__fsub_rn(__fmul_rn(q0.x, jc), __fmul_rn(q0.y, js)));
+                const int y0 = round_half_even(__fadd_rn(__fmul_rn(q0.x, js), __fmul_rn(q0.y, jc)));
+                const int x1 = round_half_even(__fsub_rn(__fmul_rn(q1.x, jc), __fmul_rn(q1.y, js)));
+                const int y1 = round_half_even(__fadd_rn(__fmul_rn(q1.x, js), __fmul_rn(q1.y, jc)));
                 byte |= (int)(bl[y0 * pitch + x0] < bl[y1 * pitch + x1]) << bit;
             }
             d.desc[(out0 + base + j) * 32 + lane] = (uint8_t)byte;
