@@ -1,7 +1,9 @@
 /*
  * mvslam_b200.h — C ABI of libmvslam_b200.so: the B200 (sm_100a) implementation of mvSLAM's
  * two-view front-end hot path (descriptor matching -> RANSAC fundamental/essential matrix ->
- * pose recovery -> linear triangulation).
+ * pose recovery -> linear triangulation) and of the steps on either side of it:
+ * feature extraction (cv::ORB), pnp_solve (cv::solvePnPRansac with P3P) and the one-/two-frame bundle
+ * adjustment behind sfm_refine / pnp_refine.
  *
  * The reference (lonelycorn/mvSLAM) has no plugin/FFI layer; its boundary for this path is a set
  * of C++ entry points.  Each function below names the reference interface it replaces
