@@ -972,9 +972,9 @@ static int orb_extract_impl(mvs_ctx *ctx, const uint8_t *const *h_images, const 
     }
     const OrbGeom &g = ctx->orb_geom;
     // chunk size: keep the workspace (2 pyramids + candidate lists + kept lists per image) near 2 GB
-    const size_t per_image = 2 * (size_t)g.slab + 8 * (size_t)g.cand_total + (size_t)kOrbLevels * kOrbSortCap * 4 + (size_t)height * stride;
+    const size_t per_image = 2 * (size_t)g.slab + 8 * (size_t)g.cand_total + (size_t)kOrbLevels * kOrbSortCap * 4 + (h_images ? (size_t)height * stride : 0);
     const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_images, ((size_t)2 << 30) / per_image));
-    CK(ctx->o_stage.ensure((size_t)chunk * height * stride));
+    if (h_images) CK(ctx->o_stage.ensure((size_t)chunk * height * stride));
     CK(ctx->o_pyr.ensure((size_t)chunk * g.slab));
     CK(ctx->o_blur.ensure((size_t)chunk * g.slab));
     CK(ctx->o_cxy.ensure((size_t)chunk * g.cand_total * 4));
