@@ -520,6 +520,13 @@ def test_cpp_vo_tool_from_images(tmp_path):
         assert "valid=1" in l
         t = [float(x) for x in l.split("t=(")[1].rstrip(")").split()]
         assert np.allclose(t, [1, 0, 0], atol=1e-3)
+    # utility/reconstruct-scene.cpp on two images: extract (2000 features), match_and_filter, sfm_solve
+    r = subprocess.run([os.path.join(root, "tools", "reconstruct_scene"), out + "/1.pgm", out + "/2.pgm", out + "/camera.config", "30", "2000"],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rows = [l for l in r.stdout.splitlines() if "|" in l]
+    Rt = np.array([[float(x) for x in l.replace("|", " ").split()] for l in rows])
+    assert np.allclose(Rt[:, :3], np.eye(3), atol=1e-3) and np.allclose(Rt[:, 3], [1, 0, 0], atol=1e-3)
 
 
 def test_frames_append_equals_bulk_upload(ctx, tsukuba):

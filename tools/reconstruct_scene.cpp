@@ -1,7 +1,7 @@
 // reconstruct_scene — the flow of the reference's utility/reconstruct-scene.cpp:22-81 on top of the adapters:
-//   features(1), features(2) -> match_and_filter_visual_features -> sfm_solve -> print pose + points.
-// Image loading and ORB extraction are outside the hot path: the inputs are pre-extracted feature files
-// (include/mvslam/feature-io.hpp; tools/export_features.py writes them with cv2.ORB).
+//   image(1), image(2) -> VisualFeature::extract -> match_and_filter_visual_features -> sfm_solve -> print pose + points.
+// Inputs ending in .pgm are 8-bit binary PGM images, extracted on the device like the reference does with OpenCV
+// (reconstruct-scene.cpp:36-39); anything else is a pre-extracted feature file (include/mvslam/feature-io.hpp).
 #include <cstdio>
 #include <iostream>
 
@@ -10,16 +10,24 @@
 
 static void print_help(const char *cmdline)
 {
-    std::printf("Usage: %s <features_1> <features_2> <intrinsics> <max_dist>\n", cmdline);
-    std::printf("\tReconstruct scene using the features of two images.\n");
+    std::printf("Usage: %s <image_1.pgm|features_1> <image_2.pgm|features_2> <intrinsics> <max_dist> [nfeatures=500]\n", cmdline);
+    std::printf("\tReconstruct scene using two images (or their pre-extracted features).\n");
 }
 
 int main(int argc, char **argv)
 {
-    if (argc != 5) { print_help(argv[0]); return 1; }
+    if (argc != 5 && argc != 6) { print_help(argv[0]); return 1; }
     try {
-        auto vf1 = mvSLAM::load_visual_feature(argv[1]);
-        auto vf2 = mvSLAM::load_visual_feature(argv[2]);
+        const int nfeatures = argc == 6 ? std::stoi(argv[5]) : mvSLAM::VisualFeature::MAX_FEATURE_COUNT;
+        auto load = [&](const std::string &fn) {
+            if (fn.size() > 4 && fn.substr(fn.size() - 4) == ".pgm") {
+                std::vector<uint8_t> pixels;
+                return mvSLAM::VisualFeature::extract(mvSLAM::load_pgm(fn, pixels), nfeatures);
+            }
+            return mvSLAM::load_visual_feature(fn);
+        };
+        auto vf1 = load(argv[1]);
+        auto vf2 = load(argv[2]);
         const mvSLAM::CameraIntrinsics K = mvSLAM::load_camera_intrinsics(argv[3]);
         const mvSLAM::ScalarType max_dist = std::stoi(std::string(argv[4]));
         auto matched = mvSLAM::VisualFeature::match_and_filter_visual_features(vf1, vf2, max_dist);
