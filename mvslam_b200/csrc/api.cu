@@ -74,6 +74,7 @@ struct mvs_ctx {
     // asynchronously into the staging area and scattered to the caller's buffers after the one synchronisation
     uint8_t *h_stage = nullptr;
     size_t h_stage_cap = 0, h_stage_used = 0;
+    bool allow_stage = false;   // set by the synchronous entry points only: _enqueue callers may synchronise the stream themselves
     struct StagedCopy { void *dst; size_t dpitch; size_t src_off; size_t width; size_t rows; };
     std::vector<StagedCopy> staged;
     // profiling
@@ -839,7 +840,7 @@ static int pair_batch_chunk(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, con
     const size_t w = (size_t)std::min(capacity, qs);
     const size_t detail_bytes = (size_t)n_pairs * w * ((matches ? sizeof(mvs_match) : 0) + (inlier_mask ? 1 : 0) + (points ? 24 : 0) + (indexes ? 8 : 0));
     const size_t stage_bytes = detail_bytes + (size_t)n_pairs * sizeof(mvs_pair_result);
-    bool stage = stage_bytes <= ((size_t)4 << 20);
+    bool stage = ctx->allow_stage && stage_bytes <= ((size_t)4 << 20);
     if (stage) {
         cudaPointerAttributes at{};
         if (cudaPointerGetAttributes(&at, results) == cudaSuccess && at.type == cudaMemoryTypeHost) stage = false;   // pinned already
@@ -935,7 +936,10 @@ int mvs_pair_batch(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, const double
                    mvs_pair_result *results, mvs_match *matches, uint8_t *inlier_mask,
                    double *points, uint64_t *indexes, int capacity)
 {
+    if (!ctx) return MVS_E_BAD_ARG;
+    ctx->allow_stage = true;
     int st = mvs_pair_batch_enqueue(ctx, pairs, n_pairs, K, mparams, rparams, results, matches, inlier_mask, points, indexes, capacity);
+    ctx->allow_stage = false;
     if (st != MVS_OK) { cudaStreamSynchronize(ctx->stream); flush_staged(ctx); return st; }
     CK(cudaStreamSynchronize(ctx->stream));
     flush_staged(ctx);
