@@ -1,3 +1,6 @@
+#!/usr/bin/env python
+"""Single-pair mvs_pair_batch latency: wall time per call with / without detail outputs and the per-stage device times
+(run on the GPU box)."""
 import sys, os, time, json
 import numpy as np
 sys.path.insert(0, os.getcwd())
