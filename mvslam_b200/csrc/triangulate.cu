@@ -16,7 +16,7 @@ namespace mvs {
 
 constexpr int TRI_THREADS = 128;
 
-__global__ void __launch_bounds__(TRI_THREADS)
+__global__ void __launch_bounds__(TRI_THREADS, 5)
 triangulate_kernel(TriArgs a)
 {
     __shared__ int s_cnt;
