@@ -286,7 +286,7 @@ pnp_score_kernel(PnpArgs a)
 // ------------------------------------------------------------------------------------------ Q3
 constexpr int PNP_SEL_THREADS = 256;
 
-__global__ void __launch_bounds__(PNP_SEL_THREADS)
+__global__ void __launch_bounds__(PNP_SEL_THREADS, 2)
 pnp_select_refine_kernel(PnpArgs a)
 {
     __shared__ unsigned long long s_best;
