@@ -146,6 +146,68 @@ __device__ __forceinline__ void reduce_rows(const double *acc, int n, double *ou
     __syncthreads();
 }
 
+// One point's contribution to the reduced camera system, N = 6 (one frame) or 12 (two): (W Vl^-1 W^T) into my[0 .. N(N+1)/2)
+// and, when WITH_RHS, W Vl^-1 g into my[N(N+1)/2 ..).  Fully unrolled for a compile-time N so that W Vl^-1 stays in registers
+// (with a run-time N the arrays live in local memory and this loop was a fifth of the kernel's instructions).
+template <int N, bool WITH_RHS>
+__device__ __forceinline__ void schur_accumulate(const double *w, double lam, double *my)
+{
+    const double Vl[6] = {w[0] + lam, w[1], w[2], w[3] + lam, w[4], w[5] + lam};
+    double Vi[6];
+    sym3_inverse(Vl, Vi);
+    double Wm[N * 3], Y[N * 3];
+#pragma unroll
+    for (int k = 0; k < N * 3; ++k) Wm[k] = w[9 + k];
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+        Y[r * 3] = Wm[r * 3] * Vi[0] + Wm[r * 3 + 1] * Vi[1] + Wm[r * 3 + 2] * Vi[2];
+        Y[r * 3 + 1] = Wm[r * 3] * Vi[1] + Wm[r * 3 + 1] * Vi[3] + Wm[r * 3 + 2] * Vi[4];
+        Y[r * 3 + 2] = Wm[r * 3] * Vi[2] + Wm[r * 3 + 1] * Vi[4] + Wm[r * 3 + 2] * Vi[5];
+    }
+    int k = 0;
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+#pragma unroll
+        for (int c = r; c < N; ++c) { my[k] += Y[r * 3] * Wm[c * 3] + Y[r * 3 + 1] * Wm[c * 3 + 1] + Y[r * 3 + 2] * Wm[c * 3 + 2]; ++k; }
+    }
+    if (WITH_RHS) {
+#pragma unroll
+        for (int r = 0; r < N; ++r) my[N * (N + 1) / 2 + r] += Y[r * 3] * w[6] + Y[r * 3 + 1] * w[7] + Y[r * 3 + 2] * w[8];
+    }
+}
+
+// marginal covariance of one point: V^-1 + (V^-1 W^T) C (W V^-1), C = inverse of the reduced camera system (N x N, shared)
+template <int N>
+__device__ __forceinline__ void point_covariance(const double *w, const double *C, double *out)
+{
+    double Vi[6];
+    sym3_inverse(w, Vi);
+    const double Vf[9] = {Vi[0], Vi[1], Vi[2], Vi[1], Vi[3], Vi[4], Vi[2], Vi[4], Vi[5]};
+    double T[3][N];                                         // V^-1 W^T
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < N; ++c) T[r][c] = Vf[r * 3] * w[9 + c * 3] + Vf[r * 3 + 1] * w[9 + c * 3 + 1] + Vf[r * 3 + 2] * w[9 + c * 3 + 2];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        double m[N];                                        // C T[c]^T
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            double tc = 0.0;
+#pragma unroll
+            for (int q = 0; q < N; ++q) tc += C[k * N + q] * T[c][q];
+            m[k] = tc;
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            double v = Vf[r * 3 + c];
+#pragma unroll
+            for (int k = 0; k < N; ++k) v += T[r][k] * m[k];
+            out[r * 3 + c] = v;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(BA_THREADS)
 ba_solve_kernel(BaArgs a)
 {
@@ -319,20 +381,7 @@ ba_solve_kernel(BaArgs a)
         for (int k = 0; k < nu + n; ++k) my[k] = 0.0;
         for (int j = tid; j < P; j += BA_THREADS) {
             const double *w = a.ws + (size_t)(p0 + j) * BA_WS;
-            const double Vl[6] = {w[0] + lam, w[1], w[2], w[3] + lam, w[4], w[5] + lam};
-            double Vi[6];
-            sym3_inverse(Vl, Vi);
-            double Y[36];                                    // W Vi  (n x 3)
-            for (int r = 0; r < n; ++r) {
-                const double *wr = w + 9 + r * 3;
-                Y[r * 3] = wr[0] * Vi[0] + wr[1] * Vi[1] + wr[2] * Vi[2];
-                Y[r * 3 + 1] = wr[0] * Vi[1] + wr[1] * Vi[3] + wr[2] * Vi[4];
-                Y[r * 3 + 2] = wr[0] * Vi[2] + wr[1] * Vi[4] + wr[2] * Vi[5];
-            }
-            int k = 0;
-            for (int r = 0; r < n; ++r)
-                for (int c = r; c < n; ++c) { const double *wc = w + 9 + c * 3; my[k++] += Y[r * 3] * wc[0] + Y[r * 3 + 1] * wc[1] + Y[r * 3 + 2] * wc[2]; }
-            for (int r = 0; r < n; ++r) my[nu + r] += Y[r * 3] * w[6] + Y[r * 3 + 1] * w[7] + Y[r * 3 + 2] * w[8];
+            if (n == 12) schur_accumulate<12, true>(w, lam, my); else schur_accumulate<6, true>(w, lam, my);
         }
         reduce_rows(acc, nu + n, s_red);
         if (tid == 0) {
@@ -439,31 +488,29 @@ ba_solve_kernel(BaArgs a)
         for (int k = 0; k < nu; ++k) my[k] = 0.0;
         for (int j = tid; j < P; j += BA_THREADS) {
             const double *w = a.ws + (size_t)(p0 + j) * BA_WS;
-            double Vi[6];
-            sym3_inverse(w, Vi);
-            int k = 0;
-            for (int r = 0; r < n; ++r) {
-                const double *wr = w + 9 + r * 3;
-                const double y0 = wr[0] * Vi[0] + wr[1] * Vi[1] + wr[2] * Vi[2], y1 = wr[0] * Vi[1] + wr[1] * Vi[3] + wr[2] * Vi[4],
-                             y2 = wr[0] * Vi[2] + wr[1] * Vi[4] + wr[2] * Vi[5];
-                for (int c = r; c < n; ++c) { const double *wc = w + 9 + c * 3; my[k++] += y0 * wc[0] + y1 * wc[1] + y2 * wc[2]; }
-            }
+            if (n == 12) schur_accumulate<12, false>(w, 0.0, my); else schur_accumulate<6, false>(w, 0.0, my);
         }
         reduce_rows(acc, nu, s_red);
+        __shared__ double s_L[144];
+        __shared__ int s_ok;
         if (tid == 0) {
-            double L[144], col[12], x[12];
             for (int r = 0; r < n; ++r)
                 for (int c = r; c < n; ++c) {
                     double u = 0.0;
                     if (r / 6 == c / 6) { const int f = r / 6; u = s_U[f * 21 + sym_idx(r % 6, c % 6, 6)]; }
-                    L[r * n + c] = u - s_red[sym_idx(r, c, n)];
+                    s_L[r * n + c] = u - s_red[sym_idx(r, c, n)];
                 }
-            const bool ok = cholesky(L, n);
-            for (int c = 0; c < n; ++c) {
-                for (int k = 0; k < n; ++k) col[k] = k == c ? 1.0 : 0.0;
-                if (ok) cholesky_solve(L, n, col, x);
-                for (int k = 0; k < n; ++k) s_S[k * n + c] = ok ? x[k] : NAN;
-            }
+            s_ok = cholesky(s_L, n);
+        }
+        __syncthreads();
+        if (tid < n) {                                      // column tid of the inverse: solve L L^T x = e_tid
+            double col[12], x[12];
+            for (int k = 0; k < n; ++k) col[k] = k == tid ? 1.0 : 0.0;
+            if (s_ok) cholesky_solve(s_L, n, col, x);
+            for (int k = 0; k < n; ++k) s_S[k * n + tid] = s_ok ? x[k] : NAN;
+        }
+        __syncthreads();
+        if (tid == 0) {
             for (int f = 0; f < F; ++f) {
                 for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) a.pose_cov_out[(size_t)(f0 + f) * 36 + r * 6 + c] = s_S[(f * 6 + r) * n + f * 6 + c];
                 for (int k = 0; k < 9; ++k) a.pose_R_out[(size_t)(f0 + f) * 9 + k] = s_pose[f * 12 + k];
@@ -475,26 +522,8 @@ ba_solve_kernel(BaArgs a)
         // point covariance = Vi + (Vi W^T) C (W Vi)
         for (int j = tid; j < P; j += BA_THREADS) {
             const double *w = a.ws + (size_t)(p0 + j) * BA_WS;
-            double Vi[6];
-            sym3_inverse(w, Vi);
-            const double Vf[9] = {Vi[0], Vi[1], Vi[2], Vi[1], Vi[3], Vi[4], Vi[2], Vi[4], Vi[5]};
-            double T[36];                                   // Vi W^T : 3 x n
-            for (int r = 0; r < 3; ++r)
-                for (int c = 0; c < n; ++c) T[r * n + c] = Vf[r * 3] * w[9 + c * 3] + Vf[r * 3 + 1] * w[9 + c * 3 + 1] + Vf[r * 3 + 2] * w[9 + c * 3 + 2];
             double *out = a.point_cov_out + (size_t)(p0 + j) * 9;
-            for (int c = 0; c < 3; ++c) {
-                double m[12];                               // column c of C T^T
-                for (int k = 0; k < n; ++k) {
-                    double tc = 0.0;
-                    for (int q = 0; q < n; ++q) tc += s_S[k * n + q] * T[c * n + q];
-                    m[k] = tc;
-                }
-                for (int r = 0; r < 3; ++r) {
-                    double v = Vf[r * 3 + c];
-                    for (int k = 0; k < n; ++k) v += T[r * n + k] * m[k];
-                    out[r * 3 + c] = v;
-                }
-            }
+            if (n == 12) point_covariance<12>(w, s_S, out); else point_covariance<6>(w, s_S, out);
         }
     }
 }
