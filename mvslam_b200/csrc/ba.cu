@@ -62,22 +62,36 @@ __device__ __forceinline__ void so3_jr_inv(const double p[3], double J[9])
         }
 }
 
-// in-place Cholesky of a symmetric n x n matrix stored dense (upper part read), L in the lower part; false if not PD
-__device__ bool cholesky(double *A, int n)
+// in-place Cholesky of a symmetric N x N matrix stored dense (upper part read), L in the lower part; false if not PD.
+// N is a compile-time constant (6 or 12) so that the loops unroll.
+template <int N>
+__device__ bool cholesky(double *A)
 {
-    for (int r = 0; r < n; ++r)
+#pragma unroll
+    for (int r = 0; r < N; ++r)
+#pragma unroll
         for (int c = 0; c <= r; ++c) {
-            double s = A[c * n + r];
-            for (int k = 0; k < c; ++k) s -= A[r * n + k] * A[c * n + k];
-            if (r == c) { if (!(s > 0.0)) return false; A[r * n + r] = sqrt(s); }
-            else A[r * n + c] = s / A[c * n + c];
+            double s = A[c * N + r];
+#pragma unroll
+            for (int k = 0; k < c; ++k) s -= A[r * N + k] * A[c * N + k];
+            if (r == c) { if (!(s > 0.0)) return false; A[r * N + r] = sqrt(s); }
+            else A[r * N + c] = s / A[c * N + c];
         }
     return true;
 }
-__device__ void cholesky_solve(const double *L, int n, const double *b, double *x)
+template <int N>
+__device__ void cholesky_solve(const double *L, const double *b, double *x)
 {
-    for (int r = 0; r < n; ++r) { double s = b[r]; for (int k = 0; k < r; ++k) s -= L[r * n + k] * x[k]; x[r] = s / L[r * n + r]; }
-    for (int r = n - 1; r >= 0; --r) { double s = x[r]; for (int k = r + 1; k < n; ++k) s -= L[k * n + r] * x[k]; x[r] = s / L[r * n + r]; }
+#pragma unroll
+    for (int r = 0; r < N; ++r) { double s = b[r];
+#pragma unroll
+        for (int k = 0; k < r; ++k) s -= L[r * N + k] * x[k];
+        x[r] = s / L[r * N + r]; }
+#pragma unroll
+    for (int r = N - 1; r >= 0; --r) { double s = x[r];
+#pragma unroll
+        for (int k = r + 1; k < N; ++k) s -= L[k * N + r] * x[k];
+        x[r] = s / L[r * N + r]; }
 }
 
 struct Proj {
@@ -241,10 +255,10 @@ ba_solve_kernel(BaArgs a)
             // information = C^-1 through Cholesky: solve C X = I column by column
             double L[36], col[6], x[6];
             for (int k = 0; k < 36; ++k) L[k] = C[k];
-            if (!cholesky(L, 6)) { s_flag[3] = 2; break; }
+            if (!cholesky<6>(L)) { s_flag[3] = 2; break; }
             for (int c = 0; c < 6; ++c) {
                 for (int k = 0; k < 6; ++k) col[k] = k == c ? 1.0 : 0.0;
-                cholesky_solve(L, 6, col, x);
+                cholesky_solve<6>(L, col, x);
                 for (int k = 0; k < 6; ++k) s_pinfo[f * 36 + k * 6 + c] = x[k];
             }
         }
@@ -395,9 +409,9 @@ ba_solve_kernel(BaArgs a)
                 }
                 b[r] = -s_gc[r] + s_red[nu + r];
             }
-            bool ok = cholesky(s_S, n);
+            bool ok = n == 12 ? cholesky<12>(s_S) : cholesky<6>(s_S);
             if (ok) {
-                cholesky_solve(s_S, n, b, s_dc);
+                if (n == 12) cholesky_solve<12>(s_S, b, s_dc); else cholesky_solve<6>(s_S, b, s_dc);
                 for (int f = 0; f < F; ++f) {
                     const double *R = s_pose + f * 12, *t = R + 9, *d = s_dc + f * 6;
                     double E[9];
@@ -500,13 +514,13 @@ ba_solve_kernel(BaArgs a)
                     if (r / 6 == c / 6) { const int f = r / 6; u = s_U[f * 21 + sym_idx(r % 6, c % 6, 6)]; }
                     s_L[r * n + c] = u - s_red[sym_idx(r, c, n)];
                 }
-            s_ok = cholesky(s_L, n);
+            s_ok = n == 12 ? cholesky<12>(s_L) : cholesky<6>(s_L);
         }
         __syncthreads();
         if (tid < n) {                                      // column tid of the inverse: solve L L^T x = e_tid
             double col[12], x[12];
             for (int k = 0; k < n; ++k) col[k] = k == tid ? 1.0 : 0.0;
-            if (s_ok) cholesky_solve(s_L, n, col, x);
+            if (s_ok) { if (n == 12) cholesky_solve<12>(s_L, col, x); else cholesky_solve<6>(s_L, col, x); }
             for (int k = 0; k < n; ++k) s_S[k * n + tid] = s_ok ? x[k] : NAN;
         }
         __syncthreads();
