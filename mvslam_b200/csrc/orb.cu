@@ -651,6 +651,12 @@ orb_describe_kernel(const __grid_constant__ OrbGeom g, OrbBuffers b, OrbDescribe
     const int total = s_start[kOrbLevels];
     const int lane = threadIdx.x & 31;
     const int warps = gridDim.x * 8;
+    // circular patch: lane = column u + 15; bit v + 15 of rowmask says whether (u, v) lies inside (|u| <= umax[|v|])
+    const int u = lane - kOrbHalfPatch;
+    uint32_t rowmask = 0;
+    if (lane < 31)
+        for (int v = -kOrbHalfPatch; v <= kOrbHalfPatch; ++v)
+            if (abs(u) <= g.umax[abs(v)]) rowmask |= 1u << (v + kOrbHalfPatch);
     const size_t out0 = (size_t)d.img_off[img];
     const uint8_t *pyr = b.pyr + (size_t)img * g.slab, *blur = b.blur + (size_t)img * g.slab;
     for (int base = (blockIdx.x * 8 + (threadIdx.x >> 5)) * G; base < total; base += warps * G) {
@@ -669,19 +675,18 @@ orb_describe_kernel(const __grid_constant__ OrbGeom g, OrbBuffers b, OrbDescribe
         }
         const int n_here = min(G, total - base);
         // ICAngles: moments over the circular patch of the un-blurred level; lane = u + 15
-        const int u = lane - kOrbHalfPatch;
         int m10_own = 0, m01_own = 0;
         for (int j = 0; j < n_here; ++j) {
             const int jl = __shfl_sync(0xffffffffu, l, j), jx = __shfl_sync(0xffffffffu, cx, j), jy = __shfl_sync(0xffffffffu, cy, j);
             const int pitch = g.lv[jl].pitch;
             const uint8_t *im = pyr + g.lv[jl].off + (size_t)jy * pitch + jx;
             int m10 = 0, m01 = 0;
-            if (lane < 31) {
-                for (int v = -kOrbHalfPatch; v <= kOrbHalfPatch; ++v) {
-                    if (abs(u) <= g.umax[abs(v)]) {
-                        const int p = im[v * pitch + u];
-                        m10 += u * p; m01 += v * p;
-                    }
+            const uint8_t *row = im - kOrbHalfPatch * pitch + u;
+#pragma unroll
+            for (int v = -kOrbHalfPatch; v <= kOrbHalfPatch; ++v, row += pitch) {
+                if ((rowmask >> (v + kOrbHalfPatch)) & 1u) {
+                    const int p = *row;
+                    m10 += u * p; m01 += v * p;
                 }
             }
 #pragma unroll
