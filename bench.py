@@ -231,6 +231,26 @@ def extraction_extra(ctx, stream, n_img=256, nf=2000, steps=5, cpu=True):
     vo_res = np.frombuffer(res_t.numpy(), dtype=mvs.RESULT_DTYPE)
     ctx.frames_clear()
     pyr_px = sum(int(round(w / 1.2 ** l)) * int(round(h / 1.2 ** l)) for l in range(8))
+    # HBM roofline of every extraction kernel: algorithmic bytes per launch / measured launch time
+    hbm_peak = 6444.4
+    mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(mp):
+        hbm_peak = json.load(open(mp)).get("hbm_gbs", hbm_peak)
+    nkp = float(counts.sum())
+    cand = 3.0 * nkp                                  # 3x3 maxima per image are ~3x the kept keypoints on these frames
+    alg = dict(orb_pyramid=n_img * (w * h + 2.0 * pyr_px),            # input read + every level written and read once by the next
+               orb_fast=n_img * 1.0 * pyr_px + 8.0 * cand,            # each level read once, candidate list written
+               orb_harris=cand * (8.0 + 81.0),                        # candidate + its 9x9 neighbourhood
+               orb_select=cand * 8.0 + nkp * 4.0,
+               orb_blur=n_img * 2.0 * pyr_px,                         # read + write
+               orb_describe=nkp * (709.0 + 512.0 + 32.0 + 24.0 + 8.0))   # patch, steered tests, descriptor, record, frame point
+    roof = {}
+    for k_, b_ in alg.items():
+        ms_k = prof[k_][0] / steps
+        if ms_k > 0:
+            gbs = b_ / (ms_k * 1e-3) / 1e9
+            roof[k_] = dict(bound="hbm", algorithmic_bytes=int(b_), launch_ms=round(ms_k, 4), achieved=round(gbs, 1), peak=hbm_peak,
+                            unit="GB/s", frac=round(gbs / hbm_peak, 4))
     r = dict(what="VisualFeature::extract = cv::ORB(nfeatures) detect+compute, bit-exact vs cv2 (tests/test_gpu_orb.py)",
              images_per_step=n_img, width=w, height=h, n_features=nf, keypoints_per_image=float(counts.mean()),
              value=n_img / (ms * 1e-3), unit="frames/s", ms_per_step=ms, gpu_launches_per_step=int(launches),
@@ -242,7 +262,8 @@ def extraction_extra(ctx, stream, n_img=256, nf=2000, steps=5, cpu=True):
                                   note="host images -> mvs_orb_extract(append_frames) -> mvs_pair_batch over consecutive pairs "
                                        "(max_dist 10, H 1024, bounded matcher) -> records on the host"),
              stage_ms_per_step={k: round(v[0] / steps, 4) for k, v in prof.items() if k.startswith("orb")},
-             pyramid_pixels_per_image=pyr_px)
+             pyramid_pixels_per_image=pyr_px, roofline=roof,
+             roofline_note="small-image kernels: issue- or latency-bound (profiles/ncu_summary), far from the HBM line by design size")
     if cpu:
         try:
             import cv2
