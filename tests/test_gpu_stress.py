@@ -102,3 +102,27 @@ def test_ba_partial_priors_and_single_view_points(ctx):
     assert np.abs(g["points"] - o["points"]).max() < 1e-7 and np.abs(g["pose_t"][1] - o["poses"][1][1]).max() < 1e-8
     for j in range(n):
         assert np.abs(g["point_cov"][j] - o["point_cov"][j]).max() <= 1e-5 * np.abs(o["point_cov"][j]).max()
+
+
+def test_ba_many_random_problems_in_one_batch(ctx):
+    """40 seeded problems of mixed shape (one- and two-frame, 6..150 points) in a single call: cost, poses, points and
+    every marginal covariance against the oracle."""
+    from test_gpu_ba import pnp_case, sfm_case
+    cases = []
+    for k in range(40):
+        if k % 4 == 3:
+            cases.append(pnp_case(500 + k))
+        else:
+            n = [None, 6, 25, 150][k % 4] if k % 4 else None
+            cases.append(sfm_case(500 + k, n=n) if n else sfm_case(500 + k))
+    res = ctx.ba_solve_batch(np.eye(3), [c[2] for c in cases])
+    for k, ((s, prob, abi), g) in enumerate(zip(cases, res)):
+        o = prob.solve()
+        assert g["status"] == mvs.OK, k
+        assert abs(g["final_error"] - o["error"]) <= 1e-8 * max(o["error"], 1e-12), k
+        for f, (R, t) in enumerate(o["poses"]):
+            assert np.abs(g["pose_R"][f] - R).max() < 1e-7 and np.abs(g["pose_t"][f] - t).max() < 1e-7, k
+            assert np.abs(g["pose_cov"][f] - o["pose_cov"][f]).max() <= 1e-5 * np.abs(o["pose_cov"][f]).max(), k
+        assert np.abs(g["points"] - o["points"]).max() < 1e-7, k
+        for j, C in enumerate(o["point_cov"]):
+            assert np.abs(g["point_cov"][j] - C).max() <= 1e-5 * np.abs(C).max(), (k, j)
