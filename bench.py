@@ -487,7 +487,7 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (Hamming kNN): algorithmic popc32 ops / measured launch time
+    # ---- roofline of the dominant kernel (Hamming kNN): algorithmic ops / measured launch time
     counts = np.array([d.shape[0] for d in descs], np.int64)
     n_calls = (B + CH - 1) // CH
     desc_pairs = int((counts[pairs[:, 0]] * counts[pairs[:, 1]]).sum()) // n_calls     # per launch
@@ -516,19 +516,44 @@ def main():
             traffic = tj["dram_bytes"].get("knn2_hamming_kernel")
     tot_ms = max(sum(v[0] for v in prof.values()), 1e-9)
     stage_share = {s: round(prof[s][0] / tot_ms, 4) for s in mvs.STAGES[:7]}
-    roofline = dict(kernel="knn2_hamming_kernel", bound="int-pipes (XU popc / ALU lop3); not hbm, not tensor",
-                    achieved=8.0 * pair_rate / 1e9, peak=8.0 * pair_peak / 1e9,
-                    unit="G algorithmic popc32/s (8 per 256-bit descriptor pair, SURVEY 8d)", frac=pair_rate / pair_peak,
-                    binding_pipe="xu-popc" if popc_rate / 5.0 <= alu_rate / 18.0 else "alu",
-                    peak_source=("measured pipe rates (tools/ubench on this pool's B200, profiles/ubench_peaks.json)"
-                                 if peaks else "nominal 148 SM x (16 popc | 64 lop3)/clk x 1.965 GHz")
-                    + " / per-pair SASS mix 5 POPC + 15 LOP3 + 3 VIMNMX",
-                    launch_ms=launch_s * 1e3, desc_pairs_per_launch=desc_pairs, desc_pairs_per_s=pair_rate,
-                    hbm=dict(algorithmic_bytes=alg_bytes, achieved_gbs=alg_bytes / launch_s / 1e9, peak_gbs=hbm_peak,
-                             frac=alg_bytes / launch_s / 1e9 / hbm_peak,
-                             note="compute-bound kernel: the HBM fraction is reported for completeness only"),
-                    traffic=traffic, stage_share=stage_share,
-                    stage_ms_per_step={s: round(prof[s][0] / args.steps, 4) for s in mvs.STAGES[:7]})
+    hbm = dict(algorithmic_bytes=alg_bytes, achieved_gbs=alg_bytes / launch_s / 1e9, peak_gbs=hbm_peak,
+               frac=alg_bytes / launch_s / 1e9 / hbm_peak,
+               note="compute-bound kernel: the HBM fraction is reported for completeness only")
+    tensor_matcher = os.environ.get("MVS_MATCHER", "tc")[:1] != "p" and int(counts.max()) <= 32768
+    if tensor_matcher:
+        # knn2_hamming_tc_kernel: S = Q T^T over +-1 bytes on the tensor cores (tcgen05.mma kind::i8, K = 256), so one
+        # descriptor pair is 256 MACs = 512 integer ops.  Peak: int8 runs at twice the bf16 rate on sm_100a; the bf16 figure
+        # is the measured cuBLAS one of MEASURED_PEAKS.json (burst: the kernel is timed alone by its own stage events).
+        bf16 = 1701.5
+        if os.path.exists(mp):
+            bf16 = json.load(open(mp)).get("bf16_tflops", bf16)
+        tensor_peak = 2.0 * bf16
+        tops = 512.0 * pair_rate / 1e12
+        # the epilogue's running top-2 (3 integer min/max per accumulator, ALU pipe) is the binding resource, not the MMA
+        vimnmx = peaks.get("vimnmx_per_s", 148 * 64 * 1.965e9)
+        if traffic is None and os.path.exists(tp):
+            tj = json.load(open(tp))
+            if tj.get("workload") == cfg["workload"] and B == 1024:
+                traffic = tj["dram_bytes"].get("knn2_hamming_tc_kernel")
+        roofline = dict(kernel="knn2_hamming_tc_kernel", bound="tensor", achieved=tops, peak=tensor_peak, unit="TOP/s (int8, 512 per descriptor pair)",
+                        frac=tops / tensor_peak,
+                        peak_source="2 x MEASURED_PEAKS.json bf16_tflops (kind::i8 issues at twice the bf16 rate on sm_100a)",
+                        epilogue_alu=dict(ops_per_pair=3, peak_pairs_per_s=vimnmx / 3.0, frac=pair_rate / (vimnmx / 3.0),
+                                          note="binding pipe: 3 VIMNMX per accumulator at the measured ALU rate (profiles/ubench_peaks.json)"),
+                        launch_ms=launch_s * 1e3, desc_pairs_per_launch=desc_pairs, desc_pairs_per_s=pair_rate,
+                        hbm=hbm, traffic=traffic, stage_share=stage_share,
+                        stage_ms_per_step={s: round(prof[s][0] / args.steps, 4) for s in mvs.STAGES[:7]})
+    else:
+        roofline = dict(kernel="knn2_hamming_kernel", bound="int-pipes (XU popc / ALU lop3); not hbm, not tensor",
+                        achieved=8.0 * pair_rate / 1e9, peak=8.0 * pair_peak / 1e9,
+                        unit="G algorithmic popc32/s (8 per 256-bit descriptor pair, SURVEY 8d)", frac=pair_rate / pair_peak,
+                        binding_pipe="xu-popc" if popc_rate / 5.0 <= alu_rate / 18.0 else "alu",
+                        peak_source=("measured pipe rates (tools/ubench on this pool's B200, profiles/ubench_peaks.json)"
+                                     if peaks else "nominal 148 SM x (16 popc | 64 lop3)/clk x 1.965 GHz")
+                        + " / per-pair SASS mix 5 POPC + 15 LOP3 + 3 VIMNMX",
+                        launch_ms=launch_s * 1e3, desc_pairs_per_launch=desc_pairs, desc_pairs_per_s=pair_rate,
+                        hbm=hbm, traffic=traffic, stage_share=stage_share,
+                        stage_ms_per_step={s: round(prof[s][0] / args.steps, 4) for s in mvs.STAGES[:7]})
     scored = res["n_matches"] >= 8                           # pairs that reach RANSAC
     m_total = int(res["n_matches"][scored].astype(np.int64).sum())
     evals = float(params["H"]) * m_total
@@ -575,7 +600,7 @@ def main():
     value = n_job * args.steps / (total_ms * 1e-3)
     line = dict(metric=METRIC, value=value, unit="pairs/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=total_ms / args.steps, higher_is_better=True, scaling="strong" if strong else "weak",
-                vs_baseline=None, dtype="u32-popc/f64",
+                vs_baseline=None, dtype="s8-mma/s32 + f64" if tensor_matcher else "u32-popc/f64",
                 data="bundled Tsukuba ORB features (host-extracted), no network" if args.workload == "tsukuba" else "synthetic",
                 config=dict(cfg, l2_policy="256 MiB flush buffer written between timed steps", solved_pairs_per_step=n_ok,
                             final_gather_ms=gather_ms),

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -58,6 +59,11 @@ struct mvs_ctx {
     std::vector<int32_t> h_off, h_cnt;
     // scratch frame table of the two-set matcher entry points
     DevBuf t_desc, t_foff, t_fcnt;
+    // tensor-core matcher (match_hamming_tc.cu): the descriptor tables expanded to one +-1 byte per bit ([rows][256]);
+    // rows [0, desc8_rows) of d_desc8 mirror d_desc
+    DevBuf d_desc8, t_desc8;
+    size_t desc8_rows = 0;
+    bool use_tc = true;          // MVS_MATCHER=popc selects the integer-pipe kernel (A/B measurements, > 32768 train descriptors)
     // workspace
     DevBuf d_pairs, d_partial, d_rev, d_matches, d_nmatch, d_points, d_state, d_Fall, d_pc, d_pr, d_mask,
         d_valid, d_tri, d_opts, d_oidx, d_results, d_table, d_in1, d_in2, d_knn_i, d_knn_d, d_counts, d_pres;
@@ -253,6 +259,24 @@ int run_geometry(mvs_ctx *ctx, int n_pairs, int p_stride, const RansacCfg &rc, b
     return MVS_OK;
 }
 
+// Tensor-core matcher eligibility: train index must fit the epilogue key, the expanded table must fit comfortably.
+bool tc_eligible(const mvs_ctx *ctx, int max_nq, int max_nt, bool cross, size_t table_rows)
+{
+    return ctx->use_tc && max_nt <= tc_max_train() && (!cross || max_nq <= tc_max_train()) && table_rows * 256 <= ((size_t)16 << 30);
+}
+
+// bring d_desc8 up to date with the first `total` rows of d_desc (lazy: only rows added since the last call are expanded)
+int sync_desc8(mvs_ctx *ctx, size_t total)
+{
+    if (ctx->d_desc8.cap < total * 256) { CK(ctx->d_desc8.ensure(total * 256)); ctx->desc8_rows = 0; }
+    if (ctx->desc8_rows < total) {
+        launch_expand_desc(ctx->d_desc.as<uint4>(), ctx->desc8_rows, total - ctx->desc8_rows, ctx->d_desc8.p, ctx->stream);
+        ctx->launches += 1; ctx->acc.launches[MVS_STAGE_KNN] += 1;
+        ctx->desc8_rows = total;
+    }
+    return MVS_OK;
+}
+
 int choose_splits(int q_tiles, int n_pairs, int nt_max)
 {
     const int train_tiles = std::max(1, (nt_max + 255) / 256);
@@ -336,6 +360,7 @@ int mvs_create(mvs_ctx **out, int device)
     if (prop.major != 10) return MVS_E_UNSUPPORTED;  // sm_100a binary only
     mvs_ctx *ctx = new mvs_ctx();
     ctx->device = device;
+    { const char *e = std::getenv("MVS_MATCHER"); ctx->use_tc = !(e && e[0] == 'p'); }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MVS_E_CUDA; }
     ctx->own_stream = true;
     std::memset(&ctx->acc, 0, sizeof(ctx->acc));
@@ -348,7 +373,7 @@ void mvs_destroy(mvs_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->d_desc, &ctx->d_kp, &ctx->d_foff, &ctx->d_fcnt, &ctx->t_desc, &ctx->t_foff, &ctx->t_fcnt,
+    DevBuf *bufs[] = {&ctx->d_desc, &ctx->d_kp, &ctx->d_foff, &ctx->d_fcnt, &ctx->t_desc, &ctx->t_foff, &ctx->t_fcnt, &ctx->d_desc8, &ctx->t_desc8,
                       &ctx->d_pairs, &ctx->d_partial, &ctx->d_rev, &ctx->d_matches, &ctx->d_nmatch, &ctx->d_points,
                       &ctx->d_state, &ctx->d_Fall, &ctx->d_pc, &ctx->d_pr, &ctx->d_mask, &ctx->d_valid, &ctx->d_tri,
                       &ctx->d_opts, &ctx->d_oidx, &ctx->d_results, &ctx->d_table, &ctx->d_in1, &ctx->d_in2,
@@ -441,8 +466,9 @@ static int match_two_sets(mvs_ctx *ctx, const uint8_t *query, int nq, const uint
     CK(cudaMemcpyAsync(ctx->t_foff.p, off, sizeof(off), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->t_fcnt.p, cnt, sizeof(cnt), cudaMemcpyHostToDevice, ctx->stream));
     const bool cross = mp && mp->cross_check;
-    const int splits = choose_splits((nq + 255) / 256, 1, nt);
-    const int rsplits = cross ? choose_splits((nt + 255) / 256, 1, nq) : 0;
+    const bool tc = tc_eligible(ctx, nq, nt, cross, (size_t)nq + nt);
+    const int splits = tc ? 2 : choose_splits((nq + 255) / 256, 1, nt);
+    const int rsplits = cross ? (tc ? 2 : choose_splits((nt + 255) / 256, 1, nq)) : 0;
     CK(ctx->d_partial.ensure((size_t)splits * nq * sizeof(uint2)));
     if (cross) CK(ctx->d_rev.ensure((size_t)rsplits * nt * sizeof(uint2)));
     CK(ctx->d_matches.ensure((size_t)nq * sizeof(mvs_match)));
@@ -451,8 +477,19 @@ static int match_two_sets(mvs_ctx *ctx, const uint8_t *query, int nq, const uint
     KnnArgs ka{};
     ka.desc = ctx->t_desc.as<uint4>(); ka.frame_off = ctx->t_foff.as<int32_t>(); ka.frame_cnt = ctx->t_fcnt.as<int32_t>();
     ka.pairs = nullptr; ka.partial = ctx->d_partial.as<uint2>(); ka.q_stride = nq; ka.reverse = 0;
-    ka.bound = want_knn ? 0 : search_bound(mp);
-    {
+    ka.bound = (want_knn || tc) ? 0 : search_bound(mp);
+    if (tc) {
+        CK(ctx->t_desc8.ensure(((size_t)nq + nt) * 256));
+        StageTimer t(ctx, MVS_STAGE_KNN, cross ? 3 : 2);
+        launch_expand_desc(ctx->t_desc.as<uint4>(), 0, (size_t)nq + nt, ctx->t_desc8.p, ctx->stream);
+        TcKnnArgs ta{};
+        ta.frame_off = ka.frame_off; ta.frame_cnt = ka.frame_cnt; ta.pairs = nullptr; ta.partial = ka.partial; ta.q_stride = nq; ta.reverse = 0;
+        CK(launch_knn2_hamming_tc(ctx->t_desc8.p, (size_t)nq + nt, ta, nq, 1, ctx->stream));
+        if (cross) {
+            ta.partial = ctx->d_rev.as<uint2>(); ta.q_stride = nt; ta.reverse = 1;
+            CK(launch_knn2_hamming_tc(ctx->t_desc8.p, (size_t)nq + nt, ta, nt, 1, ctx->stream));
+        }
+    } else {
         StageTimer t(ctx, MVS_STAGE_KNN, cross ? 2 : 1);
         launch_knn2_hamming(ka, nq, splits, 1, ctx->stream);
         if (cross) {
@@ -767,6 +804,7 @@ int mvs_frames_upload(mvs_ctx *ctx, int n_frames, const uint8_t *const *desc, co
     CK(cudaMemcpyAsync(ctx->d_fcnt.p, cnt.data(), (size_t)n_frames * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));  // off/cnt are stack/vector memory
     ctx->h_off.swap(off); ctx->h_cnt.swap(cnt);
+    ctx->desc8_rows = 0;
     return MVS_OK;
 }
 
@@ -794,8 +832,10 @@ static int pair_batch_chunk(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, con
     CK(cudaSetDevice(ctx->device));
     const int qs = max_nq;
     const bool cross = mparams && mparams->cross_check;
-    const int splits = choose_splits((max_nq + 255) / 256, n_pairs, max_nt);
-    const int rsplits = cross ? choose_splits((max_nt + 255) / 256, n_pairs, max_nq) : 0;
+    const size_t table_rows = (size_t)ctx->h_off[nf - 1] + (size_t)ctx->h_cnt[nf - 1];
+    const bool tc = tc_eligible(ctx, max_nq, max_nt, cross, table_rows);
+    const int splits = tc ? 2 : choose_splits((max_nq + 255) / 256, n_pairs, max_nt);
+    const int rsplits = cross ? (tc ? 2 : choose_splits((max_nt + 255) / 256, n_pairs, max_nq)) : 0;
     CK(ctx->d_pairs.ensure((size_t)n_pairs * sizeof(int2)));
     CK(ctx->d_partial.ensure((size_t)n_pairs * splits * qs * sizeof(uint2)));
     if (cross) CK(ctx->d_rev.ensure((size_t)n_pairs * rsplits * max_nt * sizeof(uint2)));
@@ -808,8 +848,18 @@ static int pair_batch_chunk(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, con
     KnnArgs ka{};
     ka.desc = ctx->d_desc.as<uint4>(); ka.frame_off = ctx->d_foff.as<int32_t>(); ka.frame_cnt = ctx->d_fcnt.as<int32_t>();
     ka.pairs = ctx->d_pairs.as<int2>(); ka.partial = ctx->d_partial.as<uint2>(); ka.q_stride = qs; ka.reverse = 0;
-    ka.bound = search_bound(mparams);
-    {
+    ka.bound = tc ? 0 : search_bound(mparams);     // the tensor-core kernel evaluates every pair: nothing to bound
+    if (tc) {
+        StageTimer t(ctx, MVS_STAGE_KNN, cross ? 2 : 1);
+        if ((st = sync_desc8(ctx, table_rows)) != MVS_OK) return st;
+        TcKnnArgs ta{};
+        ta.frame_off = ka.frame_off; ta.frame_cnt = ka.frame_cnt; ta.pairs = ka.pairs; ta.partial = ka.partial; ta.q_stride = qs; ta.reverse = 0;
+        CK(launch_knn2_hamming_tc(ctx->d_desc8.p, table_rows, ta, max_nq, n_pairs, ctx->stream));
+        if (cross) {
+            ta.partial = ctx->d_rev.as<uint2>(); ta.q_stride = max_nt; ta.reverse = 1;
+            CK(launch_knn2_hamming_tc(ctx->d_desc8.p, table_rows, ta, max_nt, n_pairs, ctx->stream));
+        }
+    } else {
         StageTimer t(ctx, MVS_STAGE_KNN, cross ? 2 : 1);
         launch_knn2_hamming(ka, max_nq, splits, n_pairs, ctx->stream);
         if (cross) {
@@ -878,6 +928,7 @@ int mvs_frames_clear(mvs_ctx *ctx)
 {
     if (!ctx) return MVS_E_BAD_ARG;
     ctx->h_off.clear(); ctx->h_cnt.clear();
+    ctx->desc8_rows = 0;
     return MVS_OK;
 }
 

@@ -18,6 +18,16 @@ struct KnnArgs {
     uint32_t bound;            // bounded search: distances >= bound are "far" (0 = evaluate everything)
 };
 
+// tensor-core matcher (match_hamming_tc.cu): same frame table, descriptors expanded to one byte per bit ([rows][256])
+struct TcKnnArgs {
+    const int32_t *frame_off;
+    const int32_t *frame_cnt;
+    const int2 *pairs;         // as KnnArgs
+    uint2 *partial;            // [pairs][2][q_stride]: the two column halves of the train tiles are the "splits"
+    int q_stride;
+    int reverse;
+};
+
 struct FinalizeArgs {
     const int32_t *frame_off;
     const int32_t *frame_cnt;
@@ -94,6 +104,10 @@ struct FinishArgs {
 };
 
 void launch_knn2_hamming(const KnnArgs &a, int max_nq, int splits, int n_pairs, cudaStream_t s);
+int tc_max_train();            // largest train set of the tensor-core matcher
+bool tc_kind_i8();             // operand kind of the expanded table (S8, or E4M3 with MVS_TC_KIND=f8)
+void launch_expand_desc(const uint4 *desc, size_t row_begin, size_t n_rows, void *desc8, cudaStream_t s);
+cudaError_t launch_knn2_hamming_tc(const void *desc8, size_t total_rows, const TcKnnArgs &a, int max_nq, int n_pairs, cudaStream_t s);
 int finalize_sort_capacity(int max_nq);
 cudaError_t launch_match_finalize(const FinalizeArgs &a, int max_nq, int n_pairs, cudaStream_t s);
 void launch_normalize_points(const double *xy1, const double *xy2, int n, const NormArgs &a, double *pts, PairState *st,

@@ -349,6 +349,13 @@ def test_profile_and_launch_counters(ctx, tsukuba):
     n0 = ctx.kernel_launches()
     ctx.pair_batch([(0, 1)] * 8, tsukuba["K"], max_dist=10.0, H=64, details=False)
     prof = ctx.profile_read()
+    # first batch after an upload: the 7 stage kernels + the one-off expansion of the new frames for the tensor-core matcher
+    assert ctx.kernel_launches() - n0 == 8 and prof["knn"][1] == 2
+    assert all(prof[s][1] == 1 and prof[s][0] > 0 for s in mvs.STAGES[1:7])
+    n0 = ctx.kernel_launches()
+    ctx.profile_read(reset=True)
+    ctx.pair_batch([(0, 1)] * 8, tsukuba["K"], max_dist=10.0, H=64, details=False)
+    prof = ctx.profile_read()
     ctx.profile_enable(False)
     assert ctx.kernel_launches() - n0 == 7
     assert all(prof[s][1] == 1 and prof[s][0] > 0 for s in mvs.STAGES[:7])
