@@ -105,7 +105,6 @@ struct FinishArgs {
 
 void launch_knn2_hamming(const KnnArgs &a, int max_nq, int splits, int n_pairs, cudaStream_t s);
 int tc_max_train();            // largest train set of the tensor-core matcher
-bool tc_kind_i8();             // operand kind of the expanded table (S8, or E4M3 with MVS_TC_KIND=f8)
 void launch_expand_desc(const uint4 *desc, size_t row_begin, size_t n_rows, void *desc8, cudaStream_t s);
 cudaError_t launch_knn2_hamming_tc(const void *desc8, size_t total_rows, const TcKnnArgs &a, int max_nq, int n_pairs, cudaStream_t s);
 int finalize_sort_capacity(int max_nq);

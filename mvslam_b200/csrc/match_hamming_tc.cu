@@ -3,16 +3,15 @@
 // Same contract as knn2_hamming_kernel (match_hamming.cu; cv::BFMatcher(NORM_HAMMING).knnMatch(k=2) of
 // reference source/vision/visual-feature.cpp:59-62): per query the two smallest (distance, trainIdx) keys, bit-exact.
 //
-//   Every descriptor bit b is stored as the 8-bit value s(b) = +1 / -1 (expand_desc_kernel, 256 B per descriptor).
-//   For two descriptors  S = sum_k s(q_k) s(t_k) = 256 - 2 hamming(q, t),  an even integer in [-256, 256]: the
-//   products are +-1 and the partial sums are small integers, so the accumulation is exact in S32 (kind::i8) and in
-//   FP32 (kind::f8f6f4, E4M3 +-1.0) alike and  hamming = 128 - S/2  is the popcount distance, not an approximation.
+//   Every descriptor bit b is stored as the signed byte s(b) = +8 / -8 (expand_desc_kernel, 256 B per descriptor).
+//   For two descriptors  sum_k s(q_k) s(t_k) = 64 (256 - 2 hamming(q, t)):  the products are +-64 and the partial sums
+//   small integers, exact in the S32 accumulators of kind::i8, so  hamming  is the popcount distance, not an
+//   approximation.  (kind::f8f6f4 with E4M3 +-1 was measured too: exact as well, 13 % slower.)
 //
-//   S = Q T^T runs as tcgen05.mma (M = N = 128, K = 8 x 32) with both operands staged by TMA (128-byte swizzle) and
-//   the accumulators double-buffered in TMEM.  The epilogue never materialises S: thread <-> (query row, column half)
-//   turns each accumulator into the sortable key  hamming * 32768 + trainIdx  with one FMA-pipe instruction and keeps a
-//   running (best, second) pair with 3 integer min/max per element.  The epilogue's min/max instructions, not the
-//   tensor pipe, bound the kernel.
+//   The contraction runs as tcgen05.mma (M = N = 128, K = 8 x 32, plus a ninth K step that adds the column index, see
+//   the kernel) with both operands staged by TMA (128-byte swizzle) and the accumulators double-buffered in TMEM.  The
+//   epilogue never materialises the score matrix: thread <-> (query row, column half) keeps a running (best, second)
+//   pair on packed 16-bit keys, 1.75 ALU instructions per accumulator.
 //
 // Warp roles (320 threads, 2 CTAs per SM so that one CTA's TMA/MMA overlaps the other's epilogue):
 //   warp 0   TMA producer (query tile once, train tiles through a STAGES-deep mbarrier ring)
@@ -38,8 +37,7 @@ constexpr int KSLABS = 2;            // 256 one-byte elements per descriptor
 constexpr int EPI_WARPS = 8;         // two per TMEM lane quarter: each takes half of a tile's columns
 constexpr int TC_THREADS = 64 + EPI_WARPS * 32;
 constexpr uint32_t TMEM_COLS = 2 * BN;   // two accumulator buffers
-constexpr int TC_MAX_TRAIN = 32768;  // trainIdx field of the epilogue key (15 bits: the key stays below 2^24, exact in FP32)
-constexpr float kKeyScale = 16384.f; // key = (128 - S/2) * 32768 + idx = 4194304 - 16384 S + idx
+constexpr int TC_MAX_TRAIN = 32768;  // trainIdx field of the thread's running key (hamming * 32768 + trainIdx)
 
 // ------------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -90,25 +88,16 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr)
     d |= (uint64_t)2 << 61;
     return d;
 }
-// instruction descriptor: A and B K-major, M = 128, N = BN;  kind::i8: S8 x S8 -> S32;  kind::f8f6f4: E4M3 x E4M3 -> F32
+// instruction descriptor: kind::i8, S8 x S8 -> S32, A and B K-major, M = 128, N = BN
 constexpr uint32_t kInstrDescI8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-constexpr uint32_t kInstrDescF8 = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
-template <bool I8>
-__device__ __forceinline__ void umma_8bit(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate)
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate)
 {
-    if (I8)
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-            ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(kInstrDescI8), "r"(accumulate) : "memory");
-    else
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
-            ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(kInstrDescF8), "r"(accumulate) : "memory");
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(kInstrDescI8), "r"(accumulate) : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
@@ -131,25 +120,7 @@ __device__ __forceinline__ void top2(uint32_t &b1, uint32_t &b2, uint32_t key)
     b2 = min(b2, hi);
 }
 
-// accumulator -> key.  FP32 accumulators: the key is an integer-valued float below 2^24, and non-negative floats order
-// like their bit patterns, so the running pair is kept with integer min/max on the bits (no conversion in the loop).
-template <bool I8>
-__device__ __forceinline__ uint32_t make_key(uint32_t acc, int base_i, float base_f, int j)
-{
-    if (I8) return (uint32_t)((base_i + j) - (int)acc * (int)kKeyScale);
-    return __float_as_uint(fmaf(__uint_as_float(acc), -kKeyScale, base_f + (float)j));
-}
-
-template <bool I8>
-__device__ __forceinline__ uint32_t export_key(uint32_t k)
-{   // epilogue key -> the (distance << kIdxBits | trainIdx) key of match_finalize_kernel
-    if (k == kKeyNone) return kKeyNone;
-    const uint32_t ki = I8 ? k : (uint32_t)__uint_as_float(k);
-    return ((ki >> 15) << kIdxBits) | (ki & 32767u);
-}
-
-// ------------------------------------------------------------------------------------------ bits -> +-1 bytes
-template <bool I8>
+// ------------------------------------------------------------------------------------------ bits -> +-8 bytes
 __global__ void __launch_bounds__(256)
 expand_desc_kernel(const uint32_t *__restrict__ desc, size_t word_begin, size_t n_words, uint4 *__restrict__ out)
 {
@@ -160,7 +131,7 @@ expand_desc_kernel(const uint32_t *__restrict__ desc, size_t word_begin, size_t 
 #pragma unroll
     for (int nib = 0; nib < 8; ++nib) {
         const uint32_t spread = (((w >> (4 * nib)) & 15u) * 0x00204081u) & 0x01010101u;   // bit k -> byte k
-        o[nib] = I8 ? (0xFFFFFFFFu ^ (spread * 0xFEu)) : (0xB8B8B8B8u ^ (spread << 7));    // 1 -> +1, 0 -> -1
+        o[nib] = 0xF8F8F8F8u ^ (spread * 0xF0u);                                           // 1 -> +8, 0 -> -8
     }
     uint4 *dst = out + (word_begin + i) * 2;
     dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
@@ -168,7 +139,21 @@ expand_desc_kernel(const uint32_t *__restrict__ desc, size_t word_begin, size_t 
 }
 
 // ------------------------------------------------------------------------------------------ GEMM + running top-2
-template <bool I8, int STAGES>
+// Epilogue arithmetic.  With every bit stored as +-8 the contraction gives 64 S = 128 (S/2); a ninth K step over one
+// constant slab (query side: 1 in byte 0 of every row; train side: 127 - column-in-tile in byte 32 of every row) adds
+// 127 - c, so the accumulator itself is the signed 16-bit key
+//      k16 = 128 (128 - hamming) + (127 - c)          in [-16384, 16511]
+// that orders the columns of a tile by (smaller distance, then smaller index) under MAX.  Two accumulators are packed
+// into one register with a single PRMT and the running (best, second) pair of both 16-bit lanes costs 2.5 VIMNMX.S16x2
+// per register: 1.75 ALU instructions per accumulator and none on the FMA pipe.  At the end of a tile the four lane
+// results are widened to  hamming * 32768 + trainIdx  and merged into the thread's 32-bit pair (minimum = best).
+__device__ __forceinline__ uint32_t widen_key(uint32_t k16, uint32_t tile_base)
+{
+    const int k = (int)(short)k16;                         // empty lane: -32768 -> distance 384, dropped at the export
+    return (uint32_t)(128 - (k >> 7)) * 32768u + tile_base + (127u - ((uint32_t)k & 127u));
+}
+
+template <int STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
 {
@@ -186,15 +171,17 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
     const int row_q = a.frame_off[fq] + q0, row_t = a.frame_off[ft];
     const int n_tiles = (nt + BN - 1) / BN;
 
-    uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t *sA = base;
+    // the launch requests no static shared memory, so the dynamic window starts 1024-byte aligned (checked)
+    uint8_t *sA = smem_raw;
     uint8_t *sB = sA + KSLABS * BM * SLAB;
-    uint64_t *bars = (uint64_t *)(sB + STAGES * KSLABS * BN * SLAB);
+    uint8_t *sX = sB + STAGES * KSLABS * BN * SLAB;        // constant slab of the ninth K step
+    uint64_t *bars = (uint64_t *)(sX + BN * SLAB);
     uint64_t *barA = bars, *full = bars + 1, *empty = full + STAGES, *tfull = empty + STAGES, *tempty = tfull + 2;
     uint32_t *tmem_slot = (uint32_t *)(tempty + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
+        if (smem_u32(smem_raw) & 1023u) __trap();
         mbar_init(barA, 1);
         for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, EPI_WARPS * 32); }
@@ -204,6 +191,16 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    // constant slab in the 128-byte-swizzle layout (16-byte chunk index XOR row mod 8): row r holds 1 at byte 0 (read as
+    // the query operand, K bytes 0..31) and 127 - r at byte 32 (read as the train operand, K bytes 32..63)
+    for (int i = threadIdx.x; i < BN * SLAB / 16; i += TC_THREADS) {
+        const int r = i >> 3, chunk = (i & 7) ^ (r & 7);
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (chunk == 0) v.x = 1u;
+        if (chunk == 2) v.x = (uint32_t)(127 - r);
+        reinterpret_cast<uint4 *>(sX)[i] = v;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> visible to the tensor core
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
@@ -226,6 +223,7 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
             mbar_wait(barA, 0);
+            const uint64_t x_a = make_smem_desc(smem_u32(sX)), x_b = make_smem_desc(smem_u32(sX) + 32);
             for (int i = 0; i < n_tiles; ++i) {
                 const int s = i % STAGES, acc = i & 1;
                 if (i >= 2) mbar_wait(tempty + acc, ((i >> 1) - 1) & 1);   // epilogue drained this accumulator
@@ -238,9 +236,10 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
                     const uint32_t b_addr = smem_u32(sB + (s * KSLABS + ks) * BN * SLAB);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)   // UMMA_K = 32 one-byte elements = 32 bytes inside the swizzle atom
-                        umma_8bit<I8>(d_tmem, make_smem_desc(a_addr + k * 32), make_smem_desc(b_addr + k * 32), (ks | k) ? 1u : 0u);
+                        umma_i8(d_tmem, make_smem_desc(a_addr + k * 32), make_smem_desc(b_addr + k * 32), (ks | k) ? 1u : 0u);
                 }
                 tcgen05_commit(empty + s);     // train stage reusable once these MMAs retire
+                umma_i8(d_tmem, x_a, x_b, 1u);  // + (127 - column): the index half of the key
                 tcgen05_commit(tfull + acc);   // accumulator ready for the epilogue
             }
         }
@@ -249,8 +248,7 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
         const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;                // which 64 columns of every 128-column tile
         const int q = q0 + quarter * 32 + lane;          // row within the tile == TMEM lane
-        // two independent running pairs (even / odd columns) halve the dependent min/max chain; merged at the end
-        uint32_t e1 = kKeyNone, e2 = kKeyNone, o1 = kKeyNone, o2 = kKeyNone;
+        uint32_t g1 = kKeyNone, g2 = kKeyNone;
         for (int i = 0; i < n_tiles; ++i) {
             const int acc = i & 1;
             const int col0 = i * BN + half * (BN / 2);
@@ -258,32 +256,45 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
             const bool ragged = col0 + BN / 2 > nt;      // warp-uniform: only a frame's last tile
+            uint32_t a1 = 0x80008000u, a2 = 0x80008000u, b1 = 0x80008000u, b2 = 0x80008000u;   // two chains for ILP
 #pragma unroll 1
             for (int c0 = 0; c0 < BN / 2; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(taddr + c0, v);
-                const int base_i = 4194304 + col0 + c0;
-                const float base_f = (float)base_i;
                 if (!ragged) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        top2(e1, e2, make_key<I8>(v[j], base_i, base_f, j));
-                        top2(o1, o2, make_key<I8>(v[j + 1], base_i, base_f, j + 1));
+                    for (int m = 0; m < 16; m += 2) {
+                        const uint32_t pa = __byte_perm(v[2 * m], v[2 * m + 1], 0x5410);
+                        const uint32_t pb = __byte_perm(v[2 * m + 2], v[2 * m + 3], 0x5410);
+                        const uint32_t la = __vmins2(a1, pa), lb = __vmins2(b1, pb);
+                        a1 = __vmaxs2(a1, pa); b1 = __vmaxs2(b1, pb);
+                        a2 = __vmaxs2(a2, la); b2 = __vmaxs2(b2, lb);
                     }
-                } else {
+                } else {                                 // rows of the next frame / zero fill lose to every real key
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const uint32_t key = make_key<I8>(v[j], base_i, base_f, j);
-                        top2(e1, e2, (col0 + c0 + j < nt) ? key : kKeyNone);   // rows of the next frame / zero fill
+                    for (int m = 0; m < 16; ++m) {
+                        const int c = col0 + c0 + 2 * m;
+                        const uint32_t pk = __byte_perm(c < nt ? v[2 * m] : 0x8000u, c + 1 < nt ? v[2 * m + 1] : 0x8000u, 0x5410);
+                        const uint32_t lo = __vmins2(a1, pk);
+                        a1 = __vmaxs2(a1, pk); a2 = __vmaxs2(a2, lo);
                     }
                 }
             }
             tcgen05_fence_before();
             mbar_arrive(tempty + acc);
+            // the tile's two best of each lane pair -> the thread's running pair
+            const uint32_t n1 = __vmaxs2(a1, b1), n2 = __vimax3_s16x2(__vmins2(a1, b1), a2, b2);
+            const uint32_t tile_base = (uint32_t)(i * BN);
+            top2(g1, g2, widen_key(n1 & 0xFFFFu, tile_base));
+            top2(g1, g2, widen_key(n1 >> 16, tile_base));
+            top2(g1, g2, widen_key(n2 & 0xFFFFu, tile_base));
+            top2(g1, g2, widen_key(n2 >> 16, tile_base));
         }
-        top2(e1, e2, o1);
-        top2(e1, e2, o2);
-        if (q < nq) a.partial[((size_t)pair * 2 + half) * a.q_stride + q] = make_uint2(export_key<I8>(e1), export_key<I8>(e2));
+        if (q < nq) {
+            const uint32_t x1 = (g1 >> 15) > 256u ? kKeyNone : (((g1 >> 15) << kIdxBits) | (g1 & 32767u));
+            const uint32_t x2 = (g2 >> 15) > 256u ? kKeyNone : (((g2 >> 15) << kIdxBits) | (g2 & 32767u));
+            a.partial[((size_t)pair * 2 + half) * a.q_stride + q] = make_uint2(x1, x2);
+        }
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -311,13 +322,12 @@ EncodeTiledFn get_encode_fn()
     return fn;
 }
 
-template <bool I8>
 cudaError_t launch_tc(const CUtensorMap &map, const TcKnnArgs &a, int max_nq, int n_pairs, cudaStream_t s)
 {
     constexpr int STAGES = 2;   // 2 CTAs per SM (<= 113 KB each)
-    const size_t smem = 1024 + (size_t)KSLABS * BM * SLAB + (size_t)STAGES * KSLABS * BN * SLAB +
+    const size_t smem = (size_t)KSLABS * BM * SLAB + (size_t)STAGES * KSLABS * BN * SLAB + (size_t)BN * SLAB +
                         (1 + 2 * STAGES + 4) * sizeof(uint64_t) + 16;
-    auto kern = knn2_hamming_tc_kernel<I8, STAGES>;
+    auto kern = knn2_hamming_tc_kernel<STAGES>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -333,25 +343,11 @@ cudaError_t launch_tc(const CUtensorMap &map, const TcKnnArgs &a, int max_nq, in
 
 int tc_max_train() { return TC_MAX_TRAIN; }
 
-bool tc_kind_i8()
-{
-    static int kind = -1;
-    if (kind < 0) {
-        const char *e = getenv("MVS_TC_KIND");      // "f8": E4M3 operands with FP32 accumulators instead of S8 / S32
-        kind = (e && e[0] == 'f') ? 0 : 1;
-    }
-    return kind == 1;
-}
-
 void launch_expand_desc(const uint4 *desc, size_t row_begin, size_t n_rows, void *desc8, cudaStream_t s)
 {
     if (!n_rows) return;
     const size_t n_words = n_rows * 8;
-    const unsigned blocks = (unsigned)((n_words + 255) / 256);
-    if (tc_kind_i8())
-        expand_desc_kernel<true><<<blocks, 256, 0, s>>>((const uint32_t *)desc, row_begin * 8, n_words, (uint4 *)desc8);
-    else
-        expand_desc_kernel<false><<<blocks, 256, 0, s>>>((const uint32_t *)desc, row_begin * 8, n_words, (uint4 *)desc8);
+    expand_desc_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, s>>>((const uint32_t *)desc, row_begin * 8, n_words, (uint4 *)desc8);
 }
 
 cudaError_t launch_knn2_hamming_tc(const void *desc8, size_t total_rows, const TcKnnArgs &a, int max_nq, int n_pairs, cudaStream_t s)
@@ -366,7 +362,7 @@ cudaError_t launch_knn2_hamming_tc(const void *desc8, size_t total_rows, const T
     if (fn(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(desc8), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return cudaErrorInvalidValue;
-    return tc_kind_i8() ? launch_tc<true>(map, a, max_nq, n_pairs, s) : launch_tc<false>(map, a, max_nq, n_pairs, s);
+    return launch_tc(map, a, max_nq, n_pairs, s);
 }
 
 }  // namespace mvs

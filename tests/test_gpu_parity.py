@@ -25,6 +25,22 @@ def ctx():
     c.close()
 
 
+@pytest.fixture(scope="module")
+def ctx_popc():
+    """A context on the integer-pipe matcher (knn2_hamming_kernel): the kernel choice is read at mvs_create."""
+    old = os.environ.get("MVS_MATCHER")
+    os.environ["MVS_MATCHER"] = "popc"
+    try:
+        c = mvs.Context(0)
+    finally:
+        if old is None:
+            del os.environ["MVS_MATCHER"]
+        else:
+            os.environ["MVS_MATCHER"] = old
+    yield c
+    c.close()
+
+
 def same_up_to_scale(Fa, Fb, atol):
     Fa = Fa / np.linalg.norm(Fa); Fb = Fb / np.linalg.norm(Fb)
     return min(np.abs(Fa - Fb).max(), np.abs(Fa + Fb).max()) <= atol
@@ -60,6 +76,63 @@ def test_knn2_hamming_bit_exact(ctx, nq, nt, rand_bytes):
     ig, dg = ctx.knn2_hamming(q, t)
     io, do = orc.knn2_hamming(q, t)
     assert np.array_equal(ig, io) and np.array_equal(dg, do)
+
+
+def test_tensor_matcher_extreme_distances_and_duplicates(ctx):
+    """knn2_hamming_tc_kernel: S = 256 - 2 d must be exact at both ends (d = 0, d = 256), with duplicated train rows
+    (lowest index wins) and a train set that ends inside a 128-row tile."""
+    rng = np.random.default_rng(5)
+    t = rng.integers(0, 256, (200, 32), dtype=np.uint8)
+    t[0] = 0; t[1] = 255; t[7] = t[150]; t[199] = t[3]
+    q = np.concatenate([t[:5], ~t[:5], np.zeros((1, 32), np.uint8), np.full((1, 32), 255, np.uint8)])
+    ig, dg = ctx.knn2_hamming(q, t)
+    io, do = orc.knn2_hamming(q, t)
+    assert np.array_equal(ig, io) and np.array_equal(dg, do)
+    assert dg[0, 0] == 0 and dg[10, 0] == 0 and dg[11, 0] == 0
+    only = ctx.knn2_hamming(np.zeros((3, 32), np.uint8), np.full((2, 32), 255, np.uint8))
+    assert np.array_equal(only[1], np.full((3, 2), 256)) and np.array_equal(only[0], np.tile([0, 1], (3, 1)))
+
+
+@pytest.mark.parametrize("nq,nt,rand_bytes", [(129, 128, 32), (128, 129, 32), (1000, 127, 1), (2000, 2047, 32), (300, 4097, 2)])
+@pytest.mark.parametrize("cross", [False, True])
+def test_tensor_matcher_equals_popc_matcher(ctx, ctx_popc, nq, nt, rand_bytes, cross):
+    rng = np.random.default_rng(nq + 3 * nt)
+    q = np.zeros((nq, 32), np.uint8); t = np.zeros((nt, 32), np.uint8)
+    q[:, :rand_bytes] = rng.integers(0, 256, (nq, rand_bytes)); t[:, :rand_bytes] = rng.integers(0, 256, (nt, rand_bytes))
+    a, b = ctx.knn2_hamming(q, t), ctx_popc.knn2_hamming(q, t)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    ma, mb = ctx.match_hamming(q, t, 0.8, -1.0, cross), ctx_popc.match_hamming(q, t, 0.8, -1.0, cross)
+    assert np.array_equal(ma, mb) and np.array_equal(ma, as_mvs(orc.match_hamming(q, t, 0.8, -1.0, cross)))
+
+
+def test_more_than_32768_train_descriptors_take_the_popc_kernel(ctx):
+    """The tensor-core epilogue key holds 15 index bits; larger train sets run on knn2_hamming_kernel."""
+    rng = np.random.default_rng(9)
+    q = rng.integers(0, 256, (200, 32), dtype=np.uint8); t = rng.integers(0, 256, (33000, 32), dtype=np.uint8)
+    t[32900] = q[5]
+    ig, dg = ctx.knn2_hamming(q, t)
+    io, do = orc.knn2_hamming(q, t)
+    assert np.array_equal(ig, io) and np.array_equal(dg, do) and ig[5, 0] == 32900
+
+
+def test_pair_batch_records_identical_on_both_matchers(ctx, ctx_popc, tsukuba):
+    descs = [tsukuba[f"desc{i}"] for i in range(1, 6)]; kps = [tsukuba[f"kp{i}"] for i in range(1, 6)]
+    pairs = [(a, b) for a in range(5) for b in range(5) if a != b]
+    out = []
+    for c in (ctx, ctx_popc):
+        c.frames_upload(descs, kps)
+        out.append(c.pair_batch(pairs, tsukuba["K"], max_dist=30.0, H=64, seed=3, cross_check=True))
+        out.append(c.pair_batch(pairs, tsukuba["K"], max_dist=10.0, H=64, seed=3))
+    for k in (0, 1):
+        ra, rb = out[k][0], out[k + 2][0]
+        for f in ra.dtype.names:
+            assert np.array_equal(ra[f], rb[f], equal_nan=True), (k, f, ra[f], rb[f])
+        for i in range(len(pairs)):
+            m, n = ra["n_matches"][i], ra["n_points"][i]
+            assert np.array_equal(out[k][1]["matches"][i][:m], out[k + 2][1]["matches"][i][:m])
+            assert np.array_equal(out[k][1]["mask"][i][:m], out[k + 2][1]["mask"][i][:m])
+            assert np.array_equal(out[k][1]["points"][i][:n], out[k + 2][1]["points"][i][:n])
+            assert np.array_equal(out[k][1]["indexes"][i][:n], out[k + 2][1]["indexes"][i][:n])
 
 
 @pytest.mark.parametrize("max_dist,cross", [(-1.0, False), (10.0, False), (30.0, False), (-1.0, True), (64.0, True)])
@@ -426,8 +499,9 @@ def test_pair_batch_large_batch_is_chunked_consistently(ctx, tsukuba):
 
 
 @pytest.mark.parametrize("max_dist,cross", [(0.0, False), (10.0, False), (30.0, False), (64.0, True), (10.0, True), (200.0, False)])
-def test_bounded_search_returns_identical_matches(ctx, tsukuba, max_dist, cross):
-    """mvs_match_params.bounded: early-abandoned train descriptors can never change the filtered result."""
+def test_bounded_search_returns_identical_matches(ctx, ctx_popc, tsukuba, max_dist, cross):
+    """mvs_match_params.bounded: early-abandoned train descriptors can never change the filtered result (the early
+    abandon lives in knn2_hamming_kernel; the tensor-core matcher evaluates every pair and ignores the flag)."""
     sets = [(tsukuba["desc2"], tsukuba["desc1"])]
     d1, _, d2, _, _ = synth.synthetic_pair(21, n=2500)
     sets.append((d2, d1))
@@ -436,13 +510,15 @@ def test_bounded_search_returns_identical_matches(ctx, tsukuba, max_dist, cross)
     a[:, :2] = rng.integers(0, 256, (700, 2)); b[:, :2] = rng.integers(0, 256, (650, 2))
     sets.append((a, b))
     for q, t in sets:
-        full = ctx.match_hamming(q, t, 0.7, max_dist, cross, bounded=False)
-        fast = ctx.match_hamming(q, t, 0.7, max_dist, cross, bounded=True)
-        assert np.array_equal(full, fast)
-        assert np.array_equal(full, as_mvs(orc.match_hamming(q, t, 0.7, max_dist, cross)))
+        want = as_mvs(orc.match_hamming(q, t, 0.7, max_dist, cross))
+        for c in (ctx, ctx_popc):
+            full = c.match_hamming(q, t, 0.7, max_dist, cross, bounded=False)
+            fast = c.match_hamming(q, t, 0.7, max_dist, cross, bounded=True)
+            assert np.array_equal(full, fast) and np.array_equal(full, want)
 
 
-def test_bounded_pair_batch_identical_records(ctx, tsukuba):
+def test_bounded_pair_batch_identical_records(ctx_popc, tsukuba):
+    ctx = ctx_popc
     descs = [tsukuba[f"desc{i}"] for i in range(1, 6)]; kps = [tsukuba[f"kp{i}"] for i in range(1, 6)]
     pairs = [(a, b) for a in range(5) for b in range(5) if a != b]
     ctx.frames_upload(descs, kps)
