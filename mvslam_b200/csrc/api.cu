@@ -467,8 +467,8 @@ static int match_two_sets(mvs_ctx *ctx, const uint8_t *query, int nq, const uint
     CK(cudaMemcpyAsync(ctx->t_fcnt.p, cnt, sizeof(cnt), cudaMemcpyHostToDevice, ctx->stream));
     const bool cross = mp && mp->cross_check;
     const bool tc = tc_eligible(ctx, nq, nt, cross, (size_t)nq + nt);
-    const int splits = tc ? 2 : choose_splits((nq + 255) / 256, 1, nt);
-    const int rsplits = cross ? (tc ? 2 : choose_splits((nt + 255) / 256, 1, nq)) : 0;
+    const int splits = tc ? tc_splits() : choose_splits((nq + 255) / 256, 1, nt);
+    const int rsplits = cross ? (tc ? tc_splits() : choose_splits((nt + 255) / 256, 1, nq)) : 0;
     CK(ctx->d_partial.ensure((size_t)splits * nq * sizeof(uint2)));
     if (cross) CK(ctx->d_rev.ensure((size_t)rsplits * nt * sizeof(uint2)));
     CK(ctx->d_matches.ensure((size_t)nq * sizeof(mvs_match)));
@@ -834,8 +834,8 @@ static int pair_batch_chunk(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, con
     const bool cross = mparams && mparams->cross_check;
     const size_t table_rows = (size_t)ctx->h_off[nf - 1] + (size_t)ctx->h_cnt[nf - 1];
     const bool tc = tc_eligible(ctx, max_nq, max_nt, cross, table_rows);
-    const int splits = tc ? 2 : choose_splits((max_nq + 255) / 256, n_pairs, max_nt);
-    const int rsplits = cross ? (tc ? 2 : choose_splits((max_nt + 255) / 256, n_pairs, max_nq)) : 0;
+    const int splits = tc ? tc_splits() : choose_splits((max_nq + 255) / 256, n_pairs, max_nt);
+    const int rsplits = cross ? (tc ? tc_splits() : choose_splits((max_nt + 255) / 256, n_pairs, max_nq)) : 0;
     CK(ctx->d_pairs.ensure((size_t)n_pairs * sizeof(int2)));
     CK(ctx->d_partial.ensure((size_t)n_pairs * splits * qs * sizeof(uint2)));
     if (cross) CK(ctx->d_rev.ensure((size_t)n_pairs * rsplits * max_nt * sizeof(uint2)));

@@ -23,9 +23,10 @@ struct TcKnnArgs {
     const int32_t *frame_off;
     const int32_t *frame_cnt;
     const int2 *pairs;         // as KnnArgs
-    uint2 *partial;            // [pairs][2][q_stride]: the two column halves of the train tiles are the "splits"
+    uint2 *partial;            // [pairs][tc_splits()][q_stride]: the column halves of the train tiles are the "splits"
     int q_stride;
     int reverse;
+    int q_tiles, n_pairs;      // filled by the launcher: items = q_tiles x n_pairs
 };
 
 struct FinalizeArgs {
@@ -105,6 +106,7 @@ struct FinishArgs {
 
 void launch_knn2_hamming(const KnnArgs &a, int max_nq, int splits, int n_pairs, cudaStream_t s);
 int tc_max_train();            // largest train set of the tensor-core matcher
+int tc_splits();               // partial top-2 pairs per query it writes
 void launch_expand_desc(const uint4 *desc, size_t row_begin, size_t n_rows, void *desc8, cudaStream_t s);
 cudaError_t launch_knn2_hamming_tc(const void *desc8, size_t total_rows, const TcKnnArgs &a, int max_nq, int n_pairs, cudaStream_t s);
 int finalize_sort_capacity(int max_nq);

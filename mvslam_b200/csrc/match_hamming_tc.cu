@@ -20,6 +20,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdlib>
 
@@ -34,9 +35,13 @@ constexpr int BM = 128;              // query rows per CTA  (UMMA M)
 constexpr int BN = 128;              // train rows per tile (UMMA N)
 constexpr int SLAB = 128;            // bytes of K per 128-byte swizzle slab
 constexpr int KSLABS = 2;            // 256 one-byte elements per descriptor
-constexpr int EPI_WARPS = 8;         // two per TMEM lane quarter: each takes half of a tile's columns
+constexpr int RB = 2;                // 128-row blocks of a query tile (each train tile is multiplied with both)
+constexpr int EPI_GROUP = 8;         // warps per epilogue group: two per TMEM lane quarter, each takes half of a tile's columns
+constexpr int EPI_WARPS = RB * EPI_GROUP;  // one group per row block
 constexpr int TC_THREADS = 64 + EPI_WARPS * 32;
-constexpr uint32_t TMEM_COLS = 2 * BN;   // two accumulator buffers
+constexpr int NACC = 2 * RB;         // TMEM accumulator buffers: double-buffered per row block
+constexpr uint32_t TMEM_COLS = NACC * BN;
+constexpr int TC_SPLITS = 2;         // partial results per query: one per column half
 constexpr int TC_MAX_TRAIN = 32768;  // trainIdx field of the thread's running key (hamming * 32768 + trainIdx)
 
 // ------------------------------------------------------------------------------------------ PTX helpers
@@ -91,13 +96,35 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr)
 // instruction descriptor: kind::i8, S8 x S8 -> S32, A and B K-major, M = 128, N = BN
 constexpr uint32_t kInstrDescI8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate)
+// The MMA warp runs converged and only predicates the tensor-core instructions on its elected lane: the descriptors
+// stay warp-uniform values (uniform datapath, no per-instruction register -> uniform-register moves), which keeps the
+// issue cost of one tcgen05.mma well below the 64 clocks it occupies the tensor pipe.
+constexpr uint32_t kDescHi = 0x40004040u;   // make_smem_desc >> 32: SBO 1024 B, version 1, SWIZZLE_128B
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3FFFu) | (1u << 16); }
+
+template <bool ACCUMULATE>
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t leader)
 {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(kInstrDescI8), "r"(accumulate) : "memory");
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 e, %4, 0;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %6};\n\t"
+        "mov.b64 db, {%2, %6};\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(kInstrDescI8), "r"(leader), "n"(ACCUMULATE ? 1 : 0), "r"(kDescHi) : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_if(uint64_t *bar, uint32_t leader)
+{
+    asm volatile("{\n\t.reg .pred e;\n\tsetp.ne.b32 e, %1, 0;\n\t"
+                 "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+                 ::"r"(smem_u32(bar)), "r"(leader) : "memory");
+}
+__device__ __forceinline__ uint32_t elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, e;\n\t}" : "=r"(pred));
+    return pred;
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
@@ -153,38 +180,51 @@ __device__ __forceinline__ uint32_t widen_key(uint32_t k16, uint32_t tile_base)
     return (uint32_t)(128 - (k >> 7)) * 32768u + tile_base + (127u - ((uint32_t)k & 127u));
 }
 
-template <int STAGES>
-__global__ void __launch_bounds__(TC_THREADS, 2)
-knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
+// Persistent kernel: one CTA per SM walks the (pair, 256-row query tile) items of the batch with a stride of gridDim.x.
+// A 128-row train tile is loaded once and multiplied with BOTH 128-row blocks of the query tile: the L2 -> shared
+// traffic per descriptor pair is 1 byte instead of 2 (the L2 slices cap at ~6300 B/clk chip-wide, which a 128-row
+// query tile saturates at half the tensor rate).  The three roles keep running counters, so the TMA ring (STAGES train
+// tiles in flight) and the four TMEM accumulators (2 row blocks x 2 steps) stay full across item boundaries.
+struct ItemInfo { int pair, q0, nq, nt, row_q, row_t, n_tiles, n_rb; };
+
+__device__ __forceinline__ bool load_item(const TcKnnArgs &a, int item, ItemInfo &it)
 {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    const int pair = blockIdx.z;
+    it.pair = item / a.q_tiles;
+    it.q0 = (item - it.pair * a.q_tiles) * (RB * BM);
     int fq, ft;
     if (a.pairs) {  // query = pair frame (second), train = base frame (first): visual-feature.cpp:59-60
-        const int2 pr = a.pairs[pair];
+        const int2 pr = a.pairs[it.pair];
         fq = a.reverse ? pr.x : pr.y;
         ft = a.reverse ? pr.y : pr.x;
     } else { fq = a.reverse ? 0 : 1; ft = a.reverse ? 1 : 0; }
-    const int nq = a.frame_cnt[fq], nt = a.frame_cnt[ft];
-    const int q0 = blockIdx.x * BM;
-    if (q0 >= nq) return;                                   // whole CTA, before any barrier or TMEM allocation
-    const int row_q = a.frame_off[fq] + q0, row_t = a.frame_off[ft];
-    const int n_tiles = (nt + BN - 1) / BN;
+    it.nq = a.frame_cnt[fq]; it.nt = a.frame_cnt[ft];
+    it.row_q = a.frame_off[fq] + it.q0; it.row_t = a.frame_off[ft];
+    it.n_tiles = (it.nt + BN - 1) / BN;
+    it.n_rb = (it.q0 + BM < it.nq) ? 2 : 1;                 // the second row block may be empty (every role skips it)
+    return it.q0 < it.nq;                                   // every role skips the same items
+}
 
+template <int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     // the launch requests no static shared memory, so the dynamic window starts 1024-byte aligned (checked)
-    uint8_t *sA = smem_raw;
-    uint8_t *sB = sA + KSLABS * BM * SLAB;
-    uint8_t *sX = sB + STAGES * KSLABS * BN * SLAB;        // constant slab of the ninth K step
+    uint8_t *sA = smem_raw;                                 // [RB row blocks][KSLABS] query slabs
+    uint8_t *sB = sA + RB * KSLABS * BM * SLAB;             // [STAGES][KSLABS] train slabs
+    uint8_t *sX = sB + STAGES * KSLABS * BN * SLAB;         // constant slab of the ninth K step
     uint64_t *bars = (uint64_t *)(sX + BN * SLAB);
-    uint64_t *barA = bars, *full = bars + 1, *empty = full + STAGES, *tfull = empty + STAGES, *tempty = tfull + 2;
-    uint32_t *tmem_slot = (uint32_t *)(tempty + 2);
+    uint64_t *afull = bars, *aempty = afull + 1, *full = aempty + 1, *empty = full + STAGES, *tfull = empty + STAGES,
+             *tempty = tfull + NACC;
+    uint32_t *tmem_slot = (uint32_t *)(tempty + NACC);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_items = a.q_tiles * a.n_pairs;
 
     if (threadIdx.x == 0) {
         if (smem_u32(smem_raw) & 1023u) __trap();
-        mbar_init(barA, 1);
+        mbar_init(afull, 1); mbar_init(aempty, 1);
         for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, EPI_WARPS * 32); }
+        for (int b = 0; b < NACC; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, EPI_GROUP * 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -206,94 +246,129 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // mbarrier parity convention: a consumer waits for fill number n with parity n & 1; a producer waits for the n-th
+    // release with parity (n & 1) ^ 1, which passes at once for n = 0 (nothing to wait for on first use)
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            mbar_expect_tx(barA, KSLABS * BM * SLAB);
-            for (int ks = 0; ks < KSLABS; ++ks) tma_load_2d(&map, barA, sA + ks * BM * SLAB, ks * SLAB, row_q);
-            for (int i = 0; i < n_tiles; ++i) {
-                const int s = i % STAGES;
-                if (i >= STAGES) mbar_wait(empty + s, ((i / STAGES) - 1) & 1);
-                mbar_expect_tx(full + s, KSLABS * BN * SLAB);
-                for (int ks = 0; ks < KSLABS; ++ks)
-                    tma_load_2d(&map, full + s, sB + (s * KSLABS + ks) * BN * SLAB, ks * SLAB, row_t + i * BN);
+            uint32_t tile_no = 0, item_no = 0;
+            ItemInfo it;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                if (!load_item(a, item, it)) continue;
+                mbar_wait(aempty, (item_no & 1) ^ 1);
+                mbar_expect_tx(afull, it.n_rb * KSLABS * BM * SLAB);
+                for (int rb = 0; rb < it.n_rb; ++rb)
+                    for (int ks = 0; ks < KSLABS; ++ks)
+                        tma_load_2d(&map, afull, sA + (rb * KSLABS + ks) * BM * SLAB, ks * SLAB, it.row_q + rb * BM);
+                for (int i = 0; i < it.n_tiles; ++i, ++tile_no) {
+                    const uint32_t s = tile_no % STAGES;
+                    mbar_wait(empty + s, ((tile_no / STAGES) & 1) ^ 1);
+                    mbar_expect_tx(full + s, KSLABS * BN * SLAB);
+                    for (int ks = 0; ks < KSLABS; ++ks)
+                        tma_load_2d(&map, full + s, sB + (s * KSLABS + ks) * BN * SLAB, ks * SLAB, it.row_t + i * BN);
+                }
+                ++item_no;
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
-            mbar_wait(barA, 0);
-            const uint64_t x_a = make_smem_desc(smem_u32(sX)), x_b = make_smem_desc(smem_u32(sX) + 32);
-            for (int i = 0; i < n_tiles; ++i) {
-                const int s = i % STAGES, acc = i & 1;
-                if (i >= 2) mbar_wait(tempty + acc, ((i >> 1) - 1) & 1);   // epilogue drained this accumulator
-                mbar_wait(full + s, (i / STAGES) & 1);
-                tcgen05_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        // ===== MMA issuer (converged warp, elected lane issues) =====
+        {
+            const uint32_t leader = elect_one();
+            const uint32_t xa_lo = desc_lo(smem_u32(sX)), xb_lo = desc_lo(smem_u32(sX) + 32);
+            const uint32_t a_lo0 = desc_lo(smem_u32(sA)), b_lo0 = desc_lo(smem_u32(sB));
+            uint32_t tile_no = 0, item_no = 0, use_no[RB] = {0, 0};
+            ItemInfo it;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                if (!load_item(a, item, it)) continue;
+                mbar_wait(afull, item_no & 1);
+                for (int i = 0; i < it.n_tiles; ++i, ++tile_no) {
+                    const uint32_t s = tile_no % STAGES;
+                    const uint32_t b_lo = b_lo0 + s * (KSLABS * BN * SLAB >> 4);
+                    mbar_wait(full + s, (tile_no / STAGES) & 1);
 #pragma unroll
-                for (int ks = 0; ks < KSLABS; ++ks) {
-                    const uint32_t a_addr = smem_u32(sA + ks * BM * SLAB);
-                    const uint32_t b_addr = smem_u32(sB + (s * KSLABS + ks) * BN * SLAB);
+                    for (int rb = 0; rb < RB; ++rb) {
+                        if (rb >= it.n_rb) break;
+                        const uint32_t acc = (use_no[rb] & 1) * RB + rb;
+                        mbar_wait(tempty + acc, ((use_no[rb] >> 1) & 1) ^ 1);     // epilogue drained this accumulator
+                        tcgen05_fence_after();
+                        const uint32_t d_tmem = tmem_base + acc * BN;
+                        const uint32_t a_lo = a_lo0 + rb * (KSLABS * BM * SLAB >> 4);
+                        // UMMA_K = 32 one-byte elements = 32 bytes inside the swizzle atom; 4 steps per 128-byte slab
+                        umma_i8<false>(d_tmem, a_lo, b_lo, leader);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)   // UMMA_K = 32 one-byte elements = 32 bytes inside the swizzle atom
-                        umma_i8(d_tmem, make_smem_desc(a_addr + k * 32), make_smem_desc(b_addr + k * 32), (ks | k) ? 1u : 0u);
+                        for (int k = 1; k < 4 * KSLABS; ++k)
+                            umma_i8<true>(d_tmem, a_lo + (k >> 2) * (BM * SLAB >> 4) + (k & 3) * 2,
+                                          b_lo + (k >> 2) * (BN * SLAB >> 4) + (k & 3) * 2, leader);
+                        umma_i8<true>(d_tmem, xa_lo, xb_lo, leader);  // + (127 - column): the index half of the key
+                        tcgen05_commit_if(tfull + acc, leader);      // accumulator ready for the epilogue
+                        ++use_no[rb];
+                    }
+                    tcgen05_commit_if(empty + s, leader);            // train stage reusable once these MMAs retire
                 }
-                tcgen05_commit(empty + s);     // train stage reusable once these MMAs retire
-                umma_i8(d_tmem, x_a, x_b, 1u);  // + (127 - column): the index half of the key
-                tcgen05_commit(tfull + acc);   // accumulator ready for the epilogue
+                tcgen05_commit_if(aempty, leader);                   // query tile reusable once the item's MMAs retire
+                ++item_no;
             }
         }
     } else {
-        // ===== epilogue: thread <-> (query row, column half) =====
+        // ===== epilogue: thread <-> (query row, column half), warp group <-> row block =====
         const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;                // which 64 columns of every 128-column tile
-        const int q = q0 + quarter * 32 + lane;          // row within the tile == TMEM lane
-        uint32_t g1 = kKeyNone, g2 = kKeyNone;
-        for (int i = 0; i < n_tiles; ++i) {
-            const int acc = i & 1;
-            const int col0 = i * BN + half * (BN / 2);
-            mbar_wait(tfull + acc, (i >> 1) & 1);
-            tcgen05_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
-            const bool ragged = col0 + BN / 2 > nt;      // warp-uniform: only a frame's last tile
-            uint32_t a1 = 0x80008000u, a2 = 0x80008000u, b1 = 0x80008000u, b2 = 0x80008000u;   // two chains for ILP
+        const int ew = warp - 2;
+        const int half = (ew >> 2) & 1;                  // which 64 columns of every 128-column tile
+        const int rb = ew >> 3;                          // row block of the query tile
+        uint32_t use_no = 0;
+        ItemInfo it;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            if (!load_item(a, item, it)) continue;
+            if (rb >= it.n_rb) continue;
+            const int q = it.q0 + rb * BM + quarter * 32 + lane;   // row within the block == TMEM lane
+            uint32_t g1 = kKeyNone, g2 = kKeyNone;
+            for (int i = 0; i < it.n_tiles; ++i, ++use_no) {
+                const uint32_t acc = (use_no & 1) * RB + rb;
+                const int col0 = i * BN + half * (BN / 2);
+                mbar_wait(tfull + acc, (use_no >> 1) & 1);
+                tcgen05_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
+                const bool ragged = col0 + BN / 2 > it.nt;   // warp-uniform: only a frame's last tile
+                uint32_t a1 = 0x80008000u, a2 = 0x80008000u, b1 = 0x80008000u, b2 = 0x80008000u;   // two chains for ILP
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN / 2; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(taddr + c0, v);
-                if (!ragged) {
+                for (int c0 = 0; c0 < BN / 2; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c0, v);
+                    if (!ragged) {
 #pragma unroll
-                    for (int m = 0; m < 16; m += 2) {
-                        const uint32_t pa = __byte_perm(v[2 * m], v[2 * m + 1], 0x5410);
-                        const uint32_t pb = __byte_perm(v[2 * m + 2], v[2 * m + 3], 0x5410);
-                        const uint32_t la = __vmins2(a1, pa), lb = __vmins2(b1, pb);
-                        a1 = __vmaxs2(a1, pa); b1 = __vmaxs2(b1, pb);
-                        a2 = __vmaxs2(a2, la); b2 = __vmaxs2(b2, lb);
-                    }
-                } else {                                 // rows of the next frame / zero fill lose to every real key
+                        for (int m = 0; m < 16; m += 2) {
+                            const uint32_t pa = __byte_perm(v[2 * m], v[2 * m + 1], 0x5410);
+                            const uint32_t pb = __byte_perm(v[2 * m + 2], v[2 * m + 3], 0x5410);
+                            const uint32_t la = __vmins2(a1, pa), lb = __vmins2(b1, pb);
+                            a1 = __vmaxs2(a1, pa); b1 = __vmaxs2(b1, pb);
+                            a2 = __vmaxs2(a2, la); b2 = __vmaxs2(b2, lb);
+                        }
+                    } else {                             // rows of the next frame / zero fill lose to every real key
 #pragma unroll
-                    for (int m = 0; m < 16; ++m) {
-                        const int c = col0 + c0 + 2 * m;
-                        const uint32_t pk = __byte_perm(c < nt ? v[2 * m] : 0x8000u, c + 1 < nt ? v[2 * m + 1] : 0x8000u, 0x5410);
-                        const uint32_t lo = __vmins2(a1, pk);
-                        a1 = __vmaxs2(a1, pk); a2 = __vmaxs2(a2, lo);
+                        for (int m = 0; m < 16; ++m) {
+                            const int c = col0 + c0 + 2 * m;
+                            const uint32_t pk = __byte_perm(c < it.nt ? v[2 * m] : 0x8000u, c + 1 < it.nt ? v[2 * m + 1] : 0x8000u, 0x5410);
+                            const uint32_t lo = __vmins2(a1, pk);
+                            a1 = __vmaxs2(a1, pk); a2 = __vmaxs2(a2, lo);
+                        }
                     }
                 }
+                tcgen05_fence_before();
+                mbar_arrive(tempty + acc);
+                // the tile's two best over both 16-bit lanes (in both lanes of m1 / m2) -> the thread's running pair
+                const uint32_t n1 = __vmaxs2(a1, b1), n2 = __vimax3_s16x2(__vmins2(a1, b1), a2, b2);
+                const uint32_t r1 = __byte_perm(n1, 0, 0x1032), r2 = __byte_perm(n2, 0, 0x1032);
+                const uint32_t m1 = __vmaxs2(n1, r1);
+                const uint32_t m2 = __vmaxs2(__vmins2(n1, r1), __vmaxs2(n2, r2));
+                const uint32_t tile_base = (uint32_t)(i * BN);
+                top2(g1, g2, widen_key(m1 & 0xFFFFu, tile_base));
+                top2(g1, g2, widen_key(m2 & 0xFFFFu, tile_base));
             }
-            tcgen05_fence_before();
-            mbar_arrive(tempty + acc);
-            // the tile's two best of each lane pair -> the thread's running pair
-            const uint32_t n1 = __vmaxs2(a1, b1), n2 = __vimax3_s16x2(__vmins2(a1, b1), a2, b2);
-            const uint32_t tile_base = (uint32_t)(i * BN);
-            top2(g1, g2, widen_key(n1 & 0xFFFFu, tile_base));
-            top2(g1, g2, widen_key(n1 >> 16, tile_base));
-            top2(g1, g2, widen_key(n2 & 0xFFFFu, tile_base));
-            top2(g1, g2, widen_key(n2 >> 16, tile_base));
-        }
-        if (q < nq) {
-            const uint32_t x1 = (g1 >> 15) > 256u ? kKeyNone : (((g1 >> 15) << kIdxBits) | (g1 & 32767u));
-            const uint32_t x2 = (g2 >> 15) > 256u ? kKeyNone : (((g2 >> 15) << kIdxBits) | (g2 & 32767u));
-            a.partial[((size_t)pair * 2 + half) * a.q_stride + q] = make_uint2(x1, x2);
+            if (q < it.nq) {
+                const uint32_t x1 = (g1 >> 15) > 256u ? kKeyNone : (((g1 >> 15) << kIdxBits) | (g1 & 32767u));
+                const uint32_t x2 = (g2 >> 15) > 256u ? kKeyNone : (((g2 >> 15) << kIdxBits) | (g2 & 32767u));
+                a.partial[((size_t)it.pair * TC_SPLITS + half) * a.q_stride + q] = make_uint2(x1, x2);
+            }
         }
     }
     tcgen05_fence_before();
@@ -322,26 +397,32 @@ EncodeTiledFn get_encode_fn()
     return fn;
 }
 
-cudaError_t launch_tc(const CUtensorMap &map, const TcKnnArgs &a, int max_nq, int n_pairs, cudaStream_t s)
+cudaError_t launch_tc(const CUtensorMap &map, TcKnnArgs a, int max_nq, int n_pairs, cudaStream_t s)
 {
-    constexpr int STAGES = 2;   // 2 CTAs per SM (<= 113 KB each)
-    const size_t smem = (size_t)KSLABS * BM * SLAB + (size_t)STAGES * KSLABS * BN * SLAB + (size_t)BN * SLAB +
-                        (1 + 2 * STAGES + 4) * sizeof(uint64_t) + 16;
+    constexpr int STAGES = 4;   // one persistent CTA per SM: 64 KB query tile + 128 KB train ring + 16 KB constant slab
+    const size_t smem = (size_t)RB * KSLABS * BM * SLAB + (size_t)STAGES * KSLABS * BN * SLAB + (size_t)BN * SLAB +
+                        (2 + 2 * STAGES + 2 * NACC) * sizeof(uint64_t) + 16;
     auto kern = knn2_hamming_tc_kernel<STAGES>;
-    static bool configured = false;
-    if (!configured) {
+    static int n_sm = 0;
+    if (!n_sm) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) { n_sm = 0; return e; }
     }
-    dim3 grid((max_nq + BM - 1) / BM, 1, n_pairs);
-    kern<<<grid, TC_THREADS, smem, s>>>(map, a);
+    a.q_tiles = (max_nq + RB * BM - 1) / (RB * BM);
+    a.n_pairs = n_pairs;
+    const long items = (long)a.q_tiles * n_pairs;
+    kern<<<(unsigned)std::min<long>(items, n_sm), TC_THREADS, smem, s>>>(map, a);
     return cudaGetLastError();
 }
 
 }  // namespace
 
 int tc_max_train() { return TC_MAX_TRAIN; }
+int tc_splits() { return TC_SPLITS; }
 
 void launch_expand_desc(const uint4 *desc, size_t row_begin, size_t n_rows, void *desc8, cudaStream_t s)
 {

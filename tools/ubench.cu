@@ -8,7 +8,7 @@
 constexpr int ILP = 8;
 constexpr int ITERS = 4096;
 
-enum Op { POPC, XOR, IADD3, MNMX, DADD, DMUL, DFMA, HAMMING, HAM_CSA3, HAM_CSA4, HAM_CSA3M };
+enum Op { POPC, XOR, IADD3, MNMX, DADD, DMUL, DFMA, HAMMING, HAM_CSA3, HAM_CSA4, HAM_CSA3M, MNMX16, MNMX3, MNMX3_16, PRMT, IMAD };
 
 template <int OP>
 __global__ void __launch_bounds__(256) k(uint32_t *out, uint32_t seed, double dseed)
@@ -27,6 +27,11 @@ __global__ void __launch_bounds__(256) k(uint32_t *out, uint32_t seed, double ds
             if (OP == XOR) r[i] = (r[i] ^ seed) ^ (r[i] >> 1);
             if (OP == IADD3) r[i] = r[i] + seed + it;
             if (OP == MNMX) r[i] = max(min(r[i], seed + it), (uint32_t)it);
+            if (OP == MNMX16) r[i] = __vmaxs2(__vmins2(r[i], seed + it), (uint32_t)it);
+            if (OP == MNMX3) r[i] = max(max(r[i], seed + it), (uint32_t)it ^ seed);
+            if (OP == MNMX3_16) r[i] = __vimax3_s16x2(r[i], seed + it, (uint32_t)it ^ seed);
+            if (OP == PRMT) r[i] = __byte_perm(r[i], seed + it, 0x5410) ^ 0u, r[i] = __byte_perm(r[i], it, 0x1032);
+            if (OP == IMAD) r[i] = r[i] * seed + it;
             if (OP == DADD) d[i] = d[i] + dseed;
             if (OP == DMUL) d[i] = d[i] * dseed;
             if (OP == DFMA) d[i] = fma(d[i], dseed, dseed);
@@ -112,6 +117,11 @@ int main()
     printf(", \"hamming256_csa3_pairs_per_s\": %.4e", run<HAM_CSA3>(out, blocks, ILP));
     printf(", \"hamming256_csa4_pairs_per_s\": %.4e", run<HAM_CSA4>(out, blocks, ILP));
     printf(", \"hamming256_csa3m_pairs_per_s\": %.4e", run<HAM_CSA3M>(out, blocks, ILP));
+    printf(", \"vimnmx_16x2_per_s\": %.4e", run<MNMX16>(out, blocks, ILP * 2));
+    printf(", \"vimnmx3_per_s\": %.4e", run<MNMX3>(out, blocks, ILP));
+    printf(", \"vimnmx3_16x2_per_s\": %.4e", run<MNMX3_16>(out, blocks, ILP));
+    printf(", \"prmt_per_s\": %.4e", run<PRMT>(out, blocks, ILP * 2));
+    printf(", \"imad_per_s\": %.4e", run<IMAD>(out, blocks, ILP));
     printf("}\n");
     return cudaGetLastError() != cudaSuccess;
 }
