@@ -137,8 +137,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
                    "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
                    "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                  : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void top2(uint32_t &b1, uint32_t &b2, uint32_t key)
 {
@@ -330,10 +330,18 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
                 const bool ragged = col0 + BN / 2 > it.nt;   // warp-uniform: only a frame's last tile
                 uint32_t a1 = 0x80008000u, a2 = 0x80008000u, b1 = 0x80008000u, b2 = 0x80008000u;   // two chains for ILP
-#pragma unroll 1
-                for (int c0 = 0; c0 < BN / 2; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld32(taddr + c0, v);
+                // both 32-column chunks are in flight before the wait, and the accumulator goes back to the MMA warp as
+                // soon as its 64 values sit in registers
+                uint32_t va[32], vb[32];
+                tmem_ld32(taddr, va);
+                tmem_ld32(taddr + 32, vb);
+                tmem_ld_wait();
+                tcgen05_fence_before();
+                mbar_arrive(tempty + acc);
+#pragma unroll
+                for (int ch = 0; ch < 2; ++ch) {
+                    const uint32_t (&v)[32] = ch ? vb : va;
+                    const int c0 = ch * 32;
                     if (!ragged) {
 #pragma unroll
                         for (int m = 0; m < 16; m += 2) {
@@ -353,8 +361,6 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
                         }
                     }
                 }
-                tcgen05_fence_before();
-                mbar_arrive(tempty + acc);
                 // the tile's two best over both 16-bit lanes (in both lanes of m1 / m2) -> the thread's running pair
                 const uint32_t n1 = __vmaxs2(a1, b1), n2 = __vimax3_s16x2(__vmins2(a1, b1), a2, b2);
                 const uint32_t r1 = __byte_perm(n1, 0, 0x1032), r2 = __byte_perm(n2, 0, 0x1032);
