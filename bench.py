@@ -521,7 +521,7 @@ def main():
                note="compute-bound kernel: the HBM fraction is reported for completeness only")
     tensor_matcher = os.environ.get("MVS_MATCHER", "tc")[:1] != "p" and int(counts.max()) <= 32768
     if tensor_matcher:
-        # knn2_hamming_tc_kernel: S = Q T^T over +-1 bytes on the tensor cores (tcgen05.mma kind::i8, K = 256), so one
+        # knn2_hamming_tc_kernel: S = Q T^T over +-8 bytes on the tensor cores (tcgen05.mma kind::i8, K = 256), so one
         # descriptor pair is 256 MACs = 512 integer ops.  Peak: int8 runs at twice the bf16 rate on sm_100a; the bf16 figure
         # is the measured cuBLAS one of MEASURED_PEAKS.json (burst: the kernel is timed alone by its own stage events).
         bf16 = 1701.5
@@ -529,8 +529,10 @@ def main():
             bf16 = json.load(open(mp)).get("bf16_tflops", bf16)
         tensor_peak = 2.0 * bf16
         tops = 512.0 * pair_rate / 1e12
-        # the epilogue's running top-2 (3 integer min/max per accumulator, ALU pipe) is the binding resource, not the MMA
-        vimnmx = peaks.get("vimnmx_per_s", 148 * 64 * 1.965e9)
+        # second ceiling: the epilogue's running top-2 on packed 16-bit keys, 2.1 ALU-pipe instructions per accumulator
+        # (0.5 PRMT + 1.25 VIMNMX.S16x2 + 0.34 per-tile merge), at the measured ALU rate
+        alu_ops = 2.1
+        vimnmx = min(peaks.get("vimnmx_16x2_per_s", 148 * 64 * 1.965e9), peaks.get("prmt_per_s", 148 * 64 * 1.965e9))
         if traffic is None and os.path.exists(tp):
             tj = json.load(open(tp))
             if tj.get("workload") == cfg["workload"] and B == 1024:
@@ -538,8 +540,8 @@ def main():
         roofline = dict(kernel="knn2_hamming_tc_kernel", bound="tensor", achieved=tops, peak=tensor_peak, unit="TOP/s (int8, 512 per descriptor pair)",
                         frac=tops / tensor_peak,
                         peak_source="2 x MEASURED_PEAKS.json bf16_tflops (kind::i8 issues at twice the bf16 rate on sm_100a)",
-                        epilogue_alu=dict(ops_per_pair=3, peak_pairs_per_s=vimnmx / 3.0, frac=pair_rate / (vimnmx / 3.0),
-                                          note="binding pipe: 3 VIMNMX per accumulator at the measured ALU rate (profiles/ubench_peaks.json)"),
+                        epilogue_alu=dict(ops_per_pair=alu_ops, peak_pairs_per_s=vimnmx / alu_ops, frac=pair_rate / (vimnmx / alu_ops),
+                                          note="ALU-pipe ceiling of the epilogue at the measured PRMT / VIMNMX.S16x2 rate (profiles/ubench_peaks.json)"),
                         launch_ms=launch_s * 1e3, desc_pairs_per_launch=desc_pairs, desc_pairs_per_s=pair_rate,
                         hbm=hbm, traffic=traffic, stage_share=stage_share,
                         stage_ms_per_step={s: round(prof[s][0] / args.steps, 4) for s in mvs.STAGES[:7]})
