@@ -420,7 +420,8 @@ def main():
 
     # ---- optional extra: the same workload with the opt-in early-abandon matcher (identical results, less work)
     bounded_extra = None
-    if params["max_dist"] >= 0 and not args.bounded and world == 1 and not args.no_extras:
+    popc_matcher = os.environ.get("MVS_MATCHER", "tc")[:1] == "p"     # the early abandon lives in the integer-pipe kernel only
+    if params["max_dist"] >= 0 and not args.bounded and world == 1 and not args.no_extras and popc_matcher:
         kwb = dict(kw, bounded=True)
 
         def step_b():
@@ -508,18 +509,19 @@ def main():
     mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(mp):
         hbm_peak = json.load(open(mp)).get("hbm_gbs", hbm_peak)
+    tensor_matcher = os.environ.get("MVS_MATCHER", "tc")[:1] != "p" and int(counts.max()) <= 32768
+    knn_kernel = "knn2_hamming_tc_kernel" if tensor_matcher else "knn2_hamming_kernel"
     traffic = None      # dram read+write bytes per launch from the committed ncu --set full capture of this workload
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tp):
         tj = json.load(open(tp))
         if tj.get("workload") == cfg["workload"] and B == 1024:
-            traffic = tj["dram_bytes"].get("knn2_hamming_kernel")
+            traffic = tj["dram_bytes"].get(knn_kernel)
     tot_ms = max(sum(v[0] for v in prof.values()), 1e-9)
     stage_share = {s: round(prof[s][0] / tot_ms, 4) for s in mvs.STAGES[:7]}
     hbm = dict(algorithmic_bytes=alg_bytes, achieved_gbs=alg_bytes / launch_s / 1e9, peak_gbs=hbm_peak,
                frac=alg_bytes / launch_s / 1e9 / hbm_peak,
                note="compute-bound kernel: the HBM fraction is reported for completeness only")
-    tensor_matcher = os.environ.get("MVS_MATCHER", "tc")[:1] != "p" and int(counts.max()) <= 32768
     if tensor_matcher:
         # knn2_hamming_tc_kernel: S = Q T^T over +-8 bytes on the tensor cores (tcgen05.mma kind::i8, K = 256), so one
         # descriptor pair is 256 MACs = 512 integer ops.  Peak: int8 runs at twice the bf16 rate on sm_100a; the bf16 figure
@@ -533,10 +535,6 @@ def main():
         # (0.5 PRMT + 1.25 VIMNMX.S16x2 + 0.34 per-tile merge), at the measured ALU rate
         alu_ops = 2.1
         vimnmx = min(peaks.get("vimnmx_16x2_per_s", 148 * 64 * 1.965e9), peaks.get("prmt_per_s", 148 * 64 * 1.965e9))
-        if traffic is None and os.path.exists(tp):
-            tj = json.load(open(tp))
-            if tj.get("workload") == cfg["workload"] and B == 1024:
-                traffic = tj["dram_bytes"].get("knn2_hamming_tc_kernel")
         roofline = dict(kernel="knn2_hamming_tc_kernel", bound="tensor", achieved=tops, peak=tensor_peak, unit="TOP/s (int8, 512 per descriptor pair)",
                         frac=tops / tensor_peak,
                         peak_source="2 x MEASURED_PEAKS.json bf16_tflops (kind::i8 issues at twice the bf16 rate on sm_100a)",

@@ -59,7 +59,7 @@ for rep, title in ((f"prof_path_{R}.ncu-rep", "two-view path (bench.py default w
     lines += [f"## {title}", "", "| kernel | " + " | ".join(k.split(".")[0].replace("sm__inst_executed_pipe_", "pipe_") for k in KEEP if k in idx) + " |",
               "|---|" + "---|" * sum(k in idx for k in KEEP)]
     for r in data:
-        name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "").replace("mvs::", "").replace("<unnamed>::", "")
+        name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "").replace("mvs::", "").replace("<unnamed>::", "").replace("unnamed>::", "")
         vals = []
         for k in KEEP:
             if k in idx:
@@ -75,7 +75,7 @@ for rep, title in ((f"prof_path_{R}.ncu-rep", "two-view path (bench.py default w
         tot = sum(k["stalls"].values()) or 1
         top = ", ".join(f"{n} {v / tot:.0%}" for n, v in k["stalls"].most_common(5))
         ops = ", ".join(f"{n} {v:,}" for n, v in k["ops"].most_common(8))
-        nm = k["name"].split("(")[0].replace("void ", "").replace("mvs::", "")
+        nm = k["name"].split("(")[0].replace("void ", "").replace("mvs::", "").replace("<unnamed>::", "").replace("unnamed>::", "")
         lines += [f"* `{nm}` — warp-stall samples: {top}; executed warp instructions: {ops}"]
     lines.append("")
 open(os.path.join(P, f"ncu_summary_{R}.md"), "w").write("\n".join(lines))
@@ -111,7 +111,7 @@ if os.path.exists(pp):
     idx = {h: i for i, h in enumerate(H)}
     traffic = {}
     for r in data:
-        name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "").replace("mvs::", "").split("<")[0]
+        name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "").replace("mvs::", "").replace("<unnamed>::", "").replace("unnamed>::", "").replace("unnamed>::", "").split("<")[0]
         scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         b = sum(float(r[idx[k]].replace(",", "")) * scale.get(U[idx[k]], 1) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
         traffic[name] = int(b)
