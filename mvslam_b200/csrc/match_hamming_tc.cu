@@ -74,32 +74,19 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *ba
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
-__device__ __forceinline__ void tcgen05_commit(uint64_t *bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// K-major operand, 128-byte swizzle, dense slab of [rows][128 B]: LBO unused, SBO = 1024 B (8 rows x 128 B),
-// descriptor version 1 (Blackwell), layout_type 2 = SWIZZLE_128B
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr)
-{
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
+// Shared-memory matrix descriptor of a K-major operand in a dense [rows][128 B] slab with 128-byte swizzle: start address
+// >> 4 in bits 0-13, LBO (unused for swizzled K-major) = 1 in bits 16-29, SBO = 1024 B (8 rows x 128 B) >> 4 in bits 32-45,
+// descriptor version 1 (Blackwell) in bit 46, layout type 2 = SWIZZLE_128B in bits 61-63.  Built as (desc_lo, kDescHi).
 // instruction descriptor: kind::i8, S8 x S8 -> S32, A and B K-major, M = 128, N = BN
 constexpr uint32_t kInstrDescI8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 // The MMA warp runs converged and only predicates the tensor-core instructions on its elected lane: the descriptors
 // stay warp-uniform values (uniform datapath, no per-instruction register -> uniform-register moves), which keeps the
 // issue cost of one tcgen05.mma well below the 64 clocks it occupies the tensor pipe.
-constexpr uint32_t kDescHi = 0x40004040u;   // make_smem_desc >> 32: SBO 1024 B, version 1, SWIZZLE_128B
+constexpr uint32_t kDescHi = 0x40004040u;   // high word: SBO 1024 B, version 1, SWIZZLE_128B
 __device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3FFFu) | (1u << 16); }
 
 template <bool ACCUMULATE>
@@ -409,15 +396,19 @@ cudaError_t launch_tc(const CUtensorMap &map, TcKnnArgs a, int max_nq, int n_pai
     const size_t smem = (size_t)RB * KSLABS * BM * SLAB + (size_t)STAGES * KSLABS * BN * SLAB + (size_t)BN * SLAB +
                         (2 + 2 * STAGES + 2 * NACC) * sizeof(uint64_t) + 16;
     auto kern = knn2_hamming_tc_kernel<STAGES>;
-    static int n_sm = 0;
-    if (!n_sm) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static int sm_count[64] = {0};          // per device: the shared-memory opt-in is a per-device function attribute
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess || dev < 0 || dev >= 64) return e != cudaSuccess ? e : cudaErrorInvalidDevice;
+    if (!sm_count[dev]) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        int dev = 0;
-        cudaGetDevice(&dev);
-        e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (e != cudaSuccess) { n_sm = 0; return e; }
+        int n = 0;
+        e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        sm_count[dev] = n;
     }
+    const int n_sm = sm_count[dev];
     a.q_tiles = (max_nq + RB * BM - 1) / (RB * BM);
     a.n_pairs = n_pairs;
     const long items = (long)a.q_tiles * n_pairs;
