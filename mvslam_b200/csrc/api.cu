@@ -75,6 +75,9 @@ struct mvs_ctx {
     DevBuf p_world, p_image, p_off, p_table, p_poses, p_valid, p_pc, p_maskws, p_mask, p_counts, p_results;
     DevBuf b_foff, b_poff, b_R, b_t, b_pc, b_X, b_xc, b_obs, b_ooff, b_ws, b_Ro, b_to, b_pco, b_Xo, b_xco, b_res;
     int32_t *o_pinned = nullptr;
+    // host images are fetched one chunk ahead on a copy stream (orb_extract_impl)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copy_done[2] = {nullptr, nullptr};
     size_t o_pinned_cap = 0;
     // pinned staging for small device->host results that the caller wants in pageable memory: the copies are enqueued
     // asynchronously into the staging area and scattered to the caller's buffers after the one synchronisation
@@ -385,6 +388,8 @@ void mvs_destroy(mvs_ctx *ctx)
                       &ctx->b_ws, &ctx->b_Ro, &ctx->b_to, &ctx->b_pco, &ctx->b_Xo, &ctx->b_xco, &ctx->b_res};
     if (ctx->o_pinned) cudaFreeHost(ctx->o_pinned);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    for (cudaEvent_t e : ctx->copy_done) if (e) cudaEventDestroy(e);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (DevBuf *b : bufs) b->release();
     ctx->l2.release();
     for (auto &p : ctx->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
@@ -1028,8 +1033,45 @@ static int orb_extract_impl(mvs_ctx *ctx, const uint8_t *const *h_images, const 
     const OrbGeom &g = ctx->orb_geom;
     // chunk size: keep the workspace (2 pyramids + candidate lists + kept lists per image) near 2 GB
     const size_t per_image = 2 * (size_t)g.slab + 8 * (size_t)g.cand_total + (size_t)kOrbLevels * kOrbSortCap * 4 + (h_images ? (size_t)height * stride : 0);
-    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_images, ((size_t)2 << 30) / per_image));
-    if (h_images) CK(ctx->o_stage.ensure((size_t)chunk * height * stride));
+    int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_images, ((size_t)2 << 30) / per_image));
+    // Host images: chunks of at most kOrbHostChunk frames, fetched one chunk ahead on a copy stream into a double-buffered
+    // staging area, so that the host-to-device copy of chunk k+1 (for pageable memory: the driver's staged copy, which
+    // occupies the calling thread) runs under the kernels of chunk k.
+    constexpr int kOrbHostChunk = 64;
+    const bool prefetch = h_images && n_images > kOrbHostChunk;
+    if (prefetch) chunk = std::min(chunk, kOrbHostChunk);
+    const size_t isz = (size_t)height * stride;
+    if (h_images) CK(ctx->o_stage.ensure((size_t)(prefetch ? 2 : 1) * chunk * isz));
+    if (prefetch && !ctx->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (cudaEvent_t &e : ctx->copy_done) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    // one copy per run of images that are contiguous in host memory
+    auto copy_chunk = [&](int k, cudaStream_t st) -> cudaError_t {
+        const int c0 = k * chunk, n = std::min(chunk, n_images - c0);
+        uint8_t *dst = ctx->o_stage.as<uint8_t>() + (prefetch ? (size_t)(k & 1) * chunk * isz : 0);
+        for (int i = 0; i < n;) {
+            int j = i + 1;
+            while (j < n && h_images[c0 + j] == h_images[c0 + j - 1] + isz) ++j;
+            cudaError_t e = cudaMemcpyAsync(dst + (size_t)i * isz, h_images[c0 + i], (size_t)(j - i) * isz, cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess) return e;
+            i = j;
+        }
+        return cudaSuccess;
+    };
+    if (h_images)
+        for (int i = 0; i < n_images; ++i)
+            if (!h_images[i]) return fail(ctx, MVS_E_BAD_ARG, "orb_extract: null image");
+    struct CopyGuard {      // never return while the copy stream may still read the caller's images
+        cudaStream_t s = nullptr;
+        ~CopyGuard() { if (s) cudaStreamSynchronize(s); }
+    } copy_guard;
+    if (prefetch) {
+        copy_guard.s = ctx->copy_stream;
+        CK(cudaStreamSynchronize(ctx->stream));     // earlier work of this context may still read the staging area
+        CK(copy_chunk(0, ctx->copy_stream));
+        CK(cudaEventRecord(ctx->copy_done[0], ctx->copy_stream));
+    }
     CK(ctx->o_pyr.ensure((size_t)chunk * g.slab));
     CK(ctx->o_blur.ensure((size_t)chunk * g.slab));
     CK(ctx->o_cxy.ensure((size_t)chunk * g.cand_total * 4));
@@ -1059,18 +1101,14 @@ static int orb_extract_impl(mvs_ctx *ctx, const uint8_t *const *h_images, const 
     for (int c0 = 0; c0 < n_images; c0 += chunk) {
         const int n = std::min(chunk, n_images - c0);
         const uint8_t *stage = nullptr;
+        const int ck = c0 / chunk;
         if (d_images) {
             stage = d_images + (size_t)c0 * height * stride;
+        } else if (prefetch) {
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->copy_done[ck & 1], 0));
+            stage = ctx->o_stage.as<uint8_t>() + (size_t)(ck & 1) * chunk * isz;
         } else {
-            const size_t isz = (size_t)height * stride;
-            for (int i = 0; i < n;) {      // one copy per run of images that are contiguous in host memory
-                if (!h_images[c0 + i]) return fail(ctx, MVS_E_BAD_ARG, "orb_extract: null image");
-                int j = i + 1;
-                while (j < n && h_images[c0 + j] == h_images[c0 + j - 1] + isz) ++j;
-                CK(cudaMemcpyAsync(ctx->o_stage.as<uint8_t>() + (size_t)i * isz, h_images[c0 + i], (size_t)(j - i) * isz,
-                                   cudaMemcpyHostToDevice, ctx->stream));
-                i = j;
-            }
+            CK(copy_chunk(ck, ctx->stream));
             stage = ctx->o_stage.as<uint8_t>();
         }
         CK(cudaMemsetAsync(b.cand_cnt, 0, (size_t)chunk * kOrbLevels * 257 * sizeof(int32_t), ctx->stream));
@@ -1084,6 +1122,10 @@ static int orb_extract_impl(mvs_ctx *ctx, const uint8_t *const *h_images, const 
         { StageTimer t(ctx, MVS_STAGE_ORB_SELECT); launch_orb_select(g, b, n, ctx->stream); CK(cudaGetLastError()); }
         CK(cudaMemcpyAsync(ctx->o_pinned, b.kept_cnt, (size_t)n * kOrbLevels * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
         { StageTimer t(ctx, MVS_STAGE_ORB_BLUR); launch_orb_blur(g, b, n, ctx->stream); CK(cudaGetLastError()); }
+        if (prefetch && c0 + chunk < n_images) {    // the other staging half was last read by chunk k-1, which has completed
+            CK(copy_chunk(ck + 1, ctx->copy_stream));
+            CK(cudaEventRecord(ctx->copy_done[(ck + 1) & 1], ctx->copy_stream));
+        }
         CK(cudaStreamSynchronize(ctx->stream));
         int32_t *off = ctx->o_pinned + (size_t)chunk * kOrbLevels;
         size_t chunk_total = 0;

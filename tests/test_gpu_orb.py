@@ -163,3 +163,32 @@ def test_strided_rows(ctx):
     st = L.mvs_orb_extract(ctx._h, ptrs, 1, 300, 200, 320, C.byref(op), 0, None, counts.ctypes.data_as(C.c_void_p),
                            kp.ctypes.data_as(C.c_void_p), desc.ctypes.data_as(C.c_void_p), C.c_int64(10))
     assert st == mvs.E_CAPACITY and counts[0] == c1[0]
+
+
+def test_many_host_images_take_the_prefetch_path(ctx):
+    """More than 64 host images per call: chunks of 64 fetched one ahead on the copy stream (api.cu orb_extract_impl).
+    The result must not depend on the chunking: same keypoints as one image per call, separate or contiguous buffers,
+    and the same frame table when appended."""
+    n = 150
+    imgs = [synth.synthetic_image(1000 + i, 200, 150) for i in range(n)]
+    counts, kp, desc, _ = ctx.orb_extract(imgs, 300)
+    stack = np.ascontiguousarray(np.stack(imgs))
+    c2, kp2, d2, _ = ctx.orb_extract(list(stack), 300)
+    assert np.array_equal(counts, c2) and np.array_equal(kp, kp2) and np.array_equal(desc, d2)
+    parts = split(counts, kp, desc)
+    for i in (0, 63, 64, 65, 127, 128, 149):
+        c1, k1, d1, _ = ctx.orb_extract([imgs[i]], 300)
+        assert c1[0] == counts[i] and np.array_equal(parts[i][0], k1) and np.array_equal(parts[i][1], d1), i
+    assert_same(O.orb_extract(imgs[129], 300), parts[129][0], parts[129][1], "image 129 of 150")
+    ctx.frames_clear()
+    c3, _, _, first = ctx.orb_extract(imgs, 300, append_frames=True)
+    assert first == 0 and np.array_equal(c3, counts)
+    K = np.array([[200.0, 0, 100], [0, 200.0, 75], [0, 0, 1]])
+    res, det = ctx.pair_batch([(0, 0 + 1), (64, 65), (148, 149)], K, H=8)
+    ctx.frames_upload([d for _, d in parts], [np.stack([k["x"], k["y"]], 1) for k, _ in parts])
+    res2, det2 = ctx.pair_batch([(0, 1), (64, 65), (148, 149)], K, H=8)
+    assert np.array_equal(res["n_matches"], res2["n_matches"]) and np.array_equal(res["status"], res2["status"])
+    for i in range(3):
+        m = res["n_matches"][i]
+        assert np.array_equal(det["matches"][i][:m], det2["matches"][i][:m])
+    ctx.frames_clear()
