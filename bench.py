@@ -351,13 +351,13 @@ def main():
     def upload():
         ctx.frames_upload([t.numpy() for t in pd], [t.numpy() for t in pk])
 
-    def step(out):
+    def step(out, enqueue_only=True):
         for c0 in range(0, B, CH):
             c1 = min(B, c0 + CH)
             o = dict(out, results=out["results"] + c0 * item)
             if "matches" in o:      # detail buffers hold one chunk and are overwritten chunk by chunk
                 assert B <= CH
-            ctx.pair_batch(pairs[c0:c1], K, out=o, enqueue_only=True, pair_id_base=pair_base + c0, **kw)
+            ctx.pair_batch(pairs[c0:c1], K, out=o, enqueue_only=enqueue_only, pair_id_base=pair_base + c0, **kw)
 
     upload()
     for _ in range(args.warmup):
@@ -470,18 +470,23 @@ def main():
 
     # ---- end to end through the public call with host buffers (H2D of the frames + D2H of everything)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    upload(); step(out_all); torch.cuda.synchronize()
+    # the synchronous call (mvs_pair_batch): what a caller of the reference's ImagePair / visual-odometer path makes
+    upload(); step(out_all, enqueue_only=False); torch.cuda.synchronize()
     n_e2e = max(3, min(args.steps, 10))
     e0.record(stream)
     for _ in range(n_e2e):
-        upload(); step(out_all); ctx.synchronize()
+        upload(); step(out_all, enqueue_only=False)
     e1.record(stream); torch.cuda.synchronize()
     e2e_ms = e0.elapsed_time(e1) / n_e2e
     if world > 1:
         t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_ms = float(t.item())
     h2d = sum(d.nbytes for d in descs) + sum(k.nbytes for k in kps) + pairs.nbytes
-    d2h = res_t.numel() + (0 if strong else mat_t.numel() + msk_t.numel() + pts_t.numel() * 8 + idx_t.numel() * 8)
+    # bytes the synchronous call copies back: the records, and per pair as many detail entries (45 B each) as the fullest
+    # pair of the batch holds (the library reads the counts first when the details exceed 1 MB)
+    e2e_res = np.frombuffer(res_t.numpy(), dtype=mvs.RESULT_DTYPE)
+    wc = cap if Bd * cap * 45 <= (1 << 20) else min(cap, max(1, int(e2e_res["n_matches"].max())))
+    d2h = res_t.numel() + (0 if strong else Bd * wc * 45 + 4 * Bd)
 
     if rank != 0:
         if world > 1:

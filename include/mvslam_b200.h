@@ -311,7 +311,8 @@ int mvs_frames_clear(mvs_ctx *ctx);
  * results[n_pairs] always filled (status per pair; one bad pair never aborts the batch).
  * Optional per-pair detail outputs use a common stride `capacity` (>= 1): matches[n_pairs][capacity],
  * inlier_mask[n_pairs][capacity], points[n_pairs][capacity][3], indexes[n_pairs][capacity] (index into that
- * pair's matches).  Only the first `capacity` entries of a pair are copied back: a pair whose
+ * pair's matches).  Entries of a pair beyond its counts (n_matches for matches / inlier_mask, n_points for points /
+ * indexes) are unspecified.  Only the first `capacity` entries of a pair are copied back: a pair whose
  * results[i].n_matches exceeds `capacity` is truncated (pass the largest pair-frame keypoint count to rule
  * that out; the VO default max_dist = 10 leaves ~100 matches per 2k-keypoint pair). */
 int mvs_pair_batch(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, const double K[9],

@@ -75,6 +75,8 @@ struct mvs_ctx {
     DevBuf p_world, p_image, p_off, p_table, p_poses, p_valid, p_pc, p_maskws, p_mask, p_counts, p_results;
     DevBuf b_foff, b_poff, b_R, b_t, b_pc, b_X, b_xc, b_obs, b_ooff, b_ws, b_Ro, b_to, b_pco, b_Xo, b_xco, b_res;
     int32_t *o_pinned = nullptr;
+    int32_t *h_counts = nullptr;         // pinned: per-pair match counts read back before the detail copies (synchronous calls)
+    size_t h_counts_cap = 0;
     // host images are fetched one chunk ahead on a copy stream (orb_extract_impl)
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t copy_done[2] = {nullptr, nullptr};
@@ -387,6 +389,7 @@ void mvs_destroy(mvs_ctx *ctx)
                       &ctx->b_foff, &ctx->b_poff, &ctx->b_R, &ctx->b_t, &ctx->b_pc, &ctx->b_X, &ctx->b_xc, &ctx->b_obs, &ctx->b_ooff,
                       &ctx->b_ws, &ctx->b_Ro, &ctx->b_to, &ctx->b_pco, &ctx->b_Xo, &ctx->b_xco, &ctx->b_res};
     if (ctx->o_pinned) cudaFreeHost(ctx->o_pinned);
+    if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     for (cudaEvent_t e : ctx->copy_done) if (e) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -906,11 +909,28 @@ static int pair_batch_chunk(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, con
         else { (void)cudaGetLastError(); stage = false; }
     }
     CK(d2h_rows(ctx, stage, results, sizeof(mvs_pair_result), ctx->d_results.p, sizeof(mvs_pair_result), sizeof(mvs_pair_result), (size_t)n_pairs));
-    // details: the first min(capacity, stride) entries of every pair (a pair with n_matches > capacity is truncated)
-    if (matches) CK(d2h_rows(ctx, stage, matches, (size_t)capacity * sizeof(mvs_match), ctx->d_matches.p, (size_t)qs * sizeof(mvs_match), w * sizeof(mvs_match), (size_t)n_pairs));
-    if (inlier_mask) CK(d2h_rows(ctx, stage, inlier_mask, (size_t)capacity, ctx->d_mask.p, (size_t)qs, w, (size_t)n_pairs));
-    if (points) CK(d2h_rows(ctx, stage, points, (size_t)capacity * 24, ctx->d_opts.p, (size_t)qs * 24, w * 24, (size_t)n_pairs));
-    if (indexes) CK(d2h_rows(ctx, stage, indexes, (size_t)capacity * 8, ctx->d_oidx.p, (size_t)qs * 8, w * 8, (size_t)n_pairs));
+    // details: the first min(capacity, stride) entries of every pair (a pair with n_matches > capacity is truncated).
+    // A synchronous call with more than 1 MB of details first reads the match counts back (one small round trip after
+    // the kernels) and copies only as many entries per pair as the fullest pair holds: with the VO threshold a pair keeps
+    // ~100 of its 256 slots, and the device-to-host copy is a fifth of an end-to-end step.
+    size_t wc = w;
+    if (ctx->allow_stage && !stage && detail_bytes > ((size_t)1 << 20)) {
+        if (ctx->h_counts_cap < (size_t)n_pairs) {
+            if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
+            ctx->h_counts = nullptr; ctx->h_counts_cap = 0;
+            CK(cudaMallocHost((void **)&ctx->h_counts, (size_t)n_pairs * sizeof(int32_t)));
+            ctx->h_counts_cap = (size_t)n_pairs;
+        }
+        CK(cudaMemcpyAsync(ctx->h_counts, ctx->d_nmatch.p, (size_t)n_pairs * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        int32_t most = 1;
+        for (int i = 0; i < n_pairs; ++i) most = std::max(most, ctx->h_counts[i]);
+        wc = std::min(w, (size_t)most);       // inliers and points are subsets of the matches
+    }
+    if (matches) CK(d2h_rows(ctx, stage, matches, (size_t)capacity * sizeof(mvs_match), ctx->d_matches.p, (size_t)qs * sizeof(mvs_match), wc * sizeof(mvs_match), (size_t)n_pairs));
+    if (inlier_mask) CK(d2h_rows(ctx, stage, inlier_mask, (size_t)capacity, ctx->d_mask.p, (size_t)qs, wc, (size_t)n_pairs));
+    if (points) CK(d2h_rows(ctx, stage, points, (size_t)capacity * 24, ctx->d_opts.p, (size_t)qs * 24, wc * 24, (size_t)n_pairs));
+    if (indexes) CK(d2h_rows(ctx, stage, indexes, (size_t)capacity * 8, ctx->d_oidx.p, (size_t)qs * 8, wc * 8, (size_t)n_pairs));
     return MVS_OK;
 }
 

@@ -136,7 +136,7 @@ def test_device_images_and_frame_table_handoff(ctx, gray):
     ctx.frames_upload([d for _, d in parts], [np.stack([k["x"], k["y"]], 1) for k, _ in parts])
     res_up, det_up = ctx.pair_batch([(0, 1), (1, 2), (0, 2)], K, max_dist=10.0, H=64)
     assert res_dev.tobytes() == res_up.tobytes()
-    assert np.array_equal(det_dev["matches"], det_up["matches"])
+    assert all(np.array_equal(det_dev["matches"][i][:m], det_up["matches"][i][:m]) for i, m in enumerate(res_dev["n_matches"]))
     assert (res_dev["status"] == mvs.OK).all() and (res_dev["n_points"] > 20).all()
     # a second append continues the table
     c2, _, _, first2 = ctx.orb_extract([gray[3]], 2000, append_frames=True)

@@ -533,6 +533,25 @@ def test_bounded_pair_batch_identical_records(ctx_popc, tsukuba):
             assert np.array_equal(d0["points"][i][:n], d1["points"][i][:n]) and np.array_equal(d0["indexes"][i][:n], d1["indexes"][i][:n])
 
 
+def test_large_synchronous_batch_trims_detail_copies(ctx, tsukuba):
+    """A synchronous mvs_pair_batch with more than 1 MB of details copies only as many entries per pair as the fullest
+    pair holds (api.cu pair_batch_chunk); everything inside the counts must equal the small-batch result."""
+    descs = [tsukuba[f"desc{i}"] for i in range(1, 6)]; kps = [tsukuba[f"kp{i}"] for i in range(1, 6)]
+    ctx.frames_upload(descs, kps)
+    base = [(a, b) for a in range(5) for b in range(5) if a != b]
+    pairs = [base[i % len(base)] for i in range(60)]              # 60 pairs x 1759 slots x 45 B = 4.7 MB of details
+    big, dbig = ctx.pair_batch(pairs, tsukuba["K"], max_dist=30.0, H=16, seed=4)
+    for i in range(0, 60, 7):
+        one, done = ctx.pair_batch([pairs[i]], tsukuba["K"], max_dist=30.0, H=16, seed=4, pair_id_base=i)
+        assert one.tobytes() == big[i:i + 1].tobytes()
+        m, n = int(one["n_matches"][0]), int(one["n_points"][0])
+        assert m > 20
+        assert np.array_equal(dbig["matches"][i][:m], done["matches"][0][:m]) and np.array_equal(dbig["mask"][i][:m], done["mask"][0][:m])
+        assert np.array_equal(dbig["points"][i][:n], done["points"][0][:n]) and np.array_equal(dbig["indexes"][i][:n], done["indexes"][0][:n])
+    most = int(big["n_matches"].max())
+    assert not dbig["matches"][:, most:]["distance"].any()         # slots beyond the fullest pair were not copied (host zeros)
+
+
 def test_empty_and_degenerate_inputs(ctx):
     """Empty / minimal inputs: status codes instead of the reference's asserts or undefined behaviour."""
     q = np.zeros((0, 32), np.uint8); t = np.random.default_rng(0).integers(0, 256, (10, 32), dtype=np.uint8)
@@ -628,4 +647,5 @@ def test_frames_append_equals_bulk_upload(ctx, tsukuba):
             one, _ = ctx.pair_batch([(0, 1)], tsukuba["K"], max_dist=30.0, H=16, seed=4)
             assert one.tobytes() == ref[:1].tobytes()
     got, dgot = ctx.pair_batch(pairs, tsukuba["K"], max_dist=30.0, H=16, seed=4)
-    assert got.tobytes() == ref.tobytes() and np.array_equal(dgot["matches"], dref["matches"])
+    assert got.tobytes() == ref.tobytes()
+    assert all(np.array_equal(dgot["matches"][i][:m], dref["matches"][i][:m]) for i, m in enumerate(ref["n_matches"]))
