@@ -1,0 +1,57 @@
+"""Host-side model of the arithmetic of the tensor-core matcher (mvslam_b200/csrc/match_hamming_tc.cu), checked against the
+CPU oracle without a GPU: the +-8 byte encoding, the ninth K step that adds 127 - column, the signed 16-bit key
+`128 (128 - hamming) + (127 - c)` maximised per 128-column tile, and its widening to `hamming * 32768 + trainIdx`.
+The CUDA kernel is tested against the same oracle in tests/test_gpu_parity.py; this file pins the algebra it relies on."""
+import numpy as np
+import pytest
+
+from oracle import cbind as orc
+
+BN = 128
+
+
+def expand(desc):
+    """expand_desc_kernel: bit k of the descriptor -> byte k, 1 -> +8, 0 -> -8."""
+    bits = np.unpackbits(desc, axis=1, bitorder="little").astype(np.int32)
+    return 16 * bits - 8
+
+
+def model_knn2(q, t):
+    Q, T = expand(q), expand(t)
+    nt = t.shape[0]
+    g = np.full((q.shape[0], 2), np.iinfo(np.int64).max, np.int64)          # running (best, second) of hamming*32768+idx
+    for t0 in range(0, nt, BN):
+        tile = T[t0:t0 + BN]
+        acc = Q @ tile.T + (127 - np.arange(tile.shape[0]))[None, :]        # 8 K steps + the constant ninth one
+        assert acc.min() >= -16384 and acc.max() <= 16511                    # fits the signed 16-bit lane
+        k16 = acc.astype(np.int16)
+        order = np.sort(k16, axis=1)[:, ::-1][:, :2].astype(np.int64)         # per tile: the two LARGEST keys
+        if order.shape[1] < 2:
+            order = np.concatenate([order, np.full((q.shape[0], 1), -32768, np.int64)], 1)
+        wide = (128 - (order >> 7)) * 32768 + t0 + (127 - (order & 127))     # widen_key()
+        g = np.sort(np.concatenate([g, wide], 1), axis=1)[:, :2]
+    dist, idx = g >> 15, g & 32767
+    none = dist > 256                                                        # empty lane / nothing found
+    return np.where(none, -1, idx), np.where(none, -1, dist)
+
+
+@pytest.mark.parametrize("nq,nt,rand_bytes", [(5, 2, 32), (40, 127, 32), (33, 129, 1), (64, 300, 2), (17, 1000, 32)])
+def test_model_equals_oracle(nq, nt, rand_bytes):
+    rng = np.random.default_rng(nq * 131 + nt)
+    q = np.zeros((nq, 32), np.uint8); t = np.zeros((nt, 32), np.uint8)
+    q[:, :rand_bytes] = rng.integers(0, 256, (nq, rand_bytes)); t[:, :rand_bytes] = rng.integers(0, 256, (nt, rand_bytes))
+    t[nt // 2] = t[0]; q[0] = 255 - t[1]; q[1] = t[1]                         # duplicates, distance 256 and distance 0
+    im, dm = model_knn2(q, t)
+    io, do = orc.knn2_hamming(q, t)
+    assert np.array_equal(im, io) and np.array_equal(dm, do)
+
+
+def test_key_is_monotone_in_distance_then_index():
+    """Larger 16-bit key <=> (smaller distance, then smaller column); the widened key orders the same way under MIN."""
+    d = np.arange(0, 257)[:, None]; c = np.arange(0, 128)[None, :]
+    k16 = 128 * (128 - d) + (127 - c)
+    flat = k16.ravel()
+    assert len(np.unique(flat)) == flat.size and flat.min() == -16384 and flat.max() == 16511
+    wide = (128 - (k16 >> 7)) * 32768 + (127 - (k16 & 127))
+    assert np.array_equal(wide, d * 32768 + c)
+    assert np.array_equal(np.argsort(-flat, kind="stable"), np.argsort(wide.ravel(), kind="stable"))
