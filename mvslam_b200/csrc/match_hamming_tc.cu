@@ -11,7 +11,7 @@
 //   The contraction runs as tcgen05.mma (M = N = 128, K = 8 x 32, plus a ninth K step that adds the column index, see
 //   the kernel) with both operands staged by TMA (128-byte swizzle) and the accumulators double-buffered in TMEM.  The
 //   epilogue never materialises the score matrix: thread <-> (query row, column half) keeps a running (best, second)
-//   pair on packed 16-bit keys, 1.75 ALU instructions per accumulator.
+//   pair on packed 16-bit keys, 1.25 ALU instructions per accumulator plus a per-tile merge.
 //
 // Warp roles (320 threads, 2 CTAs per SM so that one CTA's TMA/MMA overlaps the other's epilogue):
 //   warp 0   TMA producer (query tile once, train tiles through a STAGES-deep mbarrier ring)
@@ -114,18 +114,14 @@ __device__ __forceinline__ uint32_t elect_one()
     return pred;
 }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
-{
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                 : "r"(taddr));
-}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 64 accumulator columns as 32 registers: .pack::16b keeps the low 16 bits of every 32-bit column and puts two adjacent
+// columns into one register (even column low, odd column high) -- the accumulators are signed 16-bit keys by construction
+__device__ __forceinline__ void tmem_ld64_packed(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]) : "r"(taddr));
+}
 
 __device__ __forceinline__ void top2(uint32_t &b1, uint32_t &b2, uint32_t key)
 {
@@ -157,9 +153,9 @@ expand_desc_kernel(const uint32_t *__restrict__ desc, size_t word_begin, size_t 
 // constant slab (query side: 1 in byte 0 of every row; train side: 127 - column-in-tile in byte 32 of every row) adds
 // 127 - c, so the accumulator itself is the signed 16-bit key
 //      k16 = 128 (128 - hamming) + (127 - c)          in [-16384, 16511]
-// that orders the columns of a tile by (smaller distance, then smaller index) under MAX.  Two accumulators are packed
-// into one register with a single PRMT and the running (best, second) pair of both 16-bit lanes costs 2.5 VIMNMX.S16x2
-// per register: 1.75 ALU instructions per accumulator and none on the FMA pipe.  At the end of a tile the four lane
+// that orders the columns of a tile by (smaller distance, then smaller index) under MAX.  tcgen05.ld.pack::16b delivers
+// two adjacent accumulators per register (their low 16 bits), and the running (best, second) pair of both 16-bit lanes
+// costs 2.5 VIMNMX.S16x2 per register: 1.25 ALU instructions per accumulator and none on the FMA pipe.  At the end of a tile the four lane
 // results are widened to  hamming * 32768 + trainIdx  and merged into the thread's 32-bit pair (minimum = best).
 __device__ __forceinline__ uint32_t widen_key(uint32_t k16, uint32_t tile_base)
 {
@@ -317,35 +313,28 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
                 const bool ragged = col0 + BN / 2 > it.nt;   // warp-uniform: only a frame's last tile
                 uint32_t a1 = 0x80008000u, a2 = 0x80008000u, b1 = 0x80008000u, b2 = 0x80008000u;   // two chains for ILP
-                // both 32-column chunks are in flight before the wait, and the accumulator goes back to the MMA warp as
-                // soon as its 64 values sit in registers
-                uint32_t va[32], vb[32];
-                tmem_ld32(taddr, va);
-                tmem_ld32(taddr + 32, vb);
+                // one packed load brings the 64 columns as 32 registers; the accumulator goes back to the MMA warp as soon as
+                // they have arrived
+                uint32_t v[32];
+                tmem_ld64_packed(taddr, v);
                 tmem_ld_wait();
                 tcgen05_fence_before();
                 mbar_arrive(tempty + acc);
+                if (!ragged) {
 #pragma unroll
-                for (int ch = 0; ch < 2; ++ch) {
-                    const uint32_t (&v)[32] = ch ? vb : va;
-                    const int c0 = ch * 32;
-                    if (!ragged) {
+                    for (int m = 0; m < 32; m += 2) {
+                        const uint32_t pa = v[m], pb = v[m + 1];
+                        const uint32_t la = __vmins2(a1, pa), lb = __vmins2(b1, pb);
+                        a1 = __vmaxs2(a1, pa); b1 = __vmaxs2(b1, pb);
+                        a2 = __vmaxs2(a2, la); b2 = __vmaxs2(b2, lb);
+                    }
+                } else {                                 // rows of the next frame / zero fill lose to every real key
 #pragma unroll
-                        for (int m = 0; m < 16; m += 2) {
-                            const uint32_t pa = __byte_perm(v[2 * m], v[2 * m + 1], 0x5410);
-                            const uint32_t pb = __byte_perm(v[2 * m + 2], v[2 * m + 3], 0x5410);
-                            const uint32_t la = __vmins2(a1, pa), lb = __vmins2(b1, pb);
-                            a1 = __vmaxs2(a1, pa); b1 = __vmaxs2(b1, pb);
-                            a2 = __vmaxs2(a2, la); b2 = __vmaxs2(b2, lb);
-                        }
-                    } else {                             // rows of the next frame / zero fill lose to every real key
-#pragma unroll
-                        for (int m = 0; m < 16; ++m) {
-                            const int c = col0 + c0 + 2 * m;
-                            const uint32_t pk = __byte_perm(c < it.nt ? v[2 * m] : 0x8000u, c + 1 < it.nt ? v[2 * m + 1] : 0x8000u, 0x5410);
-                            const uint32_t lo = __vmins2(a1, pk);
-                            a1 = __vmaxs2(a1, pk); a2 = __vmaxs2(a2, lo);
-                        }
+                    for (int m = 0; m < 32; ++m) {
+                        const int c = col0 + 2 * m;
+                        const uint32_t pk = (c < it.nt ? (v[m] & 0xFFFFu) : 0x8000u) | (c + 1 < it.nt ? (v[m] & 0xFFFF0000u) : 0x80000000u);
+                        const uint32_t lo = __vmins2(a1, pk);
+                        a1 = __vmaxs2(a1, pk); a2 = __vmaxs2(a2, lo);
                     }
                 }
                 // the tile's two best over both 16-bit lanes (in both lanes of m1 / m2) -> the thread's running pair
