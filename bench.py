@@ -537,7 +537,8 @@ def main():
         tensor_peak = 2.0 * bf16
         tops = 512.0 * pair_rate / 1e12
         # second ceiling: the epilogue's running top-2 on packed 16-bit keys, 2.1 ALU-pipe instructions per accumulator
-        # (1.25 VIMNMX.S16x2 + 0.3 per-tile merge; the 16-bit packing is done by tcgen05.ld.pack::16b), at the measured ALU rate
+        # (1.25 VIMNMX.S16x2 + 0.3 per-tile merge; the 16-bit packing is done by tcgen05.ld.pack::16b, the column index
+        # is inserted by one IMAD per register on the FMA pipe), at the measured ALU rate
         alu_ops = 1.6
         vimnmx = min(peaks.get("vimnmx_16x2_per_s", 148 * 64 * 1.965e9), peaks.get("prmt_per_s", 148 * 64 * 1.965e9))
         roofline = dict(kernel="knn2_hamming_tc_kernel", bound="tensor", achieved=tops, peak=tensor_peak, unit="TOP/s (int8, 512 per descriptor pair)",
@@ -545,7 +546,6 @@ def main():
                         peak_source="2 x MEASURED_PEAKS.json bf16_tflops (kind::i8 issues at twice the bf16 rate on sm_100a; cuBLAS "
                                     "bf16 itself reaches ~76 % of the nominal 2.25 PFLOP/s, so long-tile workloads can exceed 1.0)",
                         frac_of_nominal=tops / 4500.0, nominal_peak="4.5 POP/s dense int8 (2 x the nominal 2.25 PFLOP/s bf16)",
-                        tensor_ops_issued_per_algorithmic_op=9.0 / 8.0,
                         epilogue_alu=dict(ops_per_pair=alu_ops, peak_pairs_per_s=vimnmx / alu_ops, frac=pair_rate / (vimnmx / alu_ops),
                                           note="ALU-pipe ceiling of the epilogue at the measured PRMT / VIMNMX.S16x2 rate (profiles/ubench_peaks.json)"),
                         launch_ms=launch_s * 1e3, desc_pairs_per_launch=desc_pairs, desc_pairs_per_s=pair_rate,

@@ -27,6 +27,7 @@ struct TcKnnArgs {
     int q_stride;
     int reverse;
     int q_tiles, n_pairs;      // filled by the launcher: items = q_tiles x n_pairs
+    int one;                   // 1 (opaque to the compiler, see the epilogue)
 };
 
 struct FinalizeArgs {

@@ -8,15 +8,15 @@
 //   small integers, exact in the S32 accumulators of kind::i8, so  hamming  is the popcount distance, not an
 //   approximation.  (kind::f8f6f4 with E4M3 +-1 was measured too: exact as well, 13 % slower.)
 //
-//   The contraction runs as tcgen05.mma (M = N = 128, K = 8 x 32, plus a ninth K step that adds the column index, see
-//   the kernel) with both operands staged by TMA (128-byte swizzle) and the accumulators double-buffered in TMEM.  The
+//   The contraction runs as tcgen05.mma (M = N = 128, K = 8 x 32) with both operands staged by TMA (128-byte swizzle)
+//   and the accumulators double-buffered in TMEM.  The
 //   epilogue never materialises the score matrix: thread <-> (query row, column half) keeps a running (best, second)
 //   pair on packed 16-bit keys, 1.25 ALU instructions per accumulator plus a per-tile merge.
 //
-// Warp roles (320 threads, 2 CTAs per SM so that one CTA's TMA/MMA overlaps the other's epilogue):
-//   warp 0   TMA producer (query tile once, train tiles through a STAGES-deep mbarrier ring)
-//   warp 1   TMEM allocator + single-thread tcgen05.mma issuer
-//   warps 2-9 epilogue
+// Warp roles (576 threads, one persistent CTA per SM):
+//   warp 0      TMA producer (256-row query tile per item, 128-row train tiles through a STAGES-deep mbarrier ring)
+//   warp 1      TMEM allocator + tcgen05.mma issuer (converged warp, elected lane)
+//   warps 2-17  epilogue: two groups of 8 (one per 128-row block of the query tile)
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -149,18 +149,20 @@ expand_desc_kernel(const uint32_t *__restrict__ desc, size_t word_begin, size_t 
 }
 
 // ------------------------------------------------------------------------------------------ GEMM + running top-2
-// Epilogue arithmetic.  With every bit stored as +-8 the contraction gives 64 S = 128 (S/2); a ninth K step over one
-// constant slab (query side: 1 in byte 0 of every row; train side: 127 - column-in-tile in byte 32 of every row) adds
-// 127 - c, so the accumulator itself is the signed 16-bit key
-//      k16 = 128 (128 - hamming) + (127 - c)          in [-16384, 16511]
-// that orders the columns of a tile by (smaller distance, then smaller index) under MAX.  tcgen05.ld.pack::16b delivers
-// two adjacent accumulators per register (their low 16 bits), and the running (best, second) pair of both 16-bit lanes
-// costs 2.5 VIMNMX.S16x2 per register: 1.25 ALU instructions per accumulator and none on the FMA pipe.  At the end of a tile the four lane
-// results are widened to  hamming * 32768 + trainIdx  and merged into the thread's 32-bit pair (minimum = best).
-__device__ __forceinline__ uint32_t widen_key(uint32_t k16, uint32_t tile_base)
+// Epilogue arithmetic.  With every bit stored as +-8 the contraction gives 64 S = 128 (S/2), a multiple of 128 that fits
+// a signed 16-bit lane.  tcgen05.ld.pack::16b delivers two adjacent accumulators per register (their low 16 bits); one
+// integer multiply-add on the otherwise idle FMA pipe (x * 1 + constant, the 1 being a kernel argument so that it stays
+// an IMAD) puts  63 - c'  (c' = column inside the thread's 64-column half) into the free low 7 bits of both lanes:
+//      k16 = 128 (128 - hamming) + (63 - c')          in [-16384, 16447]
+// orders the columns of the half by (smaller distance, then smaller index) under MAX, and the running (best, second)
+// pair of both lanes costs 2.5 VIMNMX.S16x2 per register = 1.25 ALU instructions per accumulator.  At the end of a tile
+// the two survivors are widened to  hamming * 32768 + trainIdx  and merged into the thread's 32-bit pair (minimum = best).
+// (Measured alternative: a ninth K step over a constant slab that adds the index inside the MMA -- no epilogue
+// instruction at all, but 12.5 % more tensor work on a kernel whose tensor pipe is 88 % busy.)
+__device__ __forceinline__ uint32_t widen_key(uint32_t k16, uint32_t tile_base /* first column of the thread's half */)
 {
     const int k = (int)(short)k16;                         // empty lane: -32768 -> distance 384, dropped at the export
-    return (uint32_t)(128 - (k >> 7)) * 32768u + tile_base + (127u - ((uint32_t)k & 127u));
+    return (uint32_t)(128 - (k >> 7)) * 32768u + tile_base + (63u - ((uint32_t)k & 127u));
 }
 
 // Persistent kernel: one CTA per SM walks the (pair, 256-row query tile) items of the batch with a stride of gridDim.x.
@@ -195,8 +197,7 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
     // the launch requests no static shared memory, so the dynamic window starts 1024-byte aligned (checked)
     uint8_t *sA = smem_raw;                                 // [RB row blocks][KSLABS] query slabs
     uint8_t *sB = sA + RB * KSLABS * BM * SLAB;             // [STAGES][KSLABS] train slabs
-    uint8_t *sX = sB + STAGES * KSLABS * BN * SLAB;         // constant slab of the ninth K step
-    uint64_t *bars = (uint64_t *)(sX + BN * SLAB);
+    uint64_t *bars = (uint64_t *)(sB + STAGES * KSLABS * BN * SLAB);
     uint64_t *afull = bars, *aempty = afull + 1, *full = aempty + 1, *empty = full + STAGES, *tfull = empty + STAGES,
              *tempty = tfull + NACC;
     uint32_t *tmem_slot = (uint32_t *)(tempty + NACC);
@@ -214,16 +215,6 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // constant slab in the 128-byte-swizzle layout (16-byte chunk index XOR row mod 8): row r holds 1 at byte 0 (read as
-    // the query operand, K bytes 0..31) and 127 - r at byte 32 (read as the train operand, K bytes 32..63)
-    for (int i = threadIdx.x; i < BN * SLAB / 16; i += TC_THREADS) {
-        const int r = i >> 3, chunk = (i & 7) ^ (r & 7);
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (chunk == 0) v.x = 1u;
-        if (chunk == 2) v.x = (uint32_t)(127 - r);
-        reinterpret_cast<uint4 *>(sX)[i] = v;
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> visible to the tensor core
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
@@ -257,7 +248,6 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
         // ===== MMA issuer (converged warp, elected lane issues) =====
         {
             const uint32_t leader = elect_one();
-            const uint32_t xa_lo = desc_lo(smem_u32(sX)), xb_lo = desc_lo(smem_u32(sX) + 32);
             const uint32_t a_lo0 = desc_lo(smem_u32(sA)), b_lo0 = desc_lo(smem_u32(sB));
             uint32_t tile_no = 0, item_no = 0, use_no[RB] = {0, 0};
             ItemInfo it;
@@ -282,7 +272,6 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
                         for (int k = 1; k < 4 * KSLABS; ++k)
                             umma_i8<true>(d_tmem, a_lo + (k >> 2) * (BM * SLAB >> 4) + (k & 3) * 2,
                                           b_lo + (k >> 2) * (BN * SLAB >> 4) + (k & 3) * 2, leader);
-                        umma_i8<true>(d_tmem, xa_lo, xb_lo, leader);  // + (127 - column): the index half of the key
                         tcgen05_commit_if(tfull + acc, leader);      // accumulator ready for the epilogue
                         ++use_no[rb];
                     }
@@ -320,10 +309,12 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
                 tmem_ld_wait();
                 tcgen05_fence_before();
                 mbar_arrive(tempty + acc);
+                const uint32_t one = (uint32_t)a.one;    // opaque 1: keeps the index insertion an IMAD (FMA pipe)
+#define MVS_KEY(m) (v[m] * one + (uint32_t)(((63 - (2 * (m) + 1)) << 16) | (63 - 2 * (m))))
                 if (!ragged) {
 #pragma unroll
                     for (int m = 0; m < 32; m += 2) {
-                        const uint32_t pa = v[m], pb = v[m + 1];
+                        const uint32_t pa = MVS_KEY(m), pb = MVS_KEY(m + 1);
                         const uint32_t la = __vmins2(a1, pa), lb = __vmins2(b1, pb);
                         a1 = __vmaxs2(a1, pa); b1 = __vmaxs2(b1, pb);
                         a2 = __vmaxs2(a2, la); b2 = __vmaxs2(b2, lb);
@@ -332,7 +323,8 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
 #pragma unroll
                     for (int m = 0; m < 32; ++m) {
                         const int c = col0 + 2 * m;
-                        const uint32_t pk = (c < it.nt ? (v[m] & 0xFFFFu) : 0x8000u) | (c + 1 < it.nt ? (v[m] & 0xFFFF0000u) : 0x80000000u);
+                        const uint32_t key = MVS_KEY(m);
+                        const uint32_t pk = (c < it.nt ? (key & 0xFFFFu) : 0x8000u) | (c + 1 < it.nt ? (key & 0xFFFF0000u) : 0x80000000u);
                         const uint32_t lo = __vmins2(a1, pk);
                         a1 = __vmaxs2(a1, pk); a2 = __vmaxs2(a2, lo);
                     }
@@ -342,7 +334,8 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
                 const uint32_t r1 = __byte_perm(n1, 0, 0x1032), r2 = __byte_perm(n2, 0, 0x1032);
                 const uint32_t m1 = __vmaxs2(n1, r1);
                 const uint32_t m2 = __vmaxs2(__vmins2(n1, r1), __vmaxs2(n2, r2));
-                const uint32_t tile_base = (uint32_t)(i * BN);
+#undef MVS_KEY
+                const uint32_t tile_base = (uint32_t)col0;
                 top2(g1, g2, widen_key(m1 & 0xFFFFu, tile_base));
                 top2(g1, g2, widen_key(m2 & 0xFFFFu, tile_base));
             }
@@ -381,8 +374,8 @@ EncodeTiledFn get_encode_fn()
 
 cudaError_t launch_tc(const CUtensorMap &map, TcKnnArgs a, int max_nq, int n_pairs, cudaStream_t s)
 {
-    constexpr int STAGES = 4;   // one persistent CTA per SM: 64 KB query tile + 128 KB train ring + 16 KB constant slab
-    const size_t smem = (size_t)RB * KSLABS * BM * SLAB + (size_t)STAGES * KSLABS * BN * SLAB + (size_t)BN * SLAB +
+    constexpr int STAGES = 4;   // one persistent CTA per SM: 64 KB query tile + 128 KB train ring
+    const size_t smem = (size_t)RB * KSLABS * BM * SLAB + (size_t)STAGES * KSLABS * BN * SLAB +
                         (2 + 2 * STAGES + 2 * NACC) * sizeof(uint64_t) + 16;
     auto kern = knn2_hamming_tc_kernel<STAGES>;
     static int sm_count[64] = {0};          // per device: the shared-memory opt-in is a per-device function attribute
@@ -400,6 +393,7 @@ cudaError_t launch_tc(const CUtensorMap &map, TcKnnArgs a, int max_nq, int n_pai
     const int n_sm = sm_count[dev];
     a.q_tiles = (max_nq + RB * BM - 1) / (RB * BM);
     a.n_pairs = n_pairs;
+    a.one = 1;
     const long items = (long)a.q_tiles * n_pairs;
     kern<<<(unsigned)std::min<long>(items, n_sm), TC_THREADS, smem, s>>>(map, a);
     return cudaGetLastError();

@@ -1,6 +1,6 @@
 """Host-side model of the arithmetic of the tensor-core matcher (mvslam_b200/csrc/match_hamming_tc.cu), checked against the
-CPU oracle without a GPU: the +-8 byte encoding, the ninth K step that adds 127 - column, the signed 16-bit key
-`128 (128 - hamming) + (127 - c)` maximised per 128-column tile, and its widening to `hamming * 32768 + trainIdx`.
+CPU oracle without a GPU: the +-8 byte encoding, the signed 16-bit key `128 (128 - hamming) + (63 - c')` (c' = column
+inside a thread's 64-column half of a 128-column tile) maximised per half, and its widening to `hamming * 32768 + trainIdx`.
 The CUDA kernel is tested against the same oracle in tests/test_gpu_parity.py; this file pins the algebra it relies on."""
 import numpy as np
 import pytest
@@ -8,6 +8,7 @@ import pytest
 from oracle import cbind as orc
 
 BN = 128
+HALF = 64
 
 
 def expand(desc):
@@ -20,15 +21,15 @@ def model_knn2(q, t):
     Q, T = expand(q), expand(t)
     nt = t.shape[0]
     g = np.full((q.shape[0], 2), np.iinfo(np.int64).max, np.int64)          # running (best, second) of hamming*32768+idx
-    for t0 in range(0, nt, BN):
-        tile = T[t0:t0 + BN]
-        acc = Q @ tile.T + (127 - np.arange(tile.shape[0]))[None, :]        # 8 K steps + the constant ninth one
-        assert acc.min() >= -16384 and acc.max() <= 16511                    # fits the signed 16-bit lane
-        k16 = acc.astype(np.int16)
-        order = np.sort(k16, axis=1)[:, ::-1][:, :2].astype(np.int64)         # per tile: the two LARGEST keys
+    for t0 in range(0, nt, HALF):                                            # one thread's share of a tile: 64 columns
+        tile = T[t0:t0 + HALF]
+        acc = Q @ tile.T                                                     # 8 K steps: 64 (256 - 2 hamming)
+        assert (acc % 128 == 0).all() and acc.min() >= -16384 and acc.max() <= 16384
+        k16 = (acc + (63 - np.arange(tile.shape[0]))[None, :]).astype(np.int16)   # the IMAD of the epilogue
+        order = np.sort(k16, axis=1)[:, ::-1][:, :2].astype(np.int64)         # per half: the two LARGEST keys
         if order.shape[1] < 2:
             order = np.concatenate([order, np.full((q.shape[0], 1), -32768, np.int64)], 1)
-        wide = (128 - (order >> 7)) * 32768 + t0 + (127 - (order & 127))     # widen_key()
+        wide = (128 - (order >> 7)) * 32768 + t0 + (63 - (order & 127))      # widen_key()
         g = np.sort(np.concatenate([g, wide], 1), axis=1)[:, :2]
     dist, idx = g >> 15, g & 32767
     none = dist > 256                                                        # empty lane / nothing found
@@ -48,10 +49,10 @@ def test_model_equals_oracle(nq, nt, rand_bytes):
 
 def test_key_is_monotone_in_distance_then_index():
     """Larger 16-bit key <=> (smaller distance, then smaller column); the widened key orders the same way under MIN."""
-    d = np.arange(0, 257)[:, None]; c = np.arange(0, 128)[None, :]
-    k16 = 128 * (128 - d) + (127 - c)
+    d = np.arange(0, 257)[:, None]; c = np.arange(0, 64)[None, :]
+    k16 = 128 * (128 - d) + (63 - c)
     flat = k16.ravel()
-    assert len(np.unique(flat)) == flat.size and flat.min() == -16384 and flat.max() == 16511
-    wide = (128 - (k16 >> 7)) * 32768 + (127 - (k16 & 127))
+    assert len(np.unique(flat)) == flat.size and flat.min() == -16384 and flat.max() == 16447
+    wide = (128 - (k16 >> 7)) * 32768 + (63 - (k16 & 127))
     assert np.array_equal(wide, d * 32768 + c)
     assert np.array_equal(np.argsort(-flat, kind="stable"), np.argsort(wide.ravel(), kind="stable"))
