@@ -90,3 +90,22 @@ def test_cpp_adapters_compile_and_refuse_to_run_without_gpu():
     if not torch.cuda.is_available():
         r = subprocess.run([exe], capture_output=True, text=True)
         assert r.returncode != 0 and "no CPU fallback" in r.stdout
+
+
+def test_tensor_matcher_sass_uses_tcgen05_tma_and_tmem():
+    """Static evidence (no GPU): the shipped library's knn2_hamming_tc_kernel issues integer tcgen05 MMAs (UTCIMMA),
+    TMA tensor loads (UTMALDG), packed TMEM loads (LDTM ... PACK16BIT) and packed 16-bit min/max (VIMNMX.S16x2)."""
+    import shutil
+    import subprocess
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    lib = os.path.join(ROOT, "mvslam_b200", "libmvslam_b200.so")
+    out = subprocess.run([exe, "-sass", lib], capture_output=True, text=True, timeout=600).stdout
+    start = out.find("knn2_hamming_tc_kernel")
+    assert start >= 0, "kernel not found in the library"
+    end = out.find("Function :", start)
+    body = out[start:end if end > 0 else None]
+    for mnemonic in ("UTCIMMA", "UTMALDG", "LDTM", "PACK16BIT", "VIMNMX.S16x2", "UTCBAR"):
+        assert mnemonic in body, f"{mnemonic} missing from knn2_hamming_tc_kernel"
+    assert "sm_100a" in out or "sm_100" in out
