@@ -374,7 +374,7 @@ EncodeTiledFn get_encode_fn()
 
 cudaError_t launch_tc(const CUtensorMap &map, TcKnnArgs a, int max_nq, int n_pairs, cudaStream_t s)
 {
-    constexpr int STAGES = 4;   // one persistent CTA per SM: 64 KB query tile + 128 KB train ring
+    constexpr int STAGES = 5;   // one persistent CTA per SM: 64 KB query tile + 160 KB train ring
     const size_t smem = (size_t)RB * KSLABS * BM * SLAB + (size_t)STAGES * KSLABS * BN * SLAB +
                         (2 + 2 * STAGES + 2 * NACC) * sizeof(uint64_t) + 16;
     auto kern = knn2_hamming_tc_kernel<STAGES>;
