@@ -10,7 +10,8 @@ namespace b200 {
 /** Knobs the reference hard-codes (sfm-solve.cpp:18-23,67): process-wide defaults for the adapters. */
 inline mvs_ransac_params &ransac_defaults()
 {
-    static mvs_ransac_params p{1, MVS_SCORE_ALGEBRAIC, 0.0, 0, 0, 0, 0};   // H = 1: the reference's single sample
+    static mvs_ransac_params p{1, MVS_SCORE_ALGEBRAIC, 0.0, 0, 0, MVS_SOLVER_REFERENCE, 0};   // H = 1: the reference's single sample,
+                                                                                              // literal A^T A / cv::SVDecomp arithmetic
     return p;
 }
 inline std::vector<double> flatten(const std::vector<ImagePoint> &p)
@@ -62,7 +63,8 @@ inline void sfm_triangulate(const std::vector<ImagePoint> &p1, const std::vector
     std::vector<uint64_t> idx((size_t)n + 1);
     int m = 0;
     int st = mvs_sfm_triangulate(ctx, a.data(), b.data(), n, K.m, pose1.rotation().get_matrix().m, pose1.translation().v,
-                                 pose2.rotation().get_matrix().m, pose2.translation().v, pts.data(), idx.data(), n, &m);
+                                 pose2.rotation().get_matrix().m, pose2.translation().v, b200::ransac_defaults().solver, pts.data(),
+                                 idx.data(), n, &m);
     b200::check(ctx, st, "sfm_triangulate");
     points.resize(m);
     point_indexes.resize(m);
@@ -77,7 +79,7 @@ inline bool find_fundamental_matrix(const std::vector<Vector3Type> &p1_sample, c
     mvs_ctx *ctx = b200::Context::thread_default().get();
     double a[24], b[24];
     for (int i = 0; i < 8; ++i) for (int k = 0; k < 3; ++k) { a[3 * i + k] = p1_sample[i][k]; b[3 * i + k] = p2_sample[i][k]; }
-    int st = mvs_find_fundamental_matrix(ctx, a, b, 1, F21.m);
+    int st = mvs_find_fundamental_matrix(ctx, a, b, 1, b200::ransac_defaults().solver, F21.m);
     b200::check(ctx, st, "find_fundamental_matrix");
     return st == MVS_OK;
 }
@@ -100,7 +102,8 @@ public:
         std::vector<double> a((size_t)n * 3), b((size_t)n * 3);
         for (int i = 0; i < n; ++i) for (int k = 0; k < 3; ++k) { a[3 * i + k] = p1[i][k]; b[3 * i + k] = p2[i][k]; }
         std::vector<uint8_t> mask((size_t)n + 1);
-        const mvs_ransac_params rp{(int32_t)max_iteration, MVS_SCORE_ALGEBRAIC, max_error_sq, m_seed, 0, 0, 0};
+        const mvs_ransac_params rp{(int32_t)max_iteration, MVS_SCORE_ALGEBRAIC, max_error_sq, m_seed, 0,
+                                   b200::ransac_defaults().solver, 0};
         Matrix3Type F;
         int cnt = 0, bh = -1;
         double res = 0;

@@ -9,6 +9,20 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 (OK, E_BAD_ARG, E_TOO_FEW_POINTS, E_NO_MODEL, E_TOO_FEW_INLIERS, E_NO_CHEIRALITY, E_CUDA, E_CAPACITY,
  E_UNSUPPORTED) = range(9)
 SCORE_ALGEBRAIC, SCORE_SAMPSON = 0, 1
+SOLVER_REFERENCE, SOLVER_FAST = 0, 1
+_SOLVERS = {"reference": SOLVER_REFERENCE, "fast": SOLVER_FAST, SOLVER_REFERENCE: SOLVER_REFERENCE, SOLVER_FAST: SOLVER_FAST}
+# solver the geometry calls below use unless they name one (include/mvslam_b200.h, MVS_SOLVER_*)
+DEFAULT_SOLVER = "reference"
+
+
+def set_default_solver(name):
+    global DEFAULT_SOLVER
+    assert name in ("reference", "fast")
+    DEFAULT_SOLVER = name
+
+
+def _solver(solver):
+    return _SOLVERS[DEFAULT_SOLVER if solver is None else solver]
 STAGES = ("knn", "match_finalize", "hypotheses", "score", "select", "triangulate", "finalize", "l2",
           "orb_pyramid", "orb_fast", "orb_harris", "orb_select", "orb_blur", "orb_describe", "pnp", "ba")
 
@@ -28,7 +42,7 @@ class MatchParams(C.Structure):
 
 class RansacParams(C.Structure):
     _fields_ = [("n_hypotheses", C.c_int32), ("score_mode", C.c_int32), ("max_error_sq", C.c_double),
-                ("seed", C.c_uint64), ("min_inliers", C.c_int32), ("reserved", C.c_int32),
+                ("seed", C.c_uint64), ("min_inliers", C.c_int32), ("solver", C.c_int32),
                 ("pair_id_base", C.c_uint64)]
 
 
@@ -108,7 +122,7 @@ def load_library():
     L.mvs_destroy.argtypes = [C.c_void_p]
     L.mvs_sample_table.restype = None
     L.mvs_pnp_sample_table.restype = None
-    if L.mvs_abi_version() != 2:
+    if L.mvs_abi_version() != 3:
         raise ImportError("libmvslam_b200.so ABI version mismatch")
     _lib = L
     return L
@@ -278,18 +292,24 @@ class Context:
         return dict(fallback_fwd=int(out[0]), fallback_rev=int(out[1]), gemm_us=int(out[2]), total_us=int(out[3]))
 
     # ---- geometry
-    def find_fundamental_matrix(self, p1s, p2s):
+    def find_fundamental_matrix(self, p1s, p2s, solver=None):
         p1s = _f64(p1s).reshape(-1, 8, 3); p2s = _f64(p2s).reshape(-1, 8, 3)
         F = np.empty((p1s.shape[0], 3, 3))
-        self._check(self._L.mvs_find_fundamental_matrix(self._h, _p(p1s), _p(p2s), p1s.shape[0], _p(F)))
+        self._check(self._L.mvs_find_fundamental_matrix(self._h, _p(p1s), _p(p2s), p1s.shape[0], _solver(solver), _p(F)))
         return F
 
+    def svd_batch(self, A, solver=None):
+        A = _f64(A); cnt, n = A.shape[0], A.shape[1]
+        U = np.empty_like(A); Vt = np.empty_like(A); w = np.empty((cnt, n))
+        self._check(self._L.mvs_svd_batch(self._h, n, _p(A), cnt, _solver(solver), _p(U), _p(w), _p(Vt)))
+        return U, w, Vt
+
     def ransac_fundamental(self, p1, p2, samples=None, H=1, max_error_sq=1e-3, mode=SCORE_ALGEBRAIC, seed=0,
-                           want_all=False):
+                           want_all=False, solver=None):
         p1 = _f64(p1); p2 = _f64(p2); n = p1.shape[0]
         if samples is not None:
             samples = np.ascontiguousarray(samples, np.uint32); H = samples.shape[0]
-        rp = RansacParams(H, mode, max_error_sq, seed, 0, 0, 0)
+        rp = RansacParams(H, mode, max_error_sq, seed, 0, _solver(solver), 0)
         F = np.zeros((3, 3)); mask = np.zeros(max(n, 1), np.uint8)
         cnt = C.c_int(); res = C.c_double(); bh = C.c_int(-1)
         allc = np.zeros(H, np.int32) if want_all else None
@@ -301,11 +321,12 @@ class Context:
             out["all_counts"] = allc
         return out
 
-    def sfm_solve(self, xy1, xy2, K, samples=None, H=1, seed=0, pair_id=0, mode=SCORE_ALGEBRAIC, max_error_sq=0.0):
+    def sfm_solve(self, xy1, xy2, K, samples=None, H=1, seed=0, pair_id=0, mode=SCORE_ALGEBRAIC, max_error_sq=0.0,
+                  solver=None):
         xy1 = _f64(xy1); xy2 = _f64(xy2); n = xy1.shape[0]
         if samples is not None:
             samples = np.ascontiguousarray(samples, np.uint32); H = samples.shape[0]
-        rp = RansacParams(H, mode, max_error_sq, seed, 0, 0, pair_id)
+        rp = RansacParams(H, mode, max_error_sq, seed, 0, _solver(solver), pair_id)
         res = np.zeros(1, RESULT_DTYPE); mask = np.zeros(max(n, 1), np.uint8)
         pts = np.empty((max(n, 1), 3)); idx = np.empty(max(n, 1), np.uint64)
         st = self._L.mvs_sfm_solve(self._h, _p(xy1), _p(xy2), n, _p(_f64(K)), C.byref(rp), _p(samples), _p(res),
@@ -317,11 +338,11 @@ class Context:
         d["mask"] = mask[:n]; d["points"] = pts[:m].copy(); d["indexes"] = idx[:m].copy()
         return d
 
-    def sfm_triangulate(self, xy1, xy2, K, R1, t1, R2, t2):
+    def sfm_triangulate(self, xy1, xy2, K, R1, t1, R2, t2, solver=None):
         xy1 = _f64(xy1); xy2 = _f64(xy2); n = xy1.shape[0]
         pts = np.empty((max(n, 1), 3)); idx = np.empty(max(n, 1), np.uint64); m = C.c_int(0)
         self._check(self._L.mvs_sfm_triangulate(self._h, _p(xy1), _p(xy2), n, _p(_f64(K)), _p(_f64(R1)), _p(_f64(t1)),
-                                                _p(_f64(R2)), _p(_f64(t2)), _p(pts), _p(idx), max(n, 1), C.byref(m)))
+                                                _p(_f64(R2)), _p(_f64(t2)), _solver(solver), _p(pts), _p(idx), max(n, 1), C.byref(m)))
         return pts[:m.value].copy(), idx[:m.value].copy()
 
     # ---- pnp_solve
@@ -420,12 +441,12 @@ class Context:
         return idx.value
 
     def pair_batch(self, pairs, K, ratio=0.7, max_dist=-1.0, cross_check=False, H=1, seed=0, mode=SCORE_ALGEBRAIC,
-                   max_error_sq=0.0, pair_id_base=0, details=True, out=None, enqueue_only=False, bounded=False):
+                   max_error_sq=0.0, pair_id_base=0, details=True, out=None, enqueue_only=False, bounded=False, solver=None):
         """Returns (results[RESULT_DTYPE], details dict or None).  `out` may hold preallocated (e.g. pinned)
         buffers: dict(results=addr/array, matches=, mask=, points=, indexes=, capacity=int)."""
         pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2); npairs = pairs.shape[0]
         mp = MatchParams(ratio, max_dist, int(cross_check), int(bounded))
-        rp = RansacParams(H, mode, max_error_sq, seed, 0, 0, pair_id_base)
+        rp = RansacParams(H, mode, max_error_sq, seed, 0, _solver(solver), pair_id_base)
         fn = self._L.mvs_pair_batch_enqueue if enqueue_only else self._L.mvs_pair_batch
         if out is not None:
             st = fn(self._h, _p(pairs), npairs, _p(_f64(K)), C.byref(mp), C.byref(rp), _p(out["results"]),

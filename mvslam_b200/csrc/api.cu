@@ -181,7 +181,7 @@ void h_inverse3(const double K[9], double Ki[9])
     Ki[6] = c02 * id; Ki[7] = c12 * id; Ki[8] = c22 * id;
 }
 
-struct RansacCfg { int H; int mode; double thr; uint64_t seed; int min_inl; uint64_t pair_base; };
+struct RansacCfg { int H; int mode; double thr; uint64_t seed; int min_inl; uint64_t pair_base; int solver; };
 
 int resolve_ransac(mvs_ctx *ctx, const mvs_ransac_params *rp, const double *K, RansacCfg &c)
 {
@@ -191,6 +191,8 @@ int resolve_ransac(mvs_ctx *ctx, const mvs_ransac_params *rp, const double *K, R
     c.seed = rp ? rp->seed : 0;
     c.pair_base = rp ? rp->pair_id_base : 0;
     c.min_inl = (rp && rp->min_inliers > 0) ? rp->min_inliers : kMinInliers;
+    c.solver = rp ? rp->solver : MVS_SOLVER_REFERENCE;
+    if (c.solver != MVS_SOLVER_REFERENCE && c.solver != MVS_SOLVER_FAST) return fail(ctx, MVS_E_BAD_ARG, "bad solver");
     if (c.H < 1) return fail(ctx, MVS_E_BAD_ARG, "n_hypotheses must be >= 1");
     if (c.mode != MVS_SCORE_ALGEBRAIC && c.mode != MVS_SCORE_SAMPSON) return fail(ctx, MVS_E_BAD_ARG, "bad score_mode");
     if (!(c.thr > 0.0)) {
@@ -219,6 +221,7 @@ int run_geometry(mvs_ctx *ctx, int n_pairs, int p_stride, const RansacCfg &rc, b
         HypArgs a{};
         a.points = ctx->d_points.as<double>(); a.p_stride = p_stride; a.state = state;
         a.table = d_table; a.seed = rc.seed; a.pair_id_base = pair_id_base; a.H = rc.H; a.F_all = ctx->d_Fall.as<double>();
+        a.solver = rc.solver;
         launch_hypotheses(a, n_pairs, ctx->stream);
     }
     {
@@ -226,7 +229,7 @@ int run_geometry(mvs_ctx *ctx, int n_pairs, int p_stride, const RansacCfg &rc, b
         ScoreArgs a{};
         a.points = ctx->d_points.as<double>(); a.p_stride = p_stride; a.state = state; a.F_all = ctx->d_Fall.as<double>();
         a.H = rc.H; a.max_error_sq = rc.thr; a.zc1 = zc1; a.zc2 = zc2; a.tiles = tiles; a.part_count = ctx->d_pc.as<uint32_t>();
-        a.part_res = k4_res ? ctx->d_pres.as<double>() : nullptr;
+        a.part_res = k4_res ? ctx->d_pres.as<double>() : nullptr; a.solver = rc.solver;
         launch_score(a, rc.mode, unit_z, n_pairs, ctx->stream);
     }
     {
@@ -237,6 +240,7 @@ int run_geometry(mvs_ctx *ctx, int n_pairs, int p_stride, const RansacCfg &rc, b
         a.part_res = k4_res ? ctx->d_pres.as<double>() : nullptr;
         a.max_error_sq = rc.thr; a.zc1 = zc1; a.zc2 = zc2; a.min_inliers = rc.min_inl; a.decompose = decompose ? 1 : 0;
         a.mask = ctx->d_mask.as<uint8_t>(); a.all_counts = want_all_counts ? ctx->d_counts.as<int32_t>() : nullptr;
+        a.solver = rc.solver;
         launch_select(a, rc.mode, unit_z, n_pairs, ctx->stream);
     }
     if (!decompose) return MVS_OK;
@@ -249,7 +253,7 @@ int run_geometry(mvs_ctx *ctx, int n_pairs, int p_stride, const RansacCfg &rc, b
         StageTimer t(ctx, MVS_STAGE_TRIANGULATE);
         TriArgs a{};
         a.points = ctx->d_points.as<double>(); a.p_stride = p_stride; a.state = state; a.mask = ctx->d_mask.as<uint8_t>();
-        a.n_cand = 4; a.valid = ctx->d_valid.as<uint8_t>(); a.tri = ctx->d_tri.as<double>();
+        a.n_cand = 4; a.valid = ctx->d_valid.as<uint8_t>(); a.tri = ctx->d_tri.as<double>(); a.solver = rc.solver;
         launch_triangulate(a, p_stride, n_pairs, ctx->stream);
     }
     {
@@ -595,8 +599,9 @@ int mvs_l2_stats(const mvs_ctx *ctx, uint64_t out[4])
 }
 
 // ------------------------------------------------------------------------------------------ geometry
-int mvs_find_fundamental_matrix(mvs_ctx *ctx, const double *p1s, const double *p2s, int n_sets, double *F_out)
+int mvs_find_fundamental_matrix(mvs_ctx *ctx, const double *p1s, const double *p2s, int n_sets, int solver, double *F_out)
 {
+    if (ctx && solver != MVS_SOLVER_REFERENCE && solver != MVS_SOLVER_FAST) return fail(ctx, MVS_E_BAD_ARG, "bad solver");
     if (!ctx) return MVS_E_BAD_ARG;
     if (!p1s || !p2s || !F_out || n_sets < 1) return fail(ctx, MVS_E_BAD_ARG, "null argument or n_sets < 1");
     CK(cudaSetDevice(ctx->device));
@@ -607,10 +612,34 @@ int mvs_find_fundamental_matrix(mvs_ctx *ctx, const double *p1s, const double *p
     CK(cudaMemcpyAsync(ctx->d_in2.p, p2s, in_b, cudaMemcpyHostToDevice, ctx->stream));
     {
         StageTimer t(ctx, MVS_STAGE_HYPOTHESES);
-        launch_fundamental_sets(ctx->d_in1.as<double>(), ctx->d_in2.as<double>(), n_sets, ctx->d_Fall.as<double>(), ctx->stream);
+        launch_fundamental_sets(ctx->d_in1.as<double>(), ctx->d_in2.as<double>(), n_sets, ctx->d_Fall.as<double>(), solver, ctx->stream);
     }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(F_out, ctx->d_Fall.p, (size_t)n_sets * 9 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MVS_OK;
+}
+
+int mvs_svd_batch(mvs_ctx *ctx, int n, const double *A, int count, int solver, double *U, double *w, double *Vt)
+{
+    if (!ctx) return MVS_E_BAD_ARG;
+    if (!A || !U || !w || !Vt || count < 1) return fail(ctx, MVS_E_BAD_ARG, "null argument or count < 1");
+    if (solver != MVS_SOLVER_REFERENCE && solver != MVS_SOLVER_FAST) return fail(ctx, MVS_E_BAD_ARG, "bad solver");
+    if (!(n == 3 || ((n == 4 || n == 9) && solver == MVS_SOLVER_REFERENCE)))
+        return fail(ctx, MVS_E_UNSUPPORTED, "n must be 3, or 4 / 9 with MVS_SOLVER_REFERENCE");
+    CK(cudaSetDevice(ctx->device));
+    const size_t mb = (size_t)count * n * n * sizeof(double), wb = (size_t)count * n * sizeof(double);
+    CK(ctx->d_in1.ensure(mb)); CK(ctx->d_in2.ensure(mb)); CK(ctx->d_Fall.ensure(mb + wb));
+    CK(cudaMemcpyAsync(ctx->d_in1.p, A, mb, cudaMemcpyHostToDevice, ctx->stream));
+    double *dVt = ctx->d_Fall.as<double>(), *dw = dVt + (size_t)count * n * n;
+    {
+        StageTimer t(ctx, MVS_STAGE_HYPOTHESES);
+        launch_svd_batch(n, ctx->d_in1.as<double>(), count, solver, ctx->d_in2.as<double>(), dw, dVt, ctx->stream);
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(U, ctx->d_in2.p, mb, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(Vt, dVt, mb, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(w, dw, wb, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return MVS_OK;
 }
@@ -719,10 +748,11 @@ int mvs_sfm_solve(mvs_ctx *ctx, const double *xy1, const double *xy2, int n, con
 }
 
 int mvs_sfm_triangulate(mvs_ctx *ctx, const double *xy1, const double *xy2, int n, const double K[9],
-                        const double R1[9], const double t1[3], const double R2[9], const double t2[3],
+                        const double R1[9], const double t1[3], const double R2[9], const double t2[3], int solver,
                         double *points, uint64_t *indexes, int capacity, int *n_out)
 {
     if (!ctx) return MVS_E_BAD_ARG;
+    if (solver != MVS_SOLVER_REFERENCE && solver != MVS_SOLVER_FAST) return fail(ctx, MVS_E_BAD_ARG, "bad solver");
     if (!xy1 || !xy2 || !K || !R1 || !t1 || !R2 || !t2 || !n_out || n < 0) return fail(ctx, MVS_E_BAD_ARG, "null argument");
     *n_out = 0;
     if (n == 0) return MVS_OK;
@@ -756,7 +786,7 @@ int mvs_sfm_triangulate(mvs_ctx *ctx, const double *xy1, const double *xy2, int 
         StageTimer t(ctx, MVS_STAGE_TRIANGULATE);
         TriArgs a{};
         a.points = ctx->d_points.as<double>(); a.p_stride = n; a.state = ctx->d_state.as<PairState>(); a.mask = nullptr;
-        a.n_cand = 1; a.valid = ctx->d_valid.as<uint8_t>(); a.tri = ctx->d_tri.as<double>();
+        a.n_cand = 1; a.valid = ctx->d_valid.as<uint8_t>(); a.tri = ctx->d_tri.as<double>(); a.solver = solver;
         launch_triangulate(a, n, 1, ctx->stream);
     }
     {

@@ -210,6 +210,200 @@ static __device__ __noinline__ void svd3(const double A[9], double U[9], double 
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// REFERENCE solver: cv::SVDecomp(MODIFY_A | FULL_UV) restated bit for bit.  For the 3x3, 4x4 and 9x9 matrices of
+// this path OpenCV (un-vendored dependency, "opencv >= 3.0", README.md:12) never reaches LAPACK: it transposes the
+// input and runs its own one-sided Hestenes Jacobi on the ROWS of A^T in plain cyclic (i<j) order, with its own
+// scaled hypot, carried squared norms, a selection sort by norm and — for zero singular values — left vectors
+// regenerated from cv::RNG(0x12345678).  Everything is IEEE + - * / sqrt in a fixed order (OpenCV's x86-64 baseline
+// has no FMA; these translation units are compiled with -fmad=false), so the results equal cv2.SVDecomp's to the
+// last bit; tests/test_gpu_reference_solver.py checks that against committed cv2 outputs and live cv2.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double cv_hypot(double a, double b)
+{
+    a = fabs(a); b = fabs(b);
+    if (a > b) { b /= a; return a * sqrt(1 + b * b); }
+    if (b > 0) { a /= b; return b * sqrt(1 + a * a); }
+    return 0;
+}
+
+// At holds A^T on entry (row i = column i of A).  On exit: rows rotated to mutual orthogonality (NOT yet sorted or
+// normalised), V the accumulated rotations (row i belongs to row i of At), W[i] = |At row i|.
+template <int N>
+__device__ __forceinline__ void cv_jacobi(double (&At)[N][N], double (&V)[N][N], double (&W)[N])
+{
+    constexpr double eps = DBL_EPSILON * 10;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        double sd = 0;
+#pragma unroll
+        for (int k = 0; k < N; ++k) { const double t = At[i][k]; sd += t * t; }
+        W[i] = sd;
+#pragma unroll
+        for (int k = 0; k < N; ++k) V[i][k] = (i == k) ? 1.0 : 0.0;
+    }
+    for (int iter = 0; iter < 30; ++iter) {   // max_iter = max(m, 30)
+        bool changed = false;
+#pragma unroll
+        for (int i = 0; i < N - 1; ++i)
+#pragma unroll
+            for (int j = i + 1; j < N; ++j) {
+                double a = W[i], p = 0, b = W[j];
+#pragma unroll
+                for (int k = 0; k < N; ++k) p += At[i][k] * At[j][k];
+                if (!(fabs(p) <= eps * sqrt(a * b))) {
+                    p *= 2;
+                    const double beta = a - b, gamma = cv_hypot(p, beta);
+                    double c, s;
+                    if (beta < 0) {
+                        const double delta = (gamma - beta) * 0.5;
+                        s = sqrt(delta / gamma);
+                        c = p / (gamma * s * 2);
+                    } else {
+                        c = sqrt((gamma + beta) / (gamma * 2));
+                        s = p / (gamma * c * 2);
+                    }
+                    a = b = 0;
+#pragma unroll
+                    for (int k = 0; k < N; ++k) {
+                        const double t0 = c * At[i][k] + s * At[j][k];
+                        const double t1 = -s * At[i][k] + c * At[j][k];
+                        At[i][k] = t0; At[j][k] = t1;
+                        a += t0 * t0; b += t1 * t1;
+                    }
+                    W[i] = a; W[j] = b;
+                    changed = true;
+#pragma unroll
+                    for (int k = 0; k < N; ++k) {
+                        const double t0 = c * V[i][k] + s * V[j][k];
+                        const double t1 = -s * V[i][k] + c * V[j][k];
+                        V[i][k] = t0; V[j][k] = t1;
+                    }
+                }
+            }
+        if (!changed) break;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        double sd = 0;
+#pragma unroll
+        for (int k = 0; k < N; ++k) { const double t = At[i][k]; sd += t * t; }
+        W[i] = sqrt(sd);
+    }
+}
+
+// OpenCV's descending selection sort (swap position i with the FIRST maximum of the tail), applied to W and to a
+// permutation instead of the rows themselves: afterwards sorted row r is original row perm[r].
+template <int N>
+__device__ __forceinline__ void cv_sort_perm(double (&W)[N], int (&perm)[N])
+{
+#pragma unroll
+    for (int i = 0; i < N; ++i) perm[i] = i;
+#pragma unroll
+    for (int i = 0; i < N - 1; ++i) {
+        int j = i;
+        double wj = W[i];
+#pragma unroll
+        for (int k = i + 1; k < N; ++k)
+            if (wj < W[k]) { j = k; wj = W[k]; }
+        // swap(W[i], W[j]), swap(perm[i], perm[j]) with j only known at run time
+        const double wi = W[i];
+        const int pi = perm[i];
+        int pj = pi;
+#pragma unroll
+        for (int k = i + 1; k < N; ++k)
+            if (k == j) { pj = perm[k]; perm[k] = pi; W[k] = wi; }
+        W[i] = wj; perm[i] = pj;
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void cv_pick_row(const double (&M)[N][N], int r, double (&out)[N])
+{
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        double v = M[0][k];
+#pragma unroll
+        for (int i = 1; i < N; ++i) v = (r == i) ? M[i][k] : v;
+        out[k] = v;
+    }
+}
+
+// Right singular vector of the smallest singular value = vt.row(N-1) of cv::SVDecomp(A) (what the 8-point solve
+// and the DLT triangulation take: fundamental-matrix.cpp:114-118, sfm-solve.cpp:193-195).  At = A^T on entry.
+template <int N>
+__device__ __forceinline__ void cv_svd_last_vt(double (&At)[N][N], double (&x)[N])
+{
+    double V[N][N], W[N];
+    int perm[N];
+    cv_jacobi<N>(At, V, W);
+    cv_sort_perm<N>(W, perm);
+    cv_pick_row<N>(V, perm[N - 1], x);
+}
+
+// Full cv::SVDecomp of an N x N matrix: A row-major in, U row-major, w descending, Vt row-major (the SVD<> wrapper of
+// source/math/svd.hpp:59-72 then takes V = vt^T).
+template <int N>
+__device__ __forceinline__ void cv_svd_full(const double *A, double *U, double *w, double *Vt)
+{
+    constexpr double eps = DBL_EPSILON * 10, minval = DBL_MIN;
+    double At[N][N], V[N][N], W[N];
+    int perm[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int k = 0; k < N; ++k) At[i][k] = A[k * N + i];
+    cv_jacobi<N>(At, V, W);
+    cv_sort_perm<N>(W, perm);
+    double As[N][N];
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+        double a[N], v[N];
+        cv_pick_row<N>(At, perm[r], a);
+        cv_pick_row<N>(V, perm[r], v);
+#pragma unroll
+        for (int k = 0; k < N; ++k) { As[r][k] = a[k]; Vt[r * N + k] = v[k]; }
+        w[r] = W[r];
+    }
+    // left singular vectors: normalised rows; zero rows are regenerated from cv::RNG (multiply-with-carry)
+    uint64_t rng = 0x12345678ull;
+    for (int i = 0; i < N; ++i) {
+        double sd = W[i];
+        for (int ii = 0; ii < 100 && sd <= minval; ++ii) {
+            const double val0 = 1. / N;
+            for (int k = 0; k < N; ++k) {
+                rng = (uint64_t)(uint32_t)rng * 4164903690u + (uint32_t)(rng >> 32);
+                As[i][k] = ((uint32_t)rng & 256u) != 0 ? val0 : -val0;
+            }
+            for (int it = 0; it < 2; ++it)
+                for (int j = 0; j < i; ++j) {
+                    sd = 0;
+                    for (int k = 0; k < N; ++k) sd += As[i][k] * As[j][k];
+                    double asum = 0;
+                    for (int k = 0; k < N; ++k) {
+                        const double t = As[i][k] - sd * As[j][k];
+                        As[i][k] = t;
+                        asum += fabs(t);
+                    }
+                    asum = asum > eps * 100 ? 1 / asum : 0;
+                    for (int k = 0; k < N; ++k) As[i][k] *= asum;
+                }
+            sd = 0;
+            for (int k = 0; k < N; ++k) { const double t = As[i][k]; sd += t * t; }
+            sd = sqrt(sd);
+        }
+        const double s = sd > minval ? 1 / sd : 0.;
+        for (int k = 0; k < N; ++k) As[i][k] *= s;
+    }
+    for (int i = 0; i < N; ++i)
+        for (int k = 0; k < N; ++k) U[i * N + k] = As[k][i];
+}
+
+static __device__ __noinline__ void cv_svd3(const double A[9], double U[9], double w[3], double Vt[9])
+{
+    cv_svd_full<3>(A, U, w, Vt);
+}
+
 __device__ __forceinline__ void mat3_mul(const double A[9], const double B[9], double C[9])
 {
 #pragma unroll
@@ -277,12 +471,19 @@ __device__ __forceinline__ FzConst make_fz(const double (&F)[9], double z1, doub
     return c;
 }
 
-template <bool CONST_Z, int MODE, bool WANT_RES = true>
+template <bool CONST_Z, int MODE, bool WANT_RES = true, bool LIT = false>
 __device__ __forceinline__ bool point_residual(double x1, double y1, double z1, double x2, double y2, double z2,
                                                const double (&F)[9], const FzConst &zc, double thr, double &res)
 {
     double v0, v1, v2, r;
-    if (CONST_Z) {
+    if (LIT) {
+        // REFERENCE solver: (p2^T F) p1 as Eigen's coefficient-based products evaluate it in the reference build
+        // (no FMA, EIGEN_DONT_VECTORIZE: SConstruct:70,86): every product rounded, sums left to right
+        v0 = (x2 * F[0] + y2 * F[3]) + (CONST_Z ? zc.F6z : z2 * F[6]);
+        v1 = (x2 * F[1] + y2 * F[4]) + (CONST_Z ? zc.F7z : z2 * F[7]);
+        v2 = (x2 * F[2] + y2 * F[5]) + (CONST_Z ? zc.F8z : z2 * F[8]);
+        r = (v0 * x1 + v1 * y1) + v2 * (CONST_Z ? zc.z1 : z1);
+    } else if (CONST_Z) {
         v0 = fma(x2, F[0], fma(y2, F[3], zc.F6z));
         v1 = fma(x2, F[1], fma(y2, F[4], zc.F7z));
         v2 = fma(x2, F[2], fma(y2, F[5], zc.F8z));
@@ -297,15 +498,21 @@ __device__ __forceinline__ bool point_residual(double x1, double y1, double z1, 
         res = fabs(r);
         return res < thr;
     }
-    double l0, l1;
-    if (CONST_Z) {
-        l0 = fma(F[0], x1, fma(F[1], y1, zc.F2z));
-        l1 = fma(F[3], x1, fma(F[4], y1, zc.F5z));
+    double l0, l1, den;
+    if (LIT) {
+        l0 = (F[0] * x1 + F[1] * y1) + (CONST_Z ? zc.F2z : F[2] * z1);
+        l1 = (F[3] * x1 + F[4] * y1) + (CONST_Z ? zc.F5z : F[5] * z1);
+        den = (l0 * l0 + l1 * l1) + (v0 * v0 + v1 * v1);
     } else {
-        l0 = fma(F[0], x1, fma(F[1], y1, F[2] * z1));
-        l1 = fma(F[3], x1, fma(F[4], y1, F[5] * z1));
+        if (CONST_Z) {
+            l0 = fma(F[0], x1, fma(F[1], y1, zc.F2z));
+            l1 = fma(F[3], x1, fma(F[4], y1, zc.F5z));
+        } else {
+            l0 = fma(F[0], x1, fma(F[1], y1, F[2] * z1));
+            l1 = fma(F[3], x1, fma(F[4], y1, F[5] * z1));
+        }
+        den = fma(l0, l0, l1 * l1) + fma(v0, v0, v1 * v1);
     }
-    const double den = fma(l0, l0, l1 * l1) + fma(v0, v0, v1 * v1);
     const double r2 = r * r;
     if (!(r2 < thr * den)) return false;
     if (WANT_RES) res = r2 / den;

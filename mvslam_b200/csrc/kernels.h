@@ -58,6 +58,8 @@ struct HypArgs {
     uint64_t pair_id_base;
     int H;
     double *F_all;             // [pairs][H][9]
+    int solver;                // MVS_SOLVER_*
+    int n_pairs;               // filled by the launcher
 };
 
 struct ScoreArgs {
@@ -69,6 +71,7 @@ struct ScoreArgs {
     int tiles;                 // point tiles per pair
     uint32_t *part_count;      // [pairs][tiles][H]
     double *part_res;          // [pairs][tiles][H] residual sums (ALGEBRAIC mode only, else nullptr)
+    int solver;
 };
 
 struct SelectArgs {
@@ -84,6 +87,7 @@ struct SelectArgs {
     int decompose;             // 0: stop after the mask (mvs_ransac_fundamental)
     uint8_t *mask;             // [pairs][p_stride]
     int32_t *all_counts;       // optional [pairs][H]
+    int solver;
 };
 
 struct TriArgs {
@@ -93,6 +97,7 @@ struct TriArgs {
     int n_cand;                // 4 (recover_pose_and_points) or 1 (sfm_triangulate: Rc[0], tc as given)
     uint8_t *valid;            // [pairs][4][p_stride]
     double *tri;               // [pairs][4][p_stride][3]
+    int solver;
 };
 
 struct FinishArgs {
@@ -116,7 +121,8 @@ void launch_normalize_points(const double *xy1, const double *xy2, int n, const 
                              cudaStream_t s);
 
 void launch_hypotheses(const HypArgs &a, int n_pairs, cudaStream_t s);
-void launch_fundamental_sets(const double *p1s, const double *p2s, int n_sets, double *F_out, cudaStream_t s);
+void launch_fundamental_sets(const double *p1s, const double *p2s, int n_sets, double *F_out, int solver, cudaStream_t s);
+bool launch_svd_batch(int n, const double *A, int count, int solver, double *U, double *w, double *Vt, cudaStream_t s);
 int score_tiles(int max_points);
 void launch_score(const ScoreArgs &a, int mode, bool const_z, int n_pairs, cudaStream_t s);
 void launch_select(const SelectArgs &a, int mode, bool const_z, int n_pairs, cudaStream_t s);

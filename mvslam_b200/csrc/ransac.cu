@@ -130,14 +130,55 @@ __device__ __forceinline__ void eight_point(const double *pts, const uint32_t (&
     mat3_mul(tmp, T1m, F);
 }
 
-__global__ void __launch_bounds__(HYP_THREADS)
-hypotheses_kernel(HypArgs a)
+// REFERENCE solver of the same sample: find_normalization_transform (fundamental-matrix.cpp:18-54),
+// find_fundamental_matrix_8point (:56-140) and the de-normalisation (:245) exactly as written there — normalised
+// points as (p - mean) * scale, A^T A accumulated element by element over the 8 rows (:104-111), f = vt.row(8) of
+// cv::SVDecomp (:114-118), singular constraint u * diag(w0, w1, 0) * vt through a second cv::SVDecomp (:128-136).
+__device__ __forceinline__ void eight_point_reference(const double *pts, const uint32_t (&idx)[8], double (&F)[9])
 {
-    const int pair = blockIdx.y;
+    double T1[3], T2[3], mx1, my1, mx2, my2;
+    normalize8(pts, idx, 0, T1, mx1, my1);
+    normalize8(pts, idx, 3, T2, mx2, my2);
+    double At[9][9];
+    {
+        double A[8][9];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) epipolar_row(pts + (size_t)idx[r] * 6, T1, mx1, my1, T2, mx2, my2, A[r]);
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+#pragma unroll
+            for (int j = i; j < 9; ++j) {
+                double acc = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc += A[k][i] * A[k][j];
+                At[i][j] = acc; At[j][i] = acc;   // products commute bitwise: A^T A is exactly symmetric, (A^T A)^T = A^T A
+            }
+    }
+    double Fp[9];
+    cv_svd_last_vt<9>(At, Fp);
+    double U[9], w3[3], Vt[9], Fh[9], T2t[9], tmp[9];
+    cv_svd3(Fp, U, w3, Vt);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            Fh[i * 3 + j] = (U[i * 3 + 0] * w3[0]) * Vt[0 * 3 + j] + (U[i * 3 + 1] * w3[1]) * Vt[1 * 3 + j];
+    const double T1m[9] = {T1[0], 0.0, T1[1], 0.0, T1[0], T1[2], 0.0, 0.0, 1.0};
+    const double T2m[9] = {T2[0], 0.0, T2[1], 0.0, T2[0], T2[2], 0.0, 0.0, 1.0};
+    mat3_transpose(T2m, T2t);
+    mat3_mul(T2t, Fh, tmp);
+    mat3_mul(tmp, T1m, F);
+}
+
+// One thread per (pair, hypothesis), flattened so that H = 1 (the reference's only sample) still fills warps.
+template <bool REF>
+__device__ __forceinline__ void hypothesis_body(const HypArgs &a)
+{
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int pair = (int)(gid / a.H), h = (int)(gid % a.H);
+    if (pair >= a.n_pairs) return;
     if (a.state[pair].status != MVS_OK) return;
     const int n = a.state[pair].n_matches;
-    const int h = blockIdx.x * HYP_THREADS + threadIdx.x;
-    if (h >= a.H) return;
     uint32_t idx[8];
     if (a.table) {
 #pragma unroll
@@ -146,15 +187,23 @@ hypotheses_kernel(HypArgs a)
         sample_row(a.seed, a.pair_id_base + (uint64_t)pair, (uint32_t)n, h, idx);
     }
     double F[9];
-    eight_point(a.points + (size_t)pair * a.p_stride * 6, idx, F);
+    if (REF) eight_point_reference(a.points + (size_t)pair * a.p_stride * 6, idx, F);
+    else eight_point(a.points + (size_t)pair * a.p_stride * 6, idx, F);
     double *o = a.F_all + ((size_t)pair * a.H + h) * 9;
 #pragma unroll
     for (int i = 0; i < 9; ++i) o[i] = F[i];
 }
 
+constexpr int HYP_REF_THREADS = 64;
+__global__ void __launch_bounds__(HYP_REF_THREADS)
+hypotheses_reference_kernel(HypArgs a) { hypothesis_body<true>(a); }
+
+__global__ void __launch_bounds__(HYP_THREADS)
+hypotheses_kernel(HypArgs a) { hypothesis_body<false>(a); }
+
 // a9 entry for explicit 8-point sets: p1s/p2s [n_sets][8][3]
 __global__ void __launch_bounds__(HYP_THREADS)
-fundamental_sets_kernel(const double *p1s, const double *p2s, int n_sets, double *pts6, double *F_out)
+fundamental_sets_kernel(const double *p1s, const double *p2s, int n_sets, double *pts6, double *F_out, int solver)
 {
     const int h = blockIdx.x * HYP_THREADS + threadIdx.x;
     if (h >= n_sets) return;
@@ -167,7 +216,8 @@ fundamental_sets_kernel(const double *p1s, const double *p2s, int n_sets, double
         }
     const uint32_t idx[8] = {0, 1, 2, 3, 4, 5, 6, 7};
     double F[9];
-    eight_point(blk, idx, F);
+    if (solver == MVS_SOLVER_REFERENCE) eight_point_reference(blk, idx, F);
+    else eight_point(blk, idx, F);
 #pragma unroll
     for (int i = 0; i < 9; ++i) F_out[(size_t)h * 9 + i] = F[i];
 }
@@ -182,7 +232,7 @@ fundamental_sets_kernel(const double *p1s, const double *p2s, int n_sets, double
 constexpr int SC_THREADS = 128;
 constexpr int SC_TILE = 512;
 
-template <bool UNIT_Z, int MODE>
+template <bool UNIT_Z, int MODE, bool LIT>
 __global__ void __launch_bounds__(SC_THREADS)
 score_kernel(ScoreArgs a)
 {
@@ -222,12 +272,12 @@ score_kernel(ScoreArgs a)
         if (UNIT_Z) {
             const double2 u = *reinterpret_cast<const double2 *>(sp + 4 * i);
             const double2 v = *reinterpret_cast<const double2 *>(sp + 4 * i + 2);
-            in = point_residual<true, MODE, kRes>(u.x, u.y, 0.0, v.x, v.y, 0.0, F, zc, thr, r);
+            in = point_residual<true, MODE, kRes, LIT>(u.x, u.y, 0.0, v.x, v.y, 0.0, F, zc, thr, r);
         } else {
             const double2 u = *reinterpret_cast<const double2 *>(sp + 6 * i);
             const double2 v = *reinterpret_cast<const double2 *>(sp + 6 * i + 2);
             const double2 w = *reinterpret_cast<const double2 *>(sp + 6 * i + 4);
-            in = point_residual<false, MODE, kRes>(u.x, u.y, v.x, v.y, w.x, w.y, F, zc, thr, r);
+            in = point_residual<false, MODE, kRes, LIT>(u.x, u.y, v.x, v.y, w.x, w.y, F, zc, thr, r);
         }
         c += in ? 1u : 0u;
         if (kRes && in) res += r;
@@ -251,10 +301,10 @@ __device__ __forceinline__ bool better(const Best &x, const Best &y)
 }
 
 // find_essential_matrix own branch (sfm-solve.cpp:73-87)
-static __device__ __noinline__ void project_essential(const double F[9], double E[9])
+static __device__ __noinline__ void project_essential(const double F[9], double E[9], bool ref)
 {
     double U[9], w[3], Vt[9];
-    svd3(F, U, w, Vt);
+    if (ref) cv_svd3(F, U, w, Vt); else svd3(F, U, w, Vt);
     const double v = sqrt(w[0] * w[1]);
 #pragma unroll
     for (int i = 0; i < 3; ++i)
@@ -264,10 +314,10 @@ static __device__ __noinline__ void project_essential(const double F[9], double 
 }
 
 // decompose_essential_matrix (sfm-solve.cpp:97-127)
-static __device__ __noinline__ void decompose_essential(const double E[9], double Ra[9], double Rb[9], double t[3])
+static __device__ __noinline__ void decompose_essential(const double E[9], double Ra[9], double Rb[9], double t[3], bool ref)
 {
     double U[9], w[3], Vt[9], V[9];
-    svd3(E, U, w, Vt);
+    if (ref) cv_svd3(E, U, w, Vt); else svd3(E, U, w, Vt);
     mat3_transpose(Vt, V);
     if (det3(U) < 0) {
 #pragma unroll
@@ -291,7 +341,7 @@ static __device__ __noinline__ void decompose_essential(const double E[9], doubl
     t[0] = -S12; t[1] = S02; t[2] = -S01;
 }
 
-template <bool UNIT_Z, int MODE>
+template <bool UNIT_Z, int MODE, bool LIT>
 __global__ void __launch_bounds__(SEL_THREADS)
 select_kernel(SelectArgs a)
 {
@@ -368,7 +418,7 @@ select_kernel(SelectArgs a)
             for (int i = sub; i < n; i += L) {
                 const double *p = pts + (size_t)i * 6;
                 double r;
-                if (point_residual<UNIT_Z, MODE>(p[0], p[1], p[2], p[3], p[4], p[5], F, zc, a.max_error_sq, r)) res += r;
+                if (point_residual<UNIT_Z, MODE, true, LIT>(p[0], p[1], p[2], p[3], p[4], p[5], F, zc, a.max_error_sq, r)) res += r;
             }
             for (int off = L >> 1; off > 0; off >>= 1) res += __shfl_xor_sync(__activemask(), res, off);
             Best x; x.cnt = cmax; x.res = res; x.h = h;
@@ -404,13 +454,13 @@ select_kernel(SelectArgs a)
         if (b.cnt == 0) status = MVS_E_NO_MODEL;
         if (status == MVS_OK && a.decompose) {
             double E[9];
-            project_essential(F, E);
+            project_essential(F, E, LIT);
 #pragma unroll
             for (int i = 0; i < 9; ++i) st->E[i] = E[i];
             if ((int)b.cnt < a.min_inliers) status = MVS_E_TOO_FEW_INLIERS;
             else {
                 double Ra[9], Rb[9], t[3];
-                decompose_essential(E, Ra, Rb, t);
+                decompose_essential(E, Ra, Rb, t, LIT);
 #pragma unroll
                 for (int i = 0; i < 9; ++i) { st->Rc[0][i] = Ra[i]; st->Rc[1][i] = Rb[i]; }
                 st->tc[0] = t[0]; st->tc[1] = t[1]; st->tc[2] = t[2];
@@ -429,47 +479,92 @@ select_kernel(SelectArgs a)
     for (int i = threadIdx.x; i < n; i += SEL_THREADS) {
         const double *p = pts + (size_t)i * 6;
         double r;
-        mask[i] = point_residual<UNIT_Z, MODE, false>(p[0], p[1], p[2], p[3], p[4], p[5], F, zc, a.max_error_sq, r) ? 1 : 0;
+        mask[i] = point_residual<UNIT_Z, MODE, false, LIT>(p[0], p[1], p[2], p[3], p[4], p[5], F, zc, a.max_error_sq, r) ? 1 : 0;
     }
+}
+
+// SVD<M> (source/math/svd.hpp:13-73) for a batch of N x N matrices, one thread per matrix.
+template <int N>
+__global__ void __launch_bounds__(64)
+svd_batch_kernel(const double *A, int count, int solver, double *U, double *w, double *Vt)
+{
+    const int i = blockIdx.x * 64 + threadIdx.x;
+    if (i >= count) return;
+    double Ul[N * N], wl[N], Vl[N * N];
+    if (N == 3 && solver == MVS_SOLVER_FAST) svd3(A + (size_t)i * 9, Ul, wl, Vl);
+    else cv_svd_full<N>(A + (size_t)i * N * N, Ul, wl, Vl);
+    for (int k = 0; k < N * N; ++k) { U[(size_t)i * N * N + k] = Ul[k]; Vt[(size_t)i * N * N + k] = Vl[k]; }
+    for (int k = 0; k < N; ++k) w[(size_t)i * N + k] = wl[k];
+}
+
+bool launch_svd_batch(int n, const double *A, int count, int solver, double *U, double *w, double *Vt, cudaStream_t s)
+{
+    const int blocks = (count + 63) / 64;
+    if (n == 3) svd_batch_kernel<3><<<blocks, 64, 0, s>>>(A, count, solver, U, w, Vt);
+    else if (n == 4 && solver == MVS_SOLVER_REFERENCE) svd_batch_kernel<4><<<blocks, 64, 0, s>>>(A, count, solver, U, w, Vt);
+    else if (n == 9 && solver == MVS_SOLVER_REFERENCE) svd_batch_kernel<9><<<blocks, 64, 0, s>>>(A, count, solver, U, w, Vt);
+    else return false;
+    return true;
 }
 
 // ------------------------------------------------------------------------------------------ launchers
 void launch_hypotheses(const HypArgs &a, int n_pairs, cudaStream_t s)
 {
-    dim3 grid((a.H + HYP_THREADS - 1) / HYP_THREADS, n_pairs);
-    hypotheses_kernel<<<grid, HYP_THREADS, 0, s>>>(a);
+    HypArgs b = a;
+    b.n_pairs = n_pairs;
+    const long long total = (long long)n_pairs * a.H;
+    if (a.solver == MVS_SOLVER_REFERENCE)
+        hypotheses_reference_kernel<<<(unsigned)((total + HYP_REF_THREADS - 1) / HYP_REF_THREADS), HYP_REF_THREADS, 0, s>>>(b);
+    else
+        hypotheses_kernel<<<(unsigned)((total + HYP_THREADS - 1) / HYP_THREADS), HYP_THREADS, 0, s>>>(b);
 }
 
-void launch_fundamental_sets(const double *p1s, const double *p2s, int n_sets, double *F_out, cudaStream_t s)
+void launch_fundamental_sets(const double *p1s, const double *p2s, int n_sets, double *F_out, int solver, cudaStream_t s)
 {
     // scratch for the interleaved [n_sets][8][6] view lives right behind F_out's device buffer: the
     // caller passes F_out with room for n_sets*9 + n_sets*48 doubles
     fundamental_sets_kernel<<<(n_sets + HYP_THREADS - 1) / HYP_THREADS, HYP_THREADS, 0, s>>>(
-        p1s, p2s, n_sets, F_out + (size_t)n_sets * 9, F_out);
+        p1s, p2s, n_sets, F_out + (size_t)n_sets * 9, F_out, solver);
 }
 
 int score_tiles(int max_points) { return max_points > 0 ? (max_points + SC_TILE - 1) / SC_TILE : 1; }
 
+template <bool UNIT_Z, int MODE>
+static void launch_score_t(const ScoreArgs &a, bool lit, dim3 grid, cudaStream_t s)
+{
+    if (lit) score_kernel<UNIT_Z, MODE, true><<<grid, SC_THREADS, 0, s>>>(a);
+    else score_kernel<UNIT_Z, MODE, false><<<grid, SC_THREADS, 0, s>>>(a);
+}
+
 void launch_score(const ScoreArgs &a, int mode, bool unit_z, int n_pairs, cudaStream_t s)
 {
     dim3 grid((a.H + SC_THREADS - 1) / SC_THREADS, a.tiles, n_pairs);
+    const bool lit = a.solver == MVS_SOLVER_REFERENCE;
     if (unit_z) {
-        if (mode == MVS_SCORE_ALGEBRAIC) score_kernel<true, MVS_SCORE_ALGEBRAIC><<<grid, SC_THREADS, 0, s>>>(a);
-        else score_kernel<true, MVS_SCORE_SAMPSON><<<grid, SC_THREADS, 0, s>>>(a);
+        if (mode == MVS_SCORE_ALGEBRAIC) launch_score_t<true, MVS_SCORE_ALGEBRAIC>(a, lit, grid, s);
+        else launch_score_t<true, MVS_SCORE_SAMPSON>(a, lit, grid, s);
     } else {
-        if (mode == MVS_SCORE_ALGEBRAIC) score_kernel<false, MVS_SCORE_ALGEBRAIC><<<grid, SC_THREADS, 0, s>>>(a);
-        else score_kernel<false, MVS_SCORE_SAMPSON><<<grid, SC_THREADS, 0, s>>>(a);
+        if (mode == MVS_SCORE_ALGEBRAIC) launch_score_t<false, MVS_SCORE_ALGEBRAIC>(a, lit, grid, s);
+        else launch_score_t<false, MVS_SCORE_SAMPSON>(a, lit, grid, s);
     }
+}
+
+template <bool UNIT_Z, int MODE>
+static void launch_select_t(const SelectArgs &a, bool lit, int n_pairs, cudaStream_t s)
+{
+    if (lit) select_kernel<UNIT_Z, MODE, true><<<n_pairs, SEL_THREADS, 0, s>>>(a);
+    else select_kernel<UNIT_Z, MODE, false><<<n_pairs, SEL_THREADS, 0, s>>>(a);
 }
 
 void launch_select(const SelectArgs &a, int mode, bool unit_z, int n_pairs, cudaStream_t s)
 {
+    const bool lit = a.solver == MVS_SOLVER_REFERENCE;
     if (unit_z) {
-        if (mode == MVS_SCORE_ALGEBRAIC) select_kernel<true, MVS_SCORE_ALGEBRAIC><<<n_pairs, SEL_THREADS, 0, s>>>(a);
-        else select_kernel<true, MVS_SCORE_SAMPSON><<<n_pairs, SEL_THREADS, 0, s>>>(a);
+        if (mode == MVS_SCORE_ALGEBRAIC) launch_select_t<true, MVS_SCORE_ALGEBRAIC>(a, lit, n_pairs, s);
+        else launch_select_t<true, MVS_SCORE_SAMPSON>(a, lit, n_pairs, s);
     } else {
-        if (mode == MVS_SCORE_ALGEBRAIC) select_kernel<false, MVS_SCORE_ALGEBRAIC><<<n_pairs, SEL_THREADS, 0, s>>>(a);
-        else select_kernel<false, MVS_SCORE_SAMPSON><<<n_pairs, SEL_THREADS, 0, s>>>(a);
+        if (mode == MVS_SCORE_ALGEBRAIC) launch_select_t<false, MVS_SCORE_ALGEBRAIC>(a, lit, n_pairs, s);
+        else launch_select_t<false, MVS_SCORE_SAMPSON>(a, lit, n_pairs, s);
     }
 }
 

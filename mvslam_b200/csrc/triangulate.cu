@@ -16,7 +16,8 @@ namespace mvs {
 
 constexpr int TRI_THREADS = 128;
 
-__global__ void __launch_bounds__(TRI_THREADS, 5)
+template <bool REF>
+__global__ void __launch_bounds__(TRI_THREADS, REF ? 4 : 5)
 triangulate_kernel(TriArgs a)
 {
     __shared__ int s_cnt;
@@ -54,6 +55,16 @@ triangulate_kernel(TriArgs a)
             W[2][j] = x2 * p2j - p0j;
             W[3][j] = y2 * p2j - p1j;
         }
+        double X[4];
+        if (REF) {
+            // X = V.col(3) = vt.row(3) of cv::SVDecomp(A) (svd.hpp:65-67), bit for bit
+            double At[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) At[c][r] = W[r][c];
+            cv_svd_last_vt<4>(At, X);
+        } else {
         jacobi_svd<4>(W, V);
         // X = V column of the smallest singular value (V.col(3), :193-195)
         double best = CUDART_INF;
@@ -66,9 +77,9 @@ triangulate_kernel(TriArgs a)
             s = sqrt(s);
             if (s <= best) { best = s; bj = j; }
         }
-        double X[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) X[k] = bj == 0 ? V[k][0] : (bj == 1 ? V[k][1] : (bj == 2 ? V[k][2] : V[k][3]));
+        }
         if (!(fabs(X[3]) < kTolerance)) {
             const double scale = 1.0 / X[3];
             pt[0] = X[0] * scale; pt[1] = X[1] * scale; pt[2] = X[2] * scale;
@@ -182,7 +193,8 @@ finish_kernel(FinishArgs a)
 void launch_triangulate(const TriArgs &a, int max_points, int n_pairs, cudaStream_t s)
 {
     dim3 grid(max_points > 0 ? (max_points + TRI_THREADS - 1) / TRI_THREADS : 1, a.n_cand, n_pairs);
-    triangulate_kernel<<<grid, TRI_THREADS, 0, s>>>(a);
+    if (a.solver == MVS_SOLVER_REFERENCE) triangulate_kernel<true><<<grid, TRI_THREADS, 0, s>>>(a);
+    else triangulate_kernel<false><<<grid, TRI_THREADS, 0, s>>>(a);
 }
 
 void launch_finish(const FinishArgs &a, int n_pairs, cudaStream_t s)

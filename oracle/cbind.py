@@ -14,6 +14,21 @@ _LIB_PATH = os.path.join(_HERE, "_build", "libmvs_oracle.so")
 
 OK, E_BAD_ARG, E_TOO_FEW_POINTS, E_NO_MODEL, E_TOO_FEW_INLIERS, E_NO_CHEIRALITY = range(6)
 SCORE_ALGEBRAIC, SCORE_SAMPSON = 0, 1
+SOLVER_REFERENCE, SOLVER_FAST = 0, 1
+_SOLVERS = {"reference": SOLVER_REFERENCE, "fast": SOLVER_FAST, SOLVER_REFERENCE: SOLVER_REFERENCE, SOLVER_FAST: SOLVER_FAST}
+# solver used by every geometry wrapper below unless the call names one ("reference" = literal A^T A + cv::SVDecomp
+# restatement, "fast" = Householder/round-robin-Jacobi/fma contract); tests switch it with set_default_solver()
+DEFAULT_SOLVER = "reference"
+
+
+def set_default_solver(name):
+    global DEFAULT_SOLVER
+    assert name in ("reference", "fast")
+    DEFAULT_SOLVER = name
+
+
+def _use(solver):
+    lib().orc_set_solver(_SOLVERS[DEFAULT_SOLVER if solver is None else solver])
 
 MATCH_DTYPE = np.dtype([("query", np.int32), ("train", np.int32), ("distance", np.float32)])
 
@@ -96,7 +111,8 @@ def match_l2(q, t, ratio=0.7, max_dist=-1.0, cross_check=False):
     return out[:n].copy()
 
 
-def svd(A):
+def svd(A, solver=None):
+    _use(solver)
     A = _f64(A); n = A.shape[0]
     U = np.empty((n, n)); w = np.empty(n); Vt = np.empty((n, n))
     sweeps = lib().orc_svd(n, _p(A), _p(U), _p(w), _p(Vt))
@@ -117,7 +133,8 @@ def normalize_points(K, xy):
     lib().orc_normalize_points(_p(_f64(K)), _p(xy), xy.shape[0], _p(out)); return out
 
 
-def find_fundamental_matrix(p1s, p2s):
+def find_fundamental_matrix(p1s, p2s, solver=None):
+    _use(solver)
     F = np.empty((3, 3))
     lib().orc_find_fundamental_matrix(_p(_f64(p1s)), _p(_f64(p2s)), _p(F)); return F
 
@@ -128,7 +145,8 @@ def sample_table(seed, pair_id, n_points, H):
     return out
 
 
-def count_inliers(p1, p2, F, max_error_sq, mode=SCORE_ALGEBRAIC):
+def count_inliers(p1, p2, F, max_error_sq, mode=SCORE_ALGEBRAIC, solver=None):
+    _use(solver)
     p1 = _f64(p1); p2 = _f64(p2); n = p1.shape[0]
     mask = np.empty(n, np.uint8); res = C.c_double()
     cnt = lib().orc_count_inliers(_p(p1), _p(p2), n, _p(_f64(F)), C.c_double(max_error_sq), mode,
@@ -136,7 +154,8 @@ def count_inliers(p1, p2, F, max_error_sq, mode=SCORE_ALGEBRAIC):
     return cnt, res.value, mask
 
 
-def ransac_fundamental(p1, p2, samples, max_error_sq, mode=SCORE_ALGEBRAIC, want_all=False):
+def ransac_fundamental(p1, p2, samples, max_error_sq, mode=SCORE_ALGEBRAIC, want_all=False, solver=None):
+    _use(solver)
     p1 = _f64(p1); p2 = _f64(p2); n = p1.shape[0]
     samples = np.ascontiguousarray(samples, np.uint32); H = samples.shape[0]
     F = np.zeros((3, 3)); mask = np.zeros(max(n, 1), np.uint8)
@@ -152,16 +171,19 @@ def ransac_fundamental(p1, p2, samples, max_error_sq, mode=SCORE_ALGEBRAIC, want
     return out
 
 
-def project_essential(F):
+def project_essential(F, solver=None):
+    _use(solver)
     E = np.empty((3, 3)); lib().orc_project_essential(_p(_f64(F)), _p(E)); return E
 
 
-def decompose_essential(E):
+def decompose_essential(E, solver=None):
+    _use(solver)
     Ra = np.empty((3, 3)); Rb = np.empty((3, 3)); t = np.empty(3)
     lib().orc_decompose_essential(_p(_f64(E)), _p(Ra), _p(Rb), _p(t)); return Ra, Rb, t
 
 
-def triangulate_points(R, t, p1, p2, mask=None):
+def triangulate_points(R, t, p1, p2, mask=None, solver=None):
+    _use(solver)
     p1 = _f64(p1); p2 = _f64(p2); n = p1.shape[0]
     pts = np.empty((max(n, 1), 3)); idx = np.empty(max(n, 1), np.uint64)
     if mask is not None:
@@ -180,7 +202,8 @@ def _result_dict(r):
     return d
 
 
-def sfm_solve(xy1, xy2, K, samples=None, H=1, seed=0, pair_id=0, mode=SCORE_ALGEBRAIC, max_error_sq=0.0):
+def sfm_solve(xy1, xy2, K, samples=None, H=1, seed=0, pair_id=0, mode=SCORE_ALGEBRAIC, max_error_sq=0.0, solver=None):
+    _use(solver)
     xy1 = _f64(xy1); xy2 = _f64(xy2); n = xy1.shape[0]
     if samples is not None:
         samples = np.ascontiguousarray(samples, np.uint32); H = samples.shape[0]
@@ -193,7 +216,8 @@ def sfm_solve(xy1, xy2, K, samples=None, H=1, seed=0, pair_id=0, mode=SCORE_ALGE
     return d
 
 
-def sfm_triangulate(xy1, xy2, K, R1, t1, R2, t2):
+def sfm_triangulate(xy1, xy2, K, R1, t1, R2, t2, solver=None):
+    _use(solver)
     xy1 = _f64(xy1); xy2 = _f64(xy2); n = xy1.shape[0]
     pts = np.empty((max(n, 1), 3)); idx = np.empty(max(n, 1), np.uint64)
     m = lib().orc_sfm_triangulate(_p(xy1), _p(xy2), n, _p(_f64(K)), _p(_f64(R1)), _p(_f64(t1)),
@@ -202,7 +226,8 @@ def sfm_triangulate(xy1, xy2, K, R1, t1, R2, t2):
 
 
 def image_pair(desc1, kp1, desc2, kp2, K, ratio=0.7, max_dist=-1.0, cross_check=False, H=1, seed=0,
-               pair_id=0, mode=SCORE_ALGEBRAIC, max_error_sq=0.0):
+               pair_id=0, mode=SCORE_ALGEBRAIC, max_error_sq=0.0, solver=None):
+    _use(solver)
     desc1 = np.ascontiguousarray(desc1, np.uint8); desc2 = np.ascontiguousarray(desc2, np.uint8)
     kp1 = np.ascontiguousarray(kp1, np.float32); kp2 = np.ascontiguousarray(kp2, np.float32)
     n1, n2 = desc1.shape[0], desc2.shape[0]
@@ -219,7 +244,8 @@ def image_pair(desc1, kp1, desc2, kp2, K, ratio=0.7, max_dist=-1.0, cross_check=
 
 
 def pair_batch(descs, kps, pairs, K, ratio=0.7, max_dist=-1.0, cross_check=False, H=1, seed=0,
-               mode=SCORE_ALGEBRAIC, threads=0, max_error_sq=0.0):
+               mode=SCORE_ALGEBRAIC, threads=0, max_error_sq=0.0, solver=None):
+    _use(solver)
     descs = [np.ascontiguousarray(d, np.uint8) for d in descs]
     kps = [np.ascontiguousarray(k, np.float32) for k in kps]
     nf = len(descs)

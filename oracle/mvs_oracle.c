@@ -237,6 +237,140 @@ static int jacobi_svd_core(int n, double W[SVD_MAX_N][SVD_MAX_N], double V[SVD_M
     return sweep;
 }
 
+
+/* ------------------------------------------------------------------------------------------
+ * Solver mode.  ORC_SOLVER_REFERENCE (default) is the LITERAL restatement: the 8-point null vector is
+ * vt.row(8) of cv::SVDecomp(A^T A) (fundamental-matrix.cpp:104-118), every SVD is OpenCV's own routine
+ * restated bit for bit (orc_cv_svd below), and nothing is fused.  ORC_SOLVER_FAST is the library's
+ * accuracy/throughput mode (Householder null vector of A, round-robin Jacobi, explicit fma contract).
+ * A process-wide switch keeps the many call signatures unchanged; it is read once per entry point.
+ * ------------------------------------------------------------------------------------------ */
+static int g_solver = ORC_SOLVER_REFERENCE;
+void orc_set_solver(int solver) { g_solver = solver; }
+int orc_get_solver(void) { return g_solver; }
+
+/* cv::SVDecomp(A, w, u, vt, MODIFY_A | FULL_UV) for a square n x n double matrix (n <= 9), the only way the
+ * reference calls it (source/math/svd.hpp:65, fundamental-matrix.cpp:115,131).  OpenCV is an un-vendored
+ * dependency ("opencv >= 3.0", README.md:12); for matrices this small it never reaches LAPACK but runs its own
+ * one-sided Hestenes Jacobi (modules/core/src/lapack.cpp, JacobiSVDImpl_): the input is transposed, ROWS i<j of
+ * A^T are rotated in plain cyclic order until |<Ai,Aj>| <= 10*eps*sqrt(|Ai|^2 |Aj|^2), with the rotation from
+ * OpenCV's own scaled hypot; the squared row norms are carried along (W), rows are then sorted by norm
+ * (selection sort, swap with the first maximum), normalised rows of A^T are U^T, and rows with a zero norm are
+ * replaced by a pseudo-random vector (cv::RNG(0x12345678), +-1/m entries) orthogonalised against the others.
+ * Every operation is IEEE +,-,*,/,sqrt in a fixed order and OpenCV's x86-64 baseline build has no FMA, so this
+ * restatement is BIT-IDENTICAL to cv2.SVDecomp of this image (4.13.0): tests/test_oracle_pinning.py checks
+ * w, u and vt for equality on 3x3, 4x4 and 9x9 inputs, rank-deficient ones included, and tests/golden/
+ * cv_svd_golden.npz carries cv2's outputs to the GPU box. */
+static double cv_hypot(double a, double b)
+{
+    a = fabs(a); b = fabs(b);
+    if (a > b) { b /= a; return a * sqrt(1 + b * b); }
+    if (b > 0) { a /= b; return b * sqrt(1 + a * a); }
+    return 0;
+}
+
+int orc_cv_svd(int n, const double *A, double *U, double *w, double *Vt)
+{
+    if (n < 1 || n > SVD_MAX_N) return -1;
+    const int m = n;
+    const double eps = DBL_EPSILON * 10, minval = DBL_MIN;
+    double At[SVD_MAX_N][SVD_MAX_N], V[SVD_MAX_N][SVD_MAX_N], W[SVD_MAX_N];
+    for (int i = 0; i < n; ++i) for (int k = 0; k < m; ++k) At[i][k] = A[k * n + i];   /* transpose(src, temp_a) */
+    for (int i = 0; i < n; ++i) {
+        double sd = 0;
+        for (int k = 0; k < m; ++k) { double t = At[i][k]; sd += t * t; }
+        W[i] = sd;
+        for (int k = 0; k < n; ++k) V[i][k] = 0;
+        V[i][i] = 1;
+    }
+    const int max_iter = m > 30 ? m : 30;
+    int iter;
+    for (iter = 0; iter < max_iter; ++iter) {
+        int changed = 0;
+        for (int i = 0; i < n - 1; ++i)
+            for (int j = i + 1; j < n; ++j) {
+                double *Ai = At[i], *Aj = At[j];
+                double a = W[i], p = 0, b = W[j];
+                for (int k = 0; k < m; ++k) p += Ai[k] * Aj[k];
+                if (fabs(p) <= eps * sqrt(a * b)) continue;
+                p *= 2;
+                double beta = a - b, gamma = cv_hypot(p, beta), c, s;
+                if (beta < 0) {
+                    double delta = (gamma - beta) * 0.5;
+                    s = sqrt(delta / gamma);
+                    c = p / (gamma * s * 2);
+                } else {
+                    c = sqrt((gamma + beta) / (gamma * 2));
+                    s = p / (gamma * c * 2);
+                }
+                a = b = 0;
+                for (int k = 0; k < m; ++k) {
+                    double t0 = c * Ai[k] + s * Aj[k];
+                    double t1 = -s * Ai[k] + c * Aj[k];
+                    Ai[k] = t0; Aj[k] = t1;
+                    a += t0 * t0; b += t1 * t1;
+                }
+                W[i] = a; W[j] = b;
+                changed = 1;
+                double *Vi = V[i], *Vj = V[j];
+                for (int k = 0; k < n; ++k) {
+                    double t0 = c * Vi[k] + s * Vj[k];
+                    double t1 = -s * Vi[k] + c * Vj[k];
+                    Vi[k] = t0; Vj[k] = t1;
+                }
+            }
+        if (!changed) break;
+    }
+    for (int i = 0; i < n; ++i) {
+        double sd = 0;
+        for (int k = 0; k < m; ++k) { double t = At[i][k]; sd += t * t; }
+        W[i] = sqrt(sd);
+    }
+    for (int i = 0; i < n - 1; ++i) {
+        int j = i;
+        for (int k = i + 1; k < n; ++k) if (W[j] < W[k]) j = k;
+        if (i != j) {
+            double t = W[i]; W[i] = W[j]; W[j] = t;
+            for (int k = 0; k < m; ++k) { t = At[i][k]; At[i][k] = At[j][k]; At[j][k] = t; }
+            for (int k = 0; k < n; ++k) { t = V[i][k]; V[i][k] = V[j][k]; V[j][k] = t; }
+        }
+    }
+    for (int i = 0; i < n; ++i) w[i] = W[i];
+    /* left singular vectors: normalised rows of A^T; zero rows are regenerated (cv::RNG multiply-with-carry) */
+    uint64_t rng = 0x12345678;
+    for (int i = 0; i < n; ++i) {
+        double sd = W[i];
+        for (int ii = 0; ii < 100 && sd <= minval; ++ii) {
+            const double val0 = 1. / m;
+            for (int k = 0; k < m; ++k) {
+                rng = (uint64_t)(uint32_t)rng * 4164903690U + (uint32_t)(rng >> 32);
+                At[i][k] = ((uint32_t)rng & 256) != 0 ? val0 : -val0;
+            }
+            for (int it = 0; it < 2; ++it)
+                for (int j = 0; j < i; ++j) {
+                    sd = 0;
+                    for (int k = 0; k < m; ++k) sd += At[i][k] * At[j][k];
+                    double asum = 0;
+                    for (int k = 0; k < m; ++k) {
+                        double t = At[i][k] - sd * At[j][k];
+                        At[i][k] = t;
+                        asum += fabs(t);
+                    }
+                    asum = asum > eps * 100 ? 1 / asum : 0;
+                    for (int k = 0; k < m; ++k) At[i][k] *= asum;
+                }
+            sd = 0;
+            for (int k = 0; k < m; ++k) { double t = At[i][k]; sd += t * t; }
+            sd = sqrt(sd);
+        }
+        double s = sd > minval ? 1 / sd : 0.;
+        for (int k = 0; k < m; ++k) At[i][k] *= s;
+    }
+    if (U) for (int i = 0; i < n; ++i) for (int k = 0; k < n; ++k) U[i * n + k] = At[k][i];   /* transpose(temp_u, u) */
+    if (Vt) for (int i = 0; i < n; ++i) for (int k = 0; k < n; ++k) Vt[i * n + k] = V[i][k];
+    return iter;
+}
+
 static void cross3(const double a[3], const double b[3], double o[3])
 {
     o[0] = a[1] * b[2] - a[2] * b[1];
@@ -247,6 +381,7 @@ static void cross3(const double a[3], const double b[3], double o[3])
 int orc_svd(int n, const double *A, double *U, double *w, double *Vt)
 {
     if (n < 1 || n > SVD_MAX_N) return -1;
+    if (g_solver == ORC_SOLVER_REFERENCE) return orc_cv_svd(n, A, U, w, Vt);
     double W[SVD_MAX_N][SVD_MAX_N], V[SVD_MAX_N][SVD_MAX_N];
     for (int i = 0; i < n; ++i)
         for (int j = 0; j < n; ++j) W[i][j] = A[i * n + j];
@@ -469,7 +604,18 @@ static void find_fundamental_matrix_8point(double n1[8][3], double n2[8][3], dou
         A[i][6] = x1; A[i][7] = y1; A[i][8] = 1.0;
     }
     double Fp[9];
-    null_vector_8x9(A, Fp);
+    if (g_solver == ORC_SOLVER_REFERENCE) {
+        /* A^T A accumulated element by element over the 8 rows (:104-111), f = vt.row(8) (:114-118) */
+        double AtA[81], w9[9], Vt9[81];
+        for (int i = 0; i < 9; ++i)
+            for (int j = 0; j < 9; ++j) {
+                double acc = 0;
+                for (int k = 0; k < 8; ++k) acc += A[k][i] * A[k][j];
+                AtA[i * 9 + j] = acc;
+            }
+        orc_cv_svd(9, AtA, NULL, w9, Vt9);
+        for (int i = 0; i < 9; ++i) Fp[i] = Vt9[72 + i];
+    } else null_vector_8x9(A, Fp);
     /* singular constraint (:128-136): F = u * diag(w0,w1,0) * vt */
     double U[9], w[3], Vt[9];
     orc_svd(3, Fp, U, w, Vt);
@@ -529,8 +675,34 @@ void orc_sample_table(uint64_t seed, uint64_t pair_id, uint32_t n_points, int H,
  * cv::findEssentialMat's RANSAC (default-build branch, sfm-solve.cpp:42-63; north-star mode). */
 /* ALGEBRAIC: e = |r| < thr.  SAMPSON: r^2 / den < thr, decided as r^2 < thr * den (den > 0) so that the
  * division is only needed for the residual of actual inliers.  Explicit fma() = shared contract with the GPU. */
+static inline int point_residual_fast(const double *a, const double *b, const double F[9], int mode, double thr, double *res);
+
+/* REFERENCE solver: r = (p2^T F) p1 with every product and sum rounded separately, left to right
+ * (Eigen coefficient-based products of the reference build: no FMA, EIGEN_DONT_VECTORIZE, SConstruct:70,86). */
 static inline int point_residual(const double *a /*p1*/, const double *b /*p2*/, const double F[9], int mode,
                                  double thr, double *res)
+{
+    if (g_solver != ORC_SOLVER_REFERENCE) return point_residual_fast(a, b, F, mode, thr, res);
+    double v0 = (b[0] * F[0] + b[1] * F[3]) + b[2] * F[6];
+    double v1 = (b[0] * F[1] + b[1] * F[4]) + b[2] * F[7];
+    double v2 = (b[0] * F[2] + b[1] * F[5]) + b[2] * F[8];
+    double r = (v0 * a[0] + v1 * a[1]) + v2 * a[2];
+    if (mode == ORC_SCORE_ALGEBRAIC) {
+        double e = r < 0 ? -r : r;
+        *res = e;
+        return e < thr;
+    }
+    double l0 = (F[0] * a[0] + F[1] * a[1]) + F[2] * a[2];
+    double l1 = (F[3] * a[0] + F[4] * a[1]) + F[5] * a[2];
+    double den = (l0 * l0 + l1 * l1) + (v0 * v0 + v1 * v1);
+    double r2 = r * r;
+    if (!(r2 < thr * den)) return 0;
+    *res = r2 / den;
+    return 1;
+}
+
+static inline int point_residual_fast(const double *a /*p1*/, const double *b /*p2*/, const double F[9], int mode,
+                                      double thr, double *res)
 {
     double v0 = fma(b[0], F[0], fma(b[1], F[3], b[2] * F[6]));
     double v1 = fma(b[0], F[1], fma(b[1], F[4], b[2] * F[7]));

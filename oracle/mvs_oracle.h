@@ -40,6 +40,11 @@ enum {
 };
 
 enum { ORC_SCORE_ALGEBRAIC = 0, ORC_SCORE_SAMPSON = 1 };
+/* REFERENCE: literal A^T A + cv::SVDecomp route, unfused arithmetic (what the reference executes).
+ * FAST: Householder null vector + round-robin Jacobi + explicit fma (the library's throughput mode). */
+enum { ORC_SOLVER_REFERENCE = 0, ORC_SOLVER_FAST = 1 };
+void orc_set_solver(int solver);   /* process-wide; default ORC_SOLVER_REFERENCE */
+int  orc_get_solver(void);
 
 typedef struct {
     int32_t query;   /* cv::DMatch::queryIdx  (index into frame 2 / pair frame)  */
@@ -63,6 +68,8 @@ int orc_match_l2(const float *q, int nq, const float *t, int nt, int dim,
 /* ---- small dense algebra (source/math/svd.hpp:59-72, cv::SVDecomp restated as one-sided Jacobi) ---- */
 /* A is n x n row-major. Outputs: U n x n row-major (may be NULL), w[n] descending, Vt n x n row-major. */
 int orc_svd(int n, const double *A, double *U, double *w, double *Vt);
+/* cv::SVDecomp(MODIFY_A|FULL_UV) restated bit for bit (OpenCV's own Hestenes Jacobi for small matrices). */
+int orc_cv_svd(int n, const double *A, double *U, double *w, double *Vt);
 
 /* ---- lie group pieces on the path (source/math/lie-group.hpp:84-96,75-79,203-234) ---- */
 void orc_so3_rectify(const double R[9], double out[9]);

@@ -5,9 +5,14 @@ TEST INFRASTRUCTURE ONLY (never imported by the product package).
 It calls the *same third-party routines* the reference calls — cv2.BFMatcher.knnMatch /
 cv2.batchDistance (source/vision/visual-feature.cpp:59-62) and cv2.SVDecomp
 (source/math/svd.hpp:65, source/vision/fundamental-matrix.cpp:115,131) — and restates the
-reference's Eigen arithmetic around them in numpy float64.  Its job is to pin Oracle B
-(oracle/mvs_oracle.c, the dependency-free C restatement with an own Jacobi SVD that the CUDA
-kernels are checked against) and to generate the golden fixtures in tests/golden/.
+reference's Eigen arithmetic around them.  Everything UPSTREAM of an SVD (K^-1, Hartley
+normalisation, the rows of A, A^T A, the residuals) is written in the reference's own loop order
+with one rounding per operation (numpy elementwise ufuncs / Python floats; never BLAS, whose FMA
+kernels round differently): on an ill-conditioned 8-point sample a single different last bit in
+A^T A moves the null vector by ~eps*cond(A)^2 (4e-5 on Tsukuba pair 4-5), so only an exact
+restatement pins the reference there.  Its job is to pin Oracle B (oracle/mvs_oracle.c, whose
+REFERENCE solver restates cv::SVDecomp itself bit for bit and is what the CUDA kernels are checked
+against) and to generate the golden fixtures in tests/golden/.
 File:line citations are relative to /root/reference.
 """
 import numpy as np
@@ -59,27 +64,52 @@ def match_visual_features(desc1, desc2, max_dist=-1.0, norm="hamming"):
 # ---------------------------------------------------------------- algebra
 def svd(A):
     """SVD<> wrapper (source/math/svd.hpp:59-72): returns U, w (descending), V (= vt^T)."""
-    w, u, vt = cv2.SVDecomp(np.ascontiguousarray(A, np.float64), flags=cv2.SVD_FULL_UV)
+    w, u, vt = cv2.SVDecomp(np.array(A, np.float64, order="C"), flags=cv2.SVD_MODIFY_A | cv2.SVD_FULL_UV)
     return u, w.ravel(), vt.T
+
+
+def mat3_mul(A, B):
+    """Eigen fixed-size coefficient-based product: sum over k left to right, no FMA (SConstruct:70,86)."""
+    A = np.asarray(A, np.float64); B = np.asarray(B, np.float64)
+    return (A[:, 0:1] * B[0] + A[:, 1:2] * B[1]) + A[:, 2:3] * B[2]
+
+
+def mat3_vec(A, v):
+    A = np.asarray(A, np.float64)
+    return (A[:, 0] * v[0] + A[:, 1] * v[1]) + A[:, 2] * v[2]
+
+
+def inverse3(K):
+    """Eigen's fixed 3x3 inverse (camera.cpp:14-18 K_.inverse()): cofactor^T * (1/det)."""
+    K = [[float(x) for x in r] for r in np.asarray(K, np.float64)]
+    c00 = K[1][1] * K[2][2] - K[1][2] * K[2][1]; c01 = K[1][2] * K[2][0] - K[1][0] * K[2][2]
+    c02 = K[1][0] * K[2][1] - K[1][1] * K[2][0]; c10 = K[0][2] * K[2][1] - K[0][1] * K[2][2]
+    c11 = K[0][0] * K[2][2] - K[0][2] * K[2][0]; c12 = K[0][1] * K[2][0] - K[0][0] * K[2][1]
+    c20 = K[0][1] * K[1][2] - K[0][2] * K[1][1]; c21 = K[0][2] * K[1][0] - K[0][0] * K[1][2]
+    c22 = K[0][0] * K[1][1] - K[0][1] * K[1][0]
+    idet = 1.0 / (K[0][0] * c00 + K[0][1] * c01 + K[0][2] * c02)
+    return np.array([[c00 * idet, c10 * idet, c20 * idet], [c01 * idet, c11 * idet, c21 * idet],
+                     [c02 * idet, c12 * idet, c22 * idet]])
 
 
 def so3_rectify(R):
     """SO3::rectify (source/math/lie-group.hpp:84-96); row 1 is NOT normalised."""
-    u0 = R[0] / np.linalg.norm(R[0])
-    u1 = R[1] - np.dot(R[1], u0) * u0
+    R = np.asarray(R, np.float64)
+    u0 = R[0] / np.sqrt(R[0, 0] * R[0, 0] + R[0, 1] * R[0, 1] + R[0, 2] * R[0, 2])
+    u1 = R[1] - (R[1, 0] * u0[0] + R[1, 1] * u0[1] + R[1, 2] * u0[2]) * u0
     u2 = np.cross(u0, u1)
     return np.stack([u0, u1, u2])
 
 
 def se3_inverse(R, t):
     """SE3::inverse (lie-group.hpp:203-207): RT = SO3(R^T) (rectified again), t' = -(RT t)."""
-    RT = so3_rectify(R.T)
-    return RT, -(RT @ t)
+    RT = so3_rectify(np.asarray(R).T)
+    return RT, -mat3_vec(RT, t)
 
 
 def se3_compose(Ra, ta, Rb, tb):
     """SE3::operator* (lie-group.hpp:220-225)."""
-    return so3_rectify(Ra @ Rb), Ra @ tb + ta
+    return so3_rectify(mat3_mul(Ra, Rb)), mat3_vec(Ra, tb) + ta
 
 
 def rodrigues(v):
@@ -125,9 +155,9 @@ def se3_ln(R, t):
 # ---------------------------------------------------------------- camera
 def normalize_points(K, xy):
     """PinholeCamera::normalize_points (source/vision/camera.cpp:55-79): K^-1 (u, v, 1)."""
-    Kinv = np.linalg.inv(K)
-    h = np.concatenate([np.asarray(xy, np.float64), np.ones((len(xy), 1))], axis=1)
-    return h @ Kinv.T
+    Kinv = inverse3(K)
+    xy = np.asarray(xy, np.float64).reshape(-1, 2)
+    return np.stack([(Kinv[r, 0] * xy[:, 0] + Kinv[r, 1] * xy[:, 1]) + Kinv[r, 2] * 1.0 for r in range(3)], axis=1)
 
 
 def project_points(K, R_w2c, t_w2c, pts):
@@ -140,9 +170,18 @@ def project_points(K, R_w2c, t_w2c, pts):
 # ---------------------------------------------------------------- 8-point
 def find_normalization_transform(p):
     """source/vision/fundamental-matrix.cpp:18-54 (mean distance -> sqrt(2))."""
-    mean = p.mean(axis=0)
+    p = np.asarray(p, np.float64)
+    inv = 1.0 / len(p)
+    mean = np.zeros(3)
+    for q in p:                       # :29-35, sequential accumulation
+        mean = mean + q
+    mean = mean * inv
     c = p - mean
-    scale = np.sqrt(2.0) / np.linalg.norm(c, axis=1).mean()
+    scale = 0.0
+    for q in c:                       # :39-43, Eigen norm() = sqrt(x^2 + y^2 + z^2)
+        scale = scale + float(np.sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]))
+    scale = scale * inv
+    scale = float(np.sqrt(2.0)) / scale
     T = np.array([[scale, 0, -mean[0] * scale], [0, scale, -mean[1] * scale], [0, 0, 1]])
     return c * scale, T
 
@@ -151,36 +190,43 @@ def find_fundamental_matrix_8point(n1, n2):
     """source/vision/fundamental-matrix.cpp:56-140"""
     x1, y1, x2, y2 = n1[:, 0], n1[:, 1], n2[:, 0], n2[:, 1]
     A = np.stack([x2 * x1, x2 * y1, x2, y2 * x1, y2 * y1, y2, x1, y1, np.ones(8)], axis=1)
-    AtA = A.T @ A
-    _, _, vt = cv2.SVDecomp(AtA, flags=cv2.SVD_FULL_UV)
-    F = vt[8].reshape(3, 3)
-    w, u, vt3 = cv2.SVDecomp(F, flags=cv2.SVD_FULL_UV)
+    AtA = np.zeros((9, 9))
+    for k in range(8):                # :104-111: AT_A(i,j) += A(k,i)*A(k,j), k outermost per element = same order
+        AtA = AtA + np.outer(A[k], A[k])
+    _, _, vt = cv2.SVDecomp(AtA, flags=cv2.SVD_MODIFY_A | cv2.SVD_FULL_UV)
+    F = vt[8].reshape(3, 3).copy()
+    w, u, vt3 = cv2.SVDecomp(F.copy(), flags=cv2.SVD_MODIFY_A | cv2.SVD_FULL_UV)
     w = w.ravel().copy(); w[2] = 0
-    return u @ np.diag(w) @ vt3
+    # u * diag(w) * vt (:134) through cv::gemm's small-matrix path: products summed left to right
+    return mat3_mul(mat3_mul(u, np.diag(w)), vt3)
 
 
 def find_fundamental_matrix(p1s, p2s):
     """source/vision/fundamental-matrix.cpp:204-267"""
     n1, T1 = find_normalization_transform(np.asarray(p1s, np.float64))
     n2, T2 = find_normalization_transform(np.asarray(p2s, np.float64))
-    return T2.T @ find_fundamental_matrix_8point(n1, n2) @ T1
+    return mat3_mul(mat3_mul(T2.T, find_fundamental_matrix_8point(n1, n2)), T1)
 
 
 # ---------------------------------------------------------------- RANSAC
 def residuals(p1, p2, F, mode="algebraic"):
-    v = p2 @ F                       # rows: p2^T F
-    r = np.einsum("ij,ij->i", v, p1)
+    p1 = np.asarray(p1, np.float64); p2 = np.asarray(p2, np.float64); F = np.asarray(F, np.float64)
+    v = (p2[:, 0:1] * F[0] + p2[:, 1:2] * F[1]) + p2[:, 2:3] * F[2]      # rows: p2^T F, left to right
+    r = (v[:, 0] * p1[:, 0] + v[:, 1] * p1[:, 1]) + v[:, 2] * p1[:, 2]
     if mode == "algebraic":
         return np.abs(r)             # estimator-RANSAC.cpp:114-116
-    l = p1 @ F.T                     # rows: F p1
-    return r * r / (l[:, 0] ** 2 + l[:, 1] ** 2 + v[:, 0] ** 2 + v[:, 1] ** 2)
+    l = (p1[:, 0:1] * F[:, 0] + p1[:, 1:2] * F[:, 1]) + p1[:, 2:3] * F[:, 2]   # rows: F p1
+    return r * r / ((l[:, 0] * l[:, 0] + l[:, 1] * l[:, 1]) + (v[:, 0] * v[:, 0] + v[:, 1] * v[:, 1]))
 
 
 def count_inliers(p1, p2, F, max_error_sq, mode="algebraic"):
     """source/vision/estimator-RANSAC.cpp:100-129"""
     r = residuals(p1, p2, F, mode)
     mask = r < max_error_sq
-    return int(mask.sum()), float(r[mask].sum()), mask.astype(np.uint8)
+    res = 0.0
+    for x in r[mask]:                # residual += r in point order (:120)
+        res += float(x)
+    return int(mask.sum()), res, mask.astype(np.uint8)
 
 
 def ransac_fundamental(p1, p2, samples, max_error_sq, mode="algebraic"):
@@ -201,21 +247,26 @@ def project_essential(F):
     """source/vision/sfm-solve.cpp:73-87"""
     U, s, V = svd(F)
     v = np.sqrt(s[0] * s[1])
-    return U @ np.diag([v, v, 0.0]) @ V.T
+    return mat3_mul(mat3_mul(U, np.diag([v, v, 0.0])), V.T)
+
+
+def det3(M):
+    return (M[0, 0] * (M[1, 1] * M[2, 2] - M[1, 2] * M[2, 1]) - M[0, 1] * (M[1, 0] * M[2, 2] - M[1, 2] * M[2, 0])
+            + M[0, 2] * (M[1, 0] * M[2, 1] - M[1, 1] * M[2, 0]))
 
 
 def decompose_essential(E):
     """source/vision/sfm-solve.cpp:97-127"""
     U, _, V = svd(E)
-    if np.linalg.det(U) < 0:
+    if det3(U) < 0:
         U = -U
-    if np.linalg.det(V) < 0:
+    if det3(V) < 0:
         V = -V
     W = np.array([[0, -1, 0], [1, 0, 0], [0, 0, 1]], float)
     Z = np.array([[0, 1, 0], [-1, 0, 0], [0, 0, 0]], float)
-    Ra = U @ W @ V.T
-    Rb = U @ W.T @ V.T
-    S = U @ Z @ U.T
+    Ra = mat3_mul(mat3_mul(U, W), V.T)
+    Rb = mat3_mul(mat3_mul(U, W.T), V.T)
+    S = mat3_mul(mat3_mul(U, Z), U.T)
     return Ra, Rb, np.array([-S[1, 2], S[0, 2], -S[0, 1]])
 
 
@@ -237,7 +288,7 @@ def triangulate_points(R, t, p1, p2, mask=None):
         pt = X[:3] * (1.0 / X[3])
         if pt[2] < TOLERANCE:
             continue
-        if (R @ pt + t)[2] < TOLERANCE:
+        if ((R[2, 0] * pt[0] + R[2, 1] * pt[1]) + R[2, 2] * pt[2]) + t[2] < TOLERANCE:
             continue
         pts.append(pt); idx.append(i)
     return np.array(pts).reshape(-1, 3), np.array(idx, np.uint64)

@@ -30,3 +30,15 @@ def tsukuba_golden():
 def synthetic_golden():
     import numpy as np
     return np.load(os.path.join(GOLDEN, "synthetic_golden.npz"))
+
+
+@pytest.fixture(params=["reference", "fast"])
+def solver(request):
+    """Runs a geometry test once per solver (include/mvslam_b200.h MVS_SOLVER_*): sets the default of both the
+    library binding and the oracle binding, so GPU and oracle are always compared in the same mode."""
+    from mvslam_b200 import capi
+    from oracle import cbind
+    old = (capi.DEFAULT_SOLVER, cbind.DEFAULT_SOLVER)
+    capi.set_default_solver(request.param); cbind.set_default_solver(request.param)
+    yield request.param
+    capi.set_default_solver(old[0]); cbind.set_default_solver(old[1])

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 20
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/mvslam_b200.h but not exported"
-    assert L.mvs_abi_version() == 2
+    assert L.mvs_abi_version() == 3
 
 
 def test_struct_layouts():

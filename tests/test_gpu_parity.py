@@ -184,7 +184,7 @@ def test_match_full_size_properties(ctx):
 
 
 # ------------------------------------------------------------------------------------------ 8-point / RANSAC
-def test_find_fundamental_matrix_vs_oracle(ctx):
+def test_find_fundamental_matrix_vs_oracle(ctx, solver):
     K, x1, x2 = general_scene(400, 3, noise=0.3)
     p1 = orc.normalize_points(K, x1); p2 = orc.normalize_points(K, x2)
     tab = orc.sample_table(9, 1, 400, 200)
@@ -194,14 +194,14 @@ def test_find_fundamental_matrix_vs_oracle(ctx):
         Fo = orc.find_fundamental_matrix(p1[tab[h]], p2[tab[h]])
         assert same_up_to_scale(Fg[h], Fo, 1e-9)
         exact += np.array_equal(Fg[h], Fo)
-    print(f"bit-identical F: {exact}/200")
-    assert exact >= 100      # same operation order on both sides: most hypotheses agree to the last bit
+    print(f"bit-identical F ({solver}): {exact}/200")
+    assert exact == 200      # same IEEE operations in the same order on both sides: every hypothesis, every bit
 
 
 @pytest.mark.parametrize("mode", [mvs.SCORE_ALGEBRAIC, mvs.SCORE_SAMPSON])
 @pytest.mark.parametrize("n,H,noise,outl,thr", [(300, 64, 0.0, 0.3, 1e-7), (1000, 513, 0.3, 0.3, 1e-3),
                                                 (1500, 300, 0.5, 0.5, 1e-6), (8, 1, 0.0, 0.0, 1e-7)])
-def test_ransac_identical_inlier_sets(ctx, mode, n, H, noise, outl, thr):
+def test_ransac_identical_inlier_sets(ctx, solver, mode, n, H, noise, outl, thr):
     K, x1, x2 = general_scene(n, n + H, noise, outl)
     p1 = orc.normalize_points(K, x1); p2 = orc.normalize_points(K, x2)
     tab = orc.sample_table(4, 2, n, H)
@@ -217,7 +217,7 @@ def test_ransac_identical_inlier_sets(ctx, mode, n, H, noise, outl, thr):
     assert g["count"] == o["count"]
 
 
-def test_ransac_general_z_points(ctx):
+def test_ransac_general_z_points(ctx, solver):
     """FundamentalMatrixEstimatorRANSAC::compute takes arbitrary homogeneous 3-vectors."""
     K, x1, x2 = general_scene(200, 77, 0.2, 0.2)
     p1 = orc.normalize_points(K, x1); p2 = orc.normalize_points(K, x2)
@@ -230,7 +230,7 @@ def test_ransac_general_z_points(ctx):
     assert np.array_equal(g["mask"], o["mask"])
 
 
-def test_ransac_seeded_table_on_device_equals_host_table(ctx):
+def test_ransac_seeded_table_on_device_equals_host_table(ctx, solver):
     K, x1, x2 = general_scene(500, 5, 0.3, 0.3)
     p1 = orc.normalize_points(K, x1); p2 = orc.normalize_points(K, x2)
     a = ctx.ransac_fundamental(p1, p2, samples=None, H=128, seed=99, max_error_sq=1e-3, want_all=True)
@@ -239,9 +239,15 @@ def test_ransac_seeded_table_on_device_equals_host_table(ctx):
 
 
 # ------------------------------------------------------------------------------------------ sfm_solve / triangulate
-def check_solution(g, o, pose_tol=1e-9, strict=True):
+def check_solution(g, o, pose_tol=1e-9, strict=True, exact=False):
     assert g["status"] == o["status"]
     if o["status"] != orc.OK:
+        return
+    if exact:   # REFERENCE solver: the device executes the oracle's IEEE operations one for one
+        for k in ("F", "E", "mask", "R1to2", "t1to2", "R2in1", "t2in1", "points", "indexes"):
+            assert np.array_equal(g[k], o[k]), k
+        assert g["n_inliers"] == o["n_inliers"] and g["best_hypothesis"] == o["best_hypothesis"]
+        assert g["candidate"] == o["candidate"] and np.isclose(g["residual"], o["residual"], rtol=1e-12)
         return
     assert g["n_inliers"] == o["n_inliers"] and g["n_points"] == o["n_points"]
     if strict:
@@ -253,16 +259,19 @@ def check_solution(g, o, pose_tol=1e-9, strict=True):
 
 
 @pytest.mark.parametrize("mode", [mvs.SCORE_ALGEBRAIC, mvs.SCORE_SAMPSON])
-def test_sfm_solve_vs_oracle_and_golden(ctx, synthetic_golden, mode):
+def test_sfm_solve_vs_oracle_and_golden(ctx, solver, synthetic_golden, mode):
     s = synthetic_golden
     tagm = "alg_" if mode == mvs.SCORE_ALGEBRAIC else "smp_"
     for c in range(4):
         xy1, xy2, K, tab = s[f"s{c}_xy1"], s[f"s{c}_xy2"], s[f"s{c}_K"], s[f"s{c}_tab"]
         g = ctx.sfm_solve(xy1, xy2, K, samples=tab, mode=mode)
         o = orc.sfm_solve(xy1, xy2, K, samples=tab, mode=mode)
-        check_solution(g, o, strict=(c >= 2))
+        check_solution(g, o, strict=(c >= 2), exact=(solver == "reference"))
         t = f"s{c}_{tagm}"
         assert (g["status"] == mvs.OK) == bool(s[t + "ok"])
+        if g["status"] == mvs.OK and solver == "reference":
+            for k in ("F", "E", "mask", "R2in1", "t2in1", "points", "indexes"):
+                assert np.array_equal(g[k], s[t + k]), (t, k)
         if g["status"] == mvs.OK:      # Oracle-A (cv2.SVDecomp) golden: north-star tolerances
             assert g["n_inliers"] == int(s[t + "n_inliers"])
             assert np.allclose(g["R2in1"], s[t + "R2in1"], atol=1e-6)
@@ -271,17 +280,17 @@ def test_sfm_solve_vs_oracle_and_golden(ctx, synthetic_golden, mode):
                 assert np.allclose(g["points"], s[t + "points"], rtol=1e-4, atol=1e-6)
 
 
-def test_sfm_solve_reference_single_sample_lshape(ctx, synthetic_golden):
+def test_sfm_solve_reference_single_sample_lshape(ctx, solver, synthetic_golden):
     """H=1 == the reference's behaviour (sample {0..7}); L-shape rig of test/test-sfm.cpp."""
     s = synthetic_golden
     g = ctx.sfm_solve(s["lshape_xy1"], s["lshape_xy2"], np.eye(3))
     assert g["status"] == mvs.OK and g["n_points"] == 8
     assert np.allclose(g["t2in1"], [1, 0, 0], atol=1e-9) and np.allclose(g["R2in1"], np.eye(3), atol=1e-9)
     assert np.allclose(g["points"], s["lshape_P"], atol=1e-9)
-    check_solution(g, orc.sfm_solve(s["lshape_xy1"], s["lshape_xy2"], np.eye(3)), strict=False)
+    check_solution(g, orc.sfm_solve(s["lshape_xy1"], s["lshape_xy2"], np.eye(3)), strict=False, exact=(solver == "reference"))
 
 
-def test_sfm_solve_tsukuba_golden(ctx, tsukuba, tsukuba_golden):
+def test_sfm_solve_tsukuba_golden(ctx, solver, tsukuba, tsukuba_golden):
     K = tsukuba["K"]; gl = tsukuba_golden
     for a in range(1, 5):
         for md, H in ((10, 1), (30, 1), (-1, 1)):
@@ -289,17 +298,29 @@ def test_sfm_solve_tsukuba_golden(ctx, tsukuba, tsukuba_golden):
             xy1 = tsukuba[f"kp{a}"][gl[tag + "t"]]; xy2 = tsukuba[f"kp{a + 1}"][gl[tag + "q"]]
             g = ctx.sfm_solve(xy1, xy2, K)
             o = orc.sfm_solve(xy1, xy2, K)
-            check_solution(g, o, pose_tol=1e-7)
+            check_solution(g, o, pose_tol=1e-7, exact=(solver == "reference"))
+            if solver == "reference":
+                # the reference's own configuration (H = 1, sample {0..7}) against the numpy + real cv2.SVDecomp
+                # goldens: identical inlier sets AND identical bits in F, E, pose and points, pair 4-5 included
+                t1 = tag + "h1_"
+                assert g["n_inliers"] == int(gl[t1 + "n_inliers"])
+                for k in ("F", "E", "mask", "R2in1", "t2in1", "points", "indexes"):
+                    assert np.array_equal(g[k], gl[t1 + k]), (t1, k)
             # reference expectation (test/test-image-pair.cpp:40-45): pose ~ (I,(1,0,0)) to 1e-3
             assert np.allclose(g["t2in1"], [1, 0, 0], atol=1e-3) and np.allclose(g["R2in1"], np.eye(3), atol=1e-3)
         tag = f"p{a}{a + 1}_md30_"
         xy1 = tsukuba[f"kp{a}"][gl[tag + "t"]]; xy2 = tsukuba[f"kp{a + 1}"][gl[tag + "q"]]
         g = ctx.sfm_solve(xy1, xy2, K, samples=gl[tag + "tab256"])
-        assert g["n_inliers"] == int(gl[tag + "h256_n_inliers"])
-        assert np.allclose(g["t2in1"], gl[tag + "h256_t2in1"], atol=1e-6)
+        if solver == "reference":
+            assert g["n_inliers"] == int(gl[tag + "h256_n_inliers"]) and g["best_hypothesis"] == int(gl[tag + "h256_best_h"])
+            for k in ("F", "E", "mask", "R2in1", "t2in1", "points"):
+                assert np.array_equal(g[k], gl[tag + "h256_" + k]), (tag, k)
+        else:
+            assert abs(g["n_inliers"] - int(gl[tag + "h256_n_inliers"])) <= 2
+            assert np.allclose(g["t2in1"], gl[tag + "h256_t2in1"], atol=1e-5)
 
 
-def test_sfm_triangulate_cube_known_answer(ctx, synthetic_golden):
+def test_sfm_triangulate_cube_known_answer(ctx, solver, synthetic_golden):
     """test/test-sfm.cpp:92-155"""
     s = synthetic_golden
     pts, idx = ctx.sfm_triangulate(s["cube_xy1"], s["cube_xy2"], np.eye(3), np.eye(3), np.zeros(3), np.eye(3),
@@ -308,18 +329,22 @@ def test_sfm_triangulate_cube_known_answer(ctx, synthetic_golden):
     po, io = orc.sfm_triangulate(s["cube_xy1"], s["cube_xy2"], np.eye(3), np.eye(3), np.zeros(3), np.eye(3),
                                  np.array([1.0, 0, 0]))
     assert np.allclose(pts, po, atol=1e-12)
+    if solver == "reference":
+        assert np.array_equal(pts, po) and np.array_equal(pts, s["cube_tri_pts"])
 
 
-def test_sfm_triangulate_general_and_behind_camera(ctx):
+def test_sfm_triangulate_general_and_behind_camera(ctx, solver):
     K, x1, x2 = general_scene(700, 21, 0.2, 0.3)
     R2 = synth._rodrigues(np.array([0.02, -0.05, 0.01])); t2 = np.array([0.4, 0.1, -0.2])
     pg, ig = ctx.sfm_triangulate(x1, x2, K, np.eye(3), np.zeros(3), R2, t2)
     po, io = orc.sfm_triangulate(x1, x2, K, np.eye(3), np.zeros(3), R2, t2)
     assert 0 < len(io) < 700 and np.array_equal(ig, io)
     assert np.allclose(pg, po, rtol=1e-9, atol=1e-10)
+    if solver == "reference":
+        assert np.array_equal(pg, po)
 
 
-def test_failure_codes(ctx):
+def test_failure_codes(ctx, solver):
     xy = np.random.default_rng(0).uniform(0, 100, (5, 2))
     assert ctx.sfm_solve(xy, xy, np.eye(3))["status"] == mvs.E_TOO_FEW_POINTS
     r = np.random.default_rng(1)
@@ -331,7 +356,7 @@ def test_failure_codes(ctx):
 
 
 # ------------------------------------------------------------------------------------------ batched pairs
-def test_pair_batch_tsukuba_all_pairs(ctx, tsukuba):
+def test_pair_batch_tsukuba_all_pairs(ctx, solver, tsukuba):
     """ImagePair ctor + reconstruct over every ordered pair of the 5 bundled frames, VO default max_dist=10."""
     descs = [tsukuba[f"desc{i}"] for i in range(1, 6)]; kps = [tsukuba[f"kp{i}"] for i in range(1, 6)]
     K = tsukuba["K"]
@@ -352,12 +377,16 @@ def test_pair_batch_tsukuba_all_pairs(ctx, tsukuba):
             assert n == o["n_points"] and np.array_equal(det["indexes"][i][:n], o["indexes"])
             assert np.allclose(det["points"][i][:n], o["points"], rtol=1e-6, atol=1e-8)
             assert np.allclose(r["R2in1"], o["R2in1"], atol=1e-7) and np.allclose(r["t2in1"], o["t2in1"], atol=1e-7)
+            if solver == "reference":
+                assert np.array_equal(det["points"][i][:n], o["points"])
+                for k in ("F", "E", "R1to2", "t1to2", "R2in1", "t2in1"):
+                    assert np.array_equal(r[k], o[k]), (a, b, k)
             ssd = int((o["matches"]["distance"][o["indexes"].astype(int)].astype(np.int64) ** 2).sum())
             assert int(r["match_inlier_ssd"]) == ssd
 
 
 @pytest.mark.parametrize("mode,thr", [(mvs.SCORE_SAMPSON, 0.0), (mvs.SCORE_ALGEBRAIC, 1e-3)])
-def test_pair_batch_synthetic_s8k_shape(ctx, mode, thr):
+def test_pair_batch_synthetic_s8k_shape(ctx, solver, mode, thr):
     """Config-3-shaped pairs (general motion, 0.5 px noise, outliers), ragged keypoint counts in one batch,
     sharding-invariant sampling through pair_id_base."""
     sizes = [2048, 1500, 2048, 777]
@@ -379,13 +408,16 @@ def test_pair_batch_synthetic_s8k_shape(ctx, mode, thr):
         assert same_up_to_scale(r["E"], o["E"], 1e-9)
         assert np.allclose(r["R2in1"], o["R2in1"], atol=1e-9) and np.allclose(r["t2in1"], o["t2in1"], atol=1e-9)
         assert np.allclose(det["points"][i][:r["n_points"]], o["points"], rtol=1e-7, atol=1e-9)
+        if solver == "reference":
+            assert np.array_equal(det["points"][i][:r["n_points"]], o["points"]) and np.array_equal(r["E"], o["E"])
+            assert np.array_equal(r["R2in1"], o["R2in1"]) and np.array_equal(r["t2in1"], o["t2in1"])
     # the second half of the batch alone, with pair_id_base=2, must reproduce entries 2,3
     res2, _ = ctx.pair_batch(pairs[2:], synth.K_S8K, H=256, seed=5, mode=mode, max_error_sq=thr, pair_id_base=2)
     for k in ("n_inliers", "best_hypothesis", "n_points", "R2in1", "t2in1", "F"):
         assert np.array_equal(res2[k], res[2:][k])
 
 
-def test_pair_batch_full_size_8k_h4096(ctx):
+def test_pair_batch_full_size_8k_h4096(ctx, solver):
     """BASELINE config 3 at full size (8192 kpts, H=4096): oracle check of the whole pipeline on one pair."""
     d1, k1, d2, k2, tr = synth.synthetic_pair(1, n=8192)
     ctx.frames_upload([d1, d2], [k1, k2])
@@ -634,7 +666,7 @@ def test_cpp_vo_tool_from_images(tmp_path):
     assert np.allclose(Rt[:, :3], np.eye(3), atol=1e-3) and np.allclose(Rt[:, 3], [1, 0, 0], atol=1e-3)
 
 
-def test_frames_append_equals_bulk_upload(ctx, tsukuba):
+def test_frames_append_equals_bulk_upload(ctx, solver, tsukuba):
     """Streaming use (FrameManager::add_frame per image): appended frames behave exactly like a bulk upload."""
     descs = [tsukuba[f"desc{i}"] for i in range(1, 6)]; kps = [tsukuba[f"kp{i}"] for i in range(1, 6)]
     pairs = [(0, 1), (1, 2), (0, 4), (3, 2)]

@@ -1,0 +1,86 @@
+"""GPU tests of the REFERENCE solver's building block: cv::SVDecomp restated bit for bit on the device
+(csrc/common.cuh cv_jacobi / cv_svd_full, entry mvs_svd_batch = the SVD<M> wrapper of source/math/svd.hpp:13-73),
+and of the borderline-point count the parity claim rests on.  The pipeline-level reference-solver checks (F, E,
+mask, pose, points identical to the numpy + real cv2.SVDecomp goldens) live in tests/test_gpu_parity.py."""
+import os
+
+import numpy as np
+import pytest
+
+import mvslam_b200 as mvs
+from conftest import GOLDEN
+from oracle import cbind as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = mvs.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("n", [3, 4, 9])
+def test_device_svd_equals_committed_cv2_outputs(ctx, n):
+    g = np.load(os.path.join(GOLDEN, "cv_svd_golden.npz"))
+    U, w, Vt = ctx.svd_batch(g[f"A{n}"], solver="reference")
+    assert np.array_equal(w, g[f"w{n}"]) and np.array_equal(U, g[f"u{n}"]) and np.array_equal(Vt, g[f"vt{n}"])
+
+
+@pytest.mark.parametrize("n", [3, 4, 9])
+def test_device_svd_equals_live_cv2(ctx, n):
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(5 + n)
+    M = rng.normal(size=(500, n, n)) * 10.0 ** rng.integers(-3, 4, (500, 1, 1))
+    M[1::4, :, -1] = M[1::4, :, 0] - M[1::4, :, 1]
+    M[2::4, n - 1, :] = 0.0
+    U, w, Vt = ctx.svd_batch(M, solver="reference")
+    for i in range(500):
+        wc, uc, vtc = cv2.SVDecomp(M[i].copy(), flags=cv2.SVD_MODIFY_A | cv2.SVD_FULL_UV)
+        assert np.array_equal(w[i], wc.ravel()) and np.array_equal(U[i], uc) and np.array_equal(Vt[i], vtc), i
+
+
+def test_fast_svd3_reconstructs(ctx):
+    rng = np.random.default_rng(1)
+    M = rng.normal(size=(64, 3, 3))
+    U, w, Vt = ctx.svd_batch(M, solver="fast")
+    assert np.allclose(U @ (w[:, :, None] * Vt), M, atol=1e-13) and np.all(np.diff(w, axis=1) <= 0)
+    with pytest.raises(mvs.MvsError):
+        ctx.svd_batch(rng.normal(size=(2, 4, 4)), solver="fast")
+
+
+def test_ill_conditioned_tsukuba_pair_is_reproduced_exactly(ctx, tsukuba, tsukuba_golden):
+    """on Tsukuba pair 4-5 (sigma_8(A) ~ 5e-6) the Householder solver is 6e-5 away from the
+    reference's A^T A route and 8/42/61 inliers off.  The REFERENCE solver must land on cv2's own bits; the FAST
+    solver's deviation is asserted, not hidden."""
+    K = tsukuba["K"]; gl = tsukuba_golden
+    for md in (10, 30, -1):
+        tag = f"p45_md{md}_"
+        xy1 = tsukuba["kp4"][gl[tag + "t"]]; xy2 = tsukuba["kp5"][gl[tag + "q"]]
+        r = ctx.sfm_solve(xy1, xy2, K, solver="reference")
+        assert np.array_equal(r["F"], gl[tag + "h1_F"]) and np.array_equal(r["mask"], gl[tag + "h1_mask"])
+        assert np.array_equal(r["points"], gl[tag + "h1_points"]) and r["n_inliers"] == int(gl[tag + "h1_n_inliers"])
+        f = ctx.sfm_solve(xy1, xy2, K, solver="fast")
+        Fa = f["F"] / np.linalg.norm(f["F"]); Fb = gl[tag + "h1_F"] / np.linalg.norm(gl[tag + "h1_F"])
+        d = min(np.abs(Fa - Fb).max(), np.abs(Fa + Fb).max())
+        assert 1e-6 < d < 1e-4, d
+
+
+def test_borderline_points_near_the_threshold(ctx, tsukuba, tsukuba_golden):
+    """inlier-set identity across implementations needs no residual within round-off of the strict
+    threshold.  Count |r - thr| < 1e-9 * thr over every Tsukuba golden case (the fused-vs-unfused residual
+    evaluations differ by ~1e-16 absolute = 2.5e-10 * thr)."""
+    K = tsukuba["K"]; gl = tsukuba_golden
+    thr = 5e-2 / K[0, 0] / K[1, 1]
+    border = total = 0
+    for a in range(1, 5):
+        for md in (10, 30, -1):
+            tag = f"p{a}{a + 1}_md{md}_"
+            xy1 = tsukuba[f"kp{a}"][gl[tag + "t"]]; xy2 = tsukuba[f"kp{a + 1}"][gl[tag + "q"]]
+            p1 = orc.normalize_points(K, xy1); p2 = orc.normalize_points(K, xy2)
+            F = gl[tag + "h1_F"]
+            r = np.abs(np.einsum("ij,jk,ik->i", p2, F, p1))
+            border += int((np.abs(r - thr) < 1e-9 * thr).sum()); total += len(r)
+    print(f"borderline residuals: {border} of {total}")
+    assert border == 0

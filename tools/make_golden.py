@@ -14,6 +14,10 @@ runs this — it only reads the committed .npz files.
                         sample {0..7} (H=1) and with a 256-row seeded table.
   synthetic_golden.npz  Oracle-A outputs on small general-motion scenes (noise-free and noisy,
                         with outliers) and the L-shape / cube rigs of the reference's tests.
+  cv_svd_golden.npz     cv2.SVDecomp(MODIFY_A | FULL_UV) outputs (w, u, vt) for 3x3, 4x4 and 9x9 inputs of the
+                        kinds the path produces (general, A^T A of 8-point samples, rank-deficient, exactly
+                        singular): the known-answer vectors of the bit-for-bit restatement of OpenCV's
+                        small-matrix SVD (oracle orc_cv_svd, device cv_svd_full / MVS_SOLVER_REFERENCE).
 """
 import os
 import sys
@@ -108,6 +112,36 @@ def main():
         pts, idx = A.sfm_triangulate(x1, x2, np.eye(3), np.eye(3), np.zeros(3), np.eye(3), np.array([1.0, 0, 0]))
         s[name + "_tri_pts"], s[name + "_tri_idx"] = pts, idx
     np.savez_compressed(os.path.join(OUT, "synthetic_golden.npz"), **s)
+    v = {}
+    r = np.random.default_rng(2024)
+    for n in (3, 4, 9):
+        mats = []
+        for t in range(96):
+            M = r.normal(size=(n, n))
+            kind = t % 6
+            if kind == 1:
+                M[:, -1] = M[:, 0] * 2                       # rank n-1, sigma_n ~ round-off
+            elif kind == 2:
+                M = M @ np.diag([1.0] * (n - 1) + [0.0])     # exactly singular: cv::RNG regenerates a left vector
+            elif kind == 3:
+                M = np.zeros((n, n)); M[t % n, (t // n) % n] = 1.0 + t
+            elif kind == 4 and n == 9:                       # A^T A of a noisy 8-point sample
+                x1 = r.normal(size=(8, 2)); x2 = x1 + r.normal(size=(8, 2)) * 0.05
+                Am = np.stack([x2[:, 0] * x1[:, 0], x2[:, 0] * x1[:, 1], x2[:, 0], x2[:, 1] * x1[:, 0],
+                               x2[:, 1] * x1[:, 1], x2[:, 1], x1[:, 0], x1[:, 1], np.ones(8)], 1)
+                M = np.zeros((9, 9))
+                for k in range(8):
+                    M = M + np.outer(Am[k], Am[k])
+            elif kind == 5:
+                M = M * 10.0 ** r.integers(-8, 8)
+            mats.append(M)
+        mats = np.array(mats)
+        ws, us, vts = [], [], []
+        for M in mats:
+            w, u, vt = cv2.SVDecomp(M.copy(), flags=cv2.SVD_MODIFY_A | cv2.SVD_FULL_UV)
+            ws.append(w.ravel()); us.append(u); vts.append(vt)
+        v[f"A{n}"], v[f"w{n}"], v[f"u{n}"], v[f"vt{n}"] = mats, np.array(ws), np.array(us), np.array(vts)
+    np.savez_compressed(os.path.join(OUT, "cv_svd_golden.npz"), **v)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
