@@ -518,6 +518,7 @@ static int match_two_sets(mvs_ctx *ctx, const uint8_t *query, int nq, const uint
     fa.kp = nullptr; fa.matches = ctx->d_matches.as<mvs_match>(); fa.n_matches = ctx->d_nmatch.as<int32_t>();
     fa.points = nullptr; fa.state = nullptr;
     fa.knn_idx = want_knn ? ctx->d_knn_i.as<int32_t>() : nullptr; fa.knn_dist = want_knn ? ctx->d_knn_d.as<int32_t>() : nullptr;
+    fa.refine_desc = tc ? ctx->t_desc.as<uint4>() : nullptr;
     {
         StageTimer t(ctx, MVS_STAGE_MATCH_FINALIZE);
         CK(launch_match_finalize(fa, nq, 1, ctx->stream));
@@ -857,9 +858,11 @@ static int pair_batch_chunk(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, con
     for (int i = 0; i < n_pairs; ++i) {
         const int a = pairs[2 * i], b = pairs[2 * i + 1];
         if (a < 0 || a >= nf || b < 0 || b >= nf || a == b) return fail(ctx, MVS_E_BAD_ARG, "bad frame index in pairs");  // image-pair.cpp:49
-        if (ctx->h_cnt[b] < 1 || ctx->h_cnt[a] < 2) return fail(ctx, MVS_E_BAD_ARG, "frame with too few keypoints (visual-feature.cpp:56)");
+        // a frame with fewer than 2 (base) / 1 (pair) keypoints (a dark image in a window) gives that pair no matches:
+        // it comes back with MVS_E_TOO_FEW_POINTS and n_matches = 0; the other pairs of the batch are unaffected
         max_nq = std::max(max_nq, ctx->h_cnt[b]); max_nt = std::max(max_nt, ctx->h_cnt[a]);
     }
+    max_nq = std::max(max_nq, 1); max_nt = std::max(max_nt, 1);
     const bool details = matches || inlier_mask || points || indexes;
     if (details && capacity < 1) return fail(ctx, MVS_E_CAPACITY, "detail capacity must be >= 1");
     if ((size_t)finalize_sort_capacity(max_nq) * sizeof(uint32_t) > 200 * 1024)
@@ -917,6 +920,7 @@ static int pair_batch_chunk(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, con
     fa.matches = ctx->d_matches.as<mvs_match>(); fa.n_matches = ctx->d_nmatch.as<int32_t>();
     fa.points = ctx->d_points.as<double>(); fa.state = ctx->d_state.as<PairState>();
     fa.knn_idx = nullptr; fa.knn_dist = nullptr;
+    fa.refine_desc = tc ? ctx->d_desc.as<uint4>() : nullptr;
     {
         StageTimer t(ctx, MVS_STAGE_MATCH_FINALIZE);
         CK(launch_match_finalize(fa, max_nq, n_pairs, ctx->stream));

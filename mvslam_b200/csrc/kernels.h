@@ -45,6 +45,10 @@ struct FinalizeArgs {
     double *points;            // [pairs][q_stride][6] = (x1,y1,z1,x2,y2,z2) or nullptr
     PairState *state;          // [pairs] or nullptr
     int32_t *knn_idx, *knn_dist;  // optional raw knnMatch output [pairs][q_stride][2]
+    // tensor-core matcher: the second key of a partial is the best of all column streams OTHER than the best's (an upper
+    // bound of the true second distance); K2 then evaluates the best's 15 stream-mates from the raw descriptors where the
+    // result depends on them (refine_second).  desc = the frame table's 32-byte descriptors, nullptr = partials are exact.
+    const uint4 *refine_desc;
 };
 
 struct NormArgs { double Kinv[9]; };

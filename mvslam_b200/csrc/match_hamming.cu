@@ -7,6 +7,8 @@
 // (source/front-end/image-pair.cpp:123-140, source/vision/sfm-solve.cpp:300-302, camera.cpp:55-79).
 #include <math_constants.h>
 
+#include <mutex>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -131,7 +133,42 @@ __device__ __forceinline__ uint2 merge_partials(const uint2 *partial, int splits
     return b;
 }
 
-__global__ void __launch_bounds__(FIN_THREADS)
+// Exact second neighbour from the tensor-core matcher's partials (match_hamming_tc.cu).  Its epilogue tracks, per 64-column
+// block of train rows, the maximum of the four streams t = 0..3 (mod 4); `second` is the best key over every stream except
+// the one the best came from.  The only train rows that can beat it are therefore the best's stream-mates: the rows of the
+// same 64-row block with the same index mod 4 (15 of them).  Warp-cooperative: for every lane that asks (`want`), lanes
+// 0..15 evaluate one stream slot each with popcounts and a shuffle-minimum brings the result back to the asking lane.
+__device__ __forceinline__ uint32_t refine_second_warp(const uint4 *desc, bool want, int row_q, int row_t0, int nt, uint32_t best,
+                                                       uint32_t second)
+{
+    const int lane = threadIdx.x & 31, sub = lane & 15, hi = lane >> 4;
+    unsigned bal = __ballot_sync(0xFFFFFFFFu, want);
+    while (bal) {                       // two asking lanes per round: lanes 0-15 serve the first, lanes 16-31 the second
+        const int L0 = __ffs(bal) - 1;
+        bal &= bal - 1;
+        const int L1 = bal ? __ffs(bal) - 1 : -1;
+        if (bal) bal &= bal - 1;
+        const int L = hi ? L1 : L0;
+        const uint32_t bL = __shfl_sync(0xFFFFFFFFu, best, L < 0 ? 0 : L);
+        const int rq = __shfl_sync(0xFFFFFFFFu, row_q, L < 0 ? 0 : L);
+        const int t1 = (int)(bL & kIdxMask);
+        const int t = (t1 & ~63) + (t1 & 3) + 4 * sub;
+        uint32_t key = kKeyNone;
+        if (L >= 0 && t != t1 && t < nt) {
+            const uint4 qa = desc[2 * (size_t)rq], qb = desc[2 * (size_t)rq + 1];
+            const uint4 ta = desc[2 * (size_t)(row_t0 + t)], tb = desc[2 * (size_t)(row_t0 + t) + 1];
+            key = (hamming256(qa, qb, ta, tb) << kIdxBits) | (uint32_t)t;
+        }
+#pragma unroll
+        for (int off = 8; off > 0; off >>= 1) key = min(key, __shfl_xor_sync(0xFFFFFFFFu, key, off));   // stays inside a half
+        const uint32_t k0 = __shfl_sync(0xFFFFFFFFu, key, 0), k1 = __shfl_sync(0xFFFFFFFFu, key, 16);
+        if (lane == L0) second = min(second, k0);
+        if (lane == L1) second = min(second, k1);
+    }
+    return second;
+}
+
+__global__ void __launch_bounds__(FIN_THREADS, 2)   // 32 registers: two CTAs (pairs) per SM
 match_finalize_kernel(FinalizeArgs a)
 {
     extern __shared__ uint32_t keys[];  // sort_cap entries
@@ -145,21 +182,30 @@ match_finalize_kernel(FinalizeArgs a)
     if (threadIdx.x == 0) s_count = 0;
     __syncthreads();
 
-    for (int q = threadIdx.x; q < nq; q += FIN_THREADS) {
-        const uint2 b = merge_partials(part, a.splits, a.q_stride, q);
-        if (a.knn_idx) {  // raw knnMatch(k=2) output
+    for (int q0 = 0; q0 < nq; q0 += FIN_THREADS) {    // warp-uniform trip count (refine_second_warp shuffles)
+        const int q = q0 + threadIdx.x;
+        const bool valid = q < nq;
+        uint2 b = valid ? merge_partials(part, a.splits, a.q_stride, q) : make_uint2(kKeyNone, kKeyNone);
+        if (a.refine_desc && a.knn_idx)    // raw output: every query needs its exact second neighbour
+            b.y = refine_second_warp(a.refine_desc, valid && b.x != kKeyNone, a.frame_off[fq] + q, a.frame_off[ft], nt, b.x, b.y);
+        if (valid && a.knn_idx) {  // raw knnMatch(k=2) output
             int32_t *ki = a.knn_idx + ((size_t)pair * a.q_stride + q) * 2;
             int32_t *kd = a.knn_dist + ((size_t)pair * a.q_stride + q) * 2;
             ki[0] = b.x == kKeyNone ? -1 : (int)(b.x & kIdxMask); kd[0] = b.x == kKeyNone ? -1 : (int)(b.x >> kIdxBits);
             ki[1] = b.y == kKeyNone ? -1 : (int)(b.y & kIdxMask); kd[1] = b.y == kKeyNone ? -1 : (int)(b.y >> kIdxBits);
         }
-        if (nt < 2) continue;
         const bool far2 = a.bound && (b.y == kKeyNone || (b.y >> kIdxBits) >= a.bound);   // bounded search: d2 >= bound
-        if (b.x == kKeyNone || (b.y == kKeyNone && !far2)) continue;
         // the reference compares float distances promoted to double (visual-feature.cpp:66-68);
         // a "far" second neighbour passes the ratio test for every d1 <= max_dist by construction of the bound
-        const double d1 = (double)(float)(b.x >> kIdxBits), d2 = (double)(float)(b.y >> kIdxBits);
-        bool keep = (far2 || d1 < a.ratio * d2) && ((a.max_dist < 0) || (d1 <= a.max_dist));
+        const double d1 = (double)(float)(b.x >> kIdxBits);
+        double d2 = (double)(float)(b.y >> kIdxBits);
+        bool keep = valid && nt >= 2 && b.x != kKeyNone && (b.y != kKeyNone || far2) &&
+                    (far2 || d1 < a.ratio * d2) && ((a.max_dist < 0) || (d1 <= a.max_dist));
+        if (a.refine_desc && !a.knn_idx) {   // passed with the upper bound of d2: decide with the exact one
+            b.y = refine_second_warp(a.refine_desc, keep, a.frame_off[fq] + q, a.frame_off[ft], nt, b.x, b.y);
+            d2 = (double)(float)(b.y >> kIdxBits);
+            keep = keep && d1 < a.ratio * d2;
+        }
         if (keep && rpart) {  // cross-check: q must be the nearest query of its train descriptor
             const uint2 rb = merge_partials(rpart, a.rev_splits, a.rev_stride, (int)(b.x & kIdxMask));
             keep = ((int)(rb.x & kIdxMask) == q);
@@ -262,11 +308,20 @@ cudaError_t launch_match_finalize(const FinalizeArgs &a, int max_nq, int n_pairs
 {
     const size_t smem = (size_t)finalize_sort_capacity(max_nq) * sizeof(uint32_t);
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(match_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > 48 * 1024) {
+        // the opt-in is a per-device function attribute: set it (to the kernel's maximum, once) on whichever device
+        // the calling context is bound to; contexts of several threads / GPUs may get here concurrently
+        static std::mutex mu;
+        static bool configured[64] = {};
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
         if (e != cudaSuccess) return e;
-        configured = smem;
+        std::lock_guard<std::mutex> lock(mu);
+        if (dev < 0 || dev >= 64 || !configured[dev]) {
+            e = cudaFuncSetAttribute(match_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e != cudaSuccess) return e;
+            if (dev >= 0 && dev < 64) configured[dev] = true;
+        }
     }
     match_finalize_kernel<<<n_pairs, FIN_THREADS, smem, s>>>(a);
     return cudaSuccess;

@@ -9,14 +9,21 @@
 //   approximation.  (kind::f8f6f4 with E4M3 +-1 was measured too: exact as well, 13 % slower.)
 //
 //   The contraction runs as tcgen05.mma (M = N = 128, K = 8 x 32) with both operands staged by TMA (128-byte swizzle)
-//   and the accumulators double-buffered in TMEM.  The
-//   epilogue never materialises the score matrix: thread <-> (query row, column half) keeps a running (best, second)
-//   pair on packed 16-bit keys, 1.25 ALU instructions per accumulator plus a per-tile merge.
+//   and the accumulators double-buffered in TMEM.  The epilogue never materialises the score matrix: thread <-> (query
+//   row, column half) keeps the running maximum of four column STREAMS (columns c' = 0, 1, 2, 3 mod 4 of its 64-column
+//   half) on packed 16-bit keys -- 0.25 three-input VIMNMX per accumulator -- and hands K2 the exact best plus the best of
+//   all OTHER streams.  That second value is an upper bound of the true second distance: the true second neighbour is
+//   either it or one of the 15 stream-mates of the best (same 64-column block, same index mod 4), which K2 evaluates
+//   with popcounts for the few queries whose fate depends on it (match_hamming.cu, refine_second).  A full (best, second)
+//   chain costs 1.25 ALU instructions per accumulator and kept the ALU pipe, not the tensor pipe, on the critical path
+//   (round 2 measurement).
 //
-// Warp roles (576 threads, one persistent CTA per SM):
-//   warp 0      TMA producer (256-row query tile per item, 128-row train tiles through a STAGES-deep mbarrier ring)
-//   warp 1      TMEM allocator + tcgen05.mma issuer (converged warp, elected lane)
+// Warp roles (640 threads, one persistent CTA per SM):
+//   warp 0      train-tile producer (128-row tiles through a STAGES-deep mbarrier ring, running ahead across items)
+//   warp 1, 18  tcgen05.mma issuers, one per 128-row block of the query tile (converged warp, elected lane); warp 1 also
+//               allocates the TMEM
 //   warps 2-17  epilogue: two groups of 8 (one per 128-row block of the query tile)
+//   warp 19     query row-block producer (3-slot ring of 128-row blocks)
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -38,7 +45,10 @@ constexpr int KSLABS = 2;            // 256 one-byte elements per descriptor
 constexpr int RB = 2;                // 128-row blocks of a query tile (each train tile is multiplied with both)
 constexpr int EPI_GROUP = 8;         // warps per epilogue group: two per TMEM lane quarter, each takes half of a tile's columns
 constexpr int EPI_WARPS = RB * EPI_GROUP;  // one group per row block
-constexpr int TC_THREADS = 64 + EPI_WARPS * 32;
+constexpr int MMA_WARP_B = 2 + EPI_WARPS;  // second issuer (row block 1)
+constexpr int A_WARP = MMA_WARP_B + 1;     // query row-block producer
+constexpr int A_SLOTS = 3;                 // 128-row query blocks resident at a time
+constexpr int TC_THREADS = (A_WARP + 1) * 32;
 constexpr int NACC = 2 * RB;         // TMEM accumulator buffers: double-buffered per row block
 constexpr uint32_t TMEM_COLS = NACC * BN;
 constexpr int TC_SPLITS = 2;         // partial results per query: one per column half
@@ -154,9 +164,9 @@ expand_desc_kernel(const uint32_t *__restrict__ desc, size_t word_begin, size_t 
 // integer multiply-add on the otherwise idle FMA pipe (x * 1 + constant, the 1 being a kernel argument so that it stays
 // an IMAD) puts  63 - c'  (c' = column inside the thread's 64-column half) into the free low 7 bits of both lanes:
 //      k16 = 128 (128 - hamming) + (63 - c')          in [-16384, 16447]
-// orders the columns of the half by (smaller distance, then smaller index) under MAX, and the running (best, second)
-// pair of both lanes costs 2.5 VIMNMX.S16x2 per register = 1.25 ALU instructions per accumulator.  At the end of a tile
-// the two survivors are widened to  hamming * 32768 + trainIdx  and merged into the thread's 32-bit pair (minimum = best).
+// orders the columns of the half by (smaller distance, then smaller index) under MAX; one three-input VIMNMX.S16x2 folds
+// two registers (four accumulators) into the running maxima of their streams.  At the end of a tile the two best of the four
+// stream maxima are widened to  hamming * 32768 + trainIdx  and merged into the thread's 32-bit pair (minimum = best).
 // (Measured alternative: a ninth K step over a constant slab that adds the index inside the MMA -- no epilogue
 // instruction at all, but 12.5 % more tensor work on a kernel whose tensor pipe is 88 % busy.)
 __device__ __forceinline__ uint32_t widen_key(uint32_t k16, uint32_t tile_base /* first column of the thread's half */)
@@ -172,8 +182,9 @@ __device__ __forceinline__ uint32_t widen_key(uint32_t k16, uint32_t tile_base /
 // tiles in flight) and the four TMEM accumulators (2 row blocks x 2 steps) stay full across item boundaries.
 struct ItemInfo { int pair, q0, nq, nt, row_q, row_t, n_tiles, n_rb; };
 
-__device__ __forceinline__ bool load_item(const TcKnnArgs &a, int item, ItemInfo &it)
+__device__ __forceinline__ bool load_item(const TcKnnArgs &a, int item, ItemInfo &it, int n_items)
 {
+    if (item >= n_items) return false;
     it.pair = item / a.q_tiles;
     it.q0 = (item - it.pair * a.q_tiles) * (RB * BM);
     int fq, ft;
@@ -189,16 +200,32 @@ __device__ __forceinline__ bool load_item(const TcKnnArgs &a, int item, ItemInfo
     return it.q0 < it.nq;                                   // every role skips the same items
 }
 
+// Pipeline (measured on the B200 box with clock64 counters in every role, round 2; clocks per 1024-clock train tile):
+//   * the tensor pipe ran 1245 clocks per tile with a single producer lane that loaded "query tile, then that item's train
+//     tiles" and waited for the previous item's MMAs before touching the query buffer: both rings ran dry at every item
+//     boundary, and a.pairs / frame_cnt / frame_off were fetched on the critical path;
+//   * with the boundaries gone the period was still ~1250: four epilogue warps per SM sub-partition shared an ALU pipe that
+//     their (best, second) chains loaded to 82 %, so accumulators came back late.  Without any epilogue arithmetic the same
+//     kernel ran 1060 clocks per tile.
+// What is left (this revision, same box, 1024 Tsukuba pairs, CUDA-event time of the launch): 0.445 ms; without the TMA
+// loads 0.441, additionally without the epilogue arithmetic 0.431, additionally without the TMEM loads 0.405 (the tcgen05.ld
+// traffic shares the TMEM read port with the accumulating MMAs: 6 %); issuing the same MMAs back to back in a micro-benchmark
+// (tools/ubench_umma.cu: 64.00 clocks per instruction in SS mode, i.e. the operands are NOT shared-memory-bandwidth bound)
+// would take 0.37 ms, and ~0.01 ms is launch + TMEM allocation.
+// Hence: the train ring (warp 0) never waits for anything but its own stages and runs across item boundaries; the query row
+// blocks go through their own 3-slot ring (warp A_WARP), so the next item's first row block is resident before the current
+// item ends and the second follows while the first is being multiplied; each row block has its own issuing warp; item
+// metadata is fetched one item ahead; the epilogue keeps stream maxima only (see the file header).
 template <int STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // the launch requests no static shared memory, so the dynamic window starts 1024-byte aligned (checked)
-    uint8_t *sA = smem_raw;                                 // [RB row blocks][KSLABS] query slabs
-    uint8_t *sB = sA + RB * KSLABS * BM * SLAB;             // [STAGES][KSLABS] train slabs
+    uint8_t *sA = smem_raw;                                 // [A_SLOTS][KSLABS] query slabs, one 128-row block per slot
+    uint8_t *sB = sA + A_SLOTS * KSLABS * BM * SLAB;        // [STAGES][KSLABS] train slabs
     uint64_t *bars = (uint64_t *)(sB + STAGES * KSLABS * BN * SLAB);
-    uint64_t *afull = bars, *aempty = afull + 1, *full = aempty + 1, *empty = full + STAGES, *tfull = empty + STAGES,
+    uint64_t *afull = bars, *aempty = afull + A_SLOTS, *full = aempty + A_SLOTS, *empty = full + STAGES, *tfull = empty + STAGES,
              *tempty = tfull + NACC;
     uint32_t *tmem_slot = (uint32_t *)(tempty + NACC);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -206,9 +233,9 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
 
     if (threadIdx.x == 0) {
         if (smem_u32(smem_raw) & 1023u) __trap();
-        mbar_init(afull, 1); mbar_init(aempty, 1);
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int b = 0; b < NACC; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, EPI_GROUP * 32); }
+        for (int s = 0; s < A_SLOTS; ++s) { mbar_init(afull + s, 1); mbar_init(aempty + s, 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, RB); }
+        for (int b = 0; b < NACC; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, EPI_GROUP); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -221,19 +248,20 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
     const uint32_t tmem_base = *tmem_slot;
 
     // mbarrier parity convention: a consumer waits for fill number n with parity n & 1; a producer waits for the n-th
-    // release with parity (n & 1) ^ 1, which passes at once for n = 0 (nothing to wait for on first use)
+    // release with parity (n & 1) ^ 1, which passes at once for n = 0 (nothing to wait for on first use).
+    // Query row blocks are numbered per CTA in the order (item, row block); number u lives in slot u % A_SLOTS.
+    // Every role walks the same item sequence and fetches the NEXT item's metadata while it works on the current one.
+    ItemInfo it, nx;
+    bool have = load_item(a, blockIdx.x, nx, n_items);
     if (warp == 0) {
-        // ===== TMA producer =====
+        // ===== train-tile producer: runs ahead across item boundaries, bounded only by its own ring =====
         if (lane == 0) {
-            uint32_t tile_no = 0, item_no = 0;
-            ItemInfo it;
+            uint32_t tile_no = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                if (!load_item(a, item, it)) continue;
-                mbar_wait(aempty, (item_no & 1) ^ 1);
-                mbar_expect_tx(afull, it.n_rb * KSLABS * BM * SLAB);
-                for (int rb = 0; rb < it.n_rb; ++rb)
-                    for (int ks = 0; ks < KSLABS; ++ks)
-                        tma_load_2d(&map, afull, sA + (rb * KSLABS + ks) * BM * SLAB, ks * SLAB, it.row_q + rb * BM);
+                it = nx;
+                const bool valid = have;
+                have = load_item(a, item + (int)gridDim.x, nx, n_items);
+                if (!valid) continue;
                 for (int i = 0; i < it.n_tiles; ++i, ++tile_no) {
                     const uint32_t s = tile_no % STAGES;
                     mbar_wait(empty + s, ((tile_no / STAGES) & 1) ^ 1);
@@ -241,56 +269,76 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
                     for (int ks = 0; ks < KSLABS; ++ks)
                         tma_load_2d(&map, full + s, sB + (s * KSLABS + ks) * BN * SLAB, ks * SLAB, it.row_t + i * BN);
                 }
-                ++item_no;
             }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer (converged warp, elected lane issues) =====
-        {
-            const uint32_t leader = elect_one();
-            const uint32_t a_lo0 = desc_lo(smem_u32(sA)), b_lo0 = desc_lo(smem_u32(sB));
-            uint32_t tile_no = 0, item_no = 0, use_no[RB] = {0, 0};
-            ItemInfo it;
+    } else if (warp == A_WARP) {
+        // ===== query row-block producer =====
+        if (lane == 0) {
+            uint32_t u = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                if (!load_item(a, item, it)) continue;
-                mbar_wait(afull, item_no & 1);
-                for (int i = 0; i < it.n_tiles; ++i, ++tile_no) {
-                    const uint32_t s = tile_no % STAGES;
-                    const uint32_t b_lo = b_lo0 + s * (KSLABS * BN * SLAB >> 4);
-                    mbar_wait(full + s, (tile_no / STAGES) & 1);
-#pragma unroll
-                    for (int rb = 0; rb < RB; ++rb) {
-                        if (rb >= it.n_rb) break;
-                        const uint32_t acc = (use_no[rb] & 1) * RB + rb;
-                        mbar_wait(tempty + acc, ((use_no[rb] >> 1) & 1) ^ 1);     // epilogue drained this accumulator
-                        tcgen05_fence_after();
-                        const uint32_t d_tmem = tmem_base + acc * BN;
-                        const uint32_t a_lo = a_lo0 + rb * (KSLABS * BM * SLAB >> 4);
-                        // UMMA_K = 32 one-byte elements = 32 bytes inside the swizzle atom; 4 steps per 128-byte slab
-                        umma_i8<false>(d_tmem, a_lo, b_lo, leader);
-#pragma unroll
-                        for (int k = 1; k < 4 * KSLABS; ++k)
-                            umma_i8<true>(d_tmem, a_lo + (k >> 2) * (BM * SLAB >> 4) + (k & 3) * 2,
-                                          b_lo + (k >> 2) * (BN * SLAB >> 4) + (k & 3) * 2, leader);
-                        tcgen05_commit_if(tfull + acc, leader);      // accumulator ready for the epilogue
-                        ++use_no[rb];
-                    }
-                    tcgen05_commit_if(empty + s, leader);            // train stage reusable once these MMAs retire
+                it = nx;
+                const bool valid = have;
+                have = load_item(a, item + (int)gridDim.x, nx, n_items);
+                if (!valid) continue;
+                for (int rb = 0; rb < it.n_rb; ++rb, ++u) {
+                    const uint32_t sl = u % A_SLOTS;
+                    mbar_wait(aempty + sl, ((u / A_SLOTS) & 1) ^ 1);
+                    mbar_expect_tx(afull + sl, KSLABS * BM * SLAB);
+                    for (int ks = 0; ks < KSLABS; ++ks)
+                        tma_load_2d(&map, afull + sl, sA + (sl * KSLABS + ks) * BM * SLAB, ks * SLAB, it.row_q + rb * BM);
                 }
-                tcgen05_commit_if(aempty, leader);                   // query tile reusable once the item's MMAs retire
-                ++item_no;
             }
+        }
+    } else if (warp == 1 || warp == MMA_WARP_B) {
+        // ===== MMA issuers (converged warps, elected lane issues): warp 1 owns row block 0, warp MMA_WARP_B row block 1 =====
+        const int rb = (warp == 1) ? 0 : 1;
+        const uint32_t leader = elect_one();
+        const uint32_t a_lo0 = desc_lo(smem_u32(sA)), b_lo0 = desc_lo(smem_u32(sB));
+        uint32_t tile_no = 0, use_no = 0, u = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            it = nx;
+            const bool valid = have;
+            have = load_item(a, item + (int)gridDim.x, nx, n_items);
+            if (!valid) continue;
+            const bool active = rb < it.n_rb;             // an item may have one row block only: stay in step with the train ring
+            const uint32_t sl = (u + rb) % A_SLOTS;
+            if (active) mbar_wait(afull + sl, ((u + rb) / A_SLOTS) & 1);
+            const uint32_t a_lo = a_lo0 + sl * (KSLABS * BM * SLAB >> 4);
+            for (int i = 0; i < it.n_tiles; ++i, ++tile_no) {
+                const uint32_t s = tile_no % STAGES;
+                const uint32_t b_lo = b_lo0 + s * (KSLABS * BN * SLAB >> 4);
+                mbar_wait(full + s, (tile_no / STAGES) & 1);
+                if (active) {
+                    const uint32_t acc = (use_no & 1) * RB + rb;
+                    mbar_wait(tempty + acc, ((use_no >> 1) & 1) ^ 1);     // epilogue drained this accumulator
+                    tcgen05_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * BN;
+                    // UMMA_K = 32 one-byte elements = 32 bytes inside the swizzle atom; 4 steps per 128-byte slab
+                    umma_i8<false>(d_tmem, a_lo, b_lo, leader);
+#pragma unroll
+                    for (int k = 1; k < 4 * KSLABS; ++k)
+                        umma_i8<true>(d_tmem, a_lo + (k >> 2) * (BM * SLAB >> 4) + (k & 3) * 2,
+                                      b_lo + (k >> 2) * (BN * SLAB >> 4) + (k & 3) * 2, leader);
+                    tcgen05_commit_if(tfull + acc, leader);      // accumulator ready for the epilogue
+                    ++use_no;
+                }
+                tcgen05_commit_if(empty + s, leader);            // train stage reusable once both issuers' MMAs retire
+            }
+            if (active) tcgen05_commit_if(aempty + sl, leader);  // this row block's slot is free once its MMAs retire
+            u += (uint32_t)it.n_rb;
         }
     } else {
         // ===== epilogue: thread <-> (query row, column half), warp group <-> row block =====
-        const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
+        const int quarter = warp & 3;                    // TMEM lane quarter this warp may access (warps 2..17)
         const int ew = warp - 2;
         const int half = (ew >> 2) & 1;                  // which 64 columns of every 128-column tile
         const int rb = ew >> 3;                          // row block of the query tile
         uint32_t use_no = 0;
-        ItemInfo it;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            if (!load_item(a, item, it)) continue;
+            it = nx;
+            const bool valid = have;
+            have = load_item(a, item + (int)gridDim.x, nx, n_items);
+            if (!valid) continue;
             if (rb >= it.n_rb) continue;
             const int q = it.q0 + rb * BM + quarter * 32 + lane;   // row within the block == TMEM lane
             uint32_t g1 = kKeyNone, g2 = kKeyNone;
@@ -301,23 +349,24 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
                 tcgen05_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
                 const bool ragged = col0 + BN / 2 > it.nt;   // warp-uniform: only a frame's last tile
-                uint32_t a1 = 0x80008000u, a2 = 0x80008000u, b1 = 0x80008000u, b2 = 0x80008000u;   // two chains for ILP
                 // one packed load brings the 64 columns as 32 registers; the accumulator goes back to the MMA warp as soon as
-                // they have arrived
+                // they have arrived (one arrival per warp)
                 uint32_t v[32];
                 tmem_ld64_packed(taddr, v);
                 tmem_ld_wait();
                 tcgen05_fence_before();
-                mbar_arrive(tempty + acc);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty + acc);
                 const uint32_t one = (uint32_t)a.one;    // opaque 1: keeps the index insertion an IMAD (FMA pipe)
 #define MVS_KEY(m) (v[m] * one + (uint32_t)(((63 - (2 * (m) + 1)) << 16) | (63 - 2 * (m))))
+                // register m holds columns 2m (low lane) and 2m + 1 (high lane): the even registers feed the streams
+                // c' = 0, 1 (mod 4), the odd ones c' = 2, 3 (mod 4)
+                uint32_t sa = 0x80008000u, sb = 0x80008000u;
                 if (!ragged) {
 #pragma unroll
-                    for (int m = 0; m < 32; m += 2) {
-                        const uint32_t pa = MVS_KEY(m), pb = MVS_KEY(m + 1);
-                        const uint32_t la = __vmins2(a1, pa), lb = __vmins2(b1, pb);
-                        a1 = __vmaxs2(a1, pa); b1 = __vmaxs2(b1, pb);
-                        a2 = __vmaxs2(a2, la); b2 = __vmaxs2(b2, lb);
+                    for (int m = 0; m < 32; m += 4) {
+                        sa = __vimax3_s16x2(sa, MVS_KEY(m), MVS_KEY(m + 2));
+                        sb = __vimax3_s16x2(sb, MVS_KEY(m + 1), MVS_KEY(m + 3));
                     }
                 } else {                                 // rows of the next frame / zero fill lose to every real key
 #pragma unroll
@@ -325,16 +374,15 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
                         const int c = col0 + 2 * m;
                         const uint32_t key = MVS_KEY(m);
                         const uint32_t pk = (c < it.nt ? (key & 0xFFFFu) : 0x8000u) | (c + 1 < it.nt ? (key & 0xFFFF0000u) : 0x80000000u);
-                        const uint32_t lo = __vmins2(a1, pk);
-                        a1 = __vmaxs2(a1, pk); a2 = __vmaxs2(a2, lo);
+                        if (m & 1) sb = __vmaxs2(sb, pk); else sa = __vmaxs2(sa, pk);
                     }
                 }
-                // the tile's two best over both 16-bit lanes (in both lanes of m1 / m2) -> the thread's running pair
-                const uint32_t n1 = __vmaxs2(a1, b1), n2 = __vimax3_s16x2(__vmins2(a1, b1), a2, b2);
+#undef MVS_KEY
+                // the two best of the four stream maxima (in both 16-bit lanes of m1 / m2) -> the thread's running pair
+                const uint32_t n1 = __vmaxs2(sa, sb), n2 = __vmins2(sa, sb);
                 const uint32_t r1 = __byte_perm(n1, 0, 0x1032), r2 = __byte_perm(n2, 0, 0x1032);
                 const uint32_t m1 = __vmaxs2(n1, r1);
                 const uint32_t m2 = __vmaxs2(__vmins2(n1, r1), __vmaxs2(n2, r2));
-#undef MVS_KEY
                 const uint32_t tile_base = (uint32_t)col0;
                 top2(g1, g2, widen_key(m1 & 0xFFFFu, tile_base));
                 top2(g1, g2, widen_key(m2 & 0xFFFFu, tile_base));
@@ -374,9 +422,9 @@ EncodeTiledFn get_encode_fn()
 
 cudaError_t launch_tc(const CUtensorMap &map, TcKnnArgs a, int max_nq, int n_pairs, cudaStream_t s)
 {
-    constexpr int STAGES = 5;   // one persistent CTA per SM: 64 KB query tile + 160 KB train ring
-    const size_t smem = (size_t)RB * KSLABS * BM * SLAB + (size_t)STAGES * KSLABS * BN * SLAB +
-                        (2 + 2 * STAGES + 2 * NACC) * sizeof(uint64_t) + 16;
+    constexpr int STAGES = 4;   // one persistent CTA per SM: 3 x 32 KB query row blocks + 4 x 32 KB train ring = 224 KB
+    const size_t smem = (size_t)A_SLOTS * KSLABS * BM * SLAB + (size_t)STAGES * KSLABS * BN * SLAB +
+                        (2 * A_SLOTS + 2 * STAGES + 2 * NACC) * sizeof(uint64_t) + 16;
     auto kern = knn2_hamming_tc_kernel<STAGES>;
     static int sm_count[64] = {0};          // per device: the shared-memory opt-in is a per-device function attribute
     int dev = 0;

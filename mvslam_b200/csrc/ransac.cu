@@ -352,7 +352,11 @@ select_kernel(SelectArgs a)
     __shared__ int s_nties;
     const int pair = blockIdx.x;
     PairState *st = a.state + pair;
-    if (st->status != MVS_OK) return;
+    if (st->status != MVS_OK) {   // no model for this pair (fewer than 8 matches): its mask row is all outliers, not stale workspace
+        uint8_t *mk = a.mask + (size_t)pair * a.p_stride;
+        for (int i = threadIdx.x; i < st->n_matches && i < a.p_stride; i += SEL_THREADS) mk[i] = 0;
+        return;
+    }
     const int n = st->n_matches;
     const int tiles_used = (n + SC_TILE - 1) / SC_TILE;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

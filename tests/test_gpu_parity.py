@@ -105,6 +105,36 @@ def test_tensor_matcher_equals_popc_matcher(ctx, ctx_popc, nq, nt, rand_bytes, c
     assert np.array_equal(ma, mb) and np.array_equal(ma, as_mvs(orc.match_hamming(q, t, 0.8, -1.0, cross)))
 
 
+@pytest.mark.parametrize("cross", [False, True])
+def test_tensor_matcher_second_neighbour_is_a_stream_mate(ctx, cross):
+    """The tensor-core epilogue keeps one maximum per column stream (train index mod 4 inside a 64-row block) and K2 looks the
+    best's stream-mates up again (refine_second_warp): plant the two nearest neighbours of every query in ONE stream, with
+    equal and with different distances, at block edges and in a ragged last block."""
+    rng = np.random.default_rng(42)
+    nt, nq = 1000, 600
+    t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+    q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+    for i in range(nq):
+        blk = int(rng.integers(0, (nt + 63) // 64)) * 64
+        r = int(rng.integers(0, 4))
+        slots = [x for x in range(blk + r, min(blk + 64, nt), 4)]
+        if len(slots) < 2:
+            continue
+        a, b = rng.choice(len(slots), 2, replace=False)
+        q[i] = t[slots[a]]                                   # distance 0 to slots[a] (t rows may be shared between queries)
+        if i % 3 == 0:
+            t[slots[b]] = t[slots[a]]                        # ... and 0 to its stream-mate: tie, lowest index first
+        elif i % 3 == 1:
+            t[slots[b]] = t[slots[a]]; t[slots[b], 0] ^= 1   # ... and 1 to its stream-mate
+    ig, dg = ctx.knn2_hamming(q, t)
+    io, do = orc.knn2_hamming(q, t)
+    assert np.array_equal(ig, io) and np.array_equal(dg, do)
+    for md in (-1.0, 5.0):
+        mg = ctx.match_hamming(q, t, max_dist=md, cross_check=cross)
+        mo = orc.match_hamming(q, t, max_dist=md, cross_check=cross)
+        assert np.array_equal(mg, as_mvs(mo))
+
+
 def test_more_than_32768_train_descriptors_take_the_popc_kernel(ctx):
     """The tensor-core epilogue key holds 15 index bits; larger train sets run on knn2_hamming_kernel."""
     rng = np.random.default_rng(9)
@@ -599,10 +629,20 @@ def test_empty_and_degenerate_inputs(ctx):
     same = np.tile(np.array([[10.0, 20.0]]), (20, 1))
     g = ctx.sfm_solve(same, same, synth.K_S8K, H=4, seed=1)
     assert g["status"] in (mvs.OK, mvs.E_NO_MODEL, mvs.E_TOO_FEW_INLIERS, mvs.E_NO_CHEIRALITY)
-    # frames with zero keypoints may be uploaded but not paired
-    ctx.frames_upload([t, np.zeros((0, 32), np.uint8)], [np.zeros((10, 2), np.float32), np.zeros((0, 2), np.float32)])
-    with pytest.raises(mvs.MvsError):
-        ctx.pair_batch([(0, 1)], synth.K_S8K)
+    # a frame without keypoints (a dark image in a window) only fails its own pairs: no matches, MVS_E_TOO_FEW_POINTS,
+    # an all-zero mask row; the other pairs of the batch are solved as usual
+    d1, k1, d2, k2, _ = synth.synthetic_pair(5, n=512, noise_px=1e-4)
+    e8 = np.zeros((0, 32), np.uint8); e2 = np.zeros((0, 2), np.float32)
+    ctx.frames_upload([d1, e8, d2, d1[:1]], [k1, e2, k2, k1[:1]])
+    res, det = ctx.pair_batch([(0, 1), (0, 2), (1, 0), (3, 2), (2, 3)], synth.K_S8K, H=8, seed=1)
+    assert [int(r["status"]) for r in res] == [mvs.E_TOO_FEW_POINTS, mvs.OK, mvs.E_TOO_FEW_POINTS, mvs.E_TOO_FEW_POINTS,
+                                               mvs.E_TOO_FEW_POINTS]
+    assert [int(r["n_matches"]) for r in res[:4]] == [0, int(res[1]["n_matches"]), 0, 0] and res[1]["n_matches"] > 100
+    assert int(res[4]["n_matches"]) <= 1      # a single query keypoint may well find its match: still too few points
+    assert all(not det["mask"][i][:int(res[i]["n_matches"])].any() for i in (0, 2, 3, 4))   # within the counts: no stale data
+    assert res["n_points"][[0, 2, 3, 4]].sum() == 0 and res["n_inliers"][[0, 2, 3, 4]].sum() == 0
+    alone, _ = ctx.pair_batch([(0, 2)], synth.K_S8K, H=8, seed=1, pair_id_base=1)
+    assert alone.tobytes() == res[1:2].tobytes()
     # bad RANSAC parameters
     with pytest.raises(mvs.MvsError):
         ctx.sfm_solve(np.zeros((10, 2)), np.zeros((10, 2)), np.eye(3), H=0)

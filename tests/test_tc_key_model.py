@@ -1,7 +1,9 @@
 """Host-side model of the arithmetic of the tensor-core matcher (mvslam_b200/csrc/match_hamming_tc.cu), checked against the
 CPU oracle without a GPU: the +-8 byte encoding, the signed 16-bit key `128 (128 - hamming) + (63 - c')` (c' = column
-inside a thread's 64-column half of a 128-column tile) maximised per half, and its widening to `hamming * 32768 + trainIdx`.
-The CUDA kernel is tested against the same oracle in tests/test_gpu_parity.py; this file pins the algebra it relies on."""
+inside a thread's 64-column half of a 128-column tile), its widening to `hamming * 32768 + trainIdx`, and the split of the
+top-2 search into "maximum of four column streams per 64-column block" (epilogue) + "the best's 15 stream-mates" (K2's
+refine_second_warp).  The CUDA kernels are tested against the same oracle in tests/test_gpu_parity.py; this file pins the
+algebra they rely on."""
 import numpy as np
 import pytest
 
@@ -25,12 +27,24 @@ def model_knn2(q, t):
         tile = T[t0:t0 + HALF]
         acc = Q @ tile.T                                                     # 8 K steps: 64 (256 - 2 hamming)
         assert (acc % 128 == 0).all() and acc.min() >= -16384 and acc.max() <= 16384
-        k16 = (acc + (63 - np.arange(tile.shape[0]))[None, :]).astype(np.int16)   # the IMAD of the epilogue
-        order = np.sort(k16, axis=1)[:, ::-1][:, :2].astype(np.int64)         # per half: the two LARGEST keys
-        if order.shape[1] < 2:
-            order = np.concatenate([order, np.full((q.shape[0], 1), -32768, np.int64)], 1)
+        k16 = np.full((q.shape[0], HALF), -32768, np.int64)
+        k16[:, :tile.shape[0]] = (acc + (63 - np.arange(tile.shape[0]))[None, :]).astype(np.int16)   # the IMAD of the epilogue
+        streams = np.stack([k16[:, r::4].max(axis=1) for r in range(4)], 1)   # VIMNMX3 chains: columns r (mod 4)
+        order = np.sort(streams, axis=1)[:, ::-1][:, :2]                      # the two best of the four stream maxima
         wide = (128 - (order >> 7)) * 32768 + t0 + (63 - (order & 127))      # widen_key()
         g = np.sort(np.concatenate([g, wide], 1), axis=1)[:, :2]
+    # K2 refine_second_warp: the true second neighbour is g[:, 1] or one of the best's stream-mates
+    dist, idx = g >> 15, g & 32767
+    for i in range(q.shape[0]):
+        if dist[i, 0] > 256:
+            continue
+        t1 = int(idx[i, 0])
+        mates = [t for t in range((t1 & ~63) + (t1 & 3), min((t1 & ~63) + 64, nt), 4) if t != t1]
+        for tm in mates:
+            d = int(np.unpackbits(q[i] ^ t[tm]).sum())
+            key = d * 32768 + tm
+            if key < g[i, 1]:
+                g[i, 1] = key
     dist, idx = g >> 15, g & 32767
     none = dist > 256                                                        # empty lane / nothing found
     return np.where(none, -1, idx), np.where(none, -1, dist)

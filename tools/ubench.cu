@@ -8,7 +8,7 @@
 constexpr int ILP = 8;
 constexpr int ITERS = 4096;
 
-enum Op { POPC, XOR, IADD3, MNMX, DADD, DMUL, DFMA, HAMMING, HAM_CSA3, HAM_CSA4, HAM_CSA3M, MNMX16, MNMX3, MNMX3_16, PRMT, IMAD };
+enum Op { POPC, XOR, IADD3, MNMX, DADD, DMUL, DFMA, HAMMING, HAM_CSA3, HAM_CSA4, HAM_CSA3M, MNMX16, MNMX3, MNMX3_16, PRMT, IMAD, HMNMX2, MIX_I16_H2, FMNMX, MIX_I16_F32 };
 
 template <int OP>
 __global__ void __launch_bounds__(256) k(uint32_t *out, uint32_t seed, double dseed)
@@ -32,6 +32,17 @@ __global__ void __launch_bounds__(256) k(uint32_t *out, uint32_t seed, double ds
             if (OP == MNMX3_16) r[i] = __vimax3_s16x2(r[i], seed + it, (uint32_t)it ^ seed);
             if (OP == PRMT) r[i] = __byte_perm(r[i], seed + it, 0x5410) ^ 0u, r[i] = __byte_perm(r[i], it, 0x1032);
             if (OP == IMAD) r[i] = r[i] * seed + it;
+            if (OP == HMNMX2 || ((OP == MIX_I16_H2) && (i & 1))) {   // max.f16x2 / min.f16x2 (does it leave the ALU pipe?)
+                uint32_t t;
+                asm volatile("min.f16x2 %0, %1, %2;" : "=r"(t) : "r"(r[i]), "r"(seed + it));
+                asm volatile("max.f16x2 %0, %1, %2;" : "=r"(r[i]) : "r"(t), "r"((uint32_t)it));
+            }
+            if ((OP == MIX_I16_H2 || OP == MIX_I16_F32) && !(i & 1)) r[i] = __vmaxs2(__vmins2(r[i], seed + it), (uint32_t)it);
+            if (OP == FMNMX || ((OP == MIX_I16_F32) && (i & 1))) {
+                float f = __uint_as_float(r[i]);
+                f = fmaxf(fminf(f, __uint_as_float(seed + it)), __uint_as_float((uint32_t)it));
+                r[i] = __float_as_uint(f);
+            }
             if (OP == DADD) d[i] = d[i] + dseed;
             if (OP == DMUL) d[i] = d[i] * dseed;
             if (OP == DFMA) d[i] = fma(d[i], dseed, dseed);
@@ -122,6 +133,10 @@ int main()
     printf(", \"vimnmx3_16x2_per_s\": %.4e", run<MNMX3_16>(out, blocks, ILP));
     printf(", \"prmt_per_s\": %.4e", run<PRMT>(out, blocks, ILP * 2));
     printf(", \"imad_per_s\": %.4e", run<IMAD>(out, blocks, ILP));
+    printf(", \"hmnmx2_per_s\": %.4e", run<HMNMX2>(out, blocks, ILP * 2));
+    printf(", \"mix_vimnmx16x2_hmnmx2_per_s\": %.4e", run<MIX_I16_H2>(out, blocks, ILP * 2));
+    printf(", \"fmnmx_per_s\": %.4e", run<FMNMX>(out, blocks, ILP * 2));
+    printf(", \"mix_vimnmx16x2_fmnmx_per_s\": %.4e", run<MIX_I16_F32>(out, blocks, ILP * 2));
     printf("}\n");
     return cudaGetLastError() != cudaSuccess;
 }
