@@ -323,6 +323,12 @@ int mvs_ba_solve_batch(mvs_ctx *ctx, int n_problems, const double K[9],
  * kp[f] is [counts[f]][2] float (cv::KeyPoint::pt).  Replaces the previous frame table. */
 int mvs_frames_upload(mvs_ctx *ctx, int n_frames, const uint8_t *const *desc, const float *const *kp,
                       const int32_t *counts, int desc_bytes);
+/* The same table from two contiguous host arrays (frame f's rows follow frame f-1's; counts[f] rows each): two copies
+ * instead of two per frame, and the call does not wait for them -- with pinned buffers it returns at once, so one
+ * context can upload the next chunk of a long sequence while another one matches the previous chunk (bench.py,
+ * e2e_distinct).  The buffers must stay valid until the next synchronising call on this ctx. */
+int mvs_frames_upload_packed(mvs_ctx *ctx, int n_frames, const uint8_t *desc_all, const float *kp_all,
+                             const int32_t *counts, int desc_bytes);
 /* Append one frame to the resident table (what FrameManager::add_frame does per new image,
  * source/front-end/frame-manager.cpp:107-125); returns its index through *frame_index.  mvs_frames_upload
  * with n_frames = 0 is not allowed: start a new sequence with mvs_frames_clear. */

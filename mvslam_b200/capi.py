@@ -428,6 +428,12 @@ class Context:
         self._check(self._L.mvs_frames_upload(self._h, nf, dptr, kptr, _p(counts), 32))
         self._frame_counts = counts
 
+    def frames_upload_packed(self, desc_all, kp_all, counts):
+        """desc_all / kp_all: addresses (e.g. of pinned torch tensors) or contiguous arrays; does not synchronise."""
+        counts = np.ascontiguousarray(counts, np.int32)
+        self._check(self._L.mvs_frames_upload_packed(self._h, len(counts), _p(desc_all), _p(kp_all), _p(counts), 32))
+        self._frame_counts = counts
+
     def frames_clear(self):
         self._check(self._L.mvs_frames_clear(self._h))
         self._frame_counts = np.zeros(0, np.int32)

@@ -847,6 +847,37 @@ int mvs_frames_upload(mvs_ctx *ctx, int n_frames, const uint8_t *const *desc, co
     return MVS_OK;
 }
 
+int mvs_frames_upload_packed(mvs_ctx *ctx, int n_frames, const uint8_t *desc_all, const float *kp_all, const int32_t *counts,
+                             int desc_bytes)
+{
+    if (!ctx) return MVS_E_BAD_ARG;
+    if (n_frames < 1 || !desc_all || !kp_all || !counts) return fail(ctx, MVS_E_BAD_ARG, "null argument or n_frames < 1");
+    if (desc_bytes != 32) return fail(ctx, MVS_E_UNSUPPORTED, "only 256-bit (32-byte) descriptors are supported");
+    CK(cudaSetDevice(ctx->device));
+    std::vector<int32_t> off(n_frames), cnt(n_frames);
+    size_t total = 0;
+    for (int f = 0; f < n_frames; ++f) {
+        if (counts[f] < 0 || counts[f] > (int)kIdxMask) return fail(ctx, MVS_E_BAD_ARG, "bad keypoint count");
+        off[f] = (int32_t)total; cnt[f] = counts[f];
+        total += (size_t)counts[f];
+        if (total > 0x7FFFFFFFull) return fail(ctx, MVS_E_UNSUPPORTED, "more than 2^31 keypoints in the frame table");
+    }
+    CK(ctx->d_desc.ensure(std::max<size_t>(total, 1) * 32));
+    CK(ctx->d_kp.ensure(std::max<size_t>(total, 1) * sizeof(float2)));
+    CK(ctx->d_foff.ensure((size_t)n_frames * sizeof(int32_t)));
+    CK(ctx->d_fcnt.ensure((size_t)n_frames * sizeof(int32_t)));
+    // the offset / count tables are copied from the ctx's own vectors, which live until the next upload: no need to wait
+    ctx->h_off.swap(off); ctx->h_cnt.swap(cnt);
+    if (total) {
+        CK(cudaMemcpyAsync(ctx->d_desc.p, desc_all, total * 32, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_kp.p, kp_all, total * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CK(cudaMemcpyAsync(ctx->d_foff.p, ctx->h_off.data(), (size_t)n_frames * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_fcnt.p, ctx->h_cnt.data(), (size_t)n_frames * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->desc8_rows = 0;
+    return MVS_OK;
+}
+
 static int pair_batch_chunk(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, const double K[9],
                             const mvs_match_params *mparams, const mvs_ransac_params *rparams,
                             mvs_pair_result *results, mvs_match *matches, uint8_t *inlier_mask,

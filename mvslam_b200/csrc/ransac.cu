@@ -194,6 +194,180 @@ __device__ __forceinline__ void hypothesis_body(const HypArgs &a)
     for (int i = 0; i < 9; ++i) o[i] = F[i];
 }
 
+// ------------------------------------------------------------------------------------------
+// The same REFERENCE solve with the 9x9 Jacobi spread over 4 lanes, for launches with few hypotheses (H = 1 is the
+// reference's configuration: one thread per pair would leave a 300-clock div/sqrt chain per rotation, ~290 rotations,
+// on the critical path of every call).  OpenCV visits the row pairs (i, j) of a sweep in lexicographic order; rotation
+// (i, j) only depends on the latest earlier rotations that touched row i or row j, i.e. on (i, j-1), (i-1, i) and
+// (i-1, j): it can run at "time" i + j, rotations with equal i + j touch disjoint rows, and the next sweep may start 9
+// time steps after the current one (row 0 is free after (0, 8)).  Four lanes therefore execute the exact sequential
+// algorithm -- every rotation sees bit for bit the operands it would see in program order -- in 9 steps per sweep
+// instead of 36.  A sweep that rotates nothing ends the iteration (OpenCV's `if (!changed) break`); the rotations of the
+// following sweep that were started early have then, by construction, rotated nothing either.
+// Rows live in shared memory: At[9][9], V[9][9], W[9] per hypothesis.
+// ------------------------------------------------------------------------------------------
+constexpr int WAVE_LANES = 4;
+constexpr int WAVE_HYP_PER_BLOCK = 16;                       // 64 threads
+constexpr int WAVE_STATE = 9 * 9 * 2 + 9 + 1;                // doubles per hypothesis (+1 keeps consecutive blocks off one bank)
+
+struct WaveSlot { int8_t i, j, older; };                    // older = 1: the rotation belongs to the previous sweep
+// phase f = T mod 9 of global step T: rotations with i + j = f (sweep started later) and i + j = f + 9 (started earlier)
+__constant__ WaveSlot kWave[9][WAVE_LANES] = {
+    {{1, 8, 1}, {2, 7, 1}, {3, 6, 1}, {4, 5, 1}},            // f = 0: t = 9
+    {{0, 1, 0}, {2, 8, 1}, {3, 7, 1}, {4, 6, 1}},            // f = 1: t = 1, 10
+    {{0, 2, 0}, {3, 8, 1}, {4, 7, 1}, {5, 6, 1}},            // f = 2: t = 2, 11
+    {{0, 3, 0}, {1, 2, 0}, {4, 8, 1}, {5, 7, 1}},            // f = 3: t = 3, 12
+    {{0, 4, 0}, {1, 3, 0}, {5, 8, 1}, {6, 7, 1}},            // f = 4: t = 4, 13
+    {{0, 5, 0}, {1, 4, 0}, {2, 3, 0}, {6, 8, 1}},            // f = 5: t = 5, 14
+    {{0, 6, 0}, {1, 5, 0}, {2, 4, 0}, {7, 8, 1}},            // f = 6: t = 6, 15
+    {{0, 7, 0}, {1, 6, 0}, {2, 5, 0}, {3, 4, 0}},            // f = 7: t = 7
+    {{0, 8, 0}, {1, 7, 0}, {2, 6, 0}, {3, 5, 0}},            // f = 8: t = 8
+};
+
+// one rotation of cv_jacobi<9> on rows i, j held in shared memory; returns whether the pair was rotated
+__device__ __forceinline__ bool wave_rotate(double *At, double *V, double *W, int i, int j)
+{
+    constexpr double eps = DBL_EPSILON * 10;
+    double ai[9], aj[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { ai[k] = At[i * 9 + k]; aj[k] = At[j * 9 + k]; }
+    double a = W[i], p = 0, b = W[j];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) p += ai[k] * aj[k];
+    if (fabs(p) <= eps * sqrt(a * b)) return false;
+    p *= 2;
+    const double beta = a - b, gamma = cv_hypot(p, beta);
+    double c, s;
+    if (beta < 0) {
+        const double delta = (gamma - beta) * 0.5;
+        s = sqrt(delta / gamma);
+        c = p / (gamma * s * 2);
+    } else {
+        c = sqrt((gamma + beta) / (gamma * 2));
+        s = p / (gamma * c * 2);
+    }
+    a = b = 0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const double t0 = c * ai[k] + s * aj[k];
+        const double t1 = -s * ai[k] + c * aj[k];
+        At[i * 9 + k] = t0; At[j * 9 + k] = t1;
+        a += t0 * t0; b += t1 * t1;
+    }
+    W[i] = a; W[j] = b;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const double vi = V[i * 9 + k], vj = V[j * 9 + k];
+        V[i * 9 + k] = c * vi + s * vj;
+        V[j * 9 + k] = -s * vi + c * vj;
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(WAVE_HYP_PER_BLOCK * WAVE_LANES)
+hypotheses_reference_wave_kernel(HypArgs a)
+{
+    __shared__ double s_state[WAVE_HYP_PER_BLOCK][WAVE_STATE];
+    __shared__ double s_T[WAVE_HYP_PER_BLOCK][10];            // T1 (s, tx, ty), T2, mx1, my1, mx2, my2 of the sample
+    const int slot = threadIdx.x / WAVE_LANES, sub = threadIdx.x % WAVE_LANES;
+    const long long gid = (long long)blockIdx.x * WAVE_HYP_PER_BLOCK + slot;
+    const int pair = (int)(gid / a.H), h = (int)(gid % a.H);
+    const bool live = pair < a.n_pairs && a.state[pair].status == MVS_OK;
+    double *At = s_state[slot], *V = At + 81, *W = V + 81;
+    const double *pts = a.points + (size_t)(live ? pair : 0) * a.p_stride * 6;
+    if (live && sub == 0) {
+        uint32_t idx[8];
+        if (a.table) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) idx[j] = a.table[(size_t)h * 8 + j];
+        } else {
+            sample_row(a.seed, a.pair_id_base + (uint64_t)pair, (uint32_t)a.state[pair].n_matches, h, idx);
+        }
+        double T1[3], T2[3], mx1, my1, mx2, my2;
+        normalize8(pts, idx, 0, T1, mx1, my1);
+        normalize8(pts, idx, 3, T2, mx2, my2);
+        double A[8][9];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) epipolar_row(pts + (size_t)idx[r] * 6, T1, mx1, my1, T2, mx2, my2, A[r]);
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+#pragma unroll
+            for (int j = i; j < 9; ++j) {
+                double acc = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc += A[k][i] * A[k][j];
+                At[i * 9 + j] = acc; At[j * 9 + i] = acc;
+            }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            double sd = 0;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) { const double t = At[i * 9 + k]; sd += t * t; }
+            W[i] = sd;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) V[i * 9 + k] = (i == k) ? 1.0 : 0.0;
+        }
+        s_T[slot][0] = T1[0]; s_T[slot][1] = T1[1]; s_T[slot][2] = T1[2]; s_T[slot][3] = T2[0]; s_T[slot][4] = T2[1]; s_T[slot][5] = T2[2];
+    }
+    __syncwarp();
+    // pipelined sweeps: global step T, sweep s covers steps 9 s + 1 .. 9 s + 15
+    if (live) {
+        unsigned changed_new = 0, changed_old = 0;              // per lane: did one of MY rotations of that sweep rotate
+        const unsigned gmask = 0xFu << ((threadIdx.x & 31) / WAVE_LANES * WAVE_LANES);
+        for (int T = 1; T <= 9 * 30 + 15; ++T) {
+            const int f = T % 9, s_new = T / 9;                 // f >= 1: sweep s_new runs its step f, sweep s_new - 1 its step f + 9
+            const WaveSlot ws = kWave[f][sub];
+            const int sweep = (f == 0) ? s_new - 1 : (ws.older ? s_new - 1 : s_new);
+            bool did = false;
+            if (sweep >= 0 && sweep < 30) did = wave_rotate(At, V, W, ws.i, ws.j);
+            const bool is_old = (f == 0) || ws.older;
+            if (did) { if (is_old) changed_old = 1; else changed_new = 1; }
+            __syncwarp(gmask);
+            if (f == 6) {                                      // local step 15 of the older sweep just ran: that sweep is complete
+                if (T >= 15) {
+                    const unsigned any = __ballot_sync(gmask, changed_old != 0) & gmask;
+                    if (!any) break;                           // `if (!changed) break`
+                    if (s_new - 1 >= 29) break;                // max_iter = 30 sweeps
+                }
+                changed_old = 0;
+            } else if (f == 8) {                               // after its local step 8 the newer sweep becomes the older one
+                changed_old = changed_new; changed_new = 0;
+            }
+        }
+    }
+    __syncwarp();
+    if (live && sub == 0) {
+        double Wn[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            double sd = 0;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) { const double t = At[i * 9 + k]; sd += t * t; }
+            Wn[i] = sqrt(sd);
+        }
+        int perm[9];
+        cv_sort_perm<9>(Wn, perm);
+        double Fp[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Fp[k] = V[perm[8] * 9 + k];
+        double U[9], w3[3], Vt[9], Fh[9], T2t[9], tmp[9], F[9];
+        cv_svd3(Fp, U, w3, Vt);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                Fh[i * 3 + j] = (U[i * 3 + 0] * w3[0]) * Vt[0 * 3 + j] + (U[i * 3 + 1] * w3[1]) * Vt[1 * 3 + j];
+        const double T1m[9] = {s_T[slot][0], 0.0, s_T[slot][1], 0.0, s_T[slot][0], s_T[slot][2], 0.0, 0.0, 1.0};
+        const double T2m[9] = {s_T[slot][3], 0.0, s_T[slot][4], 0.0, s_T[slot][3], s_T[slot][5], 0.0, 0.0, 1.0};
+        mat3_transpose(T2m, T2t);
+        mat3_mul(T2t, Fh, tmp);
+        mat3_mul(tmp, T1m, F);
+        double *o = a.F_all + ((size_t)pair * a.H + h) * 9;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) o[i] = F[i];
+    }
+}
+
 constexpr int HYP_REF_THREADS = 64;
 __global__ void __launch_bounds__(HYP_REF_THREADS)
 hypotheses_reference_kernel(HypArgs a) { hypothesis_body<true>(a); }
@@ -517,7 +691,10 @@ void launch_hypotheses(const HypArgs &a, int n_pairs, cudaStream_t s)
     HypArgs b = a;
     b.n_pairs = n_pairs;
     const long long total = (long long)n_pairs * a.H;
-    if (a.solver == MVS_SOLVER_REFERENCE)
+    if (a.solver == MVS_SOLVER_REFERENCE && total <= 148LL * 32 * 16)   // few hypotheses: latency matters, 4 lanes per Jacobi
+        hypotheses_reference_wave_kernel<<<(unsigned)((total + WAVE_HYP_PER_BLOCK - 1) / WAVE_HYP_PER_BLOCK),
+                                           WAVE_HYP_PER_BLOCK * WAVE_LANES, 0, s>>>(b);
+    else if (a.solver == MVS_SOLVER_REFERENCE)
         hypotheses_reference_kernel<<<(unsigned)((total + HYP_REF_THREADS - 1) / HYP_REF_THREADS), HYP_REF_THREADS, 0, s>>>(b);
     else
         hypotheses_kernel<<<(unsigned)((total + HYP_THREADS - 1) / HYP_THREADS), HYP_THREADS, 0, s>>>(b);
