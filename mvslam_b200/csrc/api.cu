@@ -85,6 +85,13 @@ struct mvs_ctx {
     // asynchronously into the staging area and scattered to the caller's buffers after the one synchronisation
     uint8_t *h_stage = nullptr;
     size_t h_stage_cap = 0, h_stage_used = 0;
+    // small host->device arguments (pair lists, frame offset tables) go through a pinned ring: cudaMemcpyAsync from pageable
+    // memory first waits for the stream's earlier work, which serialises contexts that are meant to overlap
+    static constexpr int kArgSlots = 32;
+    static constexpr size_t kArgSlotBytes = 64 << 10;
+    uint8_t *h_args = nullptr;
+    cudaEvent_t arg_ev[kArgSlots] = {};
+    int arg_next = 0;
     bool allow_stage = false;   // set by the synchronous entry points only: _enqueue callers may synchronise the stream themselves
     struct StagedCopy { void *dst; size_t dpitch; size_t src_off; size_t width; size_t rows; };
     std::vector<StagedCopy> staged;
@@ -110,6 +117,26 @@ int fail(mvs_ctx *ctx, int code, const char *msg)
 {
     if (ctx) ctx->err = msg;
     return code;
+}
+
+// host -> device copy of a small argument block on the ctx stream, staged through the pinned ring when it fits
+cudaError_t h2d_args(mvs_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    if (!bytes) return cudaSuccess;
+    if (bytes > mvs_ctx::kArgSlotBytes) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (!ctx->h_args) {
+        cudaError_t e = cudaMallocHost((void **)&ctx->h_args, mvs_ctx::kArgSlots * mvs_ctx::kArgSlotBytes);
+        if (e != cudaSuccess) { ctx->h_args = nullptr; (void)cudaGetLastError(); return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream); }
+        for (int i = 0; i < mvs_ctx::kArgSlots; ++i) cudaEventCreateWithFlags(&ctx->arg_ev[i], cudaEventDisableTiming);
+    }
+    const int slot = ctx->arg_next;
+    ctx->arg_next = (slot + 1) % mvs_ctx::kArgSlots;
+    cudaEventSynchronize(ctx->arg_ev[slot]);                 // the copy that last used this slot (32 calls ago) has left it
+    uint8_t *at = ctx->h_args + (size_t)slot * mvs_ctx::kArgSlotBytes;
+    std::memcpy(at, src, bytes);
+    cudaError_t e = cudaMemcpyAsync(dst, at, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->arg_ev[slot], ctx->stream);
+    return e;
 }
 
 cudaEvent_t get_event(mvs_ctx *ctx)
@@ -395,6 +422,7 @@ void mvs_destroy(mvs_ctx *ctx)
     if (ctx->o_pinned) cudaFreeHost(ctx->o_pinned);
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->h_args) { cudaFreeHost(ctx->h_args); for (auto &e : ctx->arg_ev) if (e) cudaEventDestroy(e); }
     for (cudaEvent_t e : ctx->copy_done) if (e) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (DevBuf *b : bufs) b->release();
@@ -872,8 +900,8 @@ int mvs_frames_upload_packed(mvs_ctx *ctx, int n_frames, const uint8_t *desc_all
         CK(cudaMemcpyAsync(ctx->d_desc.p, desc_all, total * 32, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(ctx->d_kp.p, kp_all, total * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
     }
-    CK(cudaMemcpyAsync(ctx->d_foff.p, ctx->h_off.data(), (size_t)n_frames * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_fcnt.p, ctx->h_cnt.data(), (size_t)n_frames * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(h2d_args(ctx, ctx->d_foff.p, ctx->h_off.data(), (size_t)n_frames * sizeof(int32_t)));
+    CK(h2d_args(ctx, ctx->d_fcnt.p, ctx->h_cnt.data(), (size_t)n_frames * sizeof(int32_t)));
     ctx->desc8_rows = 0;
     return MVS_OK;
 }
@@ -915,7 +943,7 @@ static int pair_batch_chunk(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, con
     CK(ctx->d_nmatch.ensure((size_t)n_pairs * sizeof(int32_t)));
     CK(ctx->d_points.ensure((size_t)n_pairs * qs * 6 * sizeof(double)));
     CK(ctx->d_state.ensure((size_t)n_pairs * sizeof(PairState)));
-    CK(cudaMemcpyAsync(ctx->d_pairs.p, pairs, (size_t)n_pairs * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+    CK(h2d_args(ctx, ctx->d_pairs.p, pairs, (size_t)n_pairs * sizeof(int2)));
 
     KnnArgs ka{};
     ka.desc = ctx->d_desc.as<uint4>(); ka.frame_off = ctx->d_foff.as<int32_t>(); ka.frame_cnt = ctx->d_fcnt.as<int32_t>();
