@@ -847,7 +847,7 @@ def e2e_distinct_block(mvs, torch, local, flush, n_pairs=1024, chunk=256, n_ctx=
     pinned host memory) -> 1024 pairs.  The sequence is cut into overlapping chunks; n_ctx contexts take them in turn, each on
     its own stream, so the copy engines upload chunk k+1 and download chunk k-1 while the SMs match and solve chunk k
     (mvs_frames_upload_packed + mvs_pair_batch_enqueue); records + matches + mask + points + indexes of every pair come back
-    inside the timed region.  Measured on this pool (tools/e2e_probe.py): 2 contexts x 128 pairs 3.17 ms, 4 x 128 2.52, 4 x 256
+    inside the timed region.  Measured on this pool (round-2 probe): 2 contexts x 128 pairs 3.17 ms, 4 x 128 2.52, 4 x 256
     2.45; the 84.5 MB upload alone is 1.53 ms at the measured 55 GB/s, more than the device-resident step (1.32 ms)."""
     from mvslam_b200 import synth
     descs, kps, K, pairs, params, cfg = load_workload("seq", n_pairs, 256)

@@ -15,7 +15,8 @@ namespace mvSLAM {
 namespace b200 {
 inline mvs_ba_params &ba_defaults()
 {
-    static thread_local mvs_ba_params p{100, 0, 1e-5, 1e-13};
+    // gtsam::LevenbergMarquardtParams defaults, which ba.cpp:124 uses: lambdaInitial 1e-5, relativeErrorTol 1e-5, absoluteErrorTol 1e-5
+    static thread_local mvs_ba_params p{100, 0, 1e-5, 1e-5, 1e-5};
     return p;
 }
 }  // namespace b200
@@ -45,16 +46,16 @@ inline void ba_frame_pose_and_point(const CameraIntrinsics &ci, const std::unord
     std::vector<double> R((size_t)F * 9), t((size_t)F * 3), pc((size_t)F * 36, nan), X((size_t)P * 3), xc((size_t)P * 9, nan);
     for (int32_t f = 0; f < F; ++f) {
         const Transformation &T = frame_pose_guess.at(fids[f]);
-        for (int k = 0; k < 9; ++k) R[f * 9 + k] = T.rotation().get_matrix().m[k];
+        { const auto Rr = b200::rm3(T.rotation().get_matrix()); for (int k = 0; k < 9; ++k) R[f * 9 + k] = Rr[k]; }
         for (int k = 0; k < 3; ++k) t[f * 3 + k] = T.translation()[k];
         auto it = frame_pose_prior.find(fids[f]);
-        if (it != frame_pose_prior.end()) for (int k = 0; k < 36; ++k) pc[(size_t)f * 36 + k] = it->second.m[k];   // passed to GTSAM as is
+        if (it != frame_pose_prior.end()) { const auto Cr = b200::rm<6, 6>(it->second); for (int k = 0; k < 36; ++k) pc[(size_t)f * 36 + k] = Cr[k]; }   // passed to GTSAM as is
     }
     for (int32_t j = 0; j < P; ++j) {
         const Point3 &p = point_guess.at(pids[j]);
         for (int k = 0; k < 3; ++k) X[(size_t)j * 3 + k] = p[k];
         auto it = point_prior.find(pids[j]);
-        if (it != point_prior.end()) for (int k = 0; k < 9; ++k) xc[(size_t)j * 9 + k] = it->second.m[k];
+        if (it != point_prior.end()) { const auto Cr = b200::rm3(it->second); for (int k = 0; k < 9; ++k) xc[(size_t)j * 9 + k] = Cr[k]; }
     }
     std::vector<mvs_ba_observation> obs;
     for (const auto &fo : frame_observation)
@@ -69,29 +70,27 @@ inline void ba_frame_pose_and_point(const CameraIntrinsics &ci, const std::unord
     std::vector<double> Ro(R.size()), to(t.size()), pco(pc.size()), Xo(X.size()), xco(xc.size());
     mvs_ba_result res;
     mvs_ctx *ctx = b200::Context::thread_default().get();
-    int st = mvs_ba_solve_batch(ctx, 1, ci.m, &F, &P, &O, R.data(), t.data(), pc.data(), X.data(), xc.data(), obs.data(),
+    int st = mvs_ba_solve_batch(ctx, 1, b200::rm3(ci).data(), &F, &P, &O, R.data(), t.data(), pc.data(), X.data(), xc.data(), obs.data(),
                                 &b200::ba_defaults(), Ro.data(), to.data(), pco.data(), Xo.data(), xco.data(), &res);
     b200::check(ctx, st, "ba_frame_pose_and_point");
     if (st != MVS_OK || res.status != MVS_OK) throw b200::Error(res.status, "ba_frame_pose_and_point: " + std::string(mvs_status_string(res.status)));
     frame_pose_estimate.clear();
     for (int32_t f = 0; f < F; ++f) {
-        Matrix3Type Rm; Matrix6Type C;
-        for (int k = 0; k < 9; ++k) Rm.m[k] = Ro[(size_t)f * 9 + k];
-        for (int k = 0; k < 36; ++k) C.m[k] = pco[(size_t)f * 36 + k];
+        const Matrix3Type Rm = b200::mat3_from(&Ro[(size_t)f * 9]);
+        const Matrix6Type C = b200::mat_from<Matrix6Type, 6, 6>(&pco[(size_t)f * 36]);
         frame_pose_estimate[fids[f]] = TransformationEstimate(SE3(SO3(Rm), Vector3Type(to[f * 3], to[f * 3 + 1], to[f * 3 + 2])), C);
     }
     point_estimate.clear();
     for (int32_t j = 0; j < P; ++j) {
-        Matrix3Type C;
-        for (int k = 0; k < 9; ++k) C.m[k] = xco[(size_t)j * 9 + k];
+        const Matrix3Type C = b200::mat3_from(&xco[(size_t)j * 9]);
         point_estimate[pids[j]] = Point3Estimate(Point3(Xo[(size_t)j * 3], Xo[(size_t)j * 3 + 1], Xo[(size_t)j * 3 + 2]), C);
     }
     final_error = res.final_error;
 }
 
 namespace detail {
-inline Matrix6Type diag6(ScalarType a, ScalarType b) { Matrix6Type C; for (int i = 0; i < 3; ++i) { C(i, i) = a * a; C(i + 3, i + 3) = b * b; } return C; }
-inline Matrix3Type diag3(ScalarType a) { Matrix3Type C; for (int i = 0; i < 3; ++i) C(i, i) = a * a; return C; }
+inline Matrix6Type diag6(ScalarType a, ScalarType b) { Matrix6Type C = Matrix6Type::Zero(); for (int i = 0; i < 3; ++i) { C(i, i) = a * a; C(i + 3, i + 3) = b * b; } return C; }
+inline Matrix3Type diag3(ScalarType a) { Matrix3Type C = Matrix3Type::Zero(); for (int i = 0; i < 3; ++i) C(i, i) = a * a; return C; }
 }  // namespace detail
 
 /** sfm.hpp:69-76 / sfm-refine.cpp:20-139: camera 1 anchored at the origin (1e-5), camera 2 and every point regularised (1e-2). */

@@ -24,10 +24,10 @@ inline VisualFeature load_visual_feature(const std::string &filename)
     std::vector<float> xy((size_t)n * 2);
     in.read(reinterpret_cast<char *>(xy.data()), (std::streamsize)(xy.size() * sizeof(float)));
     for (int i = 0; i < n; ++i) { kps[i].pt.x = xy[2 * i]; kps[i].pt.y = xy[2 * i + 1]; }
-    VisualFeatureConfig::ExtractorResultType desc((size_t)n * 32);
+    std::vector<uint8_t> desc((size_t)n * 32);
     in.read(reinterpret_cast<char *>(desc.data()), (std::streamsize)desc.size());
     if (!in) throw b200::Error(MVS_E_BAD_ARG, "truncated feature file " + filename);
-    return VisualFeature(std::move(kps), std::move(desc), w, h);
+    return VisualFeature(std::move(kps), b200::desc_make(desc.data(), (size_t)n), w, h);
 }
 
 /** 8-bit binary PGM (P5, maxval 255) -> pixels; the returned ImageGrayscale points into `pixels`. */
@@ -54,7 +54,11 @@ inline ImageGrayscale load_pgm(const std::string &filename, std::vector<uint8_t>
     pixels.resize((size_t)w * h);
     in.read(reinterpret_cast<char *>(pixels.data()), (std::streamsize)pixels.size());
     if (!in) throw b200::Error(MVS_E_BAD_ARG, "truncated PGM file " + filename);
+#ifdef MVSLAM_B200_WITH_EIGEN_OPENCV
+    return ImageGrayscale(h, w, CV_8U, pixels.data());
+#else
     return ImageGrayscale(h, w, pixels.data());
+#endif
 }
 
 /** PinholeCamera::load_from_file (reference source/vision/camera.cpp:105-123): first line "fx fy shear px py". */

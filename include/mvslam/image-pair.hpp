@@ -5,22 +5,35 @@
 #include <memory>
 
 #include "ba.hpp"
+#include "camera.hpp"
 #include "sfm.hpp"
 #include "visual-feature.hpp"
 
 namespace mvSLAM {
 
-struct Frame {   // the fields of front-end/data-type.hpp:19-37 the path reads
-    size_t id = static_cast<size_t>(-1);
-    VisualFeature visual_feature;
+/** front-end/data-type.hpp:11-41: what the front end keeps per image (the debugging image is optional here). */
+struct FrontEndTypes {
+    using FrameId = Id::Type;
+    struct Frame {
+        FrameId id = static_cast<FrameId>(-1);          // Id::INVALID
+        uint64_t capture_time = 0;                      // timestamp_us_t
+        VisualFeature visual_feature;
+        ImageGrayscale image;
+        Frame() = default;
+        Frame(FrameId id_, uint64_t capture_time_, const VisualFeature &vf, const ImageGrayscale &image_ = ImageGrayscale())
+            : id(id_), capture_time(capture_time_), visual_feature(vf), image(image_) {}
+    };
+    using FramePtr = std::shared_ptr<const Frame>;      // "by default, no write access"
 };
-using FramePtr = std::shared_ptr<Frame>;
+using Frame = FrontEndTypes::Frame;
+using FramePtr = FrontEndTypes::FramePtr;
 
 class ImagePair {
 public:
     struct MatchedPoint {
         Point3 position;
         size_t vf_idx_in_base, vf_idx_in_pair;
+        MatchedPoint(const Point3 &p, size_t viib, size_t viip) : position(p), vf_idx_in_base(viib), vf_idx_in_pair(viip) {}
     };
     struct Params {
         ScalarType max_match_inlier_distance = 10;      // image-pair.cpp:22-23
@@ -28,10 +41,17 @@ public:
     };
     static Params get_default_params() { return Params(); }
 
-    /** image-pair.hpp:38-40: match + reconstruct for one pair (a batch of one). */
+    /** image-pair.hpp:38-40, the reference's own signature: K comes from CameraManager::get_camera()
+     *  (image-pair.cpp:143), exactly what VisualOdometer::add_frame constructs (visual-odometer.cpp:140-148). */
+    ImagePair(const FrontEndTypes::FramePtr &base_frame_, const FrontEndTypes::FramePtr &pair_frame_, const Params &params)
+        : ImagePair(base_frame_, pair_frame_, CameraManager::get_camera().get_intrinsics(), params) {}
+
+    /** The same with an explicit camera matrix (no global state). */
     ImagePair(const FramePtr &base_frame_, const FramePtr &pair_frame_, const CameraIntrinsics &K, const Params &params)
         : base_frame(base_frame_), pair_frame(pair_frame_)
     {
+        if (!base_frame_ || !pair_frame_ || base_frame_->id == pair_frame_->id)
+            throw b200::Error(MVS_E_BAD_ARG, "ImagePair: base and pair frame must differ (image-pair.cpp:49)");
         std::vector<ImagePair> one = solve_batch({base_frame_, pair_frame_}, {{0, 1}}, K, params);
         *this = std::move(one[0]);
         if (valid && params.refine_structure_in_constructor) refine();   // image-pair.cpp:62-70
@@ -77,7 +97,8 @@ public:
                                               const std::vector<std::pair<int, int>> &pairs, const CameraIntrinsics &K,
                                               const Params &params)
     {
-        mvs_ctx *ctx = b200::Context::thread_default().get();
+        // a context of its own: the frame table a caller keeps resident on thread_default() is not replaced behind its back
+        mvs_ctx *ctx = b200::Context::thread_scratch().get();
         const int nf = (int)frames.size(), np = (int)pairs.size();
         std::vector<const uint8_t *> dp(nf);
         std::vector<std::vector<float>> kp(nf);
@@ -86,7 +107,7 @@ public:
         int cap = 1;
         for (int f = 0; f < nf; ++f) {
             const auto &vf = frames[f]->visual_feature;
-            dp[f] = vf.get_descriptors().data();
+            dp[f] = b200::desc_data(vf.get_descriptors());
             cnt[f] = (int32_t)vf.size();
             kp[f].resize(vf.size() * 2);
             for (size_t i = 0; i < vf.size(); ++i) { kp[f][2 * i] = vf.get_keypoints()[i].pt.x; kp[f][2 * i + 1] = vf.get_keypoints()[i].pt.y; }
@@ -101,7 +122,7 @@ public:
         std::vector<double> pts((size_t)np * cap * 3);
         std::vector<uint64_t> idx((size_t)np * cap);
         const mvs_match_params mp{0.7, params.max_match_inlier_distance, 0, 1};
-        b200::check(ctx, mvs_pair_batch(ctx, pr.data(), np, K.m, &mp, &b200::ransac_defaults(), res.data(), matches.data(),
+        b200::check(ctx, mvs_pair_batch(ctx, pr.data(), np, b200::rm3(K).data(), &mp, &b200::ransac_defaults(), res.data(), matches.data(),
                                         nullptr, pts.data(), idx.data(), cap), "ImagePair: pair_batch");
         std::vector<ImagePair> out;
         out.reserve(np);
@@ -114,15 +135,14 @@ public:
             ip.valid = (res[i].status == MVS_OK);
             if (ip.valid) {   // image-pair.cpp:158-167 (with points[] indexed by position, not by original index)
                 ip.match_inlier_count = (uint32_t)res[i].n_points;
-                ip.match_inlier_ssd = (uint32_t)res[i].match_inlier_ssd;
-                Matrix3Type R;
-                for (int k = 0; k < 9; ++k) R.m[k] = res[i].R2in1[k];
-                ip.T_pair_to_base = SE3(SO3(R), Vector3Type(res[i].t2in1[0], res[i].t2in1[1], res[i].t2in1[2]));
+                // the reference starts the sum at uint32_t(-1) ("deliberate overflow", image-pair.cpp:38) and adds sqr(distance)
+                ip.match_inlier_ssd = (uint32_t)(0xFFFFFFFFu + (uint32_t)res[i].match_inlier_ssd);
+                ip.T_pair_to_base = SE3(SO3(b200::mat3_from(res[i].R2in1)), Vector3Type(res[i].t2in1[0], res[i].t2in1[1], res[i].t2in1[2]));
                 ip.matched_points.reserve(res[i].n_points);
                 for (int j = 0; j < res[i].n_points; ++j) {
                     const double *p = &pts[((size_t)i * cap + j) * 3];
                     const mvs_match &m = matches[(size_t)i * cap + idx[(size_t)i * cap + j]];
-                    ip.matched_points.push_back({Point3(p[0], p[1], p[2]), (size_t)m.train, (size_t)m.query});
+                    ip.matched_points.emplace_back(Point3(p[0], p[1], p[2]), (size_t)m.train, (size_t)m.query);
                 }
             }
             out.push_back(std::move(ip));
@@ -134,7 +154,7 @@ public:
     bool valid = false;
     int status = MVS_E_BAD_ARG;
     uint32_t match_inlier_count = 0;
-    uint32_t match_inlier_ssd = 0;
+    uint32_t match_inlier_ssd = 0xFFFFFFFFu;    // image-pair.cpp:38: (uint32_t)-1 until reconstruct() succeeds
     Transformation T_pair_to_base;
     std::vector<MatchedPoint> matched_points;
     // available after refine() (image-pair.hpp:66-69)

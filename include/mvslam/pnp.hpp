@@ -35,12 +35,10 @@ inline bool pnp_solve(const std::vector<Point3> &world_points, const std::vector
     }
     std::vector<uint8_t> mask(n);
     mvs_pnp_result r;
-    const int st = mvs_pnp_solve(ctx, w.data(), im.data(), n, K.m, &b200::pnp_defaults(), nullptr, &r, mask.data(), nullptr);
+    const int st = mvs_pnp_solve(ctx, w.data(), im.data(), n, b200::rm3(K).data(), &b200::pnp_defaults(), nullptr, &r, mask.data(), nullptr);
     b200::check(ctx, st, "pnp_solve");
     if (st != MVS_OK) return false;
-    Matrix3Type R;
-    for (int k = 0; k < 9; ++k) R.m[k] = r.R_c2w[k];
-    pose = SE3(SO3(R), Vector3Type(r.t_c2w[0], r.t_c2w[1], r.t_c2w[2]));
+    pose = SE3(SO3(b200::mat3_from(r.R_c2w)), Vector3Type(r.t_c2w[0], r.t_c2w[1], r.t_c2w[2]));
     inlier_point_indexes.clear();
     for (int i = 0; i < n; ++i) if (mask[i]) inlier_point_indexes.push_back((size_t)i);
     return true;

@@ -34,13 +34,11 @@ inline bool sfm_solve(const std::vector<ImagePoint> &p1, const std::vector<Image
     std::vector<double> pts((size_t)n * 3 + 3);
     std::vector<uint64_t> idx((size_t)n + 1);
     mvs_pair_result r;
-    int st = mvs_sfm_solve(ctx, a.data(), b.data(), n, K.m, &b200::ransac_defaults(), nullptr, &r, nullptr, pts.data(),
+    int st = mvs_sfm_solve(ctx, a.data(), b.data(), n, b200::rm3(K).data(), &b200::ransac_defaults(), nullptr, &r, nullptr, pts.data(),
                            idx.data(), n);
     b200::check(ctx, st, "sfm_solve");
     if (st != MVS_OK) return false;
-    Matrix3Type R;
-    for (int i = 0; i < 9; ++i) R.m[i] = r.R2in1[i];
-    pose2in1_scaled = SE3(SO3(R), Vector3Type(r.t2in1[0], r.t2in1[1], r.t2in1[2]));
+    pose2in1_scaled = SE3(SO3(b200::mat3_from(r.R2in1)), Vector3Type(r.t2in1[0], r.t2in1[1], r.t2in1[2]));
     pointsin1_scaled.resize(r.n_points);
     point_indexes.resize(r.n_points);
     for (int i = 0; i < r.n_points; ++i) {
@@ -62,9 +60,9 @@ inline void sfm_triangulate(const std::vector<ImagePoint> &p1, const std::vector
     std::vector<double> pts((size_t)n * 3 + 3);
     std::vector<uint64_t> idx((size_t)n + 1);
     int m = 0;
-    int st = mvs_sfm_triangulate(ctx, a.data(), b.data(), n, K.m, pose1.rotation().get_matrix().m, pose1.translation().v,
-                                 pose2.rotation().get_matrix().m, pose2.translation().v, b200::ransac_defaults().solver, pts.data(),
-                                 idx.data(), n, &m);
+    int st = mvs_sfm_triangulate(ctx, a.data(), b.data(), n, b200::rm3(K).data(), b200::rm3(pose1.rotation().get_matrix()).data(),
+                                 b200::v3(pose1.translation()).data(), b200::rm3(pose2.rotation().get_matrix()).data(),
+                                 b200::v3(pose2.translation()).data(), b200::ransac_defaults().solver, pts.data(), idx.data(), n, &m);
     b200::check(ctx, st, "sfm_triangulate");
     points.resize(m);
     point_indexes.resize(m);
@@ -79,8 +77,10 @@ inline bool find_fundamental_matrix(const std::vector<Vector3Type> &p1_sample, c
     mvs_ctx *ctx = b200::Context::thread_default().get();
     double a[24], b[24];
     for (int i = 0; i < 8; ++i) for (int k = 0; k < 3; ++k) { a[3 * i + k] = p1_sample[i][k]; b[3 * i + k] = p2_sample[i][k]; }
-    int st = mvs_find_fundamental_matrix(ctx, a, b, 1, b200::ransac_defaults().solver, F21.m);
+    double F[9];
+    int st = mvs_find_fundamental_matrix(ctx, a, b, 1, b200::ransac_defaults().solver, F);
     b200::check(ctx, st, "find_fundamental_matrix");
+    if (st == MVS_OK) F21 = b200::mat3_from(F);
     return st == MVS_OK;
 }
 
@@ -104,13 +104,13 @@ public:
         std::vector<uint8_t> mask((size_t)n + 1);
         const mvs_ransac_params rp{(int32_t)max_iteration, MVS_SCORE_ALGEBRAIC, max_error_sq, m_seed, 0,
                                    b200::ransac_defaults().solver, 0};
-        Matrix3Type F;
+        double F[9];
         int cnt = 0, bh = -1;
         double res = 0;
-        int st = mvs_ransac_fundamental(ctx, a.data(), b.data(), n, nullptr, &rp, F.m, mask.data(), &cnt, &res, &bh, nullptr);
+        int st = mvs_ransac_fundamental(ctx, a.data(), b.data(), n, nullptr, &rp, F, mask.data(), &cnt, &res, &bh, nullptr);
         b200::check(ctx, st, "FundamentalMatrixEstimatorRANSAC::compute");
         if (st == MVS_E_TOO_FEW_POINTS) return false;   // estimator-RANSAC.cpp:25-29
-        F21 = F;
+        F21 = b200::mat3_from(F);
         mask.resize(n);
         inlier_mask.swap(mask);
         return cnt > 0;                                  // :89

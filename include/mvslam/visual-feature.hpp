@@ -15,7 +15,7 @@ public:
                   int image_width, int image_height)
         : m_keypoints(std::move(kps)), m_descriptors(std::move(desc)), m_image_width(image_width), m_image_height(image_height)
     {
-        if (m_descriptors.size() != m_keypoints.size() * 32) throw b200::Error(MVS_E_BAD_ARG, "descriptor rows must be 32 bytes");
+        if (!b200::desc_ok(m_descriptors, m_keypoints.size())) throw b200::Error(MVS_E_BAD_ARG, "descriptor rows must be 32 contiguous bytes");
     }
 
     static constexpr int MAX_FEATURE_COUNT = 500;   // visual-feature.cpp:9
@@ -67,7 +67,7 @@ public:
                 KeyPoint &d = vf.m_keypoints[k];
                 d.pt.x = s.x; d.pt.y = s.y; d.size = s.size; d.angle = s.angle; d.response = s.response; d.octave = s.octave;
             }
-            vf.m_descriptors.assign(desc.begin() + at * 32, desc.begin() + (at + counts[i]) * 32);
+            vf.m_descriptors = b200::desc_make(desc.data() + at * 32, (size_t)counts[i]);
             at += (size_t)counts[i];
         }
         return out;
@@ -83,7 +83,7 @@ public:
         std::vector<mvs_match> out(vf2.size());
         int n = 0;
         const mvs_match_params mp{0.7, max_dist, 0, 1};   // bounded: identical matches, less work when max_dist >= 0
-        int st = mvs_match_hamming(ctx, vf2.m_descriptors.data(), (int)vf2.size(), vf1.m_descriptors.data(), (int)vf1.size(),
+        int st = mvs_match_hamming(ctx, b200::desc_data(vf2.m_descriptors), (int)vf2.size(), b200::desc_data(vf1.m_descriptors), (int)vf1.size(),
                                    32, &mp, out.data(), (int)out.size(), &n);
         b200::check(ctx, st, "match_visual_features");
         VisualFeatureConfig::MatchResultType r(n);
@@ -101,14 +101,17 @@ public:
         VisualFeature f1, f2;
         f1.m_image_width = f2.m_image_width = vf1.m_image_width;
         f1.m_image_height = f2.m_image_height = vf1.m_image_height;
+        std::vector<uint8_t> d1(matches.size() * 32), d2(matches.size() * 32);
+        const uint8_t *s1 = b200::desc_data(vf1.m_descriptors), *s2 = b200::desc_data(vf2.m_descriptors);
+        size_t r = 0;
         for (const auto &m : matches) {
             f1.m_keypoints.push_back(vf1.m_keypoints[m.trainIdx]);
-            f1.m_descriptors.insert(f1.m_descriptors.end(), vf1.m_descriptors.begin() + 32 * m.trainIdx,
-                                    vf1.m_descriptors.begin() + 32 * (m.trainIdx + 1));
             f2.m_keypoints.push_back(vf2.m_keypoints[m.queryIdx]);
-            f2.m_descriptors.insert(f2.m_descriptors.end(), vf2.m_descriptors.begin() + 32 * m.queryIdx,
-                                    vf2.m_descriptors.begin() + 32 * (m.queryIdx + 1));
+            for (int k = 0; k < 32; ++k) { d1[r * 32 + k] = s1[32 * (size_t)m.trainIdx + k]; d2[r * 32 + k] = s2[32 * (size_t)m.queryIdx + k]; }
+            ++r;
         }
+        f1.m_descriptors = b200::desc_make(d1.data(), matches.size());
+        f2.m_descriptors = b200::desc_make(d2.data(), matches.size());
         return std::make_pair(f1, f2);
     }
 
@@ -130,7 +133,7 @@ public:
         for (const auto &kp : m_keypoints) {
             const ScalarType sd = static_cast<ScalarType>(1 << kp.octave) * 0.5;
             Point2 mu; mu[0] = kp.pt.x; mu[1] = kp.pt.y;
-            Matrix2Type C; C(0, 0) = C(1, 1) = sd * sd;
+            Matrix2Type C = Matrix2Type::Zero(); C(0, 0) = C(1, 1) = sd * sd;
             r.emplace_back(mu, C);
         }
         return r;

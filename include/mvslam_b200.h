@@ -161,8 +161,10 @@ typedef struct {
     int32_t max_iterations;      /* <= 0: 100 (GTSAM default) */
     int32_t reserved;
     double  lambda_initial;      /* <= 0: 1e-5 (GTSAM default) */
-    double  relative_tolerance;  /* <= 0: 1e-13: stop when the cost decreases by less than this fraction
-                                    (GTSAM stops at 1e-5; iterating further only moves closer to the same minimum) */
+    double  relative_tolerance;  /* <= 0: 1e-5 (GTSAM relativeErrorTol): stop when the cost decreases by less than this fraction */
+    double  absolute_tolerance;  /* 0: 1e-5 (GTSAM absoluteErrorTol): stop when the cost decreases by less than this; < 0: no such test.
+                                    ba.cpp:124 builds LevenbergMarquardtOptimizer with default parameters, so zeros reproduce its
+                                    stopping rule; {1e-13, -1} iterates to the minimum itself (what the parity tests use) */
 } mvs_ba_params;
 
 typedef struct {
@@ -185,7 +187,8 @@ typedef struct {
 /* ---- context ---------------------------------------------------------------------------- */
 int  mvs_abi_version(void);
 const char *mvs_status_string(int status);
-/* Creates a context on CUDA device `device` with its own non-blocking stream.  Replaces the
+/* Creates a context on CUDA device `device` (negative: the calling thread's current device, cudaGetDevice -- what a rank of
+ * a multi-GPU job that has already selected its GPU wants) with its own non-blocking stream.  Replaces the
  * reference's hidden globals (static matcher visual-feature.cpp:12-25, global camera
  * camera-manager.cpp:10). */
 int  mvs_create(mvs_ctx **out, int device);

@@ -76,7 +76,7 @@ BA_RESULT_DTYPE = np.dtype([("status", np.int32), ("iterations", np.int32), ("in
 
 class BaParams(C.Structure):
     _fields_ = [("max_iterations", C.c_int32), ("reserved", C.c_int32), ("lambda_initial", C.c_double),
-                ("relative_tolerance", C.c_double)]
+                ("relative_tolerance", C.c_double), ("absolute_tolerance", C.c_double)]
 
 
 assert BA_OBS_DTYPE.itemsize == 48 and BA_RESULT_DTYPE.itemsize == 24
@@ -391,12 +391,12 @@ class Context:
                     X=cat("points", (-1, 3)), xc=cat("point_prior_cov", (-1, 9)),
                     obs=np.ascontiguousarray(np.concatenate([np.asarray(p["obs"], BA_OBS_DTYPE) for p in problems])))
 
-    def ba_solve_packed(self, K, pk, max_iterations=100, lambda_initial=1e-5, relative_tolerance=1e-13):
+    def ba_solve_packed(self, K, pk, max_iterations=100, lambda_initial=1e-5, relative_tolerance=1e-13, absolute_tolerance=-1.0):
         """One mvs_ba_solve_batch call on packed arrays; returns (results, R, t, pose_cov, points, point_cov) concatenated."""
         Ro = np.empty_like(pk["R"]); to = np.empty_like(pk["t"]); pco = np.empty_like(pk["pc"])
         Xo = np.empty_like(pk["X"]); xco = np.empty_like(pk["xc"])
         res = np.zeros(len(pk["nf"]), BA_RESULT_DTYPE)
-        bp = BaParams(max_iterations, 0, lambda_initial, relative_tolerance)
+        bp = BaParams(max_iterations, 0, lambda_initial, relative_tolerance, absolute_tolerance)
         self._check(self._L.mvs_ba_solve_batch(self._h, len(pk["nf"]), _p(_f64(K)), _p(pk["nf"]), _p(pk["npt"]), _p(pk["no"]),
                                                _p(pk["R"]), _p(pk["t"]), _p(pk["pc"]), _p(pk["X"]), _p(pk["xc"]), _p(pk["obs"]),
                                                C.byref(bp), _p(Ro), _p(to), _p(pco), _p(Xo), _p(xco), _p(res)))

@@ -22,7 +22,7 @@ static_assert(sizeof(mvs_pair_result) == 376, "mvs_pair_result layout is part of
 static_assert(sizeof(mvs_match) == 12, "mvs_match layout is part of the ABI");
 static_assert(sizeof(mvs_keypoint) == 24 && sizeof(mvs_orb_params) == 16, "extraction structs are part of the ABI");
 static_assert(sizeof(mvs_pnp_result) == 208 && sizeof(mvs_pnp_params) == 40, "pnp structs are part of the ABI");
-static_assert(sizeof(mvs_ba_observation) == 48 && sizeof(mvs_ba_result) == 24 && sizeof(mvs_ba_params) == 24, "BA structs are part of the ABI");
+static_assert(sizeof(mvs_ba_observation) == 48 && sizeof(mvs_ba_result) == 24 && sizeof(mvs_ba_params) == 32, "BA structs are part of the ABI");
 static_assert(MVS_N_STAGES == 16, "mvs_profile layout is part of the ABI (capi.py STAGES)");
 
 namespace {
@@ -389,6 +389,7 @@ int mvs_create(mvs_ctx **out, int device)
     *out = nullptr;
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return MVS_E_CUDA;  // no CPU fallback
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return MVS_E_CUDA;   // negative: the caller's current device
     if (device < 0 || device >= count) return MVS_E_BAD_ARG;
     if (cudaSetDevice(device) != cudaSuccess) return MVS_E_CUDA;
     cudaDeviceProp prop;
@@ -1471,7 +1472,8 @@ int mvs_ba_solve_batch(mvs_ctx *ctx, int n_problems, const double K[9],
     a.results = ctx->b_res.as<mvs_ba_result>();
     a.max_iter = params && params->max_iterations > 0 ? params->max_iterations : 100;
     a.lambda0 = params && params->lambda_initial > 0 ? params->lambda_initial : 1e-5;
-    a.rel_tol = params && params->relative_tolerance > 0 ? params->relative_tolerance : 1e-13;
+    a.rel_tol = params && params->relative_tolerance > 0 ? params->relative_tolerance : 1e-5;     // GTSAM relativeErrorTol
+    a.abs_tol = !params || params->absolute_tolerance == 0 ? 1e-5 : params->absolute_tolerance;    // GTSAM absoluteErrorTol; < 0: off
     {
         StageTimer t(ctx, MVS_STAGE_BA);
         CK(launch_ba(a, n_problems, ctx->stream));

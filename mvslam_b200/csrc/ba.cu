@@ -471,7 +471,7 @@ ba_solve_kernel(BaArgs a)
         }
         __syncthreads();
         if (tid < 12 * F) s_pose[tid] = s_cand[tid];
-        const double rel = (cost - cn) / fmax(cost, 1e-300);
+        const double rel = (cost - cn) / fmax(cost, 1e-300), absdec = cost - cn;
         cost = cn;
         // every thread needs the same verdict: max step over the block
         __syncthreads();
@@ -487,7 +487,8 @@ ba_solve_kernel(BaArgs a)
         }
         if (tid == 0) s_lambda = fmax(s_lambda / 10.0, 1e-12);
         __syncthreads();
-        if (rel < a.rel_tol || step < 1e-14) { ++it; break; }
+        // gtsam::checkConvergence: relative decrease < relativeErrorTol or absolute decrease < absoluteErrorTol
+        if (rel < a.rel_tol || (a.abs_tol >= 0.0 && absdec < a.abs_tol) || step < 1e-14) { ++it; break; }
     }
 
     // ---- marginal covariances at the result: inverse of the Gauss-Newton Hessian, by blocks

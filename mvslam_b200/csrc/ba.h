@@ -21,7 +21,7 @@ struct BaArgs {
     double *pose_R_out, *pose_t_out, *pose_cov_out, *points_out, *point_cov_out;
     mvs_ba_result *results;
     int max_iter;
-    double lambda0, rel_tol;
+    double lambda0, rel_tol, abs_tol;   // abs_tol < 0: no absolute test
 };
 
 cudaError_t launch_ba(const BaArgs &a, int n_problems, cudaStream_t s);

@@ -20,7 +20,7 @@ _default_ctx = None
 def default_context():
     global _default_ctx
     if _default_ctx is None:
-        _default_ctx = capi.Context(0)
+        _default_ctx = capi.Context(-1)      # the process's current CUDA device (torch.cuda.set_device / cudaSetDevice)
     return _default_ctx
 
 

@@ -51,7 +51,7 @@ def test_host_pnp_sample_table_matches_oracle():
 def test_struct_layouts_of_the_added_stages():
     assert mvs.KEYPOINT_DTYPE.itemsize == 24 and ctypes.sizeof(mvs.OrbParams) == 16
     assert mvs.PNP_RESULT_DTYPE.itemsize == 208 and ctypes.sizeof(mvs.PnpParams) == 40
-    assert mvs.BA_OBS_DTYPE.itemsize == 48 and mvs.BA_RESULT_DTYPE.itemsize == 24 and ctypes.sizeof(mvs.BaParams) == 24
+    assert mvs.BA_OBS_DTYPE.itemsize == 48 and mvs.BA_RESULT_DTYPE.itemsize == 24 and ctypes.sizeof(mvs.BaParams) == 32
     assert len(mvs.STAGES) == 16
 
 

@@ -678,6 +678,37 @@ def test_cpp_tools_reconstruct_scene_and_vo_pairs(tmp_path, tsukuba, tsukuba_gol
         assert np.allclose(t, [1, 0, 0], atol=1e-3)
 
 
+def test_reference_callers_verbatim_pod_and_eigen_shaped(tmp_path, tsukuba, tsukuba_golden):
+    """VisualOdometer::add_frame's pair construction (3-argument ImagePair, K from CameraManager) and reconstruct-scene's call
+    sequence, verbatim (tests/cpp/test_reference_callers.cpp), built against the POD stand-ins and against column-major
+    Eigen-shaped / cv-shaped types: identical output, and the reference-solver numbers of the committed goldens."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "tsu")
+    subprocess.run([sys.executable, os.path.join(root, "tools", "export_features.py"), "npz",
+                    os.path.join(root, "tests", "golden", "tsukuba_orb2000.npz"), out], check=True)
+    outs = []
+    for exe in ("test_reference_callers", "test_reference_callers_eigen"):
+        r = subprocess.run([os.path.join(root, "tests", "cpp", exe), out + "/1.mvsf", out + "/2.mvsf", out + "/camera.config"],
+                           capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs.append(r.stdout)
+    assert outs[0] == outs[1]                                  # storage order of the matrix type is invisible
+    lines = outs[0].splitlines()
+    gl = tsukuba_golden
+    n10 = len(gl["p12_md10_h1_indexes"])
+    ssd = (int((gl["p12_md10_d"][gl["p12_md10_h1_indexes"].astype(int)].astype(np.int64) ** 2).sum()) + 0xFFFFFFFF) & 0xFFFFFFFF
+    assert lines[0] == f"vo: valid 1 inliers {n10} ssd {ssd} points {n10}"
+    T = [float(x) for x in lines[1].split("T_pair_to_base")[1].replace("|", " ").split()]
+    assert np.array_equal(np.array(T[:9]).reshape(3, 3), gl["p12_md10_h1_R2in1"]) and np.array_equal(T[9:], gl["p12_md10_h1_t2in1"])
+    first = [float(x) for x in lines[2].split("first point")[1].split("idx")[0].split()]
+    assert np.array_equal(first, gl["p12_md10_h1_points"][0])
+    rs = lines[3].split()
+    assert int(rs[2]) == len(gl["p12_md30_q"]) and int(rs[4]) == len(gl["p12_md30_h1_indexes"])
+    assert np.array_equal([float(x) for x in rs[6:9]], gl["p12_md30_h1_t2in1"])
+
+
 def test_cpp_vo_tool_from_images(tmp_path):
     """tools/visual_odometer_pairs fed with the Tsukuba frames themselves (PGM): VisualFeature::extract on the device,
     then the per-frame pair batches; the 2000-feature run recovers the (I, (1, 0, 0)) motion of test-visual-odometer.cpp:98-102."""
