@@ -356,6 +356,30 @@ int mvs_pair_batch_enqueue(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, cons
                            mvs_pair_result *results, mvs_match *matches, uint8_t *inlier_mask,
                            double *points, uint64_t *indexes, int capacity);
 
+/* ---- multi-GPU: pairs are independent (image-pair.cpp:30-71,143), so the pair list is cut into contiguous slices, one per
+ *      rank (one process per GPU), every rank keeps the frame table resident, and the only communication is at the end:
+ *      one gather of the fixed-size records and one of the variable-length clouds, placed by the exclusive scan of the
+ *      per-pair counts.  NCCL (libnccl.so.2) is bound at run time; nothing here is needed on one GPU. */
+typedef struct mvs_comm mvs_comm;
+/* ncclGetUniqueId: call on one rank, hand the 128 bytes to the others by any means (file, environment, MPI, ...). */
+int  mvs_comm_unique_id(uint8_t id[128]);
+/* ncclCommInitRank on ctx's device; collective over the `world` ranks. */
+int  mvs_comm_create(mvs_comm **out, mvs_ctx *ctx, const uint8_t id[128], int rank, int world);
+void mvs_comm_destroy(mvs_comm *comm);
+/* contiguous slice [lo, hi) of n units owned by `rank` (sizes differ by at most one) */
+void mvs_shard_bounds(int64_t n, int world, int rank, int64_t *lo, int64_t *hi);
+/* Every rank passes the SAME full pair list (frames resident on every rank: mvs_frames_upload / mvs_orb_extract) and solves
+ * its slice; pair i samples with pair_id = pair_id_base + i whatever the sharding, so the gathered bytes equal a single-GPU
+ * run.  On `root`: results[n_pairs_total]; if point_offsets != NULL (all ranks must agree) also the clouds of all pairs,
+ * compacted: pair i owns points[point_offsets[i] .. point_offsets[i+1]) (and indexes, into that pair's matches);
+ * likewise matches through match_offsets.  offsets arrays have n_pairs_total + 1 entries.  MVS_E_CAPACITY (with the offsets
+ * filled) when a capacity is too small.  Other ranks may pass NULL for every output but must pass non-NULL offsets pointers
+ * (any small buffer) to take part in the second gather. */
+int  mvs_pair_batch_sharded(mvs_ctx *ctx, mvs_comm *comm, const int32_t *pairs, int64_t n_pairs_total, const double K[9],
+                            const mvs_match_params *mparams, const mvs_ransac_params *rparams, int root,
+                            mvs_pair_result *results, int64_t *point_offsets, double *points, uint64_t *indexes,
+                            int64_t point_capacity, int64_t *match_offsets, mvs_match *matches, int64_t match_capacity);
+
 #ifdef __cplusplus
 }
 #endif

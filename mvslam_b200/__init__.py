@@ -6,7 +6,7 @@ the benchmark.  There is no CPU fallback: everything here fails loudly when the 
 CUDA device is missing.
 """
 from .capi import (  # noqa: F401
-    Context, MvsError, PairResult, MatchParams, RansacParams, OrbParams, PnpParams, PNP_RESULT_DTYPE, BaParams, BA_OBS_DTYPE, BA_RESULT_DTYPE, pnp_sample_table, MATCH_DTYPE, RESULT_DTYPE, KEYPOINT_DTYPE,
+    Context, Comm, MvsError, PairResult, MatchParams, RansacParams, OrbParams, PnpParams, PNP_RESULT_DTYPE, BaParams, BA_OBS_DTYPE, BA_RESULT_DTYPE, pnp_sample_table, MATCH_DTYPE, RESULT_DTYPE, KEYPOINT_DTYPE,
     SCORE_ALGEBRAIC, SCORE_SAMPSON, OK, E_BAD_ARG, E_TOO_FEW_POINTS, E_NO_MODEL, E_TOO_FEW_INLIERS,
     E_NO_CHEIRALITY, E_CUDA, E_CAPACITY, E_UNSUPPORTED, STAGES, lib_path, load_library, sample_table,
 )

@@ -140,6 +140,58 @@ def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
+class Comm:
+    """mvs_comm: the NCCL communicator of the C-ABI multi-GPU driver (mvs_pair_batch_sharded).  The 128-byte id is made on
+    one rank (Comm.unique_id()) and handed to the others by any means (a file, torch.distributed, MPI ...)."""
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_uint8 * 128)()
+        st = load_library().mvs_comm_unique_id(buf)
+        if st != OK:
+            raise MvsError(st, "mvs_comm_unique_id (libnccl.so.2 not loadable?)")
+        return bytes(buf)
+
+    def __init__(self, ctx, uid, rank, world):
+        self._L = load_library()
+        self._ctx = ctx
+        self._h = C.c_void_p()
+        self.rank, self.world = rank, world
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        ctx._check(self._L.mvs_comm_create(C.byref(self._h), ctx._h, buf, int(rank), int(world)))
+
+    def close(self):
+        if self._h:
+            self._L.mvs_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def pair_batch_sharded(self, pairs, K, ratio=0.7, max_dist=-1.0, cross_check=False, H=1, seed=0, mode=SCORE_ALGEBRAIC,
+                           max_error_sq=0.0, solver=None, root=0, clouds=True, capacity_per_pair=None):
+        """Every rank passes the full pair list.  Returns on root (results, dict(point_offsets, points, indexes, match_offsets,
+        matches)) and (None, None) elsewhere."""
+        pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2); n = pairs.shape[0]
+        mp = MatchParams(ratio, max_dist, int(cross_check), 0)
+        rp = RansacParams(H, mode, max_error_sq, seed, 0, _solver(solver), 0)
+        is_root = self.rank == root
+        res = np.zeros(n, RESULT_DTYPE) if is_root else None
+        cap = int(capacity_per_pair if capacity_per_pair is not None else self._ctx._frame_counts.max())
+        po = np.zeros(n + 1, np.int64) if clouds else None
+        mo = np.zeros(n + 1, np.int64) if clouds else None
+        pts = idx = mat = None
+        if clouds and is_root:
+            pts = np.zeros((n * cap, 3)); idx = np.zeros(n * cap, np.uint64); mat = np.zeros(n * cap, MATCH_DTYPE)
+        st = self._L.mvs_pair_batch_sharded(self._ctx._h, self._h, _p(pairs), C.c_int64(n), _p(_f64(K)), C.byref(mp), C.byref(rp),
+                                            int(root), _p(res), _p(po), _p(pts), _p(idx), C.c_int64(n * cap if is_root else 0),
+                                            _p(mo), _p(mat), C.c_int64(n * cap if is_root else 0))
+        self._ctx._check(st)
+        if not is_root:
+            return None, None
+        det = None
+        if clouds:
+            det = dict(point_offsets=po, points=pts[:po[-1]], indexes=idx[:po[-1]], match_offsets=mo, matches=mat[:mo[-1]])
+        return res, det
+
+
 def pnp_sample_table(seed, problem_id, n_points, H):
     """Host copy of the device 4-point sampler (mvs_pnp_sample_table)."""
     out = np.empty((H, 4), np.uint32)

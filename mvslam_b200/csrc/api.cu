@@ -92,6 +92,7 @@ struct mvs_ctx {
     uint8_t *h_args = nullptr;
     cudaEvent_t arg_ev[kArgSlots] = {};
     int arg_next = 0;
+    int last_stride = 0;        // detail stride (largest pair frame) of the last pair_batch chunk: sharded.cu reads the device outputs
     bool allow_stage = false;   // set by the synchronous entry points only: _enqueue callers may synchronise the stream themselves
     struct StagedCopy { void *dst; size_t dpitch; size_t src_off; size_t width; size_t rows; };
     std::vector<StagedCopy> staged;
@@ -361,6 +362,17 @@ void flush_staged(mvs_ctx *ctx)     // call only after the stream has been synch
 bool unit_z_intrinsics(const double Ki[9]) { return Ki[6] == 0.0 && Ki[7] == 0.0; }
 
 }  // namespace
+
+// ---- accessors for the multi-GPU driver (sharded.cu), which lives in its own translation unit
+int mvs_ctx_device(const mvs_ctx *ctx) { return ctx->device; }
+cudaStream_t mvs_ctx_stream(const mvs_ctx *ctx) { return ctx->stream; }
+void mvs_ctx_set_error(mvs_ctx *ctx, const std::string &msg) { if (ctx) ctx->err = msg; }
+void mvs_ctx_last_outputs(mvs_ctx *ctx, const mvs_pair_result **res, const mvs_match **matches, const double **points,
+                          const uint64_t **indexes, int *stride)
+{
+    *res = ctx->d_results.as<mvs_pair_result>(); *matches = ctx->d_matches.as<mvs_match>(); *points = ctx->d_opts.as<double>();
+    *indexes = ctx->d_oidx.as<uint64_t>(); *stride = ctx->last_stride;
+}
 
 // ============================================================================================ C ABI
 extern "C" {
@@ -932,6 +944,7 @@ static int pair_batch_chunk(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, con
     if (st != MVS_OK) return st;
     CK(cudaSetDevice(ctx->device));
     const int qs = max_nq;
+    ctx->last_stride = qs;
     const bool cross = mparams && mparams->cross_check;
     const size_t table_rows = (size_t)ctx->h_off[nf - 1] + (size_t)ctx->h_cnt[nf - 1];
     const bool tc = tc_eligible(ctx, max_nq, max_nt, cross, table_rows);

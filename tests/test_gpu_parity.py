@@ -546,6 +546,61 @@ dist.barrier(); dist.destroy_process_group()
     assert multi.tobytes() == single.tobytes()
 
 
+def test_two_gpu_c_abi_sharded_with_clouds_equals_single_gpu(tmp_path, tsukuba):
+    """mvs_pair_batch_sharded (C ABI, NCCL bound at run time; no torch.distributed anywhere): two processes, one GPU each,
+    exchange the ncclUniqueId through a file; the gathered records AND the variable-length clouds (points, indexes, matches
+    placed by exclusive-scan offsets) must equal the single-GPU bytes.  Skipped on 1-GPU boxes."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "w.py"
+    script.write_text('''
+import os, sys, time
+sys.path.insert(0, sys.argv[1])
+import numpy as np
+import mvslam_b200 as mvs
+rank, world, idf, out = int(sys.argv[2]), int(sys.argv[3]), sys.argv[4], sys.argv[5]
+f = np.load(os.path.join(sys.argv[1], "tests", "golden", "tsukuba_orb2000.npz"))
+descs = [f[f"desc{i}"] for i in range(1, 6)]; kps = [f[f"kp{i}"] for i in range(1, 6)]
+pairs = np.array([(a, b) for a in range(5) for b in range(5) if a != b], np.int32)
+ctx = mvs.Context(rank)
+if rank == 0:
+    uid = mvs.Comm.unique_id()
+    open(idf + ".tmp", "wb").write(uid); os.rename(idf + ".tmp", idf)
+else:
+    while not os.path.exists(idf): time.sleep(0.05)
+    uid = open(idf, "rb").read()
+comm = mvs.Comm(ctx, uid, rank, world)
+ctx.frames_upload(descs, kps)
+res, det = comm.pair_batch_sharded(pairs, f["K"], max_dist=30.0, H=128, seed=11, solver="fast")
+if rank == 0:
+    np.savez(out, res=res, **det)
+comm.close(); ctx.close()
+''')
+    out = str(tmp_path / "multi.npz"); idf = str(tmp_path / "nccl.id")
+    procs = [subprocess.Popen([sys.executable, str(script), root, str(r), "2", idf, out]) for r in range(2)]
+    for p in procs:
+        assert p.wait(timeout=600) == 0
+    multi = np.load(out)
+    descs = [tsukuba[f"desc{i}"] for i in range(1, 6)]; kps = [tsukuba[f"kp{i}"] for i in range(1, 6)]
+    pairs = np.array([(a, b) for a in range(5) for b in range(5) if a != b], np.int32)
+    with mvs.Context(0) as c:
+        c.frames_upload(descs, kps)
+        single, det = c.pair_batch(pairs, tsukuba["K"], max_dist=30.0, H=128, seed=11, solver="fast")
+    assert multi["res"].tobytes() == single.tobytes()
+    po, mo = multi["point_offsets"], multi["match_offsets"]
+    for i in range(len(pairs)):
+        n = int(single[i]["n_points"]) if single[i]["status"] == 0 else 0
+        m = int(single[i]["n_matches"])
+        assert po[i + 1] - po[i] == n and mo[i + 1] - mo[i] == m
+        assert np.array_equal(multi["points"][po[i]:po[i + 1]], det["points"][i][:n])
+        assert np.array_equal(multi["indexes"][po[i]:po[i + 1]], det["indexes"][i][:n])
+        assert np.array_equal(multi["matches"][mo[i]:mo[i + 1]], det["matches"][i][:m])
+
+
 def test_pair_batch_large_batch_is_chunked_consistently(ctx, tsukuba):
     """More pairs than one launch carries (grid.z / workspace chunks of 8192): same records as small batches,
     sampling tied to the global pair index."""
