@@ -36,6 +36,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "matched+solved image pairs/sec (2k kpts)"
+# NCCL writes its version / debug lines to stdout unless told otherwise; stdout carries the one JSON line
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 
 # ------------------------------------------------------------------------------------------ workloads
@@ -524,58 +526,62 @@ def main():
         mine_p = wpairs[wlo:whi]
         wctx = mvs.Context(local, stream=stream.cuda_stream)
         wctx.frames_upload(wd, wk)
-        wres = torch.empty(len(mine_p) * item, dtype=torch.uint8).pin_memory()
         wkw = dict(max_dist=-1.0, H=1024, seed=0, mode=1, max_error_sq=0.0, solver="fast")
         WK = __import__("mvslam_b200.synth", fromlist=["synth"]).K_S8K
 
-        def wstep():
-            for c0 in range(0, len(mine_p), CH):
-                c1 = min(len(mine_p), c0 + CH)
-                wctx.pair_batch(mine_p[c0:c1], WK, out=dict(results=wres.data_ptr() + c0 * item), enqueue_only=True, pair_id_base=wlo + c0, **wkw)
-        wstep(); torch.cuda.synchronize()
-        wg_cap = max(shard.shard_bounds(len(wpairs), world, r)[1] - shard.shard_bounds(len(wpairs), world, r)[0] for r in range(world)) * item
-        wg_dev = torch.empty(wg_cap, dtype=torch.uint8, device="cuda")
-        wg_bucket = [torch.empty(wg_cap, dtype=torch.uint8, device="cuda") for _ in range(world)] if rank == 0 else None
-        wg_host = torch.empty(world * wg_cap, dtype=torch.uint8).pin_memory() if rank == 0 else None
-
-        def wgather():
-            wg_dev[:wres.numel()].copy_(wres, non_blocking=True)
-            dist.gather(wg_dev, wg_bucket, dst=0)
-            if rank == 0:
-                for r in range(world):
-                    wg_host[r * wg_cap:(r + 1) * wg_cap].copy_(wg_bucket[r], non_blocking=True)
+        # the C++ driver behind the C ABI (csrc/sharded.cu): every rank passes the full pair list, solves its contiguous slice
+        # and the records are gathered on rank 0 over NCCL (bound at run time) -- no Python in the data path
         if world > 1:
-            wgather(); torch.cuda.synchronize(); dist.barrier()
+            uid = [mvs.Comm.unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            wcomm = mvs.Comm(wctx, uid[0], rank, world)
+        else:
+            wcomm = mvs.Comm(wctx, mvs.Comm.unique_id(), 0, 1)
+
+        wpin = torch.empty(len(wpairs) * item, dtype=torch.uint8).pin_memory() if rank == 0 else None
+        wview = np.frombuffer(wpin.numpy(), dtype=mvs.RESULT_DTYPE) if rank == 0 else None
+
+        def wjob():
+            return wcomm.pair_batch_sharded(wpairs, WK, clouds=False, results_out=wview, **wkw)[0]
+        wjob(); torch.cuda.synchronize()
         wctx.profile_enable(True); wctx.profile_read(reset=True)
         wn = 3
-        wev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(wn)]
-        for a, b, c in wev:
+        job_ms = []
+        for _ in range(wn):
             if world > 1:
                 dist.barrier()
-            a.record(stream); wstep(); b.record(stream)
-            if world > 1:
-                wgather()
-            c.record(stream)
-        torch.cuda.synchronize()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter(); wall = wjob(); job_ms.append((time.perf_counter() - t0) * 1e3)
         wprof = wctx.profile_read(); wctx.profile_enable(False)
-        job_ms = [a.elapsed_time(c) for a, b, c in wev]; gat_ms = [b.elapsed_time(c) for a, b, c in wev]
         mine_ms = float(np.median(job_ms)); knn_rank = wprof["knn"][0] / wn
+        compute_ms = sum(wprof[s_][0] for s_ in mvs.STAGES[:7]) / wn
         if world > 1:
-            t = torch.tensor([mine_ms, knn_rank, -knn_rank], device="cuda", dtype=torch.float64)
+            t = torch.tensor([mine_ms, knn_rank, -knn_rank, compute_ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            mine_ms, knn_max, knn_min = float(t[0]), float(t[1]), -float(t[2])
+            mine_ms, knn_max, knn_min, compute_ms = float(t[0]), float(t[1]), -float(t[2]), float(t[3])
         else:
             knn_max = knn_min = knn_rank
-        wr = np.frombuffer(wres.numpy(), dtype=mvs.RESULT_DTYPE)
-        w512 = dict(what="BASELINE config 5: all unordered pairs of a 512-frame window (2048 kpts), pair list split contiguously over the "
-                         "ranks (strong scaling), records gathered on rank 0 (NCCL) inside the timed region",
+        gat_ms = [max(0.0, m - compute_ms) for m in job_ms]
+        wr = wall[wlo:whi] if rank == 0 else None
+        # on hardware, every run: the gathered records of another rank's slice equal what rank 0 computes for the same pairs
+        if world > 1 and rank == 0:
+            l1, h1 = shard.shard_bounds(len(wpairs), world, 1)
+            nchk = min(512, h1 - l1)
+            chk, _ = wctx.pair_batch(wpairs[l1:l1 + nchk], WK, pair_id_base=l1, details=False, **wkw)
+            sharded_check = dict(headline_weak_batch=sharded_check,
+                                 w512=dict(pairs_compared=int(nchk), via="mvs_pair_batch_sharded (C ABI, NCCL)",
+                                           rank1_records_equal_rank0_recomputation=bool(chk.tobytes() == wall[l1:l1 + nchk].tobytes())))
+        wcomm.close()
+        w512 = dict(what="BASELINE config 5: all unordered pairs of a 512-frame window (2048 kpts) through mvs_pair_batch_sharded (C++ driver "
+                         "behind the C ABI): pair list split contiguously over the ranks (strong scaling), records gathered on rank 0 over "
+                         "NCCL and copied to the host inside the timed region (host wall clock, max over ranks)",
                     frames=nfr, pairs_total=int(len(wpairs)), pairs_this_rank=int(len(mine_p)), hypotheses=1024, solver="fast", score="sampson",
-                    job_ms=mine_ms, job_ms_rank0=step_stats(job_ms), gather_ms_rank0=step_stats(gat_ms) if world > 1 else None,
+                    job_ms=mine_ms, job_ms_rank0=step_stats(job_ms), compute_ms_max_rank=compute_ms,
+                    gather_and_copy_ms_rank0=step_stats(gat_ms),
                     value=len(wpairs) / (mine_ms * 1e-3), unit="pairs/s", knn_ms_per_rank=dict(max=knn_max, min=knn_min),
-                    solved_pairs_this_rank=int((wr["status"] == 0).sum()),
+                    solved_pairs_this_rank=int((wr["status"] == 0).sum()) if wr is not None else None,
                     stage_ms_rank0={s: round(wprof[s][0] / wn, 3) for s in mvs.STAGES[:7]})
         wctx.close()
-        del wg_dev, wres
 
     # ---- optional extra: the same workload with the opt-in early-abandon matcher (integer-pipe kernel only)
     bounded_extra = None
@@ -861,8 +867,8 @@ def e2e_distinct_block(mvs, torch, local, flush, n_pairs=1024, chunk=256, n_ctx=
     # host <-> device copy rate of this box for buffers of this size (pinned), one direction at a time
     dbuf = torch.empty(D.numel(), dtype=torch.uint8, device="cuda")
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    dbuf.copy_(D, non_blocking=True); torch.cuda.synchronize()
-    ev0.record(); dbuf.copy_(D, non_blocking=True); ev1.record(); torch.cuda.synchronize()
+    dbuf.copy_(D.view(-1), non_blocking=True); torch.cuda.synchronize()
+    ev0.record(); dbuf.copy_(D.view(-1), non_blocking=True); ev1.record(); torch.cuda.synchronize()
     h2d_gbs = D.numel() / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
     del dbuf
     mat_t = torch.empty(n_pairs * cap * 12, dtype=torch.uint8).pin_memory(); msk_t = torch.empty(n_pairs * cap, dtype=torch.uint8).pin_memory()

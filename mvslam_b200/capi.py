@@ -166,14 +166,15 @@ class Comm:
             self._h = C.c_void_p()
 
     def pair_batch_sharded(self, pairs, K, ratio=0.7, max_dist=-1.0, cross_check=False, H=1, seed=0, mode=SCORE_ALGEBRAIC,
-                           max_error_sq=0.0, solver=None, root=0, clouds=True, capacity_per_pair=None):
+                           max_error_sq=0.0, solver=None, root=0, clouds=True, capacity_per_pair=None, results_out=None):
         """Every rank passes the full pair list.  Returns on root (results, dict(point_offsets, points, indexes, match_offsets,
-        matches)) and (None, None) elsewhere."""
+        matches)) and (None, None) elsewhere.  results_out: a caller-owned array of n RESULT_DTYPE records (e.g. a view of pinned
+        memory) for the root's records instead of a fresh pageable one."""
         pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2); n = pairs.shape[0]
         mp = MatchParams(ratio, max_dist, int(cross_check), 0)
         rp = RansacParams(H, mode, max_error_sq, seed, 0, _solver(solver), 0)
         is_root = self.rank == root
-        res = np.zeros(n, RESULT_DTYPE) if is_root else None
+        res = (results_out if results_out is not None else np.zeros(n, RESULT_DTYPE)) if is_root else None
         cap = int(capacity_per_pair if capacity_per_pair is not None else self._ctx._frame_counts.max())
         po = np.zeros(n + 1, np.int64) if clouds else None
         mo = np.zeros(n + 1, np.int64) if clouds else None

@@ -92,6 +92,7 @@ struct mvs_ctx {
     uint8_t *h_args = nullptr;
     cudaEvent_t arg_ev[kArgSlots] = {};
     int arg_next = 0;
+    bool skip_d2h = false;      // pair_batch_chunk leaves every output on the device (mvs_pair_batch_device_only)
     int last_stride = 0;        // detail stride (largest pair frame) of the last pair_batch chunk: sharded.cu reads the device outputs
     bool allow_stage = false;   // set by the synchronous entry points only: _enqueue callers may synchronise the stream themselves
     struct StagedCopy { void *dst; size_t dpitch; size_t src_off; size_t width; size_t rows; };
@@ -1000,6 +1001,7 @@ static int pair_batch_chunk(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, con
     }
     if ((st = run_geometry(ctx, n_pairs, qs, rc, unit_z, fa.Kinv[8], fa.Kinv[8], nullptr, rc.pair_base, true, false, ctx->d_matches.as<mvs_match>())) != MVS_OK) return st;
 
+    if (ctx->skip_d2h) return MVS_OK;
     // Small batches whose outputs go to pageable memory are staged through pinned memory: one synchronisation for all
     // copies instead of one blocking copy each (a single VO pair drops from ~280 us to ~170 us per call).
     const size_t w = (size_t)std::min(capacity, qs);
@@ -1039,6 +1041,18 @@ static int pair_batch_chunk(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, con
     if (points) CK(d2h_rows(ctx, stage, points, (size_t)capacity * 24, ctx->d_opts.p, (size_t)qs * 24, wc * 24, (size_t)n_pairs));
     if (indexes) CK(d2h_rows(ctx, stage, indexes, (size_t)capacity * 8, ctx->d_oidx.p, (size_t)qs * 8, wc * 8, (size_t)n_pairs));
     return MVS_OK;
+}
+
+// one chunk (<= 8192 pairs), every output left in the ctx's device workspace (read back through mvs_ctx_last_outputs)
+int mvs_pair_batch_device_only(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, const double K[9], const mvs_match_params *mparams,
+                               const mvs_ransac_params *rparams)
+{
+    if (!ctx || !pairs || n_pairs < 1 || n_pairs > 8192 || !K) return MVS_E_BAD_ARG;
+    ctx->skip_d2h = true;
+    mvs_pair_result dummy;
+    const int st = pair_batch_chunk(ctx, pairs, n_pairs, K, mparams, rparams, &dummy, nullptr, nullptr, nullptr, nullptr, 0);
+    ctx->skip_d2h = false;
+    return st;
 }
 
 // grow a device buffer geometrically, keeping the first n_used elements (device-to-device copy on the ctx stream)

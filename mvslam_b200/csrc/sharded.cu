@@ -19,6 +19,8 @@
 
 using namespace mvs;
 
+extern "C" int mvs_pair_batch_device_only(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, const double K[9],
+                                          const mvs_match_params *mparams, const mvs_ransac_params *rparams);
 int mvs_ctx_device(const mvs_ctx *ctx);
 cudaStream_t mvs_ctx_stream(const mvs_ctx *ctx);
 void mvs_ctx_set_error(mvs_ctx *ctx, const std::string &msg);
@@ -172,7 +174,7 @@ int mvs_pair_batch_sharded(mvs_ctx *ctx, mvs_comm *c, const int32_t *pairs, int6
     const int64_t n_local = hi - lo;
     // ---- this rank's slice, chunk by chunk; records, and compacted details, accumulate on the device
     CKC(c->rec.ensure((size_t)std::max<int64_t>(n_local, 1) * sizeof(mvs_pair_result)));
-    std::vector<mvs_pair_result> h_rec((size_t)n_local);
+    std::vector<mvs_pair_result> h_rec((want_pts || want_mat) ? (size_t)n_local : 0);
     std::vector<int32_t> h_cnt;
     std::vector<int64_t> h_off;
     int64_t pts_used = 0, mat_used = 0;
@@ -181,7 +183,10 @@ int mvs_pair_batch_sharded(mvs_ctx *ctx, mvs_comm *c, const int32_t *pairs, int6
         const int n = (int)std::min(kChunk, n_local - c0);
         mvs_ransac_params rp = rparams ? *rparams : mvs_ransac_params{1, MVS_SCORE_ALGEBRAIC, 0.0, 0, 0, 0, 0};
         rp.pair_id_base += (uint64_t)(lo + c0);       // sampling is keyed by the GLOBAL pair index: results do not depend on the sharding
-        int st = mvs_pair_batch_enqueue(ctx, pairs + 2 * (lo + c0), n, K, mparams, &rp, h_rec.data() + c0, nullptr, nullptr, nullptr, nullptr, 0);
+        // records stay on the device unless the sizes of the variable-length parts are needed here
+        int st = (want_pts || want_mat)
+                     ? mvs_pair_batch_enqueue(ctx, pairs + 2 * (lo + c0), n, K, mparams, &rp, h_rec.data() + c0, nullptr, nullptr, nullptr, nullptr, 0)
+                     : mvs_pair_batch_device_only(ctx, pairs + 2 * (lo + c0), n, K, mparams, &rp);
         if (st != MVS_OK) return st;
         const mvs_pair_result *d_res; const mvs_match *d_mat; const double *d_pts; const uint64_t *d_idx; int stride;
         mvs_ctx_last_outputs(ctx, &d_res, &d_mat, &d_pts, &d_idx, &stride);

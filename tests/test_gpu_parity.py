@@ -764,6 +764,32 @@ def test_reference_callers_verbatim_pod_and_eigen_shaped(tmp_path, tsukuba, tsuk
     assert np.array_equal([float(x) for x in rs[6:9]], gl["p12_md30_h1_t2in1"])
 
 
+def test_cpp_reconstruct_window_tool_sharded(tmp_path, tsukuba):
+    """tools/reconstruct_window: the all-pairs job of BASELINE config 5 as a C++ program over the C ABI, one process per GPU
+    (one here, two when the box has them): same records whatever the number of ranks."""
+    import subprocess
+    import sys
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "tsu")
+    subprocess.run([sys.executable, os.path.join(root, "tools", "export_features.py"), "npz",
+                    os.path.join(root, "tests", "golden", "tsukuba_orb2000.npz"), out], check=True)
+    exe = os.path.join(root, "tools", "reconstruct_window")
+    outs = []
+    for world in ([1, 2] if torch.cuda.device_count() >= 2 else [1]):
+        idf = str(tmp_path / f"id{world}")
+        procs = [subprocess.Popen([exe, out, "5", idf, str(r), str(world), "30", "1"], stdout=subprocess.PIPE, text=True) for r in range(world)]
+        texts = [p.communicate(timeout=300)[0] for p in procs]
+        assert all(p.returncode == 0 for p in procs), texts
+        outs.append(texts[0].splitlines())
+    head = outs[0][0]
+    assert "pairs = 10" in head and "solved = 10" in head
+    o = orc.image_pair(tsukuba["desc1"], tsukuba["kp1"], tsukuba["desc2"], tsukuba["kp2"], tsukuba["K"], max_dist=30.0)
+    assert f"matches {o['n_matches']} points {o['n_points']}" in outs[0][1]
+    for other in outs[1:]:      # identical per-pair lines (the head line carries the rank count and the wall time)
+        assert other[1:] == outs[0][1:] and other[0].split(",")[1:4] == head.split(",")[1:4]
+
+
 def test_cpp_vo_tool_from_images(tmp_path):
     """tools/visual_odometer_pairs fed with the Tsukuba frames themselves (PGM): VisualFeature::extract on the device,
     then the per-frame pair batches; the 2000-feature run recovers the (I, (1, 0, 0)) motion of test-visual-odometer.cpp:98-102."""
