@@ -52,7 +52,7 @@ constexpr int TC_THREADS = (A_WARP + 1) * 32;
 constexpr int NACC = 2 * RB;         // TMEM accumulator buffers: double-buffered per row block
 constexpr uint32_t TMEM_COLS = NACC * BN;
 constexpr int TC_SPLITS = 2;         // partial results per query: one per column half
-constexpr int TC_MAX_TRAIN = 32768;  // trainIdx field of the thread's running key (hamming * 32768 + trainIdx)
+constexpr int TC_MAX_TRAIN = (int)kIdxMask;  // the thread's running key is already the export format (hamming << 22 | trainIdx)
 
 // ------------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -166,13 +166,13 @@ expand_desc_kernel(const uint32_t *__restrict__ desc, size_t word_begin, size_t 
 //      k16 = 128 (128 - hamming) + (63 - c')          in [-16384, 16447]
 // orders the columns of the half by (smaller distance, then smaller index) under MAX; one three-input VIMNMX.S16x2 folds
 // two registers (four accumulators) into the running maxima of their streams.  At the end of a tile the two best of the four
-// stream maxima are widened to  hamming * 32768 + trainIdx  and merged into the thread's 32-bit pair (minimum = best).
+// stream maxima are widened to  hamming << 22 | trainIdx  and merged into the thread's 32-bit pair (minimum = best).
 // (Measured alternative: a ninth K step over a constant slab that adds the index inside the MMA -- no epilogue
 // instruction at all, but 12.5 % more tensor work on a kernel whose tensor pipe is 88 % busy.)
 __device__ __forceinline__ uint32_t widen_key(uint32_t k16, uint32_t tile_base /* first column of the thread's half */)
 {
     const int k = (int)(short)k16;                         // empty lane: -32768 -> distance 384, dropped at the export
-    return (uint32_t)(128 - (k >> 7)) * 32768u + tile_base + (63u - ((uint32_t)k & 127u));
+    return ((uint32_t)(128 - (k >> 7)) << kIdxBits) + tile_base + (63u - ((uint32_t)k & 127u));
 }
 
 // Persistent kernel: one CTA per SM walks the (pair, 256-row query tile) items of the batch with a stride of gridDim.x.
@@ -388,8 +388,8 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
                 top2(g1, g2, widen_key(m2 & 0xFFFFu, tile_base));
             }
             if (q < it.nq) {
-                const uint32_t x1 = (g1 >> 15) > 256u ? kKeyNone : (((g1 >> 15) << kIdxBits) | (g1 & 32767u));
-                const uint32_t x2 = (g2 >> 15) > 256u ? kKeyNone : (((g2 >> 15) << kIdxBits) | (g2 & 32767u));
+                const uint32_t x1 = (g1 >> kIdxBits) > 256u ? kKeyNone : g1;
+                const uint32_t x2 = (g2 >> kIdxBits) > 256u ? kKeyNone : g2;
                 a.partial[((size_t)it.pair * TC_SPLITS + half) * a.q_stride + q] = make_uint2(x1, x2);
             }
         }

@@ -135,14 +135,21 @@ def test_tensor_matcher_second_neighbour_is_a_stream_mate(ctx, cross):
         assert np.array_equal(mg, as_mvs(mo))
 
 
-def test_more_than_32768_train_descriptors_take_the_popc_kernel(ctx):
-    """The tensor-core epilogue key holds 15 index bits; larger train sets run on knn2_hamming_kernel."""
+def test_more_than_32768_train_descriptors_stay_on_the_tensor_cores(ctx, ctx_popc):
+    """The tensor-core epilogue key is `hamming << 22 | trainIdx` (22 index bits, the library-wide limit): train sets beyond
+    32768 rows -- round 1's limit -- run on knn2_hamming_tc_kernel too, with the same bytes as the integer-pipe kernel."""
     rng = np.random.default_rng(9)
     q = rng.integers(0, 256, (200, 32), dtype=np.uint8); t = rng.integers(0, 256, (33000, 32), dtype=np.uint8)
     t[32900] = q[5]
     ig, dg = ctx.knn2_hamming(q, t)
     io, do = orc.knn2_hamming(q, t)
     assert np.array_equal(ig, io) and np.array_equal(dg, do) and ig[5, 0] == 32900
+    ip, dp = ctx_popc.knn2_hamming(q, t)
+    assert np.array_equal(ig, ip) and np.array_equal(dg, dp)
+    ctx.profile_enable(True); ctx.profile_read(reset=True)
+    ctx.knn2_hamming(q, t)
+    assert ctx.profile_read()["knn"][1] == 2        # expand + tensor-core kernel (the popc path is one launch)
+    ctx.profile_enable(False)
 
 
 def test_pair_batch_records_identical_on_both_matchers(ctx, ctx_popc, tsukuba):
