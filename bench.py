@@ -839,13 +839,30 @@ def l2_block(ctx, mvs, peaks_m):
         st = ctx.l2_stats(); st["wall_ms"] = wall * 1e3
         runs.append(st)
     best = min(runs[1:], key=lambda s: s["total_us"])
+    # the same call with the descriptors (and the outputs) resident in HBM
+    import torch
+    dq, dt = torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda()
+    di = torch.empty((n, 2), dtype=torch.int32, device="cuda"); dd = torch.empty((n, 2), dtype=torch.float32, device="cuda")
+    res_runs = []
+    for _ in range(4):
+        ctx.knn2_l2_ptr(dq.data_ptr(), n, dt.data_ptr(), n, 64, di.data_ptr(), dd.data_ptr())
+        res_runs.append(ctx.l2_stats())
+    rbest = min(res_runs[1:], key=lambda s: s["total_us"])
+    idx_h, _ = ctx.knn2_l2(q, t)
+    same = bool(np.array_equal(di.cpu().numpy(), idx_h))
     flops = 2.0 * n * n * 64
     tf32_peak = peaks_m["bf16_tflops"] / 2.0
     return dict(n=n, dim=64, gemm_ms=best["gemm_us"] / 1e3, call_device_ms=best["total_us"] / 1e3, call_wall_ms=best["wall_ms"],
                 gemm_tflops=flops / (best["gemm_us"] * 1e-6) / 1e12, call_tflops=flops / (best["total_us"] * 1e-6) / 1e12,
                 peak_tflops=tf32_peak, peak_source=f"{peaks_m['source']}: bf16 / 2 (TF32)", gemm_frac=flops / (best["gemm_us"] * 1e-6) / 1e12 / tf32_peak,
                 call_frac=flops / (best["total_us"] * 1e-6) / 1e12 / tf32_peak, exact_fallback_queries=best["fallback_fwd"],
-                note="call_wall_ms includes the H2D of both 8 MB descriptor sets and the D2H of the top-2 lists")
+                resident=dict(call_device_ms=rbest["total_us"] / 1e3, call_tflops=flops / (rbest["total_us"] * 1e-6) / 1e12,
+                              call_frac=flops / (rbest["total_us"] * 1e-6) / 1e12 / tf32_peak, same_indices_as_host_call=same,
+                              note="descriptors and outputs resident in HBM (device pointers through the same entry point): norms + GEMM + "
+                                   "re-rank + fallback check + sqrt"),
+                note="call_device_ms / call_wall_ms with host buffers include the upload of both 8 MB descriptor sets from pageable memory "
+                     "(~1.0 ms of the 1.44) and the download of the top-2 lists; kernels: norms 2 x 12 us, GEMM 347, re-rank 55, fallback "
+                     "check 20, sqrt 3 (ncu launch list, profiles/l2_launches_r2.csv)")
 
 
 def e2e_distinct_block(mvs, torch, local, flush, n_pairs=1024, chunk=256, n_ctx=4):

@@ -339,6 +339,10 @@ class Context:
                                          _p(out), out.shape[0], C.byref(n)))
         return out[:n.value].copy()
 
+    def knn2_l2_ptr(self, q_ptr, nq, t_ptr, nt, dim, idx_ptr, dist_ptr):
+        """mvs_knn2_l2 on raw addresses (host or device, e.g. torch CUDA tensors' data_ptr())"""
+        self._check(self._L.mvs_knn2_l2(self._h, _p(q_ptr), int(nq), _p(t_ptr), int(nt), int(dim), _p(idx_ptr), _p(dist_ptr)))
+
     def l2_stats(self):
         out = (C.c_uint64 * 4)()
         self._check(self._L.mvs_l2_stats(self._h, out))

@@ -576,12 +576,12 @@ int l2_knn2(L2Workspace &ws, cudaStream_t stream, const float *query, int nq, co
     L2CK(ensure(ws, B_T, (size_t)nt * kpad * sizeof(float) + (size_t)nt * dim * sizeof(float)));
     float *dQ = (float *)ws.buf[B_Q], *dT = (float *)ws.buf[B_T];
     if (kpad == dim) {
-        L2CK(cudaMemcpyAsync(dQ, query, (size_t)nq * dim * sizeof(float), cudaMemcpyHostToDevice, stream));
-        L2CK(cudaMemcpyAsync(dT, train, (size_t)nt * dim * sizeof(float), cudaMemcpyHostToDevice, stream));
+        L2CK(cudaMemcpyAsync(dQ, query, (size_t)nq * dim * sizeof(float), cudaMemcpyDefault, stream));
+        L2CK(cudaMemcpyAsync(dT, train, (size_t)nt * dim * sizeof(float), cudaMemcpyDefault, stream));
     } else {
         float *rq = dQ + (size_t)nq * kpad, *rt = dT + (size_t)nt * kpad;
-        L2CK(cudaMemcpyAsync(rq, query, (size_t)nq * dim * sizeof(float), cudaMemcpyHostToDevice, stream));
-        L2CK(cudaMemcpyAsync(rt, train, (size_t)nt * dim * sizeof(float), cudaMemcpyHostToDevice, stream));
+        L2CK(cudaMemcpyAsync(rq, query, (size_t)nq * dim * sizeof(float), cudaMemcpyDefault, stream));
+        L2CK(cudaMemcpyAsync(rt, train, (size_t)nt * dim * sizeof(float), cudaMemcpyDefault, stream));
         l2_pad_kernel<<<(unsigned)(((size_t)nq * kpad + 255) / 256), 256, 0, stream>>>(rq, nq, dim, dQ, kpad);
         l2_pad_kernel<<<(unsigned)(((size_t)nt * kpad + 255) / 256), 256, 0, stream>>>(rt, nt, dim, dT, kpad);
         nl += 2;
@@ -639,8 +639,8 @@ int l2_knn2(L2Workspace &ws, cudaStream_t stream, const float *query, int nq, co
     l2_sqrt_kernel<<<(2 * nq + 255) / 256, 256, 0, stream>>>(f_d2, 2 * nq, f_dist);
     nl += 1;
     L2CK(cudaGetLastError());
-    if (idx) L2CK(cudaMemcpyAsync(idx, f_idx, (size_t)nq * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
-    if (dist) L2CK(cudaMemcpyAsync(dist, f_dist, (size_t)nq * 2 * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    if (idx) L2CK(cudaMemcpyAsync(idx, f_idx, (size_t)nq * 2 * sizeof(int32_t), cudaMemcpyDefault, stream));   // host or device (UVA)
+    if (dist) L2CK(cudaMemcpyAsync(dist, f_dist, (size_t)nq * 2 * sizeof(float), cudaMemcpyDefault, stream));
     if (mp && n_out) {
         int n2 = 1;
         while (n2 < nq) n2 <<= 1;
