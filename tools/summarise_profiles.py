@@ -45,7 +45,8 @@ def stall_summary(rep):
 lines = [f"# ncu summaries ({R})", "",
          "Captured on one B200 with `tools/collect_profiles.sh` (`ncu --set full --clock-control none --import-source on`),",
          "after the same command had exited 0 without ncu.  Values are per launch; ncu times are cold-cache and serialised.", ""]
-for rep, title in ((f"prof_path_{R}.ncu-rep", "two-view path (bench.py default workload, 1024 Tsukuba pairs, H=1024)"),
+for rep, title in ((f"prof_path_{R}.ncu-rep", "two-view path (bench.py default workload, 1024 Tsukuba pairs, " + ("H=1024)" if R == "r1" else "H=1, REFERENCE solver)")),
+                   (f"prof_fast_{R}.ncu-rep", "FAST solver, H=1024 on the same pairs (bench.py --solver fast --hypotheses 1024): hypotheses / score / triangulate"),
                    (f"prof_score_s8k_{R}.ncu-rep", "score_kernel on the S8k workload (64 pairs x 8192 kpts, H=4096, Sampson)"),
                    (f"prof_l2_{R}.ncu-rep", "l2_gemm_topk_kernel, 32768 x 32768 x 64 float descriptors"),
                    (f"prof_orb_{R}.ncu-rep", "feature extraction (tools/orb_bench.py: 256 Tsukuba frames per call, nfeatures 2000)"),
