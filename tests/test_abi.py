@@ -109,3 +109,20 @@ def test_tensor_matcher_sass_uses_tcgen05_tma_and_tmem():
     for mnemonic in ("UTCIMMA", "UTMALDG", "LDTM", "PACK16BIT", "VIMNMX.S16x2", "UTCBAR"):
         assert mnemonic in body, f"{mnemonic} missing from knn2_hamming_tc_kernel"
     assert "sm_100a" in out or "sm_100" in out
+
+
+def test_shard_bounds_host_function_matches_python():
+    """mvs_shard_bounds (csrc/sharded.cu) is pure host code: same contiguous slices as mvslam_b200.shard.shard_bounds"""
+    import ctypes
+    from mvslam_b200 import shard
+    L = mvs.load_library()
+    for n in (0, 1, 7, 8, 130816):
+        for world in (1, 2, 3, 8):
+            covered = 0
+            for r in range(world):
+                lo, hi = ctypes.c_int64(), ctypes.c_int64()
+                L.mvs_shard_bounds(ctypes.c_int64(n), world, r, ctypes.byref(lo), ctypes.byref(hi))
+                assert (lo.value, hi.value) == shard.shard_bounds(n, world, r)
+                assert lo.value == covered
+                covered = hi.value
+            assert covered == n

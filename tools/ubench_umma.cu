@@ -72,6 +72,17 @@ __global__ void __launch_bounds__(WRITERS >= 32 ? 96 : 64 + WRITERS * 32 + (WRIT
         const long long t0 = clock64();
         for (int t = 0; t < tiles; ++t) {
             const uint32_t b_lo = b0 + (t % NST) * (STAGE >> 4);
+            if (WRITERS == 40) {   // the two row blocks' instruction streams interleaved (what two issuing warps produce)
+                const uint32_t d0 = tmem + (uint32_t)(((t & 1) * 2 + 0) * N) % 512u, d1 = tmem + (uint32_t)(((t & 1) * 2 + 1) * N) % 512u;
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    const uint32_t bk = b_lo + (kk >> 2) * (N * 128 >> 4) + (kk & 3) * 2;
+                    const uint32_t ak0 = a0 + (kk >> 2) * (128 * 128 >> 4) + (kk & 3) * 2, ak1 = ak0 + (2 * 128 * 128 >> 4);
+                    if (kk == 0) { umma_ss<false>(d0, ak0, bk, idesc, leader); umma_ss<false>(d1, ak1, bk, idesc, leader); }
+                    else { umma_ss<true>(d0, ak0, bk, idesc, leader); umma_ss<true>(d1, ak1, bk, idesc, leader); }
+                }
+                continue;
+            }
 #pragma unroll
             for (int rb = 0; rb < 2; ++rb) {
                 // accumulators: N = 128: 4 x 128 columns (as the matcher); N = 256: 2 x 256; TMEM-A variants keep A in the last 128 columns
@@ -176,7 +187,8 @@ int main()
     run<0, 16>("ss_n128_plus_16_ldtm_warps", p.multiProcessorCount, d_cyc, sink);
     run<0, 32>("ss_n128_commit_per_8_mma", p.multiProcessorCount, d_cyc, sink);
     run<0, 33>("ss_n128_commit_wait_fence_per_8_mma", p.multiProcessorCount, d_cyc, sink);
-    run<1, 32>("ss_n256_commit_per_8_mma", p.multiProcessorCount, d_cyc, sink, true);
+    run<1, 32>("ss_n256_commit_per_8_mma", p.multiProcessorCount, d_cyc, sink);
+    run<0, 40>("ss_n128_two_accumulators_interleaved", p.multiProcessorCount, d_cyc, sink, true);
     printf("}\n");
     return 0;
 }
