@@ -66,7 +66,7 @@ struct mvs_ctx {
     bool use_tc = true;          // MVS_MATCHER=popc selects the integer-pipe kernel (A/B measurements, > 32768 train descriptors)
     // workspace
     DevBuf d_pairs, d_partial, d_rev, d_matches, d_nmatch, d_points, d_state, d_Fall, d_pc, d_pr, d_mask,
-        d_valid, d_tri, d_opts, d_oidx, d_results, d_table, d_in1, d_in2, d_knn_i, d_knn_d, d_counts, d_pres;
+        d_valid, d_tri, d_items, d_item_total, d_opts, d_oidx, d_results, d_table, d_in1, d_in2, d_knn_i, d_knn_d, d_counts, d_pres;
     mvs::L2Workspace l2;
     // feature extraction (orb.cu): pyramid geometry cached per (width, height, nfeatures), workspace, last results
     int orb_w = 0, orb_h = 0, orb_nf = -1;
@@ -244,6 +244,11 @@ int run_geometry(mvs_ctx *ctx, int n_pairs, int p_stride, const RansacCfg &rc, b
     if (k4_res) CK(ctx->d_pres.ensure((size_t)n_pairs * tiles * rc.H * sizeof(double)));
     CK(ctx->d_mask.ensure((size_t)n_pairs * p_stride));
     if (want_all_counts) CK(ctx->d_counts.ensure((size_t)n_pairs * rc.H * sizeof(int32_t)));
+    if (decompose) {
+        CK(ctx->d_valid.ensure((size_t)n_pairs * 4 * p_stride));
+        CK(ctx->d_items.ensure((size_t)n_pairs * p_stride * sizeof(unsigned long long)));
+        CK(ctx->d_item_total.ensure(sizeof(uint32_t)));
+    }
     PairState *state = ctx->d_state.as<PairState>();
     {
         StageTimer t(ctx, MVS_STAGE_HYPOTHESES);
@@ -259,6 +264,7 @@ int run_geometry(mvs_ctx *ctx, int n_pairs, int p_stride, const RansacCfg &rc, b
         a.points = ctx->d_points.as<double>(); a.p_stride = p_stride; a.state = state; a.F_all = ctx->d_Fall.as<double>();
         a.H = rc.H; a.max_error_sq = rc.thr; a.zc1 = zc1; a.zc2 = zc2; a.tiles = tiles; a.part_count = ctx->d_pc.as<uint32_t>();
         a.part_res = k4_res ? ctx->d_pres.as<double>() : nullptr; a.solver = rc.solver;
+        a.zero_word = decompose ? ctx->d_item_total.as<uint32_t>() : nullptr;
         launch_score(a, rc.mode, unit_z, n_pairs, ctx->stream);
     }
     {
@@ -270,10 +276,13 @@ int run_geometry(mvs_ctx *ctx, int n_pairs, int p_stride, const RansacCfg &rc, b
         a.max_error_sq = rc.thr; a.zc1 = zc1; a.zc2 = zc2; a.min_inliers = rc.min_inl; a.decompose = decompose ? 1 : 0;
         a.mask = ctx->d_mask.as<uint8_t>(); a.all_counts = want_all_counts ? ctx->d_counts.as<int32_t>() : nullptr;
         a.solver = rc.solver;
-        launch_select(a, rc.mode, unit_z, n_pairs, ctx->stream);
+        if (decompose) {
+            a.items = ctx->d_items.as<unsigned long long>(); a.item_total = ctx->d_item_total.as<uint32_t>();
+            a.valid = ctx->d_valid.as<uint8_t>();
+        }
+        launch_select(a, rc.mode, unit_z, p_stride, n_pairs, ctx->stream);
     }
     if (!decompose) return MVS_OK;
-    CK(ctx->d_valid.ensure((size_t)n_pairs * 4 * p_stride));
     CK(ctx->d_tri.ensure((size_t)n_pairs * 4 * p_stride * 3 * sizeof(double)));
     CK(ctx->d_opts.ensure((size_t)n_pairs * p_stride * 3 * sizeof(double)));
     CK(ctx->d_oidx.ensure((size_t)n_pairs * p_stride * sizeof(uint64_t)));
@@ -283,7 +292,8 @@ int run_geometry(mvs_ctx *ctx, int n_pairs, int p_stride, const RansacCfg &rc, b
         TriArgs a{};
         a.points = ctx->d_points.as<double>(); a.p_stride = p_stride; a.state = state; a.mask = ctx->d_mask.as<uint8_t>();
         a.n_cand = 4; a.valid = ctx->d_valid.as<uint8_t>(); a.tri = ctx->d_tri.as<double>(); a.solver = rc.solver;
-        launch_triangulate(a, p_stride, n_pairs, ctx->stream);
+        a.items = ctx->d_items.as<unsigned long long>(); a.item_total = ctx->d_item_total.as<uint32_t>();
+        CK(launch_triangulate_items(a, (size_t)n_pairs * p_stride, ctx->stream));
     }
     {
         StageTimer t(ctx, MVS_STAGE_FINALIZE);
@@ -291,7 +301,7 @@ int run_geometry(mvs_ctx *ctx, int n_pairs, int p_stride, const RansacCfg &rc, b
         a.state = state; a.p_stride = p_stride; a.n_cand = 4; a.valid = ctx->d_valid.as<uint8_t>(); a.tri = ctx->d_tri.as<double>();
         a.matches = d_matches; a.out_points = ctx->d_opts.as<double>(); a.out_index = ctx->d_oidx.as<uint64_t>();
         a.results = ctx->d_results.as<mvs_pair_result>();
-        launch_finish(a, n_pairs, ctx->stream);
+        launch_finish(a, p_stride, n_pairs, ctx->stream);
     }
     CK(cudaGetLastError());
     return MVS_OK;
@@ -425,7 +435,7 @@ void mvs_destroy(mvs_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->d_desc, &ctx->d_kp, &ctx->d_foff, &ctx->d_fcnt, &ctx->t_desc, &ctx->t_foff, &ctx->t_fcnt, &ctx->d_desc8, &ctx->t_desc8,
                       &ctx->d_pairs, &ctx->d_partial, &ctx->d_rev, &ctx->d_matches, &ctx->d_nmatch, &ctx->d_points,
-                      &ctx->d_state, &ctx->d_Fall, &ctx->d_pc, &ctx->d_pr, &ctx->d_mask, &ctx->d_valid, &ctx->d_tri,
+                      &ctx->d_state, &ctx->d_Fall, &ctx->d_pc, &ctx->d_pr, &ctx->d_mask, &ctx->d_valid, &ctx->d_tri, &ctx->d_items, &ctx->d_item_total,
                       &ctx->d_opts, &ctx->d_oidx, &ctx->d_results, &ctx->d_table, &ctx->d_in1, &ctx->d_in2,
                       &ctx->d_knn_i, &ctx->d_knn_d, &ctx->d_counts, &ctx->d_pres, &ctx->o_tabs, &ctx->o_stage,
                       &ctx->o_pyr, &ctx->o_blur, &ctx->o_cxy, &ctx->o_cval, &ctx->o_cnt, &ctx->o_kidx, &ctx->o_kcnt,
@@ -834,11 +844,11 @@ int mvs_sfm_triangulate(mvs_ctx *ctx, const double *xy1, const double *xy2, int 
     }
     {
         StageTimer t(ctx, MVS_STAGE_FINALIZE);
-        FinishArgs a{};
-        a.state = ctx->d_state.as<PairState>(); a.p_stride = n; a.n_cand = 1; a.valid = ctx->d_valid.as<uint8_t>();
-        a.tri = ctx->d_tri.as<double>(); a.matches = nullptr; a.out_points = ctx->d_opts.as<double>();
-        a.out_index = ctx->d_oidx.as<uint64_t>(); a.results = ctx->d_results.as<mvs_pair_result>();
-        launch_finish(a, 1, ctx->stream);
+        FinishArgs f{};
+        f.state = ctx->d_state.as<PairState>(); f.p_stride = n; f.n_cand = 1; f.valid = ctx->d_valid.as<uint8_t>();
+        f.tri = ctx->d_tri.as<double>(); f.matches = nullptr; f.out_points = ctx->d_opts.as<double>();
+        f.out_index = ctx->d_oidx.as<uint64_t>(); f.results = ctx->d_results.as<mvs_pair_result>();
+        launch_finish(f, n, 1, ctx->stream);
     }
     CK(cudaGetLastError());
     mvs_pair_result r;

@@ -47,6 +47,7 @@ struct PairState {
     double E[9];
     double Rc[2][9];
     double tc[3];
+    double Rr[2][9];   // SO3(Rc[k]) (so3_rectify), written with Rc by K5
 };
 
 // ------------------------------------------------------------------------------------------
@@ -339,6 +340,79 @@ __device__ __forceinline__ void cv_svd_last_vt(double (&At)[N][N], double (&x)[N
     cv_jacobi<N>(At, V, W);
     cv_sort_perm<N>(W, perm);
     cv_pick_row<N>(V, perm[N - 1], x);
+}
+
+// cv_svd_last_vt with the accumulated rotations V kept in shared memory instead of registers: element (i,k) of this
+// thread's V is sV[(i * N + k) * stride].  V is not on the dependent chain of the sweep (the next rotation's angle
+// depends on At only), so its loads and stores hide behind the FP64 chain, and the registers it frees double the
+// number of decompositions an SM keeps in flight.  Same operations in the same order: bit-identical results.
+template <int N>
+__device__ __forceinline__ void cv_svd_last_vt_sv(double (&At)[N][N], double *sV, const int stride, double (&x)[N])
+{
+    constexpr double eps = DBL_EPSILON * 10;
+    double W[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        double sd = 0;
+#pragma unroll
+        for (int k = 0; k < N; ++k) { const double t = At[i][k]; sd += t * t; }
+        W[i] = sd;
+#pragma unroll
+        for (int k = 0; k < N; ++k) sV[(i * N + k) * stride] = (i == k) ? 1.0 : 0.0;
+    }
+    for (int iter = 0; iter < 30; ++iter) {
+        bool changed = false;
+#pragma unroll
+        for (int i = 0; i < N - 1; ++i)
+#pragma unroll
+            for (int j = i + 1; j < N; ++j) {
+                double a = W[i], p = 0, b = W[j];
+#pragma unroll
+                for (int k = 0; k < N; ++k) p += At[i][k] * At[j][k];
+                if (!(fabs(p) <= eps * sqrt(a * b))) {
+                    p *= 2;
+                    const double beta = a - b, gamma = cv_hypot(p, beta);
+                    double c, s;
+                    if (beta < 0) {
+                        const double delta = (gamma - beta) * 0.5;
+                        s = sqrt(delta / gamma);
+                        c = p / (gamma * s * 2);
+                    } else {
+                        c = sqrt((gamma + beta) / (gamma * 2));
+                        s = p / (gamma * c * 2);
+                    }
+                    a = b = 0;
+#pragma unroll
+                    for (int k = 0; k < N; ++k) {
+                        const double t0 = c * At[i][k] + s * At[j][k];
+                        const double t1 = -s * At[i][k] + c * At[j][k];
+                        At[i][k] = t0; At[j][k] = t1;
+                        a += t0 * t0; b += t1 * t1;
+                    }
+                    W[i] = a; W[j] = b;
+                    changed = true;
+#pragma unroll
+                    for (int k = 0; k < N; ++k) {
+                        const double vi = sV[(i * N + k) * stride], vj = sV[(j * N + k) * stride];
+                        sV[(i * N + k) * stride] = c * vi + s * vj;
+                        sV[(j * N + k) * stride] = -s * vi + c * vj;
+                    }
+                }
+            }
+        if (!changed) break;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        double sd = 0;
+#pragma unroll
+        for (int k = 0; k < N; ++k) { const double t = At[i][k]; sd += t * t; }
+        W[i] = sqrt(sd);
+    }
+    int perm[N];
+    cv_sort_perm<N>(W, perm);
+    const int r = perm[N - 1];
+#pragma unroll
+    for (int k = 0; k < N; ++k) x[k] = sV[(r * N + k) * stride];
 }
 
 // Full cv::SVDecomp of an N x N matrix: A row-major in, U row-major, w descending, Vt row-major (the SVD<> wrapper of

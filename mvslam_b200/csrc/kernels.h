@@ -76,6 +76,7 @@ struct ScoreArgs {
     uint32_t *part_count;      // [pairs][tiles][H]
     double *part_res;          // [pairs][tiles][H] residual sums (ALGEBRAIC mode only, else nullptr)
     int solver;
+    uint32_t *zero_word;       // optional: a counter this launch clears for the kernels after it (SelectArgs::item_total)
 };
 
 struct SelectArgs {
@@ -92,6 +93,10 @@ struct SelectArgs {
     uint8_t *mask;             // [pairs][p_stride]
     int32_t *all_counts;       // optional [pairs][H]
     int solver;
+    // work list of the triangulation (decompose only): one entry (pair << 32 | match index) per inlier of every pair
+    // that has a pose to recover, appended in any order; valid[] of the other matches is cleared here
+    unsigned long long *items; uint32_t *item_total;
+    uint8_t *valid;            // [pairs][4][p_stride]
 };
 
 struct TriArgs {
@@ -102,6 +107,7 @@ struct TriArgs {
     uint8_t *valid;            // [pairs][4][p_stride]
     double *tri;               // [pairs][4][p_stride][3]
     int solver;
+    const unsigned long long *items; const uint32_t *item_total;   // launch_triangulate_items: K5's work list
 };
 
 struct FinishArgs {
@@ -129,8 +135,9 @@ void launch_fundamental_sets(const double *p1s, const double *p2s, int n_sets, d
 bool launch_svd_batch(int n, const double *A, int count, int solver, double *U, double *w, double *Vt, cudaStream_t s);
 int score_tiles(int max_points);
 void launch_score(const ScoreArgs &a, int mode, bool const_z, int n_pairs, cudaStream_t s);
-void launch_select(const SelectArgs &a, int mode, bool const_z, int n_pairs, cudaStream_t s);
+void launch_select(const SelectArgs &a, int mode, bool const_z, int max_points, int n_pairs, cudaStream_t s);
 void launch_triangulate(const TriArgs &a, int max_points, int n_pairs, cudaStream_t s);
-void launch_finish(const FinishArgs &a, int n_pairs, cudaStream_t s);
+void launch_finish(const FinishArgs &a, int max_points, int n_pairs, cudaStream_t s);
+cudaError_t launch_triangulate_items(const TriArgs &a, size_t max_items, cudaStream_t s);
 
 }  // namespace mvs

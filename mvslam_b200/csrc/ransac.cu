@@ -413,6 +413,7 @@ score_kernel(ScoreArgs a)
     constexpr int W = UNIT_Z ? 4 : 6;
     __shared__ __align__(16) double sp[SC_TILE * W];
     const int pair = blockIdx.z, tile = blockIdx.y;
+    if (a.zero_word && (blockIdx.x | blockIdx.y | blockIdx.z | threadIdx.x) == 0) *a.zero_word = 0;
     if (a.state[pair].status != MVS_OK) return;
     const int n = a.state[pair].n_matches;
     const int p0 = tile * SC_TILE;
@@ -463,7 +464,9 @@ score_kernel(ScoreArgs a)
 // ------------------------------------------------------------------------------------------
 // K5.  One CTA per pair.
 // ------------------------------------------------------------------------------------------
-constexpr int SEL_THREADS = 256;
+// Block size: 256 threads for long match lists; 64 when a pair has at most a few thousand matches, so that every pair
+// of a 1024-pair batch is resident at once (the kernel's time is thread 0's two 3x3 SVDs, a latency every block pays).
+constexpr int SEL_THREADS_BIG = 256, SEL_THREADS_SMALL = 64, SEL_SMALL_MAX_POINTS = 4096;
 
 struct Best { uint32_t cnt; double res; int h; };
 
@@ -515,11 +518,13 @@ static __device__ __noinline__ void decompose_essential(const double E[9], doubl
     t[0] = -S12; t[1] = S02; t[2] = -S01;
 }
 
-template <bool UNIT_Z, int MODE, bool LIT>
+template <bool UNIT_Z, int MODE, bool LIT, int SEL_THREADS>
 __global__ void __launch_bounds__(SEL_THREADS)
 select_kernel(SelectArgs a)
 {
     __shared__ uint32_t s_cnt[SEL_THREADS / 32];
+    __shared__ int s_status, s_nin, s_k;
+    __shared__ uint32_t s_item_base;
     __shared__ Best s_best[SEL_THREADS / 32];
     __shared__ double s_F[9];
     __shared__ uint32_t s_max;
@@ -642,10 +647,18 @@ select_kernel(SelectArgs a)
 #pragma unroll
                 for (int i = 0; i < 9; ++i) { st->Rc[0][i] = Ra[i]; st->Rc[1][i] = Rb[i]; }
                 st->tc[0] = t[0]; st->tc[1] = t[1]; st->tc[2] = t[2];
+                double Rr[9];
+                so3_rectify(Ra, Rr);
+#pragma unroll
+                for (int i = 0; i < 9; ++i) st->Rr[0][i] = Rr[i];
+                so3_rectify(Rb, Rr);
+#pragma unroll
+                for (int i = 0; i < 9; ++i) st->Rr[1][i] = Rr[i];
             }
         }
         st->tri_count[0] = st->tri_count[1] = st->tri_count[2] = st->tri_count[3] = 0;
         st->status = status;
+        s_status = status; s_nin = 0; s_k = 0;
     }
     __syncthreads();
     // inlier mask of the winner (estimator-RANSAC.cpp:112-127), same residual expression as K4
@@ -654,10 +667,37 @@ select_kernel(SelectArgs a)
     for (int i = 0; i < 9; ++i) F[i] = s_F[i];
     const FzConst zc = make_fz(F, a.zc1, a.zc2);
     uint8_t *mask = a.mask + (size_t)pair * a.p_stride;
+    const bool list = a.items != nullptr && a.decompose;
+    int mine = 0;
     for (int i = threadIdx.x; i < n; i += SEL_THREADS) {
         const double *p = pts + (size_t)i * 6;
         double r;
-        mask[i] = point_residual<UNIT_Z, MODE, false, LIT>(p[0], p[1], p[2], p[3], p[4], p[5], F, zc, a.max_error_sq, r) ? 1 : 0;
+        const bool in = point_residual<UNIT_Z, MODE, false, LIT>(p[0], p[1], p[2], p[3], p[4], p[5], F, zc, a.max_error_sq, r);
+        mask[i] = in ? 1 : 0;
+        mine += in ? 1 : 0;
+    }
+    if (!list) return;
+    // ---- the triangulation's work list: reserve this pair's share, then append its inliers
+    const bool ok = s_status == MVS_OK;
+    if (ok) {
+        mine = __reduce_add_sync(FULL, mine);
+        if (lane == 0 && mine) atomicAdd(&s_nin, mine);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && ok) s_item_base = atomicAdd(a.item_total, (uint32_t)s_nin);
+    __syncthreads();
+    const uint32_t base = s_item_base;
+    for (int i0 = 0; i0 < n; i0 += SEL_THREADS) {
+        const int i = i0 + threadIdx.x;
+        const bool in = ok && i < n && mask[i] != 0;
+        const unsigned bal = __ballot_sync(FULL, in);
+        int at = 0;
+        if (lane == 0 && bal) at = atomicAdd(&s_k, __popc(bal));
+        at = __shfl_sync(FULL, at, 0);
+        if (in) a.items[base + at + __popc(bal & ((1u << lane) - 1u))] = ((unsigned long long)pair << 32) | (unsigned)i;
+        else if (i < n)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) a.valid[((size_t)pair * 4 + c) * a.p_stride + i] = 0;
     }
 }
 
@@ -731,21 +771,27 @@ void launch_score(const ScoreArgs &a, int mode, bool unit_z, int n_pairs, cudaSt
 }
 
 template <bool UNIT_Z, int MODE>
-static void launch_select_t(const SelectArgs &a, bool lit, int n_pairs, cudaStream_t s)
+static void launch_select_t(const SelectArgs &a, bool lit, bool small, int n_pairs, cudaStream_t s)
 {
-    if (lit) select_kernel<UNIT_Z, MODE, true><<<n_pairs, SEL_THREADS, 0, s>>>(a);
-    else select_kernel<UNIT_Z, MODE, false><<<n_pairs, SEL_THREADS, 0, s>>>(a);
+    if (small) {
+        if (lit) select_kernel<UNIT_Z, MODE, true, SEL_THREADS_SMALL><<<n_pairs, SEL_THREADS_SMALL, 0, s>>>(a);
+        else select_kernel<UNIT_Z, MODE, false, SEL_THREADS_SMALL><<<n_pairs, SEL_THREADS_SMALL, 0, s>>>(a);
+    } else {
+        if (lit) select_kernel<UNIT_Z, MODE, true, SEL_THREADS_BIG><<<n_pairs, SEL_THREADS_BIG, 0, s>>>(a);
+        else select_kernel<UNIT_Z, MODE, false, SEL_THREADS_BIG><<<n_pairs, SEL_THREADS_BIG, 0, s>>>(a);
+    }
 }
 
-void launch_select(const SelectArgs &a, int mode, bool unit_z, int n_pairs, cudaStream_t s)
+void launch_select(const SelectArgs &a, int mode, bool unit_z, int max_points, int n_pairs, cudaStream_t s)
 {
     const bool lit = a.solver == MVS_SOLVER_REFERENCE;
+    const bool small = max_points <= SEL_SMALL_MAX_POINTS && a.H <= 2048;
     if (unit_z) {
-        if (mode == MVS_SCORE_ALGEBRAIC) launch_select_t<true, MVS_SCORE_ALGEBRAIC>(a, lit, n_pairs, s);
-        else launch_select_t<true, MVS_SCORE_SAMPSON>(a, lit, n_pairs, s);
+        if (mode == MVS_SCORE_ALGEBRAIC) launch_select_t<true, MVS_SCORE_ALGEBRAIC>(a, lit, small, n_pairs, s);
+        else launch_select_t<true, MVS_SCORE_SAMPSON>(a, lit, small, n_pairs, s);
     } else {
-        if (mode == MVS_SCORE_ALGEBRAIC) launch_select_t<false, MVS_SCORE_ALGEBRAIC>(a, lit, n_pairs, s);
-        else launch_select_t<false, MVS_SCORE_SAMPSON>(a, lit, n_pairs, s);
+        if (mode == MVS_SCORE_ALGEBRAIC) launch_select_t<false, MVS_SCORE_ALGEBRAIC>(a, lit, small, n_pairs, s);
+        else launch_select_t<false, MVS_SCORE_SAMPSON>(a, lit, small, n_pairs, s);
     }
 }
 

@@ -9,12 +9,47 @@
 //                           (:364), ImagePair bookkeeping (source/front-end/image-pair.cpp:158-167).
 #include <math_constants.h>
 
+#include <algorithm>
+#include <mutex>
+
 #include "common.cuh"
 #include "kernels.h"
 
 namespace mvs {
 
 constexpr int TRI_THREADS = 128;
+
+// X = V.col(3) of SVD<4x4>(A) (source/vision/sfm-solve.cpp:193-195).  W is overwritten.
+template <bool REF>
+__device__ __forceinline__ void dlt_null_vector(double (&W)[4][4], double (&X)[4])
+{
+    if (REF) {
+        // vt.row(3) of cv::SVDecomp(A) (svd.hpp:65-67), bit for bit
+        double At[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) At[c][r] = W[r][c];
+        cv_svd_last_vt<4>(At, X);
+    } else {
+        double V[4][4];
+        jacobi_svd<4>(W, V);
+        // the V column of the smallest singular value
+        double best = CUDART_INF;
+        int bj = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s += W[k][j] * W[k][j];
+            s = sqrt(s);
+            if (s <= best) { best = s; bj = j; }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) X[k] = bj == 0 ? V[k][0] : (bj == 1 ? V[k][1] : (bj == 2 ? V[k][2] : V[k][3]));
+    }
+}
+
 
 template <bool REF>
 __global__ void __launch_bounds__(TRI_THREADS, REF ? 4 : 5)
@@ -43,7 +78,7 @@ triangulate_kernel(TriArgs a)
     if (i < n && (!a.mask || a.mask[(size_t)pair * a.p_stride + i] != 0)) {
         const double *p = a.points + ((size_t)pair * a.p_stride + i) * 6;
         const double x1 = p[0], y1 = p[1], x2 = p[3], y2 = p[4];
-        double W[4][4], V[4][4];
+        double W[4][4];
         // rows 0,1: x1[k]*P1.row(2) - P1.row(k) with P1 = I4 (:185-188)
         W[0][0] = x1 * 0.0 - 1.0; W[0][1] = x1 * 0.0 - 0.0; W[0][2] = x1 * 1.0 - 0.0; W[0][3] = x1 * 0.0 - 0.0;
         W[1][0] = y1 * 0.0 - 0.0; W[1][1] = y1 * 0.0 - 1.0; W[1][2] = y1 * 1.0 - 0.0; W[1][3] = y1 * 0.0 - 0.0;
@@ -56,30 +91,7 @@ triangulate_kernel(TriArgs a)
             W[3][j] = y2 * p2j - p1j;
         }
         double X[4];
-        if (REF) {
-            // X = V.col(3) = vt.row(3) of cv::SVDecomp(A) (svd.hpp:65-67), bit for bit
-            double At[4][4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) At[c][r] = W[r][c];
-            cv_svd_last_vt<4>(At, X);
-        } else {
-        jacobi_svd<4>(W, V);
-        // X = V column of the smallest singular value (V.col(3), :193-195)
-        double best = CUDART_INF;
-        int bj = 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            double s = 0.0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) s += W[k][j] * W[k][j];
-            s = sqrt(s);
-            if (s <= best) { best = s; bj = j; }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) X[k] = bj == 0 ? V[k][0] : (bj == 1 ? V[k][1] : (bj == 2 ? V[k][2] : V[k][3]));
-        }
+        dlt_null_vector<REF>(W, X);
         if (!(fabs(X[3]) < kTolerance)) {
             const double scale = 1.0 / X[3];
             pt[0] = X[0] * scale; pt[1] = X[1] * scale; pt[2] = X[2] * scale;
@@ -101,14 +113,16 @@ triangulate_kernel(TriArgs a)
     if (threadIdx.x == 0 && s_cnt) atomicAdd(&st->tri_count[cand], s_cnt);
 }
 
-constexpr int FIN2_THREADS = 256;
+// 256 threads for long match lists, 128 for ordinary ones (twice the pairs resident: the kernel's time is thread 0's
+// candidate choice and record, a latency every block pays).
+constexpr int FIN2_THREADS = 256, FIN2_THREADS_SMALL = 128, FIN2_SMALL_MAX_POINTS = 4096;
 
-__global__ void __launch_bounds__(FIN2_THREADS)
-finish_kernel(FinishArgs a)
+// The per-pair tail shared by finish_kernel and triangulate_finish_kernel: one block of THREADS threads per pair.
+template <int THREADS>
+__device__ __forceinline__ void finish_body(const FinishArgs &a, const int pair)
 {
-    __shared__ int s_cand, s_base, s_warp[FIN2_THREADS / 32];
+    __shared__ int s_cand, s_base, s_warp[THREADS / 32];
     __shared__ unsigned long long s_ssd;
-    const int pair = blockIdx.x;
     PairState *st = a.state + pair;
     mvs_pair_result *res = a.results ? a.results + pair : nullptr;
     if (threadIdx.x == 0) {
@@ -134,7 +148,7 @@ finish_kernel(FinishArgs a)
         const mvs_match *mt = a.matches ? a.matches + (size_t)pair * a.p_stride : nullptr;
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         unsigned long long ssd = 0ull;
-        for (int i0 = 0; i0 < n; i0 += FIN2_THREADS) {
+        for (int i0 = 0; i0 < n; i0 += THREADS) {
             const int i = i0 + threadIdx.x;
             const bool f = (i < n) && valid[i];
             const unsigned bal = __ballot_sync(0xFFFFFFFFu, f);
@@ -152,7 +166,7 @@ finish_kernel(FinishArgs a)
             __syncthreads();
             if (threadIdx.x == 0) {
                 int tot = 0;
-                for (int w = 0; w < FIN2_THREADS / 32; ++w) tot += s_warp[w];
+                for (int w = 0; w < THREADS / 32; ++w) tot += s_warp[w];
                 s_base += tot;
             }
             __syncthreads();
@@ -190,6 +204,77 @@ finish_kernel(FinishArgs a)
     }
 }
 
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+finish_kernel(FinishArgs a)
+{
+    finish_body<THREADS>(a, blockIdx.x);
+}
+
+// K6 over K5's work list (SelectArgs::items): the (inlier, candidate) pairs of the whole batch, flattened, walked by a
+// grid that just fills the GPU.  Every lane of every warp that enters the 4x4 SVD has a point, whatever the pairs'
+// inlier counts are, and no block waits for its slowest decomposition; the rectified candidates come from K5
+// (PairState::Rr).  REF keeps V in shared memory (cv_svd_last_vt_sv): 64 registers, two 512-thread blocks per SM.
+// Results go to the same per-(pair, candidate, match) scratch as triangulate_kernel, so K7 is unchanged.
+constexpr int TI_THREADS = 512;
+
+template <bool REF, bool SMEM_V>
+__global__ void __launch_bounds__(TI_THREADS, SMEM_V ? 2 : 1)
+triangulate_items_kernel(TriArgs a)
+{
+    extern __shared__ double s_V[];   // SMEM_V: [16][TI_THREADS]
+    const size_t total = (size_t)*a.item_total * 4;
+    for (size_t it = (size_t)blockIdx.x * TI_THREADS + threadIdx.x; it < total; it += (size_t)gridDim.x * TI_THREADS) {
+        const unsigned long long e = a.items[it >> 2];
+        const int cand = (int)(it & 3), pair = (int)(e >> 32), i = (int)(e & 0xFFFFFFFFu);   // (Ra,+t),(Ra,-t),(Rb,+t),(Rb,-t)
+        PairState *st = a.state + pair;
+        const double *R = st->Rc[cand >> 1], *Rr = st->Rr[cand >> 1];   // P2 = SE3(SO3(R), t).get_matrix() (:155)
+        double t[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) t[k] = (cand & 1) ? -st->tc[k] : st->tc[k];
+        const double *p = a.points + ((size_t)pair * a.p_stride + i) * 6;
+        const double x1 = p[0], y1 = p[1], x2 = p[3], y2 = p[4];
+        double W[4][4];
+        // rows 0,1: x1[k]*P1.row(2) - P1.row(k) with P1 = I4 (:185-188)
+        W[0][0] = x1 * 0.0 - 1.0; W[0][1] = x1 * 0.0 - 0.0; W[0][2] = x1 * 1.0 - 0.0; W[0][3] = x1 * 0.0 - 0.0;
+        W[1][0] = y1 * 0.0 - 0.0; W[1][1] = y1 * 0.0 - 1.0; W[1][2] = y1 * 1.0 - 0.0; W[1][3] = y1 * 0.0 - 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double p2j = j < 3 ? Rr[6 + j] : t[2];
+            const double p0j = j < 3 ? Rr[0 + j] : t[0];
+            const double p1j = j < 3 ? Rr[3 + j] : t[1];
+            W[2][j] = x2 * p2j - p0j;
+            W[3][j] = y2 * p2j - p1j;
+        }
+        double X[4];
+        if (REF) {
+            // X = vt.row(3) of cv::SVDecomp(A) (svd.hpp:65-67), bit for bit
+            double At[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) At[c][r] = W[r][c];
+            if (SMEM_V) cv_svd_last_vt_sv<4>(At, s_V + threadIdx.x, TI_THREADS, X);
+            else cv_svd_last_vt<4>(At, X);
+        } else dlt_null_vector<false>(W, X);
+        bool ok = false;
+        double pt[3] = {0.0, 0.0, 0.0};
+        if (!(fabs(X[3]) < kTolerance)) {
+            const double scale = 1.0 / X[3];
+            pt[0] = X[0] * scale; pt[1] = X[1] * scale; pt[2] = X[2] * scale;
+            if (!(pt[2] < kTolerance)) {
+                const double z2 = (R[6] * pt[0] + R[7] * pt[1] + R[8] * pt[2]) + t[2];  // un-rectified R (:218)
+                ok = !(z2 < kTolerance);
+            }
+        }
+        const size_t o = ((size_t)pair * 4 + cand) * a.p_stride + i;
+        a.valid[o] = ok ? 1 : 0;
+        double *tp = a.tri + o * 3;
+        tp[0] = pt[0]; tp[1] = pt[1]; tp[2] = pt[2];
+        if (ok) atomicAdd(&st->tri_count[cand], 1);
+    }
+}
+
 void launch_triangulate(const TriArgs &a, int max_points, int n_pairs, cudaStream_t s)
 {
     dim3 grid(max_points > 0 ? (max_points + TRI_THREADS - 1) / TRI_THREADS : 1, a.n_cand, n_pairs);
@@ -197,9 +282,41 @@ void launch_triangulate(const TriArgs &a, int max_points, int n_pairs, cudaStrea
     else triangulate_kernel<false><<<grid, TRI_THREADS, 0, s>>>(a);
 }
 
-void launch_finish(const FinishArgs &a, int n_pairs, cudaStream_t s)
+cudaError_t launch_triangulate_items(const TriArgs &a, size_t max_items, cudaStream_t s)
 {
-    finish_kernel<<<n_pairs, FIN2_THREADS, 0, s>>>(a);
+    const bool ref = a.solver == MVS_SOLVER_REFERENCE;
+    const size_t want = std::max<size_t>(1, (max_items * 4 + TI_THREADS - 1) / TI_THREADS);
+    if (!ref) {
+        triangulate_items_kernel<false, false><<<(unsigned)std::min<size_t>(want, 148), TI_THREADS, 0, s>>>(a);
+        return cudaSuccess;
+    }
+    if (want <= 148) {   // a block per SM holds the whole job: V in registers is the shorter chain (latency, not throughput)
+        triangulate_items_kernel<true, false><<<(unsigned)want, TI_THREADS, 0, s>>>(a);
+        return cudaSuccess;
+    }
+    constexpr int smem = 16 * TI_THREADS * (int)sizeof(double);
+    // per-device opt-in above 48 KB, as in launch_match_finalize
+    static std::mutex mu;
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (dev < 0 || dev >= 64 || !configured[dev]) {
+            e = cudaFuncSetAttribute(triangulate_items_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return e;
+            if (dev >= 0 && dev < 64) configured[dev] = true;
+        }
+    }
+    triangulate_items_kernel<true, true><<<(unsigned)std::min<size_t>(want, 148 * 2), TI_THREADS, smem, s>>>(a);
+    return cudaSuccess;
+}
+
+void launch_finish(const FinishArgs &a, int max_points, int n_pairs, cudaStream_t s)
+{
+    if (max_points <= FIN2_SMALL_MAX_POINTS) finish_kernel<FIN2_THREADS_SMALL><<<n_pairs, FIN2_THREADS_SMALL, 0, s>>>(a);
+    else finish_kernel<FIN2_THREADS><<<n_pairs, FIN2_THREADS, 0, s>>>(a);
 }
 
 }  // namespace mvs
