@@ -810,9 +810,32 @@ def parity_block(ctx, mvs):
 
 
 def latency_block(ctx, mvs, descs, kps, K):
-    """per-call wall time of the synchronous C-ABI call for the batches a visual odometer issues"""
-    ctx.frames_upload(descs, kps)
+    """per-call wall time of the synchronous C-ABI call for the batches a visual odometer issues: from a C++ caller
+    (tools/latency_probe, what the reference's VisualOdometer would pay) and through the Python ctypes binding"""
+    import struct
+    import subprocess
+    import tempfile
     out = {}
+    probe = os.path.join(ROOT, "tools", "latency_probe")
+    if os.path.exists(probe):
+        with tempfile.TemporaryDirectory() as d:
+            names = []
+            for i, (kp, de) in enumerate(zip(kps, descs), 1):
+                with open(os.path.join(d, f"{i}.mvsf"), "wb") as f:     # include/mvslam/feature-io.hpp
+                    f.write(b"MVSF" + struct.pack("<iii", len(kp), 384, 288))
+                    f.write(np.ascontiguousarray(kp, np.float32).tobytes()); f.write(np.ascontiguousarray(de, np.uint8).tobytes())
+                names.append(f"{i}.mvsf")
+            with open(os.path.join(d, "camera.config"), "w") as f:
+                f.write(f"{K[0, 0]:g} {K[1, 1]:g} {K[0, 1]:g} {K[0, 2]:g} {K[1, 2]:g}\n0 0 0 1.5708 0 0\n")
+            with open(os.path.join(d, "features.txt"), "w") as f:
+                f.write("\n".join(names) + "\n")
+            r = subprocess.run([probe, d], capture_output=True, text=True, timeout=120)
+            if r.returncode == 0:
+                out["cpp_caller"] = json.loads(r.stdout.strip().splitlines()[-1])
+            else:
+                out["cpp_caller"] = {"error": (r.stderr or r.stdout)[-300:]}
+    ctx.frames_upload(descs, kps)
+    py = {}
     for name, prs, H, slv in (("1_pair_reference_h1", [(0, 1)], 1, "reference"), ("1_pair_fast_h1024", [(0, 1)], 1024, "fast"),
                               ("10_pairs_reference_h1", [(i % 4, 4) for i in range(10)], 1, "reference"),
                               ("10_pairs_fast_h1024", [(i % 4, 4) for i in range(10)], 1024, "fast")):
@@ -823,8 +846,11 @@ def latency_block(ctx, mvs, descs, kps, K):
         for _ in range(200):
             t0 = time.perf_counter(); ctx.pair_batch(prs, K, **kw); ts.append(time.perf_counter() - t0)
         ts = np.array(ts) * 1e6
-        out[name] = dict(median=float(np.median(ts)), p90=float(np.percentile(ts, 90)))
-    out["note"] = "host wall clock around mvs_pair_batch (frames resident, records + matches + mask + points + indexes back in pageable memory)"
+        py[name] = dict(median=float(np.median(ts)), p90=float(np.percentile(ts, 90)))
+    out["python_ctypes"] = py
+    out["note"] = ("host wall clock around mvs_pair_batch, frames resident, median of 200 calls.  cpp_caller: call_us = records + matches + "
+                   "mask + points + indexes back in pageable memory, records_only_call_us = the 376-byte records alone; "
+                   "python_ctypes = the same call through mvslam_b200.capi (argument marshalling and fresh numpy outputs included)")
     return out
 
 

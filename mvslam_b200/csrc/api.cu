@@ -1029,11 +1029,12 @@ static int pair_batch_chunk(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, con
     }
     CK(d2h_rows(ctx, stage, results, sizeof(mvs_pair_result), ctx->d_results.p, sizeof(mvs_pair_result), sizeof(mvs_pair_result), (size_t)n_pairs));
     // details: the first min(capacity, stride) entries of every pair (a pair with n_matches > capacity is truncated).
-    // A synchronous call with more than 1 MB of details first reads the match counts back (one small round trip after
-    // the kernels) and copies only as many entries per pair as the fullest pair holds: with the VO threshold a pair keeps
-    // ~100 of its 256 slots, and the device-to-host copy is a fifth of an end-to-end step.
+    // A synchronous call with more than 1 MB of details (128 KB when they are staged and scattered by the host as well)
+    // first reads the match counts back (one small round trip after the kernels) and copies only as many entries per pair
+    // as the fullest pair holds: with the VO threshold a pair keeps ~100 of its slots, and the device-to-host copy is a
+    // fifth of an end-to-end step (ten VO pairs: 0.7 MB of slots, 100 us of a 280 us call).
     size_t wc = w;
-    if (ctx->allow_stage && !stage && detail_bytes > ((size_t)1 << 20)) {
+    if (ctx->allow_stage && detail_bytes > (stage ? (size_t)128 << 10 : (size_t)1 << 20)) {
         if (ctx->h_counts_cap < (size_t)n_pairs) {
             if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
             ctx->h_counts = nullptr; ctx->h_counts_cap = 0;

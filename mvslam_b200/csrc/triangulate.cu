@@ -214,11 +214,13 @@ finish_kernel(FinishArgs a)
 // K6 over K5's work list (SelectArgs::items): the (inlier, candidate) pairs of the whole batch, flattened, walked by a
 // grid that just fills the GPU.  Every lane of every warp that enters the 4x4 SVD has a point, whatever the pairs'
 // inlier counts are, and no block waits for its slowest decomposition; the rectified candidates come from K5
-// (PairState::Rr).  REF keeps V in shared memory (cv_svd_last_vt_sv): 64 registers, two 512-thread blocks per SM.
+// (PairState::Rr).  REF on a big job keeps V in shared memory (cv_svd_last_vt_sv): 64 registers, two 512-thread blocks per SM.
 // Results go to the same per-(pair, candidate, match) scratch as triangulate_kernel, so K7 is unchanged.
-constexpr int TI_THREADS = 512;
+// A job that one wave of small blocks covers is a latency problem, not a throughput one: 64-thread blocks spread its
+// FP64 chains over as many SMs as there are warps (V in registers: the shorter chain).
+constexpr int TI_THREADS_BIG = 512, TI_THREADS_SMALL = 64;
 
-template <bool REF, bool SMEM_V>
+template <bool REF, bool SMEM_V, int TI_THREADS>
 __global__ void __launch_bounds__(TI_THREADS, SMEM_V ? 2 : 1)
 triangulate_items_kernel(TriArgs a)
 {
@@ -285,16 +287,18 @@ void launch_triangulate(const TriArgs &a, int max_points, int n_pairs, cudaStrea
 cudaError_t launch_triangulate_items(const TriArgs &a, size_t max_items, cudaStream_t s)
 {
     const bool ref = a.solver == MVS_SOLVER_REFERENCE;
-    const size_t want = std::max<size_t>(1, (max_items * 4 + TI_THREADS - 1) / TI_THREADS);
+    const size_t lanes = std::max<size_t>(1, max_items * 4);
+    if (lanes <= (size_t)148 * TI_THREADS_BIG) {
+        const unsigned grid = (unsigned)((lanes + TI_THREADS_SMALL - 1) / TI_THREADS_SMALL);
+        if (ref) triangulate_items_kernel<true, false, TI_THREADS_SMALL><<<grid, TI_THREADS_SMALL, 0, s>>>(a);
+        else triangulate_items_kernel<false, false, TI_THREADS_SMALL><<<grid, TI_THREADS_SMALL, 0, s>>>(a);
+        return cudaSuccess;
+    }
     if (!ref) {
-        triangulate_items_kernel<false, false><<<(unsigned)std::min<size_t>(want, 148), TI_THREADS, 0, s>>>(a);
+        triangulate_items_kernel<false, false, TI_THREADS_BIG><<<148, TI_THREADS_BIG, 0, s>>>(a);
         return cudaSuccess;
     }
-    if (want <= 148) {   // a block per SM holds the whole job: V in registers is the shorter chain (latency, not throughput)
-        triangulate_items_kernel<true, false><<<(unsigned)want, TI_THREADS, 0, s>>>(a);
-        return cudaSuccess;
-    }
-    constexpr int smem = 16 * TI_THREADS * (int)sizeof(double);
+    constexpr int smem = 16 * TI_THREADS_BIG * (int)sizeof(double);
     // per-device opt-in above 48 KB, as in launch_match_finalize
     static std::mutex mu;
     static bool configured[64] = {};
@@ -304,12 +308,12 @@ cudaError_t launch_triangulate_items(const TriArgs &a, size_t max_items, cudaStr
     {
         std::lock_guard<std::mutex> lock(mu);
         if (dev < 0 || dev >= 64 || !configured[dev]) {
-            e = cudaFuncSetAttribute(triangulate_items_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            e = cudaFuncSetAttribute(triangulate_items_kernel<true, true, TI_THREADS_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             if (e != cudaSuccess) return e;
             if (dev >= 0 && dev < 64) configured[dev] = true;
         }
     }
-    triangulate_items_kernel<true, true><<<(unsigned)std::min<size_t>(want, 148 * 2), TI_THREADS, smem, s>>>(a);
+    triangulate_items_kernel<true, true, TI_THREADS_BIG><<<148 * 2, TI_THREADS_BIG, smem, s>>>(a);
     return cudaSuccess;
 }
 
