@@ -370,6 +370,18 @@ void flush_staged(mvs_ctx *ctx)     // call only after the stream has been synch
     ctx->h_stage_used = 0;
 }
 
+}  // namespace
+
+namespace mvs {
+bool pdl_enabled()
+{
+    static const bool on = [] { const char *e = std::getenv("MVS_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+}  // namespace mvs
+
+namespace {
+
 bool unit_z_intrinsics(const double Ki[9]) { return Ki[6] == 0.0 && Ki[7] == 0.0; }
 
 }  // namespace

@@ -33,6 +33,15 @@ constexpr int kIdxBits = 22;
 constexpr uint32_t kIdxMask = (1u << kIdxBits) - 1u;
 constexpr uint32_t kKeyNone = 0xFFFFFFFFu;
 
+// Programmatic dependent launch: a stage kernel launched with launch_dep() (kernels.h) may become resident while its
+// predecessor in the stream is still running; pdl_wait() -- the first statement of every stage kernel, before any read
+// of what earlier stages wrote -- blocks until that predecessor has completed and its writes are visible, and
+// pdl_launch_dependents() lets the next stage's blocks take their seats likewise.  The launch latency and block
+// scheduling of the short geometry kernels then overlap the previous kernel instead of following it (one VO pair is a
+// chain of seven launches).  Both are no-ops in a kernel that was launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // per-pair device state threaded through the stages
 struct PairState {
     int32_t status;

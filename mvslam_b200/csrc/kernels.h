@@ -4,6 +4,8 @@
 
 #include "common.cuh"
 
+#include <utility>
+
 namespace mvs {
 
 // frame table resident in HBM: descriptors as 2 x uint4 (32 B) per keypoint, keypoints as float2
@@ -139,5 +141,20 @@ void launch_select(const SelectArgs &a, int mode, bool const_z, int max_points, 
 void launch_triangulate(const TriArgs &a, int max_points, int n_pairs, cudaStream_t s);
 void launch_finish(const FinishArgs &a, int max_points, int n_pairs, cudaStream_t s);
 cudaError_t launch_triangulate_items(const TriArgs &a, size_t max_items, cudaStream_t s);
+
+bool pdl_enabled();   // api.cu: on unless MVS_PDL=0 (an A/B switch for tools/latency_probe, not a documented knob)
+
+// <<<grid, block, smem, s>>> with the programmatic-stream-serialization attribute (see pdl_wait, common.cuh)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_dep(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 }  // namespace mvs

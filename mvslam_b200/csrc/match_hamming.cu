@@ -171,6 +171,8 @@ __device__ __forceinline__ uint32_t refine_second_warp(const uint4 *desc, bool w
 __global__ void __launch_bounds__(FIN_THREADS, 2)   // 32 registers: two CTAs (pairs) per SM
 match_finalize_kernel(FinalizeArgs a)
 {
+    pdl_wait();
+    pdl_launch_dependents();
     extern __shared__ uint32_t keys[];  // sort_cap entries
     __shared__ int s_count;
     const int pair = blockIdx.x;
@@ -323,8 +325,7 @@ cudaError_t launch_match_finalize(const FinalizeArgs &a, int max_nq, int n_pairs
             if (dev >= 0 && dev < 64) configured[dev] = true;
         }
     }
-    match_finalize_kernel<<<n_pairs, FIN_THREADS, smem, s>>>(a);
-    return cudaSuccess;
+    return launch_dep(match_finalize_kernel, dim3(n_pairs), dim3(FIN_THREADS), smem, s, a);
 }
 
 void launch_normalize_points(const double *xy1, const double *xy2, int n, const NormArgs &a, double *pts, PairState *st,

@@ -230,6 +230,7 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
     uint32_t *tmem_slot = (uint32_t *)(tempty + NACC);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_items = a.q_tiles * a.n_pairs;
+    pdl_launch_dependents();   // K2's blocks may take the SMs this grid leaves free (small batches); they wait for this grid's end
 
     if (threadIdx.x == 0) {
         if (smem_u32(smem_raw) & 1023u) __trap();

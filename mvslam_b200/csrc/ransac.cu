@@ -267,6 +267,8 @@ __device__ __forceinline__ bool wave_rotate(double *At, double *V, double *W, in
 __global__ void __launch_bounds__(WAVE_HYP_PER_BLOCK * WAVE_LANES)
 hypotheses_reference_wave_kernel(HypArgs a)
 {
+    pdl_wait();
+    pdl_launch_dependents();
     __shared__ double s_state[WAVE_HYP_PER_BLOCK][WAVE_STATE];
     __shared__ double s_T[WAVE_HYP_PER_BLOCK][10];            // T1 (s, tx, ty), T2, mx1, my1, mx2, my2 of the sample
     const int slot = threadIdx.x / WAVE_LANES, sub = threadIdx.x % WAVE_LANES;
@@ -370,10 +372,10 @@ hypotheses_reference_wave_kernel(HypArgs a)
 
 constexpr int HYP_REF_THREADS = 64;
 __global__ void __launch_bounds__(HYP_REF_THREADS)
-hypotheses_reference_kernel(HypArgs a) { hypothesis_body<true>(a); }
+hypotheses_reference_kernel(HypArgs a) { pdl_wait(); pdl_launch_dependents(); hypothesis_body<true>(a); }
 
 __global__ void __launch_bounds__(HYP_THREADS)
-hypotheses_kernel(HypArgs a) { hypothesis_body<false>(a); }
+hypotheses_kernel(HypArgs a) { pdl_wait(); pdl_launch_dependents(); hypothesis_body<false>(a); }
 
 // a9 entry for explicit 8-point sets: p1s/p2s [n_sets][8][3]
 __global__ void __launch_bounds__(HYP_THREADS)
@@ -410,6 +412,8 @@ template <bool UNIT_Z, int MODE, bool LIT>
 __global__ void __launch_bounds__(SC_THREADS)
 score_kernel(ScoreArgs a)
 {
+    pdl_wait();
+    pdl_launch_dependents();
     constexpr int W = UNIT_Z ? 4 : 6;
     __shared__ __align__(16) double sp[SC_TILE * W];
     const int pair = blockIdx.z, tile = blockIdx.y;
@@ -522,6 +526,8 @@ template <bool UNIT_Z, int MODE, bool LIT, int SEL_THREADS>
 __global__ void __launch_bounds__(SEL_THREADS)
 select_kernel(SelectArgs a)
 {
+    pdl_wait();
+    pdl_launch_dependents();
     __shared__ uint32_t s_cnt[SEL_THREADS / 32];
     __shared__ int s_status, s_nin, s_k;
     __shared__ uint32_t s_item_base;
@@ -732,12 +738,12 @@ void launch_hypotheses(const HypArgs &a, int n_pairs, cudaStream_t s)
     b.n_pairs = n_pairs;
     const long long total = (long long)n_pairs * a.H;
     if (a.solver == MVS_SOLVER_REFERENCE && total <= 148LL * 32 * 16)   // few hypotheses: latency matters, 4 lanes per Jacobi
-        hypotheses_reference_wave_kernel<<<(unsigned)((total + WAVE_HYP_PER_BLOCK - 1) / WAVE_HYP_PER_BLOCK),
-                                           WAVE_HYP_PER_BLOCK * WAVE_LANES, 0, s>>>(b);
+        launch_dep(hypotheses_reference_wave_kernel, dim3((unsigned)((total + WAVE_HYP_PER_BLOCK - 1) / WAVE_HYP_PER_BLOCK)),
+                   dim3(WAVE_HYP_PER_BLOCK * WAVE_LANES), 0, s, b);
     else if (a.solver == MVS_SOLVER_REFERENCE)
-        hypotheses_reference_kernel<<<(unsigned)((total + HYP_REF_THREADS - 1) / HYP_REF_THREADS), HYP_REF_THREADS, 0, s>>>(b);
+        launch_dep(hypotheses_reference_kernel, dim3((unsigned)((total + HYP_REF_THREADS - 1) / HYP_REF_THREADS)), dim3(HYP_REF_THREADS), 0, s, b);
     else
-        hypotheses_kernel<<<(unsigned)((total + HYP_THREADS - 1) / HYP_THREADS), HYP_THREADS, 0, s>>>(b);
+        launch_dep(hypotheses_kernel, dim3((unsigned)((total + HYP_THREADS - 1) / HYP_THREADS)), dim3(HYP_THREADS), 0, s, b);
 }
 
 void launch_fundamental_sets(const double *p1s, const double *p2s, int n_sets, double *F_out, int solver, cudaStream_t s)
@@ -753,8 +759,8 @@ int score_tiles(int max_points) { return max_points > 0 ? (max_points + SC_TILE 
 template <bool UNIT_Z, int MODE>
 static void launch_score_t(const ScoreArgs &a, bool lit, dim3 grid, cudaStream_t s)
 {
-    if (lit) score_kernel<UNIT_Z, MODE, true><<<grid, SC_THREADS, 0, s>>>(a);
-    else score_kernel<UNIT_Z, MODE, false><<<grid, SC_THREADS, 0, s>>>(a);
+    if (lit) launch_dep(score_kernel<UNIT_Z, MODE, true>, grid, dim3(SC_THREADS), 0, s, a);
+    else launch_dep(score_kernel<UNIT_Z, MODE, false>, grid, dim3(SC_THREADS), 0, s, a);
 }
 
 void launch_score(const ScoreArgs &a, int mode, bool unit_z, int n_pairs, cudaStream_t s)
@@ -774,11 +780,11 @@ template <bool UNIT_Z, int MODE>
 static void launch_select_t(const SelectArgs &a, bool lit, bool small, int n_pairs, cudaStream_t s)
 {
     if (small) {
-        if (lit) select_kernel<UNIT_Z, MODE, true, SEL_THREADS_SMALL><<<n_pairs, SEL_THREADS_SMALL, 0, s>>>(a);
-        else select_kernel<UNIT_Z, MODE, false, SEL_THREADS_SMALL><<<n_pairs, SEL_THREADS_SMALL, 0, s>>>(a);
+        if (lit) launch_dep(select_kernel<UNIT_Z, MODE, true, SEL_THREADS_SMALL>, dim3(n_pairs), dim3(SEL_THREADS_SMALL), 0, s, a);
+        else launch_dep(select_kernel<UNIT_Z, MODE, false, SEL_THREADS_SMALL>, dim3(n_pairs), dim3(SEL_THREADS_SMALL), 0, s, a);
     } else {
-        if (lit) select_kernel<UNIT_Z, MODE, true, SEL_THREADS_BIG><<<n_pairs, SEL_THREADS_BIG, 0, s>>>(a);
-        else select_kernel<UNIT_Z, MODE, false, SEL_THREADS_BIG><<<n_pairs, SEL_THREADS_BIG, 0, s>>>(a);
+        if (lit) launch_dep(select_kernel<UNIT_Z, MODE, true, SEL_THREADS_BIG>, dim3(n_pairs), dim3(SEL_THREADS_BIG), 0, s, a);
+        else launch_dep(select_kernel<UNIT_Z, MODE, false, SEL_THREADS_BIG>, dim3(n_pairs), dim3(SEL_THREADS_BIG), 0, s, a);
     }
 }
 

@@ -208,6 +208,8 @@ template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 finish_kernel(FinishArgs a)
 {
+    pdl_wait();
+    pdl_launch_dependents();
     finish_body<THREADS>(a, blockIdx.x);
 }
 
@@ -224,6 +226,8 @@ template <bool REF, bool SMEM_V, int TI_THREADS>
 __global__ void __launch_bounds__(TI_THREADS, SMEM_V ? 2 : 1)
 triangulate_items_kernel(TriArgs a)
 {
+    pdl_wait();
+    pdl_launch_dependents();
     extern __shared__ double s_V[];   // SMEM_V: [16][TI_THREADS]
     const size_t total = (size_t)*a.item_total * 4;
     for (size_t it = (size_t)blockIdx.x * TI_THREADS + threadIdx.x; it < total; it += (size_t)gridDim.x * TI_THREADS) {
@@ -290,13 +294,11 @@ cudaError_t launch_triangulate_items(const TriArgs &a, size_t max_items, cudaStr
     const size_t lanes = std::max<size_t>(1, max_items * 4);
     if (lanes <= (size_t)148 * TI_THREADS_BIG) {
         const unsigned grid = (unsigned)((lanes + TI_THREADS_SMALL - 1) / TI_THREADS_SMALL);
-        if (ref) triangulate_items_kernel<true, false, TI_THREADS_SMALL><<<grid, TI_THREADS_SMALL, 0, s>>>(a);
-        else triangulate_items_kernel<false, false, TI_THREADS_SMALL><<<grid, TI_THREADS_SMALL, 0, s>>>(a);
-        return cudaSuccess;
+        if (ref) return launch_dep(triangulate_items_kernel<true, false, TI_THREADS_SMALL>, dim3(grid), dim3(TI_THREADS_SMALL), 0, s, a);
+        return launch_dep(triangulate_items_kernel<false, false, TI_THREADS_SMALL>, dim3(grid), dim3(TI_THREADS_SMALL), 0, s, a);
     }
     if (!ref) {
-        triangulate_items_kernel<false, false, TI_THREADS_BIG><<<148, TI_THREADS_BIG, 0, s>>>(a);
-        return cudaSuccess;
+        return launch_dep(triangulate_items_kernel<false, false, TI_THREADS_BIG>, dim3(148), dim3(TI_THREADS_BIG), 0, s, a);
     }
     constexpr int smem = 16 * TI_THREADS_BIG * (int)sizeof(double);
     // per-device opt-in above 48 KB, as in launch_match_finalize
@@ -313,14 +315,13 @@ cudaError_t launch_triangulate_items(const TriArgs &a, size_t max_items, cudaStr
             if (dev >= 0 && dev < 64) configured[dev] = true;
         }
     }
-    triangulate_items_kernel<true, true, TI_THREADS_BIG><<<148 * 2, TI_THREADS_BIG, smem, s>>>(a);
-    return cudaSuccess;
+    return launch_dep(triangulate_items_kernel<true, true, TI_THREADS_BIG>, dim3(148 * 2), dim3(TI_THREADS_BIG), smem, s, a);
 }
 
 void launch_finish(const FinishArgs &a, int max_points, int n_pairs, cudaStream_t s)
 {
-    if (max_points <= FIN2_SMALL_MAX_POINTS) finish_kernel<FIN2_THREADS_SMALL><<<n_pairs, FIN2_THREADS_SMALL, 0, s>>>(a);
-    else finish_kernel<FIN2_THREADS><<<n_pairs, FIN2_THREADS, 0, s>>>(a);
+    if (max_points <= FIN2_SMALL_MAX_POINTS) launch_dep(finish_kernel<FIN2_THREADS_SMALL>, dim3(n_pairs), dim3(FIN2_THREADS_SMALL), 0, s, a);
+    else launch_dep(finish_kernel<FIN2_THREADS>, dim3(n_pairs), dim3(FIN2_THREADS), 0, s, a);
 }
 
 }  // namespace mvs
