@@ -219,6 +219,22 @@ match_finalize_kernel(FinalizeArgs a)
     }
     __syncthreads();
     const int m = s_count;
+    if (m <= FIN_THREADS / 4) {
+        // few survivors (the VO threshold leaves ~100): rank sort, four lanes per key, two barriers instead of the
+        // log^2 of a bitonic network.  Keys are distinct (they end in the query index).
+        const int i = threadIdx.x >> 2, part = threadIdx.x & 3;
+        uint32_t mine = kKeyNone;
+        int rank = 0;
+        if (i < m) {
+            mine = keys[i];
+            for (int j = part; j < m; j += 4) rank += keys[j] < mine ? 1 : 0;
+        }
+        rank += __shfl_xor_sync(0xFFFFFFFFu, rank, 1);
+        rank += __shfl_xor_sync(0xFFFFFFFFu, rank, 2);
+        __syncthreads();
+        if (i < m && part == 0) keys[rank] = mine;
+        __syncthreads();
+    } else {
     int n2 = 1;
     while (n2 < m) n2 <<= 1;
     for (int i = m + threadIdx.x; i < n2; i += FIN_THREADS) keys[i] = kKeyNone;
@@ -235,6 +251,7 @@ match_finalize_kernel(FinalizeArgs a)
             }
             __syncthreads();
         }
+    }
 
     mvs_match *out = a.matches + (size_t)pair * a.q_stride;
     double *pts = a.points ? a.points + (size_t)pair * a.q_stride * 6 : nullptr;
