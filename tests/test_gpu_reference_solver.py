@@ -84,3 +84,29 @@ def test_borderline_points_near_the_threshold(ctx, tsukuba, tsukuba_golden):
             border += int((np.abs(r - thr) < 1e-9 * thr).sum()); total += len(r)
     print(f"borderline residuals: {border} of {total}")
     assert border == 0
+
+
+@pytest.mark.parametrize("slv", ["reference", "fast"])
+@pytest.mark.parametrize("max_dist", [10.0, -1.0])
+def test_every_launch_shape_of_the_tail_gives_the_same_bytes(ctx, tsukuba, slv, max_dist):
+    """The select / triangulate / finish kernels pick their block size and the triangulation's V storage (registers or
+    shared memory, csrc/triangulate.cu launch_triangulate_items) from the size of the batch: one pair at a time, a
+    ten-pair VO batch and a 600-pair batch must return identical records, masks, clouds and matches."""
+    descs = [tsukuba[f"desc{i}"] for i in range(1, 6)]; kps = [tsukuba[f"kp{i}"] for i in range(1, 6)]
+    ctx.frames_upload(descs, kps)
+    base = [(0, 1), (1, 2), (2, 3), (3, 4), (0, 4), (1, 0)]
+    kw = dict(max_dist=max_dist, H=1 if slv == "reference" else 64, seed=3, solver=slv)
+    one = []
+    for k, pr in enumerate(base):      # pair k samples with pair id k, as it will at position k of a batch
+        r, d = ctx.pair_batch([pr], tsukuba["K"], pair_id_base=k, **kw)
+        one.append((r[0], {key: np.array(v[0]) for key, v in d.items() if key != "capacity"}))
+    assert sum(int(r["status"] == 0) for r, _ in one) >= 4
+    for n in (10, 600):
+        r, d = ctx.pair_batch(base + [base[0]] * (n - 6), tsukuba["K"], pair_id_base=0, **kw)   # the rest only makes the batch large
+        for k in range(6):
+            assert r[k].tobytes() == one[k][0].tobytes(), (n, k)
+            nm, npnt = int(r[k]["n_matches"]), int(r[k]["n_points"])
+            assert np.array_equal(d["matches"][k][:nm], one[k][1]["matches"][:nm])
+            assert np.array_equal(d["mask"][k][:nm], one[k][1]["mask"][:nm])
+            assert np.array_equal(d["points"][k][:npnt], one[k][1]["points"][:npnt])
+            assert np.array_equal(d["indexes"][k][:npnt], one[k][1]["indexes"][:npnt])
