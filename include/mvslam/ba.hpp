@@ -1,7 +1,7 @@
 // ba.hpp — ba_frame_pose_and_point, sfm_refine and pnp_refine with the reference's signatures
 // (reference source/vision/ba.hpp:25-36, source/vision/sfm.hpp:69-76, source/vision/pnp.hpp:41-46), forwarding to
 // mvs_ba_solve_batch.  The reference builds a GTSAM factor graph (ba.cpp:26-156); here the same cost function is minimised
-// on the device (see mvslam_b200.h).  At most two frames per problem — all three reference callers use one or two.
+// on the device (see mvslam_b200.h).  Up to 16 frames per problem (all three reference callers use one or two).
 #pragma once
 #include <cmath>
 #include <unordered_map>

@@ -306,7 +306,8 @@ int mvs_pnp_solve_batch(mvs_ctx *ctx, const double *world, const double *image, 
 
 /* ---- ba_frame_pose_and_point (source/vision/ba.cpp:26-156, decl source/vision/ba.hpp:25-36), the optimisation behind
  *      sfm_refine (sfm-refine.cpp:20-139), pnp_refine (pnp-refine.cpp:16-110) and VisualOdometer::track_refine
- *      (visual-odometer.cpp:640-800): Levenberg-Marquardt over 1 or 2 camera poses (camera to world) and their points
+ *      (visual-odometer.cpp:640-800): Levenberg-Marquardt over 1 .. 16 camera poses (camera to world; the reference's callers
+ *      pass one or two, which have their own kernel) and their points
  *      with Gaussian priors (prior mean = the guess) and projection factors; estimates come back with the marginal
  *      covariances gtsam::Marginals would give (blocks of the inverse Gauss-Newton Hessian).
  *      n_problems independent problems per call; problem i owns n_frames[i] / n_points[i] / n_obs[i] consecutive rows

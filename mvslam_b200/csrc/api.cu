@@ -73,7 +73,7 @@ struct mvs_ctx {
     mvs::OrbGeom orb_geom;
     DevBuf o_tabs, o_stage, o_pyr, o_blur, o_cxy, o_cval, o_cnt, o_kidx, o_kcnt, o_off, o_kp, o_desc;
     DevBuf p_world, p_image, p_off, p_table, p_poses, p_valid, p_pc, p_maskws, p_mask, p_counts, p_results;
-    DevBuf b_foff, b_poff, b_R, b_t, b_pc, b_X, b_xc, b_obs, b_ooff, b_ws, b_Ro, b_to, b_pco, b_Xo, b_xco, b_res;
+    DevBuf b_foff, b_poff, b_R, b_t, b_pc, b_X, b_xc, b_obs, b_ooff, b_ws, b_wsm, b_wsm_off, b_wsobs, b_Ro, b_to, b_pco, b_Xo, b_xco, b_res;
     int32_t *o_pinned = nullptr;
     int32_t *h_counts = nullptr;         // pinned: per-pair match counts read back before the detail copies (synchronous calls)
     size_t h_counts_cap = 0;
@@ -454,7 +454,7 @@ void mvs_destroy(mvs_ctx *ctx)
                       &ctx->o_off, &ctx->o_kp, &ctx->o_desc, &ctx->p_world, &ctx->p_image, &ctx->p_off, &ctx->p_table,
                       &ctx->p_poses, &ctx->p_valid, &ctx->p_pc, &ctx->p_maskws, &ctx->p_mask, &ctx->p_counts, &ctx->p_results,
                       &ctx->b_foff, &ctx->b_poff, &ctx->b_R, &ctx->b_t, &ctx->b_pc, &ctx->b_X, &ctx->b_xc, &ctx->b_obs, &ctx->b_ooff,
-                      &ctx->b_ws, &ctx->b_Ro, &ctx->b_to, &ctx->b_pco, &ctx->b_Xo, &ctx->b_xco, &ctx->b_res};
+                      &ctx->b_ws, &ctx->b_wsm, &ctx->b_wsm_off, &ctx->b_wsobs, &ctx->b_Ro, &ctx->b_to, &ctx->b_pco, &ctx->b_Xo, &ctx->b_xco, &ctx->b_res};
     if (ctx->o_pinned) cudaFreeHost(ctx->o_pinned);
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
@@ -1472,7 +1472,7 @@ int mvs_ba_solve_batch(mvs_ctx *ctx, int n_problems, const double K[9],
     std::vector<int32_t> foff(n_problems + 1, 0), poff(n_problems + 1, 0), ooff(n_problems + 1, 0);
     for (int i = 0; i < n_problems; ++i) {
         if (n_frames[i] < 1 || n_points[i] < 0 || n_obs[i] < 0) return fail(ctx, MVS_E_BAD_ARG, "ba_solve: bad problem size");
-        if (n_frames[i] > 2) return fail(ctx, MVS_E_UNSUPPORTED, "ba_solve: more than 2 frames in a problem");
+        if (n_frames[i] > BA_MAX_FRAMES) return fail(ctx, MVS_E_UNSUPPORTED, "ba_solve: more than 16 frames in a problem");
         if ((int64_t)poff[i] + n_points[i] > 0x7FFFFFFF || (int64_t)ooff[i] + n_obs[i] > 0x7FFFFFFF)
             return fail(ctx, MVS_E_UNSUPPORTED, "ba_solve: more than 2^31 points or observations");
         foff[i + 1] = foff[i] + n_frames[i]; poff[i + 1] = poff[i] + n_points[i]; ooff[i + 1] = ooff[i] + n_obs[i];
@@ -1507,6 +1507,18 @@ int mvs_ba_solve_batch(mvs_ctx *ctx, int n_problems, const double K[9],
     CK(up(ctx->b_X, points, NP * 24)); CK(up(ctx->b_xc, point_prior_cov, NP * 72));
     CK(up(ctx->b_obs, sorted.data(), NO * sizeof(mvs_ba_observation))); CK(up(ctx->b_ooff, pobs.data(), pobs.size() * 4));
     CK(ctx->b_ws.ensure(std::max<size_t>(NP, 1) * 48 * 8));
+    // problems with more than two frames: their own per-point workspace (12 + 36 F doubles) and one 27-double slot per observation
+    int min_frames = n_frames[0], max_frames = n_frames[0];
+    std::vector<long long> wsm(n_problems + 1, 0);
+    for (int i = 0; i < n_problems; ++i) {
+        min_frames = std::min(min_frames, (int)n_frames[i]); max_frames = std::max(max_frames, (int)n_frames[i]);
+        wsm[i + 1] = wsm[i] + (n_frames[i] > 2 ? (long long)n_points[i] * (12 + 36 * n_frames[i]) : 0);
+    }
+    if (max_frames > 2) {
+        CK(up(ctx->b_wsm_off, wsm.data(), wsm.size() * sizeof(long long)));
+        CK(ctx->b_wsm.ensure(std::max<size_t>((size_t)wsm[n_problems], 1) * 8));
+        CK(ctx->b_wsobs.ensure(std::max<size_t>(NO, 1) * 27 * 8));
+    }
     CK(ctx->b_Ro.ensure(NF * 72)); CK(ctx->b_to.ensure(NF * 24)); CK(ctx->b_pco.ensure(NF * 288));
     CK(ctx->b_Xo.ensure(std::max<size_t>(NP, 1) * 24)); CK(ctx->b_xco.ensure(std::max<size_t>(NP, 1) * 72));
     CK(ctx->b_res.ensure((size_t)n_problems * sizeof(mvs_ba_result)));
@@ -1517,6 +1529,7 @@ int mvs_ba_solve_batch(mvs_ctx *ctx, int n_problems, const double K[9],
     a.points = ctx->b_X.as<double>(); a.point_prior_cov = ctx->b_xc.as<double>();
     a.obs = ctx->b_obs.as<mvs_ba_observation>(); a.point_obs_off = ctx->b_ooff.as<int32_t>();
     a.ws = ctx->b_ws.as<double>();
+    if (max_frames > 2) { a.ws_multi = ctx->b_wsm.as<double>(); a.ws_multi_off = ctx->b_wsm_off.as<long long>(); a.ws_obs = ctx->b_wsobs.as<double>(); }
     a.pose_R_out = ctx->b_Ro.as<double>(); a.pose_t_out = ctx->b_to.as<double>(); a.pose_cov_out = ctx->b_pco.as<double>();
     a.points_out = ctx->b_Xo.as<double>(); a.point_cov_out = ctx->b_xco.as<double>();
     a.results = ctx->b_res.as<mvs_ba_result>();
@@ -1526,7 +1539,7 @@ int mvs_ba_solve_batch(mvs_ctx *ctx, int n_problems, const double K[9],
     a.abs_tol = !params || params->absolute_tolerance == 0 ? 1e-5 : params->absolute_tolerance;    // GTSAM absoluteErrorTol; < 0: off
     {
         StageTimer t(ctx, MVS_STAGE_BA);
-        CK(launch_ba(a, n_problems, ctx->stream));
+        CK(launch_ba(a, n_problems, min_frames, max_frames, ctx->stream));
     }
     CK(cudaMemcpyAsync(results, ctx->b_res.p, (size_t)n_problems * sizeof(mvs_ba_result), cudaMemcpyDeviceToHost, ctx->stream));
     if (pose_R_out) CK(cudaMemcpyAsync(pose_R_out, ctx->b_Ro.p, NF * 72, cudaMemcpyDeviceToHost, ctx->stream));

@@ -1,4 +1,5 @@
-// ba.cu — bundle adjustment of one or two camera poses and their points on the device: the optimisation problem that
+// ba.cu — bundle adjustment of camera poses and their points on the device (one or two poses: ba_solve_kernel, the shape
+// of every reference caller; three to sixteen: ba_solve_multi_kernel): the optimisation problem that
 // ba_frame_pose_and_point states through GTSAM (reference source/vision/ba.cpp:26-156) for its callers sfm_refine
 // (source/vision/sfm-refine.cpp:20-139), pnp_refine (source/vision/pnp-refine.cpp:16-110) and
 // VisualOdometer::track_refine (source/front-end/visual-odometer.cpp:640-800) — SURVEY.md §8f rank 4.
@@ -248,7 +249,7 @@ ba_solve_kernel(BaArgs a)
     if (tid < 12 * F) { const int f = tid / 12, k = tid % 12; s_pose[tid] = k < 9 ? a.pose_R[(size_t)(f0 + f) * 9 + k] : a.pose_t[(size_t)(f0 + f) * 3 + k - 9]; }
     if (tid == 0) {
         s_lambda = a.lambda0; s_flag[3] = 0;
-        for (int f = 0; f < F; ++f) {
+        for (int f = 0; f < F && f < 2; ++f) {
             const double *C = a.pose_prior_cov + (size_t)(f0 + f) * 36;
             s_flag[f] = C[0] == C[0];                 // NaN = no prior
             if (!s_flag[f]) continue;
@@ -264,7 +265,8 @@ ba_solve_kernel(BaArgs a)
         }
     }
     __syncthreads();
-    if (s_flag[3] == 2 || F < 1 || F > 2) { if (tid == 0) { res->status = F < 1 || F > 2 ? MVS_E_UNSUPPORTED : MVS_E_BAD_ARG; res->iterations = 0; } return; }
+    if (F > 2) return;                                // ba_solve_multi_kernel's problem
+    if (s_flag[3] == 2 || F < 1) { if (tid == 0) { res->status = F < 1 ? MVS_E_UNSUPPORTED : MVS_E_BAD_ARG; res->iterations = 0; } return; }
 
     // current points live in a.points_out (initialised from the guesses); the guesses stay in a.points as prior means
     for (int j = tid; j < P; j += BA_THREADS)
@@ -543,13 +545,437 @@ ba_solve_kernel(BaArgs a)
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// The same optimisation for 3 .. BA_MAX_FRAMES camera poses (ba_frame_pose_and_point takes any number of frames,
+// ba.cpp:26-156; none of the reference's callers passes more than two, so this path is built for generality, not speed).
+// One CTA per problem again, same Levenberg-Marquardt policy, same Schur complement; what changes is where the sums
+// live: the reduced camera system has up to 96 unknowns, so it is assembled entry by entry -- thread (r, c) adds the
+// points' contributions in point order -- instead of in per-thread accumulator rows, and factored by a block-parallel
+// Cholesky.  Every sum has a fixed order: the result does not depend on scheduling.
+//   per point (ws_multi): V(6) g(3) candidate X(3), W[6F][3], Y = W (V + lambda I)^-1 [6F][3]
+//   per observation (ws_obs): its 6x6 camera block (21) and camera gradient (6)
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int BAM_THREADS = 128;
+
+__device__ __forceinline__ double block_sum_m(double v, double *scratch)
+{
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0.0;
+    for (int w = 0; w < BAM_THREADS / 32; ++w) r += scratch[w];
+    __syncthreads();
+    return r;
+}
+
+// in-place Cholesky of the lower triangle of the n x n matrix S (row-major, shared memory) by the whole block;
+// returns false (for every thread) if a pivot is not positive
+__device__ bool block_cholesky(double *S, int n, int *s_ok)
+{
+    const int tid = threadIdx.x;
+    if (tid == 0) *s_ok = 1;
+    __syncthreads();
+    for (int k = 0; k < n; ++k) {
+        if (tid == 0) {
+            const double d = S[k * n + k];
+            if (!(d > 0.0)) *s_ok = 0; else S[k * n + k] = sqrt(d);
+        }
+        __syncthreads();
+        if (!*s_ok) break;
+        const double dk = S[k * n + k];
+        for (int r = k + 1 + tid; r < n; r += BAM_THREADS) S[r * n + k] /= dk;
+        __syncthreads();
+        const int m = n - k - 1;
+        for (int idx = tid; idx < m * m; idx += BAM_THREADS) {
+            const int r = k + 1 + idx / m, c = k + 1 + idx % m;
+            if (c <= r) S[r * n + c] -= S[r * n + k] * S[c * n + k];
+        }
+        __syncthreads();
+    }
+    const bool ok = *s_ok != 0;
+    __syncthreads();
+    return ok;
+}
+
+// L L^T x = b with L the lower triangle of S; one thread
+__device__ void lower_solve(const double *L, int n, const double *b, double *x)
+{
+    for (int r = 0; r < n; ++r) {
+        double s = b[r];
+        for (int k = 0; k < r; ++k) s -= L[r * n + k] * x[k];
+        x[r] = s / L[r * n + r];
+    }
+    for (int r = n - 1; r >= 0; --r) {
+        double s = x[r];
+        for (int k = r + 1; k < n; ++k) s -= L[k * n + r] * x[k];
+        x[r] = s / L[r * n + r];
+    }
+}
+
+__global__ void __launch_bounds__(BAM_THREADS)
+ba_solve_multi_kernel(BaArgs a, int max_frames)
+{
+    extern __shared__ double smem[];
+    const int prob = blockIdx.x, tid = threadIdx.x;
+    const int f0 = a.frame_off[prob], F = a.frame_off[prob + 1] - f0;
+    if (F <= 2) return;                               // ba_solve_kernel's problem
+    mvs_ba_result *res = a.results + prob;
+    if (F > max_frames || F > BA_MAX_FRAMES) { if (tid == 0) { res->status = MVS_E_UNSUPPORTED; res->iterations = 0; } return; }
+    const int p0 = a.point_off[prob], P = a.point_off[prob + 1] - p0;
+    const int n = 6 * F, NM = 6 * max_frames;
+    const int o0 = a.point_obs_off[p0], o1 = a.point_obs_off[p0 + P];
+    const int WS = 12 + 36 * F;
+    double *wsp = a.ws_multi + a.ws_multi_off[prob];
+
+    double *s_S = smem;                               // [n][n] reduced system, then its factor
+    double *s_C = s_S + NM * NM;                      // [n][n] its inverse (covariance phase)
+    double *s_U = s_C + NM * NM;                      // [F][27] camera blocks (21) + gradient (6): priors, then priors + observations
+    double *s_b = s_U + max_frames * 27;              // [n]
+    double *s_dc = s_b + NM;                          // [n]
+    double *s_pose = s_dc + NM;                       // [F][12]
+    double *s_cand = s_pose + max_frames * 12;        // [F][12]
+    double *s_pinfo = s_cand + max_frames * 12;       // [F][36]
+    double *s_scr = s_pinfo + max_frames * 36;        // [8]
+    __shared__ int s_has[BA_MAX_FRAMES], s_ok, s_bad;
+    __shared__ double s_lambda;
+
+    for (int k = tid; k < 12 * F; k += BAM_THREADS) {
+        const int f = k / 12, q = k % 12;
+        s_pose[k] = q < 9 ? a.pose_R[(size_t)(f0 + f) * 9 + q] : a.pose_t[(size_t)(f0 + f) * 3 + q - 9];
+    }
+    if (tid == 0) { s_lambda = a.lambda0; s_bad = 0; }
+    __syncthreads();
+    if (tid < F) {
+        const int f = tid;
+        const double *C = a.pose_prior_cov + (size_t)(f0 + f) * 36;
+        s_has[f] = C[0] == C[0];                      // NaN = no prior
+        if (s_has[f]) {
+            double L[36], col[6], x[6];
+            for (int k = 0; k < 36; ++k) L[k] = C[k];
+            if (!cholesky<6>(L)) s_bad = 1;
+            else
+                for (int c = 0; c < 6; ++c) {
+                    for (int k = 0; k < 6; ++k) col[k] = k == c ? 1.0 : 0.0;
+                    cholesky_solve<6>(L, col, x);
+                    for (int k = 0; k < 6; ++k) s_pinfo[f * 36 + k * 6 + c] = x[k];
+                }
+        }
+    }
+    __syncthreads();
+    if (s_bad) { if (tid == 0) { res->status = MVS_E_BAD_ARG; res->iterations = 0; } return; }
+
+    for (int j = tid; j < P; j += BAM_THREADS)
+        for (int k = 0; k < 3; ++k) a.points_out[(size_t)(p0 + j) * 3 + k] = a.points[(size_t)(p0 + j) * 3 + k];
+
+    // pose-prior residual e (6) of frame f at `poses`, optionally its Jacobian
+    auto prior_residual = [&](const double *poses, int f, double e[6], double *J /*36 or null*/) {
+        const double *Rg = a.pose_R + (size_t)(f0 + f) * 9, *tg = a.pose_t + (size_t)(f0 + f) * 3;
+        const double *R = poses + f * 12, *t = R + 9;
+        double Rr[9];
+        for (int r = 0; r < 3; ++r) for (int q = 0; q < 3; ++q) Rr[r * 3 + q] = Rg[r] * R[q] + Rg[3 + r] * R[3 + q] + Rg[6 + r] * R[6 + q];
+        so3_log(Rr, e);
+        for (int r = 0; r < 3; ++r) e[3 + r] = Rg[r] * (t[0] - tg[0]) + Rg[3 + r] * (t[1] - tg[1]) + Rg[6 + r] * (t[2] - tg[2]);
+        if (!J) return;
+        double Jr[9];
+        so3_jr_inv(e, Jr);
+        for (int k = 0; k < 36; ++k) J[k] = 0.0;
+        for (int r = 0; r < 3; ++r) for (int q = 0; q < 3; ++q) { J[r * 6 + q] = Jr[r * 3 + q]; J[(3 + r) * 6 + 3 + q] = Rr[r * 3 + q]; }
+    };
+
+    auto cost_of = [&](bool cand) -> double {
+        const double *poses = cand ? s_cand : s_pose;
+        double c = 0.0;
+        for (int j = tid; j < P; j += BAM_THREADS) {
+            const size_t gp = (size_t)(p0 + j);
+            const double *X = cand ? wsp + (size_t)j * WS + 9 : a.points_out + gp * 3;
+            const double *Cp = a.point_prior_cov + gp * 9;
+            if (Cp[0] == Cp[0]) {
+                const double V[6] = {Cp[0], Cp[1], Cp[2], Cp[4], Cp[5], Cp[8]};
+                double I[6];
+                sym3_inverse(V, I);
+                const double e[3] = {X[0] - a.points[gp * 3], X[1] - a.points[gp * 3 + 1], X[2] - a.points[gp * 3 + 2]};
+                c += 0.5 * (e[0] * (I[0] * e[0] + I[1] * e[1] + I[2] * e[2]) + e[1] * (I[1] * e[0] + I[3] * e[1] + I[4] * e[2]) +
+                            e[2] * (I[2] * e[0] + I[4] * e[1] + I[5] * e[2]));
+            }
+            for (int o = a.point_obs_off[gp]; o < a.point_obs_off[gp + 1]; ++o) {
+                const mvs_ba_observation &ob = a.obs[o];
+                Proj pr;
+                project(a, poses + ob.frame * 12, poses + ob.frame * 12 + 9, X, ob.uv, false, pr);
+                double I[3];
+                info2(ob.cov, I);
+                c += 0.5 * (pr.e[0] * (I[0] * pr.e[0] + I[1] * pr.e[1]) + pr.e[1] * (I[1] * pr.e[0] + I[2] * pr.e[1]));
+            }
+        }
+        if (tid < F && s_has[tid]) {
+            double e[6];
+            prior_residual(poses, tid, e, nullptr);
+            for (int r = 0; r < 6; ++r) { double s = 0.0; for (int q = 0; q < 6; ++q) s += s_pinfo[tid * 36 + r * 6 + q] * e[q]; c += 0.5 * e[r] * s; }
+        }
+        return block_sum_m(c, s_scr);
+    };
+
+    // linearise at the current state: per point V, g, W; per observation its camera block; s_U = camera blocks and gradients
+    auto linearise = [&]() {
+        for (int j = tid; j < P; j += BAM_THREADS) {
+            const size_t gp = (size_t)(p0 + j);
+            const double *X = a.points_out + gp * 3;
+            double *w = wsp + (size_t)j * WS, *W = w + 12;
+            double V[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
+            for (int k = 0; k < 18 * F; ++k) W[k] = 0.0;
+            const double *Cp = a.point_prior_cov + gp * 9;
+            if (Cp[0] == Cp[0]) {
+                const double Vc[6] = {Cp[0], Cp[1], Cp[2], Cp[4], Cp[5], Cp[8]};
+                double I[6];
+                sym3_inverse(Vc, I);
+                const double e[3] = {X[0] - a.points[gp * 3], X[1] - a.points[gp * 3 + 1], X[2] - a.points[gp * 3 + 2]};
+                for (int k = 0; k < 6; ++k) V[k] += I[k];
+                g[0] += I[0] * e[0] + I[1] * e[1] + I[2] * e[2];
+                g[1] += I[1] * e[0] + I[3] * e[1] + I[4] * e[2];
+                g[2] += I[2] * e[0] + I[4] * e[1] + I[5] * e[2];
+            }
+            for (int o = a.point_obs_off[gp]; o < a.point_obs_off[gp + 1]; ++o) {
+                const mvs_ba_observation &ob = a.obs[o];
+                const int f = ob.frame;
+                Proj pr;
+                project(a, s_pose + f * 12, s_pose + f * 12 + 9, X, ob.uv, true, pr);
+                double I[3];
+                info2(ob.cov, I);
+                double Ac[12], AX[6];
+                for (int c = 0; c < 6; ++c) { Ac[c] = I[0] * pr.Jc[c] + I[1] * pr.Jc[6 + c]; Ac[6 + c] = I[1] * pr.Jc[c] + I[2] * pr.Jc[6 + c]; }
+                for (int c = 0; c < 3; ++c) { AX[c] = I[0] * pr.JX[c] + I[1] * pr.JX[3 + c]; AX[3 + c] = I[1] * pr.JX[c] + I[2] * pr.JX[3 + c]; }
+                const double ie0 = I[0] * pr.e[0] + I[1] * pr.e[1], ie1 = I[1] * pr.e[0] + I[2] * pr.e[1];
+                double *uo = a.ws_obs + (size_t)o * 27;
+                int k = 0;
+                for (int r = 0; r < 6; ++r) {
+                    for (int c = r; c < 6; ++c) uo[k++] = pr.Jc[r] * Ac[c] + pr.Jc[6 + r] * Ac[6 + c];
+                    uo[21 + r] = pr.Jc[r] * ie0 + pr.Jc[6 + r] * ie1;
+                    for (int c = 0; c < 3; ++c) W[f * 18 + r * 3 + c] += pr.Jc[r] * AX[c] + pr.Jc[6 + r] * AX[3 + c];
+                }
+                V[0] += pr.JX[0] * AX[0] + pr.JX[3] * AX[3]; V[1] += pr.JX[0] * AX[1] + pr.JX[3] * AX[4]; V[2] += pr.JX[0] * AX[2] + pr.JX[3] * AX[5];
+                V[3] += pr.JX[1] * AX[1] + pr.JX[4] * AX[4]; V[4] += pr.JX[1] * AX[2] + pr.JX[4] * AX[5]; V[5] += pr.JX[2] * AX[2] + pr.JX[5] * AX[5];
+                for (int c = 0; c < 3; ++c) g[c] += pr.JX[c] * ie0 + pr.JX[3 + c] * ie1;
+            }
+            for (int k = 0; k < 6; ++k) w[k] = V[k];
+            for (int k = 0; k < 3; ++k) w[6 + k] = g[k];
+        }
+        // pose priors: J^T info J and J^T info e of every frame that has one
+        for (int k = tid; k < 27 * F; k += BAM_THREADS) s_U[k] = 0.0;
+        __syncthreads();
+        if (tid < F && s_has[tid]) {
+            const int f = tid;
+            double e[6], J[36], IJ[36], Ie[6];
+            prior_residual(s_pose, f, e, J);
+            for (int r = 0; r < 6; ++r) {
+                double s = 0.0;
+                for (int q = 0; q < 6; ++q) s += s_pinfo[f * 36 + r * 6 + q] * e[q];
+                Ie[r] = s;
+                for (int c = 0; c < 6; ++c) { double v = 0.0; for (int q = 0; q < 6; ++q) v += s_pinfo[f * 36 + r * 6 + q] * J[q * 6 + c]; IJ[r * 6 + c] = v; }
+            }
+            int k = 0;
+            for (int r = 0; r < 6; ++r) {
+                for (int c = r; c < 6; ++c) { double v = 0.0; for (int q = 0; q < 6; ++q) v += J[q * 6 + r] * IJ[q * 6 + c]; s_U[f * 27 + k++] = v; }
+                double v = 0.0;
+                for (int q = 0; q < 6; ++q) v += J[q * 6 + r] * Ie[q];
+                s_U[f * 27 + 21 + r] = v;
+            }
+        }
+        __syncthreads();
+        // + the observations of each frame, in observation order
+        for (int k = tid; k < 27 * F; k += BAM_THREADS) {
+            const int f = k / 27, q = k % 27;
+            double s = s_U[k];
+            for (int o = o0; o < o1; ++o)
+                if (a.obs[o].frame == f) s += a.ws_obs[(size_t)o * 27 + q];
+            s_U[k] = s;
+        }
+        __syncthreads();
+    };
+
+    // S = U + lambda I - sum_j W_j (V_j + lambda I)^-1 W_j^T (lower triangle), b likewise when with_rhs; factor; false if not PD
+    auto reduced_system = [&](double lam, bool with_rhs) -> bool {
+        for (int j = tid; j < P; j += BAM_THREADS) {
+            double *w = wsp + (size_t)j * WS;
+            const double *W = w + 12;
+            double *Y = w + 12 + 18 * F;
+            const double Vl[6] = {w[0] + lam, w[1], w[2], w[3] + lam, w[4], w[5] + lam};
+            double Vi[6];
+            sym3_inverse(Vl, Vi);
+            for (int r = 0; r < n; ++r) {
+                Y[r * 3] = W[r * 3] * Vi[0] + W[r * 3 + 1] * Vi[1] + W[r * 3 + 2] * Vi[2];
+                Y[r * 3 + 1] = W[r * 3] * Vi[1] + W[r * 3 + 1] * Vi[3] + W[r * 3 + 2] * Vi[4];
+                Y[r * 3 + 2] = W[r * 3] * Vi[2] + W[r * 3 + 1] * Vi[4] + W[r * 3 + 2] * Vi[5];
+            }
+        }
+        __syncthreads();
+        for (int idx = tid; idx < n * n; idx += BAM_THREADS) {
+            const int r = idx / n, c = idx % n;
+            if (c > r) continue;
+            double s = 0.0;
+            for (int j = 0; j < P; ++j) {
+                const double *w = wsp + (size_t)j * WS;
+                const double *Wc = w + 12 + c * 3, *Yr = w + 12 + 18 * F + r * 3;
+                s += Yr[0] * Wc[0] + Yr[1] * Wc[1] + Yr[2] * Wc[2];
+            }
+            double u = 0.0;
+            if (r / 6 == c / 6) { const int f = r / 6; u = s_U[f * 27 + sym_idx(c % 6, r % 6, 6)]; }
+            s_S[r * n + c] = u + (r == c ? lam : 0.0) - s;
+        }
+        if (with_rhs)
+            for (int r = tid; r < n; r += BAM_THREADS) {
+                double s = 0.0;
+                for (int j = 0; j < P; ++j) {
+                    const double *w = wsp + (size_t)j * WS;
+                    const double *Yr = w + 12 + 18 * F + r * 3;
+                    s += Yr[0] * w[6] + Yr[1] * w[7] + Yr[2] * w[8];
+                }
+                s_b[r] = -s_U[(r / 6) * 27 + 21 + r % 6] + s;
+            }
+        __syncthreads();
+        return block_cholesky(s_S, n, &s_ok);
+    };
+
+    auto schur_step = [&]() -> bool {
+        const double lam = s_lambda;
+        if (!reduced_system(lam, true)) return false;
+        if (tid == 0) lower_solve(s_S, n, s_b, s_dc);
+        __syncthreads();
+        if (tid < F) {
+            const int f = tid;
+            const double *R = s_pose + f * 12, *t = R + 9, *d = s_dc + f * 6;
+            double E[9];
+            so3_exp(d, E);
+            double *Rn = s_cand + f * 12;
+            for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) Rn[r * 3 + c] = R[r * 3] * E[c] + R[r * 3 + 1] * E[3 + c] + R[r * 3 + 2] * E[6 + c];
+            for (int r = 0; r < 3; ++r) Rn[9 + r] = t[r] + R[r * 3] * d[3] + R[r * 3 + 1] * d[4] + R[r * 3 + 2] * d[5];
+        }
+        for (int j = tid; j < P; j += BAM_THREADS) {
+            double *w = wsp + (size_t)j * WS;
+            const double *W = w + 12;
+            const double Vl[6] = {w[0] + lam, w[1], w[2], w[3] + lam, w[4], w[5] + lam};
+            double Vi[6];
+            sym3_inverse(Vl, Vi);
+            double r3[3] = {w[6], w[7], w[8]};               // g_X + W^T dc
+            for (int r = 0; r < n; ++r) { r3[0] += W[r * 3] * s_dc[r]; r3[1] += W[r * 3 + 1] * s_dc[r]; r3[2] += W[r * 3 + 2] * s_dc[r]; }
+            const double *X = a.points_out + (size_t)(p0 + j) * 3;
+            w[9] = X[0] - (Vi[0] * r3[0] + Vi[1] * r3[1] + Vi[2] * r3[2]);
+            w[10] = X[1] - (Vi[1] * r3[0] + Vi[3] * r3[1] + Vi[4] * r3[2]);
+            w[11] = X[2] - (Vi[2] * r3[0] + Vi[4] * r3[1] + Vi[5] * r3[2]);
+        }
+        __syncthreads();
+        return true;
+    };
+
+    double cost = cost_of(false);
+    if (tid == 0) res->initial_error = cost;
+    int it = 0;
+    for (; it < a.max_iter; ++it) {
+        linearise();
+        bool improved = false;
+        double cn = cost, step = 0.0;
+        while (true) {
+            if (schur_step()) {
+                cn = cost_of(true);
+                if (cn <= cost) { improved = true; break; }
+            }
+            __syncthreads();
+            if (tid == 0) s_lambda *= 10.0;
+            __syncthreads();
+            if (!(s_lambda < 1e12)) break;
+        }
+        if (!improved) break;
+        for (int k = 0; k < n; ++k) step = fmax(step, fabs(s_dc[k]));
+        for (int j = tid; j < P; j += BAM_THREADS) {
+            const double *w = wsp + (size_t)j * WS;
+            double *X = a.points_out + (size_t)(p0 + j) * 3;
+            for (int k = 0; k < 3; ++k) { step = fmax(step, fabs(w[9 + k] - X[k])); X[k] = w[9 + k]; }
+        }
+        __syncthreads();
+        for (int k = tid; k < 12 * F; k += BAM_THREADS) s_pose[k] = s_cand[k];
+        const double rel = (cost - cn) / fmax(cost, 1e-300), absdec = cost - cn;
+        cost = cn;
+        __syncthreads();
+        {
+            double m = step;
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, s));
+            if ((tid & 31) == 0) s_scr[tid >> 5] = m;
+            __syncthreads();
+            step = 0.0;
+            for (int w = 0; w < BAM_THREADS / 32; ++w) step = fmax(step, s_scr[w]);
+            __syncthreads();
+        }
+        if (tid == 0) s_lambda = fmax(s_lambda / 10.0, 1e-12);
+        __syncthreads();
+        if (rel < a.rel_tol || (a.abs_tol >= 0.0 && absdec < a.abs_tol) || step < 1e-14) { ++it; break; }
+    }
+
+    // ---- marginal covariances at the result
+    linearise();
+    const bool pd = reduced_system(0.0, false);
+    for (int c = tid; c < n; c += BAM_THREADS) {      // column c of the inverse
+        double col[6 * BA_MAX_FRAMES], x[6 * BA_MAX_FRAMES];
+        for (int k = 0; k < n; ++k) col[k] = k == c ? 1.0 : 0.0;
+        if (pd) lower_solve(s_S, n, col, x);
+        for (int k = 0; k < n; ++k) s_C[k * n + c] = pd ? x[k] : NAN;
+    }
+    __syncthreads();
+    for (int k = tid; k < 36 * F; k += BAM_THREADS) {
+        const int f = k / 36, r = (k % 36) / 6, c = k % 6;
+        a.pose_cov_out[(size_t)(f0 + f) * 36 + r * 6 + c] = s_C[(f * 6 + r) * n + f * 6 + c];
+    }
+    for (int k = tid; k < 12 * F; k += BAM_THREADS) {
+        const int f = k / 12, q = k % 12;
+        if (q < 9) a.pose_R_out[(size_t)(f0 + f) * 9 + q] = s_pose[k]; else a.pose_t_out[(size_t)(f0 + f) * 3 + q - 9] = s_pose[k];
+    }
+    if (tid == 0) { res->status = MVS_OK; res->iterations = it; res->final_error = cost; }
+    // point covariance = Vi + (Vi W^T) C (W Vi)
+    for (int j = tid; j < P; j += BAM_THREADS) {
+        const double *w = wsp + (size_t)j * WS;
+        const double *Y = w + 12 + 18 * F;            // W Vi at lambda = 0 (left by reduced_system)
+        double Vi[6];
+        sym3_inverse(w, Vi);
+        const double Vf[9] = {Vi[0], Vi[1], Vi[2], Vi[1], Vi[3], Vi[4], Vi[2], Vi[4], Vi[5]};
+        double *out = a.point_cov_out + (size_t)(p0 + j) * 9;
+        for (int c = 0; c < 3; ++c) {
+            double m[6 * BA_MAX_FRAMES];               // C Y[:, c]
+            for (int k = 0; k < n; ++k) {
+                double tc = 0.0;
+                for (int q = 0; q < n; ++q) tc += s_C[k * n + q] * Y[q * 3 + c];
+                m[k] = tc;
+            }
+            for (int r = 0; r < 3; ++r) {
+                double v = Vf[r * 3 + c];
+                for (int k = 0; k < n; ++k) v += Y[k * 3 + r] * m[k];
+                out[r * 3 + c] = v;
+            }
+        }
+    }
+}
+
 size_t ba_shared_bytes() { return (size_t)(BA_THREADS * BA_ACC + 96 + 24 + 24 + 72 + 144 + 12 + 4) * sizeof(double); }
 
-cudaError_t launch_ba(const BaArgs &a, int n_problems, cudaStream_t s)
+static size_t ba_multi_shared_bytes(int mf)
 {
-    cudaError_t e = cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba_shared_bytes());
-    if (e != cudaSuccess) return e;
-    ba_solve_kernel<<<n_problems, BA_THREADS, ba_shared_bytes(), s>>>(a);
+    const size_t nm = 6 * (size_t)mf;
+    return (2 * nm * nm + (size_t)mf * 27 + 2 * nm + (size_t)mf * (12 + 12 + 36) + 8) * sizeof(double);
+}
+
+cudaError_t launch_ba(const BaArgs &a, int n_problems, int min_frames, int max_frames, cudaStream_t s)
+{
+    cudaError_t e = cudaSuccess;
+    if (min_frames <= 2) {
+        e = cudaFuncSetAttribute(ba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba_shared_bytes());
+        if (e != cudaSuccess) return e;
+        ba_solve_kernel<<<n_problems, BA_THREADS, ba_shared_bytes(), s>>>(a);
+    }
+    if (max_frames > 2) {
+        const int mf = max_frames < BA_MAX_FRAMES ? max_frames : BA_MAX_FRAMES;
+        e = cudaFuncSetAttribute(ba_solve_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba_multi_shared_bytes(mf));
+        if (e != cudaSuccess) return e;
+        ba_solve_multi_kernel<<<n_problems, BAM_THREADS, ba_multi_shared_bytes(mf), s>>>(a, mf);
+    }
     return cudaGetLastError();
 }
 

@@ -4,7 +4,7 @@ scipy.optimize.least_squares, and the reference's own known-answer tests (tolera
 import numpy as np
 import pytest
 
-from ba_scenes import one_view, two_view
+from ba_scenes import multi_view, one_view, two_view
 from oracle import ba_np as B
 
 scipy_opt = pytest.importorskip("scipy.optimize")
@@ -61,3 +61,17 @@ def test_reference_known_answer_pnp_refine_L_shape():
         r = prob.solve()
         R, t, _ = s["truth"]
         assert np.abs(r["poses"][0][1] - t).max() < 0.025 and np.abs(B.so3_log(R.T @ r["poses"][0][0])).max() < 0.025
+
+
+@pytest.mark.parametrize("n_frames", [3, 5])
+def test_minimiser_matches_scipy_with_more_than_two_frames(n_frames):
+    """ba_frame_pose_and_point takes any number of frames (ba.cpp:26-156): the same pin for a window of cameras."""
+    s = multi_view(70 + n_frames, n_frames=n_frames, n=25)
+    prob = B.Problem(s["K"], s["poses"], s["pose_prior"], s["points"], s["point_prior"], s["obs"])
+    mine = prob.solve()
+    ref = scipy_opt.least_squares(prob.residual_vector, np.zeros(6 * prob.F + 3 * prob.P), method="lm", xtol=1e-15, ftol=1e-15, gtol=1e-15)
+    poses_ref, points_ref = prob.retract(prob.poses0, prob.points0, ref.x)
+    assert abs(mine["error"] - ref.cost) < 1e-9 * max(ref.cost, 1.0)
+    assert np.abs(mine["points"] - points_ref).max() < 1e-6
+    for (Ra, ta), (Rb, tb) in zip(mine["poses"], poses_ref):
+        assert np.abs(Ra - Rb).max() < 1e-7 and np.abs(ta - tb).max() < 1e-7

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import mvslam_b200 as mvs
-from ba_scenes import one_view, two_view
+from ba_scenes import multi_view, one_view, two_view
 from oracle import ba_np as B
 
 pytestmark = pytest.mark.gpu
@@ -48,6 +48,12 @@ def pnp_case(seed):
     s = one_view(seed)
     prob = B.pnp_refine_problem(s["world"], s["world_cov"], s["image"], s["image_cov"], s["K"], s["pose_guess"])
     return s, prob, to_abi(prob, {0: np.eye(6) * B.PNP_REGULATOR_STDDEV ** 2}, {j: s["world_cov"][j] for j in range(len(s["world"]))})
+
+
+def multi_case(seed, **kw):
+    s = multi_view(seed, **kw)
+    prob = B.Problem(s["K"], s["poses"], s["pose_prior"], s["points"], s["point_prior"], s["obs"])
+    return s, prob, to_abi(prob, s["pose_prior"], s["point_prior"])
 
 
 def check(g, o):
@@ -101,7 +107,32 @@ def test_argument_checks(ctx):
     bad = dict(abi, obs=abi["obs"].copy()); bad["obs"]["point"][0] = 99
     with pytest.raises(mvs.MvsError):
         ctx.ba_solve_batch(np.eye(3), [bad])
-    three = dict(abi, pose_R=np.stack([np.eye(3)] * 3), pose_t=np.zeros((3, 3)), pose_prior_cov=np.stack([np.eye(6)] * 3))
+    many = dict(abi, pose_R=np.stack([np.eye(3)] * 17), pose_t=np.zeros((17, 3)), pose_prior_cov=np.stack([np.eye(6)] * 17))
     with pytest.raises(mvs.MvsError) as e:
-        ctx.ba_solve_batch(np.eye(3), [three])
+        ctx.ba_solve_batch(np.eye(3), [many])
     assert e.value.status == mvs.E_UNSUPPORTED
+
+
+@pytest.mark.parametrize("n_frames,n", [(3, 40), (4, 60), (8, 120), (16, 80)])
+def test_more_than_two_frames_matches_oracle(ctx, n_frames, n):
+    """ba_frame_pose_and_point accepts any number of frames (ba.cpp:26-156); 3..16 run in ba_solve_multi_kernel."""
+    s, prob, abi = multi_case(100 + n_frames, n_frames=n_frames, n=n)
+    g = ctx.ba_solve_batch(s["K"], [abi])[0]
+    o = prob.solve()
+    check(g, o)
+    assert g["final_error"] < g["initial_error"]
+    poses, X = s["truth"]
+    assert max(np.abs(g["pose_t"][f] - poses[f][1]).max() for f in range(n_frames)) < 0.05
+
+
+def test_mixed_frame_counts_in_one_batch(ctx):
+    """problems of 1, 2 and more frames in one call: two kernels, each takes its own problems; deterministic."""
+    K = np.array([[700.0, 0.8, 320.0], [0, 705.0, 240.0], [0, 0, 1.0]])
+    cases = [multi_case(200, n_frames=5, n=50, K=K, noise=0.4 / 700), sfm_case(201, n=30, noise=0.5 / 700, K=K),
+             multi_case(202, n_frames=3, n=25, K=K, noise=0.4 / 700, unprior_points=1.0)]
+    res = ctx.ba_solve_batch(K, [c[2] for c in cases])
+    for (s, prob, abi), g in zip(cases, res):
+        check(g, prob.solve())
+    again = ctx.ba_solve_batch(K, [c[2] for c in cases])
+    for a, b in zip(res, again):
+        assert a["final_error"] == b["final_error"] and np.array_equal(a["points"], b["points"]) and np.array_equal(a["pose_cov"], b["pose_cov"])
