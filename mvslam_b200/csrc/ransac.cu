@@ -170,8 +170,7 @@ __device__ __forceinline__ void eight_point_reference(const double *pts, const u
     mat3_mul(tmp, T1m, F);
 }
 
-// One thread per (pair, hypothesis), flattened so that H = 1 (the reference's only sample) still fills warps.
-template <bool REF>
+// FAST solver: one thread per (pair, hypothesis), flattened over the batch.
 __device__ __forceinline__ void hypothesis_body(const HypArgs &a)
 {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -187,17 +186,17 @@ __device__ __forceinline__ void hypothesis_body(const HypArgs &a)
         sample_row(a.seed, a.pair_id_base + (uint64_t)pair, (uint32_t)n, h, idx);
     }
     double F[9];
-    if (REF) eight_point_reference(a.points + (size_t)pair * a.p_stride * 6, idx, F);
-    else eight_point(a.points + (size_t)pair * a.p_stride * 6, idx, F);
+    eight_point(a.points + (size_t)pair * a.p_stride * 6, idx, F);
     double *o = a.F_all + ((size_t)pair * a.H + h) * 9;
 #pragma unroll
     for (int i = 0; i < 9; ++i) o[i] = F[i];
 }
 
 // ------------------------------------------------------------------------------------------
-// The same REFERENCE solve with the 9x9 Jacobi spread over 4 lanes, for launches with few hypotheses (H = 1 is the
-// reference's configuration: one thread per pair would leave a 300-clock div/sqrt chain per rotation, ~290 rotations,
-// on the critical path of every call).  OpenCV visits the row pairs (i, j) of a sweep in lexicographic order; rotation
+// The REFERENCE solve of the batch (eight_point_reference above is the one-thread form, kept for explicit 8-point sets),
+// with the 9x9 Jacobi spread over 4 lanes (H = 1 is the reference's configuration: one thread per pair would leave a
+// 300-clock div/sqrt chain per rotation, ~290 rotations, on the critical path of every call; for many hypotheses the
+// shared-memory state also beats a thread per hypothesis, whose 162 doubles spill: 145 M against 55 M hypotheses/s).  OpenCV visits the row pairs (i, j) of a sweep in lexicographic order; rotation
 // (i, j) only depends on the latest earlier rotations that touched row i or row j, i.e. on (i, j-1), (i-1, i) and
 // (i-1, j): it can run at "time" i + j, rotations with equal i + j touch disjoint rows, and the next sweep may start 9
 // time steps after the current one (row 0 is free after (0, 8)).  Four lanes therefore execute the exact sequential
@@ -264,7 +263,7 @@ __device__ __forceinline__ bool wave_rotate(double *At, double *V, double *W, in
     return true;
 }
 
-__global__ void __launch_bounds__(WAVE_HYP_PER_BLOCK * WAVE_LANES)
+__global__ void __launch_bounds__(WAVE_HYP_PER_BLOCK * WAVE_LANES, 8)
 hypotheses_reference_wave_kernel(HypArgs a)
 {
     pdl_wait();
@@ -370,12 +369,8 @@ hypotheses_reference_wave_kernel(HypArgs a)
     }
 }
 
-constexpr int HYP_REF_THREADS = 64;
-__global__ void __launch_bounds__(HYP_REF_THREADS)
-hypotheses_reference_kernel(HypArgs a) { pdl_wait(); pdl_launch_dependents(); hypothesis_body<true>(a); }
-
 __global__ void __launch_bounds__(HYP_THREADS)
-hypotheses_kernel(HypArgs a) { pdl_wait(); pdl_launch_dependents(); hypothesis_body<false>(a); }
+hypotheses_kernel(HypArgs a) { pdl_wait(); pdl_launch_dependents(); hypothesis_body(a); }
 
 // a9 entry for explicit 8-point sets: p1s/p2s [n_sets][8][3]
 __global__ void __launch_bounds__(HYP_THREADS)
@@ -737,11 +732,9 @@ void launch_hypotheses(const HypArgs &a, int n_pairs, cudaStream_t s)
     HypArgs b = a;
     b.n_pairs = n_pairs;
     const long long total = (long long)n_pairs * a.H;
-    if (a.solver == MVS_SOLVER_REFERENCE && total <= 148LL * 32 * 16)   // few hypotheses: latency matters, 4 lanes per Jacobi
+    if (a.solver == MVS_SOLVER_REFERENCE)   // 4 lanes per Jacobi: shortest chain for H = 1, and 2.6x the rate of a thread per hypothesis at H = 1024
         launch_dep(hypotheses_reference_wave_kernel, dim3((unsigned)((total + WAVE_HYP_PER_BLOCK - 1) / WAVE_HYP_PER_BLOCK)),
                    dim3(WAVE_HYP_PER_BLOCK * WAVE_LANES), 0, s, b);
-    else if (a.solver == MVS_SOLVER_REFERENCE)
-        launch_dep(hypotheses_reference_kernel, dim3((unsigned)((total + HYP_REF_THREADS - 1) / HYP_REF_THREADS)), dim3(HYP_REF_THREADS), 0, s, b);
     else
         launch_dep(hypotheses_kernel, dim3((unsigned)((total + HYP_THREADS - 1) / HYP_THREADS)), dim3(HYP_THREADS), 0, s, b);
 }
