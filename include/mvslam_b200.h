@@ -201,6 +201,12 @@ int  mvs_profile_enable(mvs_ctx *ctx, int on);
 int  mvs_profile_read(mvs_ctx *ctx, mvs_profile *out, int reset);
 /* number of kernels this ctx has launched so far */
 uint64_t mvs_kernel_launches(const mvs_ctx *ctx);
+/* Test hook.  With MVS_GUARD=1 in the environment when the library is loaded, every workspace buffer is allocated at
+ * exactly the requested size plus a 4 KB guard band; this returns how many buffers had their band overwritten since
+ * they were allocated (0 = no kernel wrote past the end of its buffer), -1 when guard mode is off. */
+int mvs_debug_guard_check(mvs_ctx *ctx);
+/* Guard mode only: writes one byte past the end of the first live buffer, so that a test can see the check fire. */
+int mvs_debug_guard_poke(mvs_ctx *ctx);
 
 /* ---- feature extraction: VisualFeature::extract (source/vision/visual-feature.cpp:40-49, decl
  *      visual-feature.hpp:14) = cv::ORB detect + compute, the step FrameManager::add_frame runs per new image

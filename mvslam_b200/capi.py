@@ -118,6 +118,10 @@ def load_library():
     L.mvs_last_error.argtypes = [C.c_void_p]
     L.mvs_kernel_launches.restype = C.c_uint64
     L.mvs_kernel_launches.argtypes = [C.c_void_p]
+    L.mvs_debug_guard_check.restype = C.c_int
+    L.mvs_debug_guard_check.argtypes = [C.c_void_p]
+    L.mvs_debug_guard_poke.restype = C.c_int
+    L.mvs_debug_guard_poke.argtypes = [C.c_void_p]
     L.mvs_destroy.restype = None
     L.mvs_destroy.argtypes = [C.c_void_p]
     L.mvs_sample_table.restype = None
@@ -207,6 +211,9 @@ def sample_table(seed, pair_id, n_points, H):
     return out
 
 
+_LIVE = __import__("weakref").WeakSet()   # open contexts (tests/conftest.py checks their guard bands in MVS_GUARD=1 runs)
+
+
 class Context:
     """One context per (thread, CUDA device): owns the stream and the HBM workspace."""
 
@@ -220,6 +227,7 @@ class Context:
         self._h = h
         self.device = device
         self._frame_counts = None
+        _LIVE.add(self)
         if stream is not None:
             self.set_stream(stream)
 
@@ -259,6 +267,13 @@ class Context:
 
     def kernel_launches(self):
         return int(self._L.mvs_kernel_launches(self._h))
+
+    def debug_guard_check(self):
+        """MVS_GUARD=1 runs only: number of workspace buffers written past their end (-1: guard mode is off)."""
+        return int(self._L.mvs_debug_guard_check(self._h))
+
+    def debug_guard_poke(self):
+        return int(self._L.mvs_debug_guard_poke(self._h))
 
     # ---- feature extraction
     def orb_extract(self, images, n_features=500, append_frames=False, want=True, device_ptr=None, shape=None, out=None):

@@ -27,6 +27,17 @@ static_assert(MVS_N_STAGES == 16, "mvs_profile layout is part of the ABI (capi.p
 
 namespace {
 
+// Guard mode (MVS_GUARD=1 in the environment when the library is loaded; a test hook, see mvs_debug_guard_check): every
+// workspace buffer is allocated at exactly the size that was asked for, followed by a 4 KB band of a known byte, so a kernel
+// that writes past the end of its buffer is caught by the check instead of landing in the allocation slack.
+constexpr size_t kGuardBytes = 4096;
+constexpr int kGuardByte = 0xA5;
+inline bool guard_mode()
+{
+    static const bool on = [] { const char *e = std::getenv("MVS_GUARD"); return e && e[0] == '1'; }();
+    return on;
+}
+
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
@@ -35,6 +46,12 @@ struct DevBuf {
         if (bytes <= cap) return cudaSuccess;
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
+        if (guard_mode()) {
+            cudaError_t e = cudaMalloc(&p, bytes + kGuardBytes);
+            if (e != cudaSuccess) return e;
+            cap = bytes;
+            return cudaMemset(static_cast<uint8_t *>(p) + bytes, kGuardByte, kGuardBytes);
+        }
         size_t want = bytes + bytes / 4 + 256;
         cudaError_t e = cudaMalloc(&p, want);
         if (e == cudaSuccess) cap = want;
@@ -440,12 +457,9 @@ int mvs_create(mvs_ctx **out, int device)
     return MVS_OK;
 }
 
-void mvs_destroy(mvs_ctx *ctx)
+static std::vector<DevBuf *> all_buffers(mvs_ctx *ctx)
 {
-    if (!ctx) return;
-    cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->d_desc, &ctx->d_kp, &ctx->d_foff, &ctx->d_fcnt, &ctx->t_desc, &ctx->t_foff, &ctx->t_fcnt, &ctx->d_desc8, &ctx->t_desc8,
+    return {&ctx->d_desc, &ctx->d_kp, &ctx->d_foff, &ctx->d_fcnt, &ctx->t_desc, &ctx->t_foff, &ctx->t_fcnt, &ctx->d_desc8, &ctx->t_desc8,
                       &ctx->d_pairs, &ctx->d_partial, &ctx->d_rev, &ctx->d_matches, &ctx->d_nmatch, &ctx->d_points,
                       &ctx->d_state, &ctx->d_Fall, &ctx->d_pc, &ctx->d_pr, &ctx->d_mask, &ctx->d_valid, &ctx->d_tri, &ctx->d_items, &ctx->d_item_total,
                       &ctx->d_opts, &ctx->d_oidx, &ctx->d_results, &ctx->d_table, &ctx->d_in1, &ctx->d_in2,
@@ -455,6 +469,41 @@ void mvs_destroy(mvs_ctx *ctx)
                       &ctx->p_poses, &ctx->p_valid, &ctx->p_pc, &ctx->p_maskws, &ctx->p_mask, &ctx->p_counts, &ctx->p_results,
                       &ctx->b_foff, &ctx->b_poff, &ctx->b_R, &ctx->b_t, &ctx->b_pc, &ctx->b_X, &ctx->b_xc, &ctx->b_obs, &ctx->b_ooff,
                       &ctx->b_ws, &ctx->b_wsm, &ctx->b_wsm_off, &ctx->b_wsobs, &ctx->b_Ro, &ctx->b_to, &ctx->b_pco, &ctx->b_Xo, &ctx->b_xco, &ctx->b_res};
+}
+
+// Guard mode only (else -1): the number of workspace buffers whose guard band no longer holds the fill byte.
+int mvs_debug_guard_check(mvs_ctx *ctx)
+{
+    if (!ctx || !guard_mode()) return -1;
+    cudaSetDevice(ctx->device);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -2;
+    std::vector<uint8_t> h(kGuardBytes);
+    int bad = 0;
+    for (DevBuf *b : all_buffers(ctx)) {
+        if (!b->p) continue;
+        if (cudaMemcpy(h.data(), static_cast<uint8_t *>(b->p) + b->cap, kGuardBytes, cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+        for (uint8_t v : h)
+            if (v != kGuardByte) { ++bad; break; }
+    }
+    return bad;
+}
+
+// Guard mode only: overwrite one byte just past the end of the first live buffer (the self-test of the check above).
+int mvs_debug_guard_poke(mvs_ctx *ctx)
+{
+    if (!ctx || !guard_mode()) return -1;
+    cudaSetDevice(ctx->device);
+    for (DevBuf *b : all_buffers(ctx))
+        if (b->p) return cudaMemset(static_cast<uint8_t *>(b->p) + b->cap, 0, 1) == cudaSuccess ? 0 : -2;
+    return -3;
+}
+
+void mvs_destroy(mvs_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    const std::vector<DevBuf *> bufs = all_buffers(ctx);
     if (ctx->o_pinned) cudaFreeHost(ctx->o_pinned);
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);

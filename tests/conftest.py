@@ -42,3 +42,15 @@ def solver(request):
     capi.set_default_solver(request.param); cbind.set_default_solver(request.param)
     yield request.param
     capi.set_default_solver(old[0]); cbind.set_default_solver(old[1])
+
+
+@pytest.fixture(autouse=True)
+def _guard_bands():
+    """MVS_GUARD=1 runs (tests/test_gpu_guards.py starts one): after every test, no kernel may have written past the end of
+    a workspace buffer of any open context (include/mvslam_b200.h mvs_debug_guard_check)."""
+    yield
+    if os.environ.get("MVS_GUARD") == "1":
+        from mvslam_b200 import capi
+        for c in list(capi._LIVE):
+            if getattr(c, "_h", None):
+                assert c.debug_guard_check() == 0, "a kernel wrote past the end of a workspace buffer"
