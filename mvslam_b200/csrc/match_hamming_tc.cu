@@ -46,8 +46,7 @@ constexpr int RB = 2;                // 128-row blocks of a query tile (each tra
 constexpr int EPI_GROUP = 8;         // warps per epilogue group: two per TMEM lane quarter, each takes half of a tile's columns
 constexpr int EPI_WARPS = RB * EPI_GROUP;  // one group per row block
 constexpr int MMA_WARP_B = 2 + EPI_WARPS;  // second issuer (row block 1)
-constexpr int A_WARP = MMA_WARP_B + 1;     // query row-block producer
-constexpr int A_SLOTS = 3;                 // 128-row query blocks resident at a time
+constexpr int A_WARP = MMA_WARP_B + 1;     // query row-block producer (ring of A_SLOTS 128-row blocks, a kernel template parameter)
 constexpr int TC_THREADS = (A_WARP + 1) * 32;
 constexpr int NACC = 2 * RB;         // TMEM accumulator buffers: double-buffered per row block
 constexpr uint32_t TMEM_COLS = NACC * BN;
@@ -182,6 +181,16 @@ __device__ __forceinline__ uint32_t widen_key(uint32_t k16, uint32_t tile_base /
 // tiles in flight) and the four TMEM accumulators (2 row blocks x 2 steps) stay full across item boundaries.
 struct ItemInfo { int pair, q0, nq, nt, row_q, row_t, n_tiles, n_rb; };
 
+#ifdef MVS_TC_PROBE   // experiment build only (tools/knn_probe.py): per-CTA clock and wall-time counters of the last launch
+__device__ unsigned long long g_tc_probe[160][10];
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define PROBE_T0() const long long pt0__ = clock64()
+#define PROBE_ADD(var) var += clock64() - pt0__
+#else
+#define PROBE_T0()
+#define PROBE_ADD(var)
+#endif
+
 __device__ __forceinline__ bool load_item(const TcKnnArgs &a, int item, ItemInfo &it, int n_items)
 {
     if (item >= n_items) return false;
@@ -216,7 +225,7 @@ __device__ __forceinline__ bool load_item(const TcKnnArgs &a, int item, ItemInfo
 // blocks go through their own 3-slot ring (warp A_WARP), so the next item's first row block is resident before the current
 // item ends and the second follows while the first is being multiplied; each row block has its own issuing warp; item
 // metadata is fetched one item ahead; the epilogue keeps stream maxima only (see the file header).
-template <int STAGES>
+template <int STAGES, int A_SLOTS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
 {
@@ -231,6 +240,11 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_items = a.q_tiles * a.n_pairs;
     pdl_launch_dependents();   // K2's blocks may take the SMs this grid leaves free (small batches); they wait for this grid's end
+#ifdef MVS_TC_PROBE
+    long long w_a = 0, w_full = 0, w_acc = 0;
+    const long long pk0 = clock64();
+    const unsigned long long pg0 = gtimer();
+#endif
 
     if (threadIdx.x == 0) {
         if (smem_u32(smem_raw) & 1023u) __trap();
@@ -303,15 +317,15 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
             if (!valid) continue;
             const bool active = rb < it.n_rb;             // an item may have one row block only: stay in step with the train ring
             const uint32_t sl = (u + rb) % A_SLOTS;
-            if (active) mbar_wait(afull + sl, ((u + rb) / A_SLOTS) & 1);
+            { PROBE_T0(); if (active) mbar_wait(afull + sl, ((u + rb) / A_SLOTS) & 1); PROBE_ADD(w_a); }
             const uint32_t a_lo = a_lo0 + sl * (KSLABS * BM * SLAB >> 4);
             for (int i = 0; i < it.n_tiles; ++i, ++tile_no) {
                 const uint32_t s = tile_no % STAGES;
                 const uint32_t b_lo = b_lo0 + s * (KSLABS * BN * SLAB >> 4);
-                mbar_wait(full + s, (tile_no / STAGES) & 1);
+                { PROBE_T0(); mbar_wait(full + s, (tile_no / STAGES) & 1); PROBE_ADD(w_full); }
                 if (active) {
                     const uint32_t acc = (use_no & 1) * RB + rb;
-                    mbar_wait(tempty + acc, ((use_no >> 1) & 1) ^ 1);     // epilogue drained this accumulator
+                    { PROBE_T0(); mbar_wait(tempty + acc, ((use_no >> 1) & 1) ^ 1); PROBE_ADD(w_acc); }   // epilogue drained this accumulator
                     tcgen05_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * BN;
                     // UMMA_K = 32 one-byte elements = 32 bytes inside the swizzle atom; 4 steps per 128-byte slab
@@ -346,7 +360,7 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
             for (int i = 0; i < it.n_tiles; ++i, ++use_no) {
                 const uint32_t acc = (use_no & 1) * RB + rb;
                 const int col0 = i * BN + half * (BN / 2);
-                mbar_wait(tfull + acc, (use_no >> 1) & 1);
+                { PROBE_T0(); mbar_wait(tfull + acc, (use_no >> 1) & 1); PROBE_ADD(w_acc); }
                 tcgen05_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
                 const bool ragged = col0 + BN / 2 > it.nt;   // warp-uniform: only a frame's last tile
@@ -395,8 +409,24 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
             }
         }
     }
+#ifdef MVS_TC_PROBE
+    // slots: 0 issuer A total clocks, 1-3 issuer A waits (query block, train tile, accumulator), 4-6 issuer B waits,
+    //        7 CTA wall time (ns), 8 one epilogue warp's wait for accumulators
+    if (lane == 0 && warp == 1) {
+        unsigned long long *o = g_tc_probe[blockIdx.x];
+        o[0] = (unsigned long long)(clock64() - pk0); o[1] = (unsigned long long)w_a; o[2] = (unsigned long long)w_full; o[3] = (unsigned long long)w_acc;
+    }
+    if (lane == 0 && warp == MMA_WARP_B) {
+        unsigned long long *o = g_tc_probe[blockIdx.x];
+        o[4] = (unsigned long long)w_a; o[5] = (unsigned long long)w_full; o[6] = (unsigned long long)w_acc;
+    }
+    if (lane == 0 && warp == 2) g_tc_probe[blockIdx.x][8] = (unsigned long long)w_acc;
+#endif
     tcgen05_fence_before();
     __syncthreads();
+#ifdef MVS_TC_PROBE
+    if (threadIdx.x == 0) g_tc_probe[blockIdx.x][7] = gtimer() - pg0;
+#endif
     if (warp == 1) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -423,10 +453,12 @@ EncodeTiledFn get_encode_fn()
 
 cudaError_t launch_tc(const CUtensorMap &map, TcKnnArgs a, int max_nq, int n_pairs, cudaStream_t s)
 {
-    constexpr int STAGES = 4;   // one persistent CTA per SM: 3 x 32 KB query row blocks + 4 x 32 KB train ring = 224 KB
+    // one persistent CTA per SM: 3 x 32 KB query row blocks + 4 x 32 KB train ring = 224 KB.  (4 query slots + a 3-deep train
+    // ring, which lets BOTH row blocks of the next item load early, measured the same: 0.439 against 0.440 ms per 1024 pairs.)
+    constexpr int STAGES = 4, A_SLOTS = 3;
     const size_t smem = (size_t)A_SLOTS * KSLABS * BM * SLAB + (size_t)STAGES * KSLABS * BN * SLAB +
                         (2 * A_SLOTS + 2 * STAGES + 2 * NACC) * sizeof(uint64_t) + 16;
-    auto kern = knn2_hamming_tc_kernel<STAGES>;
+    auto kern = knn2_hamming_tc_kernel<STAGES, A_SLOTS>;
     static int sm_count[64] = {0};          // per device: the shared-memory opt-in is a per-device function attribute
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -449,6 +481,14 @@ cudaError_t launch_tc(const CUtensorMap &map, TcKnnArgs a, int max_nq, int n_pai
 }
 
 }  // namespace
+
+#ifdef MVS_TC_PROBE
+extern "C" void mvs_debug_tc_probe_dump(unsigned long long *out /* [160][10] */)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_tc_probe, sizeof(unsigned long long) * 160 * 10);
+}
+#endif
 
 int tc_max_train() { return TC_MAX_TRAIN; }
 int tc_splits() { return TC_SPLITS; }

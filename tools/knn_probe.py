@@ -10,6 +10,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import mvslam_b200 as mvs  # noqa: E402
+from mvslam_b200 import capi  # noqa: E402
+
+if os.environ.get("MVS_LIB_OVERRIDE"):     # experiment builds (e.g. -DMVS_TC_PROBE) live outside the package directory
+    capi.lib_path = lambda: os.path.abspath(os.environ["MVS_LIB_OVERRIDE"])
 
 
 def main():
@@ -32,6 +36,17 @@ def main():
         out["total_ms"] = round(sum(out.values()), 4)
         out["checksum"] = int(res["n_inliers"].astype(np.int64).sum()); out["n_matches"] = int(res["n_matches"].sum())
         out["tag"] = os.environ.get("TAG", "")
+        L = capi.load_library()
+        if hasattr(L, "mvs_debug_tc_probe_dump"):   # -DMVS_TC_PROBE build: counters of the last matcher launch
+            import ctypes
+            buf = np.zeros((160, 10), np.uint64)
+            L.mvs_debug_tc_probe_dump(buf.ctypes.data_as(ctypes.c_void_p))
+            b = buf[:148].astype(np.float64)
+            out["probe"] = dict(issuer_clocks_max=b[:, 0].max(), issuer_clocks_mean=b[:, 0].mean(), cta_wall_us_max=b[:, 7].max() / 1e3,
+                                sm_mhz_during_kernel=float(np.median(b[:, 0] / np.maximum(b[:, 7], 1) * 1e3)),
+                                issuerA_wait_query=b[:, 1].mean(), issuerA_wait_train=b[:, 2].mean(), issuerA_wait_acc=b[:, 3].mean(),
+                                issuerB_wait_query=b[:, 4].mean(), issuerB_wait_train=b[:, 5].mean(), issuerB_wait_acc=b[:, 6].mean(),
+                                epilogue_wait_acc=b[:, 8].mean())
         print(json.dumps(out))
 
 
