@@ -3,9 +3,12 @@
 // (reference source/vision/visual-feature.cpp:59-62 with a float VisualFeatureConfig::MatcherNormType).
 //
 //   d^2(q,t) = |q|^2 + |t|^2 - 2 q.t : the contraction S = Q T^T runs on the 5th-gen tensor cores
-//   (tcgen05.mma kind::tf32, FP32 accumulators in TMEM, operands staged by TMA with 128B swizzle), the
-//   epilogue reads the accumulators back with tcgen05.ld and streams the approximate scores
-//   a = |t|^2 - 2 S through a running (best, second-best) pair per row; every column whose score is within
+//   (tcgen05.mma kind::tf32, FP32 accumulators in TMEM, operands staged by TMA with 128B swizzle).  One more
+//   K step of 8 columns adds the bias -|t|^2 / 2 inside the tensor core (the train side carries it split
+//   into three TF32-exact pieces, the query side a constant 1 1 1 0 pattern), so the accumulator is
+//   S' = q.t - |t|^2 / 2 = -a / 2 with a = |t|^2 - 2 q.t the approximate score: the epilogue reads the
+//   accumulators back with tcgen05.ld and streams them through a running (best, second-best) pair per row
+//   with three-input FMNMX only -- no multiply-add, no norm loads; every column whose score is within
 //   2E of the running second-best is appended to the row's candidate list, E being a rigorous bound of the
 //   TF32 rounding error of a (|S_tf32 - S| <= |q||t| 2^-9).  The 32k x 32k matrix is never materialised.
 //   Any column that is NOT listed is therefore provably farther than both of the two approximately-best
@@ -91,6 +94,17 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr)
     d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
     return d;
 }
+// the bias slabs: [rows][32 B] (one K step of 8 TF32 columns), 32-byte swizzle, SBO = 256 B (8 rows x 32 B), layout_type 6
+__device__ __forceinline__ uint64_t make_smem_desc32(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(256 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)6 << 61;                 // SWIZZLE_32B
+    return d;
+}
 // kind::tf32, FP32 accumulate, A and B K-major, M = 128, N = BN
 constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
@@ -103,29 +117,55 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(kInstrDesc), "r"(accumulate) : "memory");
 }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+// 32 accumulator columns of the thread's TMEM lane; asynchronous until tmem_wait64
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32])
 {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                  "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
                  "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                  : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// completes both loads; the registers are in/out operands so that no use of them is scheduled above the wait
+__device__ __forceinline__ void tmem_wait64(uint32_t (&v)[32], uint32_t (&w)[32])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31]),
+                   "+r"(w[0]), "+r"(w[1]), "+r"(w[2]), "+r"(w[3]), "+r"(w[4]), "+r"(w[5]), "+r"(w[6]), "+r"(w[7]), "+r"(w[8]), "+r"(w[9]), "+r"(w[10]), "+r"(w[11]), "+r"(w[12]), "+r"(w[13]), "+r"(w[14]), "+r"(w[15]), "+r"(w[16]), "+r"(w[17]), "+r"(w[18]), "+r"(w[19]), "+r"(w[20]), "+r"(w[21]), "+r"(w[22]), "+r"(w[23]), "+r"(w[24]), "+r"(w[25]), "+r"(w[26]), "+r"(w[27]), "+r"(w[28]), "+r"(w[29]), "+r"(w[30]), "+r"(w[31])
+                 :: "memory");
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c)
+{
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));   // FMNMX3
+    return d;
 }
 
 // ------------------------------------------------------------------------------------------ small kernels
 // squared norms (+inf padding) and their maximum (bit pattern order == value order for floats >= 0)
-__global__ void l2_norms_kernel(const float *x, int n, int n_padded, int ld, int dim, float *out, unsigned int *max_bits)
+// and the bias row of every descriptor for the contraction: -|x|^2 / 2 as three TF32-exact pieces (13 low mantissa bits
+// clear, so the tensor core's FP32 -> TF32 conversion keeps them whatever its rounding; what is lost is below 2^-30 |x|^2);
+// padding rows get a large negative bias: such a column never reaches a candidate list
+constexpr float kPadBias = -1e30f;
+__device__ __forceinline__ float tf32_head(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+__global__ void l2_norms_kernel(const float *x, int n, int n_padded, int ld, int dim, float *out, float *bias /* [n_padded][8] */,
+                                unsigned int *max_bits)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_padded) return;
-    if (i >= n) { out[i] = CUDART_INF_F; return; }
+    float4 *brow = reinterpret_cast<float4 *>(bias + (size_t)i * 8);
+    brow[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i >= n) { out[i] = CUDART_INF_F; brow[0] = make_float4(kPadBias, 0.f, 0.f, 0.f); return; }
     float s = 0.f;
     for (int k = 0; k < dim; ++k) s = fmaf(x[(size_t)i * ld + k], x[(size_t)i * ld + k], s);
     out[i] = s;
+    {
+        const float h = -0.5f * s;
+        const float h0 = tf32_head(h), r0 = h - h0;          // exact: h0 is the head of h
+        const float h1 = tf32_head(r0), r1 = r0 - h1;
+        brow[0] = make_float4(h0, h1, tf32_head(r1), 0.f);
+    }
     const unsigned m = __reduce_max_sync(__activemask(), __float_as_uint(s));
     if ((threadIdx.x & 31) == (__ffs(__activemask()) - 1)) atomicMax(max_bits, m);
 }
@@ -138,20 +178,31 @@ __global__ void l2_pad_kernel(const float *src, int n, int dim, float *dst, int 
     dst[i] = c < dim ? src[(size_t)r * dim + c] : 0.f;
 }
 
+// Half-width of the candidate band: a bound of |a_tf32 - a| / 2 for a = |t|^2 - 2 q.t computed as -2 (q.t - |t|^2 / 2) by the
+// TF32 contraction.  q.t: both operands keep 10 mantissa bits (2 x 2^-10 |q||t| when truncated; 0.0041 / 2 leaves a factor
+// of two in hand); the bias pieces are TF32-exact (what they drop is below 2^-30 |t|^2); the FP32 accumulator holds values up
+// to |q||t| + |t|^2 / 2 through nine additions (K / 8 + 1 instructions), each within 2^-23 of that: the 4e-6 term.
+__device__ __forceinline__ float l2_half_band(float qn, float tmax)
+{
+    return qn * tmax * 0.0041f + 4e-6f * (tmax * tmax + 2.f * qn * tmax);
+}
+
 // ------------------------------------------------------------------------------------------ GEMM + top-KC
 template <int KSLABS, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
 l2_gemm_topk_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapT,
-                    const float *__restrict__ t2 /* padded with +inf to a multiple of BN */,
+                    const __grid_constant__ CUtensorMap mapTb /* bias rows of the train side, padded to a multiple of BN */,
                     const float *__restrict__ q2, const unsigned int *__restrict__ tmax2_bits, int nq, int nt,
                     int tiles_per_split, int splits, float *__restrict__ cand_val, int32_t *__restrict__ cand_idx, int32_t *__restrict__ cand_cnt)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve: A (KSLABS x 16 KB), B (STAGES x KSLABS x 16 KB), t2 tiles (2 x BN floats), barriers
+    // carve: A (KSLABS x 16 KB), B (STAGES x KSLABS x 16 KB), bias slabs (A: 4 KB constant, B: STAGES x 4 KB), barriers
     uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = base;
     uint8_t *sB = sA + KSLABS * BM * 128;
-    uint64_t *bars = (uint64_t *)(sB + STAGES * KSLABS * BN * 128);
+    uint8_t *sAb = sB + STAGES * KSLABS * BN * 128;
+    uint8_t *sBb = sAb + BM * 32;
+    uint64_t *bars = (uint64_t *)(sBb + STAGES * BN * 32);
     uint64_t *barA = bars, *full = bars + 1, *empty = full + STAGES, *tfull = empty + STAGES, *tempty = tfull + 2;
     uint32_t *tmem_slot = (uint32_t *)(tempty + 2);
 
@@ -166,13 +217,17 @@ l2_gemm_topk_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
     if (threadIdx.x == 0) {
         mbar_init(barA, 1);
         for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, EPI_WARPS * 32); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    // query-side bias slab: every 16-byte chunk is (1, 1, 1, 0) -- the 32-byte swizzle only permutes 16-byte chunks, so the
+    // pattern is its own swizzled image; written through the generic proxy, read by the tensor core through the async proxy
+    for (int i = threadIdx.x; i < BM * 2; i += GEMM_THREADS) reinterpret_cast<float4 *>(sAb)[i] = make_float4(1.f, 1.f, 1.f, 0.f);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
@@ -186,9 +241,10 @@ l2_gemm_topk_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
             for (int i = 0; i < n_tiles; ++i) {
                 const int s = i % STAGES;
                 if (i >= STAGES) mbar_wait(empty + s, ((i / STAGES) - 1) & 1);
-                mbar_expect_tx(full + s, KSLABS * BN * 128);
+                mbar_expect_tx(full + s, KSLABS * BN * 128 + BN * 32);
                 for (int ks = 0; ks < KSLABS; ++ks)
                     tma_load_2d(&mapT, full + s, sB + (s * KSLABS + ks) * BN * 128, ks * KSLAB, (tile_begin + i) * BN);
+                tma_load_2d(&mapTb, full + s, sBb + s * BN * 32, 0, (tile_begin + i) * BN);
             }
         }
     } else if (warp == 1) {
@@ -209,6 +265,7 @@ l2_gemm_topk_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
                     for (int k = 0; k < 4; ++k)   // UMMA_K = 8 tf32 = 32 bytes inside the 128-byte swizzle atom
                         umma_tf32(d_tmem, make_smem_desc(a_addr + k * 32), make_smem_desc(b_addr + k * 32), (ks | k) ? 1u : 0u);
                 }
+                umma_tf32(d_tmem, make_smem_desc32(smem_u32(sAb)), make_smem_desc32(smem_u32(sBb + s * BN * 32)), 1u);   // - |t|^2 / 2
                 tcgen05_commit(empty + s);     // B stage reusable once these MMAs retire
                 tcgen05_commit(tfull + acc);   // accumulator ready for the epilogue
             }
@@ -222,12 +279,14 @@ l2_gemm_topk_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         const size_t list = ((size_t)min(q, nq - 1) * splits + split) * 2 + half;
         float *lv = cand_val + list * KC;
         int32_t *li = cand_idx + list * KC;
-        // error bound of a = |t|^2 - 2 S_tf32: each operand keeps 10 mantissa bits
+        // The accumulator is S' = q.t - |t|^2 / 2 = -a / 2 (a = |t|^2 - 2 q.t, the approximate score): the scan keeps the two
+        // LARGEST S' and lists every column with S' >= second - E, i.e. a <= second-best a + 2E.  E bounds the error of a / 2:
+        // each operand keeps 10 mantissa bits, the bias pieces are exact, nine FP32 accumulation steps.
         const float qn = sqrtf(q2[min(q, nq - 1)]);
         const float tmax = sqrtf(__uint_as_float(*tmax2_bits));
-        const float twoE = 2.f * (qn * tmax * 0.0041f + 2e-6f * (tmax * tmax + 2.f * qn * tmax));
-        // rows beyond nq (zero-filled by TMA) never list anything: their threshold is -inf
-        float b1 = CUDART_INF_F, b2 = CUDART_INF_F, thr = (q < nq) ? CUDART_INF_F : -CUDART_INF_F;
+        const float E = l2_half_band(qn, tmax);
+        // rows beyond nq (zero-filled by TMA) never list anything: their threshold is +inf
+        float c1 = -CUDART_INF_F, c2 = -CUDART_INF_F, thr = (q < nq) ? -CUDART_INF_F : CUDART_INF_F;
         int cnt = 0;
         for (int i = 0; i < n_tiles; ++i) {
             const int acc = i & 1;
@@ -235,44 +294,46 @@ l2_gemm_topk_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
             mbar_wait(tfull + acc, (i >> 1) & 1);
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN / 2; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(taddr + c0, v);
-                const float4 *tt = reinterpret_cast<const float4 *>(t2 + col0 + c0);   // same address in every lane
-                float a[32], m4[8];
+            // both 32-column chunks are fetched at once and the accumulator goes back to the MMA warp as soon as they have
+            // arrived (one arrival per warp): the tensor pipe never waits for the scan below
+            uint32_t v0[32], v1[32];
+            tmem_ld32_issue(taddr, v0);
+            tmem_ld32_issue(taddr + 32, v1);
+            tmem_wait64(v0, v1);
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty + acc);
 #pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    const float4 t4 = __ldg(tt + j4);
-                    a[4 * j4 + 0] = fmaf(-2.f, __uint_as_float(v[4 * j4 + 0]), t4.x);
-                    a[4 * j4 + 1] = fmaf(-2.f, __uint_as_float(v[4 * j4 + 1]), t4.y);
-                    a[4 * j4 + 2] = fmaf(-2.f, __uint_as_float(v[4 * j4 + 2]), t4.z);
-                    a[4 * j4 + 3] = fmaf(-2.f, __uint_as_float(v[4 * j4 + 3]), t4.w);
-                    m4[j4] = fminf(fminf(a[4 * j4], a[4 * j4 + 1]), fminf(a[4 * j4 + 2], a[4 * j4 + 3]));
-                }
-                const float m = fminf(fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3])), fminf(fminf(m4[4], m4[5]), fminf(m4[6], m4[7])));
-                if (__any_sync(0xFFFFFFFFu, m <= thr)) {
+            for (int c = 0; c < 2; ++c) {
+                const uint32_t (&v)[32] = c ? v1 : v0;
+                const int c0 = 32 * c;
+                float m4[8];
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4)
+                    m4[j4] = fmax3(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1]),
+                                   fmaxf(__uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3])));
+                const float m = fmax3(fmax3(m4[0], m4[1], m4[2]), fmax3(m4[3], m4[4], m4[5]), fmaxf(m4[6], m4[7]));
+                if (__any_sync(0xFFFFFFFFu, m >= thr)) {
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
-                        if (m4[j4] <= thr) {
+                        if (m4[j4] >= thr) {
 #pragma unroll
                             for (int jj = 0; jj < 4; ++jj) {
-                                const float av = a[4 * j4 + jj];
-                                if (av <= thr) {
-                                    if (cnt < KC) { lv[cnt] = av; li[cnt] = col0 + c0 + 4 * j4 + jj; }
+                                const float sv = __uint_as_float(v[4 * j4 + jj]);
+                                const int col = col0 + c0 + 4 * j4 + jj;
+                                if (sv >= thr && col < nt) {     // padding columns (large negative bias) pass only while thr = -inf
+                                    if (cnt < KC) { lv[cnt] = -2.f * sv; li[cnt] = col; }
                                     ++cnt;
-                                    const float hi = fmaxf(b1, av);
-                                    b1 = fminf(b1, av);
-                                    b2 = fminf(b2, hi);
-                                    thr = b2 + twoE;
+                                    const float lo = fminf(c1, sv);
+                                    c1 = fmaxf(c1, sv);
+                                    c2 = fmaxf(c2, lo);
+                                    thr = c2 - E;
                                 }
                             }
                         }
                     }
                 }
             }
-            tcgen05_fence_before();
-            mbar_arrive(tempty + acc);
         }
         if (q < nq) cand_cnt[list] = cnt;
     }
@@ -321,7 +382,7 @@ __global__ void l2_rerank_kernel(const float *__restrict__ Q, const float *__res
     if (q >= nq) return;
     const float qn = sqrtf(q2[q]);
     const float tmax = sqrtf(__uint_as_float(*tmax2_bits));
-    const float twoE = 2.f * (qn * tmax * 0.0041f + 2e-6f * (tmax * tmax + 2.f * qn * tmax));
+    const float twoE = 2.f * l2_half_band(qn, tmax);
     bool overflow = false;
     float a1 = CUDART_INF_F, a2 = CUDART_INF_F;
     for (int l = 0; l < lists; ++l) {
@@ -474,6 +535,19 @@ bool make_map(CUtensorMap *m, const float *ptr, int rows, int ld, int kpad, int 
               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// [rows][8] float bias rows, box = one 32-byte row x BN rows, 32-byte swizzle (the layout make_smem_desc32 describes)
+bool make_bias_map(CUtensorMap *m, const float *ptr, int rows)
+{
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t gdim[2] = {8, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {8 * sizeof(float)};
+    cuuint32_t box[2] = {8, (cuuint32_t)BN};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)ptr, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 enum { B_Q = 0, B_T, B_NORM, B_CAND_V, B_CAND_I, B_OUT, B_MISC, B_KEYS };
 
 cudaError_t ensure(L2Workspace &ws, int i, size_t bytes)
@@ -488,17 +562,17 @@ cudaError_t ensure(L2Workspace &ws, int i, size_t bytes)
 }
 
 template <int KSLABS>
-cudaError_t launch_gemm(const CUtensorMap &mq, const CUtensorMap &mt, const float *t2, const float *q2, const unsigned int *tmax, int nq,
+cudaError_t launch_gemm(const CUtensorMap &mq, const CUtensorMap &mt, const CUtensorMap &mtb, const float *q2, const unsigned int *tmax, int nq,
                         int nt, int tiles_per_split, int splits, float *cv, int32_t *ci, int32_t *cc, cudaStream_t s)
 {
     constexpr int STAGES = 2;   // 2 CTAs per SM (<= 113 KB each): one CTA's MMA/TMA overlaps the other's epilogue
-    const size_t smem = 1024 + (size_t)KSLABS * BM * 128 + (size_t)STAGES * KSLABS * BN * 128 +
+    const size_t smem = 1024 + (size_t)KSLABS * BM * 128 + (size_t)STAGES * KSLABS * BN * 128 + (size_t)BM * 32 + (size_t)STAGES * BN * 32 +
                         (1 + 2 * STAGES + 4) * sizeof(uint64_t) + 16;
     auto kern = l2_gemm_topk_kernel<KSLABS, STAGES>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((nq + BM - 1) / BM, splits);
-    kern<<<grid, GEMM_THREADS, smem, s>>>(mq, mt, t2, q2, tmax, nq, nt, tiles_per_split, splits, cv, ci, cc);
+    kern<<<grid, GEMM_THREADS, smem, s>>>(mq, mt, mtb, q2, tmax, nq, nt, tiles_per_split, splits, cv, ci, cc);
     return cudaGetLastError();
 }
 
@@ -524,13 +598,13 @@ void plan_splits(int na, int nb, int &splits, int &tiles_per_split)
 
 // tensor-core pass: top-KC candidates per (row of A, split of B) into ws.buf[B_CAND_V/B_CAND_I]
 int gemm_candidates(L2Workspace &ws, cudaStream_t stream, const float *dA, int na, const float *dB, int nb, int ld,
-                    int kpad, const float *d_normB, const float *d_normA, const unsigned int *bmax, int splits, int tiles_per_split,
-                    std::string &err)
+                    int kpad, const float *d_biasB /* [nb rounded up to BN][8] */, const float *d_normA, const unsigned int *bmax, int splits,
+                    int tiles_per_split, std::string &err)
 {
     L2CK(ensure(ws, B_CAND_V, (size_t)na * splits * 2 * KC * sizeof(float)));
     L2CK(ensure(ws, B_CAND_I, (size_t)na * splits * 2 * (KC + 1) * sizeof(int32_t)));
-    CUtensorMap mq, mt;
-    if (!make_map(&mq, dA, na, ld, kpad, BM) || !make_map(&mt, dB, nb, ld, kpad, BN)) {
+    CUtensorMap mq, mt, mtb;
+    if (!make_map(&mq, dA, na, ld, kpad, BM) || !make_map(&mt, dB, nb, ld, kpad, BN) || !make_bias_map(&mtb, d_biasB, (nb + BN - 1) / BN * BN)) {
         err = "cuTensorMapEncodeTiled failed";
         return MVS_E_CUDA;
     }
@@ -539,10 +613,10 @@ int gemm_candidates(L2Workspace &ws, cudaStream_t stream, const float *dA, int n
     int32_t *cc = ci + (size_t)na * splits * 2 * KC;
     cudaError_t e;
     switch (kpad / KSLAB) {
-    case 1: e = launch_gemm<1>(mq, mt, d_normB, d_normA, bmax, na, nb, tiles_per_split, splits, cv, ci, cc, stream); break;
-    case 2: e = launch_gemm<2>(mq, mt, d_normB, d_normA, bmax, na, nb, tiles_per_split, splits, cv, ci, cc, stream); break;
-    case 3: e = launch_gemm<3>(mq, mt, d_normB, d_normA, bmax, na, nb, tiles_per_split, splits, cv, ci, cc, stream); break;
-    case 4: e = launch_gemm<4>(mq, mt, d_normB, d_normA, bmax, na, nb, tiles_per_split, splits, cv, ci, cc, stream); break;
+    case 1: e = launch_gemm<1>(mq, mt, mtb, d_normA, bmax, na, nb, tiles_per_split, splits, cv, ci, cc, stream); break;
+    case 2: e = launch_gemm<2>(mq, mt, mtb, d_normA, bmax, na, nb, tiles_per_split, splits, cv, ci, cc, stream); break;
+    case 3: e = launch_gemm<3>(mq, mt, mtb, d_normA, bmax, na, nb, tiles_per_split, splits, cv, ci, cc, stream); break;
+    case 4: e = launch_gemm<4>(mq, mt, mtb, d_normA, bmax, na, nb, tiles_per_split, splits, cv, ci, cc, stream); break;
     default: err = "descriptor dimension above 128 floats"; return MVS_E_UNSUPPORTED;
     }
     L2CK(e);
@@ -590,15 +664,15 @@ int l2_knn2(L2Workspace &ws, cudaStream_t stream, const float *query, int nq, co
     // squared norms, each array padded with +inf to a multiple of the column tile (padded columns never win);
     // their maxima stay on the device (error bound of the TF32 contraction)
     const size_t nqp = ((size_t)nq + BN - 1) / BN * BN, ntp = ((size_t)nt + BN - 1) / BN * BN;
-    L2CK(ensure(ws, B_NORM, (nqp + ntp) * sizeof(float)));
+    L2CK(ensure(ws, B_NORM, (nqp + ntp) * 9 * sizeof(float)));   // squared norms, then the [row][8] bias rows of the contraction
     L2CK(ensure(ws, B_MISC, 128));
     unsigned int *d_nfb = (unsigned int *)ws.buf[B_MISC];      // [0..1] fallback counters, [4] n_out, [8..9] max |q|^2, |t|^2
     int32_t *d_nout = (int32_t *)(d_nfb + 4);
     unsigned int *d_max = d_nfb + 8;
     L2CK(cudaMemsetAsync(d_nfb, 0, 128, stream));
-    float *nQ = (float *)ws.buf[B_NORM], *nT = nQ + nqp;
-    l2_norms_kernel<<<(unsigned)((nqp + 255) / 256), 256, 0, stream>>>(dQ, nq, (int)nqp, kpad, dim, nQ, d_max);
-    l2_norms_kernel<<<(unsigned)((ntp + 255) / 256), 256, 0, stream>>>(dT, nt, (int)ntp, kpad, dim, nT, d_max + 1);
+    float *nQ = (float *)ws.buf[B_NORM], *nT = nQ + nqp, *bQ = nT + ntp, *bT = bQ + 8 * nqp;
+    l2_norms_kernel<<<(unsigned)((nqp + 255) / 256), 256, 0, stream>>>(dQ, nq, (int)nqp, kpad, dim, nQ, bQ, d_max);
+    l2_norms_kernel<<<(unsigned)((ntp + 255) / 256), 256, 0, stream>>>(dT, nt, (int)ntp, kpad, dim, nT, bT, d_max + 1);
     nl += 2;
 
     const int passes = cross ? 2 : 1;
@@ -614,13 +688,13 @@ int l2_knn2(L2Workspace &ws, cudaStream_t stream, const float *query, int nq, co
     for (int pass = 0; pass < passes; ++pass) {
         const float *A = pass == 0 ? dQ : dT, *Bm = pass == 0 ? dT : dQ;
         const int na = pass == 0 ? nq : nt, nb = pass == 0 ? nt : nq;
-        float *nA = pass == 0 ? nQ : nT, *nB = pass == 0 ? nT : nQ;
+        float *nA = pass == 0 ? nQ : nT, *biasB = pass == 0 ? bT : bQ;
         int32_t *o_idx = pass == 0 ? f_idx : r_idx; float *o_d2 = pass == 0 ? f_d2 : r_d2; uint8_t *o_flag = pass == 0 ? f_flag : r_flag;
         const unsigned int *bmax = pass == 0 ? d_max + 1 : d_max;
         int splits, tps;
         plan_splits(na, nb, splits, tps);
         cudaEventRecord(ws.ev[2], stream);
-        int st = gemm_candidates(ws, stream, A, na, Bm, nb, kpad, kpad, nB, nA, bmax, splits, tps, err);
+        int st = gemm_candidates(ws, stream, A, na, Bm, nb, kpad, kpad, biasB, nA, bmax, splits, tps, err);
         if (st != MVS_OK) return st;
         cudaEventRecord(ws.ev[3], stream);
         nl += 1;
