@@ -895,8 +895,9 @@ def l2_block(ctx, mvs, peaks_m):
                               note="descriptors and outputs resident in HBM (device pointers through the same entry point): norms + GEMM + "
                                    "re-rank + fallback check + sqrt"),
                 note="call_device_ms / call_wall_ms with host buffers include the upload of both 8 MB descriptor sets from pageable memory "
-                     "(~1.0 ms of the 1.44) and the download of the top-2 lists; kernels: norms 2 x 12 us, GEMM 347, re-rank 55, fallback "
-                     "check 20, sqrt 3 (ncu launch list, profiles/l2_launches_r2.csv)")
+                     "(~0.9 ms) and the download of the top-2 lists; resident: device descriptor sets are read in place; kernels: "
+                     "norms + bias rows 2 x ~5 us, GEMM (bias -|t|^2/2 folded into the contraction), re-rank (+ sqrt) ~55 us, fallback "
+                     "list walk ~3 us (profiles/l2_launches_r2.csv)")
 
 
 def e2e_distinct_block(mvs, torch, local, flush, n_pairs=1024, chunk=256, n_ctx=4):

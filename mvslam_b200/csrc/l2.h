@@ -12,7 +12,7 @@ struct L2Workspace {
     void *buf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t stats[4] = {0, 0, 0, 0};     // fallbacks fwd, fallbacks rev, gemm us, total us
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // call begin/end, GEMM begin/end per pass
     void release();
 };
 

@@ -152,22 +152,26 @@ __device__ __forceinline__ float tf32_head(float x) { return __uint_as_float(__f
 __global__ void l2_norms_kernel(const float *x, int n, int n_padded, int ld, int dim, float *out, float *bias /* [n_padded][8] */,
                                 unsigned int *max_bits)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_padded) return;
+    // 16 lanes per row: consecutive lanes read consecutive floats (the order of this sum is free: the norm only enters the
+    // error band and the approximate score, never an exact distance)
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 4, sub = threadIdx.x & 15;
+    float s = 0.f;
+    if (i < n)
+        for (int k = sub; k < dim; k += 16) { const float v = x[(size_t)i * ld + k]; s = fmaf(v, v, s); }
+#pragma unroll
+    for (int off = 8; off > 0; off >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, off);
+    unsigned m = (i < n) ? __float_as_uint(s) : 0u;
+    m = __reduce_max_sync(0xFFFFFFFFu, m);
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(max_bits, m);
+    if (sub != 0 || i >= n_padded) return;
     float4 *brow = reinterpret_cast<float4 *>(bias + (size_t)i * 8);
     brow[1] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (i >= n) { out[i] = CUDART_INF_F; brow[0] = make_float4(kPadBias, 0.f, 0.f, 0.f); return; }
-    float s = 0.f;
-    for (int k = 0; k < dim; ++k) s = fmaf(x[(size_t)i * ld + k], x[(size_t)i * ld + k], s);
     out[i] = s;
-    {
-        const float h = -0.5f * s;
-        const float h0 = tf32_head(h), r0 = h - h0;          // exact: h0 is the head of h
-        const float h1 = tf32_head(r0), r1 = r0 - h1;
-        brow[0] = make_float4(h0, h1, tf32_head(r1), 0.f);
-    }
-    const unsigned m = __reduce_max_sync(__activemask(), __float_as_uint(s));
-    if ((threadIdx.x & 31) == (__ffs(__activemask()) - 1)) atomicMax(max_bits, m);
+    const float h = -0.5f * s;
+    const float h0 = tf32_head(h), r0 = h - h0;          // exact: h0 is the head of h
+    const float h1 = tf32_head(r0), r1 = r0 - h1;
+    brow[0] = make_float4(h0, h1, tf32_head(r1), 0.f);
 }
 
 __global__ void l2_pad_kernel(const float *src, int n, int dim, float *dst, int ld)
@@ -375,7 +379,8 @@ __global__ void l2_rerank_kernel(const float *__restrict__ Q, const float *__res
                                  int lists,
                                  const float *__restrict__ cand_val, const int32_t *__restrict__ cand_idx,
                                  const int32_t *__restrict__ cand_cnt,
-                                 int32_t *__restrict__ out_idx, float *__restrict__ out_d2, uint8_t *__restrict__ flag)
+                                 int32_t *__restrict__ out_idx, float *__restrict__ out_d2, float *__restrict__ out_dist /* or null */,
+                                 int32_t *__restrict__ fb_list, unsigned int *__restrict__ n_fallback)
 {
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -418,47 +423,47 @@ __global__ void l2_rerank_kernel(const float *__restrict__ Q, const float *__res
     if (lane == 0) {
         out_idx[2 * q] = (g1 == ~0ull) ? -1 : (int)(g1 & 0xFFFFFFFFu);
         out_idx[2 * q + 1] = (g2 == ~0ull) ? -1 : (int)(g2 & 0xFFFFFFFFu);
-        out_d2[2 * q] = __uint_as_float((unsigned)(g1 >> 32));
-        out_d2[2 * q + 1] = __uint_as_float((unsigned)(g2 >> 32));
-        flag[q] = overflow ? 1 : 0;
+        const float d1 = __uint_as_float((unsigned)(g1 >> 32)), d2 = __uint_as_float((unsigned)(g2 >> 32));
+        out_d2[2 * q] = d1;
+        out_d2[2 * q + 1] = d2;
+        if (out_dist) { out_dist[2 * q] = sqrtf(d1); out_dist[2 * q + 1] = sqrtf(d2); }
+        if (overflow) fb_list[atomicAdd(n_fallback, 1u)] = q;      // rare: the exact kernel redoes this query
     }
 }
 
-// exact brute force for the queries whose candidate list overflowed (one CTA per flagged query)
+// exact brute force for the queries whose candidate list overflowed: the CTAs walk the list the re-rank kernel wrote
 __global__ void l2_fallback_kernel(const float *__restrict__ Q, const float *__restrict__ T, int ldq, int ldt, int dim,
-                                   int nt, const uint8_t *__restrict__ flag, int32_t *__restrict__ out_idx,
-                                   float *__restrict__ out_d2, unsigned int *__restrict__ n_fallback)
+                                   int nt, const int32_t *__restrict__ fb_list, const unsigned int *__restrict__ n_fallback,
+                                   int32_t *__restrict__ out_idx, float *__restrict__ out_d2, float *__restrict__ out_dist /* or null */)
 {
-    const int q = blockIdx.x;
-    if (!flag[q]) return;
     __shared__ unsigned long long s1[8], s2[8];
-    unsigned long long b1 = ~0ull, b2 = ~0ull;
-    for (int t = threadIdx.x; t < nt; t += blockDim.x) {
-        const unsigned long long k = key_of(exact_d2(Q + (size_t)q * ldq, T + (size_t)t * ldt, dim), t);
-        if (k < b1) { b2 = b1; b1 = k; } else if (k < b2) b2 = k;
-    }
-    const unsigned long long g1 = warp_min_u64(b1);
-    const unsigned long long g2 = warp_min_u64((b1 == g1) ? b2 : b1);
-    if ((threadIdx.x & 31) == 0) { s1[threadIdx.x >> 5] = g1; s2[threadIdx.x >> 5] = g2; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned long long f1 = ~0ull, f2 = ~0ull;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
-            const unsigned long long c[2] = {s1[w], s2[w]};
-            for (int j = 0; j < 2; ++j) { if (c[j] < f1) { f2 = f1; f1 = c[j]; } else if (c[j] < f2) f2 = c[j]; }
+    const unsigned int n = *n_fallback;
+    for (unsigned int item = blockIdx.x; item < n; item += gridDim.x) {
+        const int q = fb_list[item];
+        unsigned long long b1 = ~0ull, b2 = ~0ull;
+        for (int t = threadIdx.x; t < nt; t += blockDim.x) {
+            const unsigned long long k = key_of(exact_d2(Q + (size_t)q * ldq, T + (size_t)t * ldt, dim), t);
+            if (k < b1) { b2 = b1; b1 = k; } else if (k < b2) b2 = k;
         }
-        out_idx[2 * q] = (f1 == ~0ull) ? -1 : (int)(f1 & 0xFFFFFFFFu);
-        out_idx[2 * q + 1] = (f2 == ~0ull) ? -1 : (int)(f2 & 0xFFFFFFFFu);
-        out_d2[2 * q] = __uint_as_float((unsigned)(f1 >> 32));
-        out_d2[2 * q + 1] = __uint_as_float((unsigned)(f2 >> 32));
-        atomicAdd(n_fallback, 1u);
+        const unsigned long long g1 = warp_min_u64(b1);
+        const unsigned long long g2 = warp_min_u64((b1 == g1) ? b2 : b1);
+        if ((threadIdx.x & 31) == 0) { s1[threadIdx.x >> 5] = g1; s2[threadIdx.x >> 5] = g2; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long f1 = ~0ull, f2 = ~0ull;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+                const unsigned long long c[2] = {s1[w], s2[w]};
+                for (int j = 0; j < 2; ++j) { if (c[j] < f1) { f2 = f1; f1 = c[j]; } else if (c[j] < f2) f2 = c[j]; }
+            }
+            const float d1 = __uint_as_float((unsigned)(f1 >> 32)), d2 = __uint_as_float((unsigned)(f2 >> 32));
+            out_idx[2 * q] = (f1 == ~0ull) ? -1 : (int)(f1 & 0xFFFFFFFFu);
+            out_idx[2 * q + 1] = (f2 == ~0ull) ? -1 : (int)(f2 & 0xFFFFFFFFu);
+            out_d2[2 * q] = d1;
+            out_d2[2 * q + 1] = d2;
+            if (out_dist) { out_dist[2 * q] = sqrtf(d1); out_dist[2 * q + 1] = sqrtf(d2); }
+        }
+        __syncthreads();
     }
-}
-
-__global__ void l2_sqrt_kernel(const float *d2, int n, float *d)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) d[i] = sqrtf(d2[i]);
 }
 
 // Lowe ratio + max_dist (+ cross-check) on float distances, then sort by (distance, queryIdx); one CTA.
@@ -628,7 +633,7 @@ int gemm_candidates(L2Workspace &ws, cudaStream_t stream, const float *dA, int n
 void L2Workspace::release()
 {
     for (int i = 0; i < 8; ++i) { if (buf[i]) cudaFree(buf[i]); buf[i] = nullptr; cap[i] = 0; }
-    for (int i = 0; i < 4; ++i) { if (ev[i]) cudaEventDestroy(ev[i]); ev[i] = nullptr; }
+    for (int i = 0; i < 6; ++i) { if (ev[i]) cudaEventDestroy(ev[i]); ev[i] = nullptr; }
 }
 
 int l2_knn2(L2Workspace &ws, cudaStream_t stream, const float *query, int nq, const float *train, int nt, int dim,
@@ -637,7 +642,7 @@ int l2_knn2(L2Workspace &ws, cudaStream_t stream, const float *query, int nq, co
 {
     int nl = 0;
     if (n_launches) *n_launches = 0;
-    for (int i = 0; i < 4; ++i) if (!ws.ev[i]) cudaEventCreate(&ws.ev[i]);
+    for (int i = 0; i < 6; ++i) if (!ws.ev[i]) cudaEventCreate(&ws.ev[i]);
     cudaEventRecord(ws.ev[0], stream);
     float gemm_ms_total = 0.f;
     if (n_out) *n_out = 0;
@@ -645,20 +650,32 @@ int l2_knn2(L2Workspace &ws, cudaStream_t stream, const float *query, int nq, co
     if (nq > (1 << 22) || nt > (1 << 22)) { err = "more than 2^22 descriptors per side"; return MVS_E_UNSUPPORTED; }
     const int kpad = ((dim + KSLAB - 1) / KSLAB) * KSLAB;
     const bool cross = mp && mp->cross_check;
-    // device copies (padded to a multiple of 32 floats per row when needed)
-    L2CK(ensure(ws, B_Q, (size_t)nq * kpad * sizeof(float) + (size_t)nq * dim * sizeof(float)));
-    L2CK(ensure(ws, B_T, (size_t)nt * kpad * sizeof(float) + (size_t)nt * dim * sizeof(float)));
-    float *dQ = (float *)ws.buf[B_Q], *dT = (float *)ws.buf[B_T];
-    if (kpad == dim) {
-        L2CK(cudaMemcpyAsync(dQ, query, (size_t)nq * dim * sizeof(float), cudaMemcpyDefault, stream));
-        L2CK(cudaMemcpyAsync(dT, train, (size_t)nt * dim * sizeof(float), cudaMemcpyDefault, stream));
-    } else {
-        float *rq = dQ + (size_t)nq * kpad, *rt = dT + (size_t)nt * kpad;
-        L2CK(cudaMemcpyAsync(rq, query, (size_t)nq * dim * sizeof(float), cudaMemcpyDefault, stream));
-        L2CK(cudaMemcpyAsync(rt, train, (size_t)nt * dim * sizeof(float), cudaMemcpyDefault, stream));
-        l2_pad_kernel<<<(unsigned)(((size_t)nq * kpad + 255) / 256), 256, 0, stream>>>(rq, nq, dim, dQ, kpad);
-        l2_pad_kernel<<<(unsigned)(((size_t)nt * kpad + 255) / 256), 256, 0, stream>>>(rt, nt, dim, dT, kpad);
-        nl += 2;
+    // Operands: descriptor sets that are already in device memory with a TMA-compatible layout (rows of a multiple of 32 floats,
+    // 16-byte aligned) are read where they are; host buffers are copied, and rows of another length are padded to kpad floats.
+    auto resident = [&](const float *p) {
+        if (kpad != dim || ((uintptr_t)p & 15u)) return false;
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+        return at.type == cudaMemoryTypeDevice;
+    };
+    const float *dQ = query, *dT = train;
+    const float *const src[2] = {query, train};
+    const float **dst[2] = {&dQ, &dT};
+    const int rows[2] = {nq, nt};
+    for (int k = 0; k < 2; ++k) {
+        if (resident(src[k])) continue;
+        const int bi = k == 0 ? B_Q : B_T;
+        L2CK(ensure(ws, bi, (size_t)rows[k] * kpad * sizeof(float) + (kpad == dim ? 0 : (size_t)rows[k] * dim * sizeof(float))));
+        float *d = (float *)ws.buf[bi];
+        if (kpad == dim) {
+            L2CK(cudaMemcpyAsync(d, src[k], (size_t)rows[k] * dim * sizeof(float), cudaMemcpyDefault, stream));
+        } else {
+            float *raw = d + (size_t)rows[k] * kpad;
+            L2CK(cudaMemcpyAsync(raw, src[k], (size_t)rows[k] * dim * sizeof(float), cudaMemcpyDefault, stream));
+            l2_pad_kernel<<<(unsigned)(((size_t)rows[k] * kpad + 255) / 256), 256, 0, stream>>>(raw, rows[k], dim, d, kpad);
+            nl += 1;
+        }
+        *dst[k] = d;
     }
     // norms, |t|max (host reduction of nt floats: part of the error bound, not of the distance computation)
     // squared norms, each array padded with +inf to a multiple of the column tile (padded columns never win);
@@ -671,47 +688,42 @@ int l2_knn2(L2Workspace &ws, cudaStream_t stream, const float *query, int nq, co
     unsigned int *d_max = d_nfb + 8;
     L2CK(cudaMemsetAsync(d_nfb, 0, 128, stream));
     float *nQ = (float *)ws.buf[B_NORM], *nT = nQ + nqp, *bQ = nT + ntp, *bT = bQ + 8 * nqp;
-    l2_norms_kernel<<<(unsigned)((nqp + 255) / 256), 256, 0, stream>>>(dQ, nq, (int)nqp, kpad, dim, nQ, bQ, d_max);
-    l2_norms_kernel<<<(unsigned)((ntp + 255) / 256), 256, 0, stream>>>(dT, nt, (int)ntp, kpad, dim, nT, bT, d_max + 1);
+    l2_norms_kernel<<<(unsigned)((nqp * 16 + 255) / 256), 256, 0, stream>>>(dQ, nq, (int)nqp, kpad, dim, nQ, bQ, d_max);
+    l2_norms_kernel<<<(unsigned)((ntp * 16 + 255) / 256), 256, 0, stream>>>(dT, nt, (int)ntp, kpad, dim, nT, bT, d_max + 1);
     nl += 2;
 
     const int passes = cross ? 2 : 1;
-    // outputs: forward idx/d2/dist/flag, reverse idx/d2/flag
-    const size_t per_f = (size_t)nq * (2 * 4 + 2 * 4 + 2 * 4 + 1) + 64, per_r = (size_t)nt * (2 * 4 + 2 * 4 + 1) + 64;
+    // outputs: forward idx/d2/dist/fallback list, reverse idx/d2/fallback list
+    const size_t per_f = (size_t)nq * (2 * 4 + 2 * 4 + 2 * 4 + 4) + 64, per_r = (size_t)nt * (2 * 4 + 2 * 4 + 4) + 64;
     L2CK(ensure(ws, B_OUT, per_f + per_r + 64));
     uint8_t *ob = (uint8_t *)ws.buf[B_OUT];
     int32_t *f_idx = (int32_t *)ob; float *f_d2 = (float *)(f_idx + 2 * (size_t)nq); float *f_dist = f_d2 + 2 * (size_t)nq;
-    uint8_t *f_flag = (uint8_t *)(f_dist + 2 * (size_t)nq);
+    int32_t *f_list = (int32_t *)(f_dist + 2 * (size_t)nq);
     uint8_t *rb = ob + ((per_f + 15) & ~(size_t)15);
-    int32_t *r_idx = (int32_t *)rb; float *r_d2 = (float *)(r_idx + 2 * (size_t)nt); uint8_t *r_flag = (uint8_t *)(r_d2 + 2 * (size_t)nt);
+    int32_t *r_idx = (int32_t *)rb; float *r_d2 = (float *)(r_idx + 2 * (size_t)nt); int32_t *r_list = (int32_t *)(r_d2 + 2 * (size_t)nt);
 
     for (int pass = 0; pass < passes; ++pass) {
         const float *A = pass == 0 ? dQ : dT, *Bm = pass == 0 ? dT : dQ;
         const int na = pass == 0 ? nq : nt, nb = pass == 0 ? nt : nq;
         float *nA = pass == 0 ? nQ : nT, *biasB = pass == 0 ? bT : bQ;
-        int32_t *o_idx = pass == 0 ? f_idx : r_idx; float *o_d2 = pass == 0 ? f_d2 : r_d2; uint8_t *o_flag = pass == 0 ? f_flag : r_flag;
+        int32_t *o_idx = pass == 0 ? f_idx : r_idx; float *o_d2 = pass == 0 ? f_d2 : r_d2; int32_t *o_list = pass == 0 ? f_list : r_list;
+        float *o_dist = pass == 0 ? f_dist : nullptr;
         const unsigned int *bmax = pass == 0 ? d_max + 1 : d_max;
         int splits, tps;
         plan_splits(na, nb, splits, tps);
-        cudaEventRecord(ws.ev[2], stream);
+        cudaEventRecord(ws.ev[2 + 2 * pass], stream);
         int st = gemm_candidates(ws, stream, A, na, Bm, nb, kpad, kpad, biasB, nA, bmax, splits, tps, err);
         if (st != MVS_OK) return st;
-        cudaEventRecord(ws.ev[3], stream);
+        cudaEventRecord(ws.ev[3 + 2 * pass], stream);
         nl += 1;
         l2_rerank_kernel<<<(na + 7) / 8, 256, 0, stream>>>(A, Bm, kpad, kpad, dim, nA, bmax, na, nb, splits * 2,
                                                            (const float *)ws.buf[B_CAND_V], (const int32_t *)ws.buf[B_CAND_I],
                                                            (const int32_t *)ws.buf[B_CAND_I] + (size_t)na * splits * 2 * KC,
-                                                           o_idx, o_d2, o_flag);
-        l2_fallback_kernel<<<na, 256, 0, stream>>>(A, Bm, kpad, kpad, dim, nb, o_flag, o_idx, o_d2, d_nfb + pass);
+                                                           o_idx, o_d2, o_dist, o_list, d_nfb + pass);
+        // queries whose candidate list overflowed (heavily duplicated data): exact brute force over the list the re-rank wrote
+        l2_fallback_kernel<<<std::min(na, 592), 256, 0, stream>>>(A, Bm, kpad, kpad, dim, nb, o_list, d_nfb + pass, o_idx, o_d2, o_dist);
         nl += 2;
-        {   // per-pass GEMM time (the event pair is reused by the cross-check pass, so read it now)
-            cudaEventSynchronize(ws.ev[3]);
-            float ms = 0.f;
-            if (cudaEventElapsedTime(&ms, ws.ev[2], ws.ev[3]) == cudaSuccess) gemm_ms_total += ms;
-        }
     }
-    l2_sqrt_kernel<<<(2 * nq + 255) / 256, 256, 0, stream>>>(f_d2, 2 * nq, f_dist);
-    nl += 1;
     L2CK(cudaGetLastError());
     if (idx) L2CK(cudaMemcpyAsync(idx, f_idx, (size_t)nq * 2 * sizeof(int32_t), cudaMemcpyDefault, stream));   // host or device (UVA)
     if (dist) L2CK(cudaMemcpyAsync(dist, f_dist, (size_t)nq * 2 * sizeof(float), cudaMemcpyDefault, stream));
@@ -740,6 +752,10 @@ int l2_knn2(L2Workspace &ws, cudaStream_t stream, const float *query, int nq, co
     L2CK(cudaStreamSynchronize(stream));
     float tot_ms = 0.f;
     cudaEventElapsedTime(&tot_ms, ws.ev[0], ws.ev[1]);
+    for (int pass = 0; pass < passes; ++pass) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ws.ev[2 + 2 * pass], ws.ev[3 + 2 * pass]) == cudaSuccess) gemm_ms_total += ms;
+    }
     ws.stats[0] = hfb[0]; ws.stats[1] = hfb[1];
     ws.stats[2] = (uint64_t)(gemm_ms_total * 1000.f); ws.stats[3] = (uint64_t)(tot_ms * 1000.f);
     if (n_launches) *n_launches = nl;
