@@ -615,11 +615,11 @@ def main():
         t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_ms = float(t.item())
     h2d = sum(d.nbytes for d in descs) + sum(k.nbytes for k in kps) + pairs.nbytes
-    # bytes the synchronous call copies back: the records, and per pair as many detail entries (45 B each) as the fullest
-    # pair of the batch holds (the library reads the counts first when the details exceed 1 MB)
+    # bytes that come back: the records, and per pair exactly the entries it owns (the outputs are pinned, so the library's
+    # export kernel writes n_matches x (12 + 1) B and n_points x (24 + 8) B per pair straight into them)
     e2e_res = np.frombuffer(res_t.numpy(), dtype=mvs.RESULT_DTYPE)
-    wc = cap if Bd * cap * 45 <= (1 << 20) else min(cap, max(1, int(e2e_res["n_matches"].max())))
-    d2h = res_t.numel() + (0 if strong else Bd * wc * 45 + 4 * Bd)
+    d2h = res_t.numel() + (0 if strong else int(np.minimum(e2e_res["n_matches"][:Bd], cap).sum()) * 13
+                           + int(np.minimum(e2e_res["n_points"][:Bd], cap).sum()) * 32)
 
     if rank != 0:
         if world > 1:
@@ -758,6 +758,11 @@ def main():
 
     n_job = int(cfg.get("pairs_total", B * world))      # pairs all ranks processed per step
     value = n_job * args.steps / (total_ms * 1e-3)
+    # the same end-to-end step issued by a C++ caller (tools/latency_probe: five frames uploaded + one synchronous 1024-pair call
+    # with every detail output, pinned buffers from mvs_host_alloc, host wall clock): what the ctypes marshalling costs on top
+    e2e_cpp = None
+    if isinstance(lat, dict) and isinstance(lat.get("cpp_caller"), dict) and args.workload == "tsukuba" and solver == "reference":
+        e2e_cpp = lat["cpp_caller"].get("e2e_1024_pairs_reference_h1")
     line = dict(metric=METRIC, value=value, unit="pairs/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=total_ms / args.steps, step_ms_rank0=step_stats(step_ms), higher_is_better=True, scaling="strong" if strong else "weak",
                 vs_baseline=None, dtype="s8-mma/s32 + f64" if tensor_matcher else "u32-popc/f64",
@@ -766,7 +771,7 @@ def main():
                             final_gather_ms=gather_ms),
                 clocks=clocks.summary(),
                 e2e=dict(value=n_job / (e2e_ms * 1e-3), unit="pairs/s", h2d_bytes_per_step=int(h2d),
-                         d2h_bytes_per_step=int(d2h), ms_per_step=e2e_ms, step_ms_rank0=step_stats(e2e_steps),
+                         d2h_bytes_per_step=int(d2h), ms_per_step=e2e_ms, step_ms_rank0=step_stats(e2e_steps), cpp_caller=e2e_cpp,
                          note="the 1024 pairs cycle the 4 bundled VO pairs, so a step uploads 5 frames (0.36 MB); see e2e_distinct for a "
                               "sequence in which every pair brings a new frame" if args.workload == "tsukuba" else None),
                 e2e_distinct=dist_e2e,
@@ -958,7 +963,7 @@ def e2e_distinct_block(mvs, torch, local, flush, n_pairs=1024, chunk=256, n_ctx=
         cx[0].synchronize(); rs.append(ev0.elapsed_time(ev1))
     med = float(np.median(ts)); rmed = float(np.median(rs))
     h2d = int(D.numel() + P.numel() * 4 + (len(chunks) - 1) * nk * 40)
-    d2h = int(n_pairs * (item + cap * 45))
+    d2h = int(n_pairs * item + int(np.minimum(res["n_matches"], cap).sum()) * 13 + int(np.minimum(res["n_points"], cap).sum()) * 32)
     for c in cx:
         c.close()
     return dict(config=dict(cfg, solver="fast", chunk_pairs=chunk, contexts=n_ctx), value=n_pairs / (med * 1e-3), unit="pairs/s",

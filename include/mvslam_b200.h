@@ -201,6 +201,11 @@ int  mvs_profile_enable(mvs_ctx *ctx, int on);
 int  mvs_profile_read(mvs_ctx *ctx, mvs_profile *out, int reset);
 /* number of kernels this ctx has launched so far */
 uint64_t mvs_kernel_launches(const mvs_ctx *ctx);
+/* Page-locked host memory for callers that do not link the CUDA runtime themselves (the reference is plain C++): buffers
+ * from here make the library's host<->device copies asynchronous, and pinned detail outputs of mvs_pair_batch are written
+ * by the device directly (only the entries each pair owns).  NULL on failure.  Free with mvs_host_free. */
+void *mvs_host_alloc(size_t bytes);
+void  mvs_host_free(void *p);
 /* Test hook.  With MVS_GUARD=1 in the environment when the library is loaded, every workspace buffer is allocated at
  * exactly the requested size plus a 4 KB guard band; this returns how many buffers had their band overwritten since
  * they were allocated (0 = no kernel wrote past the end of its buffer), -1 when guard mode is off. */

@@ -676,6 +676,41 @@ def test_large_synchronous_batch_trims_detail_copies(ctx, tsukuba):
     assert not dbig["matches"][:, most:]["distance"].any()         # slots beyond the fullest pair were not copied (host zeros)
 
 
+@pytest.mark.parametrize("enqueue", [False, True])
+@pytest.mark.parametrize("cap", [2048, 40])
+def test_pinned_detail_outputs_are_written_by_the_device(ctx, tsukuba, enqueue, cap):
+    """Detail buffers in pinned host memory are filled by the library's export kernel (exactly the entries every pair owns,
+    api.cu export_details_kernel) instead of strided copies: same bytes as the pageable-buffer call inside the counts, nothing
+    written beyond them, truncation at `capacity` as documented; a bad pair leaves its rows alone."""
+    torch = pytest.importorskip("torch")
+    descs = [tsukuba[f"desc{i}"] for i in range(1, 6)] + [tsukuba["desc1"][:1]]; kps = [tsukuba[f"kp{i}"] for i in range(1, 6)] + [tsukuba["kp1"][:1]]
+    ctx.frames_upload(descs, kps)
+    pairs = [(0, 1), (1, 2), (5, 2), (3, 4), (4, 0), (2, 3)]       # (5, 2): a one-keypoint base frame cannot be matched
+    n = len(pairs)
+    kw = dict(max_dist=30.0, H=32, seed=9, solver="fast")
+    ref, dref = ctx.pair_batch(pairs, tsukuba["K"], **kw)
+    assert ref["status"][2] != 0 and (ref["status"][[0, 1, 3, 4, 5]] == 0).all()
+    assert cap == 2048 or ref["n_matches"].max() > cap          # the small capacity truncates
+    item = mvs.RESULT_DTYPE.itemsize
+    res_t = torch.zeros(n * item, dtype=torch.uint8).pin_memory()
+    mat_t = torch.full((n * cap * 12,), 0xEE, dtype=torch.uint8).pin_memory(); msk_t = torch.full((n * cap,), 0xEE, dtype=torch.uint8).pin_memory()
+    pts_t = torch.full((n * cap * 3,), -7.0, dtype=torch.float64).pin_memory(); idx_t = torch.full((n * cap,), -7, dtype=torch.int64).pin_memory()
+    ctx.pair_batch(pairs, tsukuba["K"], enqueue_only=enqueue, out=dict(
+        results=res_t.data_ptr(), matches=mat_t.data_ptr(), mask=msk_t.data_ptr(), points=pts_t.data_ptr(), indexes=idx_t.data_ptr(),
+        capacity=cap), **kw)
+    ctx.synchronize()
+    res = np.frombuffer(res_t.numpy(), dtype=mvs.RESULT_DTYPE)
+    assert res.tobytes() == ref.tobytes()
+    mat = np.frombuffer(mat_t.numpy(), dtype=mvs.MATCH_DTYPE).reshape(n, cap); msk = msk_t.numpy().reshape(n, cap)
+    pts = pts_t.numpy().reshape(n, cap, 3); idx = idx_t.numpy().reshape(n, cap)
+    for i in range(n):
+        m, k = min(int(ref["n_matches"][i]), cap), min(int(ref["n_points"][i]), cap)
+        assert np.array_equal(mat[i][:m], dref["matches"][i][:m]) and np.array_equal(msk[i][:m], dref["mask"][i][:m])
+        assert np.array_equal(pts[i][:k], dref["points"][i][:k]) and np.array_equal(idx[i][:k].astype(np.uint64), dref["indexes"][i][:k])
+        assert (mat_t.numpy().reshape(n, cap * 12)[i][m * 12:] == 0xEE).all() and (msk[i][m:] == 0xEE).all()      # untouched
+        assert (pts[i][k:] == -7.0).all() and (idx[i][k:] == -7).all()
+
+
 def test_empty_and_degenerate_inputs(ctx):
     """Empty / minimal inputs: status codes instead of the reference's asserts or undefined behaviour."""
     q = np.zeros((0, 32), np.uint8); t = np.random.default_rng(0).integers(0, 256, (10, 32), dtype=np.uint8)

@@ -89,6 +89,55 @@ int main(int argc, char **argv)
                             median(t_enq), median(t_total), median(t_rec), res[0].n_inliers, res[0].n_points);
                 first = false;
             }
+        // the bench's end-to-end step from a C++ caller: every step uploads the five frames again and makes one synchronous
+        // 1024-pair call (the four consecutive pairs cycled) with all detail outputs, REFERENCE solver, H = 1, every buffer pinned
+        // (mvs_host_alloc): host wall clock per step
+        {
+            const int n_pairs = 1024, ecap = 256;
+            struct Pinned {
+                void *p;
+                explicit Pinned(size_t b) : p(mvs_host_alloc(b)) {}
+                ~Pinned() { mvs_host_free(p); }
+            };
+            std::vector<Pinned *> keep;
+            std::vector<const uint8_t *> pdp;
+            std::vector<const float *> pkp;
+            for (size_t f = 0; f < feats.size(); ++f) {
+                Pinned *d = new Pinned((size_t)counts[f] * 32), *k = new Pinned((size_t)counts[f] * 8);
+                if (!d->p || !k->p) { std::fprintf(stderr, "mvs_host_alloc failed\n"); return 5; }
+                std::copy(dp[f], dp[f] + (size_t)counts[f] * 32, static_cast<uint8_t *>(d->p));
+                std::copy(kp[f].begin(), kp[f].end(), static_cast<float *>(k->p));
+                pdp.push_back(static_cast<const uint8_t *>(d->p)); pkp.push_back(static_cast<const float *>(k->p));
+                keep.push_back(d); keep.push_back(k);
+            }
+            Pinned res((size_t)n_pairs * sizeof(mvs_pair_result)), mat((size_t)n_pairs * ecap * sizeof(mvs_match)), msk((size_t)n_pairs * ecap),
+                pts((size_t)n_pairs * ecap * 24), idx((size_t)n_pairs * ecap * 8);
+            if (!res.p || !mat.p || !msk.p || !pts.p || !idx.p) { std::fprintf(stderr, "mvs_host_alloc failed\n"); return 5; }
+            std::vector<int32_t> pairs;
+            for (int i = 0; i < n_pairs; ++i) { pairs.push_back(i % 4); pairs.push_back(i % 4 + 1); }
+            mvs_match_params mp{};
+            mp.ratio = 0.7; mp.max_dist = 10.0;
+            mvs_ransac_params rp{};
+            rp.n_hypotheses = 1; rp.solver = MVS_SOLVER_REFERENCE;
+            std::vector<double> t_step;
+            int solved = 0;
+            for (int it = 0; it < 60; ++it) {
+                const double t0 = now_us();
+                if (mvs_frames_upload(ctx, (int)feats.size(), pdp.data(), pkp.data(), counts.data(), 32) != MVS_OK) return 3;
+                const int st = mvs_pair_batch(ctx, pairs.data(), n_pairs, K, &mp, &rp, static_cast<mvs_pair_result *>(res.p),
+                                              static_cast<mvs_match *>(mat.p), static_cast<uint8_t *>(msk.p), static_cast<double *>(pts.p),
+                                              static_cast<uint64_t *>(idx.p), ecap);
+                const double t1 = now_us();
+                if (st != MVS_OK) { std::fprintf(stderr, "pair_batch: %s\n", mvs_last_error(ctx)); return 4; }
+                if (it >= 10) t_step.push_back(t1 - t0);
+            }
+            for (int i = 0; i < n_pairs; ++i) solved += static_cast<mvs_pair_result *>(res.p)[i].status == MVS_OK;
+            std::sort(t_step.begin(), t_step.end());
+            std::printf(", \"e2e_1024_pairs_reference_h1\": {\"step_us_median\": %.1f, \"step_us_min\": %.1f, \"step_us_max\": %.1f, "
+                        "\"pairs_per_s\": %.0f, \"solved\": %d}",
+                        t_step[t_step.size() / 2], t_step.front(), t_step.back(), n_pairs / (t_step[t_step.size() / 2] * 1e-6), solved);
+            for (Pinned *q : keep) delete q;
+        }
         std::printf("}\n");
         mvs_destroy(ctx);
     } catch (const std::exception &e) {
