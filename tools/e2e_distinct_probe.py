@@ -1,0 +1,17 @@
+#!/usr/bin/env python
+"""A/B of the chunking of bench.py's e2e_distinct job (1025 distinct frames -> 1024 consecutive pairs): prints one line per
+(chunk size, context count)."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+import bench  # noqa: E402
+import mvslam_b200 as mvs  # noqa: E402
+
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+for chunk, n_ctx in [(256, 4), (128, 4), (128, 8), (64, 8), (192, 6), (512, 2)]:
+    r = bench.e2e_distinct_block(mvs, torch, 0, flush, 1024, chunk, n_ctx)
+    print(json.dumps(dict(chunk=chunk, contexts=n_ctx, ms=r["ms_per_step"]["median"], value=r["value"], frac=r["frac_of_device_resident"])))
