@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""Rewrites the measured sections of profiles/README.md (round 2) from the committed bench lines, so that no number is typed by hand."""
+import json
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P = os.path.join(ROOT, "profiles")
+
+
+def line(name):
+    p = os.path.join(P, name)
+    if not os.path.exists(p):
+        return None
+    rows = [json.loads(l) for l in open(p) if l.startswith("{")]
+    return rows[-1] if rows else None
+
+
+t, ref, n2, n8 = line("bench_tsukuba_r2.json"), line("bench_reference_r2.json"), line("bench_n2_r2.json"), line("bench_n8_r2.json")
+probe = json.load(open(os.path.join(P, "tc_probe_r2.json")))
+rf, e2e, st = t["roofline"], t["e2e"], t["step_ms_rank0"]
+L = ["## Headline (BASELINE config 2 as the reference runs it: 1024 Tsukuba VO pairs, max_dist 10, H = 1, REFERENCE solver)", ""]
+cpp = e2e.get("cpp_caller") or {}
+L += [f"* device-resident **{t['value'] / 1e6:.3f} M pairs/s**, {t['ms_per_step']:.3f} ms per step (min {st['min']:.3f}, max {st['max']:.3f}, {st['n']} steps); "
+      f"end to end through the synchronous C-ABI call with pinned host buffers **{e2e['value'] / 1e6:.3f} M pairs/s** ({e2e['ms_per_step']:.3f} ms; "
+      f"{e2e['h2d_bytes_per_step'] / 1e6:.2f} MB up, {e2e['d2h_bytes_per_step'] / 1e6:.2f} MB down per step), the same step from a C++ caller "
+      f"(`tools/latency_probe`) {cpp.get('pairs_per_s', 0) / 1e6:.3f} M pairs/s ({cpp.get('step_us_median', 0):.0f} us); CPU port "
+      f"{t['cpu_baseline']['value']:.0f} pairs/s on {t['cpu_baseline']['cores']} threads (reference arm: {ref['value']:.0f})",
+      "* stage ms per step: " + ", ".join(f"{k} {v}" for k, v in rf["stage_ms_per_step"].items()),
+      f"* `knn2_hamming_tc_kernel`: {rf['launch_ms']:.3f} ms per launch, {rf['desc_pairs_per_s']:.3g} descriptor pairs/s = {rf['achieved']:.0f} int8 TOP/s = "
+      f"**{rf['frac']:.3f}** of nominal {rf['peak']:.0f}, {rf['measured_int8_issue_rate']['frac']:.3f} of the measured back-to-back issue rate "
+      f"({rf['measured_int8_issue_rate']['pops']} POP/s); {rf['traffic'] / 1e6:.2f} MB DRAM per launch (ncu)"]
+pr = [r["probe"] for r in probe.get("probe", []) + probe.get("probe_second_box", []) if "probe" in r]
+if pr:
+    L += ["* in-kernel counters (`tc_probe_r2.json`, `-DMVS_TC_PROBE` build): slowest CTA " + " / ".join(f"{p['issuer_clocks_max'] / 1e3:.0f} k clocks at "
+          f"{p['sm_mhz_during_kernel']:.0f} MHz" for p in pr) + " against 702 k tensor-pipe clocks (49 items x 14 tiles x 2 row blocks x 8 MMAs x 64): "
+          "0.905 of the issue rate in cycles on every box; the boxes of the pool differ in the clock they sustain under this kernel"]
+pa = t["parity"]
+L += [f"* parity block of the same run: {pa['cases']} cases, {pa['inlier_sets_differ']} inlier sets / {pa['E_differs_1e5']} E / {pa['points_differ_1e4']} point "
+      f"sets differ from the numpy + cv2.SVDecomp goldens, {pa['bit_identical_F_E_pose_points']} bit-identical, {pa['borderline_residuals']} residuals within "
+      f"1e-9·thr of the threshold; FAST solver: {pa['fast_solver']['inlier_sets_differ']} cases differ (pair 4-5)", "",
+      "## Extras of the same line", ""]
+h, s8, s8r, s8c, l2, w5, ed, la = (t[k] for k in ("ransac_h1024_fast", "s8k", "s8k_reference_solver", "s8k_cross_check", "l2_32k", "w512_strong",
+                                                    "e2e_distinct", "latency_us"))
+L += [f"* `ransac_h1024_fast` (round 1's headline configuration): {h['value'] / 1e6:.3f} M pairs/s, {h['ms_per_step']['median']:.3f} ms; "
+      f"{h['hyp_pt_evals_per_s'] / 1e12:.2f} T hypothesis·point evaluations/s, {h['hypotheses_per_s'] / 1e9:.2f} G hypotheses/s",
+      f"* `s8k` (64 x 8192 keypoints, H = 4096, Sampson): FAST {s8['value']:.0f} pairs/s ({s8['ms_per_step']['median']:.2f} ms; scoring "
+      f"{s8['hyp_pt_evals_per_s'] / 1e12:.2f} T evals/s = {s8['score_fp64_pipe_frac']:.2f} of the FP64 pipe); REFERENCE {s8r['value']:.0f} pairs/s; "
+      f"cross-check {s8c['value']:.0f} pairs/s",
+      f"* `l2_32k`: GEMM {l2['gemm_ms']:.3f} ms = {l2['gemm_tflops']:.0f} TFLOP/s ({l2['gemm_frac']:.2f} of bf16/2); call with pageable host buffers "
+      f"{l2['call_device_ms']:.2f} ms; call with resident descriptors {l2['resident']['call_device_ms']:.3f} ms = {l2['resident']['call_frac']:.2f} of the "
+      f"TF32 line; {l2['exact_fallback_queries']} exact fallbacks"]
+if w5:
+    L += [f"* `w512_strong` at N = 1: {w5['job_ms']:.1f} ms for {w5['pairs_total']} pairs through `mvs_pair_batch_sharded` ({w5['value'] / 1e3:.0f} k pairs/s)"]
+for nm, b in (("2", n2), ("8", n8)):
+    if b and b.get("w512_strong"):
+        w = b["w512_strong"]
+        L += [f"* N = {nm} (`bench_n{nm}_r2.json`): headline {b['value'] / 1e6:.2f} M pairs/s device-resident, {b['e2e']['value'] / 1e6:.2f} M end to end; W512 "
+              f"{w['job_ms']:.1f} ms ({w['value'] / 1e6:.2f} M pairs/s), per-rank kNN {w['knn_ms_per_rank']['max']:.1f} ms, gather + copy "
+              f"{w['gather_and_copy_ms_rank0']['median']:.2f} ms; sharded self-check {json.dumps(b.get('sharded_self_check', {}).get('w512', {}).get('rank1_records_equal_rank0_recomputation'))}"]
+L += [f"* `e2e_distinct`: {ed['value'] / 1e3:.0f} k pairs/s ({ed['ms_per_step']['median']:.2f} ms per 1024 pairs, {ed['h2d_bytes_per_step'] / 1e6:.1f} MB up, "
+      f"{ed['d2h_bytes_per_step'] / 1e6:.1f} MB down) = {ed['frac_of_device_resident']:.2f} of the device-resident rate; upload alone "
+      f"{ed['interface_floor']['h2d_ms']:.2f} ms at {ed['interface_floor']['h2d_gbs_measured']:.1f} GB/s",
+      "* `latency_us`, C++ caller (median, records only / with details): " + ", ".join(
+          f"{k} {v['records_only_call_us']:.0f} / {v['call_us']:.0f}" for k, v in la["cpp_caller"].items() if "call_us" in v) +
+      "; Python ctypes: " + ", ".join(f"{k} {v['median']:.0f}" for k, v in la["python_ctypes"].items())]
+ex, pn, ba = t.get("extraction"), t.get("pnp"), t.get("bundle_adjustment")
+if ex:
+    L += [f"* `extraction` (GPU ORB, bit-exact): {ex['value'] / 1e3:.0f} k frames/s device-resident ({ex['ms_per_step']:.2f} ms per 256 frames), "
+          f"{ex['e2e']['value'] / 1e3:.0f} k frames/s end to end, single frame {ex['single_frame_latency_us']:.0f} us"]
+if pn:
+    L += [f"* `pnp`: {pn['problems_per_s_device'] / 1e6:.2f} M problems/s device-resident (1024 x 500 points x 100 hypotheses), {pn['e2e_problems_per_s'] / 1e3:.0f} k end to end"]
+if ba:
+    L += [f"* `bundle_adjustment`: {ba['problems_per_s_device'] / 1e3:.0f} k two-frame problems/s device-resident (512 x 200 points), {ba['e2e_problems_per_s'] / 1e3:.0f} k end to end"]
+p = os.path.join(P, "README.md")
+s = open(p).read()
+head = s[:s.index("## Headline")]
+open(p, "w").write(head + "\n".join(L) + "\n")
+print("\n".join(L))
