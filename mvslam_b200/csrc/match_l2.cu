@@ -162,7 +162,8 @@ __global__ void l2_norms_kernel(const float *x, int n, int n_padded, int ld, int
     for (int off = 8; off > 0; off >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, off);
     unsigned m = (i < n) ? __float_as_uint(s) : 0u;
     m = __reduce_max_sync(0xFFFFFFFFu, m);
-    if ((threadIdx.x & 31) == 0 && m) atomicMax(max_bits, m);
+    // one atomic per warp on one word serialises (16 k of them took ~10 us of this kernel): ask first whether it can matter
+    if ((threadIdx.x & 31) == 0 && m > __ldcg(max_bits)) atomicMax(max_bits, m);
     if (sub != 0 || i >= n_padded) return;
     float4 *brow = reinterpret_cast<float4 *>(bias + (size_t)i * 8);
     brow[1] = make_float4(0.f, 0.f, 0.f, 0.f);
