@@ -485,6 +485,10 @@ def main():
         torch.cuda.synchronize()
         gather_ms = 0.0
         if world > 1:   # the single collective of the path: final gather of the fixed-size records over NCCL
+            # every rank has finished its K steps before the collective is timed: the host loops of the ranks drift apart by
+            # up to a few ms of wall clock over K steps, and without the barrier that drift (not device time of the path, which
+            # the per-step events measure) would be booked as gather time on rank 0
+            dist.barrier(); torch.cuda.synchronize()
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             g0.record(stream); final_gather(); g1.record(stream)
             torch.cuda.synchronize()
