@@ -156,14 +156,28 @@ __global__ void l2_norms_kernel(const float *x, int n, int n_padded, int ld, int
     // error band and the approximate score, never an exact distance)
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 4, sub = threadIdx.x & 15;
     float s = 0.f;
-    if (i < n)
-        for (int k = sub; k < dim; k += 16) { const float v = x[(size_t)i * ld + k]; s = fmaf(v, v, s); }
+    if (i < n) {      // rows are 16-byte aligned with a pitch of a multiple of 32 floats, zero beyond dim
+        const float4 *row = reinterpret_cast<const float4 *>(x + (size_t)i * ld);
+#pragma unroll 2
+        for (int k = sub; k < (ld >> 2); k += 16) {
+            const float4 v = __ldg(row + k);
+            s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
+        }
+    }
 #pragma unroll
     for (int off = 8; off > 0; off >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, off);
+    // maximum of the squared norms: one atomic per block, and only when it can matter (an atomic per warp on one word
+    // serialised: ~10 us of a 14 us kernel)
+    __shared__ unsigned int s_max[8];
     unsigned m = (i < n) ? __float_as_uint(s) : 0u;
     m = __reduce_max_sync(0xFFFFFFFFu, m);
-    // one atomic per warp on one word serialises (16 k of them took ~10 us of this kernel): ask first whether it can matter
-    if ((threadIdx.x & 31) == 0 && m > __ldcg(max_bits)) atomicMax(max_bits, m);
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned bm = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) bm = max(bm, s_max[w]);
+        if (bm > __ldcg(max_bits)) atomicMax(max_bits, bm);
+    }
     if (sub != 0 || i >= n_padded) return;
     float4 *brow = reinterpret_cast<float4 *>(bias + (size_t)i * 8);
     brow[1] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -351,10 +365,20 @@ l2_gemm_topk_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------ exact re-rank
+// exact squared distance: sequential fmaf over the dimension (the order is part of the result's definition).  Rows are 16-byte
+// aligned with a pitch of a multiple of 32 floats (zero padding beyond dim adds exact zeros), so they are fetched as float4 with
+// several loads in flight: the sum is a latency chain, the loads need not be.
 __device__ __forceinline__ float exact_d2(const float *__restrict__ q, const float *__restrict__ t, int dim)
 {
+    const float4 *q4 = reinterpret_cast<const float4 *>(q), *t4 = reinterpret_cast<const float4 *>(t);
     float s = 0.f;
-    for (int k = 0; k < dim; ++k) { const float e = q[k] - t[k]; s = fmaf(e, e, s); }
+    const int n4 = (dim + 3) >> 2;
+#pragma unroll 4
+    for (int k = 0; k < n4; ++k) {
+        const float4 a = __ldg(q4 + k), b = __ldg(t4 + k);
+        const float e0 = a.x - b.x, e1 = a.y - b.y, e2 = a.z - b.z, e3 = a.w - b.w;
+        s = fmaf(e0, e0, s); s = fmaf(e1, e1, s); s = fmaf(e2, e2, s); s = fmaf(e3, e3, s);
+    }
     return s;
 }
 
@@ -389,14 +413,28 @@ __global__ void l2_rerank_kernel(const float *__restrict__ Q, const float *__res
     const float qn = sqrtf(q2[q]);
     const float tmax = sqrtf(__uint_as_float(*tmax2_bits));
     const float twoE = 2.f * l2_half_band(qn, tmax);
-    bool overflow = false;
+    // The query's lists are one flat run of lists x KC slots; slot s belongs to list s / KC and is live below that list's count.
+    // Lane l holds the count of list l (lists <= 32), the slots are walked four per lane at a time with their loads issued
+    // together: the kernel is a chain of dependent memory round trips (counts -> scores -> indexes -> rows), so what matters
+    // is that each link is one round trip, not one per slot.
+    static_assert(KC == 64, "slot -> list mapping below assumes 64 slots per list");
+    const int nslots = lists * KC;
+    const float *cv = cand_val + (size_t)q * nslots;
+    const int32_t *ci = cand_idx + (size_t)q * nslots;
+    const int my_cnt = lane < lists ? cand_cnt[(size_t)q * lists + lane] : 0;
+    const bool overflow = __any_sync(0xFFFFFFFFu, my_cnt > KC);
     float a1 = CUDART_INF_F, a2 = CUDART_INF_F;
-    for (int l = 0; l < lists; ++l) {
-        const int c = cand_cnt[(size_t)q * lists + l];
-        overflow |= c > KC;
-        for (int e = lane; e < min(c, KC); e += 32) {
-            const float av = cand_val[((size_t)q * lists + l) * KC + e];
-            if (av < a1) { a2 = a1; a1 = av; } else if (av < a2) a2 = av;
+    for (int base = 0; base < nslots; base += 128) {
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int sl = base + 32 * j + lane;
+            const int c = min(__shfl_sync(0xFFFFFFFFu, my_cnt, (base >> 6) + (j >> 1)), KC);
+            v[j] = (sl < nslots && (sl & (KC - 1)) < c) ? __ldg(cv + sl) : CUDART_INF_F;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (v[j] < a1) { a2 = a1; a1 = v[j]; } else if (v[j] < a2) a2 = v[j];
         }
     }
     // warp-wide second smallest approximate score
@@ -409,13 +447,22 @@ __global__ void l2_rerank_kernel(const float *__restrict__ Q, const float *__res
     for (int off = 16; off > 0; off >>= 1) m2 = fminf(m2, __shfl_xor_sync(0xFFFFFFFFu, m2, off));
     const float keep = m2 + twoE;
     unsigned long long b1 = ~0ull, b2 = ~0ull;
-    for (int l = 0; l < lists; ++l) {
-        const int c = min(cand_cnt[(size_t)q * lists + l], KC);
-        for (int e = lane; e < c; e += 32) {
-            const size_t o = ((size_t)q * lists + l) * KC + e;
-            if (!(cand_val[o] <= keep)) continue;
-            const int id = cand_idx[o];
-            const unsigned long long k = key_of(exact_d2(Q + (size_t)q * ldq, T + (size_t)id * ldt, dim), id);
+    const float *qrow = Q + (size_t)q * ldq;
+    for (int base = 0; base < nslots; base += 128) {
+        float v[4];
+        int id[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int sl = base + 32 * j + lane;
+            const int c = min(__shfl_sync(0xFFFFFFFFu, my_cnt, (base >> 6) + (j >> 1)), KC);
+            const bool live = sl < nslots && (sl & (KC - 1)) < c;
+            v[j] = live ? __ldg(cv + sl) : CUDART_INF_F;       // cached by the first walk
+            id[j] = live ? __ldg(ci + sl) : 0;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (!(v[j] <= keep)) continue;
+            const unsigned long long k = key_of(exact_d2(qrow, T + (size_t)id[j] * ldt, dim), id[j]);
             if (k < b1) { b2 = b1; b1 = k; } else if (k < b2) b2 = k;
         }
     }
