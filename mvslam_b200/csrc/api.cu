@@ -653,8 +653,8 @@ static int match_two_sets(mvs_ctx *ctx, const uint8_t *query, int nq, const uint
     CK(cudaMemcpyAsync(ctx->t_fcnt.p, cnt, sizeof(cnt), cudaMemcpyHostToDevice, ctx->stream));
     const bool cross = mp && mp->cross_check;
     const bool tc = tc_eligible(ctx, nq, nt, cross, (size_t)nq + nt);
-    const int splits = tc ? tc_splits() : choose_splits((nq + 255) / 256, 1, nt);
-    const int rsplits = cross ? (tc ? tc_splits() : choose_splits((nt + 255) / 256, 1, nq)) : 0;
+    const int splits = tc ? tc_splits(nq, nt, 1) : choose_splits((nq + 255) / 256, 1, nt);
+    const int rsplits = cross ? (tc ? tc_splits(nt, nq, 1) : choose_splits((nt + 255) / 256, 1, nq)) : 0;
     CK(ctx->d_partial.ensure((size_t)splits * nq * sizeof(uint2)));
     if (cross) CK(ctx->d_rev.ensure((size_t)rsplits * nt * sizeof(uint2)));
     CK(ctx->d_matches.ensure((size_t)nq * sizeof(mvs_match)));
@@ -670,9 +670,10 @@ static int match_two_sets(mvs_ctx *ctx, const uint8_t *query, int nq, const uint
         launch_expand_desc(ctx->t_desc.as<uint4>(), 0, (size_t)nq + nt, ctx->t_desc8.p, ctx->stream);
         TcKnnArgs ta{};
         ta.frame_off = ka.frame_off; ta.frame_cnt = ka.frame_cnt; ta.pairs = nullptr; ta.partial = ka.partial; ta.q_stride = nq; ta.reverse = 0;
+        ta.t_splits = tc_train_splits(nq, nt, 1);
         CK(launch_knn2_hamming_tc(ctx->t_desc8.p, (size_t)nq + nt, ta, nq, 1, ctx->stream));
         if (cross) {
-            ta.partial = ctx->d_rev.as<uint2>(); ta.q_stride = nt; ta.reverse = 1;
+            ta.partial = ctx->d_rev.as<uint2>(); ta.q_stride = nt; ta.reverse = 1; ta.t_splits = tc_train_splits(nt, nq, 1);
             CK(launch_knn2_hamming_tc(ctx->t_desc8.p, (size_t)nq + nt, ta, nt, 1, ctx->stream));
         }
     } else {
@@ -1081,8 +1082,8 @@ static int pair_batch_chunk(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, con
     const bool cross = mparams && mparams->cross_check;
     const size_t table_rows = (size_t)ctx->h_off[nf - 1] + (size_t)ctx->h_cnt[nf - 1];
     const bool tc = tc_eligible(ctx, max_nq, max_nt, cross, table_rows);
-    const int splits = tc ? tc_splits() : choose_splits((max_nq + 255) / 256, n_pairs, max_nt);
-    const int rsplits = cross ? (tc ? tc_splits() : choose_splits((max_nt + 255) / 256, n_pairs, max_nq)) : 0;
+    const int splits = tc ? tc_splits(max_nq, max_nt, n_pairs) : choose_splits((max_nq + 255) / 256, n_pairs, max_nt);
+    const int rsplits = cross ? (tc ? tc_splits(max_nt, max_nq, n_pairs) : choose_splits((max_nt + 255) / 256, n_pairs, max_nq)) : 0;
     CK(ctx->d_pairs.ensure((size_t)n_pairs * sizeof(int2)));
     CK(ctx->d_partial.ensure((size_t)n_pairs * splits * qs * sizeof(uint2)));
     if (cross) CK(ctx->d_rev.ensure((size_t)n_pairs * rsplits * max_nt * sizeof(uint2)));
@@ -1101,9 +1102,10 @@ static int pair_batch_chunk(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, con
         if ((st = sync_desc8(ctx, table_rows)) != MVS_OK) return st;
         TcKnnArgs ta{};
         ta.frame_off = ka.frame_off; ta.frame_cnt = ka.frame_cnt; ta.pairs = ka.pairs; ta.partial = ka.partial; ta.q_stride = qs; ta.reverse = 0;
+        ta.t_splits = tc_train_splits(max_nq, max_nt, n_pairs);
         CK(launch_knn2_hamming_tc(ctx->d_desc8.p, table_rows, ta, max_nq, n_pairs, ctx->stream));
         if (cross) {
-            ta.partial = ctx->d_rev.as<uint2>(); ta.q_stride = max_nt; ta.reverse = 1;
+            ta.partial = ctx->d_rev.as<uint2>(); ta.q_stride = max_nt; ta.reverse = 1; ta.t_splits = tc_train_splits(max_nt, max_nq, n_pairs);
             CK(launch_knn2_hamming_tc(ctx->d_desc8.p, table_rows, ta, max_nt, n_pairs, ctx->stream));
         }
     } else {

@@ -25,10 +25,11 @@ struct TcKnnArgs {
     const int32_t *frame_off;
     const int32_t *frame_cnt;
     const int2 *pairs;         // as KnnArgs
-    uint2 *partial;            // [pairs][tc_splits()][q_stride]: the column halves of the train tiles are the "splits"
+    uint2 *partial;            // [pairs][tc_splits(shape)][q_stride]: column halves of the train tiles x train splits
     int q_stride;
     int reverse;
-    int q_tiles, n_pairs;      // filled by the launcher: items = q_tiles x n_pairs
+    int t_splits;              // train-dimension splits (tc_train_splits of the launch shape; partial holds 2 x t_splits entries per query)
+    int q_tiles, n_pairs;      // filled by the launcher: items = q_tiles x t_splits x n_pairs
     int one;                   // 1 (opaque to the compiler, see the epilogue)
 };
 
@@ -124,7 +125,8 @@ struct FinishArgs {
 
 void launch_knn2_hamming(const KnnArgs &a, int max_nq, int splits, int n_pairs, cudaStream_t s);
 int tc_max_train();            // largest train set of the tensor-core matcher
-int tc_splits();               // partial top-2 pairs per query it writes
+int tc_train_splits(int max_nq, int max_nt, int n_pairs);   // train-dimension splits for a launch of this shape (1 for large batches)
+int tc_splits(int max_nq, int max_nt, int n_pairs);         // partial top-2 pairs per query the kernel writes: 2 x tc_train_splits
 void launch_expand_desc(const uint4 *desc, size_t row_begin, size_t n_rows, void *desc8, cudaStream_t s);
 cudaError_t launch_knn2_hamming_tc(const void *desc8, size_t total_rows, const TcKnnArgs &a, int max_nq, int n_pairs, cudaStream_t s);
 int finalize_sort_capacity(int max_nq);

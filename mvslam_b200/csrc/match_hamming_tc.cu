@@ -50,7 +50,7 @@ constexpr int A_WARP = MMA_WARP_B + 1;     // query row-block producer (ring of 
 constexpr int TC_THREADS = (A_WARP + 1) * 32;
 constexpr int NACC = 2 * RB;         // TMEM accumulator buffers: double-buffered per row block
 constexpr uint32_t TMEM_COLS = NACC * BN;
-constexpr int TC_SPLITS = 2;         // partial results per query: one per column half
+constexpr int TC_SPLITS = 2;         // partial results per query and train split: one per column half
 constexpr int TC_MAX_TRAIN = (int)kIdxMask;  // the thread's running key is already the export format (hamming << 22 | trainIdx)
 
 // ------------------------------------------------------------------------------------------ PTX helpers
@@ -179,7 +179,7 @@ __device__ __forceinline__ uint32_t widen_key(uint32_t k16, uint32_t tile_base /
 // traffic per descriptor pair is 1 byte instead of 2 (the L2 slices cap at ~6300 B/clk chip-wide, which a 128-row
 // query tile saturates at half the tensor rate).  The three roles keep running counters, so the TMA ring (STAGES train
 // tiles in flight) and the four TMEM accumulators (2 row blocks x 2 steps) stay full across item boundaries.
-struct ItemInfo { int pair, q0, nq, nt, row_q, row_t, n_tiles, n_rb; };
+struct ItemInfo { int pair, q0, nq, nt, row_q, row_t, n_tiles, n_rb, tile0, ts; };
 
 #ifdef MVS_TC_PROBE   // experiment build only (tools/knn_probe.py): per-CTA clock and wall-time counters of the last launch
 __device__ unsigned long long g_tc_probe[160][10];
@@ -194,8 +194,14 @@ __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; a
 __device__ __forceinline__ bool load_item(const TcKnnArgs &a, int item, ItemInfo &it, int n_items)
 {
     if (item >= n_items) return false;
-    it.pair = item / a.q_tiles;
-    it.q0 = (item - it.pair * a.q_tiles) * (RB * BM);
+    // item = (pair, query tile, train split): launches with fewer items than SMs cut the train dimension as well (a.t_splits,
+    // chosen by the launcher), so that one VO pair or one large pair of descriptor sets still spreads over the chip
+    const int per_pair = a.q_tiles * a.t_splits;
+    it.pair = item / per_pair;
+    const int rem = item - it.pair * per_pair;
+    const int qt = rem / a.t_splits;
+    it.ts = rem - qt * a.t_splits;
+    it.q0 = qt * (RB * BM);
     int fq, ft;
     if (a.pairs) {  // query = pair frame (second), train = base frame (first): visual-feature.cpp:59-60
         const int2 pr = a.pairs[it.pair];
@@ -204,7 +210,9 @@ __device__ __forceinline__ bool load_item(const TcKnnArgs &a, int item, ItemInfo
     } else { fq = a.reverse ? 0 : 1; ft = a.reverse ? 1 : 0; }
     it.nq = a.frame_cnt[fq]; it.nt = a.frame_cnt[ft];
     it.row_q = a.frame_off[fq] + it.q0; it.row_t = a.frame_off[ft];
-    it.n_tiles = (it.nt + BN - 1) / BN;
+    const int tiles_total = (it.nt + BN - 1) / BN, tiles_per = (tiles_total + a.t_splits - 1) / a.t_splits;
+    it.tile0 = it.ts * tiles_per;                           // a trailing split of a short frame may own no tile: it exports "none"
+    it.n_tiles = max(0, min(tiles_per, tiles_total - it.tile0));
     it.n_rb = (it.q0 + BM < it.nq) ? 2 : 1;                 // the second row block may be empty (every role skips it)
     return it.q0 < it.nq;                                   // every role skips the same items
 }
@@ -238,7 +246,7 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
              *tempty = tfull + NACC;
     uint32_t *tmem_slot = (uint32_t *)(tempty + NACC);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_items = a.q_tiles * a.n_pairs;
+    const int n_items = a.q_tiles * a.t_splits * a.n_pairs;
     pdl_launch_dependents();   // K2's blocks may take the SMs this grid leaves free (small batches); they wait for this grid's end
 #ifdef MVS_TC_PROBE
     long long w_a = 0, w_full = 0, w_acc = 0;
@@ -282,7 +290,7 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
                     mbar_wait(empty + s, ((tile_no / STAGES) & 1) ^ 1);
                     mbar_expect_tx(full + s, KSLABS * BN * SLAB);
                     for (int ks = 0; ks < KSLABS; ++ks)
-                        tma_load_2d(&map, full + s, sB + (s * KSLABS + ks) * BN * SLAB, ks * SLAB, it.row_t + i * BN);
+                        tma_load_2d(&map, full + s, sB + (s * KSLABS + ks) * BN * SLAB, ks * SLAB, it.row_t + (it.tile0 + i) * BN);
                 }
             }
         }
@@ -359,7 +367,7 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
             uint32_t g1 = kKeyNone, g2 = kKeyNone;
             for (int i = 0; i < it.n_tiles; ++i, ++use_no) {
                 const uint32_t acc = (use_no & 1) * RB + rb;
-                const int col0 = i * BN + half * (BN / 2);
+                const int col0 = (it.tile0 + i) * BN + half * (BN / 2);
                 { PROBE_T0(); mbar_wait(tfull + acc, (use_no >> 1) & 1); PROBE_ADD(w_acc); }
                 tcgen05_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
@@ -405,7 +413,7 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
             if (q < it.nq) {
                 const uint32_t x1 = (g1 >> kIdxBits) > 256u ? kKeyNone : g1;
                 const uint32_t x2 = (g2 >> kIdxBits) > 256u ? kKeyNone : g2;
-                a.partial[((size_t)it.pair * TC_SPLITS + half) * a.q_stride + q] = make_uint2(x1, x2);
+                a.partial[((size_t)it.pair * (TC_SPLITS * a.t_splits) + it.ts * TC_SPLITS + half) * a.q_stride + q] = make_uint2(x1, x2);
             }
         }
     }
@@ -475,7 +483,8 @@ cudaError_t launch_tc(const CUtensorMap &map, TcKnnArgs a, int max_nq, int n_pai
     a.q_tiles = (max_nq + RB * BM - 1) / (RB * BM);
     a.n_pairs = n_pairs;
     a.one = 1;
-    const long items = (long)a.q_tiles * n_pairs;
+    if (a.t_splits < 1) a.t_splits = 1;
+    const long items = (long)a.q_tiles * a.t_splits * n_pairs;
     kern<<<(unsigned)std::min<long>(items, n_sm), TC_THREADS, smem, s>>>(map, a);
     return cudaGetLastError();
 }
@@ -491,7 +500,19 @@ extern "C" void mvs_debug_tc_probe_dump(unsigned long long *out /* [160][10] */)
 #endif
 
 int tc_max_train() { return TC_MAX_TRAIN; }
-int tc_splits() { return TC_SPLITS; }
+// Partial top-2 pairs per query the kernel writes for a launch of this shape: two column halves x the train splits.  The train
+// dimension is cut only when the (pair, query tile) items would leave most SMs idle -- a single VO pair is 7 items -- and never
+// finer than four train tiles per split (each split pays the pipeline fill and one more partial for K2 to merge).
+int tc_train_splits(int max_nq, int max_nt, int n_pairs)
+{
+    int dev = 0, n_sm = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) { int n = 0; if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) n_sm = n; }
+    const long items = (long)((max_nq + RB * BM - 1) / (RB * BM)) * n_pairs;
+    const int tiles = (max_nt + BN - 1) / BN;
+    if (items * 2 > n_sm || tiles < 8) return 1;
+    return (int)std::max<long>(1, std::min<long>(std::min<long>(n_sm / items, tiles / 4), 16));
+}
+int tc_splits(int max_nq, int max_nt, int n_pairs) { return TC_SPLITS * tc_train_splits(max_nq, max_nt, n_pairs); }
 
 void launch_expand_desc(const uint4 *desc, size_t row_begin, size_t n_rows, void *desc8, cudaStream_t s)
 {
