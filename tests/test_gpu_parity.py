@@ -676,6 +676,31 @@ def test_large_synchronous_batch_trims_detail_copies(ctx, tsukuba):
     assert not dbig["matches"][:, most:]["distance"].any()         # slots beyond the fullest pair were not copied (host zeros)
 
 
+@pytest.mark.parametrize("cross", [False, True])
+def test_small_batches_split_the_train_dimension(ctx, cross):
+    """Launches with fewer (pair, query tile) items than SMs also cut the train frames into splits (match_hamming_tc.cu
+    tc_train_splits): ragged frames -- the trailing splits of a short base frame own no tile and must export "no neighbour" --
+    and every small batch size give the oracle's matches bit for bit."""
+    rng = np.random.default_rng(11)
+    sizes = [1764, 130, 900, 2, 1300, 257]
+    descs = [rng.integers(0, 256, (n, 32), dtype=np.uint8) for n in sizes]
+    for d in descs[1:]:                         # planted near-duplicates, so that matches survive the ratio test
+        k = min(len(d), 100)
+        d[:k] = descs[0][:k] ^ (rng.integers(0, 256, (k, 32), dtype=np.uint8) & rng.integers(0, 256, (k, 32), dtype=np.uint8)
+                                & rng.integers(0, 256, (k, 32), dtype=np.uint8) & rng.integers(0, 256, (k, 32), dtype=np.uint8))
+    kps = [rng.uniform(0, 700, (n, 2)).astype(np.float32) for n in sizes]
+    ctx.frames_upload(descs, kps)
+    all_pairs = [(a, b) for a in range(6) for b in range(6) if a != b]
+    for n_pairs in (1, 2, 5, 9, 30):
+        pairs = all_pairs[:n_pairs] if n_pairs != 2 else [(1, 0), (0, 3)]
+        res, det = ctx.pair_batch(pairs, synth.K_S8K, max_dist=-1.0, cross_check=cross, H=4, seed=1)
+        for i, (a, b) in enumerate(pairs):
+            o = orc.match_hamming(descs[b], descs[a], max_dist=-1.0, cross_check=cross) if len(descs[a]) >= 2 else np.zeros(0, mvs.MATCH_DTYPE)
+            m = int(res[i]["n_matches"])
+            assert m == len(o), (n_pairs, a, b, m, len(o))
+            assert np.array_equal(det["matches"][i][:m], as_mvs(o)), (n_pairs, a, b)
+
+
 @pytest.mark.parametrize("enqueue", [False, True])
 @pytest.mark.parametrize("cap", [2048, 40])
 def test_pinned_detail_outputs_are_written_by_the_device(ctx, tsukuba, enqueue, cap):
