@@ -34,6 +34,12 @@ if pr:
     L += ["* in-kernel counters (`tc_probe_r2.json`, `-DMVS_TC_PROBE` build): slowest CTA " + " / ".join(f"{p['issuer_clocks_max'] / 1e3:.0f} k clocks at "
           f"{p['sm_mhz_during_kernel']:.0f} MHz" for p in pr) + " against 702 k tensor-pipe clocks (49 items x 14 tiles x 2 row blocks x 8 MMAs x 64): "
           "0.905 of the issue rate in cycles on every box; the boxes of the pool differ in the clock they sustain under this kernel"]
+fast = line("bench_tsukuba_r2_box1899.json")
+if fast:
+    L += [f"* the pool's boxes differ: `bench_tsukuba_r2_box1899.json` is the same command (one build earlier: before the train-split / re-rank / "
+          f"config changes, which do not touch this workload's kernels) on a box that sustains 1899 MHz under the matcher: "
+          f"**{fast['value'] / 1e6:.3f} M pairs/s** device-resident ({fast['ms_per_step']:.3f} ms), {fast['e2e']['value'] / 1e6:.3f} M end to end, "
+          f"kNN {fast['roofline']['launch_ms']:.3f} ms = {fast['roofline']['frac']:.3f} of nominal, L2 GEMM {fast['l2_32k']['gemm_ms']:.3f} ms"]
 pa = t["parity"]
 L += [f"* parity block of the same run: {pa['cases']} cases, {pa['inlier_sets_differ']} inlier sets / {pa['E_differs_1e5']} E / {pa['points_differ_1e4']} point "
       f"sets differ from the numpy + cv2.SVDecomp goldens, {pa['bit_identical_F_E_pose_points']} bit-identical, {pa['borderline_residuals']} residuals within "
