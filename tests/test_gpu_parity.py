@@ -676,6 +676,34 @@ def test_large_synchronous_batch_trims_detail_copies(ctx, tsukuba):
     assert not dbig["matches"][:, most:]["distance"].any()         # slots beyond the fullest pair were not copied (host zeros)
 
 
+def test_frames_upload_from_pinned_memory_equals_pageable(ctx, tsukuba):
+    """Frames in pinned host memory are gathered by one kernel (api.cu gather_frames_kernel) instead of two copies per frame;
+    an empty frame, a frame at an address the kernel's 16-byte loads cannot take (falls back to the copies) and more frames
+    than one launch carries give the same table as the pageable upload."""
+    torch = pytest.importorskip("torch")
+    base_d = [tsukuba[f"desc{i}"] for i in range(1, 6)]; base_k = [tsukuba[f"kp{i}"] for i in range(1, 6)]
+    descs = base_d + [base_d[0][:0]] + [base_d[i % 5][: 40 + i] for i in range(70)]
+    kps = base_k + [base_k[0][:0]] + [base_k[i % 5][: 40 + i] for i in range(70)]
+    pairs = [(0, 1), (1, 2), (3, 4), (6, 0), (75, 1), (2, 70), (5, 1)]
+    kw = dict(max_dist=30.0, H=8, seed=3, solver="fast")
+    ctx.frames_upload(descs, kps)
+    ref, dref = ctx.pair_batch(pairs, tsukuba["K"], **kw)
+    pd = [torch.from_numpy(np.ascontiguousarray(d)).pin_memory() for d in descs]
+    pk = [torch.from_numpy(np.ascontiguousarray(k)).pin_memory() for k in kps]
+    ctx.frames_upload([t.numpy() for t in pd], [t.numpy() for t in pk])
+    res, det = ctx.pair_batch(pairs, tsukuba["K"], **kw)
+    assert res.tobytes() == ref.tobytes()
+    for i in range(len(pairs)):
+        m = int(ref["n_matches"][i])
+        assert np.array_equal(det["matches"][i][:m], dref["matches"][i][:m])
+    # a descriptor block that starts 4 bytes into a pinned buffer: not 16-byte aligned, so this upload takes the copy path
+    raw = torch.zeros(descs[0].size + 4, dtype=torch.uint8).pin_memory()
+    odd = raw.numpy()[4:].reshape(descs[0].shape); odd[:] = descs[0]
+    ctx.frames_upload([odd] + [t.numpy() for t in pd[1:]], [t.numpy() for t in pk])
+    res2, _ = ctx.pair_batch(pairs, tsukuba["K"], **kw)
+    assert res2.tobytes() == ref.tobytes()
+
+
 @pytest.mark.parametrize("cross", [False, True])
 def test_small_batches_split_the_train_dimension(ctx, cross):
     """Launches with fewer (pair, query tile) items than SMs also cut the train frames into splits (match_hamming_tc.cu
