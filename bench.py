@@ -935,7 +935,11 @@ def e2e_distinct_block(mvs, torch, local, flush, n_pairs=1024, chunk=256, n_ctx=
     mat_t = torch.empty(n_pairs * cap * 12, dtype=torch.uint8).pin_memory(); msk_t = torch.empty(n_pairs * cap, dtype=torch.uint8).pin_memory()
     pts_t = torch.empty(n_pairs * cap * 3, dtype=torch.float64).pin_memory(); idx_t = torch.empty(n_pairs * cap, dtype=torch.int64).pin_memory()
     kw = dict(max_dist=params["max_dist"], H=params["H"], seed=0, mode=params["mode"], solver="fast")
-    chunks = [(c0, min(n_pairs, c0 + chunk)) for c0 in range(0, n_pairs, chunk)]
+    if isinstance(chunk, (list, tuple)):      # explicit chunk sizes (tools/e2e_distinct_probe.py)
+        edges = np.concatenate([[0], np.cumsum(chunk)]); assert edges[-1] == n_pairs
+        chunks = [(int(a), int(b)) for a, b in zip(edges[:-1], edges[1:])]
+    else:
+        chunks = [(c0, min(n_pairs, c0 + chunk)) for c0 in range(0, n_pairs, chunk)]
 
     def run():
         for i, (c0, c1) in enumerate(chunks):
