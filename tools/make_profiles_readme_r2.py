@@ -15,7 +15,7 @@ def line(name):
     return rows[-1] if rows else None
 
 
-t, ref, n2, n8 = line("bench_tsukuba_r2.json"), line("bench_reference_r2.json"), line("bench_n2_r2.json"), line("bench_n8_r2.json")
+t, ref, n2, n4, n8 = (line(n) for n in ("bench_tsukuba_r2.json", "bench_reference_r2.json", "bench_n2_r2.json", "bench_n4_r2.json", "bench_n8_r2.json"))
 probe = json.load(open(os.path.join(P, "tc_probe_r2.json")))
 rf, e2e, st = t["roofline"], t["e2e"], t["step_ms_rank0"]
 L = ["## Headline (BASELINE config 2 as the reference runs it: 1024 Tsukuba VO pairs, max_dist 10, H = 1, REFERENCE solver)", ""]
@@ -57,7 +57,7 @@ L += [f"* `ransac_h1024_fast` (round 1's headline configuration): {h['value'] / 
       f"TF32 line; {l2['exact_fallback_queries']} exact fallbacks"]
 if w5:
     L += [f"* `w512_strong` at N = 1: {w5['job_ms']:.1f} ms for {w5['pairs_total']} pairs through `mvs_pair_batch_sharded` ({w5['value'] / 1e3:.0f} k pairs/s)"]
-for nm, b in (("2", n2), ("8", n8)):
+for nm, b in (("2", n2), ("4", n4), ("8", n8)):
     if b and b.get("w512_strong"):
         w = b["w512_strong"]
         L += [f"* N = {nm} (`bench_n{nm}_r2.json`): headline {b['value'] / 1e6:.2f} M pairs/s device-resident, {b['e2e']['value'] / 1e6:.2f} M end to end; W512 "
