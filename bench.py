@@ -891,14 +891,25 @@ def l2_block(ctx, mvs, peaks_m):
         ctx.knn2_l2_ptr(dq.data_ptr(), n, dt.data_ptr(), n, 64, di.data_ptr(), dd.data_ptr())
         res_runs.append(ctx.l2_stats())
     rbest = min(res_runs[1:], key=lambda s: s["total_us"])
+    # and with pinned host buffers on both sides (asynchronous copies at the interface rate instead of the pageable staging)
+    pq, pt = torch.from_numpy(q).pin_memory(), torch.from_numpy(t).pin_memory()
+    pi = torch.empty((n, 2), dtype=torch.int32).pin_memory(); pdist = torch.empty((n, 2), dtype=torch.float32).pin_memory()
+    pin_runs = []
+    for _ in range(4):
+        ctx.knn2_l2_ptr(pq.data_ptr(), n, pt.data_ptr(), n, 64, pi.data_ptr(), pdist.data_ptr())
+        pin_runs.append(ctx.l2_stats())
+    pbest = min(pin_runs[1:], key=lambda s: s["total_us"])
     idx_h, _ = ctx.knn2_l2(q, t)
     same = bool(np.array_equal(di.cpu().numpy(), idx_h))
+    same_p = bool(np.array_equal(pi.numpy(), idx_h))
     flops = 2.0 * n * n * 64
     tf32_peak = peaks_m["bf16_tflops"] / 2.0
     return dict(n=n, dim=64, gemm_ms=best["gemm_us"] / 1e3, call_device_ms=best["total_us"] / 1e3, call_wall_ms=best["wall_ms"],
                 gemm_tflops=flops / (best["gemm_us"] * 1e-6) / 1e12, call_tflops=flops / (best["total_us"] * 1e-6) / 1e12,
                 peak_tflops=tf32_peak, peak_source=f"{peaks_m['source']}: bf16 / 2 (TF32)", gemm_frac=flops / (best["gemm_us"] * 1e-6) / 1e12 / tf32_peak,
                 call_frac=flops / (best["total_us"] * 1e-6) / 1e12 / tf32_peak, exact_fallback_queries=best["fallback_fwd"],
+                pinned_host=dict(call_device_ms=pbest["total_us"] / 1e3, same_indices_as_pageable_call=same_p,
+                                 note="descriptor sets and outputs in pinned host memory: 16.8 MB up, 0.5 MB down at the interface rate"),
                 resident=dict(call_device_ms=rbest["total_us"] / 1e3, call_tflops=flops / (rbest["total_us"] * 1e-6) / 1e12,
                               call_frac=flops / (rbest["total_us"] * 1e-6) / 1e12 / tf32_peak, same_indices_as_host_call=same,
                               note="descriptors and outputs resident in HBM (device pointers through the same entry point): norms + GEMM + "
