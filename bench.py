@@ -675,9 +675,10 @@ def main():
                                                       note="tools/ubench_umma.cu on this pool: the same M=N=128, K=32 SS-mode instruction "
                                                            "stream issued back to back with no epilogue (profiles/ubench_umma_r2.json)"),
                         clock_note="in-kernel clock64 / %globaltimer counters (profiles/tc_probe_r2.json, -DMVS_TC_PROBE build): the SMs run "
-                                   "this kernel at 1782 MHz (nvidia-smi keeps showing the 1965 MHz maximum; the back-to-back UMMA "
-                                   "micro-benchmark runs at 1887 MHz), and the slowest CTA takes 776 k clocks for 49 items x 14336 "
-                                   "tensor-pipe clocks = 702 k: 0.905 of the tensor issue rate in cycles",
+                                   "this kernel at 1.78 GHz on some boxes of the pool and 1.90 GHz on others (nvidia-smi keeps showing the "
+                                   "1965 MHz maximum; the back-to-back UMMA micro-benchmark runs at 1.89 GHz), and on every box the slowest CTA "
+                                   "takes 776 k clocks for 49 items x 14336 tensor-pipe clocks = 702 k: 0.905 of the tensor issue rate in "
+                                   "cycles; launch_ms and frac move with the box's clock (0.45 ms / 0.81 ... 0.41 ms / 0.88)",
                         launch_ms=launch_s * 1e3, desc_pairs_per_launch=desc_pairs, desc_pairs_per_s=pair_rate,
                         hbm=hbm, traffic=traffic, stage_share=stage_share,
                         stage_ms_per_step={s: round(prof[s][0] / args.steps, 4) for s in mvs.STAGES[:7]})
@@ -690,9 +691,10 @@ def main():
                         unit="G algorithmic popc32/s (8 per 256-bit descriptor pair, SURVEY 8d)", frac=pair_rate / pair_peak,
                         peak_source="measured pipe rates (tools/ubench) / per-pair SASS mix 5 POPC + 15 LOP3 + 3 VIMNMX",
                         clock_note="in-kernel clock64 / %globaltimer counters (profiles/tc_probe_r2.json, -DMVS_TC_PROBE build): the SMs run "
-                                   "this kernel at 1782 MHz (nvidia-smi keeps showing the 1965 MHz maximum; the back-to-back UMMA "
-                                   "micro-benchmark runs at 1887 MHz), and the slowest CTA takes 776 k clocks for 49 items x 14336 "
-                                   "tensor-pipe clocks = 702 k: 0.905 of the tensor issue rate in cycles",
+                                   "this kernel at 1.78 GHz on some boxes of the pool and 1.90 GHz on others (nvidia-smi keeps showing the "
+                                   "1965 MHz maximum; the back-to-back UMMA micro-benchmark runs at 1.89 GHz), and on every box the slowest CTA "
+                                   "takes 776 k clocks for 49 items x 14336 tensor-pipe clocks = 702 k: 0.905 of the tensor issue rate in "
+                                   "cycles; launch_ms and frac move with the box's clock (0.45 ms / 0.81 ... 0.41 ms / 0.88)",
                         launch_ms=launch_s * 1e3, desc_pairs_per_launch=desc_pairs, desc_pairs_per_s=pair_rate,
                         hbm=hbm, traffic=traffic, stage_share=stage_share,
                         stage_ms_per_step={s: round(prof[s][0] / args.steps, 4) for s in mvs.STAGES[:7]})
