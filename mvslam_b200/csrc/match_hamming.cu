@@ -168,7 +168,10 @@ __device__ __forceinline__ uint32_t refine_second_warp(const uint4 *desc, bool w
     return second;
 }
 
-__global__ void __launch_bounds__(FIN_THREADS, 2)   // 32 registers: two CTAs (pairs) per SM
+// FIN_T threads per CTA (pair): 1024 (two CTAs per SM) for long frames; 512 (four per SM) for VO-sized ones, where the kernel is a
+// chain of barriers and dependent loads per pair and more resident pairs hide it better.  32 registers either way.
+template <int FIN_T>
+__global__ void __launch_bounds__(FIN_T, 2048 / FIN_T)
 match_finalize_kernel(FinalizeArgs a)
 {
     pdl_wait();
@@ -184,7 +187,7 @@ match_finalize_kernel(FinalizeArgs a)
     if (threadIdx.x == 0) s_count = 0;
     __syncthreads();
 
-    for (int q0 = 0; q0 < nq; q0 += FIN_THREADS) {    // warp-uniform trip count (refine_second_warp shuffles)
+    for (int q0 = 0; q0 < nq; q0 += FIN_T) {    // warp-uniform trip count (refine_second_warp shuffles)
         const int q = q0 + threadIdx.x;
         const bool valid = q < nq;
         uint2 b = valid ? merge_partials(part, a.splits, a.q_stride, q) : make_uint2(kKeyNone, kKeyNone);
@@ -219,7 +222,7 @@ match_finalize_kernel(FinalizeArgs a)
     }
     __syncthreads();
     const int m = s_count;
-    if (m <= FIN_THREADS / 4) {
+    if (m <= FIN_T / 4) {
         // few survivors (the VO threshold leaves ~100): rank sort, four lanes per key, two barriers instead of the
         // log^2 of a bitonic network.  Keys are distinct (they end in the query index).
         const int i = threadIdx.x >> 2, part = threadIdx.x & 3;
@@ -237,11 +240,11 @@ match_finalize_kernel(FinalizeArgs a)
     } else {
     int n2 = 1;
     while (n2 < m) n2 <<= 1;
-    for (int i = m + threadIdx.x; i < n2; i += FIN_THREADS) keys[i] = kKeyNone;
+    for (int i = m + threadIdx.x; i < n2; i += FIN_T) keys[i] = kKeyNone;
     __syncthreads();
     for (int k = 2; k <= n2; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < n2; i += FIN_THREADS) {
+            for (int i = threadIdx.x; i < n2; i += FIN_T) {
                 const int l = i ^ j;
                 if (l > i) {
                     const uint32_t x = keys[i], y = keys[l];
@@ -257,7 +260,7 @@ match_finalize_kernel(FinalizeArgs a)
     double *pts = a.points ? a.points + (size_t)pair * a.q_stride * 6 : nullptr;
     const float2 *kpq = a.kp ? a.kp + a.frame_off[fq] : nullptr;
     const float2 *kpt = a.kp ? a.kp + a.frame_off[ft] : nullptr;
-    for (int i = threadIdx.x; i < m; i += FIN_THREADS) {
+    for (int i = threadIdx.x; i < m; i += FIN_T) {
         const uint32_t key = keys[i];
         const int q = (int)(key & kIdxMask);
         const uint2 b = merge_partials(part, a.splits, a.q_stride, q);
@@ -337,12 +340,16 @@ cudaError_t launch_match_finalize(const FinalizeArgs &a, int max_nq, int n_pairs
         if (e != cudaSuccess) return e;
         std::lock_guard<std::mutex> lock(mu);
         if (dev < 0 || dev >= 64 || !configured[dev]) {
-            e = cudaFuncSetAttribute(match_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            e = cudaFuncSetAttribute(match_finalize_kernel<FIN_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             if (e != cudaSuccess) return e;
             if (dev >= 0 && dev < 64) configured[dev] = true;
         }
     }
-    return launch_dep(match_finalize_kernel, dim3(n_pairs), dim3(FIN_THREADS), smem, s, a);
+    // measured on 1764-keypoint VO frames: 1024 pairs 0.042 -> 0.035 ms with 512-thread CTAs; ten pairs 13.7 -> 16.6 us (a lone CTA
+    // walks its queries in twice as many rounds), so the small CTA is for batches that fill the GPU more than once
+    if (max_nq <= 2048 && n_pairs >= 296)
+        return launch_dep(match_finalize_kernel<FIN_THREADS / 2>, dim3(n_pairs), dim3(FIN_THREADS / 2), smem, s, a);
+    return launch_dep(match_finalize_kernel<FIN_THREADS>, dim3(n_pairs), dim3(FIN_THREADS), smem, s, a);
 }
 
 void launch_normalize_points(const double *xy1, const double *xy2, int n, const NormArgs &a, double *pts, PairState *st,
