@@ -191,16 +191,18 @@ __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; a
 #define PROBE_ADD(var)
 #endif
 
+template <bool TSPLIT>
 __device__ __forceinline__ bool load_item(const TcKnnArgs &a, int item, ItemInfo &it, int n_items)
 {
     if (item >= n_items) return false;
-    // item = (pair, query tile, train split): launches with fewer items than SMs cut the train dimension as well (a.t_splits,
+    const int t_splits = TSPLIT ? a.t_splits : 1;       // compile-time 1 for the large batches: no division beyond item / q_tiles
+    // item = (pair, query tile, train split): launches with fewer items than SMs cut the train dimension as well (t_splits,
     // chosen by the launcher), so that one VO pair or one large pair of descriptor sets still spreads over the chip
-    const int per_pair = a.q_tiles * a.t_splits;
+    const int per_pair = a.q_tiles * t_splits;
     it.pair = item / per_pair;
     const int rem = item - it.pair * per_pair;
-    const int qt = rem / a.t_splits;
-    it.ts = rem - qt * a.t_splits;
+    const int qt = rem / t_splits;
+    it.ts = rem - qt * t_splits;
     it.q0 = qt * (RB * BM);
     int fq, ft;
     if (a.pairs) {  // query = pair frame (second), train = base frame (first): visual-feature.cpp:59-60
@@ -210,7 +212,7 @@ __device__ __forceinline__ bool load_item(const TcKnnArgs &a, int item, ItemInfo
     } else { fq = a.reverse ? 0 : 1; ft = a.reverse ? 1 : 0; }
     it.nq = a.frame_cnt[fq]; it.nt = a.frame_cnt[ft];
     it.row_q = a.frame_off[fq] + it.q0; it.row_t = a.frame_off[ft];
-    const int tiles_total = (it.nt + BN - 1) / BN, tiles_per = (tiles_total + a.t_splits - 1) / a.t_splits;
+    const int tiles_total = (it.nt + BN - 1) / BN, tiles_per = (tiles_total + t_splits - 1) / t_splits;
     it.tile0 = it.ts * tiles_per;                           // a trailing split of a short frame may own no tile: it exports "none"
     it.n_tiles = max(0, min(tiles_per, tiles_total - it.tile0));
     it.n_rb = (it.q0 + BM < it.nq) ? 2 : 1;                 // the second row block may be empty (every role skips it)
@@ -233,7 +235,7 @@ __device__ __forceinline__ bool load_item(const TcKnnArgs &a, int item, ItemInfo
 // blocks go through their own 3-slot ring (warp A_WARP), so the next item's first row block is resident before the current
 // item ends and the second follows while the first is being multiplied; each row block has its own issuing warp; item
 // metadata is fetched one item ahead; the epilogue keeps stream maxima only (see the file header).
-template <int STAGES, int A_SLOTS>
+template <int STAGES, int A_SLOTS, bool TSPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
 {
@@ -246,7 +248,7 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
              *tempty = tfull + NACC;
     uint32_t *tmem_slot = (uint32_t *)(tempty + NACC);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_items = a.q_tiles * a.t_splits * a.n_pairs;
+    const int n_items = a.q_tiles * (TSPLIT ? a.t_splits : 1) * a.n_pairs;
     pdl_launch_dependents();   // K2's blocks may take the SMs this grid leaves free (small batches); they wait for this grid's end
 #ifdef MVS_TC_PROBE
     long long w_a = 0, w_full = 0, w_acc = 0;
@@ -275,7 +277,7 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
     // Query row blocks are numbered per CTA in the order (item, row block); number u lives in slot u % A_SLOTS.
     // Every role walks the same item sequence and fetches the NEXT item's metadata while it works on the current one.
     ItemInfo it, nx;
-    bool have = load_item(a, blockIdx.x, nx, n_items);
+    bool have = load_item<TSPLIT>(a, blockIdx.x, nx, n_items);
     if (warp == 0) {
         // ===== train-tile producer: runs ahead across item boundaries, bounded only by its own ring =====
         if (lane == 0) {
@@ -283,7 +285,7 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 it = nx;
                 const bool valid = have;
-                have = load_item(a, item + (int)gridDim.x, nx, n_items);
+                have = load_item<TSPLIT>(a, item + (int)gridDim.x, nx, n_items);
                 if (!valid) continue;
                 for (int i = 0; i < it.n_tiles; ++i, ++tile_no) {
                     const uint32_t s = tile_no % STAGES;
@@ -301,7 +303,7 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 it = nx;
                 const bool valid = have;
-                have = load_item(a, item + (int)gridDim.x, nx, n_items);
+                have = load_item<TSPLIT>(a, item + (int)gridDim.x, nx, n_items);
                 if (!valid) continue;
                 for (int rb = 0; rb < it.n_rb; ++rb, ++u) {
                     const uint32_t sl = u % A_SLOTS;
@@ -321,7 +323,7 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             it = nx;
             const bool valid = have;
-            have = load_item(a, item + (int)gridDim.x, nx, n_items);
+            have = load_item<TSPLIT>(a, item + (int)gridDim.x, nx, n_items);
             if (!valid) continue;
             const bool active = rb < it.n_rb;             // an item may have one row block only: stay in step with the train ring
             const uint32_t sl = (u + rb) % A_SLOTS;
@@ -360,7 +362,7 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             it = nx;
             const bool valid = have;
-            have = load_item(a, item + (int)gridDim.x, nx, n_items);
+            have = load_item<TSPLIT>(a, item + (int)gridDim.x, nx, n_items);
             if (!valid) continue;
             if (rb >= it.n_rb) continue;
             const int q = it.q0 + rb * BM + quarter * 32 + lane;   // row within the block == TMEM lane
@@ -413,7 +415,7 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap map, TcKnnArgs a)
             if (q < it.nq) {
                 const uint32_t x1 = (g1 >> kIdxBits) > 256u ? kKeyNone : g1;
                 const uint32_t x2 = (g2 >> kIdxBits) > 256u ? kKeyNone : g2;
-                a.partial[((size_t)it.pair * (TC_SPLITS * a.t_splits) + it.ts * TC_SPLITS + half) * a.q_stride + q] = make_uint2(x1, x2);
+                a.partial[((size_t)it.pair * (TC_SPLITS * (TSPLIT ? a.t_splits : 1)) + it.ts * TC_SPLITS + half) * a.q_stride + q] = make_uint2(x1, x2);
             }
         }
     }
@@ -466,13 +468,15 @@ cudaError_t launch_tc(const CUtensorMap &map, TcKnnArgs a, int max_nq, int n_pai
     constexpr int STAGES = 4, A_SLOTS = 3;
     const size_t smem = (size_t)A_SLOTS * KSLABS * BM * SLAB + (size_t)STAGES * KSLABS * BN * SLAB +
                         (2 * A_SLOTS + 2 * STAGES + 2 * NACC) * sizeof(uint64_t) + 16;
-    auto kern = knn2_hamming_tc_kernel<STAGES, A_SLOTS>;
+    auto kern = knn2_hamming_tc_kernel<STAGES, A_SLOTS, false>;      // large batches: the item decode has one division
+    auto kern_split = knn2_hamming_tc_kernel<STAGES, A_SLOTS, true>; // small launches cut the train dimension too
     static int sm_count[64] = {0};          // per device: the shared-memory opt-in is a per-device function attribute
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess || dev < 0 || dev >= 64) return e != cudaSuccess ? e : cudaErrorInvalidDevice;
     if (!sm_count[dev]) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kern_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int n = 0;
         e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
@@ -485,7 +489,8 @@ cudaError_t launch_tc(const CUtensorMap &map, TcKnnArgs a, int max_nq, int n_pai
     a.one = 1;
     if (a.t_splits < 1) a.t_splits = 1;
     const long items = (long)a.q_tiles * a.t_splits * n_pairs;
-    kern<<<(unsigned)std::min<long>(items, n_sm), TC_THREADS, smem, s>>>(map, a);
+    if (a.t_splits > 1) kern_split<<<(unsigned)std::min<long>(items, n_sm), TC_THREADS, smem, s>>>(map, a);
+    else kern<<<(unsigned)std::min<long>(items, n_sm), TC_THREADS, smem, s>>>(map, a);
     return cudaGetLastError();
 }
 
