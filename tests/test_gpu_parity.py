@@ -928,3 +928,22 @@ def test_frames_append_equals_bulk_upload(ctx, solver, tsukuba):
     got, dgot = ctx.pair_batch(pairs, tsukuba["K"], max_dist=30.0, H=16, seed=4)
     assert got.tobytes() == ref.tobytes()
     assert all(np.array_equal(dgot["matches"][i][:m], dref["matches"][i][:m]) for i, m in enumerate(ref["n_matches"]))
+
+
+def test_python_mirror_of_the_reference_entry_points(ctx, tsukuba):
+    """mvslam_b200/vision.py carries the reference's names (VisualFeature.match_visual_features, sfm_solve, sfm_triangulate,
+    image_pairs) over the same C ABI: each returns what the Context method it forwards to returns."""
+    vf1 = mvs.VisualFeature(tsukuba["kp1"], tsukuba["desc1"], 384, 288); vf2 = mvs.VisualFeature(tsukuba["kp2"], tsukuba["desc2"], 384, 288)
+    K = tsukuba["K"]
+    m = mvs.VisualFeature.match_visual_features(vf1, vf2, 30.0, ctx=ctx)
+    assert np.array_equal(m, ctx.match_hamming(tsukuba["desc2"], tsukuba["desc1"], 0.7, 30.0, False)) and len(m) > 100
+    assert np.array_equal(m, as_mvs(orc.match_hamming(tsukuba["desc2"], tsukuba["desc1"], max_dist=30.0)))
+    p1 = vf1.get_image_points()[m["train"]]; p2 = vf2.get_image_points()[m["query"]]
+    ok, (R, t), pts, idx = mvs.sfm_solve(p1, p2, K, ctx=ctx)
+    r = ctx.sfm_solve(p1, p2, K)
+    assert ok and np.array_equal(R, r["R2in1"]) and np.array_equal(t, r["t2in1"]) and np.array_equal(pts, r["points"])
+    assert np.allclose(t / np.linalg.norm(t), [1, 0, 0], atol=5e-2)          # test-image-pair.cpp:42-44: pure x translation
+    tri_pts, tri_idx = mvs.sfm_triangulate(p1, p2, K, (np.eye(3), np.zeros(3)), (R, t), ctx=ctx)
+    assert tri_pts.shape[0] == tri_idx.shape[0] >= 0.8 * len(pts)
+    res, det = mvs.image_pairs([vf1, vf2], [(0, 1)], K, max_match_inlier_distance=30.0, ctx=ctx)
+    assert res[0]["status"] == mvs.OK and res[0]["n_matches"] == len(m) and np.array_equal(det["matches"][0][:len(m)], m)
