@@ -61,6 +61,26 @@ def test_status_strings():
     assert b"CUDA" in L.mvs_status_string(mvs.E_CUDA)
 
 
+def test_host_alloc_needs_a_device_and_never_aborts():
+    """mvs_host_alloc hands out page-locked memory through the CUDA runtime: NULL (not a crash) without a device,
+    a usable buffer with one; mvs_host_free(NULL) is a no-op."""
+    import torch
+    L = mvs.load_library()
+    L.mvs_host_alloc.restype = ctypes.c_void_p
+    L.mvs_host_alloc.argtypes = [ctypes.c_size_t]
+    L.mvs_host_free.restype = None
+    L.mvs_host_free.argtypes = [ctypes.c_void_p]
+    L.mvs_host_free(None)
+    p = L.mvs_host_alloc(4096)
+    if torch.cuda.is_available():
+        assert p
+        ctypes.memset(p, 0x5A, 4096)
+        assert ctypes.string_at(p, 4) == b"ZZZZ"
+        L.mvs_host_free(p)
+    else:
+        assert not p
+
+
 def test_no_cpu_fallback_without_device():
     import torch
     if torch.cuda.is_available():
