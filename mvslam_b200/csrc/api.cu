@@ -114,6 +114,14 @@ struct mvs_ctx {
     bool allow_stage = false;   // set by the synchronous entry points only: _enqueue callers may synchronise the stream themselves
     struct StagedCopy { void *dst; size_t dpitch; size_t src_off; size_t width; size_t rows; };
     std::vector<StagedCopy> staged;
+    // details of a small synchronous batch exported by the device into the staging area (export_details_kernel): scattered to
+    // the caller's pageable buffers -- only the entries each pair owns -- by flush_staged()
+    struct StagedExport {
+        mvs_pair_result *results; mvs_match *matches; uint8_t *mask; double *points; uint64_t *indexes;
+        int n_pairs, w, capacity;
+        size_t off_res, off_m, off_k, off_p, off_i;
+    };
+    std::vector<StagedExport> staged_exports;
     // profiling
     bool prof = false;
     std::vector<cudaEvent_t> ev_pool;
@@ -459,6 +467,19 @@ void flush_staged(mvs_ctx *ctx)     // call only after the stream has been synch
         for (size_t r = 0; r < c.rows; ++r)
             std::memcpy(static_cast<uint8_t *>(c.dst) + r * c.dpitch, ctx->h_stage + c.src_off + r * c.width, c.width);
     ctx->staged.clear();
+    for (const auto &e : ctx->staged_exports) {
+        const mvs_pair_result *res = reinterpret_cast<const mvs_pair_result *>(ctx->h_stage + e.off_res);
+        std::memcpy(e.results, res, (size_t)e.n_pairs * sizeof(mvs_pair_result));
+        for (int i = 0; i < e.n_pairs; ++i) {
+            const size_t nm = (size_t)std::max(0, std::min(res[i].n_matches, e.w)), np = (size_t)std::max(0, std::min(res[i].n_points, e.w));
+            const size_t row = (size_t)i * e.w, urow = (size_t)i * e.capacity;
+            if (e.matches && nm) std::memcpy(e.matches + urow, ctx->h_stage + e.off_m + row * sizeof(mvs_match), nm * sizeof(mvs_match));
+            if (e.mask && nm) std::memcpy(e.mask + urow, ctx->h_stage + e.off_k + row, nm);
+            if (e.points && np) std::memcpy(e.points + urow * 3, ctx->h_stage + e.off_p + row * 24, np * 24);
+            if (e.indexes && np) std::memcpy(e.indexes + urow, ctx->h_stage + e.off_i + row * 8, np * 8);
+        }
+    }
+    ctx->staged_exports.clear();
     ctx->h_stage_used = 0;
 }
 
@@ -1218,6 +1239,34 @@ static int pair_batch_chunk(mvs_ctx *ctx, const int32_t *pairs, int n_pairs, con
     if (stage && !ctx->h_stage) {
         if (cudaMallocHost((void **)&ctx->h_stage, (size_t)8 << 20) == cudaSuccess) ctx->h_stage_cap = (size_t)8 << 20;
         else { (void)cudaGetLastError(); stage = false; }
+    }
+    if (stage && details) {
+        // the device writes the used entries of every pair into the staging area (one kernel, no count round trip, no strided
+        // copies); flush_staged() hands exactly those entries to the caller's buffers after the one synchronisation
+        auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
+        mvs_ctx::StagedExport e{results, matches, inlier_mask, points, indexes, n_pairs, (int)w, capacity, 0, 0, 0, 0, 0};
+        size_t off = al(ctx->h_stage_used);
+        e.off_res = off; off = al(off + (size_t)n_pairs * sizeof(mvs_pair_result));
+        e.off_m = off; if (matches) off = al(off + (size_t)n_pairs * w * sizeof(mvs_match));
+        e.off_k = off; if (inlier_mask) off = al(off + (size_t)n_pairs * w);
+        e.off_p = off; if (points) off = al(off + (size_t)n_pairs * w * 24);
+        e.off_i = off; if (indexes) off = al(off + (size_t)n_pairs * w * 8);
+        void *stage_dev = pinned_device_ptr(ctx->h_stage);
+        if (off <= ctx->h_stage_cap && stage_dev) {
+            uint8_t *sd = static_cast<uint8_t *>(stage_dev);
+            ExportArgs ea{};
+            ea.res = ctx->d_results.as<mvs_pair_result>(); ea.stride = qs; ea.capacity = (int)w;
+            ea.m = ctx->d_matches.as<mvs_match>(); ea.k = ctx->d_mask.as<uint8_t>();
+            ea.p = ctx->d_opts.as<double>(); ea.i = ctx->d_oidx.as<uint64_t>();
+            ea.mo = matches ? reinterpret_cast<mvs_match *>(sd + e.off_m) : nullptr; ea.ko = inlier_mask ? sd + e.off_k : nullptr;
+            ea.po = points ? reinterpret_cast<double *>(sd + e.off_p) : nullptr; ea.io = indexes ? reinterpret_cast<uint64_t *>(sd + e.off_i) : nullptr;
+            CK(mvs::launch_dep(export_details_kernel, dim3((unsigned)n_pairs), dim3(128), 0, ctx->stream, ea));
+            ctx->launches += 1;
+            CK(cudaMemcpyAsync(ctx->h_stage + e.off_res, ctx->d_results.p, (size_t)n_pairs * sizeof(mvs_pair_result), cudaMemcpyDeviceToHost, ctx->stream));
+            ctx->staged_exports.push_back(e);
+            ctx->h_stage_used = off;
+            return MVS_OK;
+        }
     }
     CK(d2h_rows(ctx, stage, results, sizeof(mvs_pair_result), ctx->d_results.p, sizeof(mvs_pair_result), sizeof(mvs_pair_result), (size_t)n_pairs));
     // details: the first min(capacity, stride) entries of every pair (a pair with n_matches > capacity is truncated).
