@@ -23,6 +23,6 @@ ls -la gpurun_out | tail -20
 python tools/l2_bench.py 32768 4 > gpurun_out/l2_bench_$R.json 2>/dev/null && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/l2_launches_$R.csv python tools/l2_bench.py 32768 2 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:l2_gemm -s 2 -c 1 -o gpurun_out/prof_l2_$R python tools/l2_bench.py 32768 4 > gpurun_out/ncu_l2_$R.log 2>&1
-# matcher clock / wait counters (needs tmp_ab/libprobe.so: match_hamming_tc.cu built with -DMVS_TC_PROBE)
+# matcher clock / wait counters (needs tmp_ab/libprobe.so from tools/build_tc_probe.sh: match_hamming_tc.cu with -DMVS_TC_PROBE)
 if [ -f tmp_ab/libprobe.so ]; then MVS_LIB_OVERRIDE=tmp_ab/libprobe.so TAG=probe H=1 SOLVER=reference REPS=10 python tools/knn_probe.py > gpurun_out/tc_probe_$R.json 2>/dev/null; fi
 ls -la gpurun_out | tail -8
